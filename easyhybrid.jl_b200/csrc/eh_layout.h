@@ -1,0 +1,78 @@
+// eh_layout.h -- compile-time shape math shared by the fused step kernel (device)
+// and the host planner (eh_plan.cpp).  No includes, NVRTC-clean.
+//
+// A "shape" is one Dense chain  P -> H -> ... -> H -> NOUT  with NH hidden
+// layers, every hidden width padded up to H (multiple of 4) with zero weights.
+// Reference: prepare_hidden_chain, src/models/NNModels.jl:220-231.
+#pragma once
+
+#ifndef EH_HD
+#ifdef __CUDACC__
+#define EH_HD __host__ __device__
+#else
+#define EH_HD
+#endif
+#endif
+
+namespace eh {
+
+enum : int { ACT_IDENTITY = 0, ACT_TANH = 1, ACT_SIGMOID = 2, ACT_RELU = 3, ACT_SWISH = 4 };
+enum : int { ROLE_NEURAL = 0, ROLE_GLOBAL = 1, ROLE_FIXED = 2 };
+enum : int { LOSS_MSE = 0, LOSS_RMSE = 1, LOSS_MAE = 2, LOSS_NSELOSS = 3 };
+enum : int { PM_RBQ10 = 0, PM_EXPO = 1, PM_LINEAR = 2, PM_LINEAR2 = 3, PM_PROGRAM = 100 };
+
+constexpr int MAXPS = 8;   // process-parameter slots
+constexpr int MAXT = 4;    // targets
+constexpr int MAXF = 8;    // forcings
+constexpr int CHUNK = 64;  // samples per warp pass (2 per lane)
+constexpr int ROWSTRIDE = CHUNK + 4;  // floats per staging row (bank skew)
+
+EH_HD constexpr int rup4(int x) { return (x + 3) & ~3; }
+
+// runtime/compile-time description of one chain shape
+struct ShapeDims {
+    int P, NH, H, NOUT;
+    EH_HD constexpr int nlayers() const { return NH + 1; }
+    // fan-in / padded fan-out of dense layer l (1-based)
+    EH_HD constexpr int din(int l) const { return l == 1 ? P : H; }
+    EH_HD constexpr int dout4(int l) const { return l == NH + 1 ? rup4(NOUT) : H; }
+    // rows of the augmented input [a; 1; 0..] of layer l, padded to 4
+    EH_HD constexpr int ka(int l) const { return rup4(din(l) + 1); }
+    EH_HD constexpr int nj(int l) const { return dout4(l) / 4; }
+    EH_HD constexpr int nk(int l) const { return ka(l) / 4; }
+    // staging groups (4 rows each; group g starts at row 5g): for l = 1..L: A_{l-1} then D_l
+    EH_HD constexpr int gA(int l) const
+    {
+        int g = 0;
+        for (int i = 1; i < l; i++) g += nk(i) + nj(i);
+        return g;
+    }
+    EH_HD constexpr int gD(int l) const { return gA(l) + nk(l); }
+    EH_HD constexpr int ngroups() const { return gA(NH + 2); }
+    EH_HD constexpr int nrows() const { return 5 * ngroups(); }
+    // dW blocks (4x4): layer-major, then j-block, then k-block
+    EH_HD constexpr int blk0(int l) const
+    {
+        int b = 0;
+        for (int i = 1; i < l; i++) b += nj(i) * nk(i);
+        return b;
+    }
+    EH_HD constexpr int nblocks() const { return blk0(NH + 2); }
+    // shared-memory weight image (floats)
+    EH_HD constexpr int off_w1f() const { return 0; }                     // [P][H]
+    EH_HD constexpr int off_b1() const { return P * H; }                  // [H]
+    EH_HD constexpr int off_wf(int l) const { return P * H + H + (l - 2) * (2 * H * H + H); }  // l = 2..NH, [H][H] k-major
+    EH_HD constexpr int off_b(int l) const { return off_wf(l) + H * H; }  // [H]
+    EH_HD constexpr int off_wb(int l) const { return off_b(l) + H; }      // [H][H] j-major
+    EH_HD constexpr int off_wo() const { return P * H + H + (NH - 1) * (2 * H * H + H); }  // [NOUT][H]
+    EH_HD constexpr int off_bo() const { return off_wo() + NOUT * H; }    // [4]
+    EH_HD constexpr int nweights() const { return off_bo() + 4; }
+    // per-CTA partial vector: nblocks*16 dW entries, then statistics
+    EH_HD constexpr int npart_dw() const { return nblocks() * 16; }
+};
+
+// statistics appended after the dW blocks in a partial vector:
+//   [T] sum of r^2 (or |r| for mae targets), [MAXPS] sum of g*dy/dslot for GLOBAL slots
+constexpr int NSTAT = MAXT + MAXPS;
+
+}  // namespace eh

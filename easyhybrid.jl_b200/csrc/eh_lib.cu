@@ -1,0 +1,1134 @@
+// eh_lib.cu -- C ABI of libeasyhybrid_cuda.so (see include/easyhybrid_cuda.h).
+//
+// Host-side runtime of the fused training path: descriptor -> kernel variant +
+// layout tables, device-resident datasets (packed once), per-epoch index stream,
+// step launch sequence (K1 fused step, K2 reduce+update, chained with programmatic
+// dependent launch), evaluation, timing hooks.  No PyTorch, no CPU fallback.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/easyhybrid_cuda.h"
+#include "eh_variants.h"
+#include "eh_update_kernel.cuh"
+#include "eh_eval_kernel.cuh"
+
+using namespace eh;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Split {
+    float* rec = nullptr;
+    int64_t N = 0;
+    float shift_y[MAXT] = {0, 0, 0, 0};
+    float shift_x[MAXP] = {0};
+    bool has_nan = false;
+};
+
+struct HostStage {  // device staging for eh_step_host*: raw arrays + packed records
+    float* d_X = nullptr;
+    float* d_planes = nullptr;
+    float* d_rec = nullptr;
+    int* d_cnt = nullptr;  // [MAXT] valid-target counts written by the packer
+    float* d_bscal = nullptr;
+    float* d_loss = nullptr;
+    cudaEvent_t done = nullptr;
+    int64_t cap = 0;
+};
+
+}  // namespace
+
+struct eh_ctx {
+    std::string err;
+    int device = 0;
+    int nsm = 0;
+    size_t smem_optin = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    const Variant* var = nullptr;
+    // model
+    int n_pred_raw = 0, n_forc_raw = 0, n_targ = 0;
+    int nflat = 0, ntheta = 0, nglob = 0;
+    int real_in = 0;
+    std::vector<int> h_wsrc, h_pmap;
+    std::vector<float> h_pspan;
+    PSlot slots[MAXPS];
+    float pmc[4] = {0, 0, 0, 0};
+    int loss_kind[MAXT] = {0, 0, 0, 0};
+    int agg_mean = 0;
+    int opt_kind = 0, adamw_coupled = 1;
+    float eta = 0.01f, beta1 = 0.9f, beta2 = 0.999f, eps = 1e-8f, lambda = 0.f;
+    int use_bn = 0;
+    unsigned flags = 0;
+    int src_kind[24], src_idx[24], ncols = 0;
+    int nparam_desc = 0;
+    std::vector<int> slot_of_param;  // desc parameter index -> canonical slot or -1
+    // device state
+    int *d_wsrc = nullptr, *d_pmap = nullptr;
+    float* d_pspan = nullptr;
+    float *d_theta = nullptr, *d_m = nullptr, *d_v = nullptr, *d_grad = nullptr;
+    OptState* d_ost = nullptr;
+    float *d_partial = nullptr, *d_gvec = nullptr;
+    float* d_bscal = nullptr;
+    size_t bscal_cap = 0;
+    float* d_bn_batch = nullptr;
+    size_t bn_batch_cap = 0;
+    int* d_idx = nullptr;
+    long long* d_idx64 = nullptr;
+    size_t idx_cap = 0;
+    int* d_err = nullptr;
+    float* d_loss = nullptr;
+    float* h_loss = nullptr;  // pinned
+    size_t loss_cap = 0;
+    double* d_evalpart = nullptr;
+    float* d_bn_test = nullptr;  // BS_STRIDE row with running stats for test mode
+    Split split[2];
+    int64_t perm_n = 0;
+    int64_t perm_B = 0;  // batch size the bscal rows were prepared for (0 = none)
+    std::vector<float> bn_mean, bn_var;
+    // host-step pipeline
+    HostStage hs[2];
+    int hs_next = 0;
+    std::vector<std::pair<float*, float*>> pending_loss;  // (pinned src, user dst)
+    float* h_async_loss = nullptr;                          // pinned ring
+    size_t async_cap = 0, async_used = 0;
+    // timing
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_ms = 0.f, last_step_ms = 0.f;
+    int64_t last_launches = 0;
+    int profiling = 0;
+    std::vector<cudaEvent_t> prof_ev;
+    // dp
+    int rank = 0, world = 1;
+    void* nccl_lib = nullptr;
+    void* nccl_comm = nullptr;
+};
+
+namespace {
+
+eh_status fail(eh_ctx* c, eh_status s, const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    else g_create_error = buf;
+    return s;
+}
+
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e__ = (call);                                                                     \
+        if (e__ != cudaSuccess)                                                                       \
+            return fail(c, EH_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+template <class T>
+cudaError_t dalloc(T** p, size_t n)
+{
+    return cudaMalloc((void**)p, std::max<size_t>(n, 1) * sizeof(T));
+}
+
+// n_valid-independent per-batch rows when no data statistics are needed:
+// c_t = agg_w / B_k, n_t = B_k (no NaN targets anywhere in the split)
+__global__ void k_fill_bscal(float* bscal, int nb, long long n, int Bfull, int T, int agg_mean)
+{
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    long long rem = n - (long long)b * Bfull;
+    float bk = (float)(rem < Bfull ? rem : Bfull);
+    float* o = bscal + (size_t)b * BS_STRIDE;
+    float aggw = agg_mean ? 1.f / (float)T : 1.f;
+    for (int t = 0; t < MAXT; t++) {
+        o[BS_C + t] = t < T ? aggw / bk : 0.f;
+        o[BS_N + t] = t < T ? bk : 0.f;
+        o[BS_SS + t] = 0.f;
+    }
+    for (int k = 0; k < MAXP; k++) { o[BS_BN + 2 * k] = 0.f; o[BS_BN + 2 * k + 1] = 1.f; }
+}
+
+// host-step path: c_t from the valid-target counts produced by the packer
+__global__ void k_bscal_from_counts(float* bscal, const int* cnt, int T, int agg_mean)
+{
+    int t = threadIdx.x;
+    if (t >= MAXT) return;
+    float aggw = agg_mean ? 1.f / (float)T : 1.f;
+    float n = t < T ? (float)cnt[t] : 0.f;
+    bscal[BS_C + t] = t < T ? aggw / n : 0.f;
+    bscal[BS_N + t] = n;
+    bscal[BS_SS + t] = 0.f;
+    if (t == 0)
+        for (int k = 0; k < MAXP; k++) { bscal[BS_BN + 2 * k] = 0.f; bscal[BS_BN + 2 * k + 1] = 1.f; }
+}
+
+// packer variant that also counts valid targets (integer atomics: deterministic)
+__global__ void __launch_bounds__(256) k_pack_count(const PackArgs a, int T, int ycol0, int* cnt)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int valid[MAXT] = {0, 0, 0, 0};
+    if (i < a.N) {
+        float* r = a.rec + (a.rec_base + i) * a.R4;
+        for (int c = 0; c < a.R4; c++) {
+            float v = 0.f;
+            if (c < a.ncols)
+                v = a.src_kind[c] == 0 ? a.X[i * a.P_raw + a.src_idx[c]] : a.planes[(long long)a.src_idx[c] * a.N + i];
+            r[c] = v;
+            int t = c - ycol0;
+            if (t >= 0 && t < T && v == v) valid[t] = 1;
+        }
+    }
+    for (int t = 0; t < T; t++) {
+        unsigned m = __ballot_sync(0xffffffffu, valid[t]);
+        if ((threadIdx.x & 31) == 0 && m) atomicAdd(&cnt[t], __popc(m));
+    }
+}
+
+struct Geom {
+    int grid, nwarps;
+    size_t smem;
+};
+
+Geom step_geometry(const eh_ctx* c, int64_t B)
+{
+    const Variant* v = c->var;
+    size_t fixed = (size_t)(rup4(v->NW) + 64) * 4;
+    size_t stage = (size_t)v->stage_floats * 4;
+    int wmax = (int)std::min<size_t>(8, (c->smem_optin - fixed) / stage);
+    if (wmax < 1) wmax = 1;
+    int64_t nchunks = (B + CHUNK - 1) / CHUNK;
+    Geom g;
+    if (nchunks <= (int64_t)c->nsm * wmax) {
+        int w = (int)((nchunks + c->nsm - 1) / c->nsm);
+        w = std::max(1, std::min(w, wmax));
+        g.nwarps = w;
+        g.grid = (int)((nchunks + w - 1) / w);
+    } else {
+        g.nwarps = wmax;
+        g.grid = c->nsm;
+    }
+    if (g.grid < 1) g.grid = 1;
+    g.smem = fixed + (size_t)g.nwarps * stage;
+    return g;
+}
+
+void fill_step_args(const eh_ctx* c, StepArgs& a)
+{
+    memset(&a, 0, sizeof a);
+    a.theta = c->d_theta;
+    a.wsrc = c->d_wsrc;
+    a.partial = c->d_partial;
+    a.npart = c->var->NPART;
+    for (int t = 0; t < MAXT; t++) a.loss_kind[t] = c->loss_kind[t];
+    for (int s = 0; s < MAXPS; s++) a.slot[s] = c->slots[s];
+    for (int i = 0; i < 4; i++) a.pmc[i] = c->pmc[i];
+    a.use_bn = c->use_bn;
+}
+
+void fill_update_args(const eh_ctx* c, UpdateArgs& u)
+{
+    memset(&u, 0, sizeof u);
+    u.partial = c->d_partial;
+    u.npart = c->var->NPART;
+    u.npart_dw = c->var->dims.npart_dw();
+    u.gvec = c->d_gvec;
+    u.mode = UPD_FULL;
+    u.apply = 1;
+    u.nflat = c->nflat;
+    u.ntheta = c->ntheta;
+    u.pmap = c->d_pmap;
+    u.pspan = c->d_pspan;
+    u.theta = c->d_theta;
+    u.m = c->d_m;
+    u.v = c->d_v;
+    u.ost = c->d_ost;
+    u.T = c->n_targ;
+    u.agg_mean = c->agg_mean;
+    for (int t = 0; t < MAXT; t++) u.loss_kind[t] = c->loss_kind[t];
+    u.opt_kind = c->opt_kind;
+    u.adamw_coupled = c->adamw_coupled;
+    u.eta = c->eta; u.beta1 = c->beta1; u.beta2 = c->beta2; u.eps = c->eps; u.lambda = c->lambda;
+}
+
+cudaError_t launch_update(const UpdateArgs& u, cudaStream_t st, bool pdl)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(1);
+    cfg.blockDim = dim3(512);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, k_update, u);
+}
+
+eh_status ensure_loss_cap(eh_ctx* c, size_t n)
+{
+    if (n <= c->loss_cap) return EH_OK;
+    if (c->d_loss) cudaFree(c->d_loss);
+    if (c->h_loss) cudaFreeHost(c->h_loss);
+    c->d_loss = nullptr; c->h_loss = nullptr; c->loss_cap = 0;
+    size_t cap = std::max<size_t>(n, 1024);
+    CK(dalloc(&c->d_loss, cap));
+    CK(cudaMallocHost((void**)&c->h_loss, cap * sizeof(float)));
+    c->loss_cap = cap;
+    return EH_OK;
+}
+
+eh_status ensure_idx_cap(eh_ctx* c, size_t n)
+{
+    if (n <= c->idx_cap) return EH_OK;
+    if (c->d_idx) cudaFree(c->d_idx);
+    if (c->d_idx64) cudaFree(c->d_idx64);
+    c->d_idx = nullptr; c->d_idx64 = nullptr; c->idx_cap = 0;
+    CK(dalloc(&c->d_idx, n));
+    CK(dalloc(&c->d_idx64, n));
+    c->idx_cap = n;
+    return EH_OK;
+}
+
+eh_status ensure_bscal_cap(eh_ctx* c, size_t nb)
+{
+    if (nb > c->bscal_cap) {
+        if (c->d_bscal) cudaFree(c->d_bscal);
+        c->d_bscal = nullptr; c->bscal_cap = 0;
+        CK(dalloc(&c->d_bscal, nb * BS_STRIDE));
+        c->bscal_cap = nb;
+    }
+    if (c->use_bn && nb > c->bn_batch_cap) {
+        if (c->d_bn_batch) cudaFree(c->d_bn_batch);
+        c->d_bn_batch = nullptr; c->bn_batch_cap = 0;
+        CK(dalloc(&c->d_bn_batch, nb * 2 * MAXP));
+        c->bn_batch_cap = nb;
+    }
+    return EH_OK;
+}
+
+// upload a 1-based int64 index stream and convert to 0-based int32 on the device
+eh_status upload_indices(eh_ctx* c, const int64_t* idx1, int64_t n, int64_t nmax)
+{
+    eh_status s = ensure_idx_cap(c, (size_t)n);
+    if (s != EH_OK) return s;
+    CK(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream));
+    CK(cudaMemcpyAsync(c->d_idx64, idx1, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    k_idx_convert<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_idx64, c->d_idx, n, nmax, c->d_err);
+    CK(cudaGetLastError());
+    int herr = 0;
+    CK(cudaMemcpyAsync(&herr, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (herr) return fail(c, EH_EINVAL, "index out of range 1..%lld in batch / permutation", (long long)nmax);
+    return EH_OK;
+}
+
+bool needs_data_stats(const eh_ctx* c)
+{
+    if (c->use_bn || c->split[EH_SPLIT_TRAIN].has_nan) return true;
+    for (int t = 0; t < c->n_targ; t++)
+        if (c->loss_kind[t] == LOSS_NSELOSS) return true;
+    return false;
+}
+
+// per-batch scalar rows for batches of size B over the index stream d_idx[0..n)
+eh_status prepare_batch_rows(eh_ctx* c, int64_t n, int64_t B)
+{
+    int64_t nb = (n + B - 1) / B;
+    eh_status s = ensure_bscal_cap(c, (size_t)nb);
+    if (s != EH_OK) return s;
+    const Split& sp = c->split[EH_SPLIT_TRAIN];
+    if (needs_data_stats(c)) {
+        StatArgs a;
+        memset(&a, 0, sizeof a);
+        a.rec = sp.rec;
+        a.R4 = c->var->R4;
+        a.idx = c->d_idx;
+        a.n = n;
+        a.Bfull = (int)B;
+        a.P = c->var->P; a.F = c->var->F; a.T = c->var->T;
+        for (int t = 0; t < MAXT; t++) { a.shift_y[t] = sp.shift_y[t]; a.loss_kind[t] = c->loss_kind[t]; }
+        for (int k = 0; k < MAXP; k++) a.shift_x[k] = sp.shift_x[k];
+        a.agg_mean = c->agg_mean;
+        a.use_bn = c->use_bn;
+        a.bscal = c->d_bscal;
+        a.bn_batch = c->use_bn ? c->d_bn_batch : nullptr;
+        k_batch_stats<<<(unsigned)nb, 256, 0, c->stream>>>(a);
+    } else {
+        k_fill_bscal<<<(unsigned)((nb + 127) / 128), 128, 0, c->stream>>>(c->d_bscal, (int)nb, n, (int)B, c->n_targ,
+                                                                          c->agg_mean);
+    }
+    CK(cudaGetLastError());
+    return EH_OK;
+}
+
+// the step loop: batches [first, first+nsteps) of the resident index stream
+eh_status run_steps(eh_ctx* c, int64_t n, int64_t B, int64_t first, int64_t nsteps, float* losses, int apply,
+                    float* grad_out_host)
+{
+    const Split& sp = c->split[EH_SPLIT_TRAIN];
+    if (!sp.rec) return fail(c, EH_EINVAL, "train split not uploaded");
+    int64_t nb = (n + B - 1) / B;
+    if (first < 0 || nsteps < 0 || first + nsteps > nb) return fail(c, EH_EINVAL, "step range out of bounds");
+    eh_status s = ensure_loss_cap(c, (size_t)nsteps);
+    if (s != EH_OK) return s;
+    const bool pdl = !(c->flags & EH_FLAG_NO_PDL) && !c->profiling;
+    StepArgs a;
+    fill_step_args(c, a);
+    a.rec = reinterpret_cast<const float4*>(sp.rec);
+    UpdateArgs u;
+    fill_update_args(c, u);
+    u.apply = apply;
+    u.grad_out = grad_out_host ? c->d_grad : nullptr;
+    if (c->profiling) {
+        while ((int64_t)c->prof_ev.size() < 2 * nsteps) {
+            cudaEvent_t e;
+            CK(cudaEventCreate(&e));
+            c->prof_ev.push_back(e);
+        }
+    }
+    CK(cudaEventRecord(c->ev0, c->stream));
+    int64_t launches = 0;
+    for (int64_t k = 0; k < nsteps; k++) {
+        int64_t b = first + k;
+        int64_t Bk = std::min<int64_t>(B, n - b * B);
+        Geom g = step_geometry(c, Bk);
+        a.idx = c->d_idx + b * B;
+        a.B = (int)Bk;
+        a.bscal = c->d_bscal + (size_t)b * BS_STRIDE;
+        if (c->profiling) CK(cudaEventRecord(c->prof_ev[2 * k], c->stream));
+        CK(c->var->launch_step(a, g.grid, g.nwarps, g.smem, c->stream, pdl));
+        if (c->profiling) CK(cudaEventRecord(c->prof_ev[2 * k + 1], c->stream));
+        u.G = g.grid;
+        u.bscal = a.bscal;
+        u.loss_out = c->d_loss + k;
+        if (c->world > 1) return fail(c, EH_EUNSUPPORTED, "data-parallel step not wired in this build");
+        CK(launch_update(u, c->stream, pdl));
+        launches += 2;
+    }
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaMemcpyAsync(c->h_loss, c->d_loss, (size_t)nsteps * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (grad_out_host)
+        CK(cudaMemcpyAsync(grad_out_host, c->d_grad, (size_t)c->nflat * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+    c->last_launches = launches;
+    c->last_step_ms = 0.f;
+    if (c->profiling) {
+        float tot = 0.f;
+        for (int64_t k = 0; k < nsteps; k++) {
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, c->prof_ev[2 * k], c->prof_ev[2 * k + 1]));
+            tot += ms;
+        }
+        c->last_step_ms = tot;
+    }
+    if (losses) memcpy(losses, c->h_loss, (size_t)nsteps * sizeof(float));
+    // Lux BatchNorm running statistics (momentum 0.1, unbiased variance), skipped batches excluded
+    if (c->use_bn && apply) {
+        std::vector<float> bb((size_t)nsteps * 2 * c->var->P);
+        CK(cudaMemcpy(bb.data(), c->d_bn_batch + (size_t)first * 2 * c->var->P, bb.size() * sizeof(float),
+                      cudaMemcpyDeviceToHost));
+        for (int64_t k = 0; k < nsteps; k++) {
+            if (std::isnan(c->h_loss[k])) continue;
+            int64_t Bk = std::min<int64_t>(B, n - (first + k) * B);
+            for (int i = 0; i < c->var->P; i++) {
+                float mu = bb[(size_t)k * 2 * c->var->P + 2 * i], var = bb[(size_t)k * 2 * c->var->P + 2 * i + 1];
+                float unb = Bk > 1 ? var * (float)Bk / (float)(Bk - 1) : var;
+                c->bn_mean[i] = 0.9f * c->bn_mean[i] + 0.1f * mu;
+                c->bn_var[i] = 0.9f * c->bn_var[i] + 0.1f * unb;
+            }
+        }
+    }
+    return EH_OK;
+}
+
+eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
+{
+    if (d->abi_version != EH_ABI_VERSION) return fail(c, EH_EINVAL, "abi_version %d != %d", d->abi_version, EH_ABI_VERSION);
+    if (d->n_targ < 1 || d->n_targ > MAXT) return fail(c, EH_EUNSUPPORTED, "n_targ=%d not in 1..%d", d->n_targ, MAXT);
+    if (d->n_chains != 1)
+        return fail(c, EH_EUNSUPPORTED, "n_chains=%d: only single-chain models have a fused kernel in this build", d->n_chains);
+    if (d->process_model == EH_PM_PROGRAM)
+        return fail(c, EH_EUNSUPPORTED, "traced process-model programs are not compiled in this build");
+    const eh_chain_desc& ch = d->chains[0];
+    if (ch.n_in < 1 || ch.n_in > MAXP) return fail(c, EH_EUNSUPPORTED, "chain n_in=%d not in 1..%d", ch.n_in, MAXP);
+    if (ch.n_hidden < 1) return fail(c, EH_EINVAL, "chain needs at least one hidden layer");
+    int hmax = 0;
+    for (int l = 0; l < ch.n_hidden; l++) hmax = std::max(hmax, ch.hidden[l]);
+    if (d->n_pm_args != 3 || d->pm_args[0].kind != 0 || d->pm_args[1].kind != 0 || d->pm_args[2].kind != 1)
+        return fail(c, EH_EINVAL, "built-in process models take (param, param, forcing) arguments");
+    const Variant* v = find_variant(d->process_model, ch.n_in, ch.n_hidden, rup4(hmax), ch.n_out, ch.activation,
+                                    d->scale_nn_outputs ? 1 : 0);
+    if (!v)
+        return fail(c, EH_EUNSUPPORTED,
+                    "no fused kernel variant for process_model=%d n_in=%d hidden=%dx(<=%d) n_out=%d activation=%d scale_nn_outputs=%d",
+                    d->process_model, ch.n_in, ch.n_hidden, hmax, ch.n_out, ch.activation, d->scale_nn_outputs);
+    if (v->T != d->n_targ) return fail(c, EH_EINVAL, "process model yields %d targets, descriptor has %d", v->T, d->n_targ);
+    c->var = v;
+    c->n_pred_raw = d->n_pred; c->n_forc_raw = d->n_forc; c->n_targ = d->n_targ;
+    c->use_bn = ch.input_batchnorm ? 1 : 0;
+    c->real_in = ch.n_in;
+    c->flags = (unsigned)d->flags;
+
+    // flat layout (reference ComponentArray order): per layer W (out x in, column-major) then b; then phi
+    const ShapeDims& D = v->dims;
+    const int L = ch.n_hidden + 1;
+    std::vector<int> width(L + 1);
+    width[0] = ch.n_in;
+    for (int l = 0; l < ch.n_hidden; l++) width[l + 1] = ch.hidden[l];
+    width[L] = ch.n_out;
+    std::vector<int> w_off(L), b_off(L);
+    int off = 0;
+    for (int l = 0; l < L; l++) {
+        w_off[l] = off; off += width[l] * width[l + 1];
+        b_off[l] = off; off += width[l + 1];
+    }
+    c->ntheta = off;
+    int ng = 0;
+    for (int p = 0; p < d->n_params; p++)
+        if (d->role[p] == EH_ROLE_GLOBAL) ng = std::max(ng, d->role_index[p] + 1);
+    c->nglob = ng;
+    c->nflat = off + ng;
+    if (c->nflat > 2048 - NSTAT) return fail(c, EH_EUNSUPPORTED, "parameter vector too long for the single-CTA update");
+
+    // smem weight image gather table
+    const int H = D.H, P = D.P, NH = D.NH, NOUT = D.NOUT;
+    c->h_wsrc.assign((size_t)v->NW + ng, -1);
+    auto Wsrc = [&](int l /*1-based*/, int j, int k) -> int {
+        if (j >= width[l] || k >= width[l - 1]) return -1;
+        return w_off[l - 1] + j + k * width[l];
+    };
+    auto Bsrc = [&](int l, int j) -> int { return j < width[l] ? b_off[l - 1] + j : -1; };
+    for (int k = 0; k < P; k++)
+        for (int j = 0; j < H; j++) c->h_wsrc[D.off_w1f() + k * H + j] = Wsrc(1, j, k);
+    for (int j = 0; j < H; j++) c->h_wsrc[D.off_b1() + j] = Bsrc(1, j);
+    for (int l = 2; l <= NH; l++) {
+        for (int k = 0; k < H; k++)
+            for (int j = 0; j < H; j++) {
+                c->h_wsrc[D.off_wf(l) + k * H + j] = Wsrc(l, j, k);
+                c->h_wsrc[D.off_wb(l) + j * H + k] = Wsrc(l, j, k);
+            }
+        for (int j = 0; j < H; j++) c->h_wsrc[D.off_b(l) + j] = Bsrc(l, j);
+    }
+    for (int o = 0; o < NOUT; o++)
+        for (int k = 0; k < H; k++) c->h_wsrc[D.off_wo() + o * H + k] = Wsrc(L, o, k);
+    for (int o = 0; o < 4; o++) c->h_wsrc[D.off_bo() + o] = o < NOUT ? Bsrc(L, o) : -1;
+    for (int g = 0; g < ng; g++) c->h_wsrc[(size_t)v->NW + g] = off + g;
+
+    // canonical slots from the built-in form's (param, param, forcing) binding
+    c->nparam_desc = d->n_params;
+    c->slot_of_param.assign((size_t)d->n_params, -1);
+    memset(c->slots, 0, sizeof c->slots);
+    for (int s = 0; s < MAXPS; s++) c->slots[s].role = ROLE_FIXED;
+    for (int s = 0; s < v->NPS; s++) {
+        int pi = d->pm_args[s].index;
+        if (pi < 0 || pi >= d->n_params) return fail(c, EH_EINVAL, "pm_args[%d].index out of range", s);
+        PSlot& sl = c->slots[s];
+        sl.role = d->role[pi];
+        sl.lo = d->lower[pi];
+        sl.span = d->upper[pi] - d->lower[pi];
+        sl.fixedv = d->deflt[pi];
+        if (sl.role == EH_ROLE_NEURAL) {
+            if ((d->role_index[pi] >> 16) != 0) return fail(c, EH_EINVAL, "neural parameter refers to chain != 0");
+            sl.idx = d->role_index[pi] & 0xffff;
+            if (sl.idx >= NOUT) return fail(c, EH_EINVAL, "neural parameter row %d >= n_out %d", sl.idx, NOUT);
+        } else if (sl.role == EH_ROLE_GLOBAL) {
+            sl.idx = d->role_index[pi];
+        }
+        c->slot_of_param[pi] = s;
+    }
+    for (int i = 0; i < 4; i++) c->pmc[i] = d->pm_consts[i];
+
+    // flat entry -> position in the partial vector
+    c->h_pmap.assign((size_t)c->nflat, 0);
+    c->h_pspan.assign((size_t)c->nflat, 0.f);
+    for (int l = 1; l <= L; l++) {
+        const int nk = D.nk(l), b0 = D.blk0(l);
+        for (int j = 0; j < width[l]; j++) {
+            for (int k = 0; k < width[l - 1]; k++)
+                c->h_pmap[w_off[l - 1] + j + k * width[l]] = (b0 + (j / 4) * nk + (k / 4)) * 16 + (j % 4) * 4 + (k % 4);
+            int kb = D.din(l);  // the "ones" row of the augmented input
+            c->h_pmap[b_off[l - 1] + j] = (b0 + (j / 4) * nk + (kb / 4)) * 16 + (j % 4) * 4 + (kb % 4);
+        }
+    }
+    for (int g = 0; g < ng; g++) {
+        int slot = MAXPS - 1;  // a statistics cell that stays zero (phi not used by the process model)
+        float span = 0.f;
+        for (int s = 0; s < v->NPS; s++)
+            if (c->slots[s].role == ROLE_GLOBAL && c->slots[s].idx == g) { slot = s; span = c->slots[s].span; }
+        c->h_pmap[off + g] = D.npart_dw() + MAXT + slot;
+        c->h_pspan[off + g] = span;
+    }
+
+    // record columns: chain inputs, the form's forcing, targets
+    c->ncols = 0;
+    for (int k = 0; k < ch.n_in; k++) {
+        if (ch.in_cols[k] < 0 || ch.in_cols[k] >= d->n_pred) return fail(c, EH_EINVAL, "chain in_cols[%d] out of range", k);
+        c->src_kind[c->ncols] = 0; c->src_idx[c->ncols] = ch.in_cols[k]; c->ncols++;
+    }
+    {
+        int fi = d->pm_args[2].index;
+        if (fi < 0 || fi >= d->n_forc) return fail(c, EH_EINVAL, "forcing index out of range");
+        c->src_kind[c->ncols] = 1; c->src_idx[c->ncols] = fi; c->ncols++;
+    }
+    for (int t = 0; t < d->n_targ; t++) { c->src_kind[c->ncols] = 1; c->src_idx[c->ncols] = d->n_forc + t; c->ncols++; }
+
+    // loss / optimiser
+    int n_rmse = 0;
+    for (int t = 0; t < d->n_targ; t++) {
+        int lk = d->loss_per_target[t];
+        if (lk < 0 || lk > 3) return fail(c, EH_EINVAL, "loss_per_target[%d]=%d unknown", t, lk);
+        c->loss_kind[t] = lk;
+        if (lk == EH_LOSS_RMSE) n_rmse++;
+    }
+    if (n_rmse && d->n_targ > 1) return fail(c, EH_EUNSUPPORTED, "rmse training loss with more than one target");
+    c->agg_mean = d->agg == EH_AGG_MEAN;
+    c->opt_kind = d->opt_kind;
+    if (c->opt_kind < 0 || c->opt_kind > 3) return fail(c, EH_EINVAL, "opt_kind=%d unknown", d->opt_kind);
+    c->adamw_coupled = d->adamw_decay_coupled_eta;
+    c->eta = d->eta; c->beta1 = d->beta1; c->beta2 = d->beta2; c->eps = d->eps; c->lambda = d->lambda;
+    c->bn_mean.assign((size_t)ch.n_in, 0.f);
+    c->bn_var.assign((size_t)ch.n_in, 1.f);
+    return EH_OK;
+}
+
+eh_status reset_opt_state(eh_ctx* c)
+{
+    OptState os;
+    os.b1t = c->beta1; os.b2t = c->beta2; os.t = 0; os.skipped = 0;
+    CK(cudaMemcpy(c->d_ost, &os, sizeof os, cudaMemcpyHostToDevice));
+    CK(cudaMemset(c->d_m, 0, (size_t)c->nflat * sizeof(float)));
+    CK(cudaMemset(c->d_v, 0, (size_t)c->nflat * sizeof(float)));
+    return EH_OK;
+}
+
+eh_status ensure_host_stage(eh_ctx* c, HostStage& h, int64_t B)
+{
+    if (B <= h.cap) return EH_OK;
+    if (h.d_X) cudaFree(h.d_X);
+    if (h.d_planes) cudaFree(h.d_planes);
+    if (h.d_rec) cudaFree(h.d_rec);
+    h.cap = 0;
+    int64_t cap = std::max<int64_t>(B, 4096);
+    CK(dalloc(&h.d_X, (size_t)cap * c->n_pred_raw));
+    CK(dalloc(&h.d_planes, (size_t)cap * (c->n_forc_raw + c->n_targ)));
+    CK(dalloc(&h.d_rec, (size_t)cap * c->var->R4));
+    if (!h.d_cnt) CK(dalloc(&h.d_cnt, (size_t)MAXT));
+    if (!h.d_bscal) CK(dalloc(&h.d_bscal, (size_t)BS_STRIDE));
+    if (!h.d_loss) CK(dalloc(&h.d_loss, (size_t)1));
+    if (!h.done) CK(cudaEventCreateWithFlags(&h.done, cudaEventDisableTiming));
+    h.cap = cap;
+    return EH_OK;
+}
+
+// enqueue: H2D copies of one host batch, pack, per-batch scalars, K1, K2 (all on c->stream)
+eh_status enqueue_host_step(eh_ctx* c, HostStage& h, int64_t B, const float* X, const float* const* forc,
+                            const float* const* targ)
+{
+    const Variant* v = c->var;
+    CK(cudaMemcpyAsync(h.d_X, X, (size_t)B * c->n_pred_raw * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    for (int f = 0; f < c->n_forc_raw; f++)
+        CK(cudaMemcpyAsync(h.d_planes + (size_t)f * B, forc[f], (size_t)B * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    for (int t = 0; t < c->n_targ; t++)
+        CK(cudaMemcpyAsync(h.d_planes + (size_t)(c->n_forc_raw + t) * B, targ[t], (size_t)B * sizeof(float),
+                           cudaMemcpyHostToDevice, c->stream));
+    PackArgs p;
+    memset(&p, 0, sizeof p);
+    p.X = h.d_X; p.planes = h.d_planes; p.N = B; p.P_raw = c->n_pred_raw; p.ncols = c->ncols; p.R4 = v->R4;
+    for (int i = 0; i < c->ncols; i++) { p.src_kind[i] = c->src_kind[i]; p.src_idx[i] = c->src_idx[i]; }
+    p.rec = h.d_rec; p.rec_base = 0;
+    bool heavy = c->use_bn;
+    for (int t = 0; t < c->n_targ; t++) heavy |= (c->loss_kind[t] == LOSS_NSELOSS);
+    if (!heavy) {
+        CK(cudaMemsetAsync(h.d_cnt, 0, MAXT * sizeof(int), c->stream));
+        k_pack_count<<<(unsigned)((B + 255) / 256), 256, 0, c->stream>>>(p, c->n_targ, v->P + v->F, h.d_cnt);
+        CK(cudaGetLastError());
+        k_bscal_from_counts<<<1, 32, 0, c->stream>>>(h.d_bscal, h.d_cnt, c->n_targ, c->agg_mean);
+        CK(cudaGetLastError());
+    } else {
+        k_pack<<<(unsigned)((B + 255) / 256), 256, 0, c->stream>>>(p);
+        CK(cudaGetLastError());
+        StatArgs a;
+        memset(&a, 0, sizeof a);
+        a.rec = h.d_rec; a.R4 = v->R4; a.idx = nullptr; a.rec_base = 0; a.n = B; a.Bfull = (int)B;
+        a.P = v->P; a.F = v->F; a.T = v->T;
+        const Split& sp = c->split[EH_SPLIT_TRAIN];
+        for (int t = 0; t < MAXT; t++) { a.shift_y[t] = sp.shift_y[t]; a.loss_kind[t] = c->loss_kind[t]; }
+        for (int k = 0; k < MAXP; k++) a.shift_x[k] = sp.shift_x[k];
+        a.agg_mean = c->agg_mean; a.use_bn = c->use_bn; a.bscal = h.d_bscal; a.bn_batch = nullptr;
+        k_batch_stats<<<1, 256, 0, c->stream>>>(a);
+        CK(cudaGetLastError());
+    }
+    StepArgs a;
+    fill_step_args(c, a);
+    a.rec = reinterpret_cast<const float4*>(h.d_rec);
+    a.idx = nullptr; a.rec_base = 0; a.B = (int)B; a.bscal = h.d_bscal;
+    Geom g = step_geometry(c, B);
+    const bool pdl = false;  // the step follows memcpy/pack work here, nothing to overlap with
+    CK(v->launch_step(a, g.grid, g.nwarps, g.smem, c->stream, pdl));
+    UpdateArgs u;
+    fill_update_args(c, u);
+    u.G = g.grid; u.bscal = h.d_bscal; u.loss_out = h.d_loss;
+    CK(launch_update(u, c->stream, pdl));
+    return EH_OK;
+}
+
+}  // namespace
+
+// =============================== C ABI ===============================
+extern "C" {
+
+eh_status eh_create(eh_ctx** out, const eh_model_desc* desc)
+{
+    if (!out || !desc) return fail(nullptr, EH_EINVAL, "null argument");
+    *out = nullptr;
+    eh_ctx* c = new (std::nothrow) eh_ctx();
+    if (!c) return fail(nullptr, EH_ENOMEM, "out of host memory");
+    auto bail = [&](eh_status s) {
+        g_create_error = c->err;
+        eh_destroy(c);
+        return s;
+    };
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        fail(c, EH_ECUDA, "no CUDA device available (%s); this library has no CPU fallback", cudaGetErrorString(e));
+        return bail(EH_ECUDA);
+    }
+    c->device = desc->device;
+    if (c->device < 0 || c->device >= ndev) { fail(c, EH_EINVAL, "device %d out of range 0..%d", c->device, ndev - 1); return bail(EH_EINVAL); }
+    cudaDeviceProp prop;
+    if ((e = cudaSetDevice(c->device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, c->device)) != cudaSuccess) {
+        fail(c, EH_ECUDA, "cudaSetDevice/GetDeviceProperties: %s", cudaGetErrorString(e));
+        return bail(EH_ECUDA);
+    }
+    if (prop.major != 10) {
+        fail(c, EH_ECUDA, "device %d is sm_%d%d; this library contains sm_100a code only", c->device, prop.major, prop.minor);
+        return bail(EH_ECUDA);
+    }
+    c->nsm = prop.multiProcessorCount;
+    c->smem_optin = prop.sharedMemPerBlockOptin;
+    eh_status s = build_plan(c, desc);
+    if (s != EH_OK) return bail(s);
+    const Variant* v = c->var;
+    auto cuda_setup = [&]() -> eh_status {
+        CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreate(&c->ev0));
+        CK(cudaEventCreate(&c->ev1));
+        size_t fixed = (size_t)(rup4(v->NW) + 64) * 4;
+        size_t stage = (size_t)v->stage_floats * 4;
+        int wmax = (int)std::min<size_t>(8, (c->smem_optin - fixed) / stage);
+        if (wmax < 1) return fail(c, EH_EUNSUPPORTED, "variant %s needs %zu B of shared memory per warp", v->name, stage);
+        CK(v->prepare(fixed + (size_t)wmax * stage, fixed));
+        CK(dalloc(&c->d_wsrc, c->h_wsrc.size()));
+        CK(dalloc(&c->d_pmap, c->h_pmap.size()));
+        CK(dalloc(&c->d_pspan, c->h_pspan.size()));
+        CK(cudaMemcpy(c->d_wsrc, c->h_wsrc.data(), c->h_wsrc.size() * sizeof(int), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->d_pmap, c->h_pmap.data(), c->h_pmap.size() * sizeof(int), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->d_pspan, c->h_pspan.data(), c->h_pspan.size() * sizeof(float), cudaMemcpyHostToDevice));
+        CK(dalloc(&c->d_theta, (size_t)c->nflat));
+        CK(dalloc(&c->d_m, (size_t)c->nflat));
+        CK(dalloc(&c->d_v, (size_t)c->nflat));
+        CK(dalloc(&c->d_grad, (size_t)c->nflat));
+        CK(dalloc(&c->d_ost, (size_t)1));
+        CK(dalloc(&c->d_partial, (size_t)(c->nsm + 8) * v->NPART));
+        CK(dalloc(&c->d_gvec, (size_t)v->NPART));
+        CK(dalloc(&c->d_err, (size_t)1));
+        CK(dalloc(&c->d_evalpart, (size_t)c->nsm * 4 * MAXT * EVAL_NSTAT));
+        CK(dalloc(&c->d_bn_test, (size_t)BS_STRIDE));
+        CK(cudaMemset(c->d_theta, 0, (size_t)c->nflat * sizeof(float)));
+        return reset_opt_state(c);
+    };
+    s = cuda_setup();
+    if (s != EH_OK) return bail(s);
+    *out = c;
+    return EH_OK;
+}
+
+void eh_destroy(eh_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    void* ptrs[] = {c->d_wsrc, c->d_pmap, c->d_pspan, c->d_theta, c->d_m, c->d_v, c->d_grad, c->d_ost, c->d_partial,
+                    c->d_gvec, c->d_bscal, c->d_bn_batch, c->d_idx, c->d_idx64, c->d_err, c->d_loss, c->d_evalpart,
+                    c->d_bn_test, c->split[0].rec, c->split[1].rec};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    for (HostStage& h : c->hs) {
+        void* hp[] = {h.d_X, h.d_planes, h.d_rec, h.d_cnt, h.d_bscal, h.d_loss};
+        for (void* p : hp)
+            if (p) cudaFree(p);
+        if (h.done) cudaEventDestroy(h.done);
+    }
+    if (c->h_loss) cudaFreeHost(c->h_loss);
+    if (c->h_async_loss) cudaFreeHost(c->h_async_loss);
+    for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    delete c;
+}
+
+const char* eh_last_error(const eh_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int64_t eh_num_params(const eh_ctx* c) { return c ? c->nflat : -1; }
+
+eh_status eh_upload(eh_ctx* c, int32_t split, int64_t N, const float* X, const float* const* forc,
+                    const float* const* targ)
+{
+    if (!c) return EH_EINVAL;
+    if (split < 0 || split > 1 || N < 0 || (N > 0 && (!X || !targ))) return fail(c, EH_EINVAL, "bad eh_upload arguments");
+    if (N > 0x7fffffffLL) return fail(c, EH_EUNSUPPORTED, "split larger than 2^31-1 samples");
+    CK(cudaSetDevice(c->device));
+    Split& sp = c->split[split];
+    if (sp.rec) { cudaFree(sp.rec); sp.rec = nullptr; }
+    sp.N = N;
+    sp.has_nan = false;
+    if (split == EH_SPLIT_TRAIN) { c->perm_n = 0; c->perm_B = 0; }
+    if (N == 0) return EH_OK;
+    const Variant* v = c->var;
+    // numerically convenient shifts + NaN census on the host (one pass over the targets)
+    for (int t = 0; t < c->n_targ; t++) {
+        double s = 0; int64_t n = 0;
+        for (int64_t i = 0; i < N; i++) { float y = targ[t][i]; if (y == y) { s += y; n++; } else sp.has_nan = true; }
+        sp.shift_y[t] = n ? (float)(s / (double)n) : 0.f;
+    }
+    if (c->use_bn) {
+        for (int k = 0; k < c->real_in; k++) {
+            double s = 0;
+            int col = c->src_idx[k];
+            for (int64_t i = 0; i < N; i++) s += X[(size_t)i * c->n_pred_raw + col];
+            sp.shift_x[k] = (float)(s / (double)N);
+        }
+    }
+    float *dX = nullptr, *dP = nullptr;
+    size_t nplanes = (size_t)(c->n_forc_raw + c->n_targ);
+    CK(dalloc(&sp.rec, (size_t)N * v->R4));
+    CK(dalloc(&dX, (size_t)N * c->n_pred_raw));
+    CK(dalloc(&dP, (size_t)N * nplanes));
+    CK(cudaMemcpyAsync(dX, X, (size_t)N * c->n_pred_raw * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    for (int f = 0; f < c->n_forc_raw; f++)
+        CK(cudaMemcpyAsync(dP + (size_t)f * N, forc[f], (size_t)N * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    for (int t = 0; t < c->n_targ; t++)
+        CK(cudaMemcpyAsync(dP + (size_t)(c->n_forc_raw + t) * N, targ[t], (size_t)N * sizeof(float), cudaMemcpyHostToDevice,
+                           c->stream));
+    PackArgs p;
+    memset(&p, 0, sizeof p);
+    p.X = dX; p.planes = dP; p.N = N; p.P_raw = c->n_pred_raw; p.ncols = c->ncols; p.R4 = v->R4;
+    for (int i = 0; i < c->ncols; i++) { p.src_kind[i] = c->src_kind[i]; p.src_idx[i] = c->src_idx[i]; }
+    p.rec = sp.rec; p.rec_base = 0;
+    k_pack<<<(unsigned)((N + 255) / 256), 256, 0, c->stream>>>(p);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(dX);
+    cudaFree(dP);
+    return EH_OK;
+}
+
+eh_status eh_set_params(eh_ctx* c, const float* flat, int64_t n)
+{
+    if (!c) return EH_EINVAL;
+    if (!flat || n != c->nflat) return fail(c, EH_EINVAL, "eh_set_params: expected %d entries, got %lld", c->nflat, (long long)n);
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(c->d_theta, flat, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return EH_OK;
+}
+
+eh_status eh_get_params(eh_ctx* c, float* flat, int64_t n)
+{
+    if (!c) return EH_EINVAL;
+    if (!flat || n != c->nflat) return fail(c, EH_EINVAL, "eh_get_params: expected %d entries, got %lld", c->nflat, (long long)n);
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(flat, c->d_theta, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return EH_OK;
+}
+
+eh_status eh_set_opt_state(eh_ctx* c, const float* m, const float* v, int64_t n, int64_t t)
+{
+    if (!c) return EH_EINVAL;
+    if (n != c->nflat || t < 0) return fail(c, EH_EINVAL, "eh_set_opt_state: bad size or step count");
+    CK(cudaSetDevice(c->device));
+    eh_status s = reset_opt_state(c);
+    if (s != EH_OK) return s;
+    if (m) CK(cudaMemcpy(c->d_m, m, (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
+    if (v) CK(cudaMemcpy(c->d_v, v, (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
+    OptState os;
+    os.b1t = c->beta1; os.b2t = c->beta2; os.t = t; os.skipped = 0;
+    for (int64_t i = 0; i < t; i++) { os.b1t *= c->beta1; os.b2t *= c->beta2; }
+    CK(cudaMemcpy(c->d_ost, &os, sizeof os, cudaMemcpyHostToDevice));
+    return EH_OK;
+}
+
+eh_status eh_get_opt_state(eh_ctx* c, float* m, float* v, int64_t n, int64_t* t)
+{
+    if (!c) return EH_EINVAL;
+    if (n != c->nflat) return fail(c, EH_EINVAL, "eh_get_opt_state: bad size");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    if (m) CK(cudaMemcpy(m, c->d_m, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+    if (v) CK(cudaMemcpy(v, c->d_v, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+    if (t) {
+        OptState os;
+        CK(cudaMemcpy(&os, c->d_ost, sizeof os, cudaMemcpyDeviceToHost));
+        *t = os.t;
+    }
+    return EH_OK;
+}
+
+eh_status eh_set_bn_state(eh_ctx* c, int32_t chain, const float* mean, const float* var, int32_t n)
+{
+    if (!c) return EH_EINVAL;
+    if (chain != 0 || n != c->real_in || !mean || !var) return fail(c, EH_EINVAL, "eh_set_bn_state: bad arguments");
+    for (int i = 0; i < n; i++) { c->bn_mean[i] = mean[i]; c->bn_var[i] = var[i]; }
+    return EH_OK;
+}
+
+eh_status eh_get_bn_state(eh_ctx* c, int32_t chain, float* mean, float* var, int32_t n)
+{
+    if (!c) return EH_EINVAL;
+    if (chain != 0 || n != c->real_in || !mean || !var) return fail(c, EH_EINVAL, "eh_get_bn_state: bad arguments");
+    for (int i = 0; i < n; i++) { mean[i] = c->bn_mean[i]; var[i] = c->bn_var[i]; }
+    return EH_OK;
+}
+
+static eh_status step_on_indices(eh_ctx* c, const int64_t* idx1, int64_t B, float* loss_out, float* grad_out, int apply)
+{
+    if (!c) return EH_EINVAL;
+    if (!idx1 || B <= 0) return fail(c, EH_EINVAL, "empty batch");
+    CK(cudaSetDevice(c->device));
+    const Split& sp = c->split[EH_SPLIT_TRAIN];
+    if (!sp.rec) return fail(c, EH_EINVAL, "train split not uploaded");
+    eh_status s = upload_indices(c, idx1, B, sp.N);
+    if (s != EH_OK) return s;
+    c->perm_n = 0; c->perm_B = 0;  // the resident index stream was overwritten
+    s = prepare_batch_rows(c, B, B);
+    if (s != EH_OK) return s;
+    float L = 0.f;
+    s = run_steps(c, B, B, 0, 1, &L, apply, grad_out);
+    if (s != EH_OK) return s;
+    if (loss_out) *loss_out = L;
+    return EH_OK;
+}
+
+eh_status eh_loss_grad(eh_ctx* c, const int64_t* idx1, int64_t B, float* loss_out, float* grad_out)
+{
+    return step_on_indices(c, idx1, B, loss_out, grad_out, 0);
+}
+
+eh_status eh_step(eh_ctx* c, const int64_t* idx1, int64_t B, float* loss_out, float* grad_out)
+{
+    return step_on_indices(c, idx1, B, loss_out, grad_out, 1);
+}
+
+eh_status eh_set_perm(eh_ctx* c, const int64_t* perm1, int64_t n)
+{
+    if (!c) return EH_EINVAL;
+    if (!perm1 || n <= 0) return fail(c, EH_EINVAL, "empty permutation");
+    CK(cudaSetDevice(c->device));
+    const Split& sp = c->split[EH_SPLIT_TRAIN];
+    if (!sp.rec) return fail(c, EH_EINVAL, "train split not uploaded");
+    eh_status s = upload_indices(c, perm1, n, sp.N);
+    if (s != EH_OK) return s;
+    c->perm_n = n;
+    c->perm_B = 0;
+    return EH_OK;
+}
+
+eh_status eh_run_steps(eh_ctx* c, int64_t B, int64_t first_step, int64_t n_steps, float* losses)
+{
+    if (!c) return EH_EINVAL;
+    if (c->perm_n <= 0) return fail(c, EH_EINVAL, "no resident permutation (call eh_set_perm)");
+    if (B <= 0) return fail(c, EH_EINVAL, "batch size must be positive");
+    CK(cudaSetDevice(c->device));
+    if (c->perm_B != B) {
+        eh_status s = prepare_batch_rows(c, c->perm_n, B);
+        if (s != EH_OK) return s;
+        c->perm_B = B;
+    }
+    return run_steps(c, c->perm_n, B, first_step, n_steps, losses, 1, nullptr);
+}
+
+eh_status eh_epoch(eh_ctx* c, const int64_t* perm1, int64_t n, int64_t B, float* losses)
+{
+    eh_status s = eh_set_perm(c, perm1, n);
+    if (s != EH_OK) return s;
+    if (B <= 0) return fail(c, EH_EINVAL, "batch size must be positive");
+    return eh_run_steps(c, B, 0, (n + B - 1) / B, losses);
+}
+
+eh_status eh_step_host(eh_ctx* c, int64_t B, const float* X, const float* const* forc, const float* const* targ,
+                       float* loss_out)
+{
+    if (!c) return EH_EINVAL;
+    if (B <= 0 || !X || !targ) return fail(c, EH_EINVAL, "bad eh_step_host arguments");
+    CK(cudaSetDevice(c->device));
+    HostStage& h = c->hs[0];
+    eh_status s = ensure_host_stage(c, h, B);
+    if (s != EH_OK) return s;
+    s = enqueue_host_step(c, h, B, X, forc, targ);
+    if (s != EH_OK) return s;
+    float L = 0.f;
+    CK(cudaMemcpyAsync(&L, h.d_loss, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (loss_out) *loss_out = L;
+    return EH_OK;
+}
+
+eh_status eh_step_host_async(eh_ctx* c, int64_t B, const float* X, const float* const* forc, const float* const* targ,
+                             float* loss_slot)
+{
+    if (!c) return EH_EINVAL;
+    if (B <= 0 || !X || !targ) return fail(c, EH_EINVAL, "bad eh_step_host_async arguments");
+    CK(cudaSetDevice(c->device));
+    if (c->async_used == c->async_cap) {
+        if (c->async_used) {
+            eh_status s = eh_sync(c);
+            if (s != EH_OK) return s;
+        }
+        if (!c->h_async_loss) {
+            c->async_cap = 4096;
+            CK(cudaMallocHost((void**)&c->h_async_loss, c->async_cap * sizeof(float)));
+        }
+    }
+    HostStage& h = c->hs[c->hs_next];
+    c->hs_next ^= 1;
+    // the staging buffers of this slot are free once the step that last used them has retired;
+    // everything runs in order on one stream, so reuse is already ordered.
+    eh_status s = ensure_host_stage(c, h, B);
+    if (s != EH_OK) return s;
+    s = enqueue_host_step(c, h, B, X, forc, targ);
+    if (s != EH_OK) return s;
+    float* pin = c->h_async_loss + c->async_used++;
+    CK(cudaMemcpyAsync(pin, h.d_loss, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    c->pending_loss.emplace_back(pin, loss_slot);
+    return EH_OK;
+}
+
+eh_status eh_sync(eh_ctx* c)
+{
+    if (!c) return EH_EINVAL;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    for (auto& pr : c->pending_loss)
+        if (pr.second) *pr.second = *pr.first;
+    c->pending_loss.clear();
+    c->async_used = 0;
+    return EH_OK;
+}
+
+eh_status eh_eval(eh_ctx* c, int32_t split, float* yhat, double* stats, float* nn_out)
+{
+    if (!c) return EH_EINVAL;
+    if (split < 0 || split > 1) return fail(c, EH_EINVAL, "bad split");
+    CK(cudaSetDevice(c->device));
+    const Split& sp = c->split[split];
+    if (!sp.rec) return fail(c, EH_EINVAL, "split %d not uploaded", split);
+    const Variant* v = c->var;
+    const int64_t N = sp.N;
+    float *d_yhat = nullptr, *d_par = nullptr;
+    if (yhat) CK(dalloc(&d_yhat, (size_t)N * v->T));
+    if (nn_out) CK(dalloc(&d_par, (size_t)N * v->NPS));
+    EvalArgs a;
+    memset(&a, 0, sizeof a);
+    a.rec = reinterpret_cast<const float4*>(sp.rec);
+    a.rec_base = 0; a.N = N; a.theta = c->d_theta; a.wsrc = c->d_wsrc;
+    a.use_bn = c->use_bn;
+    if (c->use_bn) {
+        // test mode: running statistics (LuxCore.testmode(st), compute_loss.jl:37)
+        float row[BS_STRIDE];
+        memset(row, 0, sizeof row);
+        for (int k = 0; k < c->real_in; k++) {
+            row[BS_BN + 2 * k] = c->bn_mean[k];
+            row[BS_BN + 2 * k + 1] = 1.0f / std::sqrt(c->bn_var[k] + 1e-5f);
+        }
+        CK(cudaMemcpyAsync(c->d_bn_test, row, sizeof row, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        a.bscal = c->d_bn_test;
+    }
+    for (int s = 0; s < MAXPS; s++) a.slot[s] = c->slots[s];
+    for (int i = 0; i < 4; i++) a.pmc[i] = c->pmc[i];
+    for (int t = 0; t < MAXT; t++) a.shift_y[t] = sp.shift_y[t];
+    a.yhat = d_yhat; a.parout = d_par; a.partial = c->d_evalpart;
+    const int nwarps = 8;
+    int64_t nchunks = (N + CHUNK - 1) / CHUNK;
+    int grid = (int)std::min<int64_t>((nchunks + nwarps - 1) / nwarps, (int64_t)c->nsm * 4);
+    if (grid < 1) grid = 1;
+    size_t smem = (size_t)(rup4(v->NW) + 64) * 4;
+    CK(cudaEventRecord(c->ev0, c->stream));
+    CK(v->launch_eval(a, grid, nwarps, smem, c->stream));
+    CK(cudaEventRecord(c->ev1, c->stream));
+    std::vector<double> part((size_t)grid * v->T * EVAL_NSTAT);
+    CK(cudaMemcpyAsync(part.data(), c->d_evalpart, part.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (yhat) CK(cudaMemcpyAsync(yhat, d_yhat, (size_t)N * v->T * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+    c->last_launches = 1;
+    if (nn_out) {
+        // rows of nn_out are indexed by the descriptor's parameter order
+        for (int pi = 0; pi < c->nparam_desc; pi++) {
+            int s = c->slot_of_param[pi];
+            if (s < 0 || c->slots[s].role != ROLE_NEURAL) continue;
+            CK(cudaMemcpy(nn_out + (size_t)pi * N, d_par + (size_t)s * N, (size_t)N * sizeof(float), cudaMemcpyDeviceToHost));
+        }
+    }
+    if (d_yhat) cudaFree(d_yhat);
+    if (d_par) cudaFree(d_par);
+    if (stats) {
+        for (int t = 0; t < v->T; t++) {
+            for (int q = 0; q < EVAL_NSTAT; q++) {
+                double s = 0;
+                for (int g = 0; g < grid; g++) s += part[(size_t)g * v->T * EVAL_NSTAT + t * EVAL_NSTAT + q];
+                stats[(size_t)t * EH_EVAL_STATS + q] = s;
+            }
+            stats[(size_t)t * EH_EVAL_STATS + 8] = sp.shift_y[t];
+        }
+    }
+    return EH_OK;
+}
+
+eh_status eh_comm_id(void* id_out)
+{
+    (void)id_out;
+    g_create_error = "data-parallel communicator not available in this build";
+    return EH_EUNSUPPORTED;
+}
+
+eh_status eh_comm_init(eh_ctx* c, int32_t rank, int32_t world, const void* id)
+{
+    (void)rank; (void)world; (void)id;
+    return fail(c, EH_EUNSUPPORTED, "data-parallel communicator not available in this build");
+}
+
+eh_status eh_last_timing(eh_ctx* c, float* total_ms, int64_t* launches, float* step_kernel_ms)
+{
+    if (!c) return EH_EINVAL;
+    if (total_ms) *total_ms = c->last_ms;
+    if (launches) *launches = c->last_launches;
+    if (step_kernel_ms) *step_kernel_ms = c->last_step_ms;
+    return EH_OK;
+}
+
+eh_status eh_set_profiling(eh_ctx* c, int32_t on)
+{
+    if (!c) return EH_EINVAL;
+    c->profiling = on ? 1 : 0;
+    return EH_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,282 @@
+// eh_update_kernel.cuh -- K2: fixed-order second-pass reduction + loss scalars +
+// optimiser update (one CTA), K0: per-batch data statistics, and the record packer.
+//
+// K2 replaces `Optimisers.update!(opt_state, ps, grads)` inside
+// Lux.Training.single_train_step! (call site src/training/epoch.jl:20-26) and the
+// scalar part of the loss (src/losses/loss_fn.jl:58-81, compute_loss.jl:50-53).
+// Optimiser rules follow Optimisers.jl (unpinned).
+#pragma once
+#include "eh_step_kernel.cuh"
+
+namespace eh {
+
+enum : int { OPT_ADAM = 0, OPT_ADAMW = 1, OPT_RMSPROP = 2, OPT_DESCENT = 3 };
+enum : int { UPD_FULL = 0, UPD_REDUCE_ONLY = 1, UPD_FROM_VECTOR = 2 };
+
+struct OptState {   // device-resident scalars
+    float b1t, b2t; // running beta^t products, as Optimisers keeps them (start at beta)
+    long long t;    // completed steps
+    long long skipped;
+};
+
+struct UpdateArgs {
+    const float* partial;  // [G][npart] from K1
+    int G, npart, npart_dw;
+    float* gvec;           // [npart] reduced vector (DP exchange buffer / UPD_FROM_VECTOR input)
+    int mode;              // UPD_*
+    int apply;             // 0: loss + gradient only (eh_loss_grad)
+    int nflat, ntheta;     // flat entries; the first ntheta are chain weights, the rest phi
+    const int* pmap;       // [nflat] index into the partial vector
+    const float* pspan;    // [nflat] phi entries: (upper - lower); 0 for theta
+    float* theta;
+    float* m;
+    float* v;
+    OptState* ost;
+    const float* bscal;    // this batch's scalar row
+    float* loss_out;       // device slot for this step's loss
+    float* grad_out;       // nullable: flat gradient of this step
+    int T, agg_mean;
+    int loss_kind[MAXT];
+    int opt_kind, adamw_coupled;
+    float eta, beta1, beta2, eps, lambda;
+    float world_scale;     // unused (reserved)
+};
+
+__global__ void __launch_bounds__(512, 1) k_update(const UpdateArgs a)
+{
+    __shared__ float red[2048];
+    __shared__ float s_loss, s_post;
+    __shared__ int s_skip;
+    pdl_wait();  // K1 of this step must be complete and flushed
+    pdl_launch_dependents();  // let the next K1 start its data prefetch
+
+    if (a.mode != UPD_FROM_VECTOR) {
+        for (int p = threadIdx.x; p < a.npart; p += blockDim.x) {
+            // fixed order over CTAs -> bitwise reproducible
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+            int g = 0;
+            for (; g + 4 <= a.G; g += 4) {
+                s0 += a.partial[(size_t)(g + 0) * a.npart + p];
+                s1 += a.partial[(size_t)(g + 1) * a.npart + p];
+                s2 += a.partial[(size_t)(g + 2) * a.npart + p];
+                s3 += a.partial[(size_t)(g + 3) * a.npart + p];
+            }
+            for (; g < a.G; g++) s0 += a.partial[(size_t)g * a.npart + p];
+            float s = (s0 + s1) + (s2 + s3);
+            red[p] = s;
+            if (a.mode == UPD_REDUCE_ONLY) a.gvec[p] = s;
+        }
+        if (a.mode == UPD_REDUCE_ONLY) return;
+    } else {
+        for (int p = threadIdx.x; p < a.npart; p += blockDim.x) red[p] = a.gvec[p];
+    }
+    __syncthreads();
+
+    if (threadIdx.x == 0) {
+        // loss_fn (loss_fn.jl:58-81) from the reduced sums, agg over targets (compute_loss.jl:50-53)
+        float L = 0.f, ntot = 0.f, post = 1.f;
+        for (int t = 0; t < a.T; t++) {
+            float n = a.bscal[BS_N + t], ss = a.bscal[BS_SS + t], acc = red[a.npart_dw + t];
+            ntot += n;
+            float lt;
+            switch (a.loss_kind[t]) {
+            case LOSS_MSE: lt = acc / n; break;
+            case LOSS_RMSE:
+                lt = sqrtf(acc / n);
+                post = 1.f / (2.f * lt);  // d sqrt(mse) = d mse / (2 rmse); single-target only (host checks)
+                break;
+            case LOSS_MAE: lt = acc / n; break;
+            default: lt = acc / ss; break;  // nseLoss = SSE / SS_tot
+            }
+            L += lt;
+        }
+        if (a.agg_mean) L /= (float)a.T;
+        // all-masked batch: skipped by run_epoch! (epoch.jl:17-19, 35-37)
+        int skip = (ntot == 0.f);
+        s_skip = skip;
+        s_post = post;
+        s_loss = skip ? __int_as_float(0x7fc00000) : L;
+        if (a.loss_out) *a.loss_out = s_loss;
+    }
+    __syncthreads();
+    const int skip = s_skip;
+    const float post = s_post;
+    const float b1t = a.ost->b1t, b2t = a.ost->b2t;
+    __syncthreads();
+
+    for (int p = threadIdx.x; p < a.nflat; p += blockDim.x) {
+        float g = red[a.pmap[p]] * post;
+        float th = a.theta[p];
+        if (p >= a.ntheta) {
+            // chain rule through scale_single_param: (u - l) sigma(raw) (1 - sigma(raw))
+            float sg = 1.f / (1.f + expf(-th));
+            g *= a.pspan[p] * sg * (1.f - sg);
+        }
+        if (a.grad_out) a.grad_out[p] = g;
+        if (!a.apply || skip) continue;
+        float dx;
+        if (a.opt_kind == OPT_ADAM || a.opt_kind == OPT_ADAMW) {
+            float mt = a.beta1 * a.m[p] + (1.f - a.beta1) * g;
+            float vt = a.beta2 * a.v[p] + (1.f - a.beta2) * g * g;
+            a.m[p] = mt;
+            a.v[p] = vt;
+            dx = mt / (1.f - b1t) / (sqrtf(vt / (1.f - b2t)) + a.eps) * a.eta;
+            if (a.opt_kind == OPT_ADAMW) dx += (a.adamw_coupled ? a.eta * a.lambda : a.lambda) * th;
+        } else if (a.opt_kind == OPT_RMSPROP) {
+            float q = a.beta2 * a.v[p] + (1.f - a.beta2) * g * g;
+            a.v[p] = q;
+            dx = g * a.eta / (sqrtf(q) + a.eps);
+        } else {
+            dx = a.eta * g;
+        }
+        a.theta[p] = th - dx;
+    }
+    if (threadIdx.x == 0 && a.apply) {
+        if (skip) {
+            a.ost->skipped += 1;
+        } else {
+            a.ost->b1t = b1t * a.beta1;
+            a.ost->b2t = b2t * a.beta2;
+            a.ost->t += 1;
+        }
+    }
+}
+
+// ---- K0: per-batch statistics that depend on the data only ------------------------
+// One CTA per batch.  Per target: n_valid, SS_tot = sum (y - mean_valid(y))^2 (nseLoss,
+// loss_fn.jl:79-81) and the seed scale c_t; per chain input the BatchNorm
+// batch mean / rstd (Lux BatchNorm training mode, biased variance, eps = 1e-5).
+struct StatArgs {
+    const float* rec;   // packed records as floats
+    int R4;             // floats per record
+    const int* idx;     // sample ids of all batches, batch b at idx + b*Bfull (NULL: rec_base + ...)
+    long long rec_base;
+    long long n;        // total samples covered
+    int Bfull;          // nominal batch size (last batch may be shorter)
+    int P, F, T;
+    float shift_y[MAXT];  // numerically convenient shift (split mean of each target)
+    float shift_x[MAXP];
+    int loss_kind[MAXT];
+    int agg_mean;
+    int use_bn;
+    float* bscal;       // [nbatches][BS_STRIDE]
+    float* bn_batch;    // nullable [nbatches][2*P]: raw (mean, biased var) for the running-stat update
+};
+
+__global__ void __launch_bounds__(256) k_batch_stats(const StatArgs a)
+{
+    __shared__ double sh[8][3 * MAXT + 2 * MAXP];
+    const int b = blockIdx.x;
+    const long long base = (long long)b * a.Bfull;
+    const int nb = (int)((a.n - base) < a.Bfull ? (a.n - base) : a.Bfull);
+    double cnt[MAXT], s1[MAXT], s2[MAXT], x1[MAXP], x2[MAXP];
+#pragma unroll
+    for (int t = 0; t < MAXT; t++) cnt[t] = s1[t] = s2[t] = 0.0;
+#pragma unroll
+    for (int k = 0; k < MAXP; k++) x1[k] = x2[k] = 0.0;
+    for (int s = threadIdx.x; s < nb; s += blockDim.x) {
+        long long i = a.idx ? (long long)a.idx[base + s] : a.rec_base + base + s;
+        const float* r = a.rec + i * a.R4;
+#pragma unroll
+        for (int t = 0; t < MAXT; t++)
+            if (t < a.T) {
+                float y = r[a.P + a.F + t];
+                if (y == y) {
+                    double d = (double)y - (double)a.shift_y[t];
+                    cnt[t] += 1.0; s1[t] += d; s2[t] += d * d;
+                }
+            }
+        if (a.use_bn) {
+#pragma unroll
+            for (int k = 0; k < MAXP; k++)
+                if (k < a.P) {
+                    double d = (double)r[k] - (double)a.shift_x[k];
+                    x1[k] += d; x2[k] += d * d;
+                }
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int t = 0; t < MAXT; t++) {
+        double c = warp_sum_d(cnt[t]), u = warp_sum_d(s1[t]), w = warp_sum_d(s2[t]);
+        if (lane == 0) { sh[warp][3 * t] = c; sh[warp][3 * t + 1] = u; sh[warp][3 * t + 2] = w; }
+    }
+#pragma unroll
+    for (int k = 0; k < MAXP; k++) {
+        double u = warp_sum_d(x1[k]), w = warp_sum_d(x2[k]);
+        if (lane == 0) { sh[warp][3 * MAXT + 2 * k] = u; sh[warp][3 * MAXT + 2 * k + 1] = w; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float* out = a.bscal + (size_t)b * BS_STRIDE;
+        const int nw = blockDim.x >> 5;
+        for (int t = 0; t < MAXT; t++) {
+            double c = 0, u = 0, w = 0;
+            for (int q = 0; q < nw; q++) { c += sh[q][3 * t]; u += sh[q][3 * t + 1]; w += sh[q][3 * t + 2]; }
+            double sstot = c > 0 ? w - u * u / c : 0.0;
+            double aggw = a.agg_mean ? 1.0 / a.T : 1.0;
+            double ct = 0.0;
+            if (t < a.T) ct = (a.loss_kind[t] == LOSS_NSELOSS) ? aggw / sstot : aggw / c;
+            out[BS_C + t] = (float)ct;
+            out[BS_N + t] = (float)c;
+            out[BS_SS + t] = (float)sstot;
+        }
+        for (int k = 0; k < MAXP; k++) {
+            double u = 0, w = 0;
+            for (int q = 0; q < nw; q++) { u += sh[q][3 * MAXT + 2 * k]; w += sh[q][3 * MAXT + 2 * k + 1]; }
+            double mu = 0.0, var = 1.0 - 1e-5;
+            if (a.use_bn && k < a.P && nb > 0) {
+                mu = u / nb;
+                var = w / nb - mu * mu;
+                mu += (double)a.shift_x[k];
+                if (var < 0) var = 0;
+            }
+            out[BS_BN + 2 * k] = (float)mu;
+            out[BS_BN + 2 * k + 1] = (float)(1.0 / sqrt((double)(float)var + 1e-5));
+            if (a.bn_batch && k < a.P) {
+                a.bn_batch[(size_t)b * 2 * a.P + 2 * k] = (float)mu;
+                a.bn_batch[(size_t)b * 2 * a.P + 2 * k + 1] = (float)var;
+            }
+        }
+    }
+}
+
+// ---- record packer: prepare_data's ((X, forcings), targets) -> canonical AoS records ----
+// canonical column c of a record comes from source plane src_plane[c] (0..P_raw-1: row of X,
+// P_raw.. : forcing / target vectors stored after X) ; X is P_raw x N column-major.
+struct PackArgs {
+    const float* X;       // [N][P_raw]
+    const float* planes;  // [(F_raw + T)][N]
+    long long N;
+    int P_raw;
+    int ncols;            // used columns of a record
+    int R4;
+    int src_kind[24];     // 0: X row, 1: plane
+    int src_idx[24];
+    float* rec;           // [N][R4]
+    long long rec_base;   // first record to write
+};
+
+__global__ void __launch_bounds__(256) k_pack(const PackArgs a)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.N) return;
+    float* r = a.rec + (a.rec_base + i) * a.R4;
+    for (int c = 0; c < a.R4; c++) {
+        float v = 0.f;
+        if (c < a.ncols) v = a.src_kind[c] == 0 ? a.X[i * a.P_raw + a.src_idx[c]] : a.planes[(long long)a.src_idx[c] * a.N + i];
+        r[c] = v;
+    }
+}
+
+// int64 1-based -> int32 0-based index conversion (Julia permutations)
+__global__ void __launch_bounds__(256) k_idx_convert(const long long* in, int* out, long long n, long long nmax, int* err)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    long long v = in[i] - 1;
+    if (v < 0 || v >= nmax) { *err = 1; v = 0; }
+    out[i] = (int)v;
+}
+
+}  // namespace eh

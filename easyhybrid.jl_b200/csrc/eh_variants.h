@@ -1,0 +1,25 @@
+// eh_variants.h -- registry of ahead-of-time compiled kernel variants (host side).
+#pragma once
+#include <cuda_runtime.h>
+#include "eh_layout.h"
+
+namespace eh {
+
+struct StepArgs;
+struct EvalArgs;
+
+struct Variant {
+    int pm, P, NH, H, NOUT, act, scale;
+    ShapeDims dims;
+    int F, T, NPS, R4, NB, NW, NPART, stage_floats;
+    const char* name;
+    cudaError_t (*prepare)(size_t step_smem, size_t eval_smem);
+    cudaError_t (*launch_step)(const StepArgs& a, int grid, int nwarps, size_t smem, cudaStream_t st, bool pdl);
+    cudaError_t (*launch_eval)(const EvalArgs& a, int grid, int nwarps, size_t smem, cudaStream_t st);
+};
+
+const Variant* find_variant(int pm, int P, int NH, int H, int NOUT, int act, int scale);
+int num_variants();
+const Variant* variant_at(int i);
+
+}  // namespace eh

@@ -1,0 +1,162 @@
+"""FusedSession: one ``eh_ctx`` of libeasyhybrid_cuda.so, wrapped for the Python host.
+
+Every method is a thin ctypes call through the C ABI (include/easyhybrid_cuda.h); numpy
+arrays are only marshalled.  There is no CPU code path behind these calls."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _abi
+from ._lib import EasyHybridCudaError, load
+from .model import build_desc, predictor_columns
+
+_fp = C.POINTER(C.c_float)
+
+
+def _f32(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a, a.ctypes.data_as(_fp)
+
+
+def _ptr_array(arrs):
+    keep = [np.ascontiguousarray(a, dtype=np.float32) for a in arrs]
+    pa = (_fp * max(len(keep), 1))(*[a.ctypes.data_as(_fp) for a in keep])
+    return keep, pa
+
+
+class FusedSession:
+    def __init__(self, model, *, training_loss="mse", agg="sum", opt=None, device=0, flags=0):
+        self.lib = load()
+        self.model = model
+        self.bundle = build_desc(model, training_loss=training_loss, agg=agg, opt=opt, device=device, flags=flags)
+        h = C.c_void_p()
+        st = self.lib.eh_create(C.byref(h), self.bundle.byref())
+        if st != _abi.EH_OK:
+            raise EasyHybridCudaError(st, (self.lib.eh_last_error(None) or b"").decode())
+        self.h = h
+        self.n_flat = int(self.lib.eh_num_params(self.h))
+        self.pcols = predictor_columns(model)
+        self.n = {0: 0, 1: 0}
+
+    def _ck(self, st):
+        if st != _abi.EH_OK:
+            raise EasyHybridCudaError(st, (self.lib.eh_last_error(self.h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.eh_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    # ---- data ----
+    def upload(self, split, xf, y):
+        X, forc = xf
+        Xc, Xp = _f32(X)
+        kf, pf = _ptr_array([forc[f] for f in self.model.forcing])
+        kt, pt = _ptr_array([y[t] for t in self.model.targets])
+        n = Xc.shape[0]
+        self._ck(self.lib.eh_upload(self.h, split, n, Xp, pf, pt))
+        self.n[split] = n
+
+    # ---- parameters / state ----
+    def set_params(self, flat):
+        a, p = _f32(flat)
+        self._ck(self.lib.eh_set_params(self.h, p, a.size))
+
+    def get_params(self):
+        out = np.empty(self.n_flat, dtype=np.float32)
+        self._ck(self.lib.eh_get_params(self.h, out.ctypes.data_as(_fp), out.size))
+        return out
+
+    def set_opt_state(self, m=None, v=None, t=0):
+        km, pm = _f32(m) if m is not None else (None, None)
+        kv, pv = _f32(v) if v is not None else (None, None)
+        self._ck(self.lib.eh_set_opt_state(self.h, pm, pv, self.n_flat, int(t)))
+
+    def get_opt_state(self):
+        m = np.empty(self.n_flat, dtype=np.float32)
+        v = np.empty(self.n_flat, dtype=np.float32)
+        t = C.c_int64(0)
+        self._ck(self.lib.eh_get_opt_state(self.h, m.ctypes.data_as(_fp), v.ctypes.data_as(_fp), self.n_flat, C.byref(t)))
+        return m, v, int(t.value)
+
+    def get_bn_state(self, chain=0):
+        n = len(self.model.chains[chain]["predictors"])
+        mean, var = np.empty(n, np.float32), np.empty(n, np.float32)
+        self._ck(self.lib.eh_get_bn_state(self.h, chain, mean.ctypes.data_as(_fp), var.ctypes.data_as(_fp), n))
+        return mean, var
+
+    def set_bn_state(self, mean, var, chain=0):
+        a, pa = _f32(mean)
+        b, pb = _f32(var)
+        self._ck(self.lib.eh_set_bn_state(self.h, chain, pa, pb, a.size))
+
+    # ---- steps ----
+    @staticmethod
+    def _idx1(idx0):
+        a = np.ascontiguousarray(np.asarray(idx0, dtype=np.int64) + 1)
+        return a, a.ctypes.data_as(C.POINTER(C.c_int64))
+
+    def loss_grad(self, idx0):
+        a, p = self._idx1(idx0)
+        loss = C.c_float(0)
+        g = np.empty(self.n_flat, dtype=np.float32)
+        self._ck(self.lib.eh_loss_grad(self.h, p, a.size, C.byref(loss), g.ctypes.data_as(_fp)))
+        return float(loss.value), g
+
+    def step(self, idx0, want_grad=False):
+        a, p = self._idx1(idx0)
+        loss = C.c_float(0)
+        g = np.empty(self.n_flat, dtype=np.float32) if want_grad else None
+        self._ck(self.lib.eh_step(self.h, p, a.size, C.byref(loss), g.ctypes.data_as(_fp) if want_grad else None))
+        return (float(loss.value), g) if want_grad else float(loss.value)
+
+    def step_host(self, xf, y):
+        X, forc = xf
+        Xc, Xp = _f32(X)
+        kf, pf = _ptr_array([forc[f] for f in self.model.forcing])
+        kt, pt = _ptr_array([y[t] for t in self.model.targets])
+        loss = C.c_float(0)
+        self._ck(self.lib.eh_step_host(self.h, Xc.shape[0], Xp, pf, pt, C.byref(loss)))
+        return float(loss.value)
+
+    def epoch(self, perm0, batchsize):
+        a, p = self._idx1(perm0)
+        nsteps = (a.size + batchsize - 1) // batchsize
+        losses = np.empty(nsteps, dtype=np.float32)
+        self._ck(self.lib.eh_epoch(self.h, p, a.size, batchsize, losses.ctypes.data_as(_fp)))
+        return losses
+
+    def set_perm(self, perm0):
+        a, p = self._idx1(perm0)
+        self._ck(self.lib.eh_set_perm(self.h, p, a.size))
+
+    def run_steps(self, batchsize, first_step, n_steps):
+        losses = np.empty(n_steps, dtype=np.float32)
+        self._ck(self.lib.eh_run_steps(self.h, batchsize, first_step, n_steps, losses.ctypes.data_as(_fp)))
+        return losses
+
+    # ---- evaluation ----
+    def eval(self, split, want_yhat=True, want_params=False):
+        n = self.n[split]
+        T = len(self.model.targets)
+        yhat = np.empty((T, n), dtype=np.float32) if want_yhat else None
+        stats = np.zeros((T, _abi.EH_EVAL_STATS), dtype=np.float64)
+        npar = len(self.model.parameters.names)
+        par = np.full((npar, n), np.nan, dtype=np.float32) if want_params else None
+        self._ck(self.lib.eh_eval(self.h, split, yhat.ctypes.data_as(_fp) if want_yhat else None,
+                                  stats.ctypes.data_as(C.POINTER(C.c_double)),
+                                  par.ctypes.data_as(_fp) if want_params else None))
+        return yhat, stats, par
+
+    # ---- timing ----
+    def last_timing(self):
+        ms, n, kms = C.c_float(0), C.c_int64(0), C.c_float(0)
+        self._ck(self.lib.eh_last_timing(self.h, C.byref(ms), C.byref(n), C.byref(kms)))
+        return float(ms.value), int(n.value), float(kms.value)
+
+    def set_profiling(self, on):
+        self._ck(self.lib.eh_set_profiling(self.h, int(bool(on))))

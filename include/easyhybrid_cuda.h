@@ -1,0 +1,271 @@
+/*
+ * easyhybrid_cuda.h -- C ABI of libeasyhybrid_cuda.so
+ *
+ * The drop-in boundary for EasyHybrid.jl's hybrid training step
+ * (forward Dense chain -> process model -> masked loss -> analytic backward
+ * -> optimiser update), implemented as hand-written sm_100a CUDA.
+ *
+ * Everything here is plain C: opaque handle, host pointers + sizes, int32/
+ * int64/float scalars.  No torch / CUDA types cross the boundary.  A Julia
+ * host reaches it with `ccall` (julia/EasyHybridCUDA.jl);
+ * this repo's tests and bench reach it with `ctypes`.
+ *
+ * Conventions
+ *   - every entry point returns eh_status and never throws/aborts; the text
+ *     for the last failure on a ctx is eh_last_error(ctx) (ctx==NULL: the
+ *     text of the last failed eh_create on this thread).
+ *   - all pointers are HOST pointers owned by the caller; the library copies
+ *     during the call and retains nothing (Julia: GC.@preserve for the call).
+ *   - index arrays are Julia 1-based int64 and converted inside.
+ *   - "flat" parameter vectors use the reference's ComponentArray order
+ *     (src/training/initialization.jl:42-44 `ps |> ComponentArray`;
+ *      src/models/GenericHybridModel.jl:236-256 initialparameters):
+ *       [chain 1: layer_1.weight (out x in, column-major), layer_1.bias, ...,
+ *        chain 2: ..., phi_raw[g] for g in global_param_names]
+ *   - a ctx is single-owner (not thread-safe); calls are synchronous unless
+ *     stated otherwise.
+ *   - there is NO CPU fallback: without a usable sm_100 device eh_create
+ *     fails with EH_ECUDA.
+ *
+ * Reference interfaces replaced (paths relative to the EasyHybrid.jl tree):
+ *   eh_create        <- constructHybridModel (src/models/GenericHybridModel.jl:89-232)
+ *                       + TrainConfig fields   (src/config/TrainingConfig.jl:9-160)
+ *                       + init_model_state     (src/training/initialization.jl:17-51)
+ *   eh_upload        <- prepare_data output layout (src/data/prepare_data.jl:3-10),
+ *                       `|> cfg.gdev` staging  (src/training/train.jl:114-116)
+ *   eh_set/get_params<- train_state.parameters (src/training/epoch.jl:29-30)
+ *   eh_step          <- Lux.Training.single_train_step! call site
+ *                       (src/training/epoch.jl:20-26) on DataLoader batch k
+ *   eh_step_host     <- collect_dim_data + `|> cfg.gdev` + single_train_step!
+ *                       (src/training/epoch.jl:1-11, 20-26)
+ *   eh_loss_grad     <- Zygote.pullback of compute_loss (src/losses/compute_loss.jl:20-35)
+ *   eh_epoch         <- run_epoch! (src/training/epoch.jl:13-33)
+ *   eh_eval          <- evaluate_acc / evaluate_epoch (src/training/train.jl:347-355,
+ *                       src/training/epoch.jl:53-66)
+ */
+#ifndef EASYHYBRID_CUDA_H
+#define EASYHYBRID_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EH_ABI_VERSION 1
+
+typedef struct eh_ctx eh_ctx; /* opaque; one per training run */
+
+typedef enum {
+    EH_OK = 0,
+    EH_EINVAL = 1,       /* bad argument / inconsistent descriptor            */
+    EH_ENOMEM = 2,       /* host or device allocation failed                  */
+    EH_ECUDA = 3,        /* CUDA runtime error or no sm_100 device            */
+    EH_ENCCL = 4,        /* NCCL / peer-memory error                          */
+    EH_EUNSUPPORTED = 5  /* valid model, but no fused kernel for it (caller   */
+                         /* may fall back to the stock Lux path explicitly)   */
+} eh_status;
+
+/* activation of the hidden Dense layers (src/models/NNModels.jl:225-230) */
+typedef enum {
+    EH_ACT_IDENTITY = 0, EH_ACT_TANH = 1, EH_ACT_SIGMOID = 2,
+    EH_ACT_RELU = 3, EH_ACT_SWISH = 4
+} eh_activation;
+
+/* role of one process-model parameter (GenericHybridModel.jl:127, 377-414) */
+typedef enum { EH_ROLE_NEURAL = 0, EH_ROLE_GLOBAL = 1, EH_ROLE_FIXED = 2 } eh_role;
+
+/* per-target loss (src/losses/loss_fn.jl:58-81) */
+typedef enum { EH_LOSS_MSE = 0, EH_LOSS_RMSE = 1, EH_LOSS_MAE = 2, EH_LOSS_NSELOSS = 3 } eh_loss;
+
+/* agg over targets (src/config/TrainingConfig.jl:77; compute_loss.jl:50-53) */
+typedef enum { EH_AGG_SUM = 0, EH_AGG_MEAN = 1 } eh_agg;
+
+/* Optimisers.jl rules routed by train (src/training/train.jl:20-22) */
+typedef enum { EH_OPT_ADAM = 0, EH_OPT_ADAMW = 1, EH_OPT_RMSPROP = 2, EH_OPT_DESCENT = 3 } eh_opt;
+
+/* built-in process-model forms.  Argument binding
+ * for each form is given by eh_model_desc.pm_args (see below).            */
+typedef enum {
+    EH_PM_RBQ10 = 0,    /* y0 = rb * Q10^(0.1*(ta - tref));  args: rb, Q10, ta ; consts: tref */
+    EH_PM_EXPO = 1,     /* y0 = Resp0 * exp(k * T);          args: Resp0, k, T               */
+    EH_PM_LINEAR = 2,   /* y0 = a * x + b;                   args: a, b, x                   */
+    EH_PM_LINEAR2 = 3,  /* y0 = a*x + b ; y1 = 2a*x + b;     args: a, b, x (test_compute_loss.jl:209-211) */
+    EH_PM_PROGRAM = 100 /* traced straight-line program, see eh_pm_instr                      */
+} eh_process_model;
+
+/* one argument of a built-in process model: where its value comes from */
+typedef struct {
+    int32_t kind;  /* 0 = process parameter (index into the parameter table), 1 = forcing column */
+    int32_t index;
+} eh_pm_arg;
+
+/* Straight-line SSA program for EH_PM_PROGRAM: instruction i defines value i.
+ * Produced by tracing the user's `mechanistic_model(; forcings..., params...)`
+ * with a symbolic number type on the host side.                             */
+typedef enum {
+    EH_OP_CONST = 0, EH_OP_FORCING = 1, EH_OP_PARAM = 2,
+    EH_OP_ADD = 10, EH_OP_SUB = 11, EH_OP_MUL = 12, EH_OP_DIV = 13, EH_OP_POW = 14,
+    EH_OP_MIN = 15, EH_OP_MAX = 16,
+    EH_OP_NEG = 20, EH_OP_EXP = 21, EH_OP_LOG = 22, EH_OP_SQRT = 23, EH_OP_TANH = 24,
+    EH_OP_SIGMOID = 25, EH_OP_ABS = 26, EH_OP_SIN = 27, EH_OP_COS = 28
+} eh_pm_op;
+
+typedef struct {
+    int32_t op;   /* eh_pm_op                                   */
+    int32_t a, b; /* operand value ids, or column / parameter index for FORCING / PARAM */
+    float imm;    /* EH_OP_CONST value                          */
+} eh_pm_instr;
+
+/* One Dense chain (prepare_hidden_chain, src/models/NNModels.jl:220-231):
+ *   Chain(identity|BatchNorm(affine=false), Dense(in,h1,act), ..., Dense(hk,out))
+ * SingleNNHybridModel has one chain with n_out = #neural params;
+ * MultiNNHybridModel has one chain per neural param, each with n_out = 1.   */
+typedef struct {
+    int32_t n_in;             /* predictors feeding this chain                        */
+    const int32_t* in_cols;   /* [n_in] indices into the predictor columns of a record */
+    int32_t n_hidden;         /* number of hidden layers (>= 1)                        */
+    const int32_t* hidden;    /* [n_hidden] widths                                     */
+    int32_t n_out;            /* output width                                          */
+    int32_t activation;       /* eh_activation of the hidden layers                    */
+    int32_t input_batchnorm;  /* 0/1: BatchNorm(n_in, affine=false) in front           */
+} eh_chain_desc;
+
+typedef struct {
+    int32_t abi_version; /* = EH_ABI_VERSION */
+
+    /* record layout: predictors, forcings, targets (prepare_data.jl:3-10) */
+    int32_t n_pred, n_forc, n_targ;
+
+    /* Dense chains */
+    int32_t n_chains;
+    const eh_chain_desc* chains;
+
+    /* process parameters, ParameterContainer order (helpers_for_HybridModel.jl:95-102) */
+    int32_t n_params;
+    const int32_t* role;        /* [n_params] eh_role                                     */
+    const int32_t* role_index;  /* NEURAL: chain*65536 + output row; GLOBAL: position in   */
+                                /* global_param_names (= position in the flat vector tail) */
+    const float* deflt;         /* [n_params] */
+    const float* lower;         /* [n_params] */
+    const float* upper;         /* [n_params] */
+    int32_t scale_nn_outputs;   /* GenericHybridModel.jl:394-401 */
+
+    /* process model */
+    int32_t process_model;      /* eh_process_model */
+    int32_t n_pm_args;
+    const eh_pm_arg* pm_args;   /* built-ins: canonical argument order of the form         */
+    float pm_consts[4];         /* built-ins: e.g. tref for RBQ10                          */
+    const eh_pm_instr* pm_prog; /* EH_PM_PROGRAM */
+    int32_t pm_len;
+    const int32_t* pm_outputs;  /* [n_targ] value ids of the targets                       */
+
+    /* loss: training_loss (one per target; the same value repeated unless PerTarget) */
+    const int32_t* loss_per_target; /* [n_targ] eh_loss */
+    int32_t agg;                    /* eh_agg */
+
+    /* optimiser (one rule over the whole flat vector, phi included) */
+    int32_t opt_kind;               /* eh_opt */
+    float eta, beta1, beta2, eps, lambda; /* rho of RMSProp travels in beta2 */
+    int32_t adamw_decay_coupled_eta;  /* 1: theta -= eta*lambda*theta (Optimisers >= 0.4); 0: lambda*theta */
+
+    /* device / data parallel */
+    int32_t device;                 /* CUDA device ordinal for this ctx */
+    int32_t flags;                  /* EH_FLAG_* */
+} eh_model_desc;
+
+#define EH_FLAG_NO_GRAPH 1u   /* launch every step individually (debug / profiling) */
+#define EH_FLAG_NO_PDL   2u   /* no programmatic dependent launch                   */
+
+enum { EH_SPLIT_TRAIN = 0, EH_SPLIT_VAL = 1 };
+
+/* number of doubles written per target by eh_eval (sufficient statistics):
+ *  n, sum_y, sum_yhat, sum_yy, sum_hh, sum_yh, sse, sae    -- sums are shifted by the
+ *  per-split target mean estimate that is written in slot 8 (shift), so callers
+ *  compute mse/rmse/mae/r2/nse/pearson/kge from them without cancellation. */
+#define EH_EVAL_STATS 9
+
+eh_status eh_create(eh_ctx** out, const eh_model_desc* desc);
+void eh_destroy(eh_ctx* ctx);
+const char* eh_last_error(const eh_ctx* ctx);
+
+/* number of entries of the flat parameter vector (theta then phi) */
+int64_t eh_num_params(const eh_ctx* ctx);
+
+/* Stage one split on the device, once.  X is n_pred x N column-major (each
+ * sample's predictors contiguous, Julia Matrix{Float32} P x N), forc/targ are
+ * arrays of n_forc / n_targ pointers to N-vectors; NaN target = missing
+ * (valid_mask, src/training/train.jl:221-232, is derived on the device).    */
+eh_status eh_upload(eh_ctx* ctx, int32_t split, int64_t N, const float* X,
+                    const float* const* forc, const float* const* targ);
+
+eh_status eh_set_params(eh_ctx* ctx, const float* flat, int64_t n);
+eh_status eh_get_params(eh_ctx* ctx, float* flat, int64_t n);
+/* optimiser state: m, v (Adam/AdamW; RMSProp uses v only), step count t */
+eh_status eh_set_opt_state(eh_ctx* ctx, const float* m, const float* v, int64_t n, int64_t t);
+eh_status eh_get_opt_state(eh_ctx* ctx, float* m, float* v, int64_t n, int64_t* t);
+/* input-BatchNorm running statistics of chain c (Lux `st`): mean, var [n_in] */
+eh_status eh_set_bn_state(eh_ctx* ctx, int32_t chain, const float* mean, const float* var, int32_t n);
+eh_status eh_get_bn_state(eh_ctx* ctx, int32_t chain, float* mean, float* var, int32_t n);
+
+/* loss and gradient of the training objective on batch idx1 of the TRAIN split,
+ * no update (parity hook; grad_out has eh_num_params entries, may be NULL)   */
+eh_status eh_loss_grad(eh_ctx* ctx, const int64_t* idx1, int64_t B, float* loss_out, float* grad_out);
+
+/* one optimiser step on batch idx1 (1-based indices into the TRAIN split).
+ * An all-masked batch is skipped (src/training/epoch.jl:17-19): *loss_out = NaN,
+ * parameters and step count unchanged.                                       */
+eh_status eh_step(eh_ctx* ctx, const int64_t* idx1, int64_t B, float* loss_out, float* grad_out);
+
+/* same, on a batch handed over as host arrays laid out like eh_upload's
+ * (collect_dim_data |> gdev, src/training/epoch.jl:1-11); the H2D copy is
+ * part of the call.                                                          */
+eh_status eh_step_host(eh_ctx* ctx, int64_t B, const float* X, const float* const* forc,
+                       const float* const* targ, float* loss_out);
+
+/* Pipelined form of eh_step_host for streaming callers: enqueue the copy and
+ * the step asynchronously (double-buffered pinned staging inside the ctx) and
+ * return; losses[slot] is filled when the step retires.  eh_sync waits for
+ * everything enqueued so far.                                                */
+eh_status eh_step_host_async(eh_ctx* ctx, int64_t B, const float* X, const float* const* forc,
+                             const float* const* targ, float* loss_slot);
+eh_status eh_sync(eh_ctx* ctx);
+
+/* run_epoch!: batches k = perm1[(k-1)B+1 : min(kB,n)] in order, one step each,
+ * last batch partial; losses (nullable) receives ceil(n/B) per-step losses.  */
+eh_status eh_epoch(eh_ctx* ctx, const int64_t* perm1, int64_t n, int64_t B, float* losses);
+
+/* same, with the index stream already resident (set once with eh_set_perm):
+ * runs steps [first_step, first_step + n_steps) of the stored permutation.   */
+eh_status eh_set_perm(eh_ctx* ctx, const int64_t* perm1, int64_t n);
+eh_status eh_run_steps(eh_ctx* ctx, int64_t B, int64_t first_step, int64_t n_steps, float* losses);
+
+/* test-mode forward on a whole split (evaluate_acc): yhat (nullable) is
+ * n_targ x N row-major-by-target (target t at yhat + t*N); stats (nullable) is
+ * n_targ x EH_EVAL_STATS doubles.  nn_out (nullable) is n_params x N: the
+ * scaled per-sample value of every NEURAL parameter (rows of other roles are
+ * left untouched) -- the `parameters` entry of the reference forward output. */
+eh_status eh_eval(eh_ctx* ctx, int32_t split, float* yhat, double* stats, float* nn_out);
+
+/* ---- data parallel (one process per GPU) ---------------------------------
+ * Rank r owns the contiguous slice [r*B/W, (r+1)*B/W) of every global batch.
+ * Exchange = one sum-allreduce per step of the scaled gradient and the loss
+ * statistics; parameters and optimiser state stay replicated bit-identically.
+ * The caller transports `id` (EH_COMM_ID_BYTES, from rank 0's eh_comm_id)
+ * to all ranks with its own plumbing (torch.distributed / MPI / files).     */
+#define EH_COMM_ID_BYTES 128
+eh_status eh_comm_id(void* id_out);
+eh_status eh_comm_init(eh_ctx* ctx, int32_t rank, int32_t world, const void* id);
+
+/* timing hook: device time in ms of the last eh_epoch / eh_run_steps call,
+ * measured with CUDA events on the stream the kernels ran on; kernel launches
+ * made by that call; and the accumulated device time of the fused step kernel
+ * alone when profiling is enabled with eh_set_profiling(ctx, 1).             */
+eh_status eh_last_timing(eh_ctx* ctx, float* total_ms, int64_t* launches, float* step_kernel_ms);
+eh_status eh_set_profiling(eh_ctx* ctx, int32_t on);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EASYHYBRID_CUDA_H */
