@@ -1,0 +1,279 @@
+#!/usr/bin/env python
+"""bench.py -- training samples/s of the fused hybrid step (fwd + bwd + optimiser).
+
+Workload (BASELINE.json configs[2], "C3"): RbQ10, MLP [2 -> 16 -> 16 -> 1] tanh,
+scale_nn_outputs, global Q10, mse, Adam(0.01), N = 2^24 synthetic Q10-shaped samples resident
+in HBM, batch 65536.  A "step" is one optimiser step on one batch.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+value      : samples/s, device-timed (CUDA events on the launching stream inside the library),
+             data + index stream already resident in HBM.
+e2e        : same metric through the C ABI with HOST batches: every step copies that batch
+             (X, forcing, target; pinned host memory) host->device and reads the loss back.
+roofline   : algorithmic bytes (16 B/sample) of one fused-step launch / its mean duration
+             (per-launch CUDA events in profiling mode) vs the measured HBM peak.
+cpu_baseline: the oracle (CPU restatement of the reference algorithm; the reference itself is
+             Julia and cannot run in this image) on all host cores, bounded sample.
+With --impl reference the same CPU implementation is what is timed.
+Multi-GPU (torchrun, one rank per GPU): weak scaling, every rank owns its own 2^24-sample shard
+and trains on per-GPU batches of 65536; gradients are combined once per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B = 65536
+N_PER_GPU = 1 << 24
+BYTES_PER_SAMPLE = 16           # 4 (P + F + T) = 4 * (2 + 1 + 1), SURVEY.md section 8(d)
+FMA_PER_SAMPLE = 880            # fwd + bwd of [2,16,16,1], SURVEY.md section 7.3
+
+
+def synth(n, seed):
+    rng = np.random.default_rng(seed)
+    ta = (10 + 10 * rng.standard_normal(n, dtype=np.float32)).astype(np.float32)
+    sw = np.abs(50 + 20 * rng.standard_normal(n, dtype=np.float32)).astype(np.float32)
+    dsw = np.empty_like(sw)
+    dsw[0] = 0
+    dsw[1:] = sw[1:] - sw[:-1]
+    rb = 3.0 + 0.02 * (sw - sw.mean())
+    reco = (rb * np.exp2(0.1 * (ta - 15.0)) + 0.1 * rng.standard_normal(n, dtype=np.float32)).astype(np.float32)
+    return (np.ascontiguousarray(np.stack([sw, dsw], 1)), {"ta": ta}), {"reco": reco}
+
+
+def make_model(eh):
+    return eh.constructHybridModel(["sw_pot", "dsw_pot"], ["ta"], ["reco"], eh.RbQ10,
+                                   dict(rb=(3.0, 0.0, 13.0), Q10=(2.0, 1.0, 4.0)), ["rb"], ["Q10"],
+                                   hidden_layers=[16, 16], activation="tanh", scale_nn_outputs=True)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for (t, line) in self.rows:
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                if t0 - 0.02 <= t <= t1 + 0.02:
+                    sm.append(float(p[0]))
+                smax = float(p[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[3:7]):
+                if v.lower().startswith("active") and t0 - 0.02 <= t <= t1 + 0.02:
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_baseline(eh, model, seconds=12.0, max_steps=120):
+    """oracle on all host cores, bounded sample of the same workload (batch 65536 out of 2^22 samples)"""
+    from oracle import oracle as orc
+    n = 1 << 22
+    xf, y = synth(n, 1234)
+    o = orc.Oracle(model, opt=eh.Adam(0.01))
+    flat = model.initialparameters(np.random.default_rng(0))
+    rng = np.random.default_rng(1)
+    threads = orc.max_threads()
+    o.train_steps(flat, xf, y, rng.permutation(n)[: 2 * B], B, nthreads=threads)  # warm-up
+    steps, t0 = 0, time.perf_counter()
+    while steps < max_steps and time.perf_counter() - t0 < seconds:
+        k = 4
+        o.train_steps(flat, xf, y, rng.permutation(n)[: k * B], B, nthreads=threads)
+        steps += k
+    dt = time.perf_counter() - t0
+    return {"value": steps * B / dt, "unit": "samples/s", "cores": threads, "kind": "port",
+            "sample": f"{steps} steps of batch {B} drawn from 2^22 synthetic samples, {dt:.1f} s, "
+                      "C oracle (CPU restatement of the reference algorithm; Julia reference not runnable here)"}, steps, dt
+
+
+def run_reference(args):
+    import easyhybrid_b200 as eh
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    model = make_model(eh)
+    cb, steps, dt = cpu_baseline(eh, model, seconds=max(5.0, min(60.0, 0.5 * (args.steps + args.warmup))),
+                                 max_steps=max(8, args.steps))
+    line = {"impl": "reference", "metric": "training samples/sec (fwd+bwd+Adam)", "value": cb["value"],
+            "unit": "samples/s", "n_gpus": args.gpus, "steps": steps, "warmup": 2, "ms_per_step": 1e3 * dt / steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C3: RbQ10 [2-16-16-1] tanh, mse, Adam(0.01), batch 65536 (CPU: bounded sample of 2^22)"},
+            "cpu_baseline": cb, "gpu_launches": 0,
+            "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4096)
+    ap.add_argument("--warmup", type=int, default=256)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--n", type=int, default=N_PER_GPU)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_
+        torch.cuda.set_device(local)
+        dist_.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist = dist_
+
+    import easyhybrid_b200 as eh
+    W = max(args.warmup, 3)
+    K = args.steps
+    model = make_model(eh)
+    n = args.n
+    xf, y = synth(n, 42 + rank)
+    sess = eh.FusedSession(model, opt=eh.Adam(0.01), device=local)
+    sess.upload(0, xf, y)
+    flat = model.initialparameters(np.random.default_rng(0))
+    sess.set_params(flat)
+    if world > 1:
+        sess.comm_init(rank, world, dist)
+    perm = np.random.default_rng(7 + rank).permutation(n)
+    sess.set_perm(perm)
+    nb = n // B
+
+    def barrier():
+        if dist is not None:
+            import torch
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value") ----
+    sess.run_steps(B, 0, W)
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.1)
+    barrier()
+    t0 = time.perf_counter()
+    losses = sess.run_steps(B, W, K)
+    t1 = time.perf_counter()
+    barrier()
+    clocks = sampler.stop(t0, t1)
+    dev_ms, launches, _ = sess.last_timing()
+    if dist is not None:
+        import torch
+        t = torch.tensor([dev_ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms = float(t.item())
+    value = world * K * B / (dev_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (K1, the fused step): per-launch CUDA events ----
+    sess.set_profiling(True)
+    kp = min(K, 256)
+    sess.run_steps(B, 0, 8)
+    sess.run_steps(B, 8, kp)
+    _, _, k1_ms = sess.last_timing()
+    sess.set_profiling(False)
+    k1_us = 1e3 * k1_ms / kp
+    peak, peak_src = measured_peaks()
+    achieved = B * BYTES_PER_SAMPLE / (k1_us * 1e-6) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "kernel": "k_step (fused fwd+process+loss+bwd)",
+                "kernel_us": k1_us,
+                "binding_roof": {"name": "fp32 FMA issue (FFMA2)", "fma_per_sample": FMA_PER_SAMPLE,
+                                 "achieved_tfma_s": B * FMA_PER_SAMPLE / (k1_us * 1e-6) / 1e12,
+                                 "peak_tfma_s": 148 * 128 * 1.965e9 / 1e12}}
+
+    # ---- end to end through the C ABI with host batches ----
+    e2e = None
+    if True:
+        pool = 16
+        hb = []
+        for i in range(pool):
+            sl = slice(i * B, (i + 1) * B)
+            hb.append((sess.pinned(xf[0][sl]), [sess.pinned(xf[1]["ta"][sl])], [sess.pinned(y["reco"][sl])]))
+        ke = min(K, 2048)
+        el = sess.pinned(np.zeros(ke + 8, dtype=np.float32))
+        for i in range(8):
+            sess.step_host_async(hb[i % pool], el, i)
+        sess.sync()
+        barrier()
+        te0 = time.perf_counter()
+        for i in range(ke):
+            sess.step_host_async(hb[i % pool], el, i)
+        sess.sync()
+        te1 = time.perf_counter()
+        barrier()
+        dt = te1 - te0
+        if dist is not None:
+            import torch
+            t = torch.tensor([dt], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": world * ke * B / dt, "unit": "samples/s", "h2d_bytes_per_step": B * BYTES_PER_SAMPLE,
+               "d2h_bytes_per_step": 4, "steps": ke, "api": "eh_step_host_async + eh_sync (pinned host batches)"}
+
+    if rank == 0:
+        line = {"metric": "training samples/sec (fwd+bwd+Adam)", "value": value, "unit": "samples/s", "n_gpus": world,
+                "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "C3: RbQ10 [2-16-16-1] tanh, scale_nn_outputs, mse, Adam(0.01), "
+                                       f"N=2^{int(np.log2(n))} per GPU resident, batch {B} per GPU",
+                           "l2": "inputs larger than L2 (268 MB of records gathered through a random permutation)",
+                           "parallelism": f"dp{world}"},
+                "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+                "final_loss": float(losses[-1])}
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(eh, model)[0]
+        print(json.dumps(line))
+    sess.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

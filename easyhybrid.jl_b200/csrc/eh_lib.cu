@@ -107,6 +107,14 @@ struct eh_ctx {
     int64_t last_launches = 0;
     int profiling = 0;
     std::vector<cudaEvent_t> prof_ev;
+    // epoch graph
+    cudaGraphExec_t gexec = nullptr;
+    int64_t g_n = 0, g_B = 0;
+    int g_pdl = 0;
+    bool g_has_pdl = false;
+    const int* g_idx = nullptr;
+    const float* g_bscal = nullptr;
+    const float* g_loss = nullptr;
     // dp
     int rank = 0, world = 1;
     void* nccl_lib = nullptr;
@@ -372,59 +380,123 @@ eh_status prepare_batch_rows(eh_ctx* c, int64_t n, int64_t B)
     return EH_OK;
 }
 
-// the step loop: batches [first, first+nsteps) of the resident index stream
-eh_status run_steps(eh_ctx* c, int64_t n, int64_t B, int64_t first, int64_t nsteps, float* losses, int apply,
-                    float* grad_out_host)
+// enqueue the K1/K2 launches of batches [b0, b1) of the resident index stream; the loss of
+// batch b goes to loss_base[b - b0]
+eh_status enqueue_steps(eh_ctx* c, int64_t n, int64_t B, int64_t b0, int64_t b1, float* loss_base, int apply,
+                        bool want_grad, bool pdl, bool profile, int64_t prof_off)
 {
     const Split& sp = c->split[EH_SPLIT_TRAIN];
-    if (!sp.rec) return fail(c, EH_EINVAL, "train split not uploaded");
-    int64_t nb = (n + B - 1) / B;
-    if (first < 0 || nsteps < 0 || first + nsteps > nb) return fail(c, EH_EINVAL, "step range out of bounds");
-    eh_status s = ensure_loss_cap(c, (size_t)nsteps);
-    if (s != EH_OK) return s;
-    const bool pdl = !(c->flags & EH_FLAG_NO_PDL) && !c->profiling;
     StepArgs a;
     fill_step_args(c, a);
     a.rec = reinterpret_cast<const float4*>(sp.rec);
     UpdateArgs u;
     fill_update_args(c, u);
     u.apply = apply;
-    u.grad_out = grad_out_host ? c->d_grad : nullptr;
-    if (c->profiling) {
+    u.grad_out = want_grad ? c->d_grad : nullptr;
+    for (int64_t b = b0; b < b1; b++) {
+        int64_t Bk = std::min<int64_t>(B, n - b * B);
+        Geom g = step_geometry(c, Bk);
+        a.idx = c->d_idx + b * B;
+        a.B = (int)Bk;
+        a.bscal = c->d_bscal + (size_t)b * BS_STRIDE;
+        if (profile) CK(cudaEventRecord(c->prof_ev[2 * (prof_off + b - b0)], c->stream));
+        CK(c->var->launch_step(a, g.grid, g.nwarps, g.smem, c->stream, pdl));
+        if (profile) CK(cudaEventRecord(c->prof_ev[2 * (prof_off + b - b0) + 1], c->stream));
+        u.G = g.grid;
+        u.bscal = a.bscal;
+        u.loss_out = loss_base + (b - b0);
+        if (c->world > 1) return fail(c, EH_EUNSUPPORTED, "data-parallel step not wired in this build");
+        CK(launch_update(u, c->stream, pdl));
+    }
+    return EH_OK;
+}
+
+void drop_graph(eh_ctx* c)
+{
+    if (c->gexec) cudaGraphExecDestroy(c->gexec);
+    c->gexec = nullptr;
+    c->g_n = c->g_B = 0;
+}
+
+// One whole pass over the resident permutation as a CUDA graph (2 kernel nodes per batch, chained
+// with programmatic-dependent-launch edges): the per-step CPU launch cost leaves the critical path.
+eh_status ensure_pass_graph(eh_ctx* c, int64_t n, int64_t B, bool pdl)
+{
+    if (c->gexec && c->g_n == n && c->g_B == B && c->g_pdl == (int)pdl && c->g_idx == c->d_idx &&
+        c->g_bscal == c->d_bscal && c->g_loss == c->d_loss)
+        return EH_OK;
+    drop_graph(c);
+    const int64_t nb = (n + B - 1) / B;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        bool use_pdl = pdl && attempt == 0;
+        cudaGraph_t graph = nullptr;
+        CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        eh_status s = enqueue_steps(c, n, B, 0, nb, c->d_loss, 1, false, use_pdl, false, 0);
+        cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+        if (s == EH_OK && e == cudaSuccess) e = cudaGraphInstantiate(&c->gexec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (s == EH_OK && e == cudaSuccess) {
+            c->g_n = n; c->g_B = B; c->g_pdl = (int)pdl; c->g_idx = c->d_idx; c->g_bscal = c->d_bscal; c->g_loss = c->d_loss;
+            c->g_has_pdl = use_pdl;
+            return EH_OK;
+        }
+        cudaGetLastError();  // clear, retry without PDL edges
+        c->gexec = nullptr;
+        if (attempt == 1) return fail(c, EH_ECUDA, "CUDA graph capture of the epoch failed: %s", cudaGetErrorString(e));
+    }
+    return EH_OK;
+}
+
+// the step loop: steps [first, first+nsteps) of the resident index stream; step s trains on batch
+// s mod nb (steps beyond one pass start another pass over the same permutation)
+eh_status run_steps(eh_ctx* c, int64_t n, int64_t B, int64_t first, int64_t nsteps, float* losses, int apply,
+                    float* grad_out_host)
+{
+    const Split& sp = c->split[EH_SPLIT_TRAIN];
+    if (!sp.rec) return fail(c, EH_EINVAL, "train split not uploaded");
+    const int64_t nb = (n + B - 1) / B;
+    if (first < 0 || nsteps < 0) return fail(c, EH_EINVAL, "step range out of bounds");
+    eh_status s = ensure_loss_cap(c, (size_t)std::max<int64_t>(nsteps, nb));
+    if (s != EH_OK) return s;
+    const bool profile = c->profiling != 0;
+    const bool pdl = !(c->flags & EH_FLAG_NO_PDL) && !profile;
+    const bool use_graph = !(c->flags & EH_FLAG_NO_GRAPH) && !profile && apply && !grad_out_host && nsteps >= nb && nb >= 4;
+    if (profile) {
         while ((int64_t)c->prof_ev.size() < 2 * nsteps) {
             cudaEvent_t e;
             CK(cudaEventCreate(&e));
             c->prof_ev.push_back(e);
         }
     }
+    if (use_graph) {
+        s = ensure_pass_graph(c, n, B, pdl);
+        if (s != EH_OK) return s;
+    }
     CK(cudaEventRecord(c->ev0, c->stream));
-    int64_t launches = 0;
-    for (int64_t k = 0; k < nsteps; k++) {
-        int64_t b = first + k;
-        int64_t Bk = std::min<int64_t>(B, n - b * B);
-        Geom g = step_geometry(c, Bk);
-        a.idx = c->d_idx + b * B;
-        a.B = (int)Bk;
-        a.bscal = c->d_bscal + (size_t)b * BS_STRIDE;
-        if (c->profiling) CK(cudaEventRecord(c->prof_ev[2 * k], c->stream));
-        CK(c->var->launch_step(a, g.grid, g.nwarps, g.smem, c->stream, pdl));
-        if (c->profiling) CK(cudaEventRecord(c->prof_ev[2 * k + 1], c->stream));
-        u.G = g.grid;
-        u.bscal = a.bscal;
-        u.loss_out = c->d_loss + k;
-        if (c->world > 1) return fail(c, EH_EUNSUPPORTED, "data-parallel step not wired in this build");
-        CK(launch_update(u, c->stream, pdl));
-        launches += 2;
+    int64_t done = 0, launches = 0;
+    while (done < nsteps) {
+        int64_t b0 = (first + done) % nb;
+        int64_t cnt = std::min<int64_t>(nb - b0, nsteps - done);
+        if (use_graph && b0 == 0 && cnt == nb) {
+            CK(cudaGraphLaunch(c->gexec, c->stream));
+            CK(cudaMemcpyAsync(c->h_loss + done, c->d_loss, (size_t)nb * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        } else {
+            // direct launches write their losses behind the graph's slots
+            s = enqueue_steps(c, n, B, b0, b0 + cnt, c->d_loss, apply, grad_out_host != nullptr, pdl, profile, done);
+            if (s != EH_OK) return s;
+            CK(cudaMemcpyAsync(c->h_loss + done, c->d_loss, (size_t)cnt * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        }
+        launches += 2 * cnt;
+        done += cnt;
     }
     CK(cudaEventRecord(c->ev1, c->stream));
-    CK(cudaMemcpyAsync(c->h_loss, c->d_loss, (size_t)nsteps * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     if (grad_out_host)
         CK(cudaMemcpyAsync(grad_out_host, c->d_grad, (size_t)c->nflat * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
     c->last_launches = launches;
     c->last_step_ms = 0.f;
-    if (c->profiling) {
+    if (profile) {
         float tot = 0.f;
         for (int64_t k = 0; k < nsteps; k++) {
             float ms = 0.f;
@@ -436,14 +508,15 @@ eh_status run_steps(eh_ctx* c, int64_t n, int64_t B, int64_t first, int64_t nste
     if (losses) memcpy(losses, c->h_loss, (size_t)nsteps * sizeof(float));
     // Lux BatchNorm running statistics (momentum 0.1, unbiased variance), skipped batches excluded
     if (c->use_bn && apply) {
-        std::vector<float> bb((size_t)nsteps * 2 * c->var->P);
-        CK(cudaMemcpy(bb.data(), c->d_bn_batch + (size_t)first * 2 * c->var->P, bb.size() * sizeof(float),
-                      cudaMemcpyDeviceToHost));
+        const int P = c->var->P;
+        std::vector<float> bb((size_t)nb * 2 * P);
+        CK(cudaMemcpy(bb.data(), c->d_bn_batch, bb.size() * sizeof(float), cudaMemcpyDeviceToHost));
         for (int64_t k = 0; k < nsteps; k++) {
             if (std::isnan(c->h_loss[k])) continue;
-            int64_t Bk = std::min<int64_t>(B, n - (first + k) * B);
-            for (int i = 0; i < c->var->P; i++) {
-                float mu = bb[(size_t)k * 2 * c->var->P + 2 * i], var = bb[(size_t)k * 2 * c->var->P + 2 * i + 1];
+            int64_t b = (first + k) % nb;
+            int64_t Bk = std::min<int64_t>(B, n - b * B);
+            for (int i = 0; i < P; i++) {
+                float mu = bb[(size_t)b * 2 * P + 2 * i], var = bb[(size_t)b * 2 * P + 2 * i + 1];
                 float unb = Bk > 1 ? var * (float)Bk / (float)(Bk - 1) : var;
                 c->bn_mean[i] = 0.9f * c->bn_mean[i] + 0.1f * mu;
                 c->bn_var[i] = 0.9f * c->bn_var[i] + 0.1f * unb;
@@ -762,6 +835,7 @@ void eh_destroy(eh_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->gexec) cudaGraphExecDestroy(c->gexec);
     void* ptrs[] = {c->d_wsrc, c->d_pmap, c->d_pspan, c->d_theta, c->d_m, c->d_v, c->d_grad, c->d_ost, c->d_partial,
                     c->d_gvec, c->d_bscal, c->d_bn_batch, c->d_idx, c->d_idx64, c->d_err, c->d_loss, c->d_evalpart,
                     c->d_bn_test, c->split[0].rec, c->split[1].rec};
@@ -1113,6 +1187,23 @@ eh_status eh_comm_init(eh_ctx* c, int32_t rank, int32_t world, const void* id)
 {
     (void)rank; (void)world; (void)id;
     return fail(c, EH_EUNSUPPORTED, "data-parallel communicator not available in this build");
+}
+
+eh_status eh_host_alloc(void** out, size_t bytes)
+{
+    if (!out) return EH_EINVAL;
+    cudaError_t e = cudaMallocHost(out, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("cudaMallocHost: ") + cudaGetErrorString(e);
+        return e == cudaErrorMemoryAllocation ? EH_ENOMEM : EH_ECUDA;
+    }
+    return EH_OK;
+}
+
+eh_status eh_host_free(void* p)
+{
+    if (p && cudaFreeHost(p) != cudaSuccess) return EH_ECUDA;
+    return EH_OK;
 }
 
 eh_status eh_last_timing(eh_ctx* c, float* total_ms, int64_t* launches, float* step_kernel_ms)

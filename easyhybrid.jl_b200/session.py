@@ -48,6 +48,9 @@ class FusedSession:
         if getattr(self, "h", None):
             self.lib.eh_destroy(self.h)
             self.h = None
+            for p in getattr(self, "_pinned", []):
+                self.lib.eh_host_free(p)
+            self._pinned = []
 
     __del__ = close
 
@@ -138,6 +141,35 @@ class FusedSession:
         losses = np.empty(n_steps, dtype=np.float32)
         self._ck(self.lib.eh_run_steps(self.h, batchsize, first_step, n_steps, losses.ctypes.data_as(_fp)))
         return losses
+
+    # ---- streaming host batches (pinned memory, asynchronous) ----
+    def pinned(self, arr):
+        """copy ``arr`` into page-locked host memory owned by this session; returns a numpy view"""
+        arr = np.ascontiguousarray(arr)
+        p = C.c_void_p()
+        st = self.lib.eh_host_alloc(C.byref(p), arr.nbytes)
+        if st != _abi.EH_OK:
+            raise EasyHybridCudaError(st, "eh_host_alloc failed")
+        self._pinned = getattr(self, "_pinned", [])
+        self._pinned.append(p)
+        buf = (C.c_char * max(arr.nbytes, 1)).from_address(p.value)
+        view = np.frombuffer(buf, dtype=arr.dtype, count=arr.size).reshape(arr.shape)
+        view[...] = arr
+        return view
+
+    def step_host_async(self, batch, loss_array, slot):
+        """batch = (X [B,P], [forcing arrays], [target arrays]) -- ideally views from ``pinned``"""
+        X, forc, targ = batch
+        pf = (_fp * max(len(forc), 1))(*[a.ctypes.data_as(_fp) for a in forc])
+        pt = (_fp * max(len(targ), 1))(*[a.ctypes.data_as(_fp) for a in targ])
+        self._inflight = getattr(self, "_inflight", [])
+        self._inflight.append((pf, pt))
+        lp = C.cast(loss_array.ctypes.data + 4 * slot, _fp)
+        self._ck(self.lib.eh_step_host_async(self.h, X.shape[0], X.ctypes.data_as(_fp), pf, pt, lp))
+
+    def sync(self):
+        self._ck(self.lib.eh_sync(self.h))
+        self._inflight = []
 
     # ---- evaluation ----
     def eval(self, split, want_yhat=True, want_params=False):

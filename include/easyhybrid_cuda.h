@@ -237,7 +237,9 @@ eh_status eh_sync(eh_ctx* ctx);
 eh_status eh_epoch(eh_ctx* ctx, const int64_t* perm1, int64_t n, int64_t B, float* losses);
 
 /* same, with the index stream already resident (set once with eh_set_perm):
- * runs steps [first_step, first_step + n_steps) of the stored permutation.   */
+ * runs steps [first_step, first_step + n_steps); step s trains on batch
+ * s mod ceil(n/B), i.e. steps past one pass start another pass over the same
+ * permutation.  Whole passes are replayed as one CUDA graph.                 */
 eh_status eh_set_perm(eh_ctx* ctx, const int64_t* perm1, int64_t n);
 eh_status eh_run_steps(eh_ctx* ctx, int64_t B, int64_t first_step, int64_t n_steps, float* losses);
 
@@ -257,6 +259,11 @@ eh_status eh_eval(eh_ctx* ctx, int32_t split, float* yhat, double* stats, float*
 #define EH_COMM_ID_BYTES 128
 eh_status eh_comm_id(void* id_out);
 eh_status eh_comm_init(eh_ctx* ctx, int32_t rank, int32_t world, const void* id);
+
+/* page-locked host buffers for callers that stream batches (eh_step_host_async copies
+ * straight out of them with cudaMemcpyAsync; pageable memory also works, but synchronously) */
+eh_status eh_host_alloc(void** out, size_t bytes);
+eh_status eh_host_free(void* p);
 
 /* timing hook: device time in ms of the last eh_epoch / eh_run_steps call,
  * measured with CUDA events on the stream the kernels ran on; kernel launches

@@ -1,0 +1,195 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle on the same seeded inputs.
+
+Tolerances (from BASELINE.json north_star): per-step loss and gradient within 1e-5 relative
+(gradient: max-norm relative), trained phi (Q10) within 1e-4 relative after a fixed number of steps.
+The float64 oracle is the truth; the float32 oracle shows what the reference's own Float32 path
+can achieve on the same inputs."""
+import numpy as np
+import pytest
+
+from conftest import expo_model, linear_model, make_expo, make_linear, make_synth, rbq10_model
+
+pytestmark = pytest.mark.gpu
+
+RTOL_LOSS = 1e-5
+RTOL_GRAD = 1e-5
+
+CASES = [
+    ("rbq10-tanh", lambda eh: rbq10_model(eh), lambda: make_synth(4000), "mse", "sum"),
+    ("rbq10-tanh-nan", lambda eh: rbq10_model(eh), lambda: make_synth(3000, nan_frac=0.05), "mse", "sum"),
+    ("rbq10-swish", lambda eh: rbq10_model(eh, activation="swish"), lambda: make_synth(2000), "mse", "sum"),
+    ("rbq10-sigmoid-rmse", lambda eh: rbq10_model(eh, activation="sigmoid"), lambda: make_synth(2000), "rmse", "sum"),
+    ("rbq10-noscale-mae", lambda eh: rbq10_model(eh, scale=False), lambda: make_synth(2000), "mae", "sum"),
+    ("rbq10-32", lambda eh: rbq10_model(eh, hidden=(32, 32)), lambda: make_synth(2000), "mse", "sum"),
+    ("rbq10-bn", lambda eh: rbq10_model(eh, bn=True), lambda: make_synth(2000), "mse", "sum"),
+    ("expo-nse", lambda eh: expo_model(eh), lambda: make_expo(500), "nseLoss", "sum"),
+    ("expo-bn-nse", lambda eh: expo_model(eh, bn=True), lambda: make_expo(500), "nseLoss", "sum"),
+    ("linear-relu", lambda eh: linear_model(eh), lambda: make_linear(1000), "mse", "sum"),
+    ("linear2-mean", lambda eh: linear_model(eh, two=True, activation="tanh"), lambda: make_linear(1000, two=True), "mse", "mean"),
+    ("linear2-pertarget", lambda eh: linear_model(eh, two=True, activation="tanh"), lambda: make_linear(1000, two=True), "PT", "sum"),
+]
+
+
+def _setup(eh, orc, mk, mkdata, loss, agg, opt=None, seed=7):
+    model = mk(eh)
+    if loss == "PT":
+        loss = eh.PerTarget("nseLoss", "mse")
+    xf, y = eh.prepare_data(model, mkdata())
+    rng = np.random.default_rng(seed)
+    flat = model.initialparameters(rng)
+    flat += (0.05 * rng.standard_normal(flat.size)).astype(np.float32)
+    sess = eh.FusedSession(model, training_loss=loss, agg=agg, opt=opt)
+    sess.upload(0, xf, y)
+    sess.set_params(flat)
+    o = orc.Oracle(model, training_loss=loss, agg=agg, opt=opt)
+    return model, xf, y, flat, sess, o, rng
+
+
+@pytest.mark.parametrize("name,mk,mkdata,loss,agg", CASES, ids=[c[0] for c in CASES])
+def test_loss_and_gradient(eh, orc, name, mk, mkdata, loss, agg):
+    model, xf, y, flat, sess, o, rng = _setup(eh, orc, mk, mkdata, loss, agg)
+    n = xf[0].shape[0]
+    for B in (n, 517, 64, 12, 1):  # full, ragged, one chunk, the reference's test batch size, single sample
+        if B == 1 and loss in ("nseLoss",) or (B == 1 and not isinstance(loss, str)):
+            continue  # SS_tot of one sample is 0: the reference yields NaN/Inf there as well
+        idx = rng.permutation(n)[:B]
+        if np.isnan(np.stack([y[t][idx] for t in model.targets])).all():
+            continue
+        L, g = sess.loss_grad(idx)
+        L64, g64 = o.loss_grad(flat, xf, y, idx, precision=64)
+        L32, g32 = o.loss_grad(flat, xf, y, idx, precision=32)
+        scale = np.abs(g64).max()
+        assert abs(L - L64) <= RTOL_LOSS * abs(L64), (name, B, L, L64)
+        err = np.abs(g - g64).max() / scale
+        err32 = np.abs(g32 - g64).max() / scale
+        assert err <= RTOL_GRAD, (name, B, err, err32)
+    sess.close()
+
+
+def test_training_trajectory_rbq10(eh, orc):
+    """50 Adam steps, batch 512 (README.md:200), per-step loss and final Q10"""
+    model, xf, y, flat, sess, o, rng = _setup(eh, orc, lambda e: rbq10_model(e), lambda: make_synth(20000), "mse", "sum",
+                                              opt=None)
+    perm = rng.permutation(20000)[: 50 * 512]
+    got = sess.epoch(perm, 512)
+    ref = flat.copy()
+    want = o.train_steps(ref, xf, y, perm, 512)
+    np.testing.assert_allclose(got, want, rtol=2e-4)
+    assert abs(got[0] - want[0]) <= 1e-5 * abs(want[0])
+    ps = sess.get_params()
+    q10 = lambda p: 1.0 + 3.0 / (1.0 + np.exp(-float(p[-1])))
+    assert abs(q10(ps) - q10(ref)) <= 1e-4 * q10(ref)
+    assert np.abs(ps - ref).max() <= 2e-4 * max(1.0, np.abs(ref).max())
+    m, v, t = sess.get_opt_state()
+    assert t == 50 and np.allclose(m, o.m, atol=1e-4 * np.abs(o.m).max()) and np.allclose(v, o.v, atol=1e-4 * np.abs(o.v).max())
+    sess.close()
+
+
+@pytest.mark.parametrize("optname", ["AdamW", "RMSProp", "Descent"])
+def test_other_optimisers(eh, orc, optname):
+    opt = {"AdamW": eh.AdamW(0.01, (0.9, 0.999), 0.01), "RMSProp": eh.RMSProp(0.001), "Descent": eh.Descent(0.001)}[optname]
+    model, xf, y, flat, sess, o, rng = _setup(eh, orc, lambda e: expo_model(e), lambda: make_expo(500), "nseLoss", "sum", opt=opt)
+    perm = rng.permutation(500)
+    got = sess.epoch(perm, 64)          # 8 steps, last one partial (52 samples)
+    ref = flat.copy()
+    want = o.train_steps(ref, xf, y, perm, 64)
+    assert got.shape == (8,)
+    np.testing.assert_allclose(got, want, rtol=1e-4)
+    np.testing.assert_allclose(sess.get_params(), ref, atol=1e-4 * max(1.0, np.abs(ref).max()))
+    sess.close()
+
+
+def test_all_masked_batch_is_skipped(eh, orc):
+    """src/training/epoch.jl:17-19"""
+    table = make_synth(256)
+    table["reco"][:64] = np.nan
+    model = rbq10_model(eh)
+    xf, y = (np.stack([table["sw_pot"], table["dsw_pot"]], 1), {"ta": table["ta"]}), {"reco": table["reco"]}
+    flat = model.initialparameters(np.random.default_rng(2))
+    sess = eh.FusedSession(model)
+    sess.upload(0, xf, y)
+    sess.set_params(flat)
+    o = orc.Oracle(model)
+    got = sess.epoch(np.arange(256), 64)
+    ref = flat.copy()
+    want = o.train_steps(ref, xf, y, np.arange(256), 64)
+    assert np.isnan(got[0]) and np.isnan(want[0])
+    np.testing.assert_allclose(got[1:], want[1:], rtol=1e-4)
+    assert sess.get_opt_state()[2] == 3
+    np.testing.assert_allclose(sess.get_params(), ref, atol=1e-4)
+    sess.close()
+
+
+def test_step_host_equals_step_on_indices(eh, orc):
+    """collect_dim_data |> gdev path == resident-dataset path, bit for bit"""
+    model, xf, y, flat, sess, o, rng = _setup(eh, orc, lambda e: rbq10_model(e), lambda: make_synth(3000, nan_frac=0.03), "mse", "sum")
+    idx = rng.permutation(3000)[:700]
+    L1, g1 = sess.step(idx, want_grad=True)
+    p1 = sess.get_params()
+    sess.set_params(flat)
+    sess.set_opt_state(None, None, 0)
+    xb = (xf[0][idx], {"ta": xf[1]["ta"][idx]})
+    L2 = sess.step_host(xb, {"reco": y["reco"][idx]})
+    p2 = sess.get_params()
+    assert L1 == L2 and np.array_equal(p1, p2)
+    sess.close()
+
+
+def test_eval_matches_oracle_forward_and_metrics(eh, orc):
+    model, xf, y, flat, sess, o, rng = _setup(eh, orc, lambda e: rbq10_model(e), lambda: make_synth(5001, nan_frac=0.1), "mse", "sum")
+    sess.upload(1, xf, y)
+    yhat, stats, par = sess.eval(1, want_yhat=True, want_params=True)
+    want, wpar = o.forward(flat, xf, precision=64, want_params=True)
+    np.testing.assert_allclose(yhat, want, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(par[0], wpar[0], rtol=1e-5)          # rb, the NEURAL parameter
+    mask = ~np.isnan(y["reco"])
+    got = eh.metrics_from_stats(stats[0])
+    for kind in eh.LOSS_TYPES:
+        assert got[kind] == pytest.approx(orc.loss_fn(want[0], y["reco"], mask, kind), rel=2e-5, abs=1e-7), kind
+    sess.close()
+
+
+def test_determinism_and_additivity_at_benchmark_batch(eh):
+    """size-independent properties at the BASELINE batch size (65536): the same step twice is
+    bit-identical (atomic-free fixed-order reduction), and n*grad is additive over a split batch"""
+    model = rbq10_model(eh)
+    t = make_synth(1 << 18)
+    xf, y = eh.prepare_data(model, t)
+    flat = model.initialparameters(np.random.default_rng(0))
+    sess = eh.FusedSession(model)
+    sess.upload(0, xf, y)
+    sess.set_params(flat)
+    idx = np.random.default_rng(1).permutation(1 << 18)[:65536]
+    L, g = sess.loss_grad(idx)
+    L2, g2 = sess.loss_grad(idx)
+    assert L == L2 and np.array_equal(g, g2)
+    La, ga = sess.loss_grad(idx[:30000])
+    Lb, gb = sess.loss_grad(idx[30000:])
+    comb = (30000 * ga.astype(np.float64) + 35536 * gb.astype(np.float64)) / 65536
+    assert np.abs(comb - g).max() <= 2e-6 * np.abs(g).max()
+    assert abs((30000 * La + 35536 * Lb) / 65536 - L) <= 2e-6 * L
+    sess.close()
+
+
+def test_unsupported_models_fail_loudly(eh):
+    from easyhybrid_b200 import _abi
+
+    def other(*, ta, Q10, rb):
+        return {"reco": rb * np.exp(Q10) + ta}
+    m = eh.constructHybridModel(["sw_pot"], ["ta"], ["reco"], other, dict(Q10=(2, 1, 4), rb=(3, 0, 13)), ["rb"], ["Q10"])
+    with pytest.raises(eh.EasyHybridCudaError) as ei:
+        eh.FusedSession(m)
+    assert ei.value.status == _abi.EH_EUNSUPPORTED
+    with pytest.raises(eh.EasyHybridCudaError) as ei:
+        eh.FusedSession(rbq10_model(eh, hidden=(512, 512, 512)))
+    assert ei.value.status == _abi.EH_EUNSUPPORTED
+
+
+def test_train_api_learns_q10(eh):
+    """train(model, data; ...) end to end: Q10 recovered from the synthetic table (true value 2)"""
+    model = rbq10_model(eh, activation="tanh", bn=True)
+    out = eh.train(model, make_synth(8192), nepochs=30, batchsize=256, opt=eh.Adam(0.01), loss_types=["mse", "r2", "nse"])
+    assert out is not None and len(out.train_history) == 31
+    assert out.val_history[-1]["mse"]["sum"] < out.val_history[0]["mse"]["sum"] * 0.05
+    assert abs(out.train_diffs["Q10"] - 2.0) < 0.15
+    assert out.ps.shape == (model.num_params(),) and out.best_epoch > 0
