@@ -155,6 +155,8 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--n", type=int, default=N_PER_GPU)
+    ap.add_argument("--flags", type=int, default=0, help="EH_FLAG_* bits (1 = no CUDA graph, 2 = no PDL)")
+    ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -176,7 +178,7 @@ def main():
     model = make_model(eh)
     n = args.n
     xf, y = synth(n, 42 + rank)
-    sess = eh.FusedSession(model, opt=eh.Adam(0.01), device=local)
+    sess = eh.FusedSession(model, opt=eh.Adam(0.01), device=local, flags=args.flags)
     sess.upload(0, xf, y)
     flat = model.initialparameters(np.random.default_rng(0))
     sess.set_params(flat)
@@ -230,7 +232,7 @@ def main():
 
     # ---- end to end through the C ABI with host batches ----
     e2e = None
-    if True:
+    if not args.no_e2e:
         pool = 16
         hb = []
         for i in range(pool):
