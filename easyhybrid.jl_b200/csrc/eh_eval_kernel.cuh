@@ -15,7 +15,8 @@ struct EvalArgs {
     const float4* rec;
     long long rec_base;
     long long N;
-    const float* theta;
+    const float* pblock;
+    int nflat;
     const int* wsrc;
     const float* bscal;    // test-mode BN row (running mean / rstd) or NULL
     int use_bn;
@@ -30,7 +31,7 @@ struct EvalArgs {
 template <class C>
 __global__ void __launch_bounds__(256) k_eval(const EvalArgs a)
 {
-    constexpr int P = C::P, H = C::H, NOUT = C::NOUT, T = C::T, F = C::F, NPS = C::NPS;
+    constexpr int P = C::P, NOUT = C::NOUT, T = C::T, F = C::F, NPS = C::NPS, HP = C::H / 2;
     using PM = typename C::PM;
     extern __shared__ float4 smem4[];
     float* sW = reinterpret_cast<float*>(smem4);
@@ -38,12 +39,15 @@ __global__ void __launch_bounds__(256) k_eval(const EvalArgs a)
     __shared__ double shd[8][MAXT * EVAL_NSTAT];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 
-    load_weights_and_scalars<C>(a.theta, a.wsrc, a.slot, a.bscal, a.use_bn, sW, sS);
-    StepCtx<C> cx;
+    load_weights_and_scalars<C>(a.pblock, a.nflat, a.wsrc, a.bscal, a.use_bn, sW, sS);
+    __syncthreads();
+    PmCtx cx;
+    cx.pms = sS + SS_PMS;
+    cx.c = a.pmc;
+    cx.uniform_mask = 0;
 #pragma unroll
-    for (int i = 0; i < 8; i++) cx.pms.s[i] = sS[16 + i];
-#pragma unroll
-    for (int i = 0; i < MAXPS; i++) cx.slot_uniform[i] = i < NPS ? (a.slot[i].role != ROLE_NEURAL) : true;
+    for (int s = 0; s < MAXPS; s++)
+        if (s >= NPS || a.slot[s].role != ROLE_NEURAL) cx.uniform_mask |= 1u << s;
 
     double st[T][EVAL_NSTAT];
 #pragma unroll
@@ -53,64 +57,42 @@ __global__ void __launch_bounds__(256) k_eval(const EvalArgs a)
 
     const long long nchunks = (a.N + CHUNK - 1) / CHUNK;
     for (long long chunk = (long long)blockIdx.x * nwarps + warp; chunk < nchunks; chunk += (long long)gridDim.x * nwarps) {
-        long long s0 = chunk * CHUNK + 2 * lane, s1 = s0 + 1;
-        bool v0 = s0 < a.N, v1 = s1 < a.N;
-        float4 r0[C::R4 / 4], r1[C::R4 / 4];
+        const long long s0 = chunk * CHUNK + lane;
+        const bool v0 = s0 < a.N;
+        float4 r[C::R4 / 4];
 #pragma unroll
-        for (int q = 0; q < C::R4 / 4; q++) {
-            r0[q] = v0 ? __ldg(a.rec + (a.rec_base + s0) * (C::R4 / 4) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-            r1[q] = v1 ? __ldg(a.rec + (a.rec_base + s1) * (C::R4 / 4) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        const float* p0 = reinterpret_cast<const float*>(r0);
-        const float* p1 = reinterpret_cast<const float*>(r1);
-        float2 x[P], f[F > 0 ? F : 1], y[T];
+        for (int q = 0; q < C::R4 / 4; q++)
+            r[q] = v0 ? __ldg(a.rec + (a.rec_base + s0) * (C::R4 / 4) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float* p0 = reinterpret_cast<const float*>(r);
+        float x[P], f[F > 0 ? F : 1], y[T];
 #pragma unroll
-        for (int k = 0; k < P; k++) x[k] = mul2s(sub2(f2(p0[k], p1[k]), f2s(sS[40 + 2 * k])), sS[40 + 2 * k + 1]);
+        for (int k = 0; k < P; k++) x[k] = (p0[k] - sS[SS_BN + 2 * k]) * sS[SS_BN + 2 * k + 1];
 #pragma unroll
-        for (int k = 0; k < F; k++) f[k] = f2(p0[P + k], p1[P + k]);
+        for (int k = 0; k < F; k++) f[k] = p0[P + k];
 #pragma unroll
-        for (int k = 0; k < T; k++) y[k] = f2(p0[P + F + k], p1[P + F + k]);
+        for (int k = 0; k < T; k++) y[k] = p0[P + F + k];
 
-        float2 h[H], zo[NOUT], pv[NPS], sg[NPS], yh[T], sv[4];
-        chain_forward<C, false>(sW, nullptr, lane, x, h, zo);
+        float2 hp[HP];
+        float zo[NOUT], pv[NPS], sg[NPS], yh[T], sv[4];
+        chain_forward<C, false>(sW, nullptr, lane, x, hp, zo);
         resolve_params<C>(a.slot, sS, zo, pv, sg);
-        PM::fwd(pv, f, a.pmc, cx, yh, sv);
+        PM::fwd(pv, f, cx, yh, sv);
 
 #pragma unroll
         for (int t = 0; t < T; t++) {
-            if (a.yhat) {
-                // two consecutive samples per lane -> one 8-byte store, fully coalesced per warp
-                float* dst = a.yhat + (size_t)t * a.N + s0;
-                if (v1 && ((((size_t)t * a.N) & 1) == 0)) *reinterpret_cast<float2*>(dst) = yh[t];
-                else {
-                    if (v0) dst[0] = yh[t].x;
-                    if (v1) dst[1] = yh[t].y;
-                }
-            }
-            const float sh = a.shift_y[t];
-#pragma unroll
-            for (int e = 0; e < 2; e++) {
-                bool v = e ? v1 : v0;
-                float yy = e ? y[t].y : y[t].x, hh = e ? yh[t].y : yh[t].x;
-                if (v && yy == yy) {
-                    double dy = (double)yy - sh, dh = (double)hh - sh, r = (double)hh - (double)yy;
-                    st[t][0] += 1.0; st[t][1] += dy; st[t][2] += dh;
-                    st[t][3] += dy * dy; st[t][4] += dh * dh; st[t][5] += dy * dh;
-                    st[t][6] += r * r; st[t][7] += fabs(r);
-                }
+            if (a.yhat && v0) a.yhat[(size_t)t * a.N + s0] = yh[t];   // consecutive lanes: coalesced
+            if (v0 && y[t] == y[t]) {
+                const double sh = a.shift_y[t];
+                double dy = (double)y[t] - sh, dh = (double)yh[t] - sh, rr = (double)yh[t] - (double)y[t];
+                st[t][0] += 1.0; st[t][1] += dy; st[t][2] += dh;
+                st[t][3] += dy * dy; st[t][4] += dh * dh; st[t][5] += dy * dh;
+                st[t][6] += rr * rr; st[t][7] += fabs(rr);
             }
         }
-        if (a.parout) {
+        if (a.parout && v0) {
 #pragma unroll
             for (int s = 0; s < NPS; s++)
-                if (a.slot[s].role == ROLE_NEURAL) {
-                    float* dst = a.parout + (size_t)s * a.N + s0;
-                    if (v1 && ((((size_t)s * a.N) & 1) == 0)) *reinterpret_cast<float2*>(dst) = pv[s];
-                    else {
-                        if (v0) dst[0] = pv[s].x;
-                        if (v1) dst[1] = pv[s].y;
-                    }
-                }
+                if (a.slot[s].role == ROLE_NEURAL) a.parout[(size_t)s * a.N + s0] = pv[s];
         }
     }
 #pragma unroll

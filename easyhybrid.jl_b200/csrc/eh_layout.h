@@ -24,7 +24,7 @@ enum : int { PM_RBQ10 = 0, PM_EXPO = 1, PM_LINEAR = 2, PM_LINEAR2 = 3, PM_PROGRA
 constexpr int MAXPS = 8;   // process-parameter slots
 constexpr int MAXT = 4;    // targets
 constexpr int MAXF = 8;    // forcings
-constexpr int CHUNK = 64;  // samples per warp pass (2 per lane)
+constexpr int CHUNK = 32;  // samples per warp pass (one per lane)
 constexpr int ROWSTRIDE = CHUNK + 4;  // floats per staging row (bank skew)
 
 EH_HD constexpr int rup4(int x) { return (x + 3) & ~3; }
@@ -70,6 +70,11 @@ struct ShapeDims {
     // per-CTA partial vector: nblocks*16 dW entries, then statistics
     EH_HD constexpr int npart_dw() const { return nblocks() * 16; }
 };
+
+// parameter block in device memory: [nflat theta/phi | MAXPS uniform slot values | MAXPS*4 derived
+// process-model scalars]; the tail is refreshed by whoever updates phi
+constexpr int PMS_PER_SLOT_L = 4;
+constexpr int PARAM_TAIL = MAXPS + MAXPS * PMS_PER_SLOT_L;
 
 // statistics appended after the dW blocks in a partial vector:
 //   [T] sum of r^2 (or |r| for mae targets), [MAXPS] sum of g*dy/dslot for GLOBAL slots

@@ -19,6 +19,7 @@
 #include "../../include/easyhybrid_cuda.h"
 #include "eh_variants.h"
 #include "eh_update_kernel.cuh"
+#include "eh_epoch_kernel.cuh"
 #include "eh_eval_kernel.cuh"
 
 using namespace eh;
@@ -77,6 +78,14 @@ struct eh_ctx {
     float* d_pspan = nullptr;
     float *d_theta = nullptr, *d_m = nullptr, *d_v = nullptr, *d_grad = nullptr;
     OptState* d_ost = nullptr;
+    // persistent epoch kernel
+    std::vector<int> h_inv, h_slot_of_flat;
+    int *d_inv = nullptr, *d_slot_of_flat = nullptr, *d_losskind = nullptr;
+    float *d_pbuf = nullptr, *d_pub = nullptr, *d_stats = nullptr;
+    unsigned* d_counter = nullptr;
+    size_t stats_cap = 0;
+    bool persist_ok = false;
+    int pm_id = 0;
     float *d_partial = nullptr, *d_gvec = nullptr;
     float* d_bscal = nullptr;
     size_t bscal_cap = 0;
@@ -210,9 +219,9 @@ struct Geom {
 Geom step_geometry(const eh_ctx* c, int64_t B)
 {
     const Variant* v = c->var;
-    size_t fixed = (size_t)(rup4(v->NW) + 64) * 4;
+    size_t fixed = (size_t)(rup4(v->NW) + SS_FLOATS) * 4;
     size_t stage = (size_t)v->stage_floats * 4;
-    int wmax = (int)std::min<size_t>(8, (c->smem_optin - fixed) / stage);
+    int wmax = (int)std::min<size_t>((size_t)v->max_warps, (c->smem_optin - fixed - 8192) / stage);
     if (wmax < 1) wmax = 1;
     int64_t nchunks = (B + CHUNK - 1) / CHUNK;
     Geom g;
@@ -233,7 +242,8 @@ Geom step_geometry(const eh_ctx* c, int64_t B)
 void fill_step_args(const eh_ctx* c, StepArgs& a)
 {
     memset(&a, 0, sizeof a);
-    a.theta = c->d_theta;
+    a.pblock = c->d_theta;
+    a.nflat = c->nflat;
     a.wsrc = c->d_wsrc;
     a.partial = c->d_partial;
     a.npart = c->var->NPART;
@@ -266,6 +276,21 @@ void fill_update_args(const eh_ctx* c, UpdateArgs& u)
     u.opt_kind = c->opt_kind;
     u.adamw_coupled = c->adamw_coupled;
     u.eta = c->eta; u.beta1 = c->beta1; u.beta2 = c->beta2; u.eps = c->eps; u.lambda = c->lambda;
+    u.slot_of_flat = c->d_slot_of_flat;
+    for (int s = 0; s < MAXPS; s++) u.slot[s] = c->slots[s];
+    u.pm_id = c->pm_id;
+}
+
+// refresh the tail of the parameter block (uniform slot values + derived scalars) from phi
+cudaError_t refresh_tail(const eh_ctx* c)
+{
+    TailArgs t;
+    memset(&t, 0, sizeof t);
+    t.pblock = c->d_theta; t.nflat = c->nflat; t.ntheta = c->ntheta; t.pm_id = c->pm_id;
+    t.slot_of_flat = c->d_slot_of_flat;
+    for (int s = 0; s < MAXPS; s++) t.slot[s] = c->slots[s];
+    k_param_tail<<<1, 64, 0, c->stream>>>(t);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_update(const UpdateArgs& u, cudaStream_t st, bool pdl)
@@ -447,6 +472,61 @@ eh_status ensure_pass_graph(eh_ctx* c, int64_t n, int64_t B, bool pdl)
     return EH_OK;
 }
 
+// Persistent path: all nsteps optimiser steps in ONE cooperative launch (eh_epoch_kernel.cuh).
+eh_status run_persistent(eh_ctx* c, int64_t n, int64_t B, int64_t first, int64_t nsteps, bool* used)
+{
+    *used = false;
+    const Variant* v = c->var;
+    const int64_t nb = (n + B - 1) / B;
+    Geom g = step_geometry(c, B);
+    const int npartp = rup4(v->NPART);
+    int SL = rup4((v->NPART + g.grid - 1) / g.grid);
+    size_t smem = g.smem + (size_t)5 * SL * sizeof(float);
+    if (smem > c->smem_optin) return EH_OK;  // does not fit: caller uses the two-kernel path
+    int per_sm = 0;
+    CK(v->epoch_max_grid(g.nwarps, smem, &per_sm));
+    if (per_sm < 1 || g.grid > per_sm * c->nsm) return EH_OK;
+    if ((size_t)nsteps > c->stats_cap) {
+        if (c->d_stats) cudaFree(c->d_stats);
+        c->d_stats = nullptr; c->stats_cap = 0;
+        CK(dalloc(&c->d_stats, (size_t)nsteps * MAXT));
+        c->stats_cap = (size_t)nsteps;
+    }
+    const size_t pb = ((size_t)c->nflat + PARAM_TAIL) * sizeof(float);
+    CK(cudaMemsetAsync(c->d_counter, 0, 4 * sizeof(unsigned), c->stream));
+    CK(cudaMemcpyAsync(c->d_pub, c->d_theta, pb, cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_pub + c->nflat + PARAM_TAIL, c->d_theta, pb, cudaMemcpyDeviceToDevice, c->stream));
+    EpochArgs a;
+    memset(&a, 0, sizeof a);
+    a.rec = reinterpret_cast<const float4*>(c->split[EH_SPLIT_TRAIN].rec);
+    a.idx = c->d_idx; a.n = n; a.B = (int)B; a.first_step = first; a.nsteps = (int)nsteps; a.nb = (int)nb;
+    a.pblock = c->d_theta; a.nflat = c->nflat; a.ntheta = c->ntheta;
+    a.m = c->d_m; a.v = c->d_v; a.ost = c->d_ost;
+    a.wsrc = c->d_wsrc; a.inv = c->d_inv; a.pspan = c->d_pspan; a.slot_of_flat = c->d_slot_of_flat;
+    a.bscal = c->d_bscal; a.pbuf = c->d_pbuf; a.pub = c->d_pub; a.counter = c->d_counter; a.stats_out = c->d_stats;
+    a.npartp = npartp; a.SL = SL; a.T = c->n_targ;
+    for (int t = 0; t < MAXT; t++) a.loss_kind[t] = c->loss_kind[t];
+    for (int s = 0; s < MAXPS; s++) a.slot[s] = c->slots[s];
+    for (int i = 0; i < 4; i++) a.pmc[i] = c->pmc[i];
+    a.use_bn = c->use_bn; a.pm_id = c->pm_id;
+    a.opt_kind = c->opt_kind; a.adamw_coupled = c->adamw_coupled;
+    a.eta = c->eta; a.beta1 = c->beta1; a.beta2 = c->beta2; a.eps = c->eps; a.lambda = c->lambda;
+    CK(cudaEventRecord(c->ev0, c->stream));
+    CK(v->launch_epoch(a, g.grid, g.nwarps, smem, c->stream));
+    CK(cudaEventRecord(c->ev1, c->stream));
+    k_losses_from_stats<<<(unsigned)((nsteps + 127) / 128), 128, 0, c->stream>>>(c->d_stats, c->d_bscal, first, (int)nb,
+                                                                                 (int)nsteps, c->n_targ, c->agg_mean,
+                                                                                 c->d_losskind, c->d_loss);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(c->h_loss, c->d_loss, (size_t)nsteps * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+    c->last_launches = 1;
+    c->last_step_ms = c->last_ms;
+    *used = true;
+    return EH_OK;
+}
+
 // the step loop: steps [first, first+nsteps) of the resident index stream; step s trains on batch
 // s mod nb (steps beyond one pass start another pass over the same permutation)
 eh_status run_steps(eh_ctx* c, int64_t n, int64_t B, int64_t first, int64_t nsteps, float* losses, int apply,
@@ -468,12 +548,18 @@ eh_status run_steps(eh_ctx* c, int64_t n, int64_t B, int64_t first, int64_t nste
             c->prof_ev.push_back(e);
         }
     }
-    if (use_graph) {
+    bool persisted = false;
+    if (c->persist_ok && !(c->flags & EH_FLAG_NO_PERSIST) && !profile && apply && !grad_out_host && nsteps >= 2 &&
+        nsteps < (1 << 30) && c->world == 1) {
+        s = run_persistent(c, n, B, first, nsteps, &persisted);
+        if (s != EH_OK) return s;
+    }
+    if (use_graph && !persisted) {
         s = ensure_pass_graph(c, n, B, pdl);
         if (s != EH_OK) return s;
     }
-    CK(cudaEventRecord(c->ev0, c->stream));
-    int64_t done = 0, launches = 0;
+    if (!persisted) CK(cudaEventRecord(c->ev0, c->stream));
+    int64_t done = persisted ? nsteps : 0, launches = 0;
     while (done < nsteps) {
         int64_t b0 = (first + done) % nb;
         int64_t cnt = std::min<int64_t>(nb - b0, nsteps - done);
@@ -489,13 +575,15 @@ eh_status run_steps(eh_ctx* c, int64_t n, int64_t B, int64_t first, int64_t nste
         launches += 2 * cnt;
         done += cnt;
     }
-    CK(cudaEventRecord(c->ev1, c->stream));
-    if (grad_out_host)
-        CK(cudaMemcpyAsync(grad_out_host, c->d_grad, (size_t)c->nflat * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
-    c->last_launches = launches;
-    c->last_step_ms = 0.f;
+    if (!persisted) {
+        CK(cudaEventRecord(c->ev1, c->stream));
+        if (grad_out_host)
+            CK(cudaMemcpyAsync(grad_out_host, c->d_grad, (size_t)c->nflat * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+        c->last_launches = launches;
+        c->last_step_ms = 0.f;
+    }
     if (profile) {
         float tot = 0.f;
         for (int64_t k = 0; k < nsteps; k++) {
@@ -644,6 +732,20 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
         c->h_pspan[off + g] = span;
     }
 
+    // inverse maps for the persistent kernel: partial index -> flat parameter, phi entry -> slot
+    c->h_inv.assign((size_t)v->NPART, -1);
+    c->h_slot_of_flat.assign((size_t)c->nflat, -1);
+    c->persist_ok = true;
+    for (int p = 0; p < c->nflat; p++) {
+        int q = c->h_pmap[p];
+        if (c->h_inv[q] >= 0) c->persist_ok = false;  // two parameters share a cell (unused global): two-kernel path only
+        c->h_inv[q] = p;
+    }
+    for (int g = 0; g < ng; g++)
+        for (int s = 0; s < v->NPS; s++)
+            if (c->slots[s].role == ROLE_GLOBAL && c->slots[s].idx == g) c->h_slot_of_flat[off + g] = s;
+    c->pm_id = d->process_model;
+
     // record columns: chain inputs, the form's forcing, targets
     c->ncols = 0;
     for (int k = 0; k < ch.n_in; k++) {
@@ -666,6 +768,7 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
         if (lk == EH_LOSS_RMSE) n_rmse++;
     }
     if (n_rmse && d->n_targ > 1) return fail(c, EH_EUNSUPPORTED, "rmse training loss with more than one target");
+    if (n_rmse) c->persist_ok = false;  // the rmse post-scale needs the reduced SSE before the update
     c->agg_mean = d->agg == EH_AGG_MEAN;
     c->opt_kind = d->opt_kind;
     if (c->opt_kind < 0 || c->opt_kind > 3) return fail(c, EH_EINVAL, "opt_kind=%d unknown", d->opt_kind);
@@ -800,18 +903,27 @@ eh_status eh_create(eh_ctx** out, const eh_model_desc* desc)
         CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
         CK(cudaEventCreate(&c->ev0));
         CK(cudaEventCreate(&c->ev1));
-        size_t fixed = (size_t)(rup4(v->NW) + 64) * 4;
+        size_t fixed = (size_t)(rup4(v->NW) + SS_FLOATS) * 4;
         size_t stage = (size_t)v->stage_floats * 4;
-        int wmax = (int)std::min<size_t>(8, (c->smem_optin - fixed) / stage);
+        int wmax = (int)std::min<size_t>((size_t)v->max_warps, (c->smem_optin - fixed - 8192) / stage);
         if (wmax < 1) return fail(c, EH_EUNSUPPORTED, "variant %s needs %zu B of shared memory per warp", v->name, stage);
-        CK(v->prepare(fixed + (size_t)wmax * stage, fixed));
+        CK(v->prepare(fixed + (size_t)wmax * stage + 8192, fixed));
         CK(dalloc(&c->d_wsrc, c->h_wsrc.size()));
         CK(dalloc(&c->d_pmap, c->h_pmap.size()));
         CK(dalloc(&c->d_pspan, c->h_pspan.size()));
         CK(cudaMemcpy(c->d_wsrc, c->h_wsrc.data(), c->h_wsrc.size() * sizeof(int), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(c->d_pmap, c->h_pmap.data(), c->h_pmap.size() * sizeof(int), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(c->d_pspan, c->h_pspan.data(), c->h_pspan.size() * sizeof(float), cudaMemcpyHostToDevice));
-        CK(dalloc(&c->d_theta, (size_t)c->nflat));
+        CK(dalloc(&c->d_theta, (size_t)c->nflat + PARAM_TAIL));
+        CK(dalloc(&c->d_inv, c->h_inv.size()));
+        CK(dalloc(&c->d_slot_of_flat, c->h_slot_of_flat.size()));
+        CK(dalloc(&c->d_losskind, (size_t)MAXT));
+        CK(cudaMemcpy(c->d_inv, c->h_inv.data(), c->h_inv.size() * sizeof(int), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->d_slot_of_flat, c->h_slot_of_flat.data(), c->h_slot_of_flat.size() * sizeof(int), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->d_losskind, c->loss_kind, MAXT * sizeof(int), cudaMemcpyHostToDevice));
+        CK(dalloc(&c->d_pbuf, (size_t)2 * (c->nsm + 8) * rup4(v->NPART)));
+        CK(dalloc(&c->d_pub, (size_t)2 * (c->nflat + PARAM_TAIL)));
+        CK(dalloc(&c->d_counter, (size_t)4));
         CK(dalloc(&c->d_m, (size_t)c->nflat));
         CK(dalloc(&c->d_v, (size_t)c->nflat));
         CK(dalloc(&c->d_grad, (size_t)c->nflat));
@@ -821,7 +933,8 @@ eh_status eh_create(eh_ctx** out, const eh_model_desc* desc)
         CK(dalloc(&c->d_err, (size_t)1));
         CK(dalloc(&c->d_evalpart, (size_t)c->nsm * 4 * MAXT * EVAL_NSTAT));
         CK(dalloc(&c->d_bn_test, (size_t)BS_STRIDE));
-        CK(cudaMemset(c->d_theta, 0, (size_t)c->nflat * sizeof(float)));
+        CK(cudaMemset(c->d_theta, 0, ((size_t)c->nflat + PARAM_TAIL) * sizeof(float)));
+        CK(refresh_tail(c));
         return reset_opt_state(c);
     };
     s = cuda_setup();
@@ -837,7 +950,7 @@ void eh_destroy(eh_ctx* c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->gexec) cudaGraphExecDestroy(c->gexec);
     void* ptrs[] = {c->d_wsrc, c->d_pmap, c->d_pspan, c->d_theta, c->d_m, c->d_v, c->d_grad, c->d_ost, c->d_partial,
-                    c->d_gvec, c->d_bscal, c->d_bn_batch, c->d_idx, c->d_idx64, c->d_err, c->d_loss, c->d_evalpart,
+                    c->d_gvec, c->d_inv, c->d_slot_of_flat, c->d_losskind, c->d_pbuf, c->d_pub, c->d_stats, c->d_counter, c->d_bscal, c->d_bn_batch, c->d_idx, c->d_idx64, c->d_err, c->d_loss, c->d_evalpart,
                     c->d_bn_test, c->split[0].rec, c->split[1].rec};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -919,6 +1032,7 @@ eh_status eh_set_params(eh_ctx* c, const float* flat, int64_t n)
     if (!flat || n != c->nflat) return fail(c, EH_EINVAL, "eh_set_params: expected %d entries, got %lld", c->nflat, (long long)n);
     CK(cudaSetDevice(c->device));
     CK(cudaMemcpyAsync(c->d_theta, flat, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CK(refresh_tail(c));
     CK(cudaStreamSynchronize(c->stream));
     return EH_OK;
 }
@@ -1121,7 +1235,7 @@ eh_status eh_eval(eh_ctx* c, int32_t split, float* yhat, double* stats, float* n
     EvalArgs a;
     memset(&a, 0, sizeof a);
     a.rec = reinterpret_cast<const float4*>(sp.rec);
-    a.rec_base = 0; a.N = N; a.theta = c->d_theta; a.wsrc = c->d_wsrc;
+    a.rec_base = 0; a.N = N; a.pblock = c->d_theta; a.nflat = c->nflat; a.wsrc = c->d_wsrc;
     a.use_bn = c->use_bn;
     if (c->use_bn) {
         // test mode: running statistics (LuxCore.testmode(st), compute_loss.jl:37)
@@ -1143,7 +1257,7 @@ eh_status eh_eval(eh_ctx* c, int32_t split, float* yhat, double* stats, float* n
     int64_t nchunks = (N + CHUNK - 1) / CHUNK;
     int grid = (int)std::min<int64_t>((nchunks + nwarps - 1) / nwarps, (int64_t)c->nsm * 4);
     if (grid < 1) grid = 1;
-    size_t smem = (size_t)(rup4(v->NW) + 64) * 4;
+    size_t smem = (size_t)(rup4(v->NW) + SS_FLOATS) * 4;
     CK(cudaEventRecord(c->ev0, c->stream));
     CK(v->launch_eval(a, grid, nwarps, smem, c->stream));
     CK(cudaEventRecord(c->ev1, c->stream));

@@ -10,15 +10,6 @@
 
 namespace eh {
 
-enum : int { OPT_ADAM = 0, OPT_ADAMW = 1, OPT_RMSPROP = 2, OPT_DESCENT = 3 };
-enum : int { UPD_FULL = 0, UPD_REDUCE_ONLY = 1, UPD_FROM_VECTOR = 2 };
-
-struct OptState {   // device-resident scalars
-    float b1t, b2t; // running beta^t products, as Optimisers keeps them (start at beta)
-    long long t;    // completed steps
-    long long skipped;
-};
-
 struct UpdateArgs {
     const float* partial;  // [G][npart] from K1
     int G, npart, npart_dw;
@@ -39,8 +30,44 @@ struct UpdateArgs {
     int loss_kind[MAXT];
     int opt_kind, adamw_coupled;
     float eta, beta1, beta2, eps, lambda;
-    float world_scale;     // unused (reserved)
+    // parameter-block tail (uniform slot values + derived process-model scalars)
+    const int* slot_of_flat;  // [nflat] phi entries: canonical slot, -1 otherwise
+    PSlot slot[MAXPS];
+    int pm_id;
 };
+
+// value + derived scalars of uniform slot sl -> tail of the parameter block
+__device__ inline void write_slot_tail(float* pblock, int nflat, int pm_id, int sl, float val)
+{
+    float o4[4];
+    pm_prep_slot(pm_id, sl, val, o4);
+    pblock[nflat + sl] = val;
+    for (int i = 0; i < 4; i++) pblock[nflat + MAXPS + sl * PMS_PER_SLOT + i] = o4[i];
+}
+
+// refresh the whole tail from the current phi (after eh_set_params)
+struct TailArgs {
+    float* pblock;
+    int nflat, ntheta, pm_id;
+    const int* slot_of_flat;
+    PSlot slot[MAXPS];
+};
+__global__ void k_param_tail(const TailArgs a)
+{
+    int t = threadIdx.x;
+    if (t < MAXPS) {
+        const PSlot sl = a.slot[t];
+        if (sl.role == ROLE_FIXED) write_slot_tail(a.pblock, a.nflat, a.pm_id, t, sl.fixedv);
+        else if (sl.role == ROLE_NEURAL) write_slot_tail(a.pblock, a.nflat, -1, t, 0.f);
+    }
+    for (int p = a.ntheta + t; p < a.nflat; p += blockDim.x) {
+        int s = a.slot_of_flat[p];
+        if (s >= 0) {
+            const PSlot sl = a.slot[s];
+            write_slot_tail(a.pblock, a.nflat, a.pm_id, s, sl.lo + sl.span * (1.f / (1.f + expf(-a.pblock[p]))));
+        }
+    }
+}
 
 __global__ void __launch_bounds__(512, 1) k_update(const UpdateArgs a)
 {
@@ -129,7 +156,12 @@ __global__ void __launch_bounds__(512, 1) k_update(const UpdateArgs a)
         } else {
             dx = a.eta * g;
         }
-        a.theta[p] = th - dx;
+        th -= dx;
+        a.theta[p] = th;
+        if (p >= a.ntheta) {
+            const int s = a.slot_of_flat[p];
+            if (s >= 0) write_slot_tail(a.theta, a.nflat, a.pm_id, s, a.slot[s].lo + a.slot[s].span * (1.f / (1.f + expf(-th))));
+        }
     }
     if (threadIdx.x == 0 && a.apply) {
         if (skip) {
@@ -277,6 +309,24 @@ __global__ void __launch_bounds__(256) k_idx_convert(const long long* in, int* o
     long long v = in[i] - 1;
     if (v < 0 || v >= nmax) { *err = 1; v = 0; }
     out[i] = (int)v;
+}
+
+// per-step loss values from the reduced sums of the persistent kernel (loss_fn.jl:58-81)
+__global__ void k_losses_from_stats(const float* stats, const float* bscal, long long first_step, int nb, int nsteps,
+                                    int T, int agg_mean, const int* loss_kind_dev, float* loss_out)
+{
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nsteps) return;
+    const float* bs = bscal + (size_t)((first_step + s) % nb) * BS_STRIDE;
+    float L = 0.f, ntot = 0.f;
+    for (int t = 0; t < T; t++) {
+        float n = bs[BS_N + t], ss = bs[BS_SS + t], acc = stats[(size_t)s * MAXT + t];
+        ntot += n;
+        int lk = loss_kind_dev[t];
+        L += (lk == LOSS_NSELOSS) ? acc / ss : acc / n;
+    }
+    if (agg_mean) L /= (float)T;
+    loss_out[s] = ntot == 0.f ? __int_as_float(0x7fc00000) : L;
 }
 
 }  // namespace eh

@@ -7,19 +7,27 @@ namespace eh {
 
 struct StepArgs;
 struct EvalArgs;
+struct EpochArgs;
 
 struct Variant {
     int pm, P, NH, H, NOUT, act, scale;
     ShapeDims dims;
-    int F, T, NPS, R4, NB, NW, NPART, stage_floats;
+    int F, T, NPS, R4, NB, NW, NPART, stage_floats, max_warps;
     const char* name;
     cudaError_t (*prepare)(size_t step_smem, size_t eval_smem);
     cudaError_t (*launch_step)(const StepArgs& a, int grid, int nwarps, size_t smem, cudaStream_t st, bool pdl);
     cudaError_t (*launch_eval)(const EvalArgs& a, int grid, int nwarps, size_t smem, cudaStream_t st);
+    cudaError_t (*launch_epoch)(const EpochArgs& a, int grid, int nwarps, size_t smem, cudaStream_t st);
+    cudaError_t (*epoch_max_grid)(int nwarps, size_t smem, int* blocks_per_sm);
 };
 
 const Variant* find_variant(int pm, int P, int NH, int H, int NOUT, int act, int scale);
 int num_variants();
 const Variant* variant_at(int i);
+
+// one translation unit per process-model family (parallel build)
+const Variant* variants_rbq10(int* n);
+const Variant* variants_expo(int* n);
+const Variant* variants_linear(int* n);
 
 }  // namespace eh

@@ -177,6 +177,7 @@ typedef struct {
 
 #define EH_FLAG_NO_GRAPH 1u   /* launch every step individually (debug / profiling) */
 #define EH_FLAG_NO_PDL   2u   /* no programmatic dependent launch                   */
+#define EH_FLAG_NO_PERSIST 4u /* never use the persistent multi-step kernel         */
 
 enum { EH_SPLIT_TRAIN = 0, EH_SPLIT_VAL = 1 };
 

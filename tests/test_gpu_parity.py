@@ -182,6 +182,36 @@ def test_determinism_and_additivity_at_benchmark_batch(eh):
     sess.close()
 
 
+def test_persistent_kernel_matches_step_kernels(eh, orc):
+    """the persistent multi-step kernel (default) and the one-launch-per-step path (EH_FLAG_NO_PERSIST),
+    with and without CUDA graph / PDL, train the same model: same losses, same parameters"""
+    model = rbq10_model(eh)
+    xf, y = eh.prepare_data(model, make_synth(30000, nan_frac=0.02))
+    n = xf[0].shape[0]
+    flat = model.initialparameters(np.random.default_rng(3))
+    perm = np.random.default_rng(4).permutation(n)
+    out = {}
+    for flags in (0, 4, 4 | 1, 4 | 1 | 2):
+        sess = eh.FusedSession(model, flags=flags)
+        sess.upload(0, xf, y)
+        sess.set_params(flat)
+        sess.set_perm(perm)
+        l1 = sess.run_steps(1000, 0, 2 * ((n + 999) // 1000) + 3)   # two passes (graph replay) + 3 steps
+        out[flags] = (l1, sess.get_params(), sess.get_opt_state())
+        sess.close()
+    o = orc.Oracle(model)
+    ref = flat.copy()
+    nb = (n + 999) // 1000
+    want = np.concatenate([o.train_steps(ref, xf, y, perm, 1000), o.train_steps(ref, xf, y, perm, 1000),
+                           o.train_steps(ref, xf, y, perm[:3000], 1000)])
+    for flags, (l1, ps, (m, v, t)) in out.items():
+        assert t == 2 * nb + 3, flags
+        np.testing.assert_allclose(l1, want, rtol=5e-4, err_msg=str(flags))
+        assert abs(float(ps[-1]) - float(ref[-1])) <= 1e-4, flags
+    # the three non-persistent variants share the reduction order: bitwise equal
+    assert np.array_equal(out[4][0], out[5][0]) and np.array_equal(out[4][1], out[7][1])
+
+
 def test_unsupported_models_fail_loudly(eh):
     from easyhybrid_b200 import _abi
 
