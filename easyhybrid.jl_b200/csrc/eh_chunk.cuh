@@ -45,7 +45,10 @@ struct StepCfg {
     static constexpr bool SCALE = SCALE_;
     using PM = PM_;
     static constexpr int F = PM::NF, T = PM::NT, NPS = PM::NPS;
-    static constexpr ShapeDims D{P_, NH_, H_, NOUT_};
+    // output-layer dW kept in registers when all per-lane scalars fit one 32-value transpose-reduce
+    static constexpr int LR = (NOUT_ * (H_ + 1) + PM_::NT + PM_::NPS <= 32) ? 1 : 0;
+    static constexpr ShapeDims D{P_, NH_, H_, NOUT_, LR};
+    static constexpr int NLAST = NOUT_ * (H_ + 1);
     static constexpr int R4 = rup4(P_ + PM::NF + PM::NT);  // floats per record
     static constexpr int NB = D.nblocks();
     static constexpr int NBI = (NB + 31) / 32;             // dW tiles per lane
@@ -53,13 +56,13 @@ struct StepCfg {
     static constexpr int AUXROW0 = D.nrows();              // swish sigma rows
     static constexpr int STAGE_FLOATS = NROWS * ROWSTRIDE;  // per warp
     static constexpr int NW = D.nweights();
-    static constexpr int NPART = D.npart_dw() + NSTAT;
+    static constexpr int NPART = D.npart();
     static_assert(P_ <= MAXP && H_ % 4 == 0 && NOUT_ <= 4, "shape limits");
 };
 
 // shared memory carve-up (floats): [weights NW pad4][scalars 128][per-warp stage ...]
 //   scalars: [0..8) uniform slot values, [16..48) per-slot derived scalars, [48..52) c_t, [56..80) BN (mu, rstd)
-constexpr int SS_SLOT = 0, SS_PMS = 16, SS_C = 48, SS_BN = 56, SS_FLOATS = 128;
+constexpr int SS_SLOT = 0, SS_PMS = 16, SS_C = 48, SS_NV = 52, SS_BN = 56, SS_FLOATS = 128;
 
 // row of feature k inside 4-row group g0 (+k/4): groups start every 5 rows (bank skew)
 __device__ __forceinline__ constexpr int grow(int g0, int k) { return 5 * (g0 + (k >> 2)) + (k & 3); }
@@ -100,9 +103,11 @@ __device__ __forceinline__ void chain_forward(const float* sW, float* stage, int
         for (int j = 0; j < HP; j++) {
             float2 aux = f2s(0.f);
             hp[j] = act_fwd2<C::ACT>(hp[j], aux);
-            if (STAGE) {
+            if (STAGE && l + 1 <= D.nlt()) {
                 stage[grow(D.gA(l + 1), 2 * j) * RS + lane] = hp[j].x;
                 stage[grow(D.gA(l + 1), 2 * j + 1) * RS + lane] = hp[j].y;
+            }
+            if (STAGE) {
                 if (C::ACT == ACT_SWISH) {
                     stage[(C::AUXROW0 + (l - 1) * H + 2 * j) * RS + lane] = aux.x;
                     stage[(C::AUXROW0 + (l - 1) * H + 2 * j + 1) * RS + lane] = aux.y;
@@ -200,13 +205,15 @@ __device__ __forceinline__ void init_stage_rows(float* stage, int lane)
     constexpr ShapeDims D = C::D;
     constexpr int RS = ROWSTRIDE;
 #pragma unroll
-    for (int l = 1; l <= C::NH + 1; l++) {
+    for (int l = 1; l <= D.nlt(); l++) {
         const int din = D.din(l), ka = D.ka(l), gA = D.gA(l);
 #pragma unroll
         for (int k = din; k < ka; k++) stage[grow(gA, k) * RS + lane] = (k == din) ? 1.f : 0.f;
     }
+    if (!C::LR) {
 #pragma unroll
-    for (int o = C::NOUT; o < rup4(C::NOUT); o++) stage[grow(D.gD(C::NH + 1), o) * RS + lane] = 0.f;
+        for (int o = C::NOUT; o < rup4(C::NOUT); o++) stage[grow(D.gD(C::NH + 1), o) * RS + lane] = 0.f;
+    }
 }
 
 // dW tile coordinates of this lane: rows of the delta / activation groups of tile b = lane + 32 i
@@ -220,7 +227,7 @@ __device__ __forceinline__ void tile_rows(int lane, int* rowD, int* rowA)
         rowD[i] = 0;
         rowA[i] = 0;
 #pragma unroll
-        for (int l = 1; l <= C::NH + 1; l++) {
+        for (int l = 1; l <= D.nlt(); l++) {
             const int b0 = D.blk0(l), nk = D.nk(l), nb = D.nj(l) * nk;
             if (b >= b0 && b < b0 + nb) {
                 int jb = (b - b0) / nk, kb = (b - b0) % nk;
@@ -236,12 +243,28 @@ struct ChunkStats {
     float gphi[MAXPS];   // sum g * dy/dslot for GLOBAL slots
 };
 
+// lane-owned gradient of the linear output layer (LR shapes): [NOUT][H/2] weight pairs + [NOUT] bias
+template <class C>
+struct LastAcc {
+    float2 w[C::LR ? C::NOUT : 1][C::H / 2];
+    float b[C::LR ? C::NOUT : 1];
+    __device__ __forceinline__ void zero()
+    {
+#pragma unroll
+        for (int o = 0; o < (C::LR ? C::NOUT : 1); o++) {
+            b[o] = 0.f;
+#pragma unroll
+            for (int k = 0; k < C::H / 2; k++) w[o][k] = f2s(0.f);
+        }
+    }
+};
+
 // ---- per-sample phase: forward, physics, masked residual, backward data pass, staging ----
 // rec: this lane's record (canonical order), valid: sample exists.
 template <class C>
 __device__ __forceinline__ void chunk_sample_phase(const float* rec, bool valid, const float* sW, const float* sS,
                                                    float* stage, int lane, const PSlot* slot, const int* loss_kind,
-                                                   const PmCtx& cx, ChunkStats& st)
+                                                   const PmCtx& cx, ChunkStats& st, LastAcc<C>& la)
 {
     constexpr ShapeDims D = C::D;
     constexpr int P = C::P, NH = C::NH, H = C::H, NOUT = C::NOUT, T = C::T, F = C::F, NPS = C::NPS, HP = C::H / 2;
@@ -301,8 +324,18 @@ __device__ __forceinline__ void chunk_sample_phase(const float* rec, bool valid,
             st.gphi[s] += gp[s];
         }
     }
+    if (C::LR) {
+        // output-layer weight gradient in registers: dWo[o][k] += dz_o a_NH[k], dbo[o] += dz_o
 #pragma unroll
-    for (int o = 0; o < NOUT; o++) stage[grow(D.gD(NH + 1), o) * RS + lane] = dz[o];
+        for (int o = 0; o < NOUT; o++) {
+            la.b[o] += dz[o];
+#pragma unroll
+            for (int k = 0; k < HP; k++) la.w[o][k] = fma2s(hp[k], dz[o], la.w[o][k]);
+        }
+    } else {
+#pragma unroll
+        for (int o = 0; o < NOUT; o++) stage[grow(D.gD(NH + 1), o) * RS + lane] = dz[o];
+    }
 
     // backward data pass: delta_l for l = NH .. 1 (hp still holds a_NH), neuron pairs
     float2 d[HP];
@@ -385,11 +418,43 @@ __device__ __forceinline__ void chunk_dw_phase(const float* stage, int lane, con
     }
 }
 
-// ---- CTA-level fixed-order reduction of lane tiles + statistics into red[NPART] (smem) ----
+// Sum NV per-lane values over the 32 lanes of a warp with a recursive-halving exchange: at each of
+// the 5 levels a lane keeps half of its values and ships the other half to its partner, so the whole
+// reduction costs NV-ish shuffles instead of 5*NV (SHFL shares the 128 B/clk LSU writeback path, which
+// is the scarce resource of this kernel).  On return lane l holds the total of value index
+// slot_of_lane(l) in v[0]; fixed exchange order -> bitwise reproducible.
+template <int NV>
+__device__ __forceinline__ void warp_transpose_reduce(float (&v)[32], int lane)
+{
+    static_assert(NV <= 32, "at most 32 values");
+#pragma unroll
+    for (int i = NV; i < 32; i++) v[i] = 0.f;
+#pragma unroll
+    for (int lvl = 0; lvl < 5; lvl++) {
+        const int half = 16 >> lvl;          // values kept after this level
+        const int mask = 16 >> lvl;          // partner = lane ^ mask
+        const bool up = (lane & mask) != 0;
+#pragma unroll
+        for (int i = 0; i < half; i++) {
+            // lanes with the bit set keep the upper half [half, 2 half), others the lower half
+            float keep = up ? v[i + half] : v[i];
+            float send = up ? v[i] : v[i + half];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+        }
+    }
+}
+// value index whose total ends up in lane l after warp_transpose_reduce
+__device__ __forceinline__ int transpose_reduce_slot(int lane)
+{
+    // level k (mask 16>>k) chooses the upper half when the lane bit is set: index bits from MSB down
+    return lane;  // bit (4-k) of the index == bit (4-k) of the lane
+}
+
+// ---- CTA-level fixed-order reduction of lane tiles + statistics into out[NPART] ----
 // scratch: [nwarps][NPART] floats (may alias the staging tiles; caller syncs before).
 template <class C>
-__device__ __forceinline__ void cta_reduce(const float2 (*acc)[16], const ChunkStats& st, float* scratch, float* out,
-                                           int out_is_global)
+__device__ __forceinline__ void cta_reduce(const float2 (*acc)[16], const ChunkStats& st, const LastAcc<C>& la,
+                                           float* scratch, float* out, int out_is_global)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
 #pragma unroll
@@ -400,15 +465,41 @@ __device__ __forceinline__ void cta_reduce(const float2 (*acc)[16], const ChunkS
             for (int e = 0; e < 16; e++) scratch[warp * C::NPART + b * 16 + e] = acc[i][e].x + acc[i][e].y;
         }
     }
+    {
+        // all per-lane scalars (loss sums, phi sums, output-layer gradient) in one exchange
+        constexpr int NLASTV = C::LR ? C::NLAST : 0;
+        constexpr int NV = C::T + C::NPS + NLASTV;
+        static_assert(NV <= 32, "per-lane scalar set too large for one transpose-reduce");
+        float v[32];
 #pragma unroll
-    for (int t = 0; t < MAXT; t++) {
-        float v = warp_sum(t < C::T ? st.loss[t] : 0.f);
-        if (lane == 0) scratch[warp * C::NPART + C::D.npart_dw() + t] = v;
-    }
+        for (int t = 0; t < C::T; t++) v[t] = st.loss[t];
 #pragma unroll
-    for (int s = 0; s < MAXPS; s++) {
-        float v = warp_sum(s < C::NPS ? st.gphi[s] : 0.f);
-        if (lane == 0) scratch[warp * C::NPART + C::D.npart_dw() + MAXT + s] = v;
+        for (int s = 0; s < C::NPS; s++) v[C::T + s] = st.gphi[s];
+        if (C::LR) {
+#pragma unroll
+            for (int o = 0; o < C::NOUT; o++) {
+#pragma unroll
+                for (int k = 0; k < C::H / 2; k++) {
+                    v[C::T + C::NPS + o * (C::H + 1) + 2 * k] = la.w[o][k].x;
+                    v[C::T + C::NPS + o * (C::H + 1) + 2 * k + 1] = la.w[o][k].y;
+                }
+                v[C::T + C::NPS + o * (C::H + 1) + C::H] = la.b[o];
+            }
+        }
+        warp_transpose_reduce<NV>(v, lane);
+        // lane l now holds the warp total of value l
+        const int i = lane;
+        int dst = -1;
+        if (i < C::T) dst = C::D.npart_dw() + i;
+        else if (i < C::T + C::NPS) dst = C::D.npart_dw() + MAXT + (i - C::T);
+        else if (i < NV) dst = C::D.off_last() + (i - C::T - C::NPS);
+        if (dst >= 0) scratch[warp * C::NPART + dst] = v[0];
+        // cells of the statistics block that no lane writes
+        for (int q = C::D.npart_dw() + lane; q < C::NPART; q += 32) {
+            bool used = (q < C::D.npart_dw() + C::T) || (q >= C::D.npart_dw() + MAXT && q < C::D.npart_dw() + MAXT + C::NPS) ||
+                        (q >= C::D.off_last() && q < C::D.off_last() + NLASTV);
+            if (!used) scratch[warp * C::NPART + q] = 0.f;
+        }
     }
     __syncthreads();
     for (int p = threadIdx.x; p < C::NPART; p += blockDim.x) {

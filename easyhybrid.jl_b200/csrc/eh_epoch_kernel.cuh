@@ -1,15 +1,17 @@
 // eh_epoch_kernel.cuh -- the persistent form of the training loop: MANY optimiser steps in one
-// cooperative launch (one CTA per SM), replacing run_epoch! (src/training/epoch.jl:13-33) as a
-// whole.  Per step every CTA
-//   1. runs the fused forward/backward on its chunks (eh_chunk.cuh) with the weights it keeps in
-//      shared memory,
-//   2. publishes its partial vector, passes a grid barrier,
-//   3. reduce-scatter: CTA c reduces slice c of the vector over all CTAs in a fixed order and
-//      applies the optimiser to the parameters that live in that slice (their Adam moments stay in
-//      the owner's shared memory for the whole launch),
-//   4. publishes the new parameter values, passes a second grid barrier, reloads its weight image.
-// Compared with one launch per step this removes two kernel launches (~2 x 5000 cycles of launch
-// ramp), the dependent-load prologue and the single-CTA second pass from every step.
+// launch (one CTA per SM, thread-block clusters), replacing run_epoch!
+// (src/training/epoch.jl:13-33) as a whole.  Per step every CTA
+//   1. runs the fused forward/backward on its chunks (eh_chunk.cuh) with the weight image it keeps
+//      in shared memory,
+//   2. reduces its lane tiles to one partial vector in shared memory; the cluster leader sums the
+//      partials of its cluster over distributed shared memory (DSMEM) in rank order and publishes
+//      ONE vector per cluster,
+//   3. one grid barrier (arrival counter; only cluster leaders arrive),
+//   4. every CTA sums the cluster vectors in a fixed order and applies the optimiser REDUNDANTLY to
+//      its own copy of theta / m / v in shared memory, patching its weight image in place.
+// All CTAs execute the same float operations in the same order, so the replicas stay bit-identical
+// and nothing has to be broadcast back.  Compared with one launch per step this removes two kernel
+// launches, the dependent-load prologue and the single-CTA second pass from every step.
 // No atomics on data: the only atomic is the barrier's arrival counter.
 #pragma once
 #include "eh_step_kernel.cuh"
@@ -29,18 +31,18 @@ struct EpochArgs {
     float* m;                  // in/out optimiser moments
     float* v;
     OptState* ost;             // in/out
-    const int* wsrc;           // [NW]
-    const int* inv;            // [NPART] partial index -> flat parameter or -1
+    const int* wsrc;           // [NW] image cell -> flat index
+    const int* pmap;           // [nflat] flat -> index into the partial vector
+    const int* cells;          // [2*nflat] flat -> up to two image cells (-1: none)
     const float* pspan;        // [nflat]
     const int* slot_of_flat;   // [nflat] phi entries: canonical slot (for the tail), -1 otherwise
     const float* bscal;        // [nb][BS_STRIDE]
-    float* pbuf;               // [2][gridDim.x][npartp] published partial vectors
-    float* pub;                // [2][nflat + PARAM_TAIL] published parameter blocks
+    float* pbuf;               // [2][nclusters][npartp] published cluster vectors
     unsigned* counter;         // grid barrier arrival counter (zeroed before launch)
     float* stats_out;          // [nsteps][MAXT] reduced loss sums
     int npartp;                // padded partial length (multiple of 4)
-    int SL;                    // slice of the partial vector owned by one CTA
-    int T;
+    int csize;                 // cluster size (1, 2, 4, 8)
+    int T, agg_mean;
     int loss_kind[MAXT];
     PSlot slot[MAXPS];
     float pmc[4];
@@ -48,6 +50,7 @@ struct EpochArgs {
     int pm_id;
     int opt_kind, adamw_coupled;
     float eta, beta1, beta2, eps, lambda;
+    long long* dbg;            // optional [nsteps][gridDim.x][32] SM-clock timestamps (EH_EPOCH_DEBUG)
 };
 
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p)
@@ -56,18 +59,25 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p)
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-
-// arrive + wait on a monotonically increasing counter; all threads of the CTA call it
-__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target)
+__device__ __forceinline__ void cluster_sync_all()
 {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(counter, 1u);
-        while (ld_acquire_gpu(counter) < target) { }
-        __threadfence();
-    }
-    __syncthreads();
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// read a float from the same shared-memory offset in CTA `rank` of this cluster (DSMEM)
+__device__ __forceinline__ float ld_dsmem(const float* local, unsigned rank)
+{
+    unsigned a = (unsigned)__cvta_generic_to_shared(local), ra;
+    float v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
+    return v;
+}
+
+template <class C>
+__host__ __device__ constexpr int epoch_extra_floats(int nflat)
+{
+    // cpart + red (padded partial vectors) + theta, m, v copies + tables (pmap, 2 cells, span, slot)
+    return 2 * rup4(C::NPART) + 8 * rup4(nflat);
 }
 
 template <class C>
@@ -79,23 +89,33 @@ __global__ void __launch_bounds__(512, 1) k_epoch(const EpochArgs a)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
     float* stage0 = sS + SS_FLOATS;
     float* stage = stage0 + warp * C::STAGE_FLOATS;
-    // owner state behind the staging tiles: [SL] theta, m, v, flat index
-    float* own = stage0 + nwarps * C::STAGE_FLOATS;
-    float* own_th = own;
-    float* own_m = own + a.SL;
-    float* own_v = own + 2 * a.SL;
-    int* own_p = reinterpret_cast<int*>(own + 3 * a.SL);
-    float* red = own + 4 * a.SL;  // [SL] reduced slice
+    float* cpart = stage0 + nwarps * C::STAGE_FLOATS;   // [npartp] this CTA's partial vector
+    float* red = cpart + rup4(C::NPART);                // [npartp] fully reduced vector
+    float* s_th = red + rup4(C::NPART);                 // [nflat] replicated parameters
+    float* s_m = s_th + rup4(a.nflat);
+    float* s_v = s_m + rup4(a.nflat);
+    int* t_pmap = reinterpret_cast<int*>(s_v + rup4(a.nflat));
+    int* t_cell0 = t_pmap + rup4(a.nflat);
+    int* t_cell1 = t_cell0 + rup4(a.nflat);
+    int* t_slot = t_cell1 + rup4(a.nflat);
+    float* t_span = reinterpret_cast<float*>(t_slot + rup4(a.nflat));
+    __shared__ float s_post;
+    __shared__ int s_skip;
     const int G = gridDim.x;
-    const int q0 = blockIdx.x * a.SL;
+    const int cs = a.csize;
+    const int NC = G / cs;                               // clusters = published vectors per step
+    const unsigned crank = (unsigned)(blockIdx.x % cs);
+    const int cid = blockIdx.x / cs;
 
-    for (int j = threadIdx.x; j < a.SL; j += blockDim.x) {
-        int q = q0 + j;
-        int p = (q < C::NPART) ? a.inv[q] : -1;
-        own_p[j] = p;
-        own_th[j] = p >= 0 ? a.pblock[p] : 0.f;
-        own_m[j] = p >= 0 ? a.m[p] : 0.f;
-        own_v[j] = p >= 0 ? a.v[p] : 0.f;
+    for (int p = threadIdx.x; p < a.nflat; p += blockDim.x) {
+        s_th[p] = a.pblock[p];
+        s_m[p] = a.m[p];
+        s_v[p] = a.v[p];
+        t_pmap[p] = a.pmap[p];
+        t_cell0[p] = a.cells[2 * p];
+        t_cell1[p] = a.cells[2 * p + 1];
+        t_slot[p] = a.slot_of_flat[p];
+        t_span[p] = a.pspan[p];
     }
     float b1t = a.ost->b1t, b2t = a.ost->b2t;
     long long tdone = 0, tskip = 0;
@@ -114,7 +134,8 @@ __global__ void __launch_bounds__(512, 1) k_epoch(const EpochArgs a)
         if (s >= C::NPS || a.slot[s].role != ROLE_NEURAL) cx.uniform_mask |= 1u << s;
 
     const int GW = G * nwarps;
-    const int gw = blockIdx.x * nwarps + warp;
+    // chunk -> warp assignment interleaves CTAs so that a ragged chunk count spreads over all SMs
+    const int gw = warp * G + blockIdx.x;
     float4 r[C::R4 / 4];
     bool valid;
     {
@@ -124,19 +145,32 @@ __global__ void __launch_bounds__(512, 1) k_epoch(const EpochArgs a)
         fetch_record<C>(a.rec, a.idx + b * a.B, 0, Bk, gw, (Bk + CHUNK - 1) / CHUNK, lane, r, valid);
     }
     unsigned bar = 0;
+    // per-batch scalars of the coming step, prefetched one step ahead (a dependent global load otherwise)
+    float pre_bs = 0.f;
+    auto prefetch_bs = [&](int step) {
+        const float* bs = a.bscal + (size_t)((a.first_step + step) % a.nb) * BS_STRIDE;
+        if (threadIdx.x < MAXT) pre_bs = bs[BS_C + threadIdx.x];
+        else if (threadIdx.x < MAXT + 2 * C::P)
+            pre_bs = a.use_bn ? bs[BS_BN + threadIdx.x - MAXT] : (((threadIdx.x - MAXT) & 1) ? 1.f : 0.f);
+        else if (threadIdx.x >= 28 && threadIdx.x < 28 + MAXT) pre_bs = bs[BS_N + threadIdx.x - 28];
+    };
+    prefetch_bs(0);
+#define EH_STAMP(slot)                                                                      \
+    if (a.dbg && threadIdx.x == 0) a.dbg[((size_t)s * G + blockIdx.x) * 32 + (slot)] = clock64();
 
     for (int s = 0; s < a.nsteps; s++) {
+        EH_STAMP(0)
         const long long b = (a.first_step + s) % a.nb;
         const long long rem = a.n - b * a.B;
         const int Bk = (int)(rem < a.B ? rem : a.B);
         const int nchunks = (Bk + CHUNK - 1) / CHUNK;
-        const float* bs = a.bscal + (size_t)b * BS_STRIDE;
         const int par = s & 1;
-        // per-batch scalars
-        if (threadIdx.x < MAXT) sS[SS_C + threadIdx.x] = bs[BS_C + threadIdx.x];
-        if (threadIdx.x < 2 * C::P)
-            sS[SS_BN + threadIdx.x] = a.use_bn ? bs[BS_BN + threadIdx.x] : ((threadIdx.x & 1) ? 1.f : 0.f);
+        if (threadIdx.x < MAXT) sS[SS_C + threadIdx.x] = pre_bs;
+        else if (threadIdx.x < MAXT + 2 * C::P) sS[SS_BN + threadIdx.x - MAXT] = pre_bs;
+        else if (threadIdx.x >= 28 && threadIdx.x < 28 + MAXT) sS[SS_NV + threadIdx.x - 28] = pre_bs;
         __syncthreads();
+        if (s + 1 < a.nsteps) prefetch_bs(s + 1);
+        EH_STAMP(1)
 
         float2 acc[C::NBI][16];
 #pragma unroll
@@ -148,6 +182,8 @@ __global__ void __launch_bounds__(512, 1) k_epoch(const EpochArgs a)
         for (int t = 0; t < MAXT; t++) st.loss[t] = 0.f;
 #pragma unroll
         for (int t = 0; t < MAXPS; t++) st.gphi[t] = 0.f;
+        LastAcc<C> la;
+        la.zero();
 
         for (int chunk = gw; chunk < nchunks; chunk += GW) {
             float rec[C::R4];
@@ -157,11 +193,12 @@ __global__ void __launch_bounds__(512, 1) k_epoch(const EpochArgs a)
             }
             const bool v = valid;
             fetch_record<C>(a.rec, a.idx + b * a.B, 0, Bk, chunk + GW, nchunks, lane, r, valid);
-            chunk_sample_phase<C>(rec, v, sW, sS, stage, lane, a.slot, a.loss_kind, cx, st);
+            chunk_sample_phase<C>(rec, v, sW, sS, stage, lane, a.slot, a.loss_kind, cx, st, la);
             __syncwarp();
             chunk_dw_phase<C>(stage, lane, rowD, rowA, acc);
             __syncwarp();
         }
+        if (a.dbg && lane == 0) a.dbg[((size_t)s * G + blockIdx.x) * 32 + 8 + warp] = clock64();
         // prefetch my first sample of the next step: its latency hides behind the exchange below
         if (s + 1 < a.nsteps) {
             long long b2 = (a.first_step + s + 1) % a.nb;
@@ -170,103 +207,153 @@ __global__ void __launch_bounds__(512, 1) k_epoch(const EpochArgs a)
             fetch_record<C>(a.rec, a.idx + b2 * a.B, 0, Bk2, gw, (Bk2 + CHUNK - 1) / CHUNK, lane, r, valid);
         }
         __syncthreads();
-        // the scratch of cta_reduce aliases the staging tiles, whose constant rows are rewritten below
-        cta_reduce<C>(acc, st, stage0, a.pbuf + ((size_t)par * G + blockIdx.x) * a.npartp, 1);
-        bar += (unsigned)G;
-        grid_barrier(a.counter, bar);
-
-        // ---- reduce-scatter + optimiser on my slice (fixed order: lane-strided partial sums, xor tree)
-        float ntot = 0.f;
-        for (int t = 0; t < a.T; t++) ntot += bs[BS_N + t];
-        const bool skip = (ntot == 0.f);  // all-masked batch: epoch.jl:17-19
-        for (int j = warp; j < a.SL; j += nwarps) {
-            const int q = q0 + j;
-            float sum = 0.f;
-            if (q < C::NPART)
-                for (int g = lane; g < G; g += 32) sum += __ldcg(a.pbuf + ((size_t)par * G + g) * a.npartp + q);
-            sum = warp_sum(sum);
-            if (lane == 0) red[j] = sum;
+        EH_STAMP(2)
+        // CTA partial -> cpart (the scratch of cta_reduce aliases the staging tiles)
+        cta_reduce<C>(acc, st, la, stage0, cpart, 0);
+        EH_STAMP(3)
+        if (cs > 1) cluster_sync_all(); else __syncthreads();
+        EH_STAMP(4)
+        if (crank == 0) {
+            // cluster vector: ranks summed in order over DSMEM, published for the whole grid
+            float* dst = a.pbuf + ((size_t)par * NC + cid) * a.npartp;
+            for (int p = threadIdx.x; p < C::NPART; p += blockDim.x) {
+                float sum = cpart[p];
+                for (int rk = 1; rk < cs; rk++) sum += ld_dsmem(cpart + p, (unsigned)rk);
+                __stcg(dst + p, sum);
+            }
+        }
+        // grid barrier: leaders arrive, everybody waits
+        bar += (unsigned)NC;
+        __syncthreads();
+        EH_STAMP(5)
+        if (threadIdx.x == 0) {
+            if (crank == 0) {
+                __threadfence();
+                atomicAdd(a.counter, 1u);
+            }
+            while (ld_acquire_gpu(a.counter) < bar) { }
+            __threadfence();
         }
         __syncthreads();
-        for (int j = threadIdx.x; j < a.SL; j += blockDim.x) {
-            const int q = q0 + j;
-            if (q >= C::NPART) continue;
-            float g = red[j];
-            if (q >= C::D.npart_dw() && q < C::D.npart_dw() + MAXT) a.stats_out[(size_t)s * MAXT + (q - C::D.npart_dw())] = g;
-            const int p = own_p[j];
-            if (p < 0) continue;
-            float th = own_th[j];
-            if (!skip) {
+        EH_STAMP(6)
+
+        // every CTA: pull all cluster vectors into shared memory with independent 128-bit loads
+        // (one L2 round trip instead of NC dependent ones), then sum them in a fixed order
+        {
+            const float4* src4 = reinterpret_cast<const float4*>(a.pbuf + (size_t)par * NC * a.npartp);
+            float4* vec4 = reinterpret_cast<float4*>(stage0);  // the staging tiles are idle here
+            const int total4 = NC * (a.npartp / 4);
+            constexpr int U = 8;
+            for (int base = threadIdx.x; base < total4; base += U * blockDim.x) {
+                float4 t[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    int i = base + u * blockDim.x;
+                    t[u] = i < total4 ? __ldcg(src4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    int i = base + u * blockDim.x;
+                    if (i < total4) vec4[i] = t[u];
+                }
+            }
+        }
+        __syncthreads();
+        for (int p = threadIdx.x; p < C::NPART; p += blockDim.x) {
+            float s0 = 0.f, s1 = 0.f;
+            int c = 0;
+            for (; c + 2 <= NC; c += 2) {
+                s0 += stage0[(size_t)c * a.npartp + p];
+                s1 += stage0[(size_t)(c + 1) * a.npartp + p];
+            }
+            if (c < NC) s0 += stage0[(size_t)c * a.npartp + p];
+            red[p] = s0 + s1;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float ntot = 0.f, post = 1.f;
+            for (int t = 0; t < a.T; t++) {
+                ntot += sS[SS_NV + t];
+                if (a.loss_kind[t] == LOSS_RMSE) post = 1.f / (2.f * sqrtf(red[C::D.npart_dw() + t] / sS[SS_NV + t]));
+            }
+            s_post = post;
+            s_skip = (ntot == 0.f);  // all-masked batch: epoch.jl:17-19
+            if (blockIdx.x == 0)
+                for (int t = 0; t < MAXT; t++) a.stats_out[(size_t)s * MAXT + t] = red[C::D.npart_dw() + t];
+        }
+        __syncthreads();
+        const bool skip = s_skip != 0;
+        if (!skip) {
+            const float post = s_post;
+            for (int p = threadIdx.x; p < a.nflat; p += blockDim.x) {
+                float g = red[t_pmap[p]] * post;
+                float th = s_th[p];
                 if (p >= a.ntheta) {
                     float sg = 1.f / (1.f + expf(-th));
-                    g *= a.pspan[p] * sg * (1.f - sg);
+                    g *= t_span[p] * sg * (1.f - sg);
                 }
                 float dx;
                 if (a.opt_kind == OPT_ADAM || a.opt_kind == OPT_ADAMW) {
-                    float mt = a.beta1 * own_m[j] + (1.f - a.beta1) * g;
-                    float vt = a.beta2 * own_v[j] + (1.f - a.beta2) * g * g;
-                    own_m[j] = mt;
-                    own_v[j] = vt;
+                    float mt = a.beta1 * s_m[p] + (1.f - a.beta1) * g;
+                    float vt = a.beta2 * s_v[p] + (1.f - a.beta2) * g * g;
+                    s_m[p] = mt;
+                    s_v[p] = vt;
                     dx = mt / (1.f - b1t) / (sqrtf(vt / (1.f - b2t)) + a.eps) * a.eta;
                     if (a.opt_kind == OPT_ADAMW) dx += (a.adamw_coupled ? a.eta * a.lambda : a.lambda) * th;
                 } else if (a.opt_kind == OPT_RMSPROP) {
-                    float qv = a.beta2 * own_v[j] + (1.f - a.beta2) * g * g;
-                    own_v[j] = qv;
+                    float qv = a.beta2 * s_v[p] + (1.f - a.beta2) * g * g;
+                    s_v[p] = qv;
                     dx = g * a.eta / (sqrtf(qv) + a.eps);
                 } else {
                     dx = a.eta * g;
                 }
                 th -= dx;
-                own_th[j] = th;
-            }
-            float* pubp = a.pub + (size_t)par * (a.nflat + PARAM_TAIL);
-            __stcg(pubp + p, th);
-            if (p >= a.ntheta) {
-                const int sl = a.slot_of_flat[p];
-                if (sl >= 0) {
-                    const PSlot ps = a.slot[sl];
-                    float val = ps.lo + ps.span * (1.f / (1.f + expf(-th)));
-                    float o4[4];
-                    pm_prep_slot(a.pm_id, sl, val, o4);
-                    __stcg(pubp + a.nflat + sl, val);
-                    for (int i = 0; i < 4; i++) __stcg(pubp + a.nflat + MAXPS + sl * PMS_PER_SLOT + i, o4[i]);
+                s_th[p] = th;
+                // patch my weight image in place
+                const int c0 = t_cell0[p], c1 = t_cell1[p];
+                if (c0 >= 0) sW[c0] = th;
+                if (c1 >= 0) sW[c1] = th;
+                if (p >= a.ntheta) {
+                    const int sl = t_slot[p];
+                    if (sl >= 0) {
+                        const PSlot ps = a.slot[sl];
+                        float val = ps.lo + ps.span * (1.f / (1.f + expf(-th)));
+                        float o4[4];
+                        pm_prep_slot(a.pm_id, sl, val, o4);
+                        sS[SS_SLOT + sl] = val;
+                        for (int i = 0; i < 4; i++) sS[SS_PMS + sl * PMS_PER_SLOT + i] = o4[i];
+                    }
                 }
             }
+            b1t *= a.beta1;
+            b2t *= a.beta2;
+            tdone++;
+        } else {
+            tskip++;
         }
-        if (skip) tskip++;
-        else { b1t *= a.beta1; b2t *= a.beta2; tdone++; }
         init_stage_rows<C>(stage, lane);  // constant rows were overwritten by the reduction scratch
-        bar += (unsigned)G;
-        grid_barrier(a.counter, bar);
-        load_weights_and_scalars<C>(a.pub + (size_t)par * (a.nflat + PARAM_TAIL), a.nflat, a.wsrc, nullptr, 0, sW, sS);
+        EH_STAMP(7)
     }
+#undef EH_STAMP
 
-    // write back the state owned by this CTA
+    // write back (CTA 0 holds the same state as everybody else)
     __syncthreads();
-    for (int j = threadIdx.x; j < a.SL; j += blockDim.x) {
-        const int p = own_p[j];
-        if (p < 0) continue;
-        a.pblock[p] = own_th[j];
-        a.m[p] = own_m[j];
-        a.v[p] = own_v[j];
-        if (p >= a.ntheta) {
-            const int sl = a.slot_of_flat[p];
-            if (sl >= 0) {
-                const PSlot ps = a.slot[sl];
-                float val = ps.lo + ps.span * (1.f / (1.f + expf(-own_th[j])));
-                float o4[4];
-                pm_prep_slot(a.pm_id, sl, val, o4);
-                a.pblock[a.nflat + sl] = val;
-                for (int i = 0; i < 4; i++) a.pblock[a.nflat + MAXPS + sl * PMS_PER_SLOT + i] = o4[i];
-            }
+    if (blockIdx.x == 0) {
+        for (int p = threadIdx.x; p < a.nflat; p += blockDim.x) {
+            a.pblock[p] = s_th[p];
+            a.m[p] = s_m[p];
+            a.v[p] = s_v[p];
+        }
+        if (threadIdx.x < MAXPS) a.pblock[a.nflat + threadIdx.x] = sS[SS_SLOT + threadIdx.x];
+        if (threadIdx.x < MAXPS * PMS_PER_SLOT) a.pblock[a.nflat + MAXPS + threadIdx.x] = sS[SS_PMS + threadIdx.x];
+        if (threadIdx.x == 0) {
+            a.ost->b1t = b1t;
+            a.ost->b2t = b2t;
+            a.ost->t += tdone;
+            a.ost->skipped += tskip;
         }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        a.ost->b1t = b1t;
-        a.ost->b2t = b2t;
-        a.ost->t += tdone;
-        a.ost->skipped += tskip;
-    }
+    if (cs > 1) cluster_sync_all();  // nobody leaves while a leader may still read its shared memory
 }
 
 }  // namespace eh

@@ -29,10 +29,13 @@ constexpr int ROWSTRIDE = CHUNK + 4;  // floats per staging row (bank skew)
 
 EH_HD constexpr int rup4(int x) { return (x + 3) & ~3; }
 
-// runtime/compile-time description of one chain shape
+// runtime/compile-time description of one chain shape.  LR = 1: the weight gradient of the
+// (narrow) linear output layer is accumulated in registers by each lane instead of through
+// staging tiles (saves the a_NH / delta_out staging rows and their tiles).
 struct ShapeDims {
-    int P, NH, H, NOUT;
+    int P, NH, H, NOUT, LR;
     EH_HD constexpr int nlayers() const { return NH + 1; }
+    EH_HD constexpr int nlt() const { return LR ? NH : NH + 1; }  // layers whose dW goes through tiles
     // fan-in / padded fan-out of dense layer l (1-based)
     EH_HD constexpr int din(int l) const { return l == 1 ? P : H; }
     EH_HD constexpr int dout4(int l) const { return l == NH + 1 ? rup4(NOUT) : H; }
@@ -40,7 +43,7 @@ struct ShapeDims {
     EH_HD constexpr int ka(int l) const { return rup4(din(l) + 1); }
     EH_HD constexpr int nj(int l) const { return dout4(l) / 4; }
     EH_HD constexpr int nk(int l) const { return ka(l) / 4; }
-    // staging groups (4 rows each; group g starts at row 5g): for l = 1..L: A_{l-1} then D_l
+    // staging groups (4 rows each; group g starts at row 5g): for l = 1..nlt: A_{l-1} then D_l
     EH_HD constexpr int gA(int l) const
     {
         int g = 0;
@@ -48,7 +51,7 @@ struct ShapeDims {
         return g;
     }
     EH_HD constexpr int gD(int l) const { return gA(l) + nk(l); }
-    EH_HD constexpr int ngroups() const { return gA(NH + 2); }
+    EH_HD constexpr int ngroups() const { return gA(nlt() + 1); }
     EH_HD constexpr int nrows() const { return 5 * ngroups(); }
     // dW blocks (4x4): layer-major, then j-block, then k-block
     EH_HD constexpr int blk0(int l) const
@@ -57,7 +60,7 @@ struct ShapeDims {
         for (int i = 1; i < l; i++) b += nj(i) * nk(i);
         return b;
     }
-    EH_HD constexpr int nblocks() const { return blk0(NH + 2); }
+    EH_HD constexpr int nblocks() const { return blk0(nlt() + 1); }
     // shared-memory weight image (floats)
     EH_HD constexpr int off_w1f() const { return 0; }                     // [P][H]
     EH_HD constexpr int off_b1() const { return P * H; }                  // [H]
@@ -67,8 +70,11 @@ struct ShapeDims {
     EH_HD constexpr int off_wo() const { return P * H + H + (NH - 1) * (2 * H * H + H); }  // [NOUT][H]
     EH_HD constexpr int off_bo() const { return off_wo() + NOUT * H; }    // [4]
     EH_HD constexpr int nweights() const { return off_bo() + 4; }
-    // per-CTA partial vector: nblocks*16 dW entries, then statistics
+    // per-CTA partial vector: nblocks*16 dW entries, statistics, then (LR) the output layer [NOUT][H+1]
     EH_HD constexpr int npart_dw() const { return nblocks() * 16; }
+    EH_HD constexpr int nlast() const { return LR ? rup4(NOUT * (H + 1)) : 0; }
+    EH_HD constexpr int off_last() const { return npart_dw() + MAXT + MAXPS; }
+    EH_HD constexpr int npart() const { return off_last() + nlast(); }
 };
 
 // parameter block in device memory: [nflat theta/phi | MAXPS uniform slot values | MAXPS*4 derived

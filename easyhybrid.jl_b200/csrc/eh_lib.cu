@@ -79,9 +79,10 @@ struct eh_ctx {
     float *d_theta = nullptr, *d_m = nullptr, *d_v = nullptr, *d_grad = nullptr;
     OptState* d_ost = nullptr;
     // persistent epoch kernel
-    std::vector<int> h_inv, h_slot_of_flat;
-    int *d_inv = nullptr, *d_slot_of_flat = nullptr, *d_losskind = nullptr;
-    float *d_pbuf = nullptr, *d_pub = nullptr, *d_stats = nullptr;
+    std::vector<int> h_cells, h_slot_of_flat;
+    int *d_cells = nullptr, *d_slot_of_flat = nullptr, *d_losskind = nullptr;
+    float *d_pbuf = nullptr, *d_stats = nullptr;
+    int epoch_csize = 0, epoch_grid = 0, epoch_warps = 0;  // last persistent launch geometry
     unsigned* d_counter = nullptr;
     size_t stats_cap = 0;
     bool persist_ok = false;
@@ -472,48 +473,86 @@ eh_status ensure_pass_graph(eh_ctx* c, int64_t n, int64_t B, bool pdl)
     return EH_OK;
 }
 
-// Persistent path: all nsteps optimiser steps in ONE cooperative launch (eh_epoch_kernel.cuh).
+// Persistent path: all nsteps optimiser steps in ONE launch (eh_epoch_kernel.cuh).
+// Geometry: cluster size cs, grid G (multiple of cs, all co-resident), w warps per CTA.  A larger
+// cluster means fewer vectors through the grid barrier but (GPC granularity) fewer usable SMs.
 eh_status run_persistent(eh_ctx* c, int64_t n, int64_t B, int64_t first, int64_t nsteps, bool* used)
 {
     *used = false;
     const Variant* v = c->var;
     const int64_t nb = (n + B - 1) / B;
-    Geom g = step_geometry(c, B);
     const int npartp = rup4(v->NPART);
-    int SL = rup4((v->NPART + g.grid - 1) / g.grid);
-    size_t smem = g.smem + (size_t)5 * SL * sizeof(float);
-    if (smem > c->smem_optin) return EH_OK;  // does not fit: caller uses the two-kernel path
-    int per_sm = 0;
-    CK(v->epoch_max_grid(g.nwarps, smem, &per_sm));
-    if (per_sm < 1 || g.grid > per_sm * c->nsm) return EH_OK;
+    const size_t fixed = (size_t)(rup4(v->NW) + SS_FLOATS) * 4;
+    const size_t stage = (size_t)v->stage_floats * 4;
+    const size_t extra = ((size_t)2 * npartp + 8 * (size_t)rup4(c->nflat)) * 4 + 64;
+    const size_t smem_cap = c->smem_optin - 256;
+    if (fixed + extra + stage > smem_cap) return EH_OK;  // does not fit: two-kernel path
+    const int wcap = (int)std::min<size_t>((size_t)v->max_warps, (smem_cap - fixed - extra) / stage);
+    const int64_t nchunks = (B + CHUNK - 1) / CHUNK;
+    const char* ecs = getenv("EH_CLUSTER_SIZE");
+    const char* ew = getenv("EH_EPOCH_WARPS");
+    int best_cs = 0, best_G = 0, best_w = 0;
+    double best_cost = 1e30;
+    for (int cs : {8, 4, 2, 1}) {
+        if (ecs && atoi(ecs) != cs) continue;
+        int wtry = ew ? std::min(atoi(ew), wcap) : wcap;
+        if (wtry < 1) wtry = 1;
+        int max_ctas = 0;
+        size_t smem_try = fixed + extra + (size_t)wtry * stage;
+        if (v->epoch_max_grid(wtry, smem_try, cs, &max_ctas) != cudaSuccess) { cudaGetLastError(); continue; }
+        max_ctas = std::min(max_ctas, (c->nsm / cs) * cs);
+        if (max_ctas < cs) continue;
+        // fewest warps per CTA that still cover the batch in the fewest rounds
+        int64_t per_round = (int64_t)max_ctas * wtry;
+        int64_t rounds = (nchunks + per_round - 1) / per_round;
+        int w = ew ? wtry : (int)std::min<int64_t>(wtry, (nchunks + rounds * max_ctas - 1) / (rounds * max_ctas));
+        int G = (int)std::min<int64_t>(max_ctas, ((nchunks + (int64_t)w * rounds - 1) / ((int64_t)w * rounds) + cs - 1) / cs * cs);
+        if (G < cs) G = cs;
+        double cost = (double)rounds * w + 0.01 * (G / cs);  // compute ~ warps sharing an SM; exchange ~ vectors
+        if (cost < best_cost) { best_cost = cost; best_cs = cs; best_G = G; best_w = w; }
+    }
+    if (!best_cs) return EH_OK;
+    const int cs = best_cs, G = best_G, w = best_w;
+    const size_t smem = fixed + extra + (size_t)w * stage;
     if ((size_t)nsteps > c->stats_cap) {
         if (c->d_stats) cudaFree(c->d_stats);
         c->d_stats = nullptr; c->stats_cap = 0;
         CK(dalloc(&c->d_stats, (size_t)nsteps * MAXT));
         c->stats_cap = (size_t)nsteps;
     }
-    const size_t pb = ((size_t)c->nflat + PARAM_TAIL) * sizeof(float);
     CK(cudaMemsetAsync(c->d_counter, 0, 4 * sizeof(unsigned), c->stream));
-    CK(cudaMemcpyAsync(c->d_pub, c->d_theta, pb, cudaMemcpyDeviceToDevice, c->stream));
-    CK(cudaMemcpyAsync(c->d_pub + c->nflat + PARAM_TAIL, c->d_theta, pb, cudaMemcpyDeviceToDevice, c->stream));
     EpochArgs a;
     memset(&a, 0, sizeof a);
     a.rec = reinterpret_cast<const float4*>(c->split[EH_SPLIT_TRAIN].rec);
     a.idx = c->d_idx; a.n = n; a.B = (int)B; a.first_step = first; a.nsteps = (int)nsteps; a.nb = (int)nb;
     a.pblock = c->d_theta; a.nflat = c->nflat; a.ntheta = c->ntheta;
     a.m = c->d_m; a.v = c->d_v; a.ost = c->d_ost;
-    a.wsrc = c->d_wsrc; a.inv = c->d_inv; a.pspan = c->d_pspan; a.slot_of_flat = c->d_slot_of_flat;
-    a.bscal = c->d_bscal; a.pbuf = c->d_pbuf; a.pub = c->d_pub; a.counter = c->d_counter; a.stats_out = c->d_stats;
-    a.npartp = npartp; a.SL = SL; a.T = c->n_targ;
+    a.wsrc = c->d_wsrc; a.pmap = c->d_pmap; a.cells = c->d_cells; a.pspan = c->d_pspan; a.slot_of_flat = c->d_slot_of_flat;
+    a.bscal = c->d_bscal; a.pbuf = c->d_pbuf; a.counter = c->d_counter; a.stats_out = c->d_stats;
+    a.npartp = npartp; a.csize = cs; a.T = c->n_targ; a.agg_mean = c->agg_mean;
     for (int t = 0; t < MAXT; t++) a.loss_kind[t] = c->loss_kind[t];
     for (int s = 0; s < MAXPS; s++) a.slot[s] = c->slots[s];
     for (int i = 0; i < 4; i++) a.pmc[i] = c->pmc[i];
     a.use_bn = c->use_bn; a.pm_id = c->pm_id;
     a.opt_kind = c->opt_kind; a.adamw_coupled = c->adamw_coupled;
     a.eta = c->eta; a.beta1 = c->beta1; a.beta2 = c->beta2; a.eps = c->eps; a.lambda = c->lambda;
+    long long* d_dbg = nullptr;
+    const char* dbg_path = getenv("EH_EPOCH_DEBUG");
+    if (dbg_path && nsteps <= 64) {
+        CK(dalloc(&d_dbg, (size_t)nsteps * G * 32));
+        CK(cudaMemsetAsync(d_dbg, 0, (size_t)nsteps * G * 32 * sizeof(long long), c->stream));
+        a.dbg = d_dbg;
+    }
     CK(cudaEventRecord(c->ev0, c->stream));
-    CK(v->launch_epoch(a, g.grid, g.nwarps, smem, c->stream));
+    cudaError_t le = v->launch_epoch(a, G, w, smem, cs, c->stream);
+    if (le != cudaSuccess) {
+        // e.g. cooperative + cluster launch refused: fall back to the two-kernel path
+        cudaGetLastError();
+        c->err = std::string("persistent launch refused: ") + cudaGetErrorString(le);
+        return EH_OK;
+    }
     CK(cudaEventRecord(c->ev1, c->stream));
+    c->epoch_csize = cs; c->epoch_grid = G; c->epoch_warps = w;
     k_losses_from_stats<<<(unsigned)((nsteps + 127) / 128), 128, 0, c->stream>>>(c->d_stats, c->d_bscal, first, (int)nb,
                                                                                  (int)nsteps, c->n_targ, c->agg_mean,
                                                                                  c->d_losskind, c->d_loss);
@@ -521,6 +560,17 @@ eh_status run_persistent(eh_ctx* c, int64_t n, int64_t B, int64_t first, int64_t
     CK(cudaMemcpyAsync(c->h_loss, c->d_loss, (size_t)nsteps * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+    if (d_dbg) {
+        std::vector<long long> h((size_t)nsteps * G * 32);
+        CK(cudaMemcpy(h.data(), d_dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        cudaFree(d_dbg);
+        if (FILE* f = fopen(dbg_path, "wb")) {
+            long long hdr[4] = {nsteps, G, w, cs};
+            fwrite(hdr, sizeof hdr, 1, f);
+            fwrite(h.data(), sizeof(long long), h.size(), f);
+            fclose(f);
+        }
+    }
     c->last_launches = 1;
     c->last_step_ms = c->last_ms;
     *used = true;
@@ -715,6 +765,14 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
     c->h_pmap.assign((size_t)c->nflat, 0);
     c->h_pspan.assign((size_t)c->nflat, 0.f);
     for (int l = 1; l <= L; l++) {
+        if (l == L && D.LR) {
+            // output layer kept in registers: [NOUT][H+1] block behind the statistics
+            for (int j = 0; j < width[l]; j++) {
+                for (int k = 0; k < width[l - 1]; k++) c->h_pmap[w_off[l - 1] + j + k * width[l]] = D.off_last() + j * (H + 1) + k;
+                c->h_pmap[b_off[l - 1] + j] = D.off_last() + j * (H + 1) + H;
+            }
+            continue;
+        }
         const int nk = D.nk(l), b0 = D.blk0(l);
         for (int j = 0; j < width[l]; j++) {
             for (int k = 0; k < width[l - 1]; k++)
@@ -732,15 +790,16 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
         c->h_pspan[off + g] = span;
     }
 
-    // inverse maps for the persistent kernel: partial index -> flat parameter, phi entry -> slot
-    c->h_inv.assign((size_t)v->NPART, -1);
+    // tables for the persistent kernel: flat parameter -> image cells, phi entry -> slot
+    c->h_cells.assign((size_t)2 * c->nflat, -1);
+    for (int i = 0; i < v->NW; i++) {
+        int p = c->h_wsrc[i];
+        if (p < 0) continue;
+        if (c->h_cells[2 * p] < 0) c->h_cells[2 * p] = i;
+        else c->h_cells[2 * p + 1] = i;
+    }
     c->h_slot_of_flat.assign((size_t)c->nflat, -1);
     c->persist_ok = true;
-    for (int p = 0; p < c->nflat; p++) {
-        int q = c->h_pmap[p];
-        if (c->h_inv[q] >= 0) c->persist_ok = false;  // two parameters share a cell (unused global): two-kernel path only
-        c->h_inv[q] = p;
-    }
     for (int g = 0; g < ng; g++)
         for (int s = 0; s < v->NPS; s++)
             if (c->slots[s].role == ROLE_GLOBAL && c->slots[s].idx == g) c->h_slot_of_flat[off + g] = s;
@@ -768,7 +827,7 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
         if (lk == EH_LOSS_RMSE) n_rmse++;
     }
     if (n_rmse && d->n_targ > 1) return fail(c, EH_EUNSUPPORTED, "rmse training loss with more than one target");
-    if (n_rmse) c->persist_ok = false;  // the rmse post-scale needs the reduced SSE before the update
+
     c->agg_mean = d->agg == EH_AGG_MEAN;
     c->opt_kind = d->opt_kind;
     if (c->opt_kind < 0 || c->opt_kind > 3) return fail(c, EH_EINVAL, "opt_kind=%d unknown", d->opt_kind);
@@ -907,7 +966,7 @@ eh_status eh_create(eh_ctx** out, const eh_model_desc* desc)
         size_t stage = (size_t)v->stage_floats * 4;
         int wmax = (int)std::min<size_t>((size_t)v->max_warps, (c->smem_optin - fixed - 8192) / stage);
         if (wmax < 1) return fail(c, EH_EUNSUPPORTED, "variant %s needs %zu B of shared memory per warp", v->name, stage);
-        CK(v->prepare(fixed + (size_t)wmax * stage + 8192, fixed));
+        CK(v->prepare(c->smem_optin - 256, fixed));  // kernels carry a few bytes of static shared memory
         CK(dalloc(&c->d_wsrc, c->h_wsrc.size()));
         CK(dalloc(&c->d_pmap, c->h_pmap.size()));
         CK(dalloc(&c->d_pspan, c->h_pspan.size()));
@@ -915,14 +974,13 @@ eh_status eh_create(eh_ctx** out, const eh_model_desc* desc)
         CK(cudaMemcpy(c->d_pmap, c->h_pmap.data(), c->h_pmap.size() * sizeof(int), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(c->d_pspan, c->h_pspan.data(), c->h_pspan.size() * sizeof(float), cudaMemcpyHostToDevice));
         CK(dalloc(&c->d_theta, (size_t)c->nflat + PARAM_TAIL));
-        CK(dalloc(&c->d_inv, c->h_inv.size()));
+        CK(dalloc(&c->d_cells, c->h_cells.size()));
         CK(dalloc(&c->d_slot_of_flat, c->h_slot_of_flat.size()));
         CK(dalloc(&c->d_losskind, (size_t)MAXT));
-        CK(cudaMemcpy(c->d_inv, c->h_inv.data(), c->h_inv.size() * sizeof(int), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(c->d_cells, c->h_cells.data(), c->h_cells.size() * sizeof(int), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(c->d_slot_of_flat, c->h_slot_of_flat.data(), c->h_slot_of_flat.size() * sizeof(int), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(c->d_losskind, c->loss_kind, MAXT * sizeof(int), cudaMemcpyHostToDevice));
         CK(dalloc(&c->d_pbuf, (size_t)2 * (c->nsm + 8) * rup4(v->NPART)));
-        CK(dalloc(&c->d_pub, (size_t)2 * (c->nflat + PARAM_TAIL)));
         CK(dalloc(&c->d_counter, (size_t)4));
         CK(dalloc(&c->d_m, (size_t)c->nflat));
         CK(dalloc(&c->d_v, (size_t)c->nflat));
@@ -950,7 +1008,7 @@ void eh_destroy(eh_ctx* c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->gexec) cudaGraphExecDestroy(c->gexec);
     void* ptrs[] = {c->d_wsrc, c->d_pmap, c->d_pspan, c->d_theta, c->d_m, c->d_v, c->d_grad, c->d_ost, c->d_partial,
-                    c->d_gvec, c->d_inv, c->d_slot_of_flat, c->d_losskind, c->d_pbuf, c->d_pub, c->d_stats, c->d_counter, c->d_bscal, c->d_bn_batch, c->d_idx, c->d_idx64, c->d_err, c->d_loss, c->d_evalpart,
+                    c->d_gvec, c->d_cells, c->d_slot_of_flat, c->d_losskind, c->d_pbuf, c->d_stats, c->d_counter, c->d_bscal, c->d_bn_batch, c->d_idx, c->d_idx64, c->d_err, c->d_loss, c->d_evalpart,
                     c->d_bn_test, c->split[0].rec, c->split[1].rec};
     for (void* p : ptrs)
         if (p) cudaFree(p);

@@ -94,6 +94,8 @@ __global__ void __launch_bounds__(512, 1) k_step(const StepArgs a)
     for (int t = 0; t < MAXT; t++) st.loss[t] = 0.f;
 #pragma unroll
     for (int s = 0; s < MAXPS; s++) st.gphi[s] = 0.f;
+    LastAcc<C> la;
+    la.zero();
 
     for (; chunk < nchunks; chunk += GW) {
         float rec[C::R4];
@@ -103,13 +105,13 @@ __global__ void __launch_bounds__(512, 1) k_step(const StepArgs a)
         }
         const bool v = valid;
         fetch_record<C>(a.rec, a.idx, a.rec_base, a.B, chunk + GW, nchunks, lane, r, valid);  // prefetch
-        chunk_sample_phase<C>(rec, v, sW, sS, stage, lane, a.slot, a.loss_kind, cx, st);
+        chunk_sample_phase<C>(rec, v, sW, sS, stage, lane, a.slot, a.loss_kind, cx, st, la);
         __syncwarp();
         chunk_dw_phase<C>(stage, lane, rowD, rowA, acc);
         __syncwarp();
     }
     __syncthreads();  // every warp is done with its staging tile; reuse it as [nwarps][NPART]
-    cta_reduce<C>(acc, st, sS + SS_FLOATS, a.partial + (size_t)blockIdx.x * a.npart, 1);
+    cta_reduce<C>(acc, st, la, sS + SS_FLOATS, a.partial + (size_t)blockIdx.x * a.npart, 1);
 }
 
 }  // namespace eh

@@ -323,7 +323,7 @@ __global__ void k_losses_from_stats(const float* stats, const float* bscal, long
         float n = bs[BS_N + t], ss = bs[BS_SS + t], acc = stats[(size_t)s * MAXT + t];
         ntot += n;
         int lk = loss_kind_dev[t];
-        L += (lk == LOSS_NSELOSS) ? acc / ss : acc / n;
+        L += (lk == LOSS_NSELOSS) ? acc / ss : (lk == LOSS_RMSE ? sqrtf(acc / n) : acc / n);
     }
     if (agg_mean) L /= (float)T;
     loss_out[s] = ntot == 0.f ? __int_as_float(0x7fc00000) : L;

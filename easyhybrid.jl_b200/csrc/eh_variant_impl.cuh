@@ -39,18 +39,67 @@ static cudaError_t launch_eval_t(const EvalArgs& a, int grid, int nwarps, size_t
     return cudaGetLastError();
 }
 
-// cooperative launch: the grid barrier inside k_epoch needs every CTA resident
+// k_epoch: thread-block clusters (DSMEM pre-reduction) + cooperative launch (the grid barrier needs
+// every CTA resident).  csize = 1 launches without a cluster attribute.
 template <class C>
-static cudaError_t launch_epoch_t(const EpochArgs& a, int grid, int nwarps, size_t smem, cudaStream_t st)
+static void epoch_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int grid, int nwarps, size_t smem, int csize,
+                      cudaStream_t st)
 {
-    void* args[] = {(void*)&a};
-    return cudaLaunchCooperativeKernel((void*)k_epoch<C>, dim3((unsigned)grid), dim3((unsigned)(nwarps * 32)), args, smem, st);
+    cfg = cudaLaunchConfig_t{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)(nwarps * 32));
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    int n = 0;
+    attr[n].id = cudaLaunchAttributeCooperative;
+    attr[n].val.cooperative = 1;
+    n++;
+    if (csize > 1) {
+        attr[n].id = cudaLaunchAttributeClusterDimension;
+        attr[n].val.clusterDim.x = (unsigned)csize;
+        attr[n].val.clusterDim.y = 1;
+        attr[n].val.clusterDim.z = 1;
+        n++;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = n;
 }
 
 template <class C>
-static cudaError_t epoch_max_grid_t(int nwarps, size_t smem, int* blocks_per_sm)
+static cudaError_t launch_epoch_t(const EpochArgs& a, int grid, int nwarps, size_t smem, int csize, cudaStream_t st)
 {
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_epoch<C>, nwarps * 32, smem);
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[2];
+    epoch_cfg<C>(cfg, attr, grid, nwarps, smem, csize, st);
+    return cudaLaunchKernelEx(&cfg, k_epoch<C>, a);
+}
+
+// how many CTAs of this shape can be co-resident (in clusters of csize)
+template <class C>
+static cudaError_t epoch_max_grid_t(int nwarps, size_t smem, int csize, int* max_ctas)
+{
+    if (csize > 1) {
+        cudaLaunchConfig_t cfg;
+        cudaLaunchAttribute attr[2];
+        epoch_cfg<C>(cfg, attr, csize, nwarps, smem, csize, nullptr);
+        cfg.numAttrs = 2;
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)csize;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.numAttrs = 1;
+        int ncl = 0;
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&ncl, k_epoch<C>, &cfg);
+        *max_ctas = ncl * csize;
+        return e;
+    }
+    int per_sm = 0, dev = 0, nsm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_epoch<C>, nwarps * 32, smem);
+    if (e != cudaSuccess) return e;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    *max_ctas = per_sm * nsm;
+    return cudaSuccess;
 }
 
 template <class C>

@@ -17,8 +17,8 @@ struct Variant {
     cudaError_t (*prepare)(size_t step_smem, size_t eval_smem);
     cudaError_t (*launch_step)(const StepArgs& a, int grid, int nwarps, size_t smem, cudaStream_t st, bool pdl);
     cudaError_t (*launch_eval)(const EvalArgs& a, int grid, int nwarps, size_t smem, cudaStream_t st);
-    cudaError_t (*launch_epoch)(const EpochArgs& a, int grid, int nwarps, size_t smem, cudaStream_t st);
-    cudaError_t (*epoch_max_grid)(int nwarps, size_t smem, int* blocks_per_sm);
+    cudaError_t (*launch_epoch)(const EpochArgs& a, int grid, int nwarps, size_t smem, int csize, cudaStream_t st);
+    cudaError_t (*epoch_max_grid)(int nwarps, size_t smem, int csize, int* max_ctas);
 };
 
 const Variant* find_variant(int pm, int P, int NH, int H, int NOUT, int act, int scale);

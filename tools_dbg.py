@@ -1,0 +1,18 @@
+"""Decode the EH_EPOCH_DEBUG timestamp dump of the persistent kernel (SM clocks per phase)."""
+import sys
+import numpy as np
+raw = np.fromfile(sys.argv[1], dtype=np.int64)
+nsteps, G, w, cs = raw[:4]
+d = raw[4:].reshape(nsteps, G, 32)
+names = ["scalars+sync", "compute(thread0 warp)", "cta_reduce", "cluster_sync", "dsmem gather+publish", "grid barrier", "read+adam+init"]
+print(f"steps {nsteps} grid {G} warps {w} cluster {cs}")
+for s in range(1, nsteps):
+    t = d[s, :, :8].astype(np.float64)
+    ph = np.diff(t, axis=1)                       # 7 phases per CTA
+    wend = d[s, :, 8:8 + w].astype(np.float64) - t[:, 1:2]   # per-warp compute time since phase-1 stamp
+    tot = (d[s, :, 7] - d[s, :, 0]).astype(np.float64)
+    if s in (1, nsteps // 2, nsteps - 1):
+        print(f"step {s}: total cycles median {np.median(tot):.0f} max {tot.max():.0f}")
+        for i, nme in enumerate(names):
+            print(f"   {nme:28s} median {np.median(ph[:, i]):8.0f}  min {ph[:, i].min():8.0f}  max {ph[:, i].max():8.0f}")
+        print(f"   per-warp compute: median {np.median(wend):.0f} min {wend.min():.0f} max {wend.max():.0f}; per-CTA slowest warp median {np.median(wend.max(axis=1)):.0f}")
