@@ -31,6 +31,7 @@ OPS = {
 EH_FLAG_NO_GRAPH = 1
 EH_FLAG_NO_PDL = 2
 EH_FLAG_NO_PERSIST = 4
+EH_FLAG_TENSOR_PIPE = 16
 EH_SPLIT_TRAIN, EH_SPLIT_VAL = 0, 1
 EH_EVAL_STATS = 9
 EH_COMM_ID_BYTES = 128

@@ -238,6 +238,14 @@ __device__ __forceinline__ void tile_rows(int lane, int* rowD, int* rowA)
     }
 }
 
+// where a batch's samples come from
+struct FetchArgs {
+    const float4* rec;
+    const int* idx;       // NULL: records rec_base .. rec_base + B
+    long long rec_base;
+    int B, nchunks;
+};
+
 struct ChunkStats {
     float loss[MAXT];    // sum r^2 (or |r|) per target
     float gphi[MAXPS];   // sum g * dy/dslot for GLOBAL slots

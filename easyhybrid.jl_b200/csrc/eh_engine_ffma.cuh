@@ -1,0 +1,89 @@
+// eh_engine_ffma.cuh -- compute engine 0: exact-fp32 FFMA2 path (eh_chunk.cuh) behind the engine
+// interface used by k_step / k_epoch.  A lane owns one sample; weights are broadcast from shared memory.
+#pragma once
+#include "eh_chunk.cuh"
+
+namespace eh {
+
+template <class C>
+struct EngFfma {
+    using Cfg = C;
+    static constexpr int ENGINE = 0;
+    static constexpr int STAGE_FLOATS = C::STAGE_FLOATS;  // per-warp shared memory
+    static constexpr int NPART = C::NPART;
+    static constexpr int OFF_STATS = C::D.npart_dw();
+    static constexpr int MAX_WARPS = 16;
+
+    struct State {
+        float2 acc[C::NBI][16];
+        ChunkStats st;
+        LastAcc<C> la;
+        int rowD[C::NBI], rowA[C::NBI];
+        float4 r[C::R4 / 4];
+        bool valid;
+    };
+
+    __device__ __forceinline__ static void init_warp(State& s, float* stage, int lane)
+    {
+        init_stage_rows<C>(stage, lane);
+        tile_rows<C>(lane, s.rowD, s.rowA);
+    }
+    __device__ __forceinline__ static void after_reduce(State& s, float* stage, int lane) { init_stage_rows<C>(stage, lane); }
+    __device__ __forceinline__ static void step_begin(State& s, const float* sW, int lane)
+    {
+#pragma unroll
+        for (int i = 0; i < C::NBI; i++)
+#pragma unroll
+            for (int e = 0; e < 16; e++) s.acc[i][e] = f2s(0.f);
+#pragma unroll
+        for (int t = 0; t < MAXT; t++) s.st.loss[t] = 0.f;
+#pragma unroll
+        for (int t = 0; t < MAXPS; t++) s.st.gphi[t] = 0.f;
+        s.la.zero();
+    }
+    // prefetch the records of chunk `chunk` of the batch (idx + its base already applied by the caller)
+    __device__ __forceinline__ static void fetch(State& s, const float4* rec, const int* idx, long long rec_base, int B,
+                                                 int chunk, int nchunks, int lane)
+    {
+        const int smp = chunk * CHUNK + lane;
+        s.valid = chunk < nchunks && smp < B;
+        long long i = rec_base + smp;
+        if (idx && s.valid) i = idx[smp];
+#pragma unroll
+        for (int q = 0; q < C::R4 / 4; q++)
+            s.r[q] = s.valid ? __ldg(rec + i * (C::R4 / 4) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    // consume the prefetched records (the caller issues the next fetch right after `take`)
+    struct Taken {
+        float rec[C::R4];
+        bool valid;
+    };
+    __device__ __forceinline__ static void take(const State& s, Taken& t)
+    {
+#pragma unroll
+        for (int q = 0; q < C::R4 / 4; q++) {
+            t.rec[4 * q] = s.r[q].x; t.rec[4 * q + 1] = s.r[q].y; t.rec[4 * q + 2] = s.r[q].z; t.rec[4 * q + 3] = s.r[q].w;
+        }
+        t.valid = s.valid;
+    }
+    // process the prefetched chunk; `next` (chunk index, may be past the end) is prefetched right after the
+    // current records have been copied out, so its latency hides behind the compute
+    __device__ __forceinline__ static void chunk(State& s, const FetchArgs& fa, int next, const float* sW, const float* sS,
+                                                 float* stage, int lane, const PSlot* slot, const int* loss_kind,
+                                                 const PmCtx& cx)
+    {
+        Taken t;
+        take(s, t);
+        fetch(s, fa.rec, fa.idx, fa.rec_base, fa.B, next, fa.nchunks, lane);
+        chunk_sample_phase<C>(t.rec, t.valid, sW, sS, stage, lane, slot, loss_kind, cx, s.st, s.la);
+        __syncwarp();
+        chunk_dw_phase<C>(stage, lane, s.rowD, s.rowA, s.acc);
+        __syncwarp();
+    }
+    __device__ __forceinline__ static void reduce(State& s, float* scratch, float* out, int out_is_global)
+    {
+        cta_reduce<C>(s.acc, s.st, s.la, scratch, out, out_is_global);
+    }
+};
+
+}  // namespace eh

@@ -41,6 +41,7 @@ struct EpochArgs {
     unsigned* counter;         // grid barrier arrival counter (zeroed before launch)
     float* stats_out;          // [nsteps][MAXT] reduced loss sums
     int npartp;                // padded partial length (multiple of 4)
+    int work_floats;           // size of the per-CTA work region (staging / scratch / vector landing zone)
     int csize;                 // cluster size (1, 2, 4, 8)
     int T, agg_mean;
     int loss_kind[MAXT];
@@ -73,25 +74,26 @@ __device__ __forceinline__ float ld_dsmem(const float* local, unsigned rank)
     return v;
 }
 
-template <class C>
+template <class E>
 __host__ __device__ constexpr int epoch_extra_floats(int nflat)
 {
     // cpart + red (padded partial vectors) + theta, m, v copies + tables (pmap, 2 cells, span, slot)
-    return 2 * rup4(C::NPART) + 8 * rup4(nflat);
+    return 2 * rup4(E::NPART) + 8 * rup4(nflat);
 }
 
-template <class C>
-__global__ void __launch_bounds__(512, 1) k_epoch(const EpochArgs a)
+template <class E>
+__global__ void __launch_bounds__(E::MAX_WARPS * 32, 1) k_epoch(const EpochArgs a)
 {
+    using C = typename E::Cfg;
     extern __shared__ float4 smem4[];
     float* sW = reinterpret_cast<float*>(smem4);
     float* sS = sW + rup4(C::NW);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    float* stage0 = sS + SS_FLOATS;
-    float* stage = stage0 + warp * C::STAGE_FLOATS;
-    float* cpart = stage0 + nwarps * C::STAGE_FLOATS;   // [npartp] this CTA's partial vector
-    float* red = cpart + rup4(C::NPART);                // [npartp] fully reduced vector
-    float* s_th = red + rup4(C::NPART);                 // [nflat] replicated parameters
+    float* stage0 = sS + SS_FLOATS;                      // work region: staging tiles / reduction scratch / vectors
+    float* stage = stage0 + warp * E::STAGE_FLOATS;
+    float* cpart = stage0 + a.work_floats;               // [npartp] this CTA's partial vector
+    float* red = cpart + rup4(E::NPART);                 // [npartp] fully reduced vector
+    float* s_th = red + rup4(E::NPART);                  // [nflat] replicated parameters
     float* s_m = s_th + rup4(a.nflat);
     float* s_v = s_m + rup4(a.nflat);
     int* t_pmap = reinterpret_cast<int*>(s_v + rup4(a.nflat));
@@ -120,9 +122,8 @@ __global__ void __launch_bounds__(512, 1) k_epoch(const EpochArgs a)
     float b1t = a.ost->b1t, b2t = a.ost->b2t;
     long long tdone = 0, tskip = 0;
 
-    init_stage_rows<C>(stage, lane);
-    int rowD[C::NBI], rowA[C::NBI];
-    tile_rows<C>(lane, rowD, rowA);
+    typename E::State st;
+    E::init_warp(st, stage, lane);
     load_weights_and_scalars<C>(a.pblock, a.nflat, a.wsrc, nullptr, 0, sW, sS);
 
     PmCtx cx;
@@ -136,13 +137,11 @@ __global__ void __launch_bounds__(512, 1) k_epoch(const EpochArgs a)
     const int GW = G * nwarps;
     // chunk -> warp assignment interleaves CTAs so that a ragged chunk count spreads over all SMs
     const int gw = warp * G + blockIdx.x;
-    float4 r[C::R4 / 4];
-    bool valid;
     {
         long long b = a.first_step % a.nb;
         long long rem = a.n - b * a.B;
         int Bk = (int)(rem < a.B ? rem : a.B);
-        fetch_record<C>(a.rec, a.idx + b * a.B, 0, Bk, gw, (Bk + CHUNK - 1) / CHUNK, lane, r, valid);
+        E::fetch(st, a.rec, a.idx + b * a.B, 0, Bk, gw, (Bk + CHUNK - 1) / CHUNK, lane);
     }
     unsigned bar = 0;
     // per-batch scalars of the coming step, prefetched one step ahead (a dependent global load otherwise)
@@ -172,51 +171,29 @@ __global__ void __launch_bounds__(512, 1) k_epoch(const EpochArgs a)
         if (s + 1 < a.nsteps) prefetch_bs(s + 1);
         EH_STAMP(1)
 
-        float2 acc[C::NBI][16];
-#pragma unroll
-        for (int i = 0; i < C::NBI; i++)
-#pragma unroll
-            for (int e = 0; e < 16; e++) acc[i][e] = f2s(0.f);
-        ChunkStats st;
-#pragma unroll
-        for (int t = 0; t < MAXT; t++) st.loss[t] = 0.f;
-#pragma unroll
-        for (int t = 0; t < MAXPS; t++) st.gphi[t] = 0.f;
-        LastAcc<C> la;
-        la.zero();
-
-        for (int chunk = gw; chunk < nchunks; chunk += GW) {
-            float rec[C::R4];
-#pragma unroll
-            for (int q = 0; q < C::R4 / 4; q++) {
-                rec[4 * q] = r[q].x; rec[4 * q + 1] = r[q].y; rec[4 * q + 2] = r[q].z; rec[4 * q + 3] = r[q].w;
-            }
-            const bool v = valid;
-            fetch_record<C>(a.rec, a.idx + b * a.B, 0, Bk, chunk + GW, nchunks, lane, r, valid);
-            chunk_sample_phase<C>(rec, v, sW, sS, stage, lane, a.slot, a.loss_kind, cx, st, la);
-            __syncwarp();
-            chunk_dw_phase<C>(stage, lane, rowD, rowA, acc);
-            __syncwarp();
-        }
+        E::step_begin(st, sW, lane);
+        const FetchArgs fa{a.rec, a.idx + b * a.B, 0, Bk, nchunks};
+        for (int chunk = gw; chunk < nchunks; chunk += GW)
+            E::chunk(st, fa, chunk + GW, sW, sS, stage, lane, a.slot, a.loss_kind, cx);
         if (a.dbg && lane == 0) a.dbg[((size_t)s * G + blockIdx.x) * 32 + 8 + warp] = clock64();
         // prefetch my first sample of the next step: its latency hides behind the exchange below
         if (s + 1 < a.nsteps) {
             long long b2 = (a.first_step + s + 1) % a.nb;
             long long rem2 = a.n - b2 * a.B;
             int Bk2 = (int)(rem2 < a.B ? rem2 : a.B);
-            fetch_record<C>(a.rec, a.idx + b2 * a.B, 0, Bk2, gw, (Bk2 + CHUNK - 1) / CHUNK, lane, r, valid);
+            E::fetch(st, a.rec, a.idx + b2 * a.B, 0, Bk2, gw, (Bk2 + CHUNK - 1) / CHUNK, lane);
         }
         __syncthreads();
         EH_STAMP(2)
         // CTA partial -> cpart (the scratch of cta_reduce aliases the staging tiles)
-        cta_reduce<C>(acc, st, la, stage0, cpart, 0);
+        E::reduce(st, stage0, cpart, 0);
         EH_STAMP(3)
         if (cs > 1) cluster_sync_all(); else __syncthreads();
         EH_STAMP(4)
         if (crank == 0) {
             // cluster vector: ranks summed in order over DSMEM, published for the whole grid
             float* dst = a.pbuf + ((size_t)par * NC + cid) * a.npartp;
-            for (int p = threadIdx.x; p < C::NPART; p += blockDim.x) {
+            for (int p = threadIdx.x; p < E::NPART; p += blockDim.x) {
                 float sum = cpart[p];
                 for (int rk = 1; rk < cs; rk++) sum += ld_dsmem(cpart + p, (unsigned)rk);
                 __stcg(dst + p, sum);
@@ -259,7 +236,7 @@ __global__ void __launch_bounds__(512, 1) k_epoch(const EpochArgs a)
             }
         }
         __syncthreads();
-        for (int p = threadIdx.x; p < C::NPART; p += blockDim.x) {
+        for (int p = threadIdx.x; p < E::NPART; p += blockDim.x) {
             float s0 = 0.f, s1 = 0.f;
             int c = 0;
             for (; c + 2 <= NC; c += 2) {
@@ -274,12 +251,12 @@ __global__ void __launch_bounds__(512, 1) k_epoch(const EpochArgs a)
             float ntot = 0.f, post = 1.f;
             for (int t = 0; t < a.T; t++) {
                 ntot += sS[SS_NV + t];
-                if (a.loss_kind[t] == LOSS_RMSE) post = 1.f / (2.f * sqrtf(red[C::D.npart_dw() + t] / sS[SS_NV + t]));
+                if (a.loss_kind[t] == LOSS_RMSE) post = 1.f / (2.f * sqrtf(red[E::OFF_STATS + t] / sS[SS_NV + t]));
             }
             s_post = post;
             s_skip = (ntot == 0.f);  // all-masked batch: epoch.jl:17-19
             if (blockIdx.x == 0)
-                for (int t = 0; t < MAXT; t++) a.stats_out[(size_t)s * MAXT + t] = red[C::D.npart_dw() + t];
+                for (int t = 0; t < MAXT; t++) a.stats_out[(size_t)s * MAXT + t] = red[E::OFF_STATS + t];
         }
         __syncthreads();
         const bool skip = s_skip != 0;
@@ -331,7 +308,7 @@ __global__ void __launch_bounds__(512, 1) k_epoch(const EpochArgs a)
         } else {
             tskip++;
         }
-        init_stage_rows<C>(stage, lane);  // constant rows were overwritten by the reduction scratch
+        E::after_reduce(st, stage, lane);  // constant staging rows were overwritten by the scratch / vectors
         EH_STAMP(7)
     }
 #undef EH_STAMP

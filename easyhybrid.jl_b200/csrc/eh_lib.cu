@@ -221,7 +221,7 @@ Geom step_geometry(const eh_ctx* c, int64_t B)
 {
     const Variant* v = c->var;
     size_t fixed = (size_t)(rup4(v->NW) + SS_FLOATS) * 4;
-    size_t stage = (size_t)v->stage_floats * 4;
+    size_t stage = (size_t)std::max(v->stage_floats, v->NPART) * 4;  // staging tile, later one row of the reduction scratch
     int wmax = (int)std::min<size_t>((size_t)v->max_warps, (c->smem_optin - fixed - 8192) / stage);
     if (wmax < 1) wmax = 1;
     int64_t nchunks = (B + CHUNK - 1) / CHUNK;
@@ -259,7 +259,7 @@ void fill_update_args(const eh_ctx* c, UpdateArgs& u)
     memset(&u, 0, sizeof u);
     u.partial = c->d_partial;
     u.npart = c->var->NPART;
-    u.npart_dw = c->var->dims.npart_dw();
+    u.npart_dw = c->var->off_stats;
     u.gvec = c->d_gvec;
     u.mode = UPD_FULL;
     u.apply = 1;
@@ -483,22 +483,26 @@ eh_status run_persistent(eh_ctx* c, int64_t n, int64_t B, int64_t first, int64_t
     const int64_t nb = (n + B - 1) / B;
     const int npartp = rup4(v->NPART);
     const size_t fixed = (size_t)(rup4(v->NW) + SS_FLOATS) * 4;
-    const size_t stage = (size_t)v->stage_floats * 4;
+    const size_t stage = (size_t)std::max(v->stage_floats, v->NPART) * 4;
     const size_t extra = ((size_t)2 * npartp + 8 * (size_t)rup4(c->nflat)) * 4 + 64;
     const size_t smem_cap = c->smem_optin - 256;
     if (fixed + extra + stage > smem_cap) return EH_OK;  // does not fit: two-kernel path
-    const int wcap = (int)std::min<size_t>((size_t)v->max_warps, (smem_cap - fixed - extra) / stage);
     const int64_t nchunks = (B + CHUNK - 1) / CHUNK;
     const char* ecs = getenv("EH_CLUSTER_SIZE");
     const char* ew = getenv("EH_EPOCH_WARPS");
     int best_cs = 0, best_G = 0, best_w = 0;
+    size_t best_work = 0;
     double best_cost = 1e30;
     for (int cs : {8, 4, 2, 1}) {
         if (ecs && atoi(ecs) != cs) continue;
+        // the work region also receives the NC published vectors: NC <= nsm / cs
+        const size_t vec_bytes = (size_t)(c->nsm / cs) * npartp * 4;
+        if (fixed + extra + std::max(stage, vec_bytes) > smem_cap) continue;
+        int wcap = (int)std::min<size_t>((size_t)v->max_warps, (smem_cap - fixed - extra) / stage);
         int wtry = ew ? std::min(atoi(ew), wcap) : wcap;
         if (wtry < 1) wtry = 1;
         int max_ctas = 0;
-        size_t smem_try = fixed + extra + (size_t)wtry * stage;
+        size_t smem_try = fixed + extra + std::max((size_t)wtry * stage, vec_bytes);
         if (v->epoch_max_grid(wtry, smem_try, cs, &max_ctas) != cudaSuccess) { cudaGetLastError(); continue; }
         max_ctas = std::min(max_ctas, (c->nsm / cs) * cs);
         if (max_ctas < cs) continue;
@@ -508,12 +512,17 @@ eh_status run_persistent(eh_ctx* c, int64_t n, int64_t B, int64_t first, int64_t
         int w = ew ? wtry : (int)std::min<int64_t>(wtry, (nchunks + rounds * max_ctas - 1) / (rounds * max_ctas));
         int G = (int)std::min<int64_t>(max_ctas, ((nchunks + (int64_t)w * rounds - 1) / ((int64_t)w * rounds) + cs - 1) / cs * cs);
         if (G < cs) G = cs;
-        double cost = (double)rounds * w + 0.01 * (G / cs);  // compute ~ warps sharing an SM; exchange ~ vectors
-        if (cost < best_cost) { best_cost = cost; best_cs = cs; best_G = G; best_w = w; }
+        // compute ~ chunks an SM has to work through; exchange ~ vectors every CTA reads
+        // cycles, calibrated with EH_EPOCH_DEBUG: ~920 per chunk an SM works through, ~110 per vector read
+        double cost = 920.0 * (double)((nchunks + G - 1) / G) + 110.0 * (G / cs);
+        if (cost < best_cost) {
+            best_cost = cost; best_cs = cs; best_G = G; best_w = w;
+            best_work = std::max((size_t)w * stage, (size_t)(G / cs) * npartp * 4);
+        }
     }
     if (!best_cs) return EH_OK;
     const int cs = best_cs, G = best_G, w = best_w;
-    const size_t smem = fixed + extra + (size_t)w * stage;
+    const size_t smem = fixed + extra + best_work;
     if ((size_t)nsteps > c->stats_cap) {
         if (c->d_stats) cudaFree(c->d_stats);
         c->d_stats = nullptr; c->stats_cap = 0;
@@ -529,7 +538,7 @@ eh_status run_persistent(eh_ctx* c, int64_t n, int64_t B, int64_t first, int64_t
     a.m = c->d_m; a.v = c->d_v; a.ost = c->d_ost;
     a.wsrc = c->d_wsrc; a.pmap = c->d_pmap; a.cells = c->d_cells; a.pspan = c->d_pspan; a.slot_of_flat = c->d_slot_of_flat;
     a.bscal = c->d_bscal; a.pbuf = c->d_pbuf; a.counter = c->d_counter; a.stats_out = c->d_stats;
-    a.npartp = npartp; a.csize = cs; a.T = c->n_targ; a.agg_mean = c->agg_mean;
+    a.npartp = npartp; a.work_floats = (int)(best_work / 4); a.csize = cs; a.T = c->n_targ; a.agg_mean = c->agg_mean;
     for (int t = 0; t < MAXT; t++) a.loss_kind[t] = c->loss_kind[t];
     for (int s = 0; s < MAXPS; s++) a.slot[s] = c->slots[s];
     for (int i = 0; i < 4; i++) a.pmc[i] = c->pmc[i];
@@ -679,8 +688,14 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
     for (int l = 0; l < ch.n_hidden; l++) hmax = std::max(hmax, ch.hidden[l]);
     if (d->n_pm_args != 3 || d->pm_args[0].kind != 0 || d->pm_args[1].kind != 0 || d->pm_args[2].kind != 1)
         return fail(c, EH_EINVAL, "built-in process models take (param, param, forcing) arguments");
-    const Variant* v = find_variant(d->process_model, ch.n_in, ch.n_hidden, rup4(hmax), ch.n_out, ch.activation,
-                                    d->scale_nn_outputs ? 1 : 0);
+    // engine 0 (exact-fp32 FFMA2) by default; engine 1 (tensor pipe, 3xTF32) on request where a variant exists
+    const Variant* v = nullptr;
+    if (d->flags & EH_FLAG_TENSOR_PIPE)
+        v = find_variant(d->process_model, ch.n_in, ch.n_hidden, rup4(hmax), ch.n_out, ch.activation,
+                         d->scale_nn_outputs ? 1 : 0, 1);
+    if (!v)
+        v = find_variant(d->process_model, ch.n_in, ch.n_hidden, rup4(hmax), ch.n_out, ch.activation,
+                         d->scale_nn_outputs ? 1 : 0, 0);
     if (!v)
         return fail(c, EH_EUNSUPPORTED,
                     "no fused kernel variant for process_model=%d n_in=%d hidden=%dx(<=%d) n_out=%d activation=%d scale_nn_outputs=%d",
@@ -764,7 +779,18 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
     // flat entry -> position in the partial vector
     c->h_pmap.assign((size_t)c->nflat, 0);
     c->h_pspan.assign((size_t)c->nflat, 0.f);
-    for (int l = 1; l <= L; l++) {
+    if (v->engine == 1) {
+        // padded-flat partial layout of the tensor-pipe engine (eh_engine_mma.cuh: O_W1 .. O_BO)
+        const int o_w1 = 0, o_b1 = H * P, o_w2 = o_b1 + H, o_b2 = o_w2 + H * H, o_wo = o_b2 + H, o_bo = o_wo + NOUT * H;
+        const int ow[3] = {o_w1, o_w2, o_wo}, ob[3] = {o_b1, o_b2, o_bo};
+        for (int l = 1; l <= L; l++)
+            for (int j = 0; j < width[l]; j++) {
+                for (int k = 0; k < width[l - 1]; k++)
+                    c->h_pmap[w_off[l - 1] + j + k * width[l]] = (l == L) ? ow[2] + j * H + k : ow[l - 1] + j + k * H;
+                c->h_pmap[b_off[l - 1] + j] = ob[l - 1] + j;
+            }
+    }
+    for (int l = 1; l <= L && v->engine == 0; l++) {
         if (l == L && D.LR) {
             // output layer kept in registers: [NOUT][H+1] block behind the statistics
             for (int j = 0; j < width[l]; j++) {
@@ -786,7 +812,7 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
         float span = 0.f;
         for (int s = 0; s < v->NPS; s++)
             if (c->slots[s].role == ROLE_GLOBAL && c->slots[s].idx == g) { slot = s; span = c->slots[s].span; }
-        c->h_pmap[off + g] = D.npart_dw() + MAXT + slot;
+        c->h_pmap[off + g] = v->off_stats + MAXT + slot;
         c->h_pspan[off + g] = span;
     }
 
@@ -963,7 +989,7 @@ eh_status eh_create(eh_ctx** out, const eh_model_desc* desc)
         CK(cudaEventCreate(&c->ev0));
         CK(cudaEventCreate(&c->ev1));
         size_t fixed = (size_t)(rup4(v->NW) + SS_FLOATS) * 4;
-        size_t stage = (size_t)v->stage_floats * 4;
+        size_t stage = (size_t)std::max(v->stage_floats, v->NPART) * 4;
         int wmax = (int)std::min<size_t>((size_t)v->max_warps, (c->smem_optin - fixed - 8192) / stage);
         if (wmax < 1) return fail(c, EH_EUNSUPPORTED, "variant %s needs %zu B of shared memory per warp", v->name, stage);
         CK(v->prepare(c->smem_optin - 256, fixed));  // kernels carry a few bytes of static shared memory

@@ -7,6 +7,11 @@ namespace eh {
     X(PmLinear, 2, 2, 32, 1, ACT_TANH, false)   \
     X(PmLinear2, 2, 2, 16, 1, ACT_TANH, false)  \
     X(PmLinear2, 2, 2, 16, 1, ACT_RELU, false)
-static const Variant g[] = {LIST(EH_MAKE)};
+#define LIST_MMA(X) \
+    X(PmLinear, 2, 2, 16, 1, ACT_RELU, false) \
+    X(PmLinear, 2, 2, 16, 1, ACT_TANH, false) \
+    X(PmLinear2, 2, 2, 16, 1, ACT_TANH, false) \
+    X(PmLinear2, 2, 2, 16, 1, ACT_RELU, false)
+static const Variant g[] = {LIST(EH_MAKE) LIST_MMA(EH_MAKE_MMA)};
 const Variant* variants_linear(int* n) { *n = (int)(sizeof(g) / sizeof(g[0])); return g; }
 }  // namespace eh

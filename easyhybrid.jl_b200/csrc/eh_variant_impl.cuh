@@ -6,17 +6,17 @@
 
 namespace eh {
 
-template <class C>
+template <class E>
 static cudaError_t prepare_t(size_t step_smem, size_t eval_smem)
 {
-    cudaError_t e = cudaFuncSetAttribute(k_step<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem);
+    cudaError_t e = cudaFuncSetAttribute(k_step<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_epoch<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem);
+    e = cudaFuncSetAttribute(k_epoch<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_eval<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eval_smem);
+    return cudaFuncSetAttribute(k_eval<typename E::Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)eval_smem);
 }
 
-template <class C>
+template <class E>
 static cudaError_t launch_step_t(const StepArgs& a, int grid, int nwarps, size_t smem, cudaStream_t st, bool pdl)
 {
     cudaLaunchConfig_t cfg{};
@@ -29,7 +29,7 @@ static cudaError_t launch_step_t(const StepArgs& a, int grid, int nwarps, size_t
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, k_step<C>, a);
+    return cudaLaunchKernelEx(&cfg, k_step<E>, a);
 }
 
 template <class C>
@@ -41,7 +41,7 @@ static cudaError_t launch_eval_t(const EvalArgs& a, int grid, int nwarps, size_t
 
 // k_epoch: thread-block clusters (DSMEM pre-reduction) + cooperative launch (the grid barrier needs
 // every CTA resident).  csize = 1 launches without a cluster attribute.
-template <class C>
+template <class E>
 static void epoch_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int grid, int nwarps, size_t smem, int csize,
                       cudaStream_t st)
 {
@@ -65,23 +65,23 @@ static void epoch_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int gr
     cfg.numAttrs = n;
 }
 
-template <class C>
+template <class E>
 static cudaError_t launch_epoch_t(const EpochArgs& a, int grid, int nwarps, size_t smem, int csize, cudaStream_t st)
 {
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attr[2];
-    epoch_cfg<C>(cfg, attr, grid, nwarps, smem, csize, st);
-    return cudaLaunchKernelEx(&cfg, k_epoch<C>, a);
+    epoch_cfg<E>(cfg, attr, grid, nwarps, smem, csize, st);
+    return cudaLaunchKernelEx(&cfg, k_epoch<E>, a);
 }
 
 // how many CTAs of this shape can be co-resident (in clusters of csize)
-template <class C>
+template <class E>
 static cudaError_t epoch_max_grid_t(int nwarps, size_t smem, int csize, int* max_ctas)
 {
     if (csize > 1) {
         cudaLaunchConfig_t cfg;
         cudaLaunchAttribute attr[2];
-        epoch_cfg<C>(cfg, attr, csize, nwarps, smem, csize, nullptr);
+        epoch_cfg<E>(cfg, attr, csize, nwarps, smem, csize, nullptr);
         cfg.numAttrs = 2;
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = (unsigned)csize;
@@ -89,12 +89,12 @@ static cudaError_t epoch_max_grid_t(int nwarps, size_t smem, int csize, int* max
         attr[0].val.clusterDim.z = 1;
         cfg.numAttrs = 1;
         int ncl = 0;
-        cudaError_t e = cudaOccupancyMaxActiveClusters(&ncl, k_epoch<C>, &cfg);
+        cudaError_t e = cudaOccupancyMaxActiveClusters(&ncl, k_epoch<E>, &cfg);
         *max_ctas = ncl * csize;
         return e;
     }
     int per_sm = 0, dev = 0, nsm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_epoch<C>, nwarps * 32, smem);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_epoch<E>, nwarps * 32, smem);
     if (e != cudaSuccess) return e;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
@@ -102,25 +102,32 @@ static cudaError_t epoch_max_grid_t(int nwarps, size_t smem, int csize, int* max
     return cudaSuccess;
 }
 
-template <class C>
+template <class E>
 static Variant make_variant(const char* name)
 {
+    using C = typename E::Cfg;
     Variant v{};
     v.pm = C::PM::ID; v.P = C::P; v.NH = C::NH; v.H = C::H; v.NOUT = C::NOUT; v.act = C::ACT; v.scale = C::SCALE ? 1 : 0;
+    v.engine = E::ENGINE;
     v.dims = C::D;
-    v.F = C::F; v.T = C::T; v.NPS = C::NPS; v.R4 = C::R4; v.NB = C::NB; v.NW = C::NW; v.NPART = C::NPART;
-    v.stage_floats = C::STAGE_FLOATS;
-    v.max_warps = 16;
+    v.F = C::F; v.T = C::T; v.NPS = C::NPS; v.R4 = C::R4; v.NW = C::NW;
+    v.NPART = E::NPART;
+    v.off_stats = E::OFF_STATS;
+    v.stage_floats = E::STAGE_FLOATS;
+    v.max_warps = E::MAX_WARPS;
     v.name = name;
-    v.prepare = prepare_t<C>;
-    v.launch_step = launch_step_t<C>;
+    v.prepare = prepare_t<E>;
+    v.launch_step = launch_step_t<E>;
     v.launch_eval = launch_eval_t<C>;
-    v.launch_epoch = launch_epoch_t<C>;
-    v.epoch_max_grid = epoch_max_grid_t<C>;
+    v.launch_epoch = launch_epoch_t<E>;
+    v.epoch_max_grid = epoch_max_grid_t<E>;
     return v;
 }
 
+// exact-fp32 FFMA2 engine and (where the shape allows) the register-resident tensor-pipe engine
 #define EH_MAKE(PMF, P, NH, H, NOUT, ACT, SCALE) \
-    make_variant<StepCfg<P, NH, H, NOUT, ACT, SCALE, PMF>>(#PMF "/P" #P "/NH" #NH "/H" #H "/O" #NOUT "/" #ACT "/scale=" #SCALE),
+    make_variant<EngFfma<StepCfg<P, NH, H, NOUT, ACT, SCALE, PMF>>>("ffma2/" #PMF "/P" #P "/NH" #NH "/H" #H "/O" #NOUT "/" #ACT "/scale=" #SCALE),
+#define EH_MAKE_MMA(PMF, P, NH, H, NOUT, ACT, SCALE) \
+    make_variant<EngMma<StepCfg<P, NH, H, NOUT, ACT, SCALE, PMF>>>("mma3xtf32/" #PMF "/P" #P "/NH" #NH "/H" #H "/O" #NOUT "/" #ACT "/scale=" #SCALE),
 
 }  // namespace eh

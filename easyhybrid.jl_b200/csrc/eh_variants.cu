@@ -31,11 +31,12 @@ const Variant* variant_at(int i)
     return nullptr;
 }
 
-const Variant* find_variant(int pm, int P, int NH, int H, int NOUT, int act, int scale)
+const Variant* find_variant(int pm, int P, int NH, int H, int NOUT, int act, int scale, int engine)
 {
     const Variant* best = nullptr;
     for (int i = 0; i < num_variants(); i++) {
         const Variant* v = variant_at(i);
+        if (v->engine != engine) continue;
         if (v->pm != pm || v->P != P || v->NH != NH || v->NOUT != NOUT || v->act != act || v->scale != scale) continue;
         if (v->H < H) continue;
         if (!best || v->H < best->H) best = v;

@@ -11,8 +11,9 @@ struct EpochArgs;
 
 struct Variant {
     int pm, P, NH, H, NOUT, act, scale;
+    int engine;      // 0: exact-fp32 FFMA2 (tile partial layout), 1: tensor pipe 3xTF32 (padded-flat partial layout)
     ShapeDims dims;
-    int F, T, NPS, R4, NB, NW, NPART, stage_floats, max_warps;
+    int F, T, NPS, R4, NW, NPART, off_stats, stage_floats, max_warps;
     const char* name;
     cudaError_t (*prepare)(size_t step_smem, size_t eval_smem);
     cudaError_t (*launch_step)(const StepArgs& a, int grid, int nwarps, size_t smem, cudaStream_t st, bool pdl);
@@ -21,7 +22,7 @@ struct Variant {
     cudaError_t (*epoch_max_grid)(int nwarps, size_t smem, int csize, int* max_ctas);
 };
 
-const Variant* find_variant(int pm, int P, int NH, int H, int NOUT, int act, int scale);
+const Variant* find_variant(int pm, int P, int NH, int H, int NOUT, int act, int scale, int engine);
 int num_variants();
 const Variant* variant_at(int i);
 

@@ -178,6 +178,9 @@ typedef struct {
 #define EH_FLAG_NO_GRAPH 1u   /* launch every step individually (debug / profiling) */
 #define EH_FLAG_NO_PDL   2u   /* no programmatic dependent launch                   */
 #define EH_FLAG_NO_PERSIST 4u /* never use the persistent multi-step kernel         */
+#define EH_FLAG_TENSOR_PIPE 16u /* hidden-layer contractions on the tensor pipe (HMMA, 3xTF32 split:
+                                  fp32-level accuracy) where a variant exists; default is the exact-fp32
+                                  FFMA2 engine */
 
 enum { EH_SPLIT_TRAIN = 0, EH_SPLIT_VAL = 1 };
 

@@ -30,7 +30,7 @@ CASES = [
 ]
 
 
-def _setup(eh, orc, mk, mkdata, loss, agg, opt=None, seed=7):
+def _setup(eh, orc, mk, mkdata, loss, agg, opt=None, seed=7, flags=0):
     model = mk(eh)
     if loss == "PT":
         loss = eh.PerTarget("nseLoss", "mse")
@@ -38,16 +38,18 @@ def _setup(eh, orc, mk, mkdata, loss, agg, opt=None, seed=7):
     rng = np.random.default_rng(seed)
     flat = model.initialparameters(rng)
     flat += (0.05 * rng.standard_normal(flat.size)).astype(np.float32)
-    sess = eh.FusedSession(model, training_loss=loss, agg=agg, opt=opt)
+    sess = eh.FusedSession(model, training_loss=loss, agg=agg, opt=opt, flags=flags)
     sess.upload(0, xf, y)
     sess.set_params(flat)
     o = orc.Oracle(model, training_loss=loss, agg=agg, opt=opt)
     return model, xf, y, flat, sess, o, rng
 
 
+# engine: 0 = default exact-fp32 FFMA2 engine, 16 = EH_FLAG_TENSOR_PIPE (HMMA 3xTF32 engine where the shape has one)
+@pytest.mark.parametrize("engine_flags", [0, 16], ids=["ffma2", "mma3xtf32"])
 @pytest.mark.parametrize("name,mk,mkdata,loss,agg", CASES, ids=[c[0] for c in CASES])
-def test_loss_and_gradient(eh, orc, name, mk, mkdata, loss, agg):
-    model, xf, y, flat, sess, o, rng = _setup(eh, orc, mk, mkdata, loss, agg)
+def test_loss_and_gradient(eh, orc, name, mk, mkdata, loss, agg, engine_flags):
+    model, xf, y, flat, sess, o, rng = _setup(eh, orc, mk, mkdata, loss, agg, flags=engine_flags)
     n = xf[0].shape[0]
     for B in (n, 517, 64, 12, 1):  # full, ragged, one chunk, the reference's test batch size, single sample
         if B == 1 and loss in ("nseLoss", "PT"):
@@ -191,7 +193,7 @@ def test_persistent_kernel_matches_step_kernels(eh, orc):
     flat = model.initialparameters(np.random.default_rng(3))
     perm = np.random.default_rng(4).permutation(n)
     out = {}
-    for flags in (0, 4, 4 | 1, 4 | 1 | 2):
+    for flags in (0, 4, 4 | 1, 4 | 1 | 2, 16, 16 | 4):
         sess = eh.FusedSession(model, flags=flags)
         sess.upload(0, xf, y)
         sess.set_params(flat)
