@@ -178,7 +178,7 @@ SIGNATURES = {
     "eh_set_perm": (C.c_int, [_p, _i64p, C.c_int64]),
     "eh_run_steps": (C.c_int, [_p, C.c_int64, C.c_int64, C.c_int64, _fp]),
     "eh_eval": (C.c_int, [_p, C.c_int32, _fp, C.POINTER(C.c_double), _fp]),
-    "eh_comm_id": (C.c_int, [_p]),
+    "eh_comm_id": (C.c_int, [_p, _p]),
     "eh_comm_init": (C.c_int, [_p, C.c_int32, C.c_int32, _p]),
     "eh_last_timing": (C.c_int, [_p, _fp, _i64p, _fp]),
     "eh_set_profiling": (C.c_int, [_p, C.c_int32]),

@@ -20,6 +20,7 @@ namespace eh {
 
 // per-batch scalar row (floats): seed scale c_t, n_valid_t, SS_tot_t, then (mu, rstd) per chain input
 constexpr int MAXP = 12;  // chain inputs
+constexpr int EH_MAX_WORLD = 8;  // GPUs of one NVSwitch box
 constexpr int BS_C = 0, BS_N = MAXT, BS_SS = 2 * MAXT, BS_BN = 3 * MAXT, BS_STRIDE = 3 * MAXT + 2 * MAXP;
 
 enum : int { OPT_ADAM = 0, OPT_ADAMW = 1, OPT_RMSPROP = 2, OPT_DESCENT = 3 };

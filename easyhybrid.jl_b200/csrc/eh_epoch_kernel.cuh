@@ -52,6 +52,12 @@ struct EpochArgs {
     int opt_kind, adamw_coupled;
     float eta, beta1, beta2, eps, lambda;
     long long* dbg;            // optional [nsteps][gridDim.x][32] SM-clock timestamps (EH_EPOCH_DEBUG)
+    // ---- data parallel: one process per GPU, peer memory mapped with CUDA IPC over NVLink ----
+    int world, rank;
+    unsigned step_base;        // steps exchanged by earlier launches (flags carry absolute step tags)
+    float* inbox_peer[EH_MAX_WORLD];      // rank r's inbox [2][world][npartp] as mapped in this process
+    unsigned* flag_peer[EH_MAX_WORLD];    // rank r's flags [2][world]
+    unsigned* err;             // set to 1 when a bounded spin gives up (peer / CTA never arrived)
 };
 
 __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p)
@@ -60,6 +66,18 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p)
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+constexpr unsigned EH_SPIN_LIMIT = 1u << 26;  // ~seconds; then give up loudly instead of hanging the GPU
+
 __device__ __forceinline__ void cluster_sync_all()
 {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -208,7 +226,10 @@ __global__ void __launch_bounds__(E::MAX_WARPS * 32, 1) k_epoch(const EpochArgs 
                 __threadfence();
                 atomicAdd(a.counter, 1u);
             }
-            while (ld_acquire_gpu(a.counter) < bar) { }
+            unsigned spins = 0;
+            while (ld_acquire_gpu(a.counter) < bar) {
+                if (++spins > EH_SPIN_LIMIT) { *a.err = 1; break; }
+            }
             __threadfence();
         }
         __syncthreads();
@@ -247,6 +268,36 @@ __global__ void __launch_bounds__(E::MAX_WARPS * 32, 1) k_epoch(const EpochArgs 
             red[p] = s0 + s1;
         }
         __syncthreads();
+        if (a.world > 1) {
+            // ---- fused exchange over NVLink peer memory: CTA 0 pushes this GPU's reduced vector into every
+            // rank's inbox (plain P2P stores) and raises a release flag; every CTA then waits for all ranks'
+            // flags in its own GPU's inbox and sums the vectors in rank order (bitwise identical everywhere).
+            const unsigned tag = a.step_base + (unsigned)s + 1u;
+            if (blockIdx.x == 0) {
+                for (int r = 0; r < a.world; r++) {
+                    float* dst = a.inbox_peer[r] + ((size_t)par * a.world + a.rank) * a.npartp;
+                    for (int p = threadIdx.x; p < E::NPART; p += blockDim.x) dst[p] = red[p];
+                }
+                __threadfence_system();
+                __syncthreads();
+                if (threadIdx.x < a.world) st_release_sys(a.flag_peer[threadIdx.x] + par * a.world + a.rank, tag);
+            }
+            if (threadIdx.x < a.world) {
+                const unsigned* fl = a.flag_peer[a.rank] + par * a.world + threadIdx.x;
+                unsigned spins = 0;
+                while (ld_acquire_sys(fl) < tag) {
+                    if (++spins > EH_SPIN_LIMIT) { *a.err = 1; break; }
+                }
+            }
+            __syncthreads();
+            const float* inbox = a.inbox_peer[a.rank] + (size_t)par * a.world * a.npartp;
+            for (int p = threadIdx.x; p < E::NPART; p += blockDim.x) {
+                float sum = 0.f;
+                for (int r = 0; r < a.world; r++) sum += __ldcg(inbox + (size_t)r * a.npartp + p);
+                red[p] = sum;
+            }
+            __syncthreads();
+        }
         if (threadIdx.x == 0) {
             float ntot = 0.f, post = 1.f;
             for (int t = 0; t < a.T; t++) {

@@ -125,10 +125,12 @@ struct eh_ctx {
     const int* g_idx = nullptr;
     const float* g_bscal = nullptr;
     const float* g_loss = nullptr;
-    // dp
+    // data parallel: inbox block = [flags 2*8 unsigned, padded to 256 B][2][8][npartp] floats, IPC-shared
     int rank = 0, world = 1;
-    void* nccl_lib = nullptr;
-    void* nccl_comm = nullptr;
+    void* dp_block = nullptr;
+    void* dp_peer[EH_MAX_WORLD] = {nullptr};
+    unsigned dp_steps = 0;  // steps exchanged so far (absolute flag tags)
+    unsigned* d_dperr = nullptr;
 };
 
 namespace {
@@ -160,12 +162,12 @@ cudaError_t dalloc(T** p, size_t n)
 
 // n_valid-independent per-batch rows when no data statistics are needed:
 // c_t = agg_w / B_k, n_t = B_k (no NaN targets anywhere in the split)
-__global__ void k_fill_bscal(float* bscal, int nb, long long n, int Bfull, int T, int agg_mean)
+__global__ void k_fill_bscal(float* bscal, int nb, long long n, int Bfull, int T, int agg_mean, int world)
 {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nb) return;
     long long rem = n - (long long)b * Bfull;
-    float bk = (float)(rem < Bfull ? rem : Bfull);
+    float bk = (float)(rem < Bfull ? rem : Bfull) * (float)world;  // data parallel: the global batch
     float* o = bscal + (size_t)b * BS_STRIDE;
     float aggw = agg_mean ? 1.f / (float)T : 1.f;
     for (int t = 0; t < MAXT; t++) {
@@ -382,6 +384,8 @@ eh_status prepare_batch_rows(eh_ctx* c, int64_t n, int64_t B)
     eh_status s = ensure_bscal_cap(c, (size_t)nb);
     if (s != EH_OK) return s;
     const Split& sp = c->split[EH_SPLIT_TRAIN];
+    if (needs_data_stats(c) && c->world > 1)
+        return fail(c, EH_EUNSUPPORTED, "data-parallel mode needs NaN-free targets, no nseLoss and no input BatchNorm in this build");
     if (needs_data_stats(c)) {
         StatArgs a;
         memset(&a, 0, sizeof a);
@@ -400,7 +404,7 @@ eh_status prepare_batch_rows(eh_ctx* c, int64_t n, int64_t B)
         k_batch_stats<<<(unsigned)nb, 256, 0, c->stream>>>(a);
     } else {
         k_fill_bscal<<<(unsigned)((nb + 127) / 128), 128, 0, c->stream>>>(c->d_bscal, (int)nb, n, (int)B, c->n_targ,
-                                                                          c->agg_mean);
+                                                                          c->agg_mean, c->world);
     }
     CK(cudaGetLastError());
     return EH_OK;
@@ -431,7 +435,6 @@ eh_status enqueue_steps(eh_ctx* c, int64_t n, int64_t B, int64_t b0, int64_t b1,
         u.G = g.grid;
         u.bscal = a.bscal;
         u.loss_out = loss_base + (b - b0);
-        if (c->world > 1) return fail(c, EH_EUNSUPPORTED, "data-parallel step not wired in this build");
         CK(launch_update(u, c->stream, pdl));
     }
     return EH_OK;
@@ -545,6 +548,12 @@ eh_status run_persistent(eh_ctx* c, int64_t n, int64_t B, int64_t first, int64_t
     a.use_bn = c->use_bn; a.pm_id = c->pm_id;
     a.opt_kind = c->opt_kind; a.adamw_coupled = c->adamw_coupled;
     a.eta = c->eta; a.beta1 = c->beta1; a.beta2 = c->beta2; a.eps = c->eps; a.lambda = c->lambda;
+    a.world = c->world; a.rank = c->rank; a.step_base = c->dp_steps; a.err = c->d_dperr;
+    for (int r = 0; r < c->world && c->world > 1; r++) {
+        a.flag_peer[r] = reinterpret_cast<unsigned*>(c->dp_peer[r]);
+        a.inbox_peer[r] = reinterpret_cast<float*>(reinterpret_cast<char*>(c->dp_peer[r]) + 256);
+    }
+    CK(cudaMemsetAsync(c->d_dperr, 0, sizeof(unsigned), c->stream));
     long long* d_dbg = nullptr;
     const char* dbg_path = getenv("EH_EPOCH_DEBUG");
     if (dbg_path && nsteps <= 64) {
@@ -567,7 +576,11 @@ eh_status run_persistent(eh_ctx* c, int64_t n, int64_t B, int64_t first, int64_t
                                                                                  c->d_losskind, c->d_loss);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(c->h_loss, c->d_loss, (size_t)nsteps * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    unsigned herr = 0;
+    CK(cudaMemcpyAsync(&herr, c->d_dperr, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    if (c->world > 1) c->dp_steps += (unsigned)nsteps;
+    if (herr) return fail(c, EH_ENCCL, "persistent kernel gave up waiting (a CTA or a data-parallel peer never arrived)");
     CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
     if (d_dbg) {
         std::vector<long long> h((size_t)nsteps * G * 32);
@@ -608,8 +621,15 @@ eh_status run_steps(eh_ctx* c, int64_t n, int64_t B, int64_t first, int64_t nste
         }
     }
     bool persisted = false;
-    if (c->persist_ok && !(c->flags & EH_FLAG_NO_PERSIST) && !profile && apply && !grad_out_host && nsteps >= 2 &&
-        nsteps < (1 << 30) && c->world == 1) {
+    if (c->world > 1) {
+        // data parallel: the exchange lives in the persistent kernel
+        if (!apply || grad_out_host || profile || !c->persist_ok)
+            return fail(c, EH_EUNSUPPORTED, "data-parallel mode trains through eh_run_steps / eh_epoch only");
+        s = run_persistent(c, n, B, first, nsteps, &persisted);
+        if (s != EH_OK) return s;
+        if (!persisted) return fail(c, EH_EUNSUPPORTED, "persistent kernel unavailable for this shape: %s", c->err.c_str());
+    } else if (c->persist_ok && !(c->flags & EH_FLAG_NO_PERSIST) && !profile && apply && !grad_out_host && nsteps >= 2 &&
+               nsteps < (1 << 30)) {
         s = run_persistent(c, n, B, first, nsteps, &persisted);
         if (s != EH_OK) return s;
     }
@@ -1008,6 +1028,7 @@ eh_status eh_create(eh_ctx** out, const eh_model_desc* desc)
         CK(cudaMemcpy(c->d_losskind, c->loss_kind, MAXT * sizeof(int), cudaMemcpyHostToDevice));
         CK(dalloc(&c->d_pbuf, (size_t)2 * (c->nsm + 8) * rup4(v->NPART)));
         CK(dalloc(&c->d_counter, (size_t)4));
+        CK(dalloc(&c->d_dperr, (size_t)1));
         CK(dalloc(&c->d_m, (size_t)c->nflat));
         CK(dalloc(&c->d_v, (size_t)c->nflat));
         CK(dalloc(&c->d_grad, (size_t)c->nflat));
@@ -1033,8 +1054,11 @@ void eh_destroy(eh_ctx* c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->gexec) cudaGraphExecDestroy(c->gexec);
+    for (int r = 0; r < c->world && c->world > 1; r++)
+        if (r != c->rank && c->dp_peer[r]) cudaIpcCloseMemHandle(c->dp_peer[r]);
+    if (c->dp_block) cudaFree(c->dp_block);
     void* ptrs[] = {c->d_wsrc, c->d_pmap, c->d_pspan, c->d_theta, c->d_m, c->d_v, c->d_grad, c->d_ost, c->d_partial,
-                    c->d_gvec, c->d_cells, c->d_slot_of_flat, c->d_losskind, c->d_pbuf, c->d_stats, c->d_counter, c->d_bscal, c->d_bn_batch, c->d_idx, c->d_idx64, c->d_err, c->d_loss, c->d_evalpart,
+                    c->d_gvec, c->d_dperr, c->d_cells, c->d_slot_of_flat, c->d_losskind, c->d_pbuf, c->d_stats, c->d_counter, c->d_bscal, c->d_bn_batch, c->d_idx, c->d_idx64, c->d_err, c->d_loss, c->d_evalpart,
                     c->d_bn_test, c->split[0].rec, c->split[1].rec};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -1374,17 +1398,46 @@ eh_status eh_eval(eh_ctx* c, int32_t split, float* yhat, double* stats, float* n
     return EH_OK;
 }
 
-eh_status eh_comm_id(void* id_out)
+eh_status eh_comm_id(eh_ctx* c, void* id_out)
 {
-    (void)id_out;
-    g_create_error = "data-parallel communicator not available in this build";
-    return EH_EUNSUPPORTED;
+    if (!c) return EH_EINVAL;
+    if (!id_out) return fail(c, EH_EINVAL, "null id_out");
+    CK(cudaSetDevice(c->device));
+    if (!c->dp_block) {
+        const size_t bytes = 256 + (size_t)2 * EH_MAX_WORLD * rup4(c->var->NPART) * sizeof(float);
+        CK(cudaMalloc(&c->dp_block, bytes));
+        CK(cudaMemset(c->dp_block, 0, bytes));
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) <= EH_COMM_ID_BYTES, "IPC handle does not fit the id blob");
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, c->dp_block));
+    memset(id_out, 0, EH_COMM_ID_BYTES);
+    memcpy(id_out, &h, sizeof h);
+    return EH_OK;
 }
 
-eh_status eh_comm_init(eh_ctx* c, int32_t rank, int32_t world, const void* id)
+eh_status eh_comm_init(eh_ctx* c, int32_t rank, int32_t world, const void* ids)
 {
-    (void)rank; (void)world; (void)id;
-    return fail(c, EH_EUNSUPPORTED, "data-parallel communicator not available in this build");
+    if (!c) return EH_EINVAL;
+    if (world < 1 || world > EH_MAX_WORLD || rank < 0 || rank >= world || !ids)
+        return fail(c, EH_EINVAL, "eh_comm_init: world must be 1..%d and 0 <= rank < world", EH_MAX_WORLD);
+    if (!c->dp_block) return fail(c, EH_EINVAL, "eh_comm_init: call eh_comm_id on this ctx first");
+    if (!c->persist_ok) return fail(c, EH_EUNSUPPORTED, "data-parallel mode needs the persistent kernel, unavailable for this model");
+    CK(cudaSetDevice(c->device));
+    for (int r = 0; r < world; r++) {
+        if (r == rank) { c->dp_peer[r] = c->dp_block; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, reinterpret_cast<const char*>(ids) + (size_t)r * EH_COMM_ID_BYTES, sizeof h);
+        cudaError_t e = cudaIpcOpenMemHandle(&c->dp_peer[r], h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess)
+            return fail(c, EH_ENCCL, "cudaIpcOpenMemHandle for rank %d failed: %s (peer access over NVLink required)", r,
+                        cudaGetErrorString(e));
+    }
+    c->rank = rank;
+    c->world = world;
+    c->dp_steps = 0;
+    c->perm_B = 0;  // per-batch scalars depend on the world size
+    return EH_OK;
 }
 
 eh_status eh_host_alloc(void** out, size_t bytes)

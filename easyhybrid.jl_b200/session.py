@@ -171,6 +171,24 @@ class FusedSession:
         self._ck(self.lib.eh_sync(self.h))
         self._inflight = []
 
+    # ---- data parallel (one process per GPU) ----
+    def comm_id(self):
+        buf = C.create_string_buffer(_abi.EH_COMM_ID_BYTES)
+        self._ck(self.lib.eh_comm_id(self.h, buf))
+        return bytes(buf.raw)
+
+    def comm_init(self, rank, world, dist=None, ids=None):
+        """connect the ranks' inboxes; ``dist`` is an initialised torch.distributed module used only to
+        all-gather the IPC handles (any other transport can pass ``ids`` = list of blobs in rank order)"""
+        if ids is None:
+            mine = self.comm_id()
+            ids = [None] * world
+            dist.all_gather_object(ids, mine)
+        blob = b"".join(ids)
+        assert len(blob) == world * _abi.EH_COMM_ID_BYTES
+        self._ck(self.lib.eh_comm_init(self.h, rank, world, C.create_string_buffer(blob, len(blob))))
+        self.rank, self.world = rank, world
+
     # ---- evaluation ----
     def eval(self, split, want_yhat=True, want_params=False):
         n = self.n[split]

@@ -254,15 +254,23 @@ eh_status eh_run_steps(eh_ctx* ctx, int64_t B, int64_t first_step, int64_t n_ste
  * left untouched) -- the `parameters` entry of the reference forward output. */
 eh_status eh_eval(eh_ctx* ctx, int32_t split, float* yhat, double* stats, float* nn_out);
 
-/* ---- data parallel (one process per GPU) ---------------------------------
- * Rank r owns the contiguous slice [r*B/W, (r+1)*B/W) of every global batch.
- * Exchange = one sum-allreduce per step of the scaled gradient and the loss
- * statistics; parameters and optimiser state stay replicated bit-identically.
- * The caller transports `id` (EH_COMM_ID_BYTES, from rank 0's eh_comm_id)
- * to all ranks with its own plumbing (torch.distributed / MPI / files).     */
+/* ---- data parallel (one process per GPU of one NVLink / NVSwitch box) --------
+ * Every rank owns a shard of the samples (its own eh_upload + eh_set_perm); global
+ * batch k is the union of the ranks' local batches k, which must have the same
+ * size on every rank.  Per step the ranks exchange ONE vector (loss-scaled
+ * gradient + loss sums) inside the persistent kernel: rank r's CTA 0 stores it
+ * into every peer's inbox through NVLink peer memory and raises a flag, all CTAs
+ * sum the rank vectors in rank order and apply the optimiser redundantly, so
+ * parameters and optimiser state stay replicated bit-identically.  No NCCL.
+ * Setup: each rank calls eh_comm_id on its ctx (allocates the inbox, returns an
+ * EH_COMM_ID_BYTES blob = a CUDA IPC handle), the caller all-gathers the blobs
+ * with its own plumbing (torch.distributed / MPI / files) and hands all of them
+ * (rank order) to eh_comm_init.  world <= 8.  In data-parallel mode only
+ * eh_run_steps / eh_epoch train; configurations that need per-batch data
+ * statistics (NaN targets, nseLoss, input BatchNorm) answer EH_EUNSUPPORTED.   */
 #define EH_COMM_ID_BYTES 128
-eh_status eh_comm_id(void* id_out);
-eh_status eh_comm_init(eh_ctx* ctx, int32_t rank, int32_t world, const void* id);
+eh_status eh_comm_id(eh_ctx* ctx, void* id_out);
+eh_status eh_comm_init(eh_ctx* ctx, int32_t rank, int32_t world, const void* ids /* world x EH_COMM_ID_BYTES */);
 
 /* page-locked host buffers for callers that stream batches (eh_step_host_async copies
  * straight out of them with cudaMemcpyAsync; pageable memory also works, but synchronously) */

@@ -1,0 +1,91 @@
+"""Worker for the data-parallel tests: `torchrun --nproc-per-node W tests/dp_worker.py [gloo|nccl]`.
+
+gloo (CPU): every rank evaluates the ORACLE on its shard of each global batch, the per-rank (n, loss,
+grad) are all-reduced and combined (easyhybrid_b200.dp.combine_mse) and must equal the oracle on the
+union batch -- the contract the device-side exchange implements.
+nccl (GPU): every rank trains its shard through the CUDA library in data-parallel mode; rank 0 checks the
+per-step losses and the trained parameters against the oracle trained on the union batches, and that
+all ranks hold bit-identical parameters."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from conftest import make_synth, rbq10_model  # noqa: E402
+
+
+def main():
+    backend = sys.argv[1] if len(sys.argv) > 1 else "gloo"
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if backend == "nccl":
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        dist.init_process_group("gloo")
+    import easyhybrid_b200 as eh
+    from easyhybrid_b200.dp import combine_mse, global_batch_indices
+    from oracle import oracle as orc
+
+    model = rbq10_model(eh)
+    n_local, B, steps = 6000, 1000, 11
+    shards = [eh.prepare_data(model, make_synth(n_local, seed=100 + r)) for r in range(world)]
+    perms = [np.random.default_rng(200 + r).permutation(n_local) for r in range(world)]
+    flat0 = model.initialparameters(np.random.default_rng(5))
+    # the union dataset, for the single-process oracle
+    Xall = np.concatenate([s[0][0] for s in shards])
+    fall = {"ta": np.concatenate([s[0][1]["ta"] for s in shards])}
+    yall = {"reco": np.concatenate([s[1]["reco"] for s in shards])}
+    o = orc.Oracle(model, opt=eh.Adam(0.01))
+
+    if backend == "gloo":
+        xf, y = shards[rank]
+        for k in range(3):
+            idx = perms[rank][k * B:(k + 1) * B][: B - 100 * rank]      # ragged shards
+            L, g = o.loss_grad(flat0, xf, y, idx, precision=64)
+            t = torch.tensor(np.concatenate([[len(idx) * L, len(idx)], len(idx) * g]))
+            dist.all_reduce(t)                                          # sum of n_r L_r, n_r, n_r g_r
+            Lg, gg = t[0].item() / t[1].item(), t[2:].numpy() / t[1].item()
+            gi = np.concatenate([r * n_local + perms[r][k * B:(k + 1) * B][: B - 100 * r] for r in range(world)])
+            Lw, gw = o.loss_grad(flat0, (Xall, fall), yall, gi, precision=64)
+            assert abs(Lg - Lw) <= 1e-12 * abs(Lw), (Lg, Lw)
+            assert np.abs(gg - gw).max() <= 1e-11 * np.abs(gw).max()
+            Lc, gc = combine_mse([len(idx)], [L], [g])
+            assert Lc == L
+        if rank == 0:
+            print("DP_GLOO_OK")
+    else:
+        xf, y = shards[rank]
+        sess = eh.FusedSession(model, opt=eh.Adam(0.01), device=local)
+        sess.upload(0, xf, y)
+        sess.set_params(flat0)
+        sess.comm_init(rank, world, dist)
+        sess.set_perm(perms[rank])
+        dist.barrier()
+        losses = sess.run_steps(B, 0, steps)
+        ps = sess.get_params()
+        allps = [None] * world
+        dist.all_gather_object(allps, ps.tobytes())
+        if rank == 0:
+            assert all(b == allps[0] for b in allps), "replicas diverged"
+            ref = flat0.copy()
+            want = []
+            nb = n_local // B
+            for s in range(steps):
+                gi = global_batch_indices(perms, [n_local] * world, B, s % nb)
+                want.append(o.train_steps(ref, (Xall, fall), yall, gi, world * B)[0])
+            np.testing.assert_allclose(losses, np.array(want), rtol=2e-4)
+            assert abs(float(ps[-1]) - float(ref[-1])) <= 1e-4, (ps[-1], ref[-1])
+            print("DP_NCCL_OK", losses[:3], want[:3])
+        sess.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
