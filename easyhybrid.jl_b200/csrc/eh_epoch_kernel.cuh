@@ -20,7 +20,7 @@ namespace eh {
 
 struct EpochArgs {
     const float4* rec;
-    const int* idx;            // resident index stream
+    const int* idx;            // resident index stream (NULL: batch b = records b*B .. of `rec`)
     long long n;               // its length
     int B;                     // nominal batch size
     long long first_step;
@@ -55,8 +55,7 @@ struct EpochArgs {
     // ---- data parallel: one process per GPU, peer memory mapped with CUDA IPC over NVLink ----
     int world, rank;
     unsigned step_base;        // steps exchanged by earlier launches (flags carry absolute step tags)
-    float* inbox_peer[EH_MAX_WORLD];      // rank r's inbox [2][world][npartp] as mapped in this process
-    unsigned* flag_peer[EH_MAX_WORLD];    // rank r's flags [2][world]
+    uint2* inbox_peer[EH_MAX_WORLD];      // rank r's inbox [2][world][npartp] of {value bits, step tag}, as mapped here
     unsigned* err;             // set to 1 when a bounded spin gives up (peer / CTA never arrived)
 };
 
@@ -64,6 +63,17 @@ __device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p)
 {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// 8-byte accesses are single-copy atomic: value and tag always travel together
+__device__ __forceinline__ void st_volatile_v2(uint2* p, unsigned x, unsigned y)
+{
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ uint2 ld_volatile_v2(const uint2* p)
+{
+    uint2 v;
+    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p)
@@ -159,7 +169,7 @@ __global__ void __launch_bounds__(E::MAX_WARPS * 32, 1) k_epoch(const EpochArgs 
         long long b = a.first_step % a.nb;
         long long rem = a.n - b * a.B;
         int Bk = (int)(rem < a.B ? rem : a.B);
-        E::fetch(st, a.rec, a.idx + b * a.B, 0, Bk, gw, (Bk + CHUNK - 1) / CHUNK, lane);
+        E::fetch(st, a.rec, a.idx ? a.idx + b * a.B : nullptr, a.idx ? 0 : b * a.B, Bk, gw, (Bk + CHUNK - 1) / CHUNK, lane);
     }
     unsigned bar = 0;
     // per-batch scalars of the coming step, prefetched one step ahead (a dependent global load otherwise)
@@ -190,7 +200,7 @@ __global__ void __launch_bounds__(E::MAX_WARPS * 32, 1) k_epoch(const EpochArgs 
         EH_STAMP(1)
 
         E::step_begin(st, sW, lane);
-        const FetchArgs fa{a.rec, a.idx + b * a.B, 0, Bk, nchunks};
+        const FetchArgs fa{a.rec, a.idx ? a.idx + b * a.B : nullptr, a.idx ? 0 : b * a.B, Bk, nchunks};
         for (int chunk = gw; chunk < nchunks; chunk += GW)
             E::chunk(st, fa, chunk + GW, sW, sS, stage, lane, a.slot, a.loss_kind, cx);
         if (a.dbg && lane == 0) a.dbg[((size_t)s * G + blockIdx.x) * 32 + 8 + warp] = clock64();
@@ -199,7 +209,7 @@ __global__ void __launch_bounds__(E::MAX_WARPS * 32, 1) k_epoch(const EpochArgs 
             long long b2 = (a.first_step + s + 1) % a.nb;
             long long rem2 = a.n - b2 * a.B;
             int Bk2 = (int)(rem2 < a.B ? rem2 : a.B);
-            E::fetch(st, a.rec, a.idx + b2 * a.B, 0, Bk2, gw, (Bk2 + CHUNK - 1) / CHUNK, lane);
+            E::fetch(st, a.rec, a.idx ? a.idx + b2 * a.B : nullptr, a.idx ? 0 : b2 * a.B, Bk2, gw, (Bk2 + CHUNK - 1) / CHUNK, lane);
         }
         __syncthreads();
         EH_STAMP(2)
@@ -268,36 +278,37 @@ __global__ void __launch_bounds__(E::MAX_WARPS * 32, 1) k_epoch(const EpochArgs 
             red[p] = s0 + s1;
         }
         __syncthreads();
+        if (a.dbg && threadIdx.x == 0) a.dbg[((size_t)s * G + blockIdx.x) * 32 + 27] = clock64();
         if (a.world > 1) {
-            // ---- fused exchange over NVLink peer memory: CTA 0 pushes this GPU's reduced vector into every
-            // rank's inbox (plain P2P stores) and raises a release flag; every CTA then waits for all ranks'
-            // flags in its own GPU's inbox and sums the vectors in rank order (bitwise identical everywhere).
+            // ---- fused exchange over NVLink peer memory, LL style: every 8-byte store carries {value, step tag},
+            // so a slot validates itself -- no fences, no separate flags, one-way NVLink latency.  CTA 0 pushes this
+            // GPU's reduced vector into every rank's inbox; every CTA of every GPU polls its own GPU's inbox and sums
+            // the rank vectors in rank order (bitwise identical everywhere).
             const unsigned tag = a.step_base + (unsigned)s + 1u;
             if (blockIdx.x == 0) {
                 for (int r = 0; r < a.world; r++) {
-                    float* dst = a.inbox_peer[r] + ((size_t)par * a.world + a.rank) * a.npartp;
-                    for (int p = threadIdx.x; p < E::NPART; p += blockDim.x) dst[p] = red[p];
+                    uint2* dst = a.inbox_peer[r] + ((size_t)par * a.world + a.rank) * a.npartp;
+                    for (int p = threadIdx.x; p < E::NPART; p += blockDim.x) st_volatile_v2(dst + p, __float_as_uint(red[p]), tag);
                 }
-                __threadfence_system();
-                __syncthreads();
-                if (threadIdx.x < a.world) st_release_sys(a.flag_peer[threadIdx.x] + par * a.world + a.rank, tag);
+                __syncthreads();  // red is about to be overwritten below
             }
-            if (threadIdx.x < a.world) {
-                const unsigned* fl = a.flag_peer[a.rank] + par * a.world + threadIdx.x;
-                unsigned spins = 0;
-                while (ld_acquire_sys(fl) < tag) {
-                    if (++spins > EH_SPIN_LIMIT) { *a.err = 1; break; }
-                }
-            }
-            __syncthreads();
-            const float* inbox = a.inbox_peer[a.rank] + (size_t)par * a.world * a.npartp;
+            const uint2* inbox = a.inbox_peer[a.rank] + (size_t)par * a.world * a.npartp;
             for (int p = threadIdx.x; p < E::NPART; p += blockDim.x) {
                 float sum = 0.f;
-                for (int r = 0; r < a.world; r++) sum += __ldcg(inbox + (size_t)r * a.npartp + p);
+                for (int r = 0; r < a.world; r++) {
+                    uint2 v = ld_volatile_v2(inbox + (size_t)r * a.npartp + p);
+                    unsigned spins = 0;
+                    while (v.y != tag) {
+                        if (++spins > EH_SPIN_LIMIT) { *a.err = 1; break; }
+                        v = ld_volatile_v2(inbox + (size_t)r * a.npartp + p);
+                    }
+                    sum += __uint_as_float(v.x);
+                }
                 red[p] = sum;
             }
             __syncthreads();
         }
+        if (a.dbg && threadIdx.x == 0) a.dbg[((size_t)s * G + blockIdx.x) * 32 + 28] = clock64();
         if (threadIdx.x == 0) {
             float ntot = 0.f, post = 1.f;
             for (int t = 0; t < a.T; t++) {

@@ -125,7 +125,7 @@ struct eh_ctx {
     const int* g_idx = nullptr;
     const float* g_bscal = nullptr;
     const float* g_loss = nullptr;
-    // data parallel: inbox block = [flags 2*8 unsigned, padded to 256 B][2][8][npartp] floats, IPC-shared
+    // data parallel: inbox block = [2 parities][8 ranks][npartp] {value, tag} slots, IPC-shared
     int rank = 0, world = 1;
     void* dp_block = nullptr;
     void* dp_peer[EH_MAX_WORLD] = {nullptr};
@@ -479,7 +479,10 @@ eh_status ensure_pass_graph(eh_ctx* c, int64_t n, int64_t B, bool pdl)
 // Persistent path: all nsteps optimiser steps in ONE launch (eh_epoch_kernel.cuh).
 // Geometry: cluster size cs, grid G (multiple of cs, all co-resident), w warps per CTA.  A larger
 // cluster means fewer vectors through the grid barrier but (GPC granularity) fewer usable SMs.
-eh_status run_persistent(eh_ctx* c, int64_t n, int64_t B, int64_t first, int64_t nsteps, bool* used)
+// enqueue only (no host synchronisation): rec/idx/bscal select the data source, per-step loss sums go to
+// c->d_stats and the losses to loss_out (device)
+eh_status enqueue_persistent(eh_ctx* c, const float* rec, const int* idx, const float* bscal, float* loss_out, int64_t n,
+                             int64_t B, int64_t first, int64_t nsteps, bool* used, long long** dbg_out)
 {
     *used = false;
     const Variant* v = c->var;
@@ -496,7 +499,10 @@ eh_status run_persistent(eh_ctx* c, int64_t n, int64_t B, int64_t first, int64_t
     int best_cs = 0, best_G = 0, best_w = 0;
     size_t best_work = 0;
     double best_cost = 1e30;
-    for (int cs : {8, 4, 2, 1}) {
+    // measured on B200 (bench.py sweep, 65 536-sample batches): clusters of 4 are the sweet spot (132 usable SMs,
+    // 33 vectors through the barrier); 2 is close; 8 loses more to GPC-constrained placement than it saves.
+    // Rule: fewest rounds over the batch first, then that preference order.
+    for (int cs : {4, 2, 1, 8}) {
         if (ecs && atoi(ecs) != cs) continue;
         // the work region also receives the NC published vectors: NC <= nsm / cs
         const size_t vec_bytes = (size_t)(c->nsm / cs) * npartp * 4;
@@ -509,15 +515,13 @@ eh_status run_persistent(eh_ctx* c, int64_t n, int64_t B, int64_t first, int64_t
         if (v->epoch_max_grid(wtry, smem_try, cs, &max_ctas) != cudaSuccess) { cudaGetLastError(); continue; }
         max_ctas = std::min(max_ctas, (c->nsm / cs) * cs);
         if (max_ctas < cs) continue;
-        // fewest warps per CTA that still cover the batch in the fewest rounds
         int64_t per_round = (int64_t)max_ctas * wtry;
         int64_t rounds = (nchunks + per_round - 1) / per_round;
+        // fewest warps per CTA that still cover the batch in that many rounds, then the smallest grid that does
         int w = ew ? wtry : (int)std::min<int64_t>(wtry, (nchunks + rounds * max_ctas - 1) / (rounds * max_ctas));
         int G = (int)std::min<int64_t>(max_ctas, ((nchunks + (int64_t)w * rounds - 1) / ((int64_t)w * rounds) + cs - 1) / cs * cs);
         if (G < cs) G = cs;
-        // compute ~ chunks an SM has to work through; exchange ~ vectors every CTA reads
-        // cycles, calibrated with EH_EPOCH_DEBUG: ~920 per chunk an SM works through, ~110 per vector read
-        double cost = 920.0 * (double)((nchunks + G - 1) / G) + 110.0 * (G / cs);
+        double cost = (double)rounds;  // strict '<' below keeps the preference order among equal round counts
         if (cost < best_cost) {
             best_cost = cost; best_cs = cs; best_G = G; best_w = w;
             best_work = std::max((size_t)w * stage, (size_t)(G / cs) * npartp * 4);
@@ -535,12 +539,12 @@ eh_status run_persistent(eh_ctx* c, int64_t n, int64_t B, int64_t first, int64_t
     CK(cudaMemsetAsync(c->d_counter, 0, 4 * sizeof(unsigned), c->stream));
     EpochArgs a;
     memset(&a, 0, sizeof a);
-    a.rec = reinterpret_cast<const float4*>(c->split[EH_SPLIT_TRAIN].rec);
-    a.idx = c->d_idx; a.n = n; a.B = (int)B; a.first_step = first; a.nsteps = (int)nsteps; a.nb = (int)nb;
+    a.rec = reinterpret_cast<const float4*>(rec);
+    a.idx = idx; a.n = n; a.B = (int)B; a.first_step = first; a.nsteps = (int)nsteps; a.nb = (int)nb;
     a.pblock = c->d_theta; a.nflat = c->nflat; a.ntheta = c->ntheta;
     a.m = c->d_m; a.v = c->d_v; a.ost = c->d_ost;
     a.wsrc = c->d_wsrc; a.pmap = c->d_pmap; a.cells = c->d_cells; a.pspan = c->d_pspan; a.slot_of_flat = c->d_slot_of_flat;
-    a.bscal = c->d_bscal; a.pbuf = c->d_pbuf; a.counter = c->d_counter; a.stats_out = c->d_stats;
+    a.bscal = bscal; a.pbuf = c->d_pbuf; a.counter = c->d_counter; a.stats_out = c->d_stats;
     a.npartp = npartp; a.work_floats = (int)(best_work / 4); a.csize = cs; a.T = c->n_targ; a.agg_mean = c->agg_mean;
     for (int t = 0; t < MAXT; t++) a.loss_kind[t] = c->loss_kind[t];
     for (int s = 0; s < MAXPS; s++) a.slot[s] = c->slots[s];
@@ -550,16 +554,14 @@ eh_status run_persistent(eh_ctx* c, int64_t n, int64_t B, int64_t first, int64_t
     a.eta = c->eta; a.beta1 = c->beta1; a.beta2 = c->beta2; a.eps = c->eps; a.lambda = c->lambda;
     a.world = c->world; a.rank = c->rank; a.step_base = c->dp_steps; a.err = c->d_dperr;
     for (int r = 0; r < c->world && c->world > 1; r++) {
-        a.flag_peer[r] = reinterpret_cast<unsigned*>(c->dp_peer[r]);
-        a.inbox_peer[r] = reinterpret_cast<float*>(reinterpret_cast<char*>(c->dp_peer[r]) + 256);
+        a.inbox_peer[r] = reinterpret_cast<uint2*>(c->dp_peer[r]);
     }
-    CK(cudaMemsetAsync(c->d_dperr, 0, sizeof(unsigned), c->stream));
     long long* d_dbg = nullptr;
-    const char* dbg_path = getenv("EH_EPOCH_DEBUG");
-    if (dbg_path && nsteps <= 64) {
+    if (dbg_out && getenv("EH_EPOCH_DEBUG") && nsteps <= 64) {
         CK(dalloc(&d_dbg, (size_t)nsteps * G * 32));
         CK(cudaMemsetAsync(d_dbg, 0, (size_t)nsteps * G * 32 * sizeof(long long), c->stream));
         a.dbg = d_dbg;
+        *dbg_out = d_dbg;
     }
     CK(cudaEventRecord(c->ev0, c->stream));
     cudaError_t le = v->launch_epoch(a, G, w, smem, cs, c->stream);
@@ -571,23 +573,38 @@ eh_status run_persistent(eh_ctx* c, int64_t n, int64_t B, int64_t first, int64_t
     }
     CK(cudaEventRecord(c->ev1, c->stream));
     c->epoch_csize = cs; c->epoch_grid = G; c->epoch_warps = w;
-    k_losses_from_stats<<<(unsigned)((nsteps + 127) / 128), 128, 0, c->stream>>>(c->d_stats, c->d_bscal, first, (int)nb,
+    if (c->world > 1) c->dp_steps += (unsigned)nsteps;
+    k_losses_from_stats<<<(unsigned)((nsteps + 127) / 128), 128, 0, c->stream>>>(c->d_stats, bscal, first, (int)nb,
                                                                                  (int)nsteps, c->n_targ, c->agg_mean,
-                                                                                 c->d_losskind, c->d_loss);
+                                                                                 c->d_losskind, loss_out);
     CK(cudaGetLastError());
+    *used = true;
+    return EH_OK;
+}
+
+// Persistent path: all nsteps optimiser steps of the resident index stream in ONE launch, synchronous
+eh_status run_persistent(eh_ctx* c, int64_t n, int64_t B, int64_t first, int64_t nsteps, bool* used)
+{
+    long long* d_dbg = nullptr;
+    eh_status s = enqueue_persistent(c, c->split[EH_SPLIT_TRAIN].rec, c->d_idx, c->d_bscal, c->d_loss, n, B, first, nsteps,
+                                     used, &d_dbg);
+    if (s != EH_OK || !*used) return s;
     CK(cudaMemcpyAsync(c->h_loss, c->d_loss, (size_t)nsteps * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     unsigned herr = 0;
     CK(cudaMemcpyAsync(&herr, c->d_dperr, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    if (c->world > 1) c->dp_steps += (unsigned)nsteps;
-    if (herr) return fail(c, EH_ENCCL, "persistent kernel gave up waiting (a CTA or a data-parallel peer never arrived)");
+    if (herr) {
+        cudaMemset(c->d_dperr, 0, sizeof(unsigned));
+        return fail(c, EH_ENCCL, "persistent kernel gave up waiting (a CTA or a data-parallel peer never arrived)");
+    }
     CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
     if (d_dbg) {
+        const int G = c->epoch_grid;
         std::vector<long long> h((size_t)nsteps * G * 32);
         CK(cudaMemcpy(h.data(), d_dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
         cudaFree(d_dbg);
-        if (FILE* f = fopen(dbg_path, "wb")) {
-            long long hdr[4] = {nsteps, G, w, cs};
+        if (FILE* f = fopen(getenv("EH_EPOCH_DEBUG"), "wb")) {
+            long long hdr[4] = {nsteps, G, c->epoch_warps, c->epoch_csize};
             fwrite(hdr, sizeof hdr, 1, f);
             fwrite(h.data(), sizeof(long long), h.size(), f);
             fclose(f);
@@ -595,7 +612,6 @@ eh_status run_persistent(eh_ctx* c, int64_t n, int64_t B, int64_t first, int64_t
     }
     c->last_launches = 1;
     c->last_step_ms = c->last_ms;
-    *used = true;
     return EH_OK;
 }
 
@@ -951,6 +967,18 @@ eh_status enqueue_host_step(eh_ctx* c, HostStage& h, int64_t B, const float* X, 
         k_batch_stats<<<1, 256, 0, c->stream>>>(a);
         CK(cudaGetLastError());
     }
+    if (c->world > 1) {
+        // data parallel: one persistent launch of a single step (the exchange lives in that kernel)
+        if (heavy) return fail(c, EH_EUNSUPPORTED, "data-parallel mode needs NaN-free targets, no nseLoss and no input BatchNorm");
+        k_fill_bscal<<<1, 32, 0, c->stream>>>(h.d_bscal, 1, B, (int)B, c->n_targ, c->agg_mean, c->world);
+        CK(cudaGetLastError());
+        if (c->stats_cap < 1) { CK(dalloc(&c->d_stats, (size_t)64 * MAXT)); c->stats_cap = 64; }
+        bool used = false;
+        eh_status s = enqueue_persistent(c, h.d_rec, nullptr, h.d_bscal, h.d_loss, B, B, 0, 1, &used, nullptr);
+        if (s != EH_OK) return s;
+        if (!used) return fail(c, EH_EUNSUPPORTED, "persistent kernel unavailable for this shape: %s", c->err.c_str());
+        return EH_OK;
+    }
     StepArgs a;
     fill_step_args(c, a);
     a.rec = reinterpret_cast<const float4*>(h.d_rec);
@@ -1029,6 +1057,7 @@ eh_status eh_create(eh_ctx** out, const eh_model_desc* desc)
         CK(dalloc(&c->d_pbuf, (size_t)2 * (c->nsm + 8) * rup4(v->NPART)));
         CK(dalloc(&c->d_counter, (size_t)4));
         CK(dalloc(&c->d_dperr, (size_t)1));
+        CK(cudaMemset(c->d_dperr, 0, sizeof(unsigned)));
         CK(dalloc(&c->d_m, (size_t)c->nflat));
         CK(dalloc(&c->d_v, (size_t)c->nflat));
         CK(dalloc(&c->d_grad, (size_t)c->nflat));
@@ -1320,7 +1349,13 @@ eh_status eh_sync(eh_ctx* c)
 {
     if (!c) return EH_EINVAL;
     CK(cudaSetDevice(c->device));
+    unsigned herr = 0;
+    CK(cudaMemcpyAsync(&herr, c->d_dperr, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    if (herr) {
+        cudaMemset(c->d_dperr, 0, sizeof(unsigned));
+        return fail(c, EH_ENCCL, "persistent kernel gave up waiting (a CTA or a data-parallel peer never arrived)");
+    }
     for (auto& pr : c->pending_loss)
         if (pr.second) *pr.second = *pr.first;
     c->pending_loss.clear();
@@ -1404,7 +1439,7 @@ eh_status eh_comm_id(eh_ctx* c, void* id_out)
     if (!id_out) return fail(c, EH_EINVAL, "null id_out");
     CK(cudaSetDevice(c->device));
     if (!c->dp_block) {
-        const size_t bytes = 256 + (size_t)2 * EH_MAX_WORLD * rup4(c->var->NPART) * sizeof(float);
+        const size_t bytes = (size_t)2 * EH_MAX_WORLD * rup4(c->var->NPART) * sizeof(uint2);  // {value, tag} slots
         CK(cudaMalloc(&c->dp_block, bytes));
         CK(cudaMemset(c->dp_block, 0, bytes));
     }

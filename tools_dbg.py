@@ -15,4 +15,7 @@ for s in range(1, nsteps):
         print(f"step {s}: total cycles median {np.median(tot):.0f} max {tot.max():.0f}")
         for i, nme in enumerate(names):
             print(f"   {nme:28s} median {np.median(ph[:, i]):8.0f}  min {ph[:, i].min():8.0f}  max {ph[:, i].max():8.0f}")
+        if d[s, :, 27].any():
+            rd = (d[s, :, 27] - d[s, :, 6]).astype(np.float64); ex = (d[s, :, 28] - d[s, :, 27]).astype(np.float64); ad = (d[s, :, 7] - d[s, :, 28]).astype(np.float64)
+            print(f"     of which: vector read median {np.median(rd):.0f}, rank exchange median {np.median(ex):.0f} (max {ex.max():.0f}), adam+init median {np.median(ad):.0f}")
         print(f"   per-warp compute: median {np.median(wend):.0f} min {wend.min():.0f} max {wend.max():.0f}; per-CTA slowest warp median {np.median(wend.max(axis=1)):.0f}")
