@@ -109,7 +109,7 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_baseline(eh, model, seconds=12.0, max_steps=120):
+def cpu_baseline(eh, model, seconds=12.0, max_steps=4000):
     """oracle on all host cores, bounded sample of the same workload (batch 65536 out of 2^22 samples)"""
     from oracle import oracle as orc
     n = 1 << 22
@@ -222,7 +222,10 @@ def main():
     per_gpu_sps = K * B / (dev_ms * 1e-3)
     achieved = per_gpu_sps * BYTES_PER_SAMPLE / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src,
+                # dram__bytes_read+write of k_epoch from ncu --set full (profiles/r1_k_epoch_v3_cs4_ncu_details.txt):
+                # 58.5 MB for a 12-step launch = 4.88 MB per step, scaled to this launch's K steps
+                "traffic": 4.88e6 * K, "traffic_algorithmic": float(K) * B * BYTES_PER_SAMPLE,
+                "peak_source": peak_src,
                 "kernel": "k_epoch (persistent: fused fwd+process+loss+bwd, grid exchange, Adam; one launch = K steps)",
                 "kernel_us_per_step": 1e3 * dev_ms / K,
                 "binding_roof": {"name": "fp32 issue / shared-memory operand bandwidth (see DESIGN.md section 4)",
@@ -246,7 +249,7 @@ def main():
         hb = []
         for i in range(pool):
             sl = slice(i * B, (i + 1) * B)
-            hb.append((sess.pinned(xf[0][sl]), [sess.pinned(xf[1]["ta"][sl])], [sess.pinned(y["reco"][sl])]))
+            hb.append(sess.host_batch(sess.pinned(xf[0][sl]), [sess.pinned(xf[1]["ta"][sl])], [sess.pinned(y["reco"][sl])]))
         ke = min(K, 2048)
         el = sess.pinned(np.zeros(ke + 8, dtype=np.float32))
         for i in range(8):
@@ -267,6 +270,26 @@ def main():
             dt = float(t.item())
         e2e = {"value": world * ke * B / dt, "unit": "samples/s", "h2d_bytes_per_step": B * BYTES_PER_SAMPLE,
                "d2h_bytes_per_step": 4, "steps": ke, "api": "eh_step_host_async + eh_sync (pinned host batches)"}
+        # the path train() takes: dataset staged once, every epoch call ships the host permutation (8 B/sample)
+        # host->device and the per-step losses back
+        kr = min(K, nb)
+        sess.epoch(perm[: 4 * B], B)
+        barrier()
+        tr0 = time.perf_counter()
+        reps = max(1, min(8, K // kr))
+        for _ in range(reps):
+            sess.epoch(perm[: kr * B], B)
+        tr1 = time.perf_counter()
+        barrier()
+        dtr = tr1 - tr0
+        if dist is not None:
+            import torch
+            t = torch.tensor([dtr], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dtr = float(t.item())
+        e2e["resident_dataset"] = {"value": world * reps * kr * B / dtr, "unit": "samples/s",
+                                   "h2d_bytes_per_step": 8 * B, "d2h_bytes_per_step": 4, "steps": reps * kr,
+                                   "api": "eh_epoch(host permutation) on the dataset staged once by eh_upload"}
 
     if rank == 0:
         line = {"metric": "training samples/sec (fwd+bwd+Adam)", "value": value, "unit": "samples/s", "n_gpus": world,

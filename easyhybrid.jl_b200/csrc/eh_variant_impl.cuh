@@ -1,5 +1,6 @@
 // eh_variant_impl.cuh -- template glue that turns a StepCfg into a registry entry.
 #pragma once
+#include <cstdlib>
 #include "eh_variants.h"
 #include "eh_epoch_kernel.cuh"
 #include "eh_eval_kernel.cuh"
@@ -51,9 +52,12 @@ static void epoch_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int gr
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     int n = 0;
-    attr[n].id = cudaLaunchAttributeCooperative;
-    attr[n].val.cooperative = 1;
-    n++;
+    // EH_NO_COOP=1 drops the co-residency guarantee (profilers refuse cooperative + cluster launches)
+    if (!getenv("EH_NO_COOP")) {
+        attr[n].id = cudaLaunchAttributeCooperative;
+        attr[n].val.cooperative = 1;
+        n++;
+    }
     if (csize > 1) {
         attr[n].id = cudaLaunchAttributeClusterDimension;
         attr[n].val.clusterDim.x = (unsigned)csize;
@@ -68,6 +72,10 @@ static void epoch_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int gr
 template <class E>
 static cudaError_t launch_epoch_t(const EpochArgs& a, int grid, int nwarps, size_t smem, int csize, cudaStream_t st)
 {
+    if (csize == 1) {
+        void* args[] = {(void*)&a};
+        return cudaLaunchCooperativeKernel((void*)k_epoch<E>, dim3((unsigned)grid), dim3((unsigned)(nwarps * 32)), args, smem, st);
+    }
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attr[2];
     epoch_cfg<E>(cfg, attr, grid, nwarps, smem, csize, st);

@@ -157,15 +157,21 @@ class FusedSession:
         view[...] = arr
         return view
 
-    def step_host_async(self, batch, loss_array, slot):
-        """batch = (X [B,P], [forcing arrays], [target arrays]) -- ideally views from ``pinned``"""
-        X, forc, targ = batch
+    def host_batch(self, X, forc, targ):
+        """marshal one host batch (X [B,P], [forcing arrays], [target arrays]) once; reusable handle"""
         pf = (_fp * max(len(forc), 1))(*[a.ctypes.data_as(_fp) for a in forc])
         pt = (_fp * max(len(targ), 1))(*[a.ctypes.data_as(_fp) for a in targ])
-        self._inflight = getattr(self, "_inflight", [])
-        self._inflight.append((pf, pt))
+        return (X.shape[0], X.ctypes.data_as(_fp), pf, pt, (X, forc, targ))
+
+    def step_host_async(self, batch, loss_array, slot):
+        """batch: a ``host_batch`` handle (or the raw tuple) -- ideally over views from ``pinned``"""
+        if len(batch) == 3:
+            batch = self.host_batch(*batch)
+        n, Xp, pf, pt, _keep = batch
         lp = C.cast(loss_array.ctypes.data + 4 * slot, _fp)
-        self._ck(self.lib.eh_step_host_async(self.h, X.shape[0], X.ctypes.data_as(_fp), pf, pt, lp))
+        st = self.lib.eh_step_host_async(self.h, n, Xp, pf, pt, lp)
+        if st != _abi.EH_OK:
+            self._ck(st)
 
     def sync(self):
         self._ck(self.lib.eh_sync(self.h))
