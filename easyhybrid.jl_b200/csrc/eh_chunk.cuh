@@ -40,10 +40,15 @@ struct PSlot {
     float fixedv;  // FIXED: default value
 };
 
-template <int P_, int NH_, int H_, int NOUT_, int ACT_, bool SCALE_, class PM_>
+// SPL = samples per lane of the FFMA2 engine: 1 -> 32-sample chunks (most warps), 2 -> 64-sample chunks
+// (every weight fetched from shared memory feeds two samples: half the LDS traffic per sample)
+template <int P_, int NH_, int H_, int NOUT_, int ACT_, bool SCALE_, class PM_, int SPL_ = 1>
 struct StepCfg {
     static constexpr int P = P_, NH = NH_, H = H_, NOUT = NOUT_, ACT = ACT_;
     static constexpr bool SCALE = SCALE_;
+    static constexpr int SPL = SPL_;
+    static constexpr int CHUNKS = 32 * SPL_;        // samples per warp pass
+    static constexpr int RS = CHUNKS + 4;           // floats per staging row (bank skew)
     using PM = PM_;
     static constexpr int F = PM::NF, T = PM::NT, NPS = PM::NPS;
     // output-layer dW kept in registers when all per-lane scalars fit one 32-value transpose-reduce
@@ -55,10 +60,10 @@ struct StepCfg {
     static constexpr int NBI = (NB + 31) / 32;             // dW tiles per lane
     static constexpr int NROWS = D.nrows() + (ACT_ == ACT_SWISH ? NH_ * H_ : 0);
     static constexpr int AUXROW0 = D.nrows();              // swish sigma rows
-    static constexpr int STAGE_FLOATS = NROWS * ROWSTRIDE;  // per warp
+    static constexpr int STAGE_FLOATS = NROWS * RS;  // per warp
     static constexpr int NW = D.nweights();
     static constexpr int NPART = D.npart();
-    static_assert(P_ <= MAXP && H_ % 4 == 0 && NOUT_ <= 4, "shape limits");
+    static_assert(P_ <= MAXP && H_ % 4 == 0 && NOUT_ <= 4 && (SPL_ == 1 || SPL_ == 2), "shape limits");
 };
 
 // shared memory carve-up (floats): [weights NW pad4][scalars 128][per-warp stage ...]
@@ -70,6 +75,25 @@ __device__ __forceinline__ constexpr int grow(int g0, int k) { return 5 * (g0 + 
 
 __device__ __forceinline__ float comp(const float2* v, int k) { return (k & 1) ? v[k >> 1].y : v[k >> 1].x; }
 
+// staging tile access: lane l owns columns SPL*l .. SPL*l + SPL - 1 of a row (one 4- or 8-byte access)
+template <int S>
+__device__ __forceinline__ void stage_put(float* row, int lane, const float (&v)[S])
+{
+    if (S == 2) *reinterpret_cast<float2*>(row + 2 * lane) = f2(v[0], v[S - 1]);
+    else row[lane] = v[0];
+}
+template <int S>
+__device__ __forceinline__ void stage_get(const float* row, int lane, float (&v)[S])
+{
+    if (S == 2) {
+        float2 t = *reinterpret_cast<const float2*>(row + 2 * lane);
+        v[0] = t.x;
+        v[S - 1] = t.y;
+    } else {
+        v[0] = row[lane];
+    }
+}
+
 // Dense chain forward for the sample of this lane (prepare_hidden_chain,
 // src/models/NNModels.jl:225-230).  hp holds neuron PAIRS; returns a_NH in hp, outputs in zo.
 template <class C, bool STAGE>
@@ -78,7 +102,8 @@ __device__ __forceinline__ void chain_forward(const float* sW, float* stage, int
 {
     constexpr ShapeDims D = C::D;
     constexpr int P = C::P, NH = C::NH, H = C::H, NOUT = C::NOUT, HP = C::H / 2;
-    constexpr int RS = ROWSTRIDE;
+    constexpr int RS = C::RS;
+    static_assert(!STAGE || C::SPL == 1, "staging forward is the single-sample form");
     {
         const float4* b4 = reinterpret_cast<const float4*>(sW + D.off_b1());
 #pragma unroll
@@ -204,16 +229,19 @@ template <class C>
 __device__ __forceinline__ void init_stage_rows(float* stage, int lane)
 {
     constexpr ShapeDims D = C::D;
-    constexpr int RS = ROWSTRIDE;
+    constexpr int RS = C::RS, S = C::SPL;
+    float one[S], zero[S];
+#pragma unroll
+    for (int i = 0; i < S; i++) { one[i] = 1.f; zero[i] = 0.f; }
 #pragma unroll
     for (int l = 1; l <= D.nlt(); l++) {
         const int din = D.din(l), ka = D.ka(l), gA = D.gA(l);
 #pragma unroll
-        for (int k = din; k < ka; k++) stage[grow(gA, k) * RS + lane] = (k == din) ? 1.f : 0.f;
+        for (int k = din; k < ka; k++) stage_put<S>(stage + grow(gA, k) * RS, lane, (k == din) ? one : zero);
     }
     if (!C::LR) {
 #pragma unroll
-        for (int o = C::NOUT; o < rup4(C::NOUT); o++) stage[grow(D.gD(C::NH + 1), o) * RS + lane] = 0.f;
+        for (int o = C::NOUT; o < rup4(C::NOUT); o++) stage_put<S>(stage + grow(D.gD(C::NH + 1), o) * RS, lane, zero);
     }
 }
 
@@ -269,95 +297,211 @@ struct LastAcc {
 };
 
 // ---- per-sample phase: forward, physics, masked residual, backward data pass, staging ----
-// rec: this lane's record (canonical order), valid: sample exists.
+// A lane owns S = SPL samples (columns S*lane .. of the staging rows).  Every weight pair fetched from
+// shared memory (one LDS.128 = two pairs) is used for all S samples: FFMA2 over NEURON pairs with the
+// activation of sample s as the scalar-broadcast operand.
+// rec[s]: record of sample s of this lane (canonical order), valid[s]: sample exists.
 template <class C>
-__device__ __forceinline__ void chunk_sample_phase(const float* rec, bool valid, const float* sW, const float* sS,
-                                                   float* stage, int lane, const PSlot* slot, const int* loss_kind,
-                                                   const PmCtx& cx, ChunkStats& st, LastAcc<C>& la)
+__device__ __forceinline__ void chunk_sample_phase(const float (*rec)[C::R4], const bool* valid, const float* sW,
+                                                   const float* sS, float* stage, int lane, const PSlot* slot,
+                                                   const int* loss_kind, const PmCtx& cx, ChunkStats& st, LastAcc<C>& la)
 {
     constexpr ShapeDims D = C::D;
     constexpr int P = C::P, NH = C::NH, H = C::H, NOUT = C::NOUT, T = C::T, F = C::F, NPS = C::NPS, HP = C::H / 2;
-    constexpr int RS = ROWSTRIDE;
+    constexpr int RS = C::RS, S = C::SPL;
     using PM = typename C::PM;
 
-    float x[P], f[F > 0 ? F : 1], y[T];
+    float x[S][P];
 #pragma unroll
     for (int k = 0; k < P; k++) {
-        // input BatchNorm(affine=false): (x - mu) * rstd with per-batch statistics (identity: mu 0, rstd 1)
-        x[k] = (rec[k] - sS[SS_BN + 2 * k]) * sS[SS_BN + 2 * k + 1];
-        stage[grow(D.gA(1), k) * RS + lane] = x[k];
+        float v[S];
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            // input BatchNorm(affine=false): (x - mu) * rstd with per-batch statistics (identity: mu 0, rstd 1)
+            x[s][k] = (rec[s][k] - sS[SS_BN + 2 * k]) * sS[SS_BN + 2 * k + 1];
+            v[s] = x[s][k];
+        }
+        stage_put<S>(stage + grow(D.gA(1), k) * RS, lane, v);
     }
-#pragma unroll
-    for (int k = 0; k < F; k++) f[k] = rec[P + k];
-#pragma unroll
-    for (int k = 0; k < T; k++) y[k] = rec[P + F + k];
 
-    float2 hp[HP];
-    float zo[NOUT];
-    chain_forward<C, true>(sW, stage, lane, x, hp, zo);
-
-    // process parameters (GenericHybridModel.jl:377-414) and physics (:425)
-    float pv[NPS], sg[NPS], yh[T], sv[4], gy[T], gp[NPS];
-    resolve_params<C>(slot, sS, zo, pv, sg);
-    PM::fwd(pv, f, cx, yh, sv);
-    // masked residual: valid_mask = !isnan(y) (train.jl:221-232); seeds dL/dyhat
+    // ---- forward (prepare_hidden_chain, src/models/NNModels.jl:225-230) ----
+    float2 hp[S][HP];
+    {
+        const float4* b4 = reinterpret_cast<const float4*>(sW + D.off_b1());
 #pragma unroll
-    for (int t = 0; t < T; t++) {
-        const bool m = valid && (y[t] == y[t]);
-        const float r = m ? yh[t] - y[t] : 0.f;
-        const float c = sS[SS_C + t];
-        if (loss_kind[t] == LOSS_MAE) {
-            st.loss[t] += fabsf(r);
-            gy[t] = r > 0.f ? c : (r < 0.f ? -c : 0.f);
-        } else {
-            st.loss[t] = fmaf(r, r, st.loss[t]);
-            gy[t] = 2.f * c * r;
+        for (int j = 0; j < HP; j += 2) {
+            float4 b = b4[j >> 1];
+#pragma unroll
+            for (int s = 0; s < S; s++) { hp[s][j] = f2(b.x, b.y); hp[s][j + 1] = f2(b.z, b.w); }
+        }
+#pragma unroll
+        for (int k = 0; k < P; k++) {
+            const float4* w4 = reinterpret_cast<const float4*>(sW + D.off_w1f() + k * H);
+#pragma unroll
+            for (int j = 0; j < HP; j += 2) {
+                float4 w = w4[j >> 1];
+#pragma unroll
+                for (int s = 0; s < S; s++) {
+                    hp[s][j] = fma2s(f2(w.x, w.y), x[s][k], hp[s][j]);
+                    hp[s][j + 1] = fma2s(f2(w.z, w.w), x[s][k], hp[s][j + 1]);
+                }
+            }
         }
     }
-    PM::bwd(pv, f, cx, yh, sv, gy, gp);
+#pragma unroll
+    for (int l = 1; l <= NH; l++) {
+#pragma unroll
+        for (int j = 0; j < HP; j++) {
+            float lo[S], hi[S], axl[S], axh[S];
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                float2 aux = f2s(0.f);
+                hp[s][j] = act_fwd2<C::ACT>(hp[s][j], aux);
+                lo[s] = hp[s][j].x; hi[s] = hp[s][j].y; axl[s] = aux.x; axh[s] = aux.y;
+            }
+            if (l + 1 <= D.nlt()) {
+                stage_put<S>(stage + grow(D.gA(l + 1), 2 * j) * RS, lane, lo);
+                stage_put<S>(stage + grow(D.gA(l + 1), 2 * j + 1) * RS, lane, hi);
+            }
+            if (C::ACT == ACT_SWISH) {
+                stage_put<S>(stage + (C::AUXROW0 + (l - 1) * H + 2 * j) * RS, lane, axl);
+                stage_put<S>(stage + (C::AUXROW0 + (l - 1) * H + 2 * j + 1) * RS, lane, axh);
+            }
+        }
+        if (l < NH) {
+            float2 z[S][HP];
+            const float4* b4 = reinterpret_cast<const float4*>(sW + D.off_b(l + 1));
+#pragma unroll
+            for (int j = 0; j < HP; j += 2) {
+                float4 b = b4[j >> 1];
+#pragma unroll
+                for (int s = 0; s < S; s++) { z[s][j] = f2(b.x, b.y); z[s][j + 1] = f2(b.z, b.w); }
+            }
+#pragma unroll
+            for (int k = 0; k < H; k++) {
+                const float4* w4 = reinterpret_cast<const float4*>(sW + D.off_wf(l + 1) + k * H);
+                float ak[S];
+#pragma unroll
+                for (int s = 0; s < S; s++) ak[s] = comp(hp[s], k);
+#pragma unroll
+                for (int j = 0; j < HP; j += 2) {
+                    float4 w = w4[j >> 1];
+#pragma unroll
+                    for (int s = 0; s < S; s++) {
+                        z[s][j] = fma2s(f2(w.x, w.y), ak[s], z[s][j]);
+                        z[s][j + 1] = fma2s(f2(w.z, w.w), ak[s], z[s][j + 1]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < S; s++)
+#pragma unroll
+                for (int j = 0; j < HP; j++) hp[s][j] = z[s][j];
+        }
+    }
+    // linear output layer, dot form: pairs over k
+    float zo[S][NOUT];
+#pragma unroll
+    for (int o = 0; o < NOUT; o++) {
+        const float4* w4 = reinterpret_cast<const float4*>(sW + D.off_wo() + o * H);
+        float2 s0[S], s1[S];
+#pragma unroll
+        for (int s = 0; s < S; s++) { s0[s] = f2(sW[D.off_bo() + o], 0.f); s1[s] = f2s(0.f); }
+#pragma unroll
+        for (int k = 0; k < HP; k += 2) {
+            float4 w = w4[k >> 1];
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                s0[s] = fma2(f2(w.x, w.y), hp[s][k], s0[s]);
+                s1[s] = fma2(f2(w.z, w.w), hp[s][k + 1], s1[s]);
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < S; s++) {
+            float2 t = add2(s0[s], s1[s]);
+            zo[s][o] = t.x + t.y;
+        }
+    }
 
-    // delta at the linear output layer; phi statistics
-    float dz[NOUT];
+    // ---- process parameters (GenericHybridModel.jl:377-414), physics (:425), masked residual, seeds ----
+    float dz[S][NOUT];
 #pragma unroll
-    for (int o = 0; o < NOUT; o++) dz[o] = 0.f;
+    for (int s = 0; s < S; s++) {
+        float f[F > 0 ? F : 1], y[T], pv[NPS], sg[NPS], yh[T], sv[4], gy[T], gp[NPS];
 #pragma unroll
-    for (int s = 0; s < NPS; s++) {
-        const PSlot sl = slot[s];
-        if (sl.role == ROLE_NEURAL) {
-            float g = gp[s];
-            if (C::SCALE) g *= sl.span * sg[s] * (1.f - sg[s]);
+        for (int k = 0; k < F; k++) f[k] = rec[s][P + k];
 #pragma unroll
-            for (int o = 0; o < NOUT; o++)
-                if (sl.idx == o) dz[o] += g;
-        } else if (sl.role == ROLE_GLOBAL) {
-            st.gphi[s] += gp[s];
+        for (int k = 0; k < T; k++) y[k] = rec[s][P + F + k];
+        resolve_params<C>(slot, sS, zo[s], pv, sg);
+        PM::fwd(pv, f, cx, yh, sv);
+        // valid_mask = !isnan(y) (train.jl:221-232); seeds dL/dyhat
+#pragma unroll
+        for (int t = 0; t < T; t++) {
+            const bool m = valid[s] && (y[t] == y[t]);
+            const float r = m ? yh[t] - y[t] : 0.f;
+            const float c = sS[SS_C + t];
+            if (loss_kind[t] == LOSS_MAE) {
+                st.loss[t] += fabsf(r);
+                gy[t] = r > 0.f ? c : (r < 0.f ? -c : 0.f);
+            } else {
+                st.loss[t] = fmaf(r, r, st.loss[t]);
+                gy[t] = 2.f * c * r;
+            }
+        }
+        PM::bwd(pv, f, cx, yh, sv, gy, gp);
+#pragma unroll
+        for (int o = 0; o < NOUT; o++) dz[s][o] = 0.f;
+#pragma unroll
+        for (int q = 0; q < NPS; q++) {
+            const PSlot sl = slot[q];
+            if (sl.role == ROLE_NEURAL) {
+                float g = gp[q];
+                if (C::SCALE) g *= sl.span * sg[q] * (1.f - sg[q]);
+#pragma unroll
+                for (int o = 0; o < NOUT; o++)
+                    if (sl.idx == o) dz[s][o] += g;
+            } else if (sl.role == ROLE_GLOBAL) {
+                st.gphi[q] += gp[q];
+            }
         }
     }
     if (C::LR) {
         // output-layer weight gradient in registers: dWo[o][k] += dz_o a_NH[k], dbo[o] += dz_o
 #pragma unroll
-        for (int o = 0; o < NOUT; o++) {
-            la.b[o] += dz[o];
+        for (int o = 0; o < NOUT; o++)
 #pragma unroll
-            for (int k = 0; k < HP; k++) la.w[o][k] = fma2s(hp[k], dz[o], la.w[o][k]);
-        }
+            for (int s = 0; s < S; s++) {
+                la.b[o] += dz[s][o];
+#pragma unroll
+                for (int k = 0; k < HP; k++) la.w[o][k] = fma2s(hp[s][k], dz[s][o], la.w[o][k]);
+            }
     } else {
 #pragma unroll
-        for (int o = 0; o < NOUT; o++) stage[grow(D.gD(NH + 1), o) * RS + lane] = dz[o];
+        for (int o = 0; o < NOUT; o++) {
+            float v[S];
+#pragma unroll
+            for (int s = 0; s < S; s++) v[s] = dz[s][o];
+            stage_put<S>(stage + grow(D.gD(NH + 1), o) * RS, lane, v);
+        }
     }
 
-    // backward data pass: delta_l for l = NH .. 1 (hp still holds a_NH), neuron pairs
-    float2 d[HP];
+    // ---- backward data pass: delta_l for l = NH .. 1 (hp still holds a_NH), neuron pairs ----
+    float2 d[S][HP];
 #pragma unroll
-    for (int k = 0; k < HP; k++) d[k] = f2s(0.f);
+    for (int s = 0; s < S; s++)
+#pragma unroll
+        for (int k = 0; k < HP; k++) d[s][k] = f2s(0.f);
 #pragma unroll
     for (int o = 0; o < NOUT; o++) {
         const float4* w4 = reinterpret_cast<const float4*>(sW + D.off_wo() + o * H);
 #pragma unroll
         for (int k = 0; k < HP; k += 2) {
             float4 w = w4[k >> 1];
-            d[k] = fma2s(f2(w.x, w.y), dz[o], d[k]);
-            d[k + 1] = fma2s(f2(w.z, w.w), dz[o], d[k + 1]);
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                d[s][k] = fma2s(f2(w.x, w.y), dz[s][o], d[s][k]);
+                d[s][k + 1] = fma2s(f2(w.z, w.w), dz[s][o], d[s][k + 1]);
+            }
         }
     }
 #pragma unroll
@@ -365,34 +509,53 @@ __device__ __forceinline__ void chunk_sample_phase(const float* rec, bool valid,
         // times act'(a_l); a_l (and sigma for swish) come back from the staging tile for l < NH
 #pragma unroll
         for (int k = 0; k < HP; k++) {
-            float2 al = hp[k];
-            if (l < NH) al = f2(stage[grow(D.gA(l + 1), 2 * k) * RS + lane], stage[grow(D.gA(l + 1), 2 * k + 1) * RS + lane]);
-            float2 aux = f2s(0.f);
-            if (C::ACT == ACT_SWISH)
-                aux = f2(stage[(C::AUXROW0 + (l - 1) * H + 2 * k) * RS + lane],
-                         stage[(C::AUXROW0 + (l - 1) * H + 2 * k + 1) * RS + lane]);
-            d[k] = mul2(d[k], act_bwd2<C::ACT>(al, aux));
-            stage[grow(D.gD(l), 2 * k) * RS + lane] = d[k].x;
-            stage[grow(D.gD(l), 2 * k + 1) * RS + lane] = d[k].y;
+            float alo[S], ahi[S], xlo[S], xhi[S], dlo[S], dhi[S];
+            if (l < NH) {
+                stage_get<S>(stage + grow(D.gA(l + 1), 2 * k) * RS, lane, alo);
+                stage_get<S>(stage + grow(D.gA(l + 1), 2 * k + 1) * RS, lane, ahi);
+            }
+            if (C::ACT == ACT_SWISH) {
+                stage_get<S>(stage + (C::AUXROW0 + (l - 1) * H + 2 * k) * RS, lane, xlo);
+                stage_get<S>(stage + (C::AUXROW0 + (l - 1) * H + 2 * k + 1) * RS, lane, xhi);
+            }
+#pragma unroll
+            for (int s = 0; s < S; s++) {
+                float2 al = (l < NH) ? f2(alo[s], ahi[s]) : hp[s][k];
+                float2 aux = (C::ACT == ACT_SWISH) ? f2(xlo[s], xhi[s]) : f2s(0.f);
+                d[s][k] = mul2(d[s][k], act_bwd2<C::ACT>(al, aux));
+                dlo[s] = d[s][k].x;
+                dhi[s] = d[s][k].y;
+            }
+            stage_put<S>(stage + grow(D.gD(l), 2 * k) * RS, lane, dlo);
+            stage_put<S>(stage + grow(D.gD(l), 2 * k + 1) * RS, lane, dhi);
         }
         if (l > 1) {
             // delta_{l-1}[k] = sum_j W_l[j][k] delta_l[j]  (j-major copy of W_l, pairs over k)
-            float2 dn[HP];
+            float2 dn[S][HP];
 #pragma unroll
-            for (int k = 0; k < HP; k++) dn[k] = f2s(0.f);
+            for (int s = 0; s < S; s++)
+#pragma unroll
+                for (int k = 0; k < HP; k++) dn[s][k] = f2s(0.f);
 #pragma unroll
             for (int j = 0; j < H; j++) {
                 const float4* w4 = reinterpret_cast<const float4*>(sW + D.off_wb(l) + j * H);
-                const float dj = comp(d, j);
+                float dj[S];
+#pragma unroll
+                for (int s = 0; s < S; s++) dj[s] = comp(d[s], j);
 #pragma unroll
                 for (int k = 0; k < HP; k += 2) {
                     float4 w = w4[k >> 1];
-                    dn[k] = fma2s(f2(w.x, w.y), dj, dn[k]);
-                    dn[k + 1] = fma2s(f2(w.z, w.w), dj, dn[k + 1]);
+#pragma unroll
+                    for (int s = 0; s < S; s++) {
+                        dn[s][k] = fma2s(f2(w.x, w.y), dj[s], dn[s][k]);
+                        dn[s][k + 1] = fma2s(f2(w.z, w.w), dj[s], dn[s][k + 1]);
+                    }
                 }
             }
 #pragma unroll
-            for (int k = 0; k < HP; k++) d[k] = dn[k];
+            for (int s = 0; s < S; s++)
+#pragma unroll
+                for (int k = 0; k < HP; k++) d[s][k] = dn[s][k];
         }
     }
 }
@@ -402,14 +565,14 @@ template <class C>
 __device__ __forceinline__ void chunk_dw_phase(const float* stage, int lane, const int* rowD, const int* rowA,
                                                float2 (*acc)[16])
 {
-    constexpr int RS = ROWSTRIDE;
+    constexpr int RS = C::RS;
 #pragma unroll
     for (int i = 0; i < C::NBI; i++) {
         if (lane + 32 * i < C::NB) {
             const float* pd = stage + rowD[i] * RS;
             const float* pa = stage + rowA[i] * RS;
 #pragma unroll 2
-            for (int c = 0; c < CHUNK; c += 4) {
+            for (int c = 0; c < C::CHUNKS; c += 4) {
                 float4 dv[4], av[4];
 #pragma unroll
                 for (int j = 0; j < 4; j++) dv[j] = *reinterpret_cast<const float4*>(pd + j * RS + c);

@@ -8,19 +8,20 @@ namespace eh {
 template <class C>
 struct EngFfma {
     using Cfg = C;
-    static constexpr int ENGINE = 0;
+    static constexpr int ENGINE = C::SPL == 2 ? 2 : 0;
     static constexpr int STAGE_FLOATS = C::STAGE_FLOATS;  // per-warp shared memory
     static constexpr int NPART = C::NPART;
     static constexpr int OFF_STATS = C::D.npart_dw();
-    static constexpr int MAX_WARPS = 16;
+    static constexpr int CHUNK = C::CHUNKS;           // samples per warp pass
+    static constexpr int MAX_WARPS = C::SPL == 2 ? 10 : 16;
 
     struct State {
         float2 acc[C::NBI][16];
         ChunkStats st;
         LastAcc<C> la;
         int rowD[C::NBI], rowA[C::NBI];
-        float4 r[C::R4 / 4];
-        bool valid;
+        float4 r[C::SPL][C::R4 / 4];
+        bool valid[C::SPL];
     };
 
     __device__ __forceinline__ static void init_warp(State& s, float* stage, int lane)
@@ -41,30 +42,21 @@ struct EngFfma {
         for (int t = 0; t < MAXPS; t++) s.st.gphi[t] = 0.f;
         s.la.zero();
     }
-    // prefetch the records of chunk `chunk` of the batch (idx + its base already applied by the caller)
+    // prefetch the records of chunk `chunk`: lane l owns samples SPL*l .. SPL*l + SPL - 1 of the chunk
     __device__ __forceinline__ static void fetch(State& s, const float4* rec, const int* idx, long long rec_base, int B,
                                                  int chunk, int nchunks, int lane)
     {
-        const int smp = chunk * CHUNK + lane;
-        s.valid = chunk < nchunks && smp < B;
-        long long i = rec_base + smp;
-        if (idx && s.valid) i = idx[smp];
 #pragma unroll
-        for (int q = 0; q < C::R4 / 4; q++)
-            s.r[q] = s.valid ? __ldg(rec + i * (C::R4 / 4) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    // consume the prefetched records (the caller issues the next fetch right after `take`)
-    struct Taken {
-        float rec[C::R4];
-        bool valid;
-    };
-    __device__ __forceinline__ static void take(const State& s, Taken& t)
-    {
+        for (int sp = 0; sp < C::SPL; sp++) {
+            const int smp = chunk * CHUNK + C::SPL * lane + sp;
+            const bool v = chunk < nchunks && smp < B;
+            s.valid[sp] = v;
+            long long i = rec_base + smp;
+            if (idx && v) i = idx[smp];
 #pragma unroll
-        for (int q = 0; q < C::R4 / 4; q++) {
-            t.rec[4 * q] = s.r[q].x; t.rec[4 * q + 1] = s.r[q].y; t.rec[4 * q + 2] = s.r[q].z; t.rec[4 * q + 3] = s.r[q].w;
+            for (int q = 0; q < C::R4 / 4; q++)
+                s.r[sp][q] = v ? __ldg(rec + i * (C::R4 / 4) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        t.valid = s.valid;
     }
     // process the prefetched chunk; `next` (chunk index, may be past the end) is prefetched right after the
     // current records have been copied out, so its latency hides behind the compute
@@ -72,10 +64,19 @@ struct EngFfma {
                                                  float* stage, int lane, const PSlot* slot, const int* loss_kind,
                                                  const PmCtx& cx)
     {
-        Taken t;
-        take(s, t);
+        float rec[C::SPL][C::R4];
+        bool valid[C::SPL];
+#pragma unroll
+        for (int sp = 0; sp < C::SPL; sp++) {
+#pragma unroll
+            for (int q = 0; q < C::R4 / 4; q++) {
+                rec[sp][4 * q] = s.r[sp][q].x; rec[sp][4 * q + 1] = s.r[sp][q].y;
+                rec[sp][4 * q + 2] = s.r[sp][q].z; rec[sp][4 * q + 3] = s.r[sp][q].w;
+            }
+            valid[sp] = s.valid[sp];
+        }
         fetch(s, fa.rec, fa.idx, fa.rec_base, fa.B, next, fa.nchunks, lane);
-        chunk_sample_phase<C>(t.rec, t.valid, sW, sS, stage, lane, slot, loss_kind, cx, s.st, s.la);
+        chunk_sample_phase<C>(rec, valid, sW, sS, stage, lane, slot, loss_kind, cx, s.st, s.la);
         __syncwarp();
         chunk_dw_phase<C>(stage, lane, s.rowD, s.rowA, s.acc);
         __syncwarp();

@@ -50,6 +50,7 @@ struct EngMma {
     static_assert(C::H == 16 && C::NH == 2, "the register-resident MMA engine covers two hidden layers of width <= 16");
     static_assert(C::P <= 4 && C::NOUT <= 2, "narrow first / output layers");
     static constexpr int ENGINE = 1;
+    static constexpr int CHUNK = 32;                  // two 16-sample tiles per warp pass
     static constexpr int P = C::P, H = C::H, NOUT = C::NOUT, T = C::T, F = C::F, NPS = C::NPS;
     static constexpr int NT = H / 8;                  // n-tiles == k-steps of the hidden layer
     static constexpr int RS_T = H + 8;                // transpose tile row stride (floats), conflict-free

@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(E::MAX_WARPS * 32, 1) k_epoch(const EpochArgs 
         long long b = a.first_step % a.nb;
         long long rem = a.n - b * a.B;
         int Bk = (int)(rem < a.B ? rem : a.B);
-        E::fetch(st, a.rec, a.idx ? a.idx + b * a.B : nullptr, a.idx ? 0 : b * a.B, Bk, gw, (Bk + CHUNK - 1) / CHUNK, lane);
+        E::fetch(st, a.rec, a.idx ? a.idx + b * a.B : nullptr, a.idx ? 0 : b * a.B, Bk, gw, (Bk + E::CHUNK - 1) / E::CHUNK, lane);
     }
     unsigned bar = 0;
     // per-batch scalars of the coming step, prefetched one step ahead (a dependent global load otherwise)
@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(E::MAX_WARPS * 32, 1) k_epoch(const EpochArgs 
         const long long b = (a.first_step + s) % a.nb;
         const long long rem = a.n - b * a.B;
         const int Bk = (int)(rem < a.B ? rem : a.B);
-        const int nchunks = (Bk + CHUNK - 1) / CHUNK;
+        const int nchunks = (Bk + E::CHUNK - 1) / E::CHUNK;
         const int par = s & 1;
         if (threadIdx.x < MAXT) sS[SS_C + threadIdx.x] = pre_bs;
         else if (threadIdx.x < MAXT + 2 * C::P) sS[SS_BN + threadIdx.x - MAXT] = pre_bs;
@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(E::MAX_WARPS * 32, 1) k_epoch(const EpochArgs 
             long long b2 = (a.first_step + s + 1) % a.nb;
             long long rem2 = a.n - b2 * a.B;
             int Bk2 = (int)(rem2 < a.B ? rem2 : a.B);
-            E::fetch(st, a.rec, a.idx ? a.idx + b2 * a.B : nullptr, a.idx ? 0 : b2 * a.B, Bk2, gw, (Bk2 + CHUNK - 1) / CHUNK, lane);
+            E::fetch(st, a.rec, a.idx ? a.idx + b2 * a.B : nullptr, a.idx ? 0 : b2 * a.B, Bk2, gw, (Bk2 + E::CHUNK - 1) / E::CHUNK, lane);
         }
         __syncthreads();
         EH_STAMP(2)

@@ -55,7 +55,8 @@ struct eh_ctx {
     int nsm = 0;
     size_t smem_optin = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
-    const Variant* var = nullptr;
+    const Variant* var = nullptr;   // engine chosen at eh_create (FFMA2 one sample per lane, or tensor pipe)
+    const Variant* var2 = nullptr;  // FFMA2 two samples per lane: same layouts, used for large batches
     // model
     int n_pred_raw = 0, n_forc_raw = 0, n_targ = 0;
     int nflat = 0, ntheta = 0, nglob = 0;
@@ -219,14 +220,24 @@ struct Geom {
     size_t smem;
 };
 
+// which compiled variant serves a batch of B samples.  The two-samples-per-lane form halves the
+// shared-memory operand traffic but also the number of warps; measured at 65 536 samples per step it is
+// 15 % slower than one sample per lane (8 vs 16 warps per SM: the step is latency- not LSU-bound), so it is
+// only used on request (EH_USE_X2=1) until large-batch measurements say otherwise.
+const Variant* pick_variant(const eh_ctx* c, int64_t B)
+{
+    if (c->var2 && getenv("EH_USE_X2") && B >= (int64_t)c->nsm * 4 * c->var2->chunk) return c->var2;
+    return c->var;
+}
+
 Geom step_geometry(const eh_ctx* c, int64_t B)
 {
-    const Variant* v = c->var;
+    const Variant* v = pick_variant(c, B);
     size_t fixed = (size_t)(rup4(v->NW) + SS_FLOATS) * 4;
     size_t stage = (size_t)std::max(v->stage_floats, v->NPART) * 4;  // staging tile, later one row of the reduction scratch
     int wmax = (int)std::min<size_t>((size_t)v->max_warps, (c->smem_optin - fixed - 8192) / stage);
     if (wmax < 1) wmax = 1;
-    int64_t nchunks = (B + CHUNK - 1) / CHUNK;
+    int64_t nchunks = (B + v->chunk - 1) / v->chunk;
     Geom g;
     if (nchunks <= (int64_t)c->nsm * wmax) {
         int w = (int)((nchunks + c->nsm - 1) / c->nsm);
@@ -430,7 +441,7 @@ eh_status enqueue_steps(eh_ctx* c, int64_t n, int64_t B, int64_t b0, int64_t b1,
         a.B = (int)Bk;
         a.bscal = c->d_bscal + (size_t)b * BS_STRIDE;
         if (profile) CK(cudaEventRecord(c->prof_ev[2 * (prof_off + b - b0)], c->stream));
-        CK(c->var->launch_step(a, g.grid, g.nwarps, g.smem, c->stream, pdl));
+        CK(pick_variant(c, Bk)->launch_step(a, g.grid, g.nwarps, g.smem, c->stream, pdl));
         if (profile) CK(cudaEventRecord(c->prof_ev[2 * (prof_off + b - b0) + 1], c->stream));
         u.G = g.grid;
         u.bscal = a.bscal;
@@ -485,7 +496,7 @@ eh_status enqueue_persistent(eh_ctx* c, const float* rec, const int* idx, const 
                              int64_t B, int64_t first, int64_t nsteps, bool* used, long long** dbg_out)
 {
     *used = false;
-    const Variant* v = c->var;
+    const Variant* v = pick_variant(c, B);
     const int64_t nb = (n + B - 1) / B;
     const int npartp = rup4(v->NPART);
     const size_t fixed = (size_t)(rup4(v->NW) + SS_FLOATS) * 4;
@@ -493,7 +504,7 @@ eh_status enqueue_persistent(eh_ctx* c, const float* rec, const int* idx, const 
     const size_t extra = ((size_t)2 * npartp + 8 * (size_t)rup4(c->nflat)) * 4 + 64;
     const size_t smem_cap = c->smem_optin - 256;
     if (fixed + extra + stage > smem_cap) return EH_OK;  // does not fit: two-kernel path
-    const int64_t nchunks = (B + CHUNK - 1) / CHUNK;
+    const int64_t nchunks = (B + v->chunk - 1) / v->chunk;
     const char* ecs = getenv("EH_CLUSTER_SIZE");
     const char* ew = getenv("EH_EPOCH_WARPS");
     int best_cs = 0, best_G = 0, best_w = 0;
@@ -738,6 +749,7 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
                     d->process_model, ch.n_in, ch.n_hidden, hmax, ch.n_out, ch.activation, d->scale_nn_outputs);
     if (v->T != d->n_targ) return fail(c, EH_EINVAL, "process model yields %d targets, descriptor has %d", v->T, d->n_targ);
     c->var = v;
+    c->var2 = (v->engine == 0) ? find_variant(v->pm, v->P, v->NH, v->H, v->NOUT, v->act, v->scale, 2) : nullptr;
     c->n_pred_raw = d->n_pred; c->n_forc_raw = d->n_forc; c->n_targ = d->n_targ;
     c->use_bn = ch.input_batchnorm ? 1 : 0;
     c->real_in = ch.n_in;
@@ -985,7 +997,7 @@ eh_status enqueue_host_step(eh_ctx* c, HostStage& h, int64_t B, const float* X, 
     a.idx = nullptr; a.rec_base = 0; a.B = (int)B; a.bscal = h.d_bscal;
     Geom g = step_geometry(c, B);
     const bool pdl = false;  // the step follows memcpy/pack work here, nothing to overlap with
-    CK(v->launch_step(a, g.grid, g.nwarps, g.smem, c->stream, pdl));
+    CK(pick_variant(c, B)->launch_step(a, g.grid, g.nwarps, g.smem, c->stream, pdl));
     UpdateArgs u;
     fill_update_args(c, u);
     u.G = g.grid; u.bscal = h.d_bscal; u.loss_out = h.d_loss;
@@ -1041,6 +1053,7 @@ eh_status eh_create(eh_ctx** out, const eh_model_desc* desc)
         int wmax = (int)std::min<size_t>((size_t)v->max_warps, (c->smem_optin - fixed - 8192) / stage);
         if (wmax < 1) return fail(c, EH_EUNSUPPORTED, "variant %s needs %zu B of shared memory per warp", v->name, stage);
         CK(v->prepare(c->smem_optin - 256, fixed));  // kernels carry a few bytes of static shared memory
+        if (c->var2) CK(c->var2->prepare(c->smem_optin - 256, fixed));
         CK(dalloc(&c->d_wsrc, c->h_wsrc.size()));
         CK(dalloc(&c->d_pmap, c->h_pmap.size()));
         CK(dalloc(&c->d_pspan, c->h_pspan.size()));

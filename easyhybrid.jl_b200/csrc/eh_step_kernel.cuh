@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(E::MAX_WARPS * 32, 1) k_step(const StepArgs a)
 
     // prologue part 1 (independent of the previous step's update): fetch my samples, constant rows
     const int GW = gridDim.x * nwarps;
-    const int nchunks = (a.B + CHUNK - 1) / CHUNK;
+    const int nchunks = (a.B + E::CHUNK - 1) / E::CHUNK;
     int chunk = blockIdx.x * nwarps + warp;
     typename E::State st;
     E::fetch(st, a.rec, a.idx, a.rec_base, a.B, chunk, nchunks, lane);

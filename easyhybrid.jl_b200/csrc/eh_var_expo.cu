@@ -9,6 +9,6 @@ namespace eh {
     X(PmExpo, 1, 2, 16, 1, ACT_SIGMOID, false) \
     X(PmExpo, 1, 2, 16, 1, ACT_SIGMOID, true) \
     X(PmExpo, 1, 2, 16, 1, ACT_TANH, false)
-static const Variant g[] = {LIST(EH_MAKE) LIST_MMA(EH_MAKE_MMA)};
+static const Variant g[] = {LIST(EH_MAKE) LIST_MMA(EH_MAKE_MMA) LIST_MMA(EH_MAKE_X2)};
 const Variant* variants_expo(int* n) { *n = (int)(sizeof(g) / sizeof(g[0])); return g; }
 }  // namespace eh

@@ -12,6 +12,6 @@ namespace eh {
     X(PmLinear, 2, 2, 16, 1, ACT_TANH, false) \
     X(PmLinear2, 2, 2, 16, 1, ACT_TANH, false) \
     X(PmLinear2, 2, 2, 16, 1, ACT_RELU, false)
-static const Variant g[] = {LIST(EH_MAKE) LIST_MMA(EH_MAKE_MMA)};
+static const Variant g[] = {LIST(EH_MAKE) LIST_MMA(EH_MAKE_MMA) LIST_MMA(EH_MAKE_X2)};
 const Variant* variants_linear(int* n) { *n = (int)(sizeof(g) / sizeof(g[0])); return g; }
 }  // namespace eh

@@ -13,6 +13,6 @@ namespace eh {
     X(PmRbQ10, 2, 2, 16, 1, ACT_SWISH, true) \
     X(PmRbQ10, 2, 2, 16, 1, ACT_SIGMOID, true) \
     X(PmRbQ10, 2, 2, 16, 1, ACT_TANH, false)
-static const Variant g[] = {LIST(EH_MAKE) LIST_MMA(EH_MAKE_MMA)};
+static const Variant g[] = {LIST(EH_MAKE) LIST_MMA(EH_MAKE_MMA) LIST_MMA(EH_MAKE_X2)};
 const Variant* variants_rbq10(int* n) { *n = (int)(sizeof(g) / sizeof(g[0])); return g; }
 }  // namespace eh

@@ -117,6 +117,7 @@ static Variant make_variant(const char* name)
     Variant v{};
     v.pm = C::PM::ID; v.P = C::P; v.NH = C::NH; v.H = C::H; v.NOUT = C::NOUT; v.act = C::ACT; v.scale = C::SCALE ? 1 : 0;
     v.engine = E::ENGINE;
+    v.chunk = E::CHUNK;
     v.dims = C::D;
     v.F = C::F; v.T = C::T; v.NPS = C::NPS; v.R4 = C::R4; v.NW = C::NW;
     v.NPART = E::NPART;
@@ -135,6 +136,8 @@ static Variant make_variant(const char* name)
 // exact-fp32 FFMA2 engine and (where the shape allows) the register-resident tensor-pipe engine
 #define EH_MAKE(PMF, P, NH, H, NOUT, ACT, SCALE) \
     make_variant<EngFfma<StepCfg<P, NH, H, NOUT, ACT, SCALE, PMF>>>("ffma2/" #PMF "/P" #P "/NH" #NH "/H" #H "/O" #NOUT "/" #ACT "/scale=" #SCALE),
+#define EH_MAKE_X2(PMF, P, NH, H, NOUT, ACT, SCALE) \
+    make_variant<EngFfma<StepCfg<P, NH, H, NOUT, ACT, SCALE, PMF, 2>>>("ffma2x2/" #PMF "/P" #P "/NH" #NH "/H" #H "/O" #NOUT "/" #ACT "/scale=" #SCALE),
 #define EH_MAKE_MMA(PMF, P, NH, H, NOUT, ACT, SCALE) \
     make_variant<EngMma<StepCfg<P, NH, H, NOUT, ACT, SCALE, PMF>>>("mma3xtf32/" #PMF "/P" #P "/NH" #NH "/H" #H "/O" #NOUT "/" #ACT "/scale=" #SCALE),
 

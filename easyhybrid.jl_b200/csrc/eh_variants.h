@@ -11,7 +11,9 @@ struct EpochArgs;
 
 struct Variant {
     int pm, P, NH, H, NOUT, act, scale;
-    int engine;      // 0: exact-fp32 FFMA2 (tile partial layout), 1: tensor pipe 3xTF32 (padded-flat partial layout)
+    int engine;      // 0: exact-fp32 FFMA2, one sample per lane; 2: same, two samples per lane (tile partial layout);
+                     // 1: tensor pipe 3xTF32 (padded-flat partial layout)
+    int chunk;       // samples per warp pass
     ShapeDims dims;
     int F, T, NPS, R4, NW, NPART, off_stats, stage_floats, max_warps;
     const char* name;
