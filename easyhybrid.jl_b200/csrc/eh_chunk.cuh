@@ -58,9 +58,9 @@ struct StepCfg {
     static constexpr int R4 = rup4(P_ + PM::NF + PM::NT);  // floats per record
     static constexpr int NB = D.nblocks();
     static constexpr int NBI = (NB + 31) / 32;             // dW tiles per lane
-    static constexpr int NROWS = D.nrows() + (ACT_ == ACT_SWISH ? NH_ * H_ : 0);
-    static constexpr int AUXROW0 = D.nrows();              // swish sigma rows
-    static constexpr int STAGE_FLOATS = NROWS * RS;  // per warp
+    static constexpr int GS = 4 * RS + 4;                  // floats per 4-row staging group (bank skew, see goff)
+    static constexpr int AUXOFF = D.ngroups() * GS;        // swish sigma rows start here
+    static constexpr int STAGE_FLOATS = AUXOFF + (ACT_ == ACT_SWISH ? NH_ * H_ * RS : 0);  // per warp
     static constexpr int NW = D.nweights();
     static constexpr int NPART = D.npart();
     static_assert(P_ <= MAXP && H_ % 4 == 0 && NOUT_ <= 4 && (SPL_ == 1 || SPL_ == 2), "shape limits");
@@ -68,10 +68,13 @@ struct StepCfg {
 
 // shared memory carve-up (floats): [weights NW pad4][scalars 128][per-warp stage ...]
 //   scalars: [0..8) uniform slot values, [16..48) per-slot derived scalars, [48..52) c_t, [56..80) BN (mu, rstd)
-constexpr int SS_SLOT = 0, SS_PMS = 16, SS_C = 48, SS_NV = 52, SS_BN = 56, SS_FLOATS = 128;
+constexpr int SS_SLOT = 0, SS_PMS = 16, SS_C = 48, SS_NV = 52, SS_BN = 56, SS_NV2 = 80, SS_FLOATS = 128;
 
-// row of feature k inside 4-row group g0 (+k/4): groups start every 5 rows (bank skew)
-__device__ __forceinline__ constexpr int grow(int g0, int k) { return 5 * (g0 + (k >> 2)) + (k & 3); }
+// float offset of the staging row of feature k inside 4-row group g0 (+k/4).  Groups are 4 rows of RS floats
+// plus 4 floats of skew: the group stride is 20 mod 32 banks, so the 8 groups a quarter-warp of dW tiles
+// reads with LDS.128 land on 8 disjoint bank quads.
+template <int RS>
+__device__ __forceinline__ constexpr int goff(int g0, int k) { return (g0 + (k >> 2)) * (4 * RS + 4) + (k & 3) * RS; }
 
 __device__ __forceinline__ float comp(const float2* v, int k) { return (k & 1) ? v[k >> 1].y : v[k >> 1].x; }
 
@@ -130,13 +133,13 @@ __device__ __forceinline__ void chain_forward(const float* sW, float* stage, int
             float2 aux = f2s(0.f);
             hp[j] = act_fwd2<C::ACT>(hp[j], aux);
             if (STAGE && l + 1 <= D.nlt()) {
-                stage[grow(D.gA(l + 1), 2 * j) * RS + lane] = hp[j].x;
-                stage[grow(D.gA(l + 1), 2 * j + 1) * RS + lane] = hp[j].y;
+                stage[goff<RS>(D.gA(l + 1), 2 * j) + lane] = hp[j].x;
+                stage[goff<RS>(D.gA(l + 1), 2 * j + 1) + lane] = hp[j].y;
             }
             if (STAGE) {
                 if (C::ACT == ACT_SWISH) {
-                    stage[(C::AUXROW0 + (l - 1) * H + 2 * j) * RS + lane] = aux.x;
-                    stage[(C::AUXROW0 + (l - 1) * H + 2 * j + 1) * RS + lane] = aux.y;
+                    stage[C::AUXOFF + ((l - 1) * H + 2 * j) * RS + lane] = aux.x;
+                    stage[C::AUXOFF + ((l - 1) * H + 2 * j + 1) * RS + lane] = aux.y;
                 }
             }
         }
@@ -237,15 +240,15 @@ __device__ __forceinline__ void init_stage_rows(float* stage, int lane)
     for (int l = 1; l <= D.nlt(); l++) {
         const int din = D.din(l), ka = D.ka(l), gA = D.gA(l);
 #pragma unroll
-        for (int k = din; k < ka; k++) stage_put<S>(stage + grow(gA, k) * RS, lane, (k == din) ? one : zero);
+        for (int k = din; k < ka; k++) stage_put<S>(stage + goff<RS>(gA, k), lane, (k == din) ? one : zero);
     }
     if (!C::LR) {
 #pragma unroll
-        for (int o = C::NOUT; o < rup4(C::NOUT); o++) stage_put<S>(stage + grow(D.gD(C::NH + 1), o) * RS, lane, zero);
+        for (int o = C::NOUT; o < rup4(C::NOUT); o++) stage_put<S>(stage + goff<RS>(D.gD(C::NH + 1), o), lane, zero);
     }
 }
 
-// dW tile coordinates of this lane: rows of the delta / activation groups of tile b = lane + 32 i
+// dW tile coordinates of this lane: float offsets of the delta / activation groups of tile b = lane + 32 i
 template <class C>
 __device__ __forceinline__ void tile_rows(int lane, int* rowD, int* rowA)
 {
@@ -260,8 +263,8 @@ __device__ __forceinline__ void tile_rows(int lane, int* rowD, int* rowA)
             const int b0 = D.blk0(l), nk = D.nk(l), nb = D.nj(l) * nk;
             if (b >= b0 && b < b0 + nb) {
                 int jb = (b - b0) / nk, kb = (b - b0) % nk;
-                rowD[i] = 5 * (D.gD(l) + jb);
-                rowA[i] = 5 * (D.gA(l) + kb);
+                rowD[i] = (D.gD(l) + jb) * C::GS;
+                rowA[i] = (D.gA(l) + kb) * C::GS;
             }
         }
     }
@@ -321,7 +324,7 @@ __device__ __forceinline__ void chunk_sample_phase(const float (*rec)[C::R4], co
             x[s][k] = (rec[s][k] - sS[SS_BN + 2 * k]) * sS[SS_BN + 2 * k + 1];
             v[s] = x[s][k];
         }
-        stage_put<S>(stage + grow(D.gA(1), k) * RS, lane, v);
+        stage_put<S>(stage + goff<RS>(D.gA(1), k), lane, v);
     }
 
     // ---- forward (prepare_hidden_chain, src/models/NNModels.jl:225-230) ----
@@ -360,12 +363,12 @@ __device__ __forceinline__ void chunk_sample_phase(const float (*rec)[C::R4], co
                 lo[s] = hp[s][j].x; hi[s] = hp[s][j].y; axl[s] = aux.x; axh[s] = aux.y;
             }
             if (l + 1 <= D.nlt()) {
-                stage_put<S>(stage + grow(D.gA(l + 1), 2 * j) * RS, lane, lo);
-                stage_put<S>(stage + grow(D.gA(l + 1), 2 * j + 1) * RS, lane, hi);
+                stage_put<S>(stage + goff<RS>(D.gA(l + 1), 2 * j), lane, lo);
+                stage_put<S>(stage + goff<RS>(D.gA(l + 1), 2 * j + 1), lane, hi);
             }
             if (C::ACT == ACT_SWISH) {
-                stage_put<S>(stage + (C::AUXROW0 + (l - 1) * H + 2 * j) * RS, lane, axl);
-                stage_put<S>(stage + (C::AUXROW0 + (l - 1) * H + 2 * j + 1) * RS, lane, axh);
+                stage_put<S>(stage + C::AUXOFF + ((l - 1) * H + 2 * j) * RS, lane, axl);
+                stage_put<S>(stage + C::AUXOFF + ((l - 1) * H + 2 * j + 1) * RS, lane, axh);
             }
         }
         if (l < NH) {
@@ -481,7 +484,7 @@ __device__ __forceinline__ void chunk_sample_phase(const float (*rec)[C::R4], co
             float v[S];
 #pragma unroll
             for (int s = 0; s < S; s++) v[s] = dz[s][o];
-            stage_put<S>(stage + grow(D.gD(NH + 1), o) * RS, lane, v);
+            stage_put<S>(stage + goff<RS>(D.gD(NH + 1), o), lane, v);
         }
     }
 
@@ -511,12 +514,12 @@ __device__ __forceinline__ void chunk_sample_phase(const float (*rec)[C::R4], co
         for (int k = 0; k < HP; k++) {
             float alo[S], ahi[S], xlo[S], xhi[S], dlo[S], dhi[S];
             if (l < NH) {
-                stage_get<S>(stage + grow(D.gA(l + 1), 2 * k) * RS, lane, alo);
-                stage_get<S>(stage + grow(D.gA(l + 1), 2 * k + 1) * RS, lane, ahi);
+                stage_get<S>(stage + goff<RS>(D.gA(l + 1), 2 * k), lane, alo);
+                stage_get<S>(stage + goff<RS>(D.gA(l + 1), 2 * k + 1), lane, ahi);
             }
             if (C::ACT == ACT_SWISH) {
-                stage_get<S>(stage + (C::AUXROW0 + (l - 1) * H + 2 * k) * RS, lane, xlo);
-                stage_get<S>(stage + (C::AUXROW0 + (l - 1) * H + 2 * k + 1) * RS, lane, xhi);
+                stage_get<S>(stage + C::AUXOFF + ((l - 1) * H + 2 * k) * RS, lane, xlo);
+                stage_get<S>(stage + C::AUXOFF + ((l - 1) * H + 2 * k + 1) * RS, lane, xhi);
             }
 #pragma unroll
             for (int s = 0; s < S; s++) {
@@ -526,8 +529,8 @@ __device__ __forceinline__ void chunk_sample_phase(const float (*rec)[C::R4], co
                 dlo[s] = d[s][k].x;
                 dhi[s] = d[s][k].y;
             }
-            stage_put<S>(stage + grow(D.gD(l), 2 * k) * RS, lane, dlo);
-            stage_put<S>(stage + grow(D.gD(l), 2 * k + 1) * RS, lane, dhi);
+            stage_put<S>(stage + goff<RS>(D.gD(l), 2 * k), lane, dlo);
+            stage_put<S>(stage + goff<RS>(D.gD(l), 2 * k + 1), lane, dhi);
         }
         if (l > 1) {
             // delta_{l-1}[k] = sum_j W_l[j][k] delta_l[j]  (j-major copy of W_l, pairs over k)
@@ -561,16 +564,23 @@ __device__ __forceinline__ void chunk_sample_phase(const float (*rec)[C::R4], co
 }
 
 // ---- weight-gradient phase: lane = one 4x4 tile of some layer's dW (bias = the "1" row) ----
+// The tile accumulators live in registers only inside this phase: between chunks (and for the CTA
+// reduction) they rest in the warp's row `wacc` of the reduction scratch, element-major
+// (cell e*NB + b: consecutive lanes on consecutive banks).  `first`: no earlier chunk this step.
 template <class C>
 __device__ __forceinline__ void chunk_dw_phase(const float* stage, int lane, const int* rowD, const int* rowA,
-                                               float2 (*acc)[16])
+                                               float* wacc, bool first)
 {
     constexpr int RS = C::RS;
 #pragma unroll
     for (int i = 0; i < C::NBI; i++) {
         if (lane + 32 * i < C::NB) {
-            const float* pd = stage + rowD[i] * RS;
-            const float* pa = stage + rowA[i] * RS;
+            const int b = lane + 32 * i;
+            float2 acc[16];
+#pragma unroll
+            for (int e = 0; e < 16; e++) acc[e] = f2(first ? 0.f : wacc[e * C::NB + b], 0.f);
+            const float* pd = stage + rowD[i];
+            const float* pa = stage + rowA[i];
 #pragma unroll 2
             for (int c = 0; c < C::CHUNKS; c += 4) {
                 float4 dv[4], av[4];
@@ -582,10 +592,12 @@ __device__ __forceinline__ void chunk_dw_phase(const float* stage, int lane, con
                 for (int j = 0; j < 4; j++)
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
-                        acc[i][j * 4 + k] = fma2(f2(dv[j].x, dv[j].y), f2(av[k].x, av[k].y), acc[i][j * 4 + k]);
-                        acc[i][j * 4 + k] = fma2(f2(dv[j].z, dv[j].w), f2(av[k].z, av[k].w), acc[i][j * 4 + k]);
+                        acc[j * 4 + k] = fma2(f2(dv[j].x, dv[j].y), f2(av[k].x, av[k].y), acc[j * 4 + k]);
+                        acc[j * 4 + k] = fma2(f2(dv[j].z, dv[j].w), f2(av[k].z, av[k].w), acc[j * 4 + k]);
                     }
             }
+#pragma unroll
+            for (int e = 0; e < 16; e++) wacc[e * C::NB + b] = acc[e].x + acc[e].y;
         }
     }
 }
@@ -622,21 +634,17 @@ __device__ __forceinline__ int transpose_reduce_slot(int lane)
     return lane;  // bit (4-k) of the index == bit (4-k) of the lane
 }
 
-// ---- CTA-level fixed-order reduction of lane tiles + statistics into out[NPART] ----
-// scratch: [nwarps][NPART] floats (may alias the staging tiles; caller syncs before).
+// ---- CTA-level fixed-order reduction of the warps' rows (dW tiles + statistics) into out[NPART] ----
+// scratch: the warps' rows of NPART floats, `stride` floats apart; the dW cells of a row were left there by
+// chunk_dw_phase (element-major; the tile-major order of the partial vector is restored by the summing
+// pass below), `nacc` = chunks this warp accumulated this step (0: its dW cells are stale and count as zero).
 template <class C>
-__device__ __forceinline__ void cta_reduce(const float2 (*acc)[16], const ChunkStats& st, const LastAcc<C>& la,
-                                           float* scratch, float* out, int out_is_global)
+__device__ __forceinline__ void cta_reduce(int nacc, const ChunkStats& st, const LastAcc<C>& la, float* scratch, int stride,
+                                           float* out, int out_is_global)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-#pragma unroll
-    for (int i = 0; i < C::NBI; i++) {
-        int b = lane + 32 * i;
-        if (b < C::NB) {
-#pragma unroll
-            for (int e = 0; e < 16; e++) scratch[warp * C::NPART + b * 16 + e] = acc[i][e].x + acc[i][e].y;
-        }
-    }
+    if (nacc == 0)
+        for (int q = lane; q < C::NB * 16; q += 32) scratch[warp * stride + q] = 0.f;
     {
         // all per-lane scalars (loss sums, phi sums, output-layer gradient) in one exchange
         constexpr int NLASTV = C::LR ? C::NLAST : 0;
@@ -665,18 +673,19 @@ __device__ __forceinline__ void cta_reduce(const float2 (*acc)[16], const ChunkS
         if (i < C::T) dst = C::D.npart_dw() + i;
         else if (i < C::T + C::NPS) dst = C::D.npart_dw() + MAXT + (i - C::T);
         else if (i < NV) dst = C::D.off_last() + (i - C::T - C::NPS);
-        if (dst >= 0) scratch[warp * C::NPART + dst] = v[0];
+        if (dst >= 0) scratch[warp * stride + dst] = v[0];
         // cells of the statistics block that no lane writes
         for (int q = C::D.npart_dw() + lane; q < C::NPART; q += 32) {
             bool used = (q < C::D.npart_dw() + C::T) || (q >= C::D.npart_dw() + MAXT && q < C::D.npart_dw() + MAXT + C::NPS) ||
                         (q >= C::D.off_last() && q < C::D.off_last() + NLASTV);
-            if (!used) scratch[warp * C::NPART + q] = 0.f;
+            if (!used) scratch[warp * stride + q] = 0.f;
         }
     }
     __syncthreads();
-    for (int p = threadIdx.x; p < C::NPART; p += blockDim.x) {
+    for (int q = threadIdx.x; q < C::NPART; q += blockDim.x) {
         float s = 0.f;
-        for (int w = 0; w < nwarps; w++) s += scratch[w * C::NPART + p];
+        for (int w = 0; w < nwarps; w++) s += scratch[w * stride + q];
+        const int p = q < C::NB * 16 ? (q % C::NB) * 16 + q / C::NB : q;
         if (out_is_global) __stcg(out + p, s);
         else out[p] = s;
     }

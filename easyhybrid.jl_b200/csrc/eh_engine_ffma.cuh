@@ -9,14 +9,16 @@ template <class C>
 struct EngFfma {
     using Cfg = C;
     static constexpr int ENGINE = C::SPL == 2 ? 2 : 0;
-    static constexpr int STAGE_FLOATS = C::STAGE_FLOATS;  // per-warp shared memory
+    // per-warp shared memory: the staging tile, then the warp's row of the CTA reduction (dW tile sums between
+    // chunks + its statistics); separate regions, so nothing has to be re-initialised after a reduction
+    static constexpr int STAGE_FLOATS = C::STAGE_FLOATS + rup4(C::NPART);
     static constexpr int NPART = C::NPART;
     static constexpr int OFF_STATS = C::D.npart_dw();
     static constexpr int CHUNK = C::CHUNKS;           // samples per warp pass
     static constexpr int MAX_WARPS = C::SPL == 2 ? 10 : 16;
 
     struct State {
-        float2 acc[C::NBI][16];
+        int nacc;  // chunks accumulated into this warp's reduction row this step
         ChunkStats st;
         LastAcc<C> la;
         int rowD[C::NBI], rowA[C::NBI];
@@ -29,13 +31,10 @@ struct EngFfma {
         init_stage_rows<C>(stage, lane);
         tile_rows<C>(lane, s.rowD, s.rowA);
     }
-    __device__ __forceinline__ static void after_reduce(State& s, float* stage, int lane) { init_stage_rows<C>(stage, lane); }
+    __device__ __forceinline__ static void after_reduce(State&, float*, int) {}
     __device__ __forceinline__ static void step_begin(State& s, const float* sW, int lane)
     {
-#pragma unroll
-        for (int i = 0; i < C::NBI; i++)
-#pragma unroll
-            for (int e = 0; e < 16; e++) s.acc[i][e] = f2s(0.f);
+        s.nacc = 0;
 #pragma unroll
         for (int t = 0; t < MAXT; t++) s.st.loss[t] = 0.f;
 #pragma unroll
@@ -78,12 +77,13 @@ struct EngFfma {
         fetch(s, fa.rec, fa.idx, fa.rec_base, fa.B, next, fa.nchunks, lane);
         chunk_sample_phase<C>(rec, valid, sW, sS, stage, lane, slot, loss_kind, cx, s.st, s.la);
         __syncwarp();
-        chunk_dw_phase<C>(stage, lane, s.rowD, s.rowA, s.acc);
+        chunk_dw_phase<C>(stage, lane, s.rowD, s.rowA, stage + C::STAGE_FLOATS, s.nacc == 0);
+        s.nacc++;
         __syncwarp();
     }
     __device__ __forceinline__ static void reduce(State& s, float* scratch, float* out, int out_is_global)
     {
-        cta_reduce<C>(s.acc, s.st, s.la, scratch, out, out_is_global);
+        cta_reduce<C>(s.nacc, s.st, s.la, scratch + C::STAGE_FLOATS, STAGE_FLOATS, out, out_is_global);
     }
 };
 

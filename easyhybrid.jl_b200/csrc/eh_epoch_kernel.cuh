@@ -3,16 +3,16 @@
 // (src/training/epoch.jl:13-33) as a whole.  Per step every CTA
 //   1. runs the fused forward/backward on its chunks (eh_chunk.cuh) with the weight image it keeps
 //      in shared memory,
-//   2. reduces its lane tiles to one partial vector in shared memory; the cluster leader sums the
-//      partials of its cluster over distributed shared memory (DSMEM) in rank order and publishes
-//      ONE vector per cluster,
-//   3. one grid barrier (arrival counter; only cluster leaders arrive),
-//   4. every CTA sums the cluster vectors in a fixed order and applies the optimiser REDUNDANTLY to
-//      its own copy of theta / m / v in shared memory, patching its weight image in place.
+//   2. reduces its lane tiles to one partial vector in shared memory,
+//   3. takes part in a three-hop grid-wide sum (cluster leader over DSMEM -> one vector per cluster
+//      in L2 -> every CTA sums a share of them -> shares exchanged over DSMEM); every slot is an
+//      8-byte {value, step tag} pair that validates itself, so there is no grid barrier, no fence
+//      and no atomic anywhere: readers poll exactly the slots they need,
+//   4. applies the optimiser REDUNDANTLY to its own copy of theta / m / v in shared memory,
+//      patching its weight image in place.
 // All CTAs execute the same float operations in the same order, so the replicas stay bit-identical
 // and nothing has to be broadcast back.  Compared with one launch per step this removes two kernel
 // launches, the dependent-load prologue and the single-CTA second pass from every step.
-// No atomics on data: the only atomic is the barrier's arrival counter.
 #pragma once
 #include "eh_step_kernel.cuh"
 
@@ -37,8 +37,8 @@ struct EpochArgs {
     const float* pspan;        // [nflat]
     const int* slot_of_flat;   // [nflat] phi entries: canonical slot (for the tail), -1 otherwise
     const float* bscal;        // [nb][BS_STRIDE]
-    float* pbuf;               // [2][nclusters][npartp] published cluster vectors
-    unsigned* counter;         // grid barrier arrival counter (zeroed before launch)
+    uint2* pbuf;               // [2][nclusters][npartp] published cluster vectors, {value bits, step tag} slots
+    unsigned tag_base;         // steps run by earlier launches of this ctx (tags are absolute, never reused)
     float* stats_out;          // [nsteps][MAXT] reduced loss sums
     int npartp;                // padded partial length (multiple of 4)
     int work_floats;           // size of the per-CTA work region (staging / scratch / vector landing zone)
@@ -102,11 +102,119 @@ __device__ __forceinline__ float ld_dsmem(const float* local, unsigned rank)
     return v;
 }
 
-template <class E>
-__host__ __device__ constexpr int epoch_extra_floats(int nflat)
+// shared-memory window address of `local` in CTA `rank` of this cluster
+__device__ __forceinline__ unsigned dsmem_addr(const void* local, unsigned rank)
 {
-    // cpart + red (padded partial vectors) + theta, m, v copies + tables (pmap, 2 cells, span, slot)
-    return 2 * rup4(E::NPART) + 8 * rup4(nflat);
+    unsigned a = (unsigned)__cvta_generic_to_shared(local), ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
+    return ra;
+}
+__device__ __forceinline__ void st_dsmem_v2(unsigned addr, unsigned x, unsigned y)
+{
+    asm volatile("st.relaxed.cluster.shared::cluster.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ uint2 ld_shared_v2(const uint2* p)
+{
+    uint2 v;
+    unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("ld.relaxed.cluster.shared::cta.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+    return v;
+}
+
+// ---- grid-wide sum of the CTA partials: three self-validating hops, no barrier, no fence, no atomic.
+// Every slot travels as an 8-byte {value, step tag} pair (single-copy atomic), so a reader simply polls the
+// slot it needs until the tag of this step shows up.  Thread p owns element p on every hop.
+//   hop 1  non-leader CTAs push their partial into the cluster leader's shared memory (DSMEM store);
+//          the leader adds the ranks in order and publishes ONE vector per cluster in L2;
+//   hop 2  CTA rank r of every cluster sums its contiguous share of the NC published vectors out of L2;
+//   hop 3  the cs shares are pushed to every CTA of the cluster (DSMEM) and added in rank order.
+// Every cluster uses the same grouping and order, so all CTAs of the grid hold bit-identical totals.
+// Kept out of line: its registers must not weigh on the allocation of the compute phase.
+static __device__ __noinline__ void grid_sum(const float* cpart, float* red, uint2* box1, uint2* box3, uint2* pbuf_par, int npartp,
+                                      int npart, int cs, int NC, unsigned tag, unsigned* err, long long* dbg)
+{
+    const unsigned crank = (unsigned)(blockIdx.x % cs);
+    const int cid = blockIdx.x / cs;
+    {
+        uint2* pub = pbuf_par + (size_t)cid * npartp;
+        if (crank != 0) {
+            const unsigned dst = dsmem_addr(box1 + (size_t)(crank - 1) * npartp, 0u);
+            for (int p = threadIdx.x; p < npart; p += blockDim.x) st_dsmem_v2(dst + 8u * (unsigned)p, __float_as_uint(cpart[p]), tag);
+        } else {
+            for (int p = threadIdx.x; p < npart; p += blockDim.x) {
+                float sum = cpart[p];
+                for (int rk = 1; rk < cs; rk++) {
+                    const uint2* slot = box1 + (size_t)(rk - 1) * npartp + p;
+                    uint2 v = ld_shared_v2(slot);
+                    unsigned spins = 0;
+                    while (v.y != tag) {
+                        if (++spins > EH_SPIN_LIMIT) { *err = 1; break; }
+                        v = ld_shared_v2(slot);
+                    }
+                    sum += __uint_as_float(v.x);
+                }
+                st_volatile_v2(pub + p, __float_as_uint(sum), tag);
+            }
+        }
+    }
+    if (dbg && threadIdx.x == 0) dbg[4] = clock64();
+    {
+        const uint2* src = pbuf_par;
+        const int per = (NC + cs - 1) / cs;
+        const int c0 = (int)crank * per;
+        const int c1 = c0 + per < NC ? c0 + per : NC;
+        constexpr int U = 12;
+        for (int p = threadIdx.x; p < npart; p += blockDim.x) {
+            float sum = 0.f;
+            for (int c = c0; c < c1; c += U) {
+                uint2 t[U];
+#pragma unroll
+                for (int u = 0; u < U; u++)
+                    if (c + u < c1) t[u] = ld_volatile_v2(src + (size_t)(c + u) * npartp + p);
+#pragma unroll
+                for (int u = 0; u < U; u++)
+                    if (c + u < c1) {
+                        unsigned spins = 0;
+                        while (t[u].y != tag) {
+                            if (++spins > EH_SPIN_LIMIT) { *err = 1; break; }
+                            t[u] = ld_volatile_v2(src + (size_t)(c + u) * npartp + p);
+                        }
+                        sum += __uint_as_float(t[u].x);
+                    }
+            }
+            if (cs > 1) {
+                for (int rk = 0; rk < cs; rk++)
+                    st_dsmem_v2(dsmem_addr(box3 + (size_t)crank * npartp + p, (unsigned)rk), __float_as_uint(sum), tag);
+            } else {
+                red[p] = sum;
+            }
+        }
+    }
+    if (dbg && threadIdx.x == 0) dbg[5] = clock64();
+    if (cs > 1) {
+        for (int p = threadIdx.x; p < npart; p += blockDim.x) {
+            float sum = 0.f;
+            for (int rk = 0; rk < cs; rk++) {
+                const uint2* slot = box3 + (size_t)rk * npartp + p;
+                uint2 v = ld_shared_v2(slot);
+                unsigned spins = 0;
+                while (v.y != tag) {
+                    if (++spins > EH_SPIN_LIMIT) { *err = 1; break; }
+                    v = ld_shared_v2(slot);
+                }
+                sum += __uint_as_float(v.x);
+            }
+            red[p] = sum;
+        }
+    }
+}
+
+// floats of shared memory besides weights / scalars / work region: cpart + red (padded partial vectors)
+// + the two {value, tag} inboxes (cs-1 and cs vectors of 8-byte slots) + theta, m, v copies
+// + tables (pmap, 2 cells, span, slot)
+__host__ __device__ constexpr int epoch_extra_floats(int npartp, int nflat, int cs)
+{
+    return (2 + 2 * (2 * cs - 1)) * npartp + 8 * rup4(nflat);
 }
 
 template <class E>
@@ -121,7 +229,9 @@ __global__ void __launch_bounds__(E::MAX_WARPS * 32, 1) k_epoch(const EpochArgs 
     float* stage = stage0 + warp * E::STAGE_FLOATS;
     float* cpart = stage0 + a.work_floats;               // [npartp] this CTA's partial vector
     float* red = cpart + rup4(E::NPART);                 // [npartp] fully reduced vector
-    float* s_th = red + rup4(E::NPART);                  // [nflat] replicated parameters
+    uint2* box1 = reinterpret_cast<uint2*>(red + rup4(E::NPART));  // [cs-1][npartp] {value, tag}: partials pushed to a cluster leader
+    uint2* box3 = box1 + (size_t)(a.csize - 1) * rup4(E::NPART);   // [cs][npartp] {value, tag}: the cluster's shares of the grid-wide sum
+    float* s_th = reinterpret_cast<float*>(box3 + (size_t)a.csize * rup4(E::NPART));  // [nflat] replicated parameters
     float* s_m = s_th + rup4(a.nflat);
     float* s_v = s_m + rup4(a.nflat);
     int* t_pmap = reinterpret_cast<int*>(s_v + rup4(a.nflat));
@@ -129,8 +239,6 @@ __global__ void __launch_bounds__(E::MAX_WARPS * 32, 1) k_epoch(const EpochArgs 
     int* t_cell1 = t_cell0 + rup4(a.nflat);
     int* t_slot = t_cell1 + rup4(a.nflat);
     float* t_span = reinterpret_cast<float*>(t_slot + rup4(a.nflat));
-    __shared__ float s_post;
-    __shared__ int s_skip;
     const int G = gridDim.x;
     const int cs = a.csize;
     const int NC = G / cs;                               // clusters = published vectors per step
@@ -150,6 +258,10 @@ __global__ void __launch_bounds__(E::MAX_WARPS * 32, 1) k_epoch(const EpochArgs 
     float b1t = a.ost->b1t, b2t = a.ost->b2t;
     long long tdone = 0, tskip = 0;
 
+    // inboxes start with tag 0 (never a valid step tag); nobody pushes before everybody has cleared
+    for (int i = threadIdx.x; i < (2 * cs - 1) * rup4(E::NPART); i += blockDim.x) box1[i] = make_uint2(0u, 0u);
+    if (cs > 1) cluster_sync_all(); else __syncthreads();
+
     typename E::State st;
     E::init_warp(st, stage, lane);
     load_weights_and_scalars<C>(a.pblock, a.nflat, a.wsrc, nullptr, 0, sW, sS);
@@ -165,38 +277,44 @@ __global__ void __launch_bounds__(E::MAX_WARPS * 32, 1) k_epoch(const EpochArgs 
     const int GW = G * nwarps;
     // chunk -> warp assignment interleaves CTAs so that a ragged chunk count spreads over all SMs
     const int gw = warp * G + blockIdx.x;
+    // batch of the current step, tracked incrementally (no 64-bit modulo in the loop)
+    int bcur = (int)(a.first_step % a.nb);
+    const int Blast = (int)(a.n - (long long)(a.nb - 1) * a.B);  // size of the (possibly partial) last batch
     {
-        long long b = a.first_step % a.nb;
-        long long rem = a.n - b * a.B;
-        int Bk = (int)(rem < a.B ? rem : a.B);
+        const long long b = bcur;
+        const int Bk = bcur == a.nb - 1 ? Blast : a.B;
         E::fetch(st, a.rec, a.idx ? a.idx + b * a.B : nullptr, a.idx ? 0 : b * a.B, Bk, gw, (Bk + E::CHUNK - 1) / E::CHUNK, lane);
     }
-    unsigned bar = 0;
     // per-batch scalars of the coming step, prefetched one step ahead (a dependent global load otherwise)
     float pre_bs = 0.f;
-    auto prefetch_bs = [&](int step) {
-        const float* bs = a.bscal + (size_t)((a.first_step + step) % a.nb) * BS_STRIDE;
+    auto prefetch_bs = [&](int batch) {
+        const float* bs = a.bscal + (size_t)batch * BS_STRIDE;
         if (threadIdx.x < MAXT) pre_bs = bs[BS_C + threadIdx.x];
         else if (threadIdx.x < MAXT + 2 * C::P)
             pre_bs = a.use_bn ? bs[BS_BN + threadIdx.x - MAXT] : (((threadIdx.x - MAXT) & 1) ? 1.f : 0.f);
         else if (threadIdx.x >= 28 && threadIdx.x < 28 + MAXT) pre_bs = bs[BS_N + threadIdx.x - 28];
     };
-    prefetch_bs(0);
+    prefetch_bs(bcur);
 #define EH_STAMP(slot)                                                                      \
     if (a.dbg && threadIdx.x == 0) a.dbg[((size_t)s * G + blockIdx.x) * 32 + (slot)] = clock64();
 
     for (int s = 0; s < a.nsteps; s++) {
         EH_STAMP(0)
-        const long long b = (a.first_step + s) % a.nb;
-        const long long rem = a.n - b * a.B;
-        const int Bk = (int)(rem < a.B ? rem : a.B);
+        const long long b = bcur;
+        const int bnext = bcur + 1 == a.nb ? 0 : bcur + 1;
+        const int Bk = bcur == a.nb - 1 ? Blast : a.B;
         const int nchunks = (Bk + E::CHUNK - 1) / E::CHUNK;
         const int par = s & 1;
         if (threadIdx.x < MAXT) sS[SS_C + threadIdx.x] = pre_bs;
         else if (threadIdx.x < MAXT + 2 * C::P) sS[SS_BN + threadIdx.x - MAXT] = pre_bs;
-        else if (threadIdx.x >= 28 && threadIdx.x < 28 + MAXT) sS[SS_NV + threadIdx.x - 28] = pre_bs;
+        else if (threadIdx.x >= 28 && threadIdx.x < 28 + MAXT) {
+            sS[SS_NV + threadIdx.x - 28] = pre_bs;
+            // second copy by step parity for the update phase: sS[SS_NV] is rewritten at the top of the next
+            // step, which a fast warp may reach while a slow one is still in this step's update
+            sS[SS_NV2 + par * MAXT + threadIdx.x - 28] = pre_bs;
+        }
         __syncthreads();
-        if (s + 1 < a.nsteps) prefetch_bs(s + 1);
+        if (s + 1 < a.nsteps) prefetch_bs(bnext);
         EH_STAMP(1)
 
         E::step_begin(st, sW, lane);
@@ -206,78 +324,21 @@ __global__ void __launch_bounds__(E::MAX_WARPS * 32, 1) k_epoch(const EpochArgs 
         if (a.dbg && lane == 0) a.dbg[((size_t)s * G + blockIdx.x) * 32 + 8 + warp] = clock64();
         // prefetch my first sample of the next step: its latency hides behind the exchange below
         if (s + 1 < a.nsteps) {
-            long long b2 = (a.first_step + s + 1) % a.nb;
-            long long rem2 = a.n - b2 * a.B;
-            int Bk2 = (int)(rem2 < a.B ? rem2 : a.B);
+            const long long b2 = bnext;
+            const int Bk2 = bnext == a.nb - 1 ? Blast : a.B;
             E::fetch(st, a.rec, a.idx ? a.idx + b2 * a.B : nullptr, a.idx ? 0 : b2 * a.B, Bk2, gw, (Bk2 + E::CHUNK - 1) / E::CHUNK, lane);
         }
         __syncthreads();
         EH_STAMP(2)
         // CTA partial -> cpart (the scratch of cta_reduce aliases the staging tiles)
         E::reduce(st, stage0, cpart, 0);
-        EH_STAMP(3)
-        if (cs > 1) cluster_sync_all(); else __syncthreads();
-        EH_STAMP(4)
-        if (crank == 0) {
-            // cluster vector: ranks summed in order over DSMEM, published for the whole grid
-            float* dst = a.pbuf + ((size_t)par * NC + cid) * a.npartp;
-            for (int p = threadIdx.x; p < E::NPART; p += blockDim.x) {
-                float sum = cpart[p];
-                for (int rk = 1; rk < cs; rk++) sum += ld_dsmem(cpart + p, (unsigned)rk);
-                __stcg(dst + p, sum);
-            }
-        }
-        // grid barrier: leaders arrive, everybody waits
-        bar += (unsigned)NC;
         __syncthreads();
-        EH_STAMP(5)
-        if (threadIdx.x == 0) {
-            if (crank == 0) {
-                __threadfence();
-                atomicAdd(a.counter, 1u);
-            }
-            unsigned spins = 0;
-            while (ld_acquire_gpu(a.counter) < bar) {
-                if (++spins > EH_SPIN_LIMIT) { *a.err = 1; break; }
-            }
-            __threadfence();
-        }
+        EH_STAMP(3)
+        // grid-wide sum of the CTA partials (grid_sum above): cpart -> red, identical bits in every CTA
+        grid_sum(cpart, red, box1, box3, a.pbuf + (size_t)par * NC * a.npartp, a.npartp, E::NPART, cs, NC, a.tag_base + (unsigned)s + 1u,
+                 a.err, a.dbg ? a.dbg + ((size_t)s * G + blockIdx.x) * 32 : nullptr);
         __syncthreads();
         EH_STAMP(6)
-
-        // every CTA: pull all cluster vectors into shared memory with independent 128-bit loads
-        // (one L2 round trip instead of NC dependent ones), then sum them in a fixed order
-        {
-            const float4* src4 = reinterpret_cast<const float4*>(a.pbuf + (size_t)par * NC * a.npartp);
-            float4* vec4 = reinterpret_cast<float4*>(stage0);  // the staging tiles are idle here
-            const int total4 = NC * (a.npartp / 4);
-            constexpr int U = 8;
-            for (int base = threadIdx.x; base < total4; base += U * blockDim.x) {
-                float4 t[U];
-#pragma unroll
-                for (int u = 0; u < U; u++) {
-                    int i = base + u * blockDim.x;
-                    t[u] = i < total4 ? __ldcg(src4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-#pragma unroll
-                for (int u = 0; u < U; u++) {
-                    int i = base + u * blockDim.x;
-                    if (i < total4) vec4[i] = t[u];
-                }
-            }
-        }
-        __syncthreads();
-        for (int p = threadIdx.x; p < E::NPART; p += blockDim.x) {
-            float s0 = 0.f, s1 = 0.f;
-            int c = 0;
-            for (; c + 2 <= NC; c += 2) {
-                s0 += stage0[(size_t)c * a.npartp + p];
-                s1 += stage0[(size_t)(c + 1) * a.npartp + p];
-            }
-            if (c < NC) s0 += stage0[(size_t)c * a.npartp + p];
-            red[p] = s0 + s1;
-        }
-        __syncthreads();
         if (a.dbg && threadIdx.x == 0) a.dbg[((size_t)s * G + blockIdx.x) * 32 + 27] = clock64();
         if (a.world > 1) {
             // ---- fused exchange over NVLink peer memory, LL style: every 8-byte store carries {value, step tag},
@@ -309,21 +370,16 @@ __global__ void __launch_bounds__(E::MAX_WARPS * 32, 1) k_epoch(const EpochArgs 
             __syncthreads();
         }
         if (a.dbg && threadIdx.x == 0) a.dbg[((size_t)s * G + blockIdx.x) * 32 + 28] = clock64();
-        if (threadIdx.x == 0) {
-            float ntot = 0.f, post = 1.f;
-            for (int t = 0; t < a.T; t++) {
-                ntot += sS[SS_NV + t];
-                if (a.loss_kind[t] == LOSS_RMSE) post = 1.f / (2.f * sqrtf(red[E::OFF_STATS + t] / sS[SS_NV + t]));
-            }
-            s_post = post;
-            s_skip = (ntot == 0.f);  // all-masked batch: epoch.jl:17-19
-            if (blockIdx.x == 0)
-                for (int t = 0; t < MAXT; t++) a.stats_out[(size_t)s * MAXT + t] = red[E::OFF_STATS + t];
+        // every thread derives the batch scalars itself (identical arithmetic everywhere): no serial section
+        float ntot = 0.f, post = 1.f;
+        for (int t = 0; t < a.T; t++) {
+            const float nv = sS[SS_NV2 + par * MAXT + t];
+            ntot += nv;
+            if (a.loss_kind[t] == LOSS_RMSE) post = 1.f / (2.f * sqrtf(red[E::OFF_STATS + t] / nv));
         }
-        __syncthreads();
-        const bool skip = s_skip != 0;
+        const bool skip = ntot == 0.f;  // all-masked batch: epoch.jl:17-19
+        if (blockIdx.x == 0 && threadIdx.x < MAXT) a.stats_out[(size_t)s * MAXT + threadIdx.x] = red[E::OFF_STATS + threadIdx.x];
         if (!skip) {
-            const float post = s_post;
             for (int p = threadIdx.x; p < a.nflat; p += blockDim.x) {
                 float g = red[t_pmap[p]] * post;
                 float th = s_th[p];
@@ -371,6 +427,7 @@ __global__ void __launch_bounds__(E::MAX_WARPS * 32, 1) k_epoch(const EpochArgs 
             tskip++;
         }
         E::after_reduce(st, stage, lane);  // constant staging rows were overwritten by the scratch / vectors
+        bcur = bnext;
         EH_STAMP(7)
     }
 #undef EH_STAMP

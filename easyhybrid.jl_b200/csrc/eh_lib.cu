@@ -131,6 +131,7 @@ struct eh_ctx {
     void* dp_block = nullptr;
     void* dp_peer[EH_MAX_WORLD] = {nullptr};
     unsigned dp_steps = 0;  // steps exchanged so far (absolute flag tags)
+    unsigned epoch_tag = 0; // steps run by the persistent kernel so far (tags of the in-GPU exchange; never reset)
     unsigned* d_dperr = nullptr;
 };
 
@@ -501,7 +502,8 @@ eh_status enqueue_persistent(eh_ctx* c, const float* rec, const int* idx, const 
     const int npartp = rup4(v->NPART);
     const size_t fixed = (size_t)(rup4(v->NW) + SS_FLOATS) * 4;
     const size_t stage = (size_t)std::max(v->stage_floats, v->NPART) * 4;
-    const size_t extra = ((size_t)2 * npartp + 8 * (size_t)rup4(c->nflat)) * 4 + 64;
+    auto extra_of = [&](int cs) { return (size_t)epoch_extra_floats(npartp, c->nflat, cs) * 4 + 64; };
+    const size_t extra = extra_of(1);
     const size_t smem_cap = c->smem_optin - 256;
     if (fixed + extra + stage > smem_cap) return EH_OK;  // does not fit: two-kernel path
     const int64_t nchunks = (B + v->chunk - 1) / v->chunk;
@@ -515,14 +517,13 @@ eh_status enqueue_persistent(eh_ctx* c, const float* rec, const int* idx, const 
     // Rule: fewest rounds over the batch first, then that preference order.
     for (int cs : {4, 2, 1, 8}) {
         if (ecs && atoi(ecs) != cs) continue;
-        // the work region also receives the NC published vectors: NC <= nsm / cs
-        const size_t vec_bytes = (size_t)(c->nsm / cs) * npartp * 4;
-        if (fixed + extra + std::max(stage, vec_bytes) > smem_cap) continue;
+        const size_t extra = extra_of(cs);
+        if (fixed + extra + stage > smem_cap) continue;
         int wcap = (int)std::min<size_t>((size_t)v->max_warps, (smem_cap - fixed - extra) / stage);
         int wtry = ew ? std::min(atoi(ew), wcap) : wcap;
         if (wtry < 1) wtry = 1;
         int max_ctas = 0;
-        size_t smem_try = fixed + extra + std::max((size_t)wtry * stage, vec_bytes);
+        size_t smem_try = fixed + extra + (size_t)wtry * stage;
         if (v->epoch_max_grid(wtry, smem_try, cs, &max_ctas) != cudaSuccess) { cudaGetLastError(); continue; }
         max_ctas = std::min(max_ctas, (c->nsm / cs) * cs);
         if (max_ctas < cs) continue;
@@ -535,19 +536,18 @@ eh_status enqueue_persistent(eh_ctx* c, const float* rec, const int* idx, const 
         double cost = (double)rounds;  // strict '<' below keeps the preference order among equal round counts
         if (cost < best_cost) {
             best_cost = cost; best_cs = cs; best_G = G; best_w = w;
-            best_work = std::max((size_t)w * stage, (size_t)(G / cs) * npartp * 4);
+            best_work = (size_t)w * stage;
         }
     }
     if (!best_cs) return EH_OK;
     const int cs = best_cs, G = best_G, w = best_w;
-    const size_t smem = fixed + extra + best_work;
+    const size_t smem = fixed + extra_of(cs) + best_work;
     if ((size_t)nsteps > c->stats_cap) {
         if (c->d_stats) cudaFree(c->d_stats);
         c->d_stats = nullptr; c->stats_cap = 0;
         CK(dalloc(&c->d_stats, (size_t)nsteps * MAXT));
         c->stats_cap = (size_t)nsteps;
     }
-    CK(cudaMemsetAsync(c->d_counter, 0, 4 * sizeof(unsigned), c->stream));
     EpochArgs a;
     memset(&a, 0, sizeof a);
     a.rec = reinterpret_cast<const float4*>(rec);
@@ -555,7 +555,7 @@ eh_status enqueue_persistent(eh_ctx* c, const float* rec, const int* idx, const 
     a.pblock = c->d_theta; a.nflat = c->nflat; a.ntheta = c->ntheta;
     a.m = c->d_m; a.v = c->d_v; a.ost = c->d_ost;
     a.wsrc = c->d_wsrc; a.pmap = c->d_pmap; a.cells = c->d_cells; a.pspan = c->d_pspan; a.slot_of_flat = c->d_slot_of_flat;
-    a.bscal = bscal; a.pbuf = c->d_pbuf; a.counter = c->d_counter; a.stats_out = c->d_stats;
+    a.bscal = bscal; a.pbuf = reinterpret_cast<uint2*>(c->d_pbuf); a.tag_base = c->epoch_tag; a.stats_out = c->d_stats;
     a.npartp = npartp; a.work_floats = (int)(best_work / 4); a.csize = cs; a.T = c->n_targ; a.agg_mean = c->agg_mean;
     for (int t = 0; t < MAXT; t++) a.loss_kind[t] = c->loss_kind[t];
     for (int s = 0; s < MAXPS; s++) a.slot[s] = c->slots[s];
@@ -585,6 +585,7 @@ eh_status enqueue_persistent(eh_ctx* c, const float* rec, const int* idx, const 
     CK(cudaEventRecord(c->ev1, c->stream));
     c->epoch_csize = cs; c->epoch_grid = G; c->epoch_warps = w;
     if (c->world > 1) c->dp_steps += (unsigned)nsteps;
+    c->epoch_tag += (unsigned)nsteps;
     k_losses_from_stats<<<(unsigned)((nsteps + 127) / 128), 128, 0, c->stream>>>(c->d_stats, bscal, first, (int)nb,
                                                                                  (int)nsteps, c->n_targ, c->agg_mean,
                                                                                  c->d_losskind, loss_out);
@@ -1067,7 +1068,8 @@ eh_status eh_create(eh_ctx** out, const eh_model_desc* desc)
         CK(cudaMemcpy(c->d_cells, c->h_cells.data(), c->h_cells.size() * sizeof(int), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(c->d_slot_of_flat, c->h_slot_of_flat.data(), c->h_slot_of_flat.size() * sizeof(int), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(c->d_losskind, c->loss_kind, MAXT * sizeof(int), cudaMemcpyHostToDevice));
-        CK(dalloc(&c->d_pbuf, (size_t)2 * (c->nsm + 8) * rup4(v->NPART)));
+        CK(dalloc(&c->d_pbuf, (size_t)4 * (c->nsm + 8) * rup4(v->NPART)));  // [2][clusters][npartp] {value, tag}
+        CK(cudaMemset(c->d_pbuf, 0, (size_t)4 * (c->nsm + 8) * rup4(v->NPART) * sizeof(float)));
         CK(dalloc(&c->d_counter, (size_t)4));
         CK(dalloc(&c->d_dperr, (size_t)1));
         CK(cudaMemset(c->d_dperr, 0, sizeof(unsigned)));

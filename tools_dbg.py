@@ -4,7 +4,7 @@ import numpy as np
 raw = np.fromfile(sys.argv[1], dtype=np.int64)
 nsteps, G, w, cs = raw[:4]
 d = raw[4:].reshape(nsteps, G, 32)
-names = ["scalars+sync", "compute(thread0 warp)", "cta_reduce", "cluster_sync", "dsmem gather+publish", "grid barrier", "read+adam+init"]
+names = ["scalars+sync", "compute(thread0 warp)", "cta_reduce", "hop1 cluster->leader->L2", "hop2 L2 share sum + push", "hop3 cluster shares", "dp exchange+adam+init"]
 print(f"steps {nsteps} grid {G} warps {w} cluster {cs}")
 for s in range(1, nsteps):
     t = d[s, :, :8].astype(np.float64)
@@ -17,5 +17,5 @@ for s in range(1, nsteps):
             print(f"   {nme:28s} median {np.median(ph[:, i]):8.0f}  min {ph[:, i].min():8.0f}  max {ph[:, i].max():8.0f}")
         if d[s, :, 27].any():
             rd = (d[s, :, 27] - d[s, :, 6]).astype(np.float64); ex = (d[s, :, 28] - d[s, :, 27]).astype(np.float64); ad = (d[s, :, 7] - d[s, :, 28]).astype(np.float64)
-            print(f"     of which: vector read median {np.median(rd):.0f}, rank exchange median {np.median(ex):.0f} (max {ex.max():.0f}), adam+init median {np.median(ad):.0f}")
+            print(f"     of which: rank exchange median {np.median(ex):.0f} (max {ex.max():.0f}), adam+init median {np.median(ad):.0f}")
         print(f"   per-warp compute: median {np.median(wend):.0f} min {wend.min():.0f} max {wend.max():.0f}; per-CTA slowest warp median {np.median(wend.max(axis=1)):.0f}")

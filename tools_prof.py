@@ -5,7 +5,8 @@ sys.path.insert(0, ".")
 import easyhybrid_b200 as eh
 from bench import synth, make_model, B
 
-n = 1 << 22
+import os
+n = 1 << int(os.environ.get('EH_PROF_LOG2N', '22'))
 model = make_model(eh)
 xf, y = synth(n, 42)
 flags = int(sys.argv[1]) if len(sys.argv) > 1 else 3
