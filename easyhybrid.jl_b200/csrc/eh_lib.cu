@@ -43,9 +43,12 @@ struct HostStage {  // device staging for eh_step_host*: raw arrays + packed rec
     int* d_cnt = nullptr;  // [MAXT] valid-target counts written by the packer
     float* d_bscal = nullptr;
     float* d_loss = nullptr;
-    cudaEvent_t done = nullptr;
+    cudaEvent_t ready = nullptr;  // the batch's H2D copies have landed (recorded on the copy stream)
+    cudaEvent_t freed = nullptr;  // the step that consumed this slot has retired (recorded on the compute stream)
+    bool used = false;
     int64_t cap = 0;
 };
+constexpr int EH_HOST_SLOTS = 4;  // batches in flight between the copy engine and the step kernels
 
 }  // namespace
 
@@ -107,13 +110,15 @@ struct eh_ctx {
     int64_t perm_B = 0;  // batch size the bscal rows were prepared for (0 = none)
     std::vector<float> bn_mean, bn_var;
     // host-step pipeline
-    HostStage hs[2];
+    HostStage hs[EH_HOST_SLOTS];
     int hs_next = 0;
     std::vector<std::pair<float*, float*>> pending_loss;  // (pinned src, user dst)
     float* h_async_loss = nullptr;                          // pinned ring
     size_t async_cap = 0, async_used = 0;
     // timing
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    std::vector<cudaEvent_t> seg_ev;  // index-segment arrival events of the pipelined epoch
+    float* d_snap = nullptr;          // trainable-state snapshot of the pipelined epoch
     float last_ms = 0.f, last_step_ms = 0.f;
     int64_t last_launches = 0;
     int profiling = 0;
@@ -181,12 +186,14 @@ __global__ void k_fill_bscal(float* bscal, int nb, long long n, int Bfull, int T
 }
 
 // host-step path: c_t from the valid-target counts produced by the packer
-__global__ void k_bscal_from_counts(float* bscal, const int* cnt, int T, int agg_mean)
+// (also re-zeroes the counters for the next batch that uses this staging slot)
+__global__ void k_bscal_from_counts(float* bscal, int* cnt, int T, int agg_mean)
 {
     int t = threadIdx.x;
     if (t >= MAXT) return;
     float aggw = agg_mean ? 1.f / (float)T : 1.f;
     float n = t < T ? (float)cnt[t] : 0.f;
+    cnt[t] = 0;
     bscal[BS_C + t] = t < T ? aggw / n : 0.f;
     bscal[BS_N + t] = n;
     bscal[BS_SS + t] = 0.f;
@@ -389,13 +396,14 @@ bool needs_data_stats(const eh_ctx* c)
     return false;
 }
 
-// per-batch scalar rows for batches of size B over the index stream d_idx[0..n)
-eh_status prepare_batch_rows(eh_ctx* c, int64_t n, int64_t B)
+// per-batch scalar rows for batches [b0, b1) of size B over the index stream d_idx[0..n), enqueued on c->stream
+eh_status prepare_batch_rows_range(eh_ctx* c, int64_t n, int64_t B, int64_t b0, int64_t b1)
 {
     int64_t nb = (n + B - 1) / B;
     eh_status s = ensure_bscal_cap(c, (size_t)nb);
     if (s != EH_OK) return s;
     const Split& sp = c->split[EH_SPLIT_TRAIN];
+    const int64_t off = b0 * B;
     if (needs_data_stats(c) && c->world > 1)
         return fail(c, EH_EUNSUPPORTED, "data-parallel mode needs NaN-free targets, no nseLoss and no input BatchNorm in this build");
     if (needs_data_stats(c)) {
@@ -403,24 +411,27 @@ eh_status prepare_batch_rows(eh_ctx* c, int64_t n, int64_t B)
         memset(&a, 0, sizeof a);
         a.rec = sp.rec;
         a.R4 = c->var->R4;
-        a.idx = c->d_idx;
-        a.n = n;
+        a.idx = c->d_idx + off;
+        a.n = std::min<int64_t>(n, b1 * B) - off;
         a.Bfull = (int)B;
         a.P = c->var->P; a.F = c->var->F; a.T = c->var->T;
         for (int t = 0; t < MAXT; t++) { a.shift_y[t] = sp.shift_y[t]; a.loss_kind[t] = c->loss_kind[t]; }
         for (int k = 0; k < MAXP; k++) a.shift_x[k] = sp.shift_x[k];
         a.agg_mean = c->agg_mean;
         a.use_bn = c->use_bn;
-        a.bscal = c->d_bscal;
-        a.bn_batch = c->use_bn ? c->d_bn_batch : nullptr;
-        k_batch_stats<<<(unsigned)nb, 256, 0, c->stream>>>(a);
+        a.bscal = c->d_bscal + (size_t)b0 * BS_STRIDE;
+        a.bn_batch = c->use_bn ? c->d_bn_batch + (size_t)b0 * 2 * c->var->P : nullptr;
+        k_batch_stats<<<(unsigned)(b1 - b0), 256, 0, c->stream>>>(a);
     } else {
-        k_fill_bscal<<<(unsigned)((nb + 127) / 128), 128, 0, c->stream>>>(c->d_bscal, (int)nb, n, (int)B, c->n_targ,
-                                                                          c->agg_mean, c->world);
+        k_fill_bscal<<<(unsigned)((b1 - b0 + 127) / 128), 128, 0, c->stream>>>(c->d_bscal + (size_t)b0 * BS_STRIDE, (int)(b1 - b0),
+                                                                               std::min<int64_t>(n, b1 * B) - off, (int)B,
+                                                                               c->n_targ, c->agg_mean, c->world);
     }
     CK(cudaGetLastError());
     return EH_OK;
 }
+
+eh_status prepare_batch_rows(eh_ctx* c, int64_t n, int64_t B) { return prepare_batch_rows_range(c, n, B, 0, (n + B - 1) / B); }
 
 // enqueue the K1/K2 launches of batches [b0, b1) of the resident index stream; the loss of
 // batch b goes to loss_base[b - b0]
@@ -627,6 +638,28 @@ eh_status run_persistent(eh_ctx* c, int64_t n, int64_t B, int64_t first, int64_t
     return EH_OK;
 }
 
+// Lux BatchNorm running statistics (momentum 0.1, unbiased variance) after steps [first, first+nsteps) whose
+// losses sit in c->h_loss[0..nsteps); skipped batches excluded
+eh_status update_bn_running(eh_ctx* c, int64_t n, int64_t B, int64_t first, int64_t nsteps)
+{
+    const int64_t nb = (n + B - 1) / B;
+    const int P = c->var->P;
+    std::vector<float> bb((size_t)nb * 2 * P);
+    CK(cudaMemcpy(bb.data(), c->d_bn_batch, bb.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    for (int64_t k = 0; k < nsteps; k++) {
+        if (std::isnan(c->h_loss[k])) continue;
+        int64_t b = (first + k) % nb;
+        int64_t Bk = std::min<int64_t>(B, n - b * B);
+        for (int i = 0; i < P; i++) {
+            float mu = bb[(size_t)b * 2 * P + 2 * i], var = bb[(size_t)b * 2 * P + 2 * i + 1];
+            float unb = Bk > 1 ? var * (float)Bk / (float)(Bk - 1) : var;
+            c->bn_mean[i] = 0.9f * c->bn_mean[i] + 0.1f * mu;
+            c->bn_var[i] = 0.9f * c->bn_var[i] + 0.1f * unb;
+        }
+    }
+    return EH_OK;
+}
+
 // the step loop: steps [first, first+nsteps) of the resident index stream; step s trains on batch
 // s mod nb (steps beyond one pass start another pass over the same permutation)
 eh_status run_steps(eh_ctx* c, int64_t n, int64_t B, int64_t first, int64_t nsteps, float* losses, int apply,
@@ -701,23 +734,109 @@ eh_status run_steps(eh_ctx* c, int64_t n, int64_t B, int64_t first, int64_t nste
         c->last_step_ms = tot;
     }
     if (losses) memcpy(losses, c->h_loss, (size_t)nsteps * sizeof(float));
-    // Lux BatchNorm running statistics (momentum 0.1, unbiased variance), skipped batches excluded
-    if (c->use_bn && apply) {
-        const int P = c->var->P;
-        std::vector<float> bb((size_t)nb * 2 * P);
-        CK(cudaMemcpy(bb.data(), c->d_bn_batch, bb.size() * sizeof(float), cudaMemcpyDeviceToHost));
-        for (int64_t k = 0; k < nsteps; k++) {
-            if (std::isnan(c->h_loss[k])) continue;
-            int64_t b = (first + k) % nb;
-            int64_t Bk = std::min<int64_t>(B, n - b * B);
-            for (int i = 0; i < P; i++) {
-                float mu = bb[(size_t)b * 2 * P + 2 * i], var = bb[(size_t)b * 2 * P + 2 * i + 1];
-                float unb = Bk > 1 ? var * (float)Bk / (float)(Bk - 1) : var;
-                c->bn_mean[i] = 0.9f * c->bn_mean[i] + 0.1f * mu;
-                c->bn_var[i] = 0.9f * c->bn_var[i] + 0.1f * unb;
+    if (c->use_bn && apply) return update_bn_running(c, n, B, first, nsteps);
+    return EH_OK;
+}
+
+// run_epoch! with the host permutation streamed in: the 8-byte indices of segment k+1 travel host->device
+// (copy stream) and are converted while segment k trains (persistent kernel, compute stream).  Used for long
+// epochs; *used = false leaves everything untouched and the caller takes the plain path.
+eh_status epoch_pipelined(eh_ctx* c, const int64_t* perm1, int64_t n, int64_t B, float* losses, bool* used)
+{
+    *used = false;
+    const int64_t nb = (n + B - 1) / B;
+    if (nb < 64 || !c->persist_ok || (c->flags & EH_FLAG_NO_PERSIST) || c->profiling) return EH_OK;
+    const Split& sp = c->split[EH_SPLIT_TRAIN];
+    if (!sp.rec) return fail(c, EH_EINVAL, "train split not uploaded");
+    if (needs_data_stats(c) && c->world > 1) return EH_OK;  // the plain path reports it
+    eh_status s = ensure_idx_cap(c, (size_t)n);
+    if (s != EH_OK) return s;
+    s = ensure_bscal_cap(c, (size_t)nb);
+    if (s != EH_OK) return s;
+    s = ensure_loss_cap(c, (size_t)nb);
+    if (s != EH_OK) return s;
+    // snapshot of the trainable state: an out-of-range index is only known once its segment has been converted,
+    // and a failed call must leave the ctx as it found it
+    if (!c->d_snap) CK(dalloc(&c->d_snap, (size_t)3 * c->nflat + PARAM_TAIL + 16));
+    float* snap = c->d_snap;
+    CK(cudaMemcpyAsync(snap, c->d_theta, ((size_t)c->nflat + PARAM_TAIL) * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaMemcpyAsync(snap + c->nflat + PARAM_TAIL, c->d_m, (size_t)c->nflat * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+    CK(cudaMemcpyAsync(snap + 2 * c->nflat + PARAM_TAIL, c->d_v, (size_t)c->nflat * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+    static_assert(sizeof(OptState) <= 16 * sizeof(float), "snapshot tail too small");
+    CK(cudaMemcpyAsync(snap + 3 * c->nflat + PARAM_TAIL, c->d_ost, sizeof(OptState), cudaMemcpyDeviceToDevice, c->stream));
+    const std::vector<float> bn_mean0 = c->bn_mean, bn_var0 = c->bn_var;
+
+    const int64_t seg = std::max<int64_t>(32, (nb + 7) / 8);  // steps per segment
+    const int64_t nseg = (nb + seg - 1) / seg;
+    while ((int64_t)c->seg_ev.size() < nseg) {
+        cudaEvent_t e;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->seg_ev.push_back(e);
+    }
+    cudaStream_t cs = c->copy_stream;
+    CK(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream));
+    CK(cudaEventRecord(c->ev2, c->stream));
+    CK(cudaStreamWaitEvent(cs, c->ev2, 0));  // earlier work on the compute stream may still read d_idx
+    auto copy_seg = [&](int64_t k) -> eh_status {
+        const int64_t off = k * seg * B, cnt = std::min<int64_t>(n, (k + 1) * seg * B) - off;
+        CK(cudaMemcpyAsync(c->d_idx64 + off, perm1 + off, (size_t)cnt * sizeof(int64_t), cudaMemcpyHostToDevice, cs));
+        k_idx_convert<<<(unsigned)((cnt + 255) / 256), 256, 0, cs>>>(c->d_idx64 + off, c->d_idx + off, cnt, sp.N, c->d_err);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(c->seg_ev[k], cs));
+        return EH_OK;
+    };
+    s = copy_seg(0);
+    if (s != EH_OK) return s;
+    const unsigned tag0 = c->epoch_tag, dp0 = c->dp_steps;
+    for (int64_t k = 0; k < nseg; k++) {
+        if (k + 1 < nseg) {
+            s = copy_seg(k + 1);
+            if (s != EH_OK) return s;
+        }
+        const int64_t s0 = k * seg, s1 = std::min<int64_t>(nb, s0 + seg);
+        CK(cudaStreamWaitEvent(c->stream, c->seg_ev[k], 0));
+        s = prepare_batch_rows_range(c, n, B, s0, s1);
+        if (s != EH_OK) return s;
+        bool u = false;
+        s = enqueue_persistent(c, sp.rec, c->d_idx, c->d_bscal, c->d_loss + s0, n, B, s0, s1 - s0, &u, nullptr);
+        if (s != EH_OK) return s;
+        if (!u) {
+            if (k == 0) {  // nothing has trained yet: hand over to the plain path
+                CK(cudaStreamSynchronize(cs));
+                CK(cudaStreamSynchronize(c->stream));
+                return EH_OK;
             }
+            return fail(c, EH_ECUDA, "persistent launch refused mid-epoch: %s", c->err.c_str());
         }
     }
+    CK(cudaEventRecord(c->ev3, c->stream));
+    CK(cudaMemcpyAsync(c->h_loss, c->d_loss, (size_t)nb * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    unsigned herr = 0;
+    int ierr = 0;
+    CK(cudaMemcpyAsync(&herr, c->d_dperr, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(&ierr, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (herr || ierr) {
+        CK(cudaMemcpy(c->d_theta, snap, ((size_t)c->nflat + PARAM_TAIL) * sizeof(float), cudaMemcpyDeviceToDevice));
+        CK(cudaMemcpy(c->d_m, snap + c->nflat + PARAM_TAIL, (size_t)c->nflat * sizeof(float), cudaMemcpyDeviceToDevice));
+        CK(cudaMemcpy(c->d_v, snap + 2 * c->nflat + PARAM_TAIL, (size_t)c->nflat * sizeof(float), cudaMemcpyDeviceToDevice));
+        CK(cudaMemcpy(c->d_ost, snap + 3 * c->nflat + PARAM_TAIL, sizeof(OptState), cudaMemcpyDeviceToDevice));
+        c->bn_mean = bn_mean0; c->bn_var = bn_var0;
+        c->perm_n = 0; c->perm_B = 0;
+        (void)tag0; (void)dp0;  // tags only ever grow: a rolled-back epoch simply leaves a gap
+        if (herr) {
+            cudaMemset(c->d_dperr, 0, sizeof(unsigned));
+            return fail(c, EH_ENCCL, "persistent kernel gave up waiting (a CTA or a data-parallel peer never arrived)");
+        }
+        return fail(c, EH_EINVAL, "index out of range 1..%lld in batch / permutation", (long long)sp.N);
+    }
+    CK(cudaEventElapsedTime(&c->last_ms, c->ev2, c->ev3));
+    c->last_launches = nseg;
+    c->last_step_ms = c->last_ms;
+    c->perm_n = n; c->perm_B = B;
+    if (losses) memcpy(losses, c->h_loss, (size_t)nb * sizeof(float));
+    *used = true;
+    if (c->use_bn) return update_bn_running(c, n, B, 0, nb);
     return EH_OK;
 }
 
@@ -934,25 +1053,37 @@ eh_status ensure_host_stage(eh_ctx* c, HostStage& h, int64_t B)
     CK(dalloc(&h.d_X, (size_t)cap * c->n_pred_raw));
     CK(dalloc(&h.d_planes, (size_t)cap * (c->n_forc_raw + c->n_targ)));
     CK(dalloc(&h.d_rec, (size_t)cap * c->var->R4));
-    if (!h.d_cnt) CK(dalloc(&h.d_cnt, (size_t)MAXT));
+    if (!h.d_cnt) {
+        CK(dalloc(&h.d_cnt, (size_t)MAXT));
+        CK(cudaMemset(h.d_cnt, 0, MAXT * sizeof(int)));  // k_bscal_from_counts re-zeroes it after every use
+    }
     if (!h.d_bscal) CK(dalloc(&h.d_bscal, (size_t)BS_STRIDE));
     if (!h.d_loss) CK(dalloc(&h.d_loss, (size_t)1));
-    if (!h.done) CK(cudaEventCreateWithFlags(&h.done, cudaEventDisableTiming));
+    if (!h.ready) CK(cudaEventCreateWithFlags(&h.ready, cudaEventDisableTiming));
+    if (!h.freed) CK(cudaEventCreateWithFlags(&h.freed, cudaEventDisableTiming));
     h.cap = cap;
     return EH_OK;
 }
 
-// enqueue: H2D copies of one host batch, pack, per-batch scalars, K1, K2 (all on c->stream)
+// enqueue one host batch: H2D copies on the copy stream (they overlap the steps of earlier batches still running on
+// the compute stream; EH_HOST_SLOTS staging slots), then pack, per-batch scalars, K1, K2 on the compute stream.
+// loss_dst: where K2 stores the step's loss -- device memory, or page-locked host memory (written over PCIe by the
+// kernel itself, so no separate D2H copy is enqueued).
 eh_status enqueue_host_step(eh_ctx* c, HostStage& h, int64_t B, const float* X, const float* const* forc,
-                            const float* const* targ)
+                            const float* const* targ, float* loss_dst)
 {
     const Variant* v = c->var;
-    CK(cudaMemcpyAsync(h.d_X, X, (size_t)B * c->n_pred_raw * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    cudaStream_t cs = c->copy_stream;
+    if (h.used) CK(cudaStreamWaitEvent(cs, h.freed, 0));  // the step that last read this slot must have retired
+    CK(cudaMemcpyAsync(h.d_X, X, (size_t)B * c->n_pred_raw * sizeof(float), cudaMemcpyHostToDevice, cs));
     for (int f = 0; f < c->n_forc_raw; f++)
-        CK(cudaMemcpyAsync(h.d_planes + (size_t)f * B, forc[f], (size_t)B * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(h.d_planes + (size_t)f * B, forc[f], (size_t)B * sizeof(float), cudaMemcpyHostToDevice, cs));
     for (int t = 0; t < c->n_targ; t++)
         CK(cudaMemcpyAsync(h.d_planes + (size_t)(c->n_forc_raw + t) * B, targ[t], (size_t)B * sizeof(float),
-                           cudaMemcpyHostToDevice, c->stream));
+                           cudaMemcpyHostToDevice, cs));
+    CK(cudaEventRecord(h.ready, cs));
+    CK(cudaStreamWaitEvent(c->stream, h.ready, 0));
+    h.used = true;
     PackArgs p;
     memset(&p, 0, sizeof p);
     p.X = h.d_X; p.planes = h.d_planes; p.N = B; p.P_raw = c->n_pred_raw; p.ncols = c->ncols; p.R4 = v->R4;
@@ -961,7 +1092,6 @@ eh_status enqueue_host_step(eh_ctx* c, HostStage& h, int64_t B, const float* X, 
     bool heavy = c->use_bn;
     for (int t = 0; t < c->n_targ; t++) heavy |= (c->loss_kind[t] == LOSS_NSELOSS);
     if (!heavy) {
-        CK(cudaMemsetAsync(h.d_cnt, 0, MAXT * sizeof(int), c->stream));
         k_pack_count<<<(unsigned)((B + 255) / 256), 256, 0, c->stream>>>(p, c->n_targ, v->P + v->F, h.d_cnt);
         CK(cudaGetLastError());
         k_bscal_from_counts<<<1, 32, 0, c->stream>>>(h.d_bscal, h.d_cnt, c->n_targ, c->agg_mean);
@@ -987,9 +1117,10 @@ eh_status enqueue_host_step(eh_ctx* c, HostStage& h, int64_t B, const float* X, 
         CK(cudaGetLastError());
         if (c->stats_cap < 1) { CK(dalloc(&c->d_stats, (size_t)64 * MAXT)); c->stats_cap = 64; }
         bool used = false;
-        eh_status s = enqueue_persistent(c, h.d_rec, nullptr, h.d_bscal, h.d_loss, B, B, 0, 1, &used, nullptr);
+        eh_status s = enqueue_persistent(c, h.d_rec, nullptr, h.d_bscal, loss_dst, B, B, 0, 1, &used, nullptr);
         if (s != EH_OK) return s;
         if (!used) return fail(c, EH_EUNSUPPORTED, "persistent kernel unavailable for this shape: %s", c->err.c_str());
+        CK(cudaEventRecord(h.freed, c->stream));
         return EH_OK;
     }
     StepArgs a;
@@ -1001,8 +1132,9 @@ eh_status enqueue_host_step(eh_ctx* c, HostStage& h, int64_t B, const float* X, 
     CK(pick_variant(c, B)->launch_step(a, g.grid, g.nwarps, g.smem, c->stream, pdl));
     UpdateArgs u;
     fill_update_args(c, u);
-    u.G = g.grid; u.bscal = h.d_bscal; u.loss_out = h.d_loss;
+    u.G = g.grid; u.bscal = h.d_bscal; u.loss_out = loss_dst;
     CK(launch_update(u, c->stream, pdl));
+    CK(cudaEventRecord(h.freed, c->stream));
     return EH_OK;
 }
 
@@ -1049,6 +1181,8 @@ eh_status eh_create(eh_ctx** out, const eh_model_desc* desc)
         CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
         CK(cudaEventCreate(&c->ev0));
         CK(cudaEventCreate(&c->ev1));
+        CK(cudaEventCreate(&c->ev2));
+        CK(cudaEventCreate(&c->ev3));
         size_t fixed = (size_t)(rup4(v->NW) + SS_FLOATS) * 4;
         size_t stage = (size_t)std::max(v->stage_floats, v->NPART) * 4;
         int wmax = (int)std::min<size_t>((size_t)v->max_warps, (c->smem_optin - fixed - 8192) / stage);
@@ -1096,6 +1230,7 @@ void eh_destroy(eh_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->gexec) cudaGraphExecDestroy(c->gexec);
     for (int r = 0; r < c->world && c->world > 1; r++)
@@ -1110,13 +1245,18 @@ void eh_destroy(eh_ctx* c)
         void* hp[] = {h.d_X, h.d_planes, h.d_rec, h.d_cnt, h.d_bscal, h.d_loss};
         for (void* p : hp)
             if (p) cudaFree(p);
-        if (h.done) cudaEventDestroy(h.done);
+        if (h.ready) cudaEventDestroy(h.ready);
+        if (h.freed) cudaEventDestroy(h.freed);
     }
     if (c->h_loss) cudaFreeHost(c->h_loss);
     if (c->h_async_loss) cudaFreeHost(c->h_async_loss);
     for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev2) cudaEventDestroy(c->ev2);
+    if (c->ev3) cudaEventDestroy(c->ev3);
+    for (cudaEvent_t e : c->seg_ev) cudaEventDestroy(e);
+    if (c->d_snap) cudaFree(c->d_snap);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     delete c;
@@ -1306,6 +1446,13 @@ eh_status eh_run_steps(eh_ctx* c, int64_t B, int64_t first_step, int64_t n_steps
 
 eh_status eh_epoch(eh_ctx* c, const int64_t* perm1, int64_t n, int64_t B, float* losses)
 {
+    if (!c) return EH_EINVAL;
+    if (!perm1 || n <= 0) return fail(c, EH_EINVAL, "empty permutation");
+    if (B <= 0) return fail(c, EH_EINVAL, "batch size must be positive");
+    CK(cudaSetDevice(c->device));
+    bool piped = false;
+    eh_status ps = epoch_pipelined(c, perm1, n, B, losses, &piped);
+    if (ps != EH_OK || piped) return ps;
     eh_status s = eh_set_perm(c, perm1, n);
     if (s != EH_OK) return s;
     if (B <= 0) return fail(c, EH_EINVAL, "batch size must be positive");
@@ -1321,7 +1468,7 @@ eh_status eh_step_host(eh_ctx* c, int64_t B, const float* X, const float* const*
     HostStage& h = c->hs[0];
     eh_status s = ensure_host_stage(c, h, B);
     if (s != EH_OK) return s;
-    s = enqueue_host_step(c, h, B, X, forc, targ);
+    s = enqueue_host_step(c, h, B, X, forc, targ, h.d_loss);
     if (s != EH_OK) return s;
     float L = 0.f;
     CK(cudaMemcpyAsync(&L, h.d_loss, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
@@ -1347,15 +1494,19 @@ eh_status eh_step_host_async(eh_ctx* c, int64_t B, const float* X, const float* 
         }
     }
     HostStage& h = c->hs[c->hs_next];
-    c->hs_next ^= 1;
-    // the staging buffers of this slot are free once the step that last used them has retired;
-    // everything runs in order on one stream, so reuse is already ordered.
+    c->hs_next = (c->hs_next + 1) % EH_HOST_SLOTS;
+    if (B > h.cap && h.used) {
+        // growing a slot frees its buffers: nothing may still be reading them
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaStreamSynchronize(c->copy_stream));
+    }
     eh_status s = ensure_host_stage(c, h, B);
     if (s != EH_OK) return s;
-    s = enqueue_host_step(c, h, B, X, forc, targ);
-    if (s != EH_OK) return s;
+    // the update kernel stores the loss straight into the page-locked ring (device-visible under UVA):
+    // the device->host read of the step's result costs no extra enqueue
     float* pin = c->h_async_loss + c->async_used++;
-    CK(cudaMemcpyAsync(pin, h.d_loss, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    s = enqueue_host_step(c, h, B, X, forc, targ, pin);
+    if (s != EH_OK) return s;
     c->pending_loss.emplace_back(pin, loss_slot);
     return EH_OK;
 }

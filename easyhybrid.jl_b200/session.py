@@ -126,8 +126,16 @@ class FusedSession:
         self._ck(self.lib.eh_step_host(self.h, Xc.shape[0], Xp, pf, pt, C.byref(loss)))
         return float(loss.value)
 
-    def epoch(self, perm0, batchsize):
-        a, p = self._idx1(perm0)
+    def epoch(self, perm0, batchsize, one_based=False):
+        """run_epoch! over a host permutation.  ``one_based=True``: ``perm0`` already is what Julia hands over
+        (1-based contiguous int64, ideally page-locked) and is passed through without a copy."""
+        if one_based:
+            a = perm0
+            if a.dtype != np.int64 or not a.flags.c_contiguous:
+                raise ValueError("one_based permutations must be contiguous int64")
+            p = a.ctypes.data_as(C.POINTER(C.c_int64))
+        else:
+            a, p = self._idx1(perm0)
         nsteps = (a.size + batchsize - 1) // batchsize
         losses = np.empty(nsteps, dtype=np.float32)
         self._ck(self.lib.eh_epoch(self.h, p, a.size, batchsize, losses.ctypes.data_as(_fp)))
