@@ -20,7 +20,7 @@ ROLE_NEURAL, ROLE_GLOBAL, ROLE_FIXED = 0, 1, 2
 LOSS = {"mse": 0, "rmse": 1, "mae": 2, "nseLoss": 3}
 AGG = {"sum": 0, "mean": 1}
 OPT = {"Adam": 0, "AdamW": 1, "RMSProp": 2, "Descent": 3}
-PM = {"RBQ10": 0, "EXPO": 1, "LINEAR": 2, "LINEAR2": 3, "PROGRAM": 100}
+PM = {"RBQ10": 0, "EXPO": 1, "LINEAR": 2, "LINEAR2": 3, "EXPO2": 4, "PROGRAM": 100}
 
 OPS = {
     "const": 0, "forcing": 1, "param": 2,

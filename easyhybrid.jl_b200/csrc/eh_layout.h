@@ -19,7 +19,7 @@ namespace eh {
 enum : int { ACT_IDENTITY = 0, ACT_TANH = 1, ACT_SIGMOID = 2, ACT_RELU = 3, ACT_SWISH = 4 };
 enum : int { ROLE_NEURAL = 0, ROLE_GLOBAL = 1, ROLE_FIXED = 2 };
 enum : int { LOSS_MSE = 0, LOSS_RMSE = 1, LOSS_MAE = 2, LOSS_NSELOSS = 3 };
-enum : int { PM_RBQ10 = 0, PM_EXPO = 1, PM_LINEAR = 2, PM_LINEAR2 = 3, PM_PROGRAM = 100 };
+enum : int { PM_RBQ10 = 0, PM_EXPO = 1, PM_LINEAR = 2, PM_LINEAR2 = 3, PM_EXPO2 = 4, PM_PROGRAM = 100 };
 
 constexpr int MAXPS = 8;   // process-parameter slots
 constexpr int MAXT = 4;    // targets

@@ -21,6 +21,7 @@
 #include "eh_update_kernel.cuh"
 #include "eh_epoch_kernel.cuh"
 #include "eh_eval_kernel.cuh"
+#include "eh_wide.h"
 
 using namespace eh;
 
@@ -60,6 +61,11 @@ struct eh_ctx {
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     const Variant* var = nullptr;   // engine chosen at eh_create (FFMA2 one sample per lane, or tensor pipe)
     const Variant* var2 = nullptr;  // FFMA2 two samples per lane: same layouts, used for large batches
+    // wide-hidden-layer path (bf16 tcgen05 GEMMs, eh_wide.cu): `var` then points at `wide_var`, a descriptor
+    // without kernels that only carries the record / slot geometry the shared host code reads
+    eh::wide::WideNet* wide = nullptr;
+    Variant wide_var{};
+    eh::wide::WideModel wide_model{};
     // model
     int n_pred_raw = 0, n_forc_raw = 0, n_targ = 0;
     int nflat = 0, ntheta = 0, nglob = 0;
@@ -660,6 +666,39 @@ eh_status update_bn_running(eh_ctx* c, int64_t n, int64_t B, int64_t first, int6
     return EH_OK;
 }
 
+// the step loop of the wide path: one sequence of launches per step on c->stream (eh_wide.cu)
+eh_status wide_run_steps(eh_ctx* c, int64_t n, int64_t B, int64_t first, int64_t nsteps, float* losses, int apply,
+                         float* grad_out_host)
+{
+    const Split& sp = c->split[EH_SPLIT_TRAIN];
+    const int64_t nb = (n + B - 1) / B;
+    if (c->world > 1) return fail(c, EH_EUNSUPPORTED, "the wide (bf16 tcgen05) path is single-GPU in this build");
+    for (int64_t b = 0; b < nb; b++)
+        if (!eh::wide::WideNet::batch_ok(std::min<int64_t>(B, n - b * B)))
+            return fail(c, EH_EUNSUPPORTED, "wide path: every batch must hold a multiple of 128 samples (got %lld)",
+                        (long long)std::min<int64_t>(B, n - b * B));
+    CK(cudaEventRecord(c->ev0, c->stream));
+    for (int64_t k = 0; k < nsteps; k++) {
+        const int64_t b = (first + k) % nb;
+        const int64_t Bk = std::min<int64_t>(B, n - b * B);
+        cudaError_t e = c->wide->step(sp.rec, c->d_idx + b * B, 0, (int)Bk, c->d_bscal + (size_t)b * BS_STRIDE, c->d_theta, c->d_m,
+                                      c->d_v, c->d_ost, c->d_grad, c->d_loss + k, apply, c->stream);
+        if (e != cudaSuccess) return fail(c, EH_ECUDA, "wide path: %s", c->wide->error());
+        if (apply) CK(refresh_tail(c));
+    }
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaMemcpyAsync(c->h_loss, c->d_loss, (size_t)nsteps * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (grad_out_host)
+        CK(cudaMemcpyAsync(grad_out_host, c->d_grad, (size_t)c->nflat * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+    c->last_launches = nsteps * (3 + 5 * (int64_t)(c->var->NH - 1) + 4);
+    c->last_step_ms = c->last_ms;
+    if (losses) memcpy(losses, c->h_loss, (size_t)nsteps * sizeof(float));
+    if (c->use_bn && apply) return update_bn_running(c, n, B, first, nsteps);
+    return EH_OK;
+}
+
 // the step loop: steps [first, first+nsteps) of the resident index stream; step s trains on batch
 // s mod nb (steps beyond one pass start another pass over the same permutation)
 eh_status run_steps(eh_ctx* c, int64_t n, int64_t B, int64_t first, int64_t nsteps, float* losses, int apply,
@@ -671,6 +710,7 @@ eh_status run_steps(eh_ctx* c, int64_t n, int64_t B, int64_t first, int64_t nste
     if (first < 0 || nsteps < 0) return fail(c, EH_EINVAL, "step range out of bounds");
     eh_status s = ensure_loss_cap(c, (size_t)std::max<int64_t>(nsteps, nb));
     if (s != EH_OK) return s;
+    if (c->wide) return wide_run_steps(c, n, B, first, nsteps, losses, apply, grad_out_host);
     const bool profile = c->profiling != 0;
     const bool pdl = !(c->flags & EH_FLAG_NO_PDL) && !profile;
     const bool use_graph = !(c->flags & EH_FLAG_NO_GRAPH) && !profile && apply && !grad_out_host && nsteps >= nb && nb >= 4;
@@ -855,9 +895,32 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
     for (int l = 0; l < ch.n_hidden; l++) hmax = std::max(hmax, ch.hidden[l]);
     if (d->n_pm_args != 3 || d->pm_args[0].kind != 0 || d->pm_args[1].kind != 0 || d->pm_args[2].kind != 1)
         return fail(c, EH_EINVAL, "built-in process models take (param, param, forcing) arguments");
+    // wide chains (all hidden layers 256 or 512 wide): bf16 tcgen05 GEMM path
+    bool wide = false;
+    if (hmax >= 256) {
+        bool same = true;
+        for (int l = 0; l < ch.n_hidden; l++) same &= (ch.hidden[l] == hmax);
+        if (!same ||
+            !eh::wide::WideNet::supported(ch.n_in, hmax, ch.n_hidden, ch.n_out, ch.activation, d->process_model))
+            return fail(c, EH_EUNSUPPORTED,
+                        "wide chains need equal hidden widths of 256 or 512, 2..6 hidden layers, <= 4 inputs, <= 2 outputs and "
+                        "a tanh / sigmoid / relu activation (got n_in=%d hidden=%dx%d n_out=%d activation=%d)",
+                        ch.n_in, ch.n_hidden, hmax, ch.n_out, ch.activation);
+        wide = true;
+        Variant& wv = c->wide_var;
+        memset(&wv, 0, sizeof wv);
+        wv.pm = d->process_model; wv.P = ch.n_in; wv.NH = ch.n_hidden; wv.H = hmax; wv.NOUT = ch.n_out; wv.act = ch.activation;
+        wv.scale = d->scale_nn_outputs ? 1 : 0;
+        wv.engine = 3; wv.chunk = 128;
+        wv.F = 1; wv.NPS = 2;
+        wv.T = (d->process_model == EH_PM_LINEAR2 || d->process_model == EH_PM_EXPO2) ? 2 : 1;
+        wv.R4 = rup4(wv.P + wv.F + wv.T);
+        wv.NW = 0; wv.NPART = NSTAT; wv.off_stats = 0; wv.stage_floats = NSTAT; wv.max_warps = 8;
+        wv.name = "wide/bf16-tcgen05";
+    }
     // engine 0 (exact-fp32 FFMA2) by default; engine 1 (tensor pipe, 3xTF32) on request where a variant exists
-    const Variant* v = nullptr;
-    if (d->flags & EH_FLAG_TENSOR_PIPE)
+    const Variant* v = wide ? &c->wide_var : nullptr;
+    if (!v && (d->flags & EH_FLAG_TENSOR_PIPE))
         v = find_variant(d->process_model, ch.n_in, ch.n_hidden, rup4(hmax), ch.n_out, ch.activation,
                          d->scale_nn_outputs ? 1 : 0, 1);
     if (!v)
@@ -894,11 +957,12 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
         if (d->role[p] == EH_ROLE_GLOBAL) ng = std::max(ng, d->role_index[p] + 1);
     c->nglob = ng;
     c->nflat = off + ng;
-    if (c->nflat > 2048 - NSTAT) return fail(c, EH_EUNSUPPORTED, "parameter vector too long for the single-CTA update");
+    if (!wide && c->nflat > 2048 - NSTAT) return fail(c, EH_EUNSUPPORTED, "parameter vector too long for the single-CTA update");
 
     // smem weight image gather table
-    const int H = D.H, P = D.P, NH = D.NH, NOUT = D.NOUT;
+    const int H = wide ? v->H : D.H, P = wide ? v->P : D.P, NH = wide ? v->NH : D.NH, NOUT = wide ? v->NOUT : D.NOUT;
     c->h_wsrc.assign((size_t)v->NW + ng, -1);
+    if (!wide) {
     auto Wsrc = [&](int l /*1-based*/, int j, int k) -> int {
         if (j >= width[l] || k >= width[l - 1]) return -1;
         return w_off[l - 1] + j + k * width[l];
@@ -918,6 +982,7 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
     for (int o = 0; o < NOUT; o++)
         for (int k = 0; k < H; k++) c->h_wsrc[D.off_wo() + o * H + k] = Wsrc(L, o, k);
     for (int o = 0; o < 4; o++) c->h_wsrc[D.off_bo() + o] = o < NOUT ? Bsrc(L, o) : -1;
+    }
     for (int g = 0; g < ng; g++) c->h_wsrc[(size_t)v->NW + g] = off + g;
 
     // canonical slots from the built-in form's (param, param, forcing) binding
@@ -958,7 +1023,7 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
                 c->h_pmap[b_off[l - 1] + j] = ob[l - 1] + j;
             }
     }
-    for (int l = 1; l <= L && v->engine == 0; l++) {
+    for (int l = 1; l <= L && v->engine == 0 && !wide; l++) {
         if (l == L && D.LR) {
             // output layer kept in registers: [NOUT][H+1] block behind the statistics
             for (int j = 0; j < width[l]; j++) {
@@ -993,7 +1058,7 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
         else c->h_cells[2 * p + 1] = i;
     }
     c->h_slot_of_flat.assign((size_t)c->nflat, -1);
-    c->persist_ok = true;
+    c->persist_ok = !wide;
     for (int g = 0; g < ng; g++)
         for (int s = 0; s < v->NPS; s++)
             if (c->slots[s].role == ROLE_GLOBAL && c->slots[s].idx == g) c->h_slot_of_flat[off + g] = s;
@@ -1029,6 +1094,24 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
     c->eta = d->eta; c->beta1 = d->beta1; c->beta2 = d->beta2; c->eps = d->eps; c->lambda = d->lambda;
     c->bn_mean.assign((size_t)ch.n_in, 0.f);
     c->bn_var.assign((size_t)ch.n_in, 1.f);
+    if (wide) {
+        if (L > 8) return fail(c, EH_EUNSUPPORTED, "wide chains: at most 7 hidden layers");
+        eh::wide::WideModel& wm = c->wide_model;
+        memset(&wm, 0, sizeof wm);
+        wm.P = P; wm.H = H; wm.NH = NH; wm.NOUT = NOUT; wm.R4 = v->R4; wm.nflat = c->nflat; wm.ntheta = c->ntheta;
+        for (int l = 0; l < L; l++) { wm.w_off[l] = w_off[l]; wm.b_off[l] = b_off[l]; }
+        wm.act = ch.activation; wm.scale = d->scale_nn_outputs ? 1 : 0; wm.pm = d->process_model;
+        wm.T = v->T; wm.F = v->F; wm.NPS = v->NPS; wm.use_bn = c->use_bn; wm.agg_mean = c->agg_mean;
+        for (int t = 0; t < MAXT; t++) wm.loss_kind[t] = c->loss_kind[t];
+        for (int s2 = 0; s2 < MAXPS; s2++) {
+            wm.slot[s2].role = c->slots[s2].role; wm.slot[s2].idx = c->slots[s2].idx; wm.slot[s2].lo = c->slots[s2].lo;
+            wm.slot[s2].span = c->slots[s2].span; wm.slot[s2].fixedv = c->slots[s2].fixedv;
+        }
+        for (int i = 0; i < 4; i++) wm.pmc[i] = c->pmc[i];
+        wm.opt_kind = c->opt_kind; wm.adamw_coupled = c->adamw_coupled;
+        wm.eta = c->eta; wm.beta1 = c->beta1; wm.beta2 = c->beta2; wm.eps = c->eps; wm.lambda = c->lambda;
+        wm.nsm = c->nsm;
+    }
     return EH_OK;
 }
 
@@ -1187,7 +1270,7 @@ eh_status eh_create(eh_ctx** out, const eh_model_desc* desc)
         size_t stage = (size_t)std::max(v->stage_floats, v->NPART) * 4;
         int wmax = (int)std::min<size_t>((size_t)v->max_warps, (c->smem_optin - fixed - 8192) / stage);
         if (wmax < 1) return fail(c, EH_EUNSUPPORTED, "variant %s needs %zu B of shared memory per warp", v->name, stage);
-        CK(v->prepare(c->smem_optin - 256, fixed));  // kernels carry a few bytes of static shared memory
+        if (v->prepare) CK(v->prepare(c->smem_optin - 256, fixed));  // kernels carry a few bytes of static shared memory
         if (c->var2) CK(c->var2->prepare(c->smem_optin - 256, fixed));
         CK(dalloc(&c->d_wsrc, c->h_wsrc.size()));
         CK(dalloc(&c->d_pmap, c->h_pmap.size()));
@@ -1218,6 +1301,17 @@ eh_status eh_create(eh_ctx** out, const eh_model_desc* desc)
         CK(dalloc(&c->d_bn_test, (size_t)BS_STRIDE));
         CK(cudaMemset(c->d_theta, 0, ((size_t)c->nflat + PARAM_TAIL) * sizeof(float)));
         CK(refresh_tail(c));
+        if (v->engine == 3) {
+            c->wide_model.d_slot_of_flat = c->d_slot_of_flat;
+            char werr[256] = {0};
+            c->wide = eh::wide::WideNet::create(c->wide_model, werr, sizeof werr);
+            if (!c->wide) return fail(c, EH_ECUDA, "%s", werr);
+            eh_status rs = reset_opt_state(c);
+            if (rs != EH_OK) return rs;
+            cudaError_t we = c->wide->refresh_images(c->d_theta, c->d_m, c->d_v, c->d_ost, c->stream);
+            if (we != cudaSuccess) return fail(c, EH_ECUDA, "wide path: %s", c->wide->error());
+            return EH_OK;
+        }
         return reset_opt_state(c);
     };
     s = cuda_setup();
@@ -1232,6 +1326,8 @@ void eh_destroy(eh_ctx* c)
     cudaSetDevice(c->device);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    delete c->wide;
+    c->wide = nullptr;
     if (c->gexec) cudaGraphExecDestroy(c->gexec);
     for (int r = 0; r < c->world && c->world > 1; r++)
         if (r != c->rank && c->dp_peer[r]) cudaIpcCloseMemHandle(c->dp_peer[r]);
@@ -1325,6 +1421,8 @@ eh_status eh_set_params(eh_ctx* c, const float* flat, int64_t n)
     CK(cudaSetDevice(c->device));
     CK(cudaMemcpyAsync(c->d_theta, flat, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     CK(refresh_tail(c));
+    if (c->wide && c->wide->refresh_images(c->d_theta, c->d_m, c->d_v, c->d_ost, c->stream) != cudaSuccess)
+        return fail(c, EH_ECUDA, "wide path: %s", c->wide->error());
     CK(cudaStreamSynchronize(c->stream));
     return EH_OK;
 }
@@ -1464,6 +1562,7 @@ eh_status eh_step_host(eh_ctx* c, int64_t B, const float* X, const float* const*
 {
     if (!c) return EH_EINVAL;
     if (B <= 0 || !X || !targ) return fail(c, EH_EINVAL, "bad eh_step_host arguments");
+    if (c->wide) return fail(c, EH_EUNSUPPORTED, "host-batch steps are not available on the wide (bf16 tcgen05) path: stage the split with eh_upload");
     CK(cudaSetDevice(c->device));
     HostStage& h = c->hs[0];
     eh_status s = ensure_host_stage(c, h, B);
@@ -1482,6 +1581,7 @@ eh_status eh_step_host_async(eh_ctx* c, int64_t B, const float* X, const float* 
 {
     if (!c) return EH_EINVAL;
     if (B <= 0 || !X || !targ) return fail(c, EH_EINVAL, "bad eh_step_host_async arguments");
+    if (c->wide) return fail(c, EH_EUNSUPPORTED, "host-batch steps are not available on the wide (bf16 tcgen05) path: stage the split with eh_upload");
     CK(cudaSetDevice(c->device));
     if (c->async_used == c->async_cap) {
         if (c->async_used) {
@@ -1562,6 +1662,43 @@ eh_status eh_eval(eh_ctx* c, int32_t split, float* yhat, double* stats, float* n
     for (int i = 0; i < 4; i++) a.pmc[i] = c->pmc[i];
     for (int t = 0; t < MAXT; t++) a.shift_y[t] = sp.shift_y[t];
     a.yhat = d_yhat; a.parout = d_par; a.partial = c->d_evalpart;
+    if (c->wide) {
+        // wide chains: forward GEMMs over chunks of rows, statistics accumulated on the device
+        double* d_acc = nullptr;
+        CK(dalloc(&d_acc, (size_t)MAXT * EVAL_NSTAT));
+        CK(cudaMemsetAsync(d_acc, 0, MAXT * EVAL_NSTAT * sizeof(double), c->stream));
+        CK(cudaEventRecord(c->ev0, c->stream));
+        const int64_t chunk = c->wide->eval_chunk();
+        for (int64_t r0 = 0; r0 < N; r0 += chunk) {
+            const int bc = (int)std::min<int64_t>(chunk, N - r0);
+            if (c->wide->eval_rows(sp.rec, N, r0, bc, a.bscal, c->d_theta, d_yhat, d_par, N, d_acc, sp.shift_y, c->stream) != cudaSuccess) {
+                cudaFree(d_acc);
+                return fail(c, EH_ECUDA, "wide path: %s", c->wide->error());
+            }
+        }
+        CK(cudaEventRecord(c->ev1, c->stream));
+        double acc[MAXT * EVAL_NSTAT];
+        CK(cudaMemcpyAsync(acc, d_acc, sizeof acc, cudaMemcpyDeviceToHost, c->stream));
+        if (yhat) CK(cudaMemcpyAsync(yhat, d_yhat, (size_t)N * v->T * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
+        cudaFree(d_acc);
+        if (nn_out) {
+            for (int pi = 0; pi < c->nparam_desc; pi++) {
+                int s = c->slot_of_param[pi];
+                if (s < 0 || c->slots[s].role != ROLE_NEURAL) continue;
+                CK(cudaMemcpy(nn_out + (size_t)pi * N, d_par + (size_t)s * N, (size_t)N * sizeof(float), cudaMemcpyDeviceToHost));
+            }
+        }
+        if (d_yhat) cudaFree(d_yhat);
+        if (d_par) cudaFree(d_par);
+        if (stats)
+            for (int t = 0; t < v->T; t++) {
+                for (int q = 0; q < EVAL_NSTAT; q++) stats[(size_t)t * EH_EVAL_STATS + q] = acc[t * EVAL_NSTAT + q];
+                stats[(size_t)t * EH_EVAL_STATS + 8] = sp.shift_y[t];
+            }
+        return EH_OK;
+    }
     const int nwarps = 8;
     int64_t nchunks = (N + CHUNK - 1) / CHUNK;
     int grid = (int)std::min<int64_t>((nchunks + nwarps - 1) / nwarps, (int64_t)c->nsm * 4);

@@ -124,4 +124,25 @@ struct PmLinear2 {
     }
 };
 
+// (var1 = Resp0 exp(k T), var2 = 2 Resp0 exp(k T)): the two-target form of BASELINE config 5 (the Expo model of
+// projects/ExpoHybrid/ExpoHybridEstim.jl:69-85 with a second target that is twice the first, the same
+// construction as test/test_compute_loss.jl:209-211 uses for the linear model)
+struct PmExpo2 {
+    static constexpr int ID = PM_EXPO2, NPS = 2, NF = 1, NT = 2;
+    __device__ __forceinline__ static void fwd(const float* p, const float* f, const PmCtx& cx, float* y, float* sv)
+    {
+        float ex = exp2_mul_hilo(p[1] * f[0], 1.4426950216f, 1.9259630e-8f);
+        y[0] = p[0] * ex;
+        y[1] = 2.f * y[0];
+        sv[0] = ex;
+    }
+    __device__ __forceinline__ static void bwd(const float* p, const float* f, const PmCtx& cx, const float* y,
+                                               const float* sv, const float* gy, float* gp)
+    {
+        const float g = fmaf(2.f, gy[1], gy[0]);
+        gp[0] = g * sv[0];
+        gp[1] = g * y[0] * f[0];
+    }
+};
+
 }  // namespace eh

@@ -1,0 +1,410 @@
+// eh_wide.cu -- host side of the wide-hidden-layer path: TMA descriptors, GEMM launches, self-test entry.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/easyhybrid_cuda.h"
+#include "eh_wide.h"
+#include "eh_wide_gemm.cuh"
+#include "eh_wide_kernels.cuh"
+
+namespace eh {
+namespace wide {
+
+namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+}  // namespace
+
+// 2-D bf16 tensor map: `inner` contiguous elements per row, `rows` rows of `pitch_elems`; box = 64 x box_rows,
+// 128-byte swizzle (the shared-memory layout tcgen05 descriptors expect)
+bool make_map_bf16(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t rows, uint64_t pitch_elems, uint32_t box_rows)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {inner, rows};
+    cuuint64_t strides[1] = {pitch_elems * 2};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+cudaError_t gemm_prepare()
+{
+    static bool done = false;
+    if (done) return cudaSuccess;
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(k_wide_gemm<GEMM_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_wide_gemm<GEMM_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_wide_gemm<GEMM_WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM)) != cudaSuccess) return e;
+    done = true;
+    return cudaSuccess;
+}
+
+// out = act(A W^T + bias): A [M x K] bf16, W [N x K] bf16 (K contiguous in both)
+cudaError_t gemm_fwd(const CUtensorMap& tmA, const CUtensorMap& tmW, int M, int N, int K, const float* bias, int act,
+                     __nv_bfloat16* out, cudaStream_t st)
+{
+    GemmArgs g{};
+    g.M = M; g.N = N; g.K = K; g.ksplits = 1; g.act = act; g.bias = bias; g.out16 = out;
+    k_wide_gemm<GEMM_FWD><<<dim3(M / BM, N / BN, 1), GEMM_THREADS, GEMM_SMEM, st>>>(tmA, tmW, g);
+    return cudaGetLastError();
+}
+// out = (D Wt^T) .* act'(aux): D [M x K] bf16, Wt [N x K] bf16, aux [M x N] bf16
+cudaError_t gemm_bwd(const CUtensorMap& tmD, const CUtensorMap& tmWt, int M, int N, int K, const __nv_bfloat16* aux, int act,
+                     __nv_bfloat16* out, cudaStream_t st)
+{
+    GemmArgs g{};
+    g.M = M; g.N = N; g.K = K; g.ksplits = 1; g.act = act; g.aux = aux; g.out16 = out;
+    k_wide_gemm<GEMM_BWD><<<dim3(M / BM, N / BN, 1), GEMM_THREADS, GEMM_SMEM, st>>>(tmD, tmWt, g);
+    return cudaGetLastError();
+}
+// partial[z] = D[rows z]^T A[rows z]: D [Kall x M] bf16, A [Kall x N] bf16 (batch rows), ksplits slices of Kall
+cudaError_t gemm_wgrad(const CUtensorMap& tmD, const CUtensorMap& tmA, int M, int N, int Kall, int ksplits, float* partial,
+                       cudaStream_t st)
+{
+    GemmArgs g{};
+    g.M = M; g.N = N; g.K = Kall / ksplits; g.ksplits = ksplits; g.out32 = partial;
+    k_wide_gemm<GEMM_WGRAD><<<dim3(M / BM, N / BN, ksplits), GEMM_THREADS, GEMM_SMEM, st>>>(tmD, tmA, g);
+    return cudaGetLastError();
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// WideNet
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+typedef void (*HeadKernel)(const HeadArgs);
+struct HeadEntry { int pm, nout, scale, hch; HeadKernel fn; };
+#define EH_HEAD(PMF, NOUT, SCALE, HCH) {PMF::ID, NOUT, SCALE, HCH, k_wide_head<HeadCfg<PMF, NOUT, (SCALE != 0)>, HCH>},
+#define EH_HEAD_PM(PMF) EH_HEAD(PMF, 1, 0, 1) EH_HEAD(PMF, 1, 1, 1) EH_HEAD(PMF, 2, 0, 1) EH_HEAD(PMF, 2, 1, 1) \
+                        EH_HEAD(PMF, 1, 0, 2) EH_HEAD(PMF, 1, 1, 2) EH_HEAD(PMF, 2, 0, 2) EH_HEAD(PMF, 2, 1, 2)
+const HeadEntry g_heads[] = {EH_HEAD_PM(PmRbQ10) EH_HEAD_PM(PmExpo) EH_HEAD_PM(PmLinear) EH_HEAD_PM(PmLinear2) EH_HEAD_PM(PmExpo2)};
+
+HeadKernel find_head(int pm, int nout, int scale, int hch)
+{
+    for (const HeadEntry& e : g_heads)
+        if (e.pm == pm && e.nout == nout && e.scale == (scale ? 1 : 0) && e.hch == hch) return e.fn;
+    return nullptr;
+}
+
+WideDims dims_of(const WideModel& m)
+{
+    WideDims d{};
+    d.P = m.P; d.H = m.H; d.NH = m.NH; d.NOUT = m.NOUT; d.R4 = m.R4; d.nflat = m.nflat; d.ntheta = m.ntheta;
+    for (int i = 0; i < 8; i++) { d.w_off[i] = m.w_off[i]; d.b_off[i] = m.b_off[i]; }
+    return d;
+}
+}  // namespace
+
+#define WN(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e__ = (call);                                                                      \
+        if (e__ != cudaSuccess) {                                                                      \
+            snprintf(err_, sizeof err_, "%s: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return e__;                                                                                \
+        }                                                                                              \
+    } while (0)
+
+bool WideNet::supported(int P, int H, int NH, int NOUT, int act, int pm)
+{
+    if (P < 1 || P > 4 || NH < 2 || NH > 6 || NOUT < 1 || NOUT > 2) return false;
+    if (H != 256 && H != 512) return false;
+    if (act != ACT_TANH && act != ACT_SIGMOID && act != ACT_RELU && act != ACT_IDENTITY) return false;
+    return find_head(pm, NOUT, 0, H / 256) != nullptr;
+}
+
+WideNet* WideNet::create(const WideModel& m, char* err, size_t errlen)
+{
+    WideNet* w = new WideNet();
+    w->m_ = m;
+    auto bail = [&](const char* what, cudaError_t e) -> WideNet* {
+        snprintf(err, errlen, "wide path: %s: %s", what, cudaGetErrorString(e));
+        delete w;
+        return nullptr;
+    };
+    cudaError_t e = gemm_prepare();
+    if (e != cudaSuccess) return bail("gemm_prepare", e);
+    HeadKernel hk = find_head(m.pm, m.NOUT, m.scale, m.H / 256);
+    if (!hk) { snprintf(err, errlen, "wide path: no head kernel for this process model / shape"); delete w; return nullptr; }
+    const int head_smem = 8 * (m.NOUT + 1) * m.H * (int)sizeof(float);
+    e = cudaFuncSetAttribute((const void*)hk, cudaFuncAttributeMaxDynamicSharedMemorySize, head_smem);
+    if (e != cudaSuccess) return bail("head smem", e);
+    const size_t HH = (size_t)m.H * m.H;
+    for (int l = 2; l <= m.NH; l++) {
+        if ((e = cudaMalloc(&w->Wf_[l - 1], HH * 2)) != cudaSuccess) return bail("cudaMalloc", e);
+        if ((e = cudaMalloc(&w->Wb_[l - 1], HH * 2)) != cudaSuccess) return bail("cudaMalloc", e);
+        if (!make_map_bf16(&w->tmWf_[l - 1], w->Wf_[l - 1], m.H, m.H, m.H, BN) ||
+            !make_map_bf16(&w->tmWb_[l - 1], w->Wb_[l - 1], m.H, m.H, m.H, BN)) {
+            snprintf(err, errlen, "wide path: cuTensorMapEncodeTiled failed for a weight image");
+            delete w;
+            return nullptr;
+        }
+    }
+    w->n_head_ = 2 * m.nsm;
+    if ((e = cudaMalloc(&w->head_partial_, (size_t)w->n_head_ * head_npart(m.H, m.NOUT) * 4)) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc(&w->stats_, 16 * 4)) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc(&w->skip_, 4)) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc(&w->evalpart_, (size_t)w->n_head_ * 4 * 8 * sizeof(double))) != cudaSuccess) return bail("cudaMalloc", e);
+    cudaMemset(w->skip_, 0, 4);
+    return w;
+}
+
+WideNet::~WideNet()
+{
+    for (int i = 0; i < 8; i++) {
+        if (A_[i]) cudaFree(A_[i]);
+        if (Wf_[i]) cudaFree(Wf_[i]);
+        if (Wb_[i]) cudaFree(Wb_[i]);
+        if (colsum_[i]) cudaFree(colsum_[i]);
+    }
+    void* ps[] = {xb_, D_[0], D_[1], partial_, head_partial_, stats_, skip_, evalpart_};
+    for (void* p : ps)
+        if (p) cudaFree(p);
+}
+
+// activation / delta buffers and their tensor maps for batches of B rows
+cudaError_t WideNet::ensure(int B)
+{
+    const int H = m_.H;
+    if (B > cap_) {
+        for (int i = 0; i < 8; i++) { if (A_[i]) cudaFree(A_[i]); A_[i] = nullptr; if (colsum_[i]) cudaFree(colsum_[i]); colsum_[i] = nullptr; }
+        for (int i = 0; i < 2; i++) { if (D_[i]) cudaFree(D_[i]); D_[i] = nullptr; }
+        if (xb_) cudaFree(xb_);
+        if (partial_) cudaFree(partial_);
+        xb_ = nullptr; partial_ = nullptr; cap_ = 0; mapB_ = 0;
+        WN(cudaMalloc(&xb_, (size_t)B * m_.R4 * 4));
+        for (int l = 1; l <= m_.NH; l++) WN(cudaMalloc(&A_[l - 1], (size_t)B * H * 2));
+        for (int i = 0; i < 2; i++) WN(cudaMalloc(&D_[i], (size_t)B * H * 2));
+        WN(cudaMalloc(&partial_, (size_t)16 * H * H * 4));
+        const int slabs = (B + 511) / 512;
+        for (int l = 1; l < m_.NH; l++) WN(cudaMalloc(&colsum_[l - 1], (size_t)slabs * (1 + (l == 1 ? m_.P : 0)) * H * 4));
+        cap_ = B;
+    }
+    if (B != mapB_) {
+        bool ok = true;
+        for (int l = 1; l <= m_.NH; l++) {
+            ok &= make_map_bf16(&tmA_k_[l - 1], A_[l - 1], H, B, H, BM);
+            ok &= make_map_bf16(&tmA_mn_[l - 1], A_[l - 1], H, B, H, BK);
+        }
+        for (int i = 0; i < 2; i++) {
+            ok &= make_map_bf16(&tmD_k_[i], D_[i], H, B, H, BM);
+            ok &= make_map_bf16(&tmD_mn_[i], D_[i], H, B, H, BK);
+        }
+        if (!ok) { snprintf(err_, sizeof err_, "cuTensorMapEncodeTiled failed"); return cudaErrorUnknown; }
+        mapB_ = B;
+        n_slab_ = (B + 511) / 512;
+        ksplit_ = 1;
+        for (int s : {16, 8, 4, 2})
+            if (B % (s * BK) == 0) { ksplit_ = s; break; }
+    }
+    return cudaSuccess;
+}
+
+cudaError_t WideNet::refresh_images(float* pblock, float* m, float* v, void* ost, cudaStream_t st)
+{
+    WUpdArgs u{};
+    u.d = dims_of(m_);
+    u.theta = pblock; u.m = m; u.v = v; u.ost = reinterpret_cast<OptState*>(ost);
+    u.skip = skip_;
+    for (int l = 2; l <= m_.NH; l++) { u.Wf[l - 1] = Wf_[l - 1]; u.Wb[l - 1] = Wb_[l - 1]; }
+    u.apply = 0;
+    k_wide_update<<<(m_.nflat + 255) / 256, 256, 0, st>>>(u);
+    WN(cudaGetLastError());
+    return cudaSuccess;
+}
+
+cudaError_t WideNet::forward(const float* rec, const int* idx, long long rec_base, long long nrec, int B, const float* bscal,
+                             const float* pblock, cudaStream_t st)
+{
+    const int H = m_.H;
+    const WideDims d = dims_of(m_);
+    k_wide_gather<<<(B + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float4*>(rec), idx, rec_base, nrec, B, m_.R4 / 4,
+                                                   reinterpret_cast<float4*>(xb_));
+    WN(cudaGetLastError());
+    const long long nt = (long long)B * (H / 8);
+    k_wide_first<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(xb_, pblock, bscal, m_.use_bn, d, B, m_.act, A_[0]);
+    WN(cudaGetLastError());
+    for (int l = 2; l <= m_.NH; l++)
+        WN(gemm_fwd(tmA_k_[l - 2], tmWf_[l - 1], B, H, H, pblock + m_.b_off[l - 1], m_.act, A_[l - 1], st));
+    return cudaSuccess;
+}
+
+cudaError_t WideNet::step(const float* rec, const int* idx, long long rec_base, int B, const float* bscal, float* pblock, float* m,
+                          float* v, void* ost, float* grad, float* loss_out, int apply, cudaStream_t st)
+{
+    const int H = m_.H, NH = m_.NH;
+    WN(ensure(B));
+    WN(forward(rec, idx, rec_base, 1ll << 62, B, bscal, pblock, st));
+    const WideDims d = dims_of(m_);
+    HeadKernel hk = find_head(m_.pm, m_.NOUT, m_.scale, H / 256);
+    HeadArgs ha{};
+    ha.A = A_[NH - 1]; ha.xb = xb_; ha.pblock = pblock; ha.bscal = bscal; ha.D = D_[NH & 1]; ha.partial = head_partial_;
+    ha.d = d; ha.B = B; ha.Bvalid = B; ha.act = m_.act; ha.train = 1;
+    for (int t = 0; t < 4; t++) ha.loss_kind[t] = m_.loss_kind[t];
+    for (int s = 0; s < 8; s++) { ha.slot[s].role = m_.slot[s].role; ha.slot[s].idx = m_.slot[s].idx; ha.slot[s].lo = m_.slot[s].lo; ha.slot[s].span = m_.slot[s].span; ha.slot[s].fixedv = m_.slot[s].fixedv; }
+    for (int i = 0; i < 4; i++) ha.pmc[i] = m_.pmc[i];
+    const int head_smem = 8 * (m_.NOUT + 1) * H * (int)sizeof(float);
+    hk<<<n_head_, 256, head_smem, st>>>(ha);
+    WN(cudaGetLastError());
+    for (int l = NH; l >= 2; l--) {
+        const int cur = l & 1, nxt = (l - 1) & 1;
+        WN(gemm_wgrad(tmD_mn_[cur], tmA_mn_[l - 2], H, H, B, ksplit_, partial_, st));
+        k_wide_wreduce<<<dim3(H / 32, H / 32), 256, 0, st>>>(partial_, ksplit_, H, grad + m_.w_off[l - 1]);
+        WN(cudaGetLastError());
+        WN(gemm_bwd(tmD_k_[cur], tmWb_[l - 1], B, H, H, A_[l - 2], m_.act, D_[nxt], st));
+        k_wide_colsum<<<n_slab_, H / 2, 0, st>>>(D_[nxt], xb_, bscal, m_.use_bn, B, H, m_.R4, (l - 1 == 1) ? m_.P : 0, 512,
+                                                 colsum_[l - 2]);
+        WN(cudaGetLastError());
+    }
+    FinArgs fa{};
+    fa.d = d; fa.head_partial = head_partial_; fa.n_head = n_head_; fa.n_slab = n_slab_;
+    for (int l = 1; l < NH; l++) fa.colsum[l - 1] = colsum_[l - 1];
+    fa.bscal = bscal; fa.theta = pblock; fa.grad = grad; fa.stats = stats_; fa.loss_out = loss_out;
+    fa.T = m_.T; fa.agg_mean = m_.agg_mean;
+    for (int t = 0; t < 4; t++) fa.loss_kind[t] = m_.loss_kind[t];
+    for (int s = 0; s < 8; s++) fa.slot[s] = ha.slot[s];
+    fa.slot_of_flat = m_.d_slot_of_flat; fa.skip_out = skip_;
+    k_wide_gradfin<<<(m_.nflat + 255) / 256, 256, 0, st>>>(fa);
+    WN(cudaGetLastError());
+    if (apply) {
+        WUpdArgs u{};
+        u.d = d; u.theta = pblock; u.m = m; u.v = v; u.ost = reinterpret_cast<OptState*>(ost); u.grad = grad; u.skip = skip_;
+        u.stats = stats_; u.bscal = bscal; u.T = m_.T;
+        for (int t = 0; t < 4; t++) u.loss_kind[t] = m_.loss_kind[t];
+        u.opt_kind = m_.opt_kind; u.adamw_coupled = m_.adamw_coupled;
+        u.eta = m_.eta; u.beta1 = m_.beta1; u.beta2 = m_.beta2; u.eps = m_.eps; u.lambda = m_.lambda;
+        for (int l = 2; l <= NH; l++) { u.Wf[l - 1] = Wf_[l - 1]; u.Wb[l - 1] = Wb_[l - 1]; }
+        u.apply = 1;
+        k_wide_update<<<(m_.nflat + 255) / 256, 256, 0, st>>>(u);
+        WN(cudaGetLastError());
+        k_wide_advance<<<1, 1, 0, st>>>(reinterpret_cast<OptState*>(ost), skip_, m_.beta1, m_.beta2, 1);
+        WN(cudaGetLastError());
+    }
+    return cudaSuccess;
+}
+
+__global__ void k_wide_evalsum(const double* part, int n, int cnt, double* acc)
+{
+    const int q = threadIdx.x;
+    if (q >= cnt) return;
+    double s = 0.0;
+    for (int g = 0; g < n; g++) s += part[(size_t)g * cnt + q];
+    acc[q] += s;
+}
+
+cudaError_t WideNet::eval_rows(const float* rec, long long nrec, long long row0, int Bvalid, const float* bscal, const float* pblock,
+                               float* yhat, float* parout, long long ldy, double* evalstat_dev, const float* shift_y,
+                               cudaStream_t st)
+{
+    const int H = m_.H, NH = m_.NH;
+    const int B = (Bvalid + 127) / 128 * 128;
+    WN(ensure(B));
+    WN(forward(rec, nullptr, row0, nrec, B, bscal, pblock, st));
+    HeadKernel hk = find_head(m_.pm, m_.NOUT, m_.scale, H / 256);
+    HeadArgs ha{};
+    ha.A = A_[NH - 1]; ha.xb = xb_; ha.pblock = pblock; ha.bscal = bscal; ha.D = nullptr; ha.partial = nullptr;
+    ha.yhat = yhat; ha.parout = parout; ha.ldy = ldy; ha.row0 = row0; ha.evalstat = evalstat_dev ? evalpart_ : nullptr;
+    for (int t = 0; t < 4; t++) { ha.shift_y[t] = shift_y[t]; ha.loss_kind[t] = m_.loss_kind[t]; }
+    ha.d = dims_of(m_); ha.B = B; ha.Bvalid = Bvalid; ha.act = m_.act; ha.train = 0;
+    for (int s = 0; s < 8; s++) { ha.slot[s].role = m_.slot[s].role; ha.slot[s].idx = m_.slot[s].idx; ha.slot[s].lo = m_.slot[s].lo; ha.slot[s].span = m_.slot[s].span; ha.slot[s].fixedv = m_.slot[s].fixedv; }
+    for (int i = 0; i < 4; i++) ha.pmc[i] = m_.pmc[i];
+    const int head_smem = 8 * (m_.NOUT + 1) * H * (int)sizeof(float);
+    hk<<<n_head_, 256, head_smem, st>>>(ha);
+    WN(cudaGetLastError());
+    if (evalstat_dev) {
+        k_wide_evalsum<<<1, 64, 0, st>>>(evalpart_, n_head_, m_.T * 8, evalstat_dev);
+        WN(cudaGetLastError());
+    }
+    return cudaSuccess;
+}
+
+}  // namespace wide
+}  // namespace eh
+
+using namespace eh::wide;
+
+#define WCK(call)                                                                             \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            fprintf(stderr, "eh_wide: %s failed: %s\n", #call, cudaGetErrorString(e__));      \
+            return EH_ECUDA;                                                                  \
+        }                                                                                     \
+    } while (0)
+
+extern "C" eh_status eh_selftest_wide_gemm(int32_t mode, int32_t M, int32_t N, int32_t K, int32_t ksplits, int32_t act,
+                                           const uint16_t* A, const uint16_t* B, const float* bias, const uint16_t* aux,
+                                           void* out, int32_t device, float* ms_out)
+{
+    if (!A || !B || !out || mode < 0 || mode > 2) return EH_EINVAL;
+    if (M % BM || N % BN || ksplits < 1) return EH_EINVAL;
+    WCK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    WCK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return EH_ECUDA;
+    WCK(gemm_prepare());
+    const bool wg = mode == GEMM_WGRAD;
+    if (wg ? (K % (ksplits * BK) != 0) : (K % BK != 0)) return EH_EINVAL;
+    // FWD/BWD: A [M x K], B [N x K].  WGRAD: A = deltas [K x M], B = activations [K x N].
+    const size_t nA = (size_t)M * K, nB = (size_t)N * K;
+    __nv_bfloat16 *dA = nullptr, *dB = nullptr, *dAux = nullptr, *dO16 = nullptr;
+    float *dBias = nullptr, *dO32 = nullptr;
+    WCK(cudaMalloc(&dA, nA * 2));
+    WCK(cudaMalloc(&dB, nB * 2));
+    WCK(cudaMemcpy(dA, A, nA * 2, cudaMemcpyHostToDevice));
+    WCK(cudaMemcpy(dB, B, nB * 2, cudaMemcpyHostToDevice));
+    if (mode == GEMM_FWD) {
+        WCK(cudaMalloc(&dBias, (size_t)N * 4));
+        WCK(cudaMemcpy(dBias, bias, (size_t)N * 4, cudaMemcpyHostToDevice));
+    }
+    if (mode == GEMM_BWD) {
+        WCK(cudaMalloc(&dAux, (size_t)M * N * 2));
+        WCK(cudaMemcpy(dAux, aux, (size_t)M * N * 2, cudaMemcpyHostToDevice));
+    }
+    if (wg) WCK(cudaMalloc(&dO32, (size_t)ksplits * M * N * 4));
+    else WCK(cudaMalloc(&dO16, (size_t)M * N * 2));
+    CUtensorMap tmA, tmB;
+    bool ok;
+    if (!wg) ok = make_map_bf16(&tmA, dA, K, M, K, BM) && make_map_bf16(&tmB, dB, K, N, K, BN);
+    else ok = make_map_bf16(&tmA, dA, M, K, M, BK) && make_map_bf16(&tmB, dB, N, K, N, BK);
+    if (!ok) return EH_ECUDA;
+    cudaEvent_t e0, e1;
+    WCK(cudaEventCreate(&e0));
+    WCK(cudaEventCreate(&e1));
+    const int reps = ms_out ? 5 : 1;
+    for (int r = 0; r < reps; r++) {
+        if (r == reps - 1) WCK(cudaEventRecord(e0));
+        if (mode == GEMM_FWD) WCK(gemm_fwd(tmA, tmB, M, N, K, dBias, act, dO16, 0));
+        else if (mode == GEMM_BWD) WCK(gemm_bwd(tmA, tmB, M, N, K, dAux, act, dO16, 0));
+        else WCK(gemm_wgrad(tmA, tmB, M, N, K, ksplits, dO32, 0));
+        if (r == reps - 1) WCK(cudaEventRecord(e1));
+    }
+    WCK(cudaDeviceSynchronize());
+    if (ms_out) WCK(cudaEventElapsedTime(ms_out, e0, e1));
+    if (wg) WCK(cudaMemcpy(out, dO32, (size_t)ksplits * M * N * 4, cudaMemcpyDeviceToHost));
+    else WCK(cudaMemcpy(out, dO16, (size_t)M * N * 2, cudaMemcpyDeviceToHost));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(dA); cudaFree(dB); cudaFree(dAux); cudaFree(dO16); cudaFree(dBias); cudaFree(dO32);
+    return EH_OK;
+}

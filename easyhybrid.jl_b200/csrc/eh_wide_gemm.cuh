@@ -1,0 +1,311 @@
+// eh_wide_gemm.cuh -- bf16 tcgen05 GEMMs of the wide-hidden-layer path (sm_100a only).
+//
+// For hidden widths of 256 and more the Dense chain of a hybrid model (prepare_hidden_chain,
+// src/models/NNModels.jl:220-231) really is a dense contraction: per optimiser step and hidden layer
+//   forward        A_l      = act(A_{l-1} W_l^T + b_l)            [B x H] = [B x H] [H x H]
+//   backward data  D_{l-1}  = (D_l W_l) .* act'(A_{l-1})          [B x H] = [B x H] [H x H]
+//   weight grad    dW_l     = D_l^T A_{l-1}                       [H x H] = [H x B] [B x H]
+// (the Zygote pullback of the chain).  One kernel template serves the three:
+//   * operands travel HBM -> shared memory with TMA (cp.async.bulk.tensor, 128-byte swizzle) through a
+//     4-stage mbarrier pipeline filled by one producer thread;
+//   * one elected thread issues tcgen05.mma (cta_group::1, kind::f16, 128 x 256 x 16, bf16 in, fp32
+//     accumulate); the 128 x 256 accumulator tile lives in tensor memory (256 columns);
+//   * four epilogue warps read it back with tcgen05.ld (32 lanes x 32 columns per instruction) and fuse
+//     the layer's elementwise tail: bias + activation -> bf16, or .* act'(a) -> bf16, or the fp32
+//     split-K partial of a weight gradient (summed later in a fixed order: no atomics).
+// The weight-gradient contraction runs over the batch, which is the slow dimension of both of its
+// operands: they are fetched as MN-major tiles (64 columns x 64 batch rows per TMA box), so neither
+// activations nor deltas are ever transposed in memory.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include "eh_device.cuh"
+
+namespace eh {
+namespace wide {
+
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4, UMMA_K = 16;
+constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
+constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int GEMM_THREADS = 192;            // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..5: epilogue
+constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int TMEM_COLS = 256;
+
+enum : int { GEMM_FWD = 0, GEMM_BWD = 1, GEMM_WGRAD = 2 };
+
+struct GemmArgs {
+    int M, N, K;             // C is M x N; K = contraction length handled by ONE split
+    int ksplits;             // WGRAD: gridDim.z; split z covers K rows [z*K, (z+1)*K)
+    int act;                 // ACT_* of the hidden layers
+    const float* bias;       // FWD: [N]
+    const __nv_bfloat16* aux;  // BWD: A_{l-1} [M x N] (activation whose derivative multiplies the tile)
+    __nv_bfloat16* out16;    // FWD / BWD: [M x N] row-major
+    float* out32;            // WGRAD: [ksplits][M x N] row-major partials
+};
+
+// ---- thin PTX wrappers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded wait: a broken pipeline must not hang the GPU (returns false after ~1 s)
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity)
+{
+    for (uint32_t spins = 0; spins < (1u << 24); spins++)
+        if (mbar_try_wait(bar, parity)) return true;
+    return false;
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map)
+{
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns of the accumulator -> 32 registers per thread
+__device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor (SWIZZLE_128B, sm_100 version 1).  K-major tiles: rows of 128 bytes,
+// 8-row swizzle atoms 1024 bytes apart (SBO), LBO unused.  MN-major tiles (TMA boxes of 64 columns x BK
+// rows): 8 K-rows per atom, atoms 1024 bytes apart along K (SBO), next 64 columns one box further (LBO).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+    return d;
+}
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n, int a_mn_major, int b_mn_major)
+{
+    return (1u << 4) /* D = f32 */ | (1u << 7) /* A = bf16 */ | (1u << 10) /* B = bf16 */ | ((uint32_t)a_mn_major << 15) |
+           ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ float tanh_fast(float z)
+{
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(z));
+    return y;
+}
+// hidden activations of the wide path: the result is rounded to bf16 (8 bits of mantissa) anyway, so one
+// MUFU.TANH (2^-11 relative) per element is as good as an exact evaluation and keeps the epilogue short
+__device__ __forceinline__ float act1(int act, float z)
+{
+    if (act == ACT_TANH) return tanh_fast(z);
+    if (act == ACT_SIGMOID) return fmaf(0.5f, tanh_fast(0.5f * z), 0.5f);
+    if (act == ACT_RELU) return fmaxf(z, 0.f);
+    return z;
+}
+// derivative from the stored output a
+__device__ __forceinline__ float dact1(int act, float a)
+{
+    if (act == ACT_TANH) return fmaf(-a, a, 1.f);
+    if (act == ACT_SIGMOID) return a * (1.f - a);
+    if (act == ACT_RELU) return a > 0.f ? 1.f : 0.f;
+    return 1.f;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi)
+{
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// grid: (M / BM, N / BN, ksplits).  FWD / BWD: tmA = [M x K] K-major (box 64 x 128), tmB = [N x K] K-major
+// (box 64 x 256).  WGRAD: tmA = deltas [Kall x M], tmB = activations [Kall x N], both MN-major (box 64 x 64).
+template <int MODE>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+k_wide_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // swizzle atoms need 1024-byte alignment
+    const uint32_t bar0 = base + STAGES * STAGE_BYTES;             // full[STAGES], empty[STAGES], tmem_full, tmem slot
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+    const uint32_t tmem_full_bar = bar0 + 8u * (2 * STAGES);
+    const uint32_t tmem_slot = bar0 + 8u * (2 * STAGES + 1);
+    uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 1));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int kbase = (MODE == GEMM_WGRAD) ? blockIdx.z * g.K : 0;
+    const int nkb = g.K / BK;
+    constexpr bool MN = (MODE == GEMM_WGRAD);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            for (int kb = 0; kb < nkb; kb++) {
+                const int s = kb % STAGES;
+                const uint32_t par = ((kb / STAGES) & 1) ^ 1;
+                if (!mbar_wait(empty_bar(s), par)) break;
+                const uint32_t sa = base + s * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+                mbar_expect_tx(full_bar(s), STAGE_BYTES);
+                const int k0 = kbase + kb * BK;
+                if (!MN) {
+                    tma_load_2d(sa, &tmA, k0, m0, full_bar(s));
+                    tma_load_2d(sb, &tmB, k0, n0, full_bar(s));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < BM / 64; j++) tma_load_2d(sa + j * (64 * BK * 2), &tmA, m0 + 64 * j, k0, full_bar(s));
+#pragma unroll
+                    for (int j = 0; j < BN / 64; j++) tma_load_2d(sb + j * (64 * BK * 2), &tmB, n0 + 64 * j, k0, full_bar(s));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, MN ? 1 : 0, MN ? 1 : 0);
+            constexpr uint32_t lbo = MN ? 64 * BK * 2 : 0;     // MN-major: next 64 columns = next TMA box
+            constexpr uint32_t sbo = 1024;                     // 8 rows (K-major) / 8 K-rows (MN-major) of 128 bytes
+            constexpr uint32_t kstep = MN ? UMMA_K * 128 : UMMA_K * 2;  // bytes per UMMA_K along the stage
+            bool ok = true;
+            for (int kb = 0; kb < nkb && ok; kb++) {
+                const int s = kb % STAGES;
+                ok = mbar_wait(full_bar(s), (kb / STAGES) & 1);
+                tc_fence_after();
+                const uint32_t sa = base + s * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; k++) {
+                    const uint64_t da = umma_desc(sa + k * kstep, lbo, sbo);
+                    const uint64_t db = umma_desc(sb + k * kstep, lbo, sbo);
+                    tc_mma_bf16(tmem_base, da, db, idesc, (kb | k) ? 1u : 0u);
+                }
+                tc_commit(empty_bar(s));   // frees the stage once these MMAs have read it
+            }
+            tc_commit(tmem_full_bar);      // accumulator complete
+        }
+    } else {
+        // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+        const int q = warp & 3;
+        const int row = m0 + q * 32 + lane;
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+            uint32_t r[32];
+            tc_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
+            const int col = n0 + c;
+            if (MODE == GEMM_WGRAD) {
+                float4* dst = reinterpret_cast<float4*>(g.out32 + ((size_t)blockIdx.z * g.M + row) * g.N + col);
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                         __uint_as_float(r[4 * j + 3]));
+            } else {
+                uint32_t o[16];
+                if (MODE == GEMM_FWD) {
+                    const float4* b4 = reinterpret_cast<const float4*>(g.bias + col);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const float4 b = __ldg(b4 + j);
+                        o[2 * j] = pack_bf16(act1(g.act, __uint_as_float(r[4 * j]) + b.x), act1(g.act, __uint_as_float(r[4 * j + 1]) + b.y));
+                        o[2 * j + 1] = pack_bf16(act1(g.act, __uint_as_float(r[4 * j + 2]) + b.z), act1(g.act, __uint_as_float(r[4 * j + 3]) + b.w));
+                    }
+                } else {
+                    const uint4* a4 = reinterpret_cast<const uint4*>(g.aux + (size_t)row * g.N + col);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const uint4 a = __ldg(a4 + j);
+                        const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            const __nv_bfloat162 ab = *reinterpret_cast<const __nv_bfloat162*>(&aw[e]);
+                            const float2 af = __bfloat1622float2(ab);
+                            o[4 * j + e] = pack_bf16(__uint_as_float(r[8 * j + 2 * e]) * dact1(g.act, af.x),
+                                                     __uint_as_float(r[8 * j + 2 * e + 1]) * dact1(g.act, af.y));
+                        }
+                    }
+                }
+                uint4* dst = reinterpret_cast<uint4*>(g.out16 + (size_t)row * g.N + col);
+#pragma unroll
+                for (int j = 0; j < 4; j++) dst[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    }
+}
+
+}  // namespace wide
+}  // namespace eh

@@ -1,0 +1,530 @@
+// eh_wide_kernels.cuh -- the non-GEMM kernels of the wide-hidden-layer training step (sm_100a).
+//
+// One optimiser step of a hybrid model whose Dense chain is  P -> H -> ... -> H -> NOUT  with H >= 256
+// (BASELINE config 5: 3 x 512) is a sequence of launches on one stream:
+//   k_wide_gather    batch records (AoS, gathered through the index stream) -> compact batch
+//   k_wide_first     layer 1 (fan-in P is tiny: elementwise)          A_1 = act(W_1 x + b_1)        bf16
+//   gemm_fwd  x(NH-1)  tcgen05                                          A_l = act(A_{l-1} W_l^T + b_l)  bf16
+//   k_wide_head      output layer (fan-out NOUT is tiny), parameter squashing, process model, masked loss
+//                    seeds, analytic backward into D_NH, gradient of the output layer and of phi
+//   per hidden layer l = NH .. 2:   gemm_wgrad (dW_l partials), gemm_bwd (D_{l-1}), k_wide_colsum (db)
+//   k_wide_wreduce   split-K partials -> flat gradient (fixed order)
+//   k_wide_gradfin   remaining gradient entries (W_1, biases, output layer, phi) and the loss value
+//   k_wide_update    optimiser over the flat vector, bf16 weight images for the next step
+// Replaces Lux.Training.single_train_step! (src/training/epoch.jl:20-26) for wide chains; formulas: SURVEY 10.2-10.5.
+#pragma once
+#include <cuda_bf16.h>
+#include "eh_chunk.cuh"
+#include "eh_wide_gemm.cuh"
+
+namespace eh {
+namespace wide {
+
+// partial vector written by one CTA of k_wide_head (floats): [NOUT][H] dWo, [NOUT] dbo(pad 4), [H] db_NH,
+// [MAXT] loss sums, [MAXPS] phi sums
+__host__ __device__ constexpr int head_off_dbo(int H, int NOUT) { return NOUT * H; }
+__host__ __device__ constexpr int head_off_dbh(int H, int NOUT) { return NOUT * H + 4; }
+__host__ __device__ constexpr int head_off_loss(int H, int NOUT) { return NOUT * H + 4 + H; }
+__host__ __device__ constexpr int head_off_phi(int H, int NOUT) { return head_off_loss(H, NOUT) + MAXT; }
+__host__ __device__ constexpr int head_npart(int H, int NOUT) { return head_off_phi(H, NOUT) + MAXPS; }
+
+struct WideDims {
+    int P, H, NH, NOUT, R4;      // chain shape; floats per record
+    int nflat, ntheta;
+    // flat offsets (reference ComponentArray order): W_l is out x in column-major, i.e. index o + i * out
+    int w_off[8], b_off[8];      // layer l (1-based) at [l-1]; l = NH+1 is the output layer
+};
+
+// ---- gather: rec[idx[b]] -> xb[b] ---------------------------------------------------------------------------
+// (rows past `nrec` -- padding of an evaluation chunk up to a multiple of 128 -- repeat the last record)
+__global__ void __launch_bounds__(256) k_wide_gather(const float4* rec, const int* idx, long long rec_base, long long nrec, int B,
+                                                     int R4q, float4* xb)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    long long i = idx ? (long long)idx[b] : rec_base + b;
+    if (i >= nrec) i = nrec - 1;
+    for (int q = 0; q < R4q; q++) xb[(size_t)b * R4q + q] = __ldg(rec + i * R4q + q);
+}
+
+__device__ __forceinline__ float act_bf16(int act, float z) { return act1(act, z); }
+__device__ __forceinline__ float dact_out(int act, float a) { return dact1(act, a); }
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) { return pack_bf16(lo, hi); }
+
+// ---- layer 1: A1[b][o] = act(b1[o] + sum_p xn[b][p] W1[o][p]); one thread = 8 consecutive o of one sample ----
+__global__ void __launch_bounds__(256) k_wide_first(const float* xb, const float* theta, const float* bscal, int use_bn,
+                                                    WideDims d, int B, int act, __nv_bfloat16* A1)
+{
+    const int per_row = d.H / 8;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)B * per_row) return;
+    const int b = (int)(t / per_row), o0 = (int)(t % per_row) * 8;
+    float z[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) z[j] = __ldg(theta + d.b_off[0] + o0 + j);
+    for (int p = 0; p < d.P; p++) {
+        float x = xb[(size_t)b * d.R4 + p];
+        if (use_bn) x = (x - bscal[BS_BN + 2 * p]) * bscal[BS_BN + 2 * p + 1];
+#pragma unroll
+        for (int j = 0; j < 8; j++) z[j] = fmaf(x, __ldg(theta + d.w_off[0] + o0 + j + p * d.H), z[j]);
+    }
+    uint4 o;
+    o.x = pack2(act_bf16(act, z[0]), act_bf16(act, z[1]));
+    o.y = pack2(act_bf16(act, z[2]), act_bf16(act, z[3]));
+    o.z = pack2(act_bf16(act, z[4]), act_bf16(act, z[5]));
+    o.w = pack2(act_bf16(act, z[6]), act_bf16(act, z[7]));
+    *reinterpret_cast<uint4*>(A1 + (size_t)b * d.H + o0) = o;
+}
+
+// the pieces of StepCfg that resolve_params / the process-model functors look at
+template <class PM_, int NOUT_, bool SCALE_>
+struct HeadCfg {
+    using PM = PM_;
+    static constexpr int NOUT = NOUT_, NPS = PM_::NPS, T = PM_::NT, F = PM_::NF;
+    static constexpr bool SCALE = SCALE_;
+};
+
+struct HeadArgs {
+    const __nv_bfloat16* A;    // [B x H] last hidden activation
+    const float* xb;           // [B x R4] compact batch records
+    const float* pblock;       // flat theta/phi + tail
+    const float* bscal;        // per-batch scalar row
+    __nv_bfloat16* D;          // out [B x H] delta of the last hidden layer
+    float* partial;            // out [gridDim.x][head_npart]
+    float* yhat;               // eval mode: nullable [T][ldy] predictions
+    float* parout;             // eval mode: nullable [NPS][ldy] neural parameter values
+    long long ldy, row0;       // eval mode: row offset of this batch inside yhat / parout
+    double* evalstat;          // eval mode: nullable [gridDim.x][T * 8] sufficient statistics (EVAL_NSTAT layout)
+    float shift_y[MAXT];
+    WideDims d;
+    int B, act, train;
+    int Bvalid;                // rows that really exist (eval chunks are padded to a multiple of 128)
+    int loss_kind[MAXT];
+    PSlot slot[MAXPS];
+    float pmc[4];
+};
+
+// ---- output layer + physics + loss seeds + backward into D_NH; one warp per sample row, 8 warps per CTA ----
+// H / 256 chunks of 8 consecutive features per lane (16-byte bf16 accesses).
+template <class HC, int HCH>
+__global__ void __launch_bounds__(256) k_wide_head(const HeadArgs a)
+{
+    using PM = typename HC::PM;
+    constexpr int NOUT = HC::NOUT, T = HC::T, F = HC::F, NPS = HC::NPS;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int H = a.d.H, P = a.d.P;
+    __shared__ float s_pms[MAXPS * PMS_PER_SLOT + MAXPS];
+    __shared__ float s_red[8][64];
+    if (threadIdx.x < MAXPS * PMS_PER_SLOT + MAXPS) s_pms[threadIdx.x] = a.pblock[a.d.nflat + threadIdx.x];
+    __syncthreads();
+    // s_pms: [0..8) uniform slot values, [8..40) derived scalars -- same order as the parameter block tail
+    PmCtx cx;
+    cx.pms = s_pms + MAXPS;
+    cx.c = a.pmc;
+    cx.uniform_mask = 0;
+#pragma unroll
+    for (int s = 0; s < MAXPS; s++)
+        if (s >= NPS || a.slot[s].role != ROLE_NEURAL) cx.uniform_mask |= 1u << s;
+
+    // output-layer weights of my features: Wo[o][i] at wo_off + o + i * NOUT
+    const int wo = a.d.w_off[a.d.NH], bo = a.d.b_off[a.d.NH];
+    float w[NOUT][HCH][8];
+#pragma unroll
+    for (int c = 0; c < HCH; c++)
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const int i = (c * 32 + lane) * 8 + e;
+#pragma unroll
+            for (int o = 0; o < NOUT; o++) w[o][c][e] = a.pblock[wo + o + i * NOUT];
+        }
+    float bout[NOUT];
+#pragma unroll
+    for (int o = 0; o < NOUT; o++) bout[o] = a.pblock[bo + o];
+
+    float gW[NOUT][HCH][8], gB[NOUT], gDb[HCH][8], lsum[MAXT], gphi[MAXPS];
+    double est[T][8];
+#pragma unroll
+    for (int o = 0; o < NOUT; o++) {
+        gB[o] = 0.f;
+#pragma unroll
+        for (int c = 0; c < HCH; c++)
+#pragma unroll
+            for (int e = 0; e < 8; e++) gW[o][c][e] = 0.f;
+    }
+#pragma unroll
+    for (int c = 0; c < HCH; c++)
+#pragma unroll
+        for (int e = 0; e < 8; e++) gDb[c][e] = 0.f;
+#pragma unroll
+    for (int t = 0; t < MAXT; t++) lsum[t] = 0.f;
+#pragma unroll
+    for (int q = 0; q < MAXPS; q++) gphi[q] = 0.f;
+#pragma unroll
+    for (int t = 0; t < T; t++)
+#pragma unroll
+        for (int q = 0; q < 8; q++) est[t][q] = 0.0;
+
+    for (int b = blockIdx.x * 8 + warp; b < a.Bvalid; b += gridDim.x * 8) {
+        float av[HCH][8];
+        float zo[NOUT];
+#pragma unroll
+        for (int o = 0; o < NOUT; o++) zo[o] = 0.f;
+#pragma unroll
+        for (int c = 0; c < HCH; c++) {
+            const uint4 raw = *reinterpret_cast<const uint4*>(a.A + (size_t)b * H + (c * 32 + lane) * 8);
+            const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rw[e]));
+                av[c][2 * e] = f.x;
+                av[c][2 * e + 1] = f.y;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; e++)
+#pragma unroll
+                for (int o = 0; o < NOUT; o++) zo[o] = fmaf(av[c][e], w[o][c][e], zo[o]);
+        }
+#pragma unroll
+        for (int o = 0; o < NOUT; o++) zo[o] = warp_sum(zo[o]) + bout[o];
+
+        // every lane evaluates the (cheap) per-sample scalar part redundantly: no broadcast needed afterwards
+        float f[F > 0 ? F : 1], y[T], pv[NPS], sg[NPS], yh[T], sv[4], gy[T], gp[NPS], dz[NOUT];
+        const float* r = a.xb + (size_t)b * a.d.R4;
+#pragma unroll
+        for (int k = 0; k < F; k++) f[k] = r[P + k];
+#pragma unroll
+        for (int k = 0; k < T; k++) y[k] = r[P + F + k];
+        resolve_params<HC>(a.slot, s_pms, zo, pv, sg);
+        PM::fwd(pv, f, cx, yh, sv);
+        if (!a.train) {
+            if (lane == 0) {
+#pragma unroll
+                for (int t = 0; t < T; t++) {
+                    if (a.yhat) a.yhat[(size_t)t * a.ldy + a.row0 + b] = yh[t];
+                    if (y[t] == y[t]) {
+                        const double yy = (double)y[t] - a.shift_y[t], hh = (double)yh[t] - a.shift_y[t], rr = (double)yh[t] - y[t];
+                        est[t][0] += 1.0; est[t][1] += yy; est[t][2] += hh; est[t][3] += yy * yy;
+                        est[t][4] += hh * hh; est[t][5] += yy * hh; est[t][6] += rr * rr; est[t][7] += fabs(rr);
+                    }
+                }
+                if (a.parout) {
+#pragma unroll
+                    for (int q = 0; q < NPS; q++)
+                        if (a.slot[q].role == ROLE_NEURAL) a.parout[(size_t)q * a.ldy + a.row0 + b] = pv[q];
+                }
+            }
+            continue;
+        }
+#pragma unroll
+        for (int t = 0; t < T; t++) {
+            const bool m = (y[t] == y[t]);   // valid_mask = !isnan(y), src/training/train.jl:221-232
+            const float rr = m ? yh[t] - y[t] : 0.f;
+            const float c = a.bscal[BS_C + t];
+            if (a.loss_kind[t] == LOSS_MAE) {
+                lsum[t] += fabsf(rr);
+                gy[t] = rr > 0.f ? c : (rr < 0.f ? -c : 0.f);
+            } else {
+                lsum[t] = fmaf(rr, rr, lsum[t]);
+                gy[t] = 2.f * c * rr;
+            }
+        }
+        PM::bwd(pv, f, cx, yh, sv, gy, gp);
+#pragma unroll
+        for (int o = 0; o < NOUT; o++) dz[o] = 0.f;
+#pragma unroll
+        for (int q = 0; q < NPS; q++) {
+            const PSlot sl = a.slot[q];
+            if (sl.role == ROLE_NEURAL) {
+                float g = gp[q];
+                if (HC::SCALE) g *= sl.span * sg[q] * (1.f - sg[q]);
+#pragma unroll
+                for (int o = 0; o < NOUT; o++)
+                    if (sl.idx == o) dz[o] += g;
+            } else if (sl.role == ROLE_GLOBAL) {
+                gphi[q] += gp[q];
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < NOUT; o++) gB[o] += dz[o];
+        // delta of the last hidden layer for my features, its column sums, and the output-layer gradient
+#pragma unroll
+        for (int c = 0; c < HCH; c++) {
+            float dv[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                float s = 0.f;
+#pragma unroll
+                for (int o = 0; o < NOUT; o++) {
+                    s = fmaf(dz[o], w[o][c][e], s);
+                    gW[o][c][e] = fmaf(dz[o], av[c][e], gW[o][c][e]);
+                }
+                // round first: db must be the column sum of the very deltas the weight-gradient GEMM reads
+                dv[e] = __bfloat162float(__float2bfloat16_rn(s * dact_out(a.act, av[c][e])));
+                gDb[c][e] += dv[e];
+            }
+            uint4 o4;
+            o4.x = pack2(dv[0], dv[1]); o4.y = pack2(dv[2], dv[3]); o4.z = pack2(dv[4], dv[5]); o4.w = pack2(dv[6], dv[7]);
+            *reinterpret_cast<uint4*>(a.D + (size_t)b * H + (c * 32 + lane) * 8) = o4;
+        }
+    }
+
+    if (!a.train) {
+        if (a.evalstat) {
+            __shared__ double s_e[8][MAXT * 8];
+            if (lane == 0)
+                for (int t = 0; t < T; t++)
+                    for (int q = 0; q < 8; q++) s_e[warp][t * 8 + q] = est[t][q];
+            __syncthreads();
+            if (threadIdx.x < T * 8) {
+                double s = 0.0;
+                for (int wv = 0; wv < 8; wv++) s += s_e[wv][threadIdx.x];
+                a.evalstat[(size_t)blockIdx.x * (T * 8) + threadIdx.x] = s;
+            }
+        }
+        return;
+    }
+    // CTA reduction in a fixed order: per-feature vectors through shared memory, warp by warp
+    float* out = a.partial + (size_t)blockIdx.x * head_npart(H, NOUT);
+    extern __shared__ float s_vec[];   // [8][(NOUT + 1) * H]
+    const int VS = (NOUT + 1) * H;
+#pragma unroll
+    for (int c = 0; c < HCH; c++)
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const int i = (c * 32 + lane) * 8 + e;
+#pragma unroll
+            for (int o = 0; o < NOUT; o++) s_vec[warp * VS + o * H + i] = gW[o][c][e];
+            s_vec[warp * VS + NOUT * H + i] = gDb[c][e];
+        }
+    if (lane == 0) {
+#pragma unroll
+        for (int o = 0; o < NOUT; o++) s_red[warp][o] = gB[o];
+#pragma unroll
+        for (int t = 0; t < MAXT; t++) s_red[warp][4 + t] = lsum[t];
+#pragma unroll
+        for (int q = 0; q < MAXPS; q++) s_red[warp][8 + q] = gphi[q];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < VS; i += blockDim.x) {
+        float s = 0.f;
+        for (int wv = 0; wv < 8; wv++) s += s_vec[wv * VS + i];
+        // s_vec order: [NOUT][H] dWo then [H] db_NH ; partial order: dWo, dbo(4), db_NH
+        out[i < NOUT * H ? i : i + 4] = s;
+    }
+    if (threadIdx.x < 4 + MAXT + MAXPS) {
+        float s = 0.f;
+        for (int wv = 0; wv < 8; wv++) s += s_red[wv][threadIdx.x];
+        const int q = threadIdx.x;
+        if (q < 4) out[head_off_dbo(H, NOUT) + q] = q < NOUT ? s : 0.f;
+        else out[head_off_loss(H, NOUT) + (q - 4)] = s;   // loss sums then phi sums are contiguous
+    }
+}
+
+// ---- column sums of a delta matrix over a slab of rows: db partials (and dW_1 for the first layer) ----
+// grid = number of slabs; block = H / 2 threads (two adjacent columns each); out [slab][(1 + P1) * H]
+__global__ void __launch_bounds__(512) k_wide_colsum(const __nv_bfloat16* D, const float* xb, const float* bscal, int use_bn,
+                                                     int B, int H, int R4, int P1, int rows_per_slab, float* out)
+{
+    const int c2 = threadIdx.x;   // column pair
+    const int r0 = blockIdx.x * rows_per_slab;
+    const int r1 = min(B, r0 + rows_per_slab);
+    float s0 = 0.f, s1 = 0.f;
+    float w0[4] = {0.f, 0.f, 0.f, 0.f}, w1[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int r = r0; r < r1; r++) {
+        const float2 dv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(D + (size_t)r * H + 2 * c2));
+        s0 += dv.x;
+        s1 += dv.y;
+        for (int p = 0; p < P1; p++) {
+            float x = xb[(size_t)r * R4 + p];
+            if (use_bn) x = (x - bscal[BS_BN + 2 * p]) * bscal[BS_BN + 2 * p + 1];
+            w0[p] = fmaf(dv.x, x, w0[p]);
+            w1[p] = fmaf(dv.y, x, w1[p]);
+        }
+    }
+    float* o = out + (size_t)blockIdx.x * (1 + P1) * H;
+    o[2 * c2] = s0;
+    o[2 * c2 + 1] = s1;
+    for (int p = 0; p < P1; p++) {
+        o[(1 + p) * H + 2 * c2] = w0[p];
+        o[(1 + p) * H + 2 * c2 + 1] = w1[p];
+    }
+}
+
+// ---- split-K partials [S][H(o)][H(i)] -> flat gradient of W_l (index o + i * H), fixed summation order ----
+__global__ void __launch_bounds__(256) k_wide_wreduce(const float* partial, int S, int H, float* grad_w)
+{
+    __shared__ float tile[32][33];
+    const int i0 = blockIdx.x * 32, o0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    for (int r = ty; r < 32; r += 8) {
+        float s = 0.f;
+        for (int z = 0; z < S; z++) s += partial[((size_t)z * H + (o0 + r)) * H + i0 + tx];
+        tile[r][tx] = s;   // [o][i]
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) grad_w[(size_t)(i0 + r) * H + o0 + tx] = tile[tx][r];
+}
+
+struct FinArgs {
+    WideDims d;
+    const float* head_partial; int n_head;        // [n_head][head_npart]
+    const float* colsum[8]; int n_slab;           // per hidden layer l (index l-1): [n_slab][(1 + P1) * H], P1 = P for l = 1
+    const float* bscal;
+    const float* theta;
+    float* grad;                                  // in/out flat gradient (hidden W_l, l >= 2, already there)
+    float* stats;                                 // out [MAXT] loss sums, [MAXT + q] unused
+    float* loss_out;                              // nullable
+    int T, agg_mean;
+    int loss_kind[MAXT];
+    PSlot slot[MAXPS];
+    const int* slot_of_flat;
+    int* skip_out;                                // 1: all-masked batch (epoch.jl:17-19)
+};
+
+// ---- everything of the gradient that is not a hidden weight matrix, plus the loss value ----
+__global__ void __launch_bounds__(256) k_wide_gradfin(const FinArgs a)
+{
+    const int H = a.d.H, NOUT = a.d.NOUT, NH = a.d.NH, P = a.d.P;
+    const int HP = head_npart(H, NOUT);
+    __shared__ float s_loss[MAXT];
+    if (threadIdx.x < MAXT) {
+        float s = 0.f;
+        for (int g = 0; g < a.n_head; g++) s += a.head_partial[(size_t)g * HP + head_off_loss(H, NOUT) + threadIdx.x];
+        s_loss[threadIdx.x] = s;
+    }
+    __syncthreads();
+    float post = 1.f, ntot = 0.f, L = 0.f;
+    for (int t = 0; t < a.T; t++) {
+        const float n = a.bscal[BS_N + t], ss = a.bscal[BS_SS + t], acc = s_loss[t];
+        ntot += n;
+        if (a.loss_kind[t] == LOSS_RMSE) post = 1.f / (2.f * sqrtf(acc / n));
+        L += (a.loss_kind[t] == LOSS_NSELOSS) ? acc / ss : (a.loss_kind[t] == LOSS_RMSE ? sqrtf(acc / n) : acc / n);
+    }
+    if (a.agg_mean) L /= (float)a.T;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (a.loss_out) *a.loss_out = ntot == 0.f ? __int_as_float(0x7fc00000) : L;
+        *a.skip_out = ntot == 0.f;
+        for (int t = 0; t < MAXT; t++) a.stats[t] = s_loss[t];
+    }
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.d.nflat) return;
+    // which block of the flat vector is p in?
+    float g;
+    bool have = false;
+    for (int l = 1; l <= NH && !have; l++) {
+        const int din = l == 1 ? P : H;
+        const int wo = a.d.w_off[l - 1], bo = a.d.b_off[l - 1];
+        if (p >= wo && p < wo + din * H) {
+            if (l >= 2) return;   // hidden weight matrix: written by k_wide_wreduce; `post` is applied by the update
+            const int o = (p - wo) % H, k = (p - wo) / H;
+            float s = 0.f;
+            for (int z = 0; z < a.n_slab; z++) s += a.colsum[0][(size_t)z * (1 + P) * H + (1 + k) * H + o];
+            g = s; have = true;
+        } else if (p >= bo && p < bo + H) {
+            const int o = p - bo;
+            const int stride = (l == 1 ? 1 + P : 1) * H;
+            float s = 0.f;
+            if (l == NH) {
+                for (int z = 0; z < a.n_head; z++) s += a.head_partial[(size_t)z * HP + head_off_dbh(H, NOUT) + o];
+            } else {
+                for (int z = 0; z < a.n_slab; z++) s += a.colsum[l - 1][(size_t)z * stride + o];
+            }
+            g = s; have = true;
+        }
+    }
+    if (!have) {
+        const int wo = a.d.w_off[NH], bo = a.d.b_off[NH];
+        if (p >= wo && p < wo + NOUT * H) {
+            const int o = (p - wo) % NOUT, i = (p - wo) / NOUT;
+            float s = 0.f;
+            for (int z = 0; z < a.n_head; z++) s += a.head_partial[(size_t)z * HP + o * H + i];
+            g = s;
+        } else if (p >= bo && p < bo + NOUT) {
+            float s = 0.f;
+            for (int z = 0; z < a.n_head; z++) s += a.head_partial[(size_t)z * HP + head_off_dbo(H, NOUT) + (p - bo)];
+            g = s;
+        } else {
+            // phi_raw[g]: sum over samples of gp, chained through the sigmoid squash
+            const int sl = a.slot_of_flat[p];
+            float s = 0.f;
+            if (sl >= 0) {
+                for (int z = 0; z < a.n_head; z++) s += a.head_partial[(size_t)z * HP + head_off_phi(H, NOUT) + sl];
+                const float sg = 1.f / (1.f + expf(-a.theta[p]));
+                s *= a.slot[sl].span * sg * (1.f - sg);
+            }
+            g = s;
+        }
+    }
+    a.grad[p] = g * post;
+}
+
+struct WUpdArgs {
+    WideDims d;
+    float* theta; float* m; float* v; OptState* ost;
+    const float* grad;
+    const int* skip;
+    const float* stats;        // loss sums (for the rmse post factor of the hidden matrices)
+    const float* bscal;
+    int loss_kind[MAXT]; int T;
+    int opt_kind, adamw_coupled;
+    float eta, beta1, beta2, eps, lambda;
+    __nv_bfloat16* Wf[8];      // [l-1], l = 2..NH: W_l as [out][in]  (B operand of the forward GEMM)
+    __nv_bfloat16* Wb[8];      //                  W_l as [in][out]  (B operand of the backward-data GEMM)
+    int apply;                 // 0: only refresh the bf16 images from theta
+};
+
+// ---- optimiser over the flat vector (Optimisers.jl rules) + bf16 weight images ----
+__global__ void __launch_bounds__(256) k_wide_update(const WUpdArgs a)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.d.nflat) return;
+    float th = a.theta[p];
+    if (a.apply && !*a.skip) {
+        float g = a.grad[p];
+        // hidden weight matrices come straight from the GEMM partials: apply the rmse factor here
+        bool hidden = false;
+        for (int l = 2; l <= a.d.NH; l++) hidden |= (p >= a.d.w_off[l - 1] && p < a.d.w_off[l - 1] + a.d.H * a.d.H);
+        if (hidden)
+            for (int t = 0; t < a.T; t++)
+                if (a.loss_kind[t] == LOSS_RMSE) g *= 1.f / (2.f * sqrtf(a.stats[t] / a.bscal[BS_N + t]));
+        const float b1t = a.ost->b1t, b2t = a.ost->b2t;
+        float dx;
+        if (a.opt_kind == OPT_ADAM || a.opt_kind == OPT_ADAMW) {
+            const float mt = a.beta1 * a.m[p] + (1.f - a.beta1) * g;
+            const float vt = a.beta2 * a.v[p] + (1.f - a.beta2) * g * g;
+            a.m[p] = mt;
+            a.v[p] = vt;
+            dx = mt / (1.f - b1t) / (sqrtf(vt / (1.f - b2t)) + a.eps) * a.eta;
+            if (a.opt_kind == OPT_ADAMW) dx += (a.adamw_coupled ? a.eta * a.lambda : a.lambda) * th;
+        } else if (a.opt_kind == OPT_RMSPROP) {
+            const float qv = a.beta2 * a.v[p] + (1.f - a.beta2) * g * g;
+            a.v[p] = qv;
+            dx = g * a.eta / (sqrtf(qv) + a.eps);
+        } else {
+            dx = a.eta * g;
+        }
+        th -= dx;
+        a.theta[p] = th;
+    }
+    for (int l = 2; l <= a.d.NH; l++) {
+        const int wo = a.d.w_off[l - 1], H = a.d.H;
+        if (p >= wo && p < wo + H * H) {
+            const int o = (p - wo) % H, i = (p - wo) / H;
+            const __nv_bfloat16 hb = __float2bfloat16_rn(th);
+            a.Wb[l - 1][(size_t)i * H + o] = hb;
+            a.Wf[l - 1][(size_t)o * H + i] = hb;
+        }
+    }
+}
+// step counters advance once per applied step (after k_wide_update of that step)
+__global__ void k_wide_advance(OptState* ost, const int* skip, float beta1, float beta2, int apply)
+{
+    if (!apply) return;
+    if (*skip) { ost->skipped++; return; }
+    ost->b1t *= beta1;
+    ost->b2t *= beta2;
+    ost->t++;
+}
+
+}  // namespace wide
+}  // namespace eh

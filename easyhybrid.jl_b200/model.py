@@ -234,8 +234,13 @@ def _linear2(p0, p1, f0, c0):
     return {"y0": p0 * f0 + p1, "y1": 2.0 * p0 * f0 + p1}
 
 
+def _expo2(p0, p1, f0, c0):
+    y0 = p0 * np.exp(p1 * f0)
+    return {"y0": y0, "y1": 2.0 * y0}
+
+
 _BUILTINS = [("RBQ10", _rbq10, 1, True), ("EXPO", _expo, 1, False), ("LINEAR", _linear, 1, False),
-             ("LINEAR2", _linear2, 2, False)]
+             ("LINEAR2", _linear2, 2, False), ("EXPO2", _expo2, 2, False)]
 
 
 def match_builtin(prog, outs, n_forc, n_params):
@@ -277,6 +282,12 @@ def Expo_resp_model(*, T, Resp0, k):
     """projects/ExpoHybrid/ExpoHybridEstim.jl:69-85."""
     Resp_obs = Resp0 * np.exp(k * T)
     return {"Resp_obs": Resp_obs, "Resp0": Resp0, "k": k}
+
+
+def Expo_resp_model2(*, T, Resp0, k):
+    """Two-target form of the Expo model (BASELINE config 5): the second target is twice the first."""
+    Resp_obs = Resp0 * np.exp(k * T)
+    return {"Resp_obs": Resp_obs, "Resp_obs2": 2.0 * Resp_obs, "Resp0": Resp0, "k": k}
 
 
 def LinearModel(*, x1, a, b):

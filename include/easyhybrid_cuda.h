@@ -92,6 +92,7 @@ typedef enum {
     EH_PM_EXPO = 1,     /* y0 = Resp0 * exp(k * T);          args: Resp0, k, T               */
     EH_PM_LINEAR = 2,   /* y0 = a * x + b;                   args: a, b, x                   */
     EH_PM_LINEAR2 = 3,  /* y0 = a*x + b ; y1 = 2a*x + b;     args: a, b, x (test_compute_loss.jl:209-211) */
+    EH_PM_EXPO2 = 4,    /* y0 = Resp0*exp(k*T) ; y1 = 2*y0;   args: Resp0, k, T (two-target form of the Expo model) */
     EH_PM_PROGRAM = 100 /* traced straight-line program, see eh_pm_instr                      */
 } eh_process_model;
 

@@ -134,6 +134,17 @@ static int build_program(eho_plan* pl, const eh_model_desc* d)
         int ex = emit(p, &n, EH_OP_EXP, kt, 0, 0);
         pl->pm_outputs[0] = emit(p, &n, EH_OP_MUL, r0, ex, 0);
     } break;
+    case EH_PM_EXPO2: {
+        /* (var1 = Resp0 .* exp.(k .* T), var2 = 2 .* var1): the two-target form of the Expo model used by the
+         * wide-MLP configuration (same construction as test/test_compute_loss.jl:209-211 for the linear model) */
+        if (d->n_pm_args != 3 || d->n_targ != 2) return -1;
+        int r0 = emit_arg(p, &n, &a[0]), k = emit_arg(p, &n, &a[1]), T = emit_arg(p, &n, &a[2]);
+        int kt = emit(p, &n, EH_OP_MUL, k, T, 0);
+        int ex = emit(p, &n, EH_OP_EXP, kt, 0, 0);
+        int two = emit(p, &n, EH_OP_CONST, 0, 0, 2.0f);
+        pl->pm_outputs[0] = emit(p, &n, EH_OP_MUL, r0, ex, 0);
+        pl->pm_outputs[1] = emit(p, &n, EH_OP_MUL, two, pl->pm_outputs[0], 0);
+    } break;
     case EH_PM_LINEAR:
     case EH_PM_LINEAR2: {
         /* a .* x1 .+ b (test/test_generic_hybrid_model.jl:10-12);
