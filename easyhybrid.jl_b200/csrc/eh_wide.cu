@@ -53,9 +53,9 @@ cudaError_t gemm_prepare()
     static bool done = false;
     if (done) return cudaSuccess;
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(k_wide_gemm<GEMM_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_wide_gemm<GEMM_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_wide_gemm<GEMM_WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_wide_gemm<GEMM_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(GEMM_FWD))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_wide_gemm<GEMM_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(GEMM_BWD))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_wide_gemm<GEMM_WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(GEMM_WGRAD))) != cudaSuccess) return e;
     done = true;
     return cudaSuccess;
 }
@@ -66,16 +66,18 @@ cudaError_t gemm_fwd(const CUtensorMap& tmA, const CUtensorMap& tmW, int M, int 
 {
     GemmArgs g{};
     g.M = M; g.N = N; g.K = K; g.ksplits = 1; g.act = act; g.bias = bias; g.out16 = out;
-    k_wide_gemm<GEMM_FWD><<<dim3(M / BM, N / BN, 1), GEMM_THREADS, GEMM_SMEM, st>>>(tmA, tmW, g);
+    k_wide_gemm<GEMM_FWD><<<dim3(M / BM, N / gemm_bn(GEMM_FWD), 1), GEMM_THREADS, gemm_smem(GEMM_FWD), st>>>(tmA, tmW, g);
     return cudaGetLastError();
 }
 // out = (D Wt^T) .* act'(aux): D [M x K] bf16, Wt [N x K] bf16, aux [M x N] bf16
 cudaError_t gemm_bwd(const CUtensorMap& tmD, const CUtensorMap& tmWt, int M, int N, int K, const __nv_bfloat16* aux, int act,
-                     __nv_bfloat16* out, cudaStream_t st)
+                     __nv_bfloat16* out, cudaStream_t st, float* colsum, const float* xb, const float* bscal, int R4, int P1,
+                     int use_bn)
 {
     GemmArgs g{};
     g.M = M; g.N = N; g.K = K; g.ksplits = 1; g.act = act; g.aux = aux; g.out16 = out;
-    k_wide_gemm<GEMM_BWD><<<dim3(M / BM, N / BN, 1), GEMM_THREADS, GEMM_SMEM, st>>>(tmD, tmWt, g);
+    g.colsum = colsum; g.xb = xb; g.bscal = bscal; g.R4 = R4; g.P1 = P1; g.use_bn = use_bn;
+    k_wide_gemm<GEMM_BWD><<<dim3(M / BM, N / gemm_bn(GEMM_BWD), 1), GEMM_THREADS, gemm_smem(GEMM_BWD), st>>>(tmD, tmWt, g);
     return cudaGetLastError();
 }
 // partial[z] = D[rows z]^T A[rows z]: D [Kall x M] bf16, A [Kall x N] bf16 (batch rows), ksplits slices of Kall
@@ -84,7 +86,7 @@ cudaError_t gemm_wgrad(const CUtensorMap& tmD, const CUtensorMap& tmA, int M, in
 {
     GemmArgs g{};
     g.M = M; g.N = N; g.K = Kall / ksplits; g.ksplits = ksplits; g.out32 = partial;
-    k_wide_gemm<GEMM_WGRAD><<<dim3(M / BM, N / BN, ksplits), GEMM_THREADS, GEMM_SMEM, st>>>(tmD, tmA, g);
+    k_wide_gemm<GEMM_WGRAD><<<dim3(M / BM, N / gemm_bn(GEMM_WGRAD), ksplits), GEMM_THREADS, gemm_smem(GEMM_WGRAD), st>>>(tmD, tmA, g);
     return cudaGetLastError();
 }
 
@@ -154,8 +156,8 @@ WideNet* WideNet::create(const WideModel& m, char* err, size_t errlen)
     for (int l = 2; l <= m.NH; l++) {
         if ((e = cudaMalloc(&w->Wf_[l - 1], HH * 2)) != cudaSuccess) return bail("cudaMalloc", e);
         if ((e = cudaMalloc(&w->Wb_[l - 1], HH * 2)) != cudaSuccess) return bail("cudaMalloc", e);
-        if (!make_map_bf16(&w->tmWf_[l - 1], w->Wf_[l - 1], m.H, m.H, m.H, BN) ||
-            !make_map_bf16(&w->tmWb_[l - 1], w->Wb_[l - 1], m.H, m.H, m.H, BN)) {
+        if (!make_map_bf16(&w->tmWf_[l - 1], w->Wf_[l - 1], m.H, m.H, m.H, gemm_bn(GEMM_FWD)) ||
+            !make_map_bf16(&w->tmWb_[l - 1], w->Wb_[l - 1], m.H, m.H, m.H, gemm_bn(GEMM_BWD))) {
             snprintf(err, errlen, "wide path: cuTensorMapEncodeTiled failed for a weight image");
             delete w;
             return nullptr;
@@ -197,7 +199,7 @@ cudaError_t WideNet::ensure(int B)
         for (int l = 1; l <= m_.NH; l++) WN(cudaMalloc(&A_[l - 1], (size_t)B * H * 2));
         for (int i = 0; i < 2; i++) WN(cudaMalloc(&D_[i], (size_t)B * H * 2));
         WN(cudaMalloc(&partial_, (size_t)16 * H * H * 4));
-        const int slabs = (B + 511) / 512;
+        const int slabs = (B + 127) / 128;
         for (int l = 1; l < m_.NH; l++) WN(cudaMalloc(&colsum_[l - 1], (size_t)slabs * (1 + (l == 1 ? m_.P : 0)) * H * 4));
         cap_ = B;
     }
@@ -213,7 +215,7 @@ cudaError_t WideNet::ensure(int B)
         }
         if (!ok) { snprintf(err_, sizeof err_, "cuTensorMapEncodeTiled failed"); return cudaErrorUnknown; }
         mapB_ = B;
-        n_slab_ = (B + 511) / 512;
+        n_slab_ = (B + 127) / 128;
         ksplit_ = 1;
         for (int s : {16, 8, 4, 2})
             if (B % (s * BK) == 0) { ksplit_ = s; break; }
@@ -242,8 +244,8 @@ cudaError_t WideNet::forward(const float* rec, const int* idx, long long rec_bas
     k_wide_gather<<<(B + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float4*>(rec), idx, rec_base, nrec, B, m_.R4 / 4,
                                                    reinterpret_cast<float4*>(xb_));
     WN(cudaGetLastError());
-    const long long nt = (long long)B * (H / 8);
-    k_wide_first<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(xb_, pblock, bscal, m_.use_bn, d, B, m_.act, A_[0]);
+    const int rows_per_cta = (256 / (H / 8)) * FIRST_ROWS;
+    k_wide_first<<<(unsigned)((B + rows_per_cta - 1) / rows_per_cta), 256, 0, st>>>(xb_, pblock, bscal, m_.use_bn, d, B, m_.act, A_[0]);
     WN(cudaGetLastError());
     for (int l = 2; l <= m_.NH; l++)
         WN(gemm_fwd(tmA_k_[l - 2], tmWf_[l - 1], B, H, H, pblock + m_.b_off[l - 1], m_.act, A_[l - 1], st));
@@ -272,10 +274,10 @@ cudaError_t WideNet::step(const float* rec, const int* idx, long long rec_base, 
         WN(gemm_wgrad(tmD_mn_[cur], tmA_mn_[l - 2], H, H, B, ksplit_, partial_, st));
         k_wide_wreduce<<<dim3(H / 32, H / 32), 256, 0, st>>>(partial_, ksplit_, H, grad + m_.w_off[l - 1]);
         WN(cudaGetLastError());
-        WN(gemm_bwd(tmD_k_[cur], tmWb_[l - 1], B, H, H, A_[l - 2], m_.act, D_[nxt], st));
-        k_wide_colsum<<<n_slab_, H / 2, 0, st>>>(D_[nxt], xb_, bscal, m_.use_bn, B, H, m_.R4, (l - 1 == 1) ? m_.P : 0, 512,
-                                                 colsum_[l - 2]);
-        WN(cudaGetLastError());
+        // backward data; its epilogue also leaves the 32-row column sums of D_{l-1} (bias gradient of layer l-1 and,
+        // for layer 1, the x-weighted sums = its weight gradient)
+        WN(gemm_bwd(tmD_k_[cur], tmWb_[l - 1], B, H, H, A_[l - 2], m_.act, D_[nxt], st, colsum_[l - 2], xb_, bscal, m_.R4,
+                    (l - 1 == 1) ? m_.P : 0, m_.use_bn));
     }
     FinArgs fa{};
     fa.d = d; fa.head_partial = head_partial_; fa.n_head = n_head_; fa.n_slab = n_slab_;
@@ -285,7 +287,7 @@ cudaError_t WideNet::step(const float* rec, const int* idx, long long rec_base, 
     for (int t = 0; t < 4; t++) fa.loss_kind[t] = m_.loss_kind[t];
     for (int s = 0; s < 8; s++) fa.slot[s] = ha.slot[s];
     fa.slot_of_flat = m_.d_slot_of_flat; fa.skip_out = skip_;
-    k_wide_gradfin<<<(m_.nflat + 255) / 256, 256, 0, st>>>(fa);
+    k_wide_gradfin<<<(gradfin_count(d) + 31) / 32, 256, 0, st>>>(fa);
     WN(cudaGetLastError());
     if (apply) {
         WUpdArgs u{};
@@ -358,7 +360,7 @@ extern "C" eh_status eh_selftest_wide_gemm(int32_t mode, int32_t M, int32_t N, i
                                            void* out, int32_t device, float* ms_out)
 {
     if (!A || !B || !out || mode < 0 || mode > 2) return EH_EINVAL;
-    if (M % BM || N % BN || ksplits < 1) return EH_EINVAL;
+    if (M % BM || N % gemm_bn(mode) || ksplits < 1) return EH_EINVAL;
     WCK(cudaSetDevice(device));
     cudaDeviceProp prop;
     WCK(cudaGetDeviceProperties(&prop, device));
@@ -386,7 +388,7 @@ extern "C" eh_status eh_selftest_wide_gemm(int32_t mode, int32_t M, int32_t N, i
     else WCK(cudaMalloc(&dO16, (size_t)M * N * 2));
     CUtensorMap tmA, tmB;
     bool ok;
-    if (!wg) ok = make_map_bf16(&tmA, dA, K, M, K, BM) && make_map_bf16(&tmB, dB, K, N, K, BN);
+    if (!wg) ok = make_map_bf16(&tmA, dA, K, M, K, BM) && make_map_bf16(&tmB, dB, K, N, K, gemm_bn(mode));
     else ok = make_map_bf16(&tmA, dA, M, K, M, BK) && make_map_bf16(&tmB, dB, N, K, N, BK);
     if (!ok) return EH_ECUDA;
     cudaEvent_t e0, e1;
@@ -396,7 +398,7 @@ extern "C" eh_status eh_selftest_wide_gemm(int32_t mode, int32_t M, int32_t N, i
     for (int r = 0; r < reps; r++) {
         if (r == reps - 1) WCK(cudaEventRecord(e0));
         if (mode == GEMM_FWD) WCK(gemm_fwd(tmA, tmB, M, N, K, dBias, act, dO16, 0));
-        else if (mode == GEMM_BWD) WCK(gemm_bwd(tmA, tmB, M, N, K, dAux, act, dO16, 0));
+        else if (mode == GEMM_BWD) WCK(gemm_bwd(tmA, tmB, M, N, K, dAux, act, dO16, 0, nullptr, nullptr, nullptr, 0, 0, 0));
         else WCK(gemm_wgrad(tmA, tmB, M, N, K, ksplits, dO32, 0));
         if (r == reps - 1) WCK(cudaEventRecord(e1));
     }

@@ -13,7 +13,8 @@ cudaError_t gemm_prepare();
 cudaError_t gemm_fwd(const CUtensorMap& tmA, const CUtensorMap& tmW, int M, int N, int K, const float* bias, int act,
                      __nv_bfloat16* out, cudaStream_t st);
 cudaError_t gemm_bwd(const CUtensorMap& tmD, const CUtensorMap& tmWt, int M, int N, int K, const __nv_bfloat16* aux, int act,
-                     __nv_bfloat16* out, cudaStream_t st);
+                     __nv_bfloat16* out, cudaStream_t st, float* colsum, const float* xb, const float* bscal, int R4, int P1,
+                     int use_bn);
 cudaError_t gemm_wgrad(const CUtensorMap& tmD, const CUtensorMap& tmA, int M, int N, int Kall, int ksplits, float* partial,
                        cudaStream_t st);
 

@@ -25,13 +25,22 @@
 namespace eh {
 namespace wide {
 
-constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4, UMMA_K = 16;
-constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
-constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KB
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int BM = 128, BK = 64, UMMA_K = 16;
+constexpr int BS_BN_OFF = 3 * MAXT;   // == BS_BN of eh_chunk.cuh (per-batch scalar row: input BatchNorm mu / rstd)
 constexpr int GEMM_THREADS = 192;            // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..5: epilogue
-constexpr int GEMM_SMEM = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
-constexpr int TMEM_COLS = 256;
+// Tile width and pipeline depth per GEMM kind.
+//  * weight gradient: 128 x 256 tiles, 64 k-blocks per CTA, 4 stages of 48 KB, one CTA per SM (main-loop bound);
+//  * forward / backward-data: only 8 k-blocks per tile, so the epilogue (TMEM -> bias/activation or act' -> bf16 ->
+//    HBM) weighs as much as the main loop.  128 x 128 tiles with 3 stages of 32 KB leave room for TWO CTAs per SM
+//    (2 x 97 KB shared memory, 2 x 128 TMEM columns): one CTA's epilogue overlaps the other's main loop without
+//    any persistent-scheduler machinery.
+__host__ __device__ constexpr int gemm_bn(int mode) { return mode == 2 ? 256 : 128; }
+__host__ __device__ constexpr int gemm_stages(int mode) { return mode == 2 ? 4 : 3; }
+__host__ __device__ constexpr int gemm_stage_bytes(int mode) { return (BM + gemm_bn(mode)) * BK * 2; }
+__host__ __device__ constexpr int gemm_smem(int mode)
+{
+    return gemm_stages(mode) * gemm_stage_bytes(mode) + 1024 /*alignment slack*/ + 1024 /*barriers, bias*/;
+}
 
 enum : int { GEMM_FWD = 0, GEMM_BWD = 1, GEMM_WGRAD = 2 };
 
@@ -43,6 +52,12 @@ struct GemmArgs {
     const __nv_bfloat16* aux;  // BWD: A_{l-1} [M x N] (activation whose derivative multiplies the tile)
     __nv_bfloat16* out16;    // FWD / BWD: [M x N] row-major
     float* out32;            // WGRAD: [ksplits][M x N] row-major partials
+    // BWD, optional: column sums of the (bf16-rounded) output tile per 32-row slab -> the bias gradient of the layer
+    // below, and for the first layer also the x-weighted sums (its weight gradient): [M / 32][(1 + P1) * N]
+    float* colsum;
+    const float* xb;         // [M x R4] compact batch records (first P1 entries = chain inputs)
+    const float* bscal;      // input BatchNorm scalars (mu, rstd per input) when use_bn
+    int R4, P1, use_bn;
 };
 
 // ---- thin PTX wrappers ---------------------------------------------------------------------------
@@ -166,20 +181,26 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi)
 }
 
 // grid: (M / BM, N / BN, ksplits).  FWD / BWD: tmA = [M x K] K-major (box 64 x 128), tmB = [N x K] K-major
-// (box 64 x 256).  WGRAD: tmA = deltas [Kall x M], tmB = activations [Kall x N], both MN-major (box 64 x 64).
+// (box 64 x 128).  WGRAD: tmA = deltas [Kall x M], tmB = activations [Kall x N], both MN-major (box 64 x 64).
 template <int MODE>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, MODE == GEMM_WGRAD ? 1 : 2)
 k_wide_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g)
 {
+    constexpr int BN = gemm_bn(MODE);
+    constexpr int STAGES = gemm_stages(MODE);
+    constexpr int A_STAGE_BYTES = BM * BK * 2, STAGE_BYTES = gemm_stage_bytes(MODE);
+    constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+    constexpr int TMEM_COLS = BN;                // fp32 accumulator: one column per output column
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // swizzle atoms need 1024-byte alignment
-    const uint32_t bar0 = base + STAGES * STAGE_BYTES;             // full[STAGES], empty[STAGES], tmem_full, tmem slot
+    const uint32_t bar0 = base + BAR_OFF;                          // full[STAGES], empty[STAGES], tmem_full, tmem slot
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
     auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
     const uint32_t tmem_full_bar = bar0 + 8u * (2 * STAGES);
     const uint32_t tmem_slot = bar0 + 8u * (2 * STAGES + 1);
     uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
-    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + STAGES * STAGE_BYTES + 8 * (2 * STAGES + 1));
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + BAR_OFF + 8 * (2 * STAGES + 1));
+    float* s_bias = reinterpret_cast<float*>(gen_base + BAR_OFF + 128);   // FWD: bias of the tile's columns
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
@@ -253,17 +274,34 @@ k_wide_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
     } else {
         // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+        // A thread owns one accumulator row (TMEM lane), i.e. a 256-byte strip of the bf16 output.  Writing that
+        // directly would scatter 16-byte pieces over 32 rows per instruction, so the strip goes through shared
+        // memory (the pipeline stages are idle once the accumulator is complete; rows padded to 272 bytes keep
+        // the 16-byte accesses conflict-free) and leaves as coalesced 256-byte row segments.
         const int q = warp & 3;
         const int row = m0 + q * 32 + lane;
+        constexpr int OPITCH = BN * 2 + 16;
+        uint8_t* stg = gen_base + q * (32 * OPITCH);
+        // while the main loop runs: fetch what the epilogue needs besides the accumulator
+        uint4 auxr[MODE == GEMM_BWD ? BN / 8 : 1];
+        if (MODE == GEMM_BWD) {
+            const uint4* ap = reinterpret_cast<const uint4*>(g.aux + (size_t)row * g.N + n0);
+#pragma unroll
+            for (int j = 0; j < BN / 8; j++) auxr[j] = __ldg(ap + j);   // my row of the activation tile, held in registers
+        }
+        if (MODE == GEMM_FWD) {
+            const int t = (warp - 2) * 32 + lane;   // 0..127
+            for (int i = t; i < BN; i += 128) s_bias[i] = __ldg(g.bias + n0 + i);
+            asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
+        }
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
-#pragma unroll 1
+#pragma unroll
         for (int c = 0; c < BN; c += 32) {
             uint32_t r[32];
             tc_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, r);
-            const int col = n0 + c;
             if (MODE == GEMM_WGRAD) {
-                float4* dst = reinterpret_cast<float4*>(g.out32 + ((size_t)blockIdx.z * g.M + row) * g.N + col);
+                float4* dst = reinterpret_cast<float4*>(g.out32 + ((size_t)blockIdx.z * g.M + row) * g.N + n0 + c);
 #pragma unroll
                 for (int j = 0; j < 8; j++)
                     dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
@@ -271,18 +309,17 @@ k_wide_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             } else {
                 uint32_t o[16];
                 if (MODE == GEMM_FWD) {
-                    const float4* b4 = reinterpret_cast<const float4*>(g.bias + col);
+                    const float4* b4 = reinterpret_cast<const float4*>(s_bias + c);
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
-                        const float4 b = __ldg(b4 + j);
+                        const float4 b = b4[j];
                         o[2 * j] = pack_bf16(act1(g.act, __uint_as_float(r[4 * j]) + b.x), act1(g.act, __uint_as_float(r[4 * j + 1]) + b.y));
                         o[2 * j + 1] = pack_bf16(act1(g.act, __uint_as_float(r[4 * j + 2]) + b.z), act1(g.act, __uint_as_float(r[4 * j + 3]) + b.w));
                     }
                 } else {
-                    const uint4* a4 = reinterpret_cast<const uint4*>(g.aux + (size_t)row * g.N + col);
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
-                        const uint4 a = __ldg(a4 + j);
+                        const uint4 a = auxr[MODE == GEMM_BWD ? (c >> 3) + j : 0];
                         const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
                         for (int e = 0; e < 4; e++) {
@@ -293,9 +330,62 @@ k_wide_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         }
                     }
                 }
-                uint4* dst = reinterpret_cast<uint4*>(g.out16 + (size_t)row * g.N + col);
 #pragma unroll
-                for (int j = 0; j < 4; j++) dst[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                for (int j = 0; j < 4; j++)
+                    *reinterpret_cast<uint4*>(stg + lane * OPITCH + ((c >> 3) + j) * 16) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+            }
+        }
+        if (MODE == GEMM_BWD && g.colsum != nullptr) {
+            // column sums over this warp's 32 rows, straight from the staged bf16 strip: lane l owns columns 4l .. 4l+3
+            __syncwarp();
+            float cs[4] = {0.f, 0.f, 0.f, 0.f}, cw[4][4];
+            float xr[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int p = 0; p < 4; p++) {
+                cw[p][0] = cw[p][1] = cw[p][2] = cw[p][3] = 0.f;
+                if (p < g.P1) {
+                    float x = g.xb[(size_t)row * g.R4 + p];
+                    if (g.use_bn) x = (x - g.bscal[BS_BN_OFF + 2 * p]) * g.bscal[BS_BN_OFF + 2 * p + 1];
+                    xr[p] = x;
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 32; r++) {
+                const uint2 v = *reinterpret_cast<const uint2*>(stg + r * OPITCH + lane * 8);
+                const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.x));
+                const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.y));
+                cs[0] += f0.x; cs[1] += f0.y; cs[2] += f1.x; cs[3] += f1.y;
+#pragma unroll
+                for (int p = 0; p < 4; p++) {
+                    if (p < g.P1) {
+                        const float x = __shfl_sync(0xffffffffu, xr[p], r);
+                        cw[p][0] = fmaf(f0.x, x, cw[p][0]); cw[p][1] = fmaf(f0.y, x, cw[p][1]);
+                        cw[p][2] = fmaf(f1.x, x, cw[p][2]); cw[p][3] = fmaf(f1.y, x, cw[p][3]);
+                    }
+                }
+            }
+            // combine the four warps (fixed order) so that one 128-row slab per CTA goes out
+            float* s_cs = reinterpret_cast<float*>(gen_base + 4 * (32 * OPITCH));   // [4 warps][1 + P1][BN], behind the strips
+            *reinterpret_cast<float4*>(s_cs + (q * 5 + 0) * BN + lane * 4) = make_float4(cs[0], cs[1], cs[2], cs[3]);
+#pragma unroll
+            for (int p = 0; p < 4; p++)
+                if (p < g.P1) *reinterpret_cast<float4*>(s_cs + (q * 5 + 1 + p) * BN + lane * 4) = make_float4(cw[p][0], cw[p][1], cw[p][2], cw[p][3]);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const int t = (warp - 2) * 32 + lane;   // column of the tile
+            for (int p = 0; p <= g.P1; p++) {
+                const float v = ((s_cs[(0 * 5 + p) * BN + t] + s_cs[(1 * 5 + p) * BN + t]) + s_cs[(2 * 5 + p) * BN + t]) + s_cs[(3 * 5 + p) * BN + t];
+                g.colsum[((size_t)blockIdx.x * (1 + g.P1) + p) * g.N + n0 + t] = v;
+            }
+        }
+        if (MODE != GEMM_WGRAD) {
+            __syncwarp();
+            // BN * 2 bytes per row = BN / 8 lanes of 16 bytes: 32 / (BN / 8) rows per instruction
+            constexpr int LPR = BN / 8, RPI = 32 / LPR;
+#pragma unroll 4
+            for (int r0 = 0; r0 < 32; r0 += RPI) {
+                const int rr = r0 + lane / LPR, cc = lane % LPR;
+                const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * OPITCH + cc * 16);
+                *(reinterpret_cast<uint4*>(g.out16 + (size_t)(m0 + q * 32 + rr) * g.N + n0) + cc) = v;
             }
         }
         tc_fence_before();

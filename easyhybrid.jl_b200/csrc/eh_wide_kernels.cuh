@@ -20,6 +20,8 @@
 namespace eh {
 namespace wide {
 
+static_assert(BS_BN_OFF == BS_BN, "per-batch scalar row layout");
+
 // partial vector written by one CTA of k_wide_head (floats): [NOUT][H] dWo, [NOUT] dbo(pad 4), [H] db_NH,
 // [MAXT] loss sums, [MAXPS] phi sums
 __host__ __device__ constexpr int head_off_dbo(int H, int NOUT) { return NOUT * H; }
@@ -51,29 +53,46 @@ __device__ __forceinline__ float act_bf16(int act, float z) { return act1(act, z
 __device__ __forceinline__ float dact_out(int act, float a) { return dact1(act, a); }
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) { return pack_bf16(lo, hi); }
 
-// ---- layer 1: A1[b][o] = act(b1[o] + sum_p xn[b][p] W1[o][p]); one thread = 8 consecutive o of one sample ----
+// ---- layer 1: A1[b][o] = act(b1[o] + sum_p xn[b][p] W1[o][p]) ----
+// A thread owns 8 consecutive outputs (their weights stay in registers) and walks FIRST_ROWS rows of the batch;
+// a CTA covers the whole width for 256 / (H / 8) row groups.
+constexpr int FIRST_ROWS = 16;
 __global__ void __launch_bounds__(256) k_wide_first(const float* xb, const float* theta, const float* bscal, int use_bn,
                                                     WideDims d, int B, int act, __nv_bfloat16* A1)
 {
-    const int per_row = d.H / 8;
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long long)B * per_row) return;
-    const int b = (int)(t / per_row), o0 = (int)(t % per_row) * 8;
-    float z[8];
+    const int per_row = d.H / 8;                       // threads across the width
+    const int groups = 256 / per_row;                  // row groups per CTA
+    const int o0 = (threadIdx.x % per_row) * 8;
+    const int r0 = (blockIdx.x * groups + threadIdx.x / per_row) * FIRST_ROWS;
+    float bias[8], w[4][8], mu[4], rs[4];
 #pragma unroll
-    for (int j = 0; j < 8; j++) z[j] = __ldg(theta + d.b_off[0] + o0 + j);
-    for (int p = 0; p < d.P; p++) {
-        float x = xb[(size_t)b * d.R4 + p];
-        if (use_bn) x = (x - bscal[BS_BN + 2 * p]) * bscal[BS_BN + 2 * p + 1];
+    for (int j = 0; j < 8; j++) bias[j] = __ldg(theta + d.b_off[0] + o0 + j);
 #pragma unroll
-        for (int j = 0; j < 8; j++) z[j] = fmaf(x, __ldg(theta + d.w_off[0] + o0 + j + p * d.H), z[j]);
+    for (int p = 0; p < 4; p++) {
+        mu[p] = (use_bn && p < d.P) ? bscal[BS_BN + 2 * p] : 0.f;
+        rs[p] = (use_bn && p < d.P) ? bscal[BS_BN + 2 * p + 1] : 1.f;
+#pragma unroll
+        for (int j = 0; j < 8; j++) w[p][j] = p < d.P ? __ldg(theta + d.w_off[0] + o0 + j + p * d.H) : 0.f;
     }
-    uint4 o;
-    o.x = pack2(act_bf16(act, z[0]), act_bf16(act, z[1]));
-    o.y = pack2(act_bf16(act, z[2]), act_bf16(act, z[3]));
-    o.z = pack2(act_bf16(act, z[4]), act_bf16(act, z[5]));
-    o.w = pack2(act_bf16(act, z[6]), act_bf16(act, z[7]));
-    *reinterpret_cast<uint4*>(A1 + (size_t)b * d.H + o0) = o;
+    for (int b = r0; b < r0 + FIRST_ROWS && b < B; b++) {
+        float z[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) z[j] = bias[j];
+#pragma unroll
+        for (int p = 0; p < 4; p++) {
+            if (p < d.P) {
+                const float x = (xb[(size_t)b * d.R4 + p] - mu[p]) * rs[p];
+#pragma unroll
+                for (int j = 0; j < 8; j++) z[j] = fmaf(x, w[p][j], z[j]);
+            }
+        }
+        uint4 o;
+        o.x = pack2(act_bf16(act, z[0]), act_bf16(act, z[1]));
+        o.y = pack2(act_bf16(act, z[2]), act_bf16(act, z[3]));
+        o.z = pack2(act_bf16(act, z[4]), act_bf16(act, z[5]));
+        o.w = pack2(act_bf16(act, z[6]), act_bf16(act, z[7]));
+        *reinterpret_cast<uint4*>(A1 + (size_t)b * d.H + o0) = o;
+    }
 }
 
 // the pieces of StepCfg that resolve_params / the process-model functors look at
@@ -330,15 +349,24 @@ __global__ void __launch_bounds__(512) k_wide_colsum(const __nv_bfloat16* D, con
     const int r1 = min(B, r0 + rows_per_slab);
     float s0 = 0.f, s1 = 0.f;
     float w0[4] = {0.f, 0.f, 0.f, 0.f}, w1[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int r = r0; r < r1; r++) {
-        const float2 dv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(D + (size_t)r * H + 2 * c2));
-        s0 += dv.x;
-        s1 += dv.y;
-        for (int p = 0; p < P1; p++) {
-            float x = xb[(size_t)r * R4 + p];
-            if (use_bn) x = (x - bscal[BS_BN + 2 * p]) * bscal[BS_BN + 2 * p + 1];
-            w0[p] = fmaf(dv.x, x, w0[p]);
-            w1[p] = fmaf(dv.y, x, w1[p]);
+    for (int rb = r0; rb < r1; rb += 8) {
+        __nv_bfloat162 raw[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++)   // independent loads first: the slab is streamed, not chased
+            raw[u] = rb + u < r1 ? *reinterpret_cast<const __nv_bfloat162*>(D + (size_t)(rb + u) * H + 2 * c2) : __floats2bfloat162_rn(0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const float2 dv = __bfloat1622float2(raw[u]);
+            s0 += dv.x;
+            s1 += dv.y;
+            if (P1 > 0 && rb + u < r1) {
+                for (int p = 0; p < P1; p++) {
+                    float x = xb[(size_t)(rb + u) * R4 + p];
+                    if (use_bn) x = (x - bscal[BS_BN + 2 * p]) * bscal[BS_BN + 2 * p + 1];
+                    w0[p] = fmaf(dv.x, x, w0[p]);
+                    w1[p] = fmaf(dv.y, x, w1[p]);
+                }
+            }
         }
     }
     float* o = out + (size_t)blockIdx.x * (1 + P1) * H;
@@ -357,8 +385,12 @@ __global__ void __launch_bounds__(256) k_wide_wreduce(const float* partial, int 
     const int i0 = blockIdx.x * 32, o0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
     for (int r = ty; r < 32; r += 8) {
+        float t[16];
+#pragma unroll
+        for (int z = 0; z < 16; z++) t[z] = z < S ? __ldcs(partial + ((size_t)z * H + (o0 + r)) * H + i0 + tx) : 0.f;
         float s = 0.f;
-        for (int z = 0; z < S; z++) s += partial[((size_t)z * H + (o0 + r)) * H + i0 + tx];
+#pragma unroll
+        for (int z = 0; z < 16; z++) s += t[z];   // fixed order
         tile[r][tx] = s;   // [o][i]
     }
     __syncthreads();
@@ -381,16 +413,28 @@ struct FinArgs {
     int* skip_out;                                // 1: all-masked batch (epoch.jl:17-19)
 };
 
+// number of flat entries k_wide_gradfin produces: W_1 + b_1 (contiguous), b_2 .. b_NH, then everything from the output
+// layer on (W_o, b_o, phi)
+__host__ __device__ inline int gradfin_count(const WideDims& d)
+{
+    return d.P * d.H + d.H + (d.NH - 1) * d.H + (d.nflat - d.w_off[d.NH]);
+}
+
 // ---- everything of the gradient that is not a hidden weight matrix, plus the loss value ----
+// 8 threads per entry walk the partial vectors (slabs of k_wide_colsum / CTAs of k_wide_head) with a stride of 8 and
+// combine in a fixed shuffle order: deterministic, and the dependent-load chains are 8x shorter.
 __global__ void __launch_bounds__(256) k_wide_gradfin(const FinArgs a)
 {
     const int H = a.d.H, NOUT = a.d.NOUT, NH = a.d.NH, P = a.d.P;
     const int HP = head_npart(H, NOUT);
     __shared__ float s_loss[MAXT];
-    if (threadIdx.x < MAXT) {
-        float s = 0.f;
-        for (int g = 0; g < a.n_head; g++) s += a.head_partial[(size_t)g * HP + head_off_loss(H, NOUT) + threadIdx.x];
-        s_loss[threadIdx.x] = s;
+    if (threadIdx.x < 32) {
+        for (int t = 0; t < MAXT; t++) {
+            float s = 0.f;
+            for (int g = threadIdx.x; g < a.n_head; g += 32) s += a.head_partial[(size_t)g * HP + head_off_loss(H, NOUT) + t];
+            s = warp_sum(s);
+            if (threadIdx.x == 0) s_loss[t] = s;
+        }
     }
     __syncthreads();
     float post = 1.f, ntot = 0.f, L = 0.f;
@@ -406,56 +450,54 @@ __global__ void __launch_bounds__(256) k_wide_gradfin(const FinArgs a)
         *a.skip_out = ntot == 0.f;
         for (int t = 0; t < MAXT; t++) a.stats[t] = s_loss[t];
     }
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= a.d.nflat) return;
-    // which block of the flat vector is p in?
-    float g;
-    bool have = false;
-    for (int l = 1; l <= NH && !have; l++) {
-        const int din = l == 1 ? P : H;
-        const int wo = a.d.w_off[l - 1], bo = a.d.b_off[l - 1];
-        if (p >= wo && p < wo + din * H) {
-            if (l >= 2) return;   // hidden weight matrix: written by k_wide_wreduce; `post` is applied by the update
-            const int o = (p - wo) % H, k = (p - wo) / H;
-            float s = 0.f;
-            for (int z = 0; z < a.n_slab; z++) s += a.colsum[0][(size_t)z * (1 + P) * H + (1 + k) * H + o];
-            g = s; have = true;
-        } else if (p >= bo && p < bo + H) {
-            const int o = p - bo;
-            const int stride = (l == 1 ? 1 + P : 1) * H;
-            float s = 0.f;
-            if (l == NH) {
-                for (int z = 0; z < a.n_head; z++) s += a.head_partial[(size_t)z * HP + head_off_dbh(H, NOUT) + o];
-            } else {
-                for (int z = 0; z < a.n_slab; z++) s += a.colsum[l - 1][(size_t)z * stride + o];
-            }
-            g = s; have = true;
-        }
-    }
-    if (!have) {
-        const int wo = a.d.w_off[NH], bo = a.d.b_off[NH];
-        if (p >= wo && p < wo + NOUT * H) {
-            const int o = (p - wo) % NOUT, i = (p - wo) / NOUT;
-            float s = 0.f;
-            for (int z = 0; z < a.n_head; z++) s += a.head_partial[(size_t)z * HP + o * H + i];
-            g = s;
-        } else if (p >= bo && p < bo + NOUT) {
-            float s = 0.f;
-            for (int z = 0; z < a.n_head; z++) s += a.head_partial[(size_t)z * HP + head_off_dbo(H, NOUT) + (p - bo)];
-            g = s;
+    const int q = blockIdx.x * 32 + (threadIdx.x >> 3), zl = threadIdx.x & 7;
+    const int nq = gradfin_count(a.d);
+    const bool live = q < nq;
+    // entry q -> flat index p and the partial column that feeds it
+    int p = 0, cnt = 0;
+    size_t stride = 0;
+    const float* src = nullptr;
+    int phi_slot = -1;
+    bool is_phi = false;
+    if (live) {
+        const int n1 = P * H + H;
+        if (q < n1) {
+            p = a.d.w_off[0] + q;
+            const int col = q < P * H ? (1 + q / H) * H + q % H : q - P * H;   // W_1[o][k] lives at (1 + k) H + o, b_1 at o
+            src = a.colsum[0] + col; stride = (size_t)(1 + P) * H; cnt = a.n_slab;
+            if (NH == 1) { src = a.head_partial + head_off_dbh(H, NOUT) + (q - P * H); stride = HP; cnt = a.n_head; }
+        } else if (q < n1 + (NH - 1) * H) {
+            const int l = 2 + (q - n1) / H, o = (q - n1) % H;
+            p = a.d.b_off[l - 1] + o;
+            if (l == NH) { src = a.head_partial + head_off_dbh(H, NOUT) + o; stride = HP; cnt = a.n_head; }
+            else { src = a.colsum[l - 1] + o; stride = H; cnt = a.n_slab; }
         } else {
-            // phi_raw[g]: sum over samples of gp, chained through the sigmoid squash
-            const int sl = a.slot_of_flat[p];
-            float s = 0.f;
-            if (sl >= 0) {
-                for (int z = 0; z < a.n_head; z++) s += a.head_partial[(size_t)z * HP + head_off_phi(H, NOUT) + sl];
-                const float sg = 1.f / (1.f + expf(-a.theta[p]));
-                s *= a.slot[sl].span * sg * (1.f - sg);
+            p = a.d.w_off[NH] + (q - n1 - (NH - 1) * H);
+            const int wo = a.d.w_off[NH], bo = a.d.b_off[NH];
+            stride = HP; cnt = a.n_head;
+            if (p < bo) { const int o = (p - wo) % NOUT, i = (p - wo) / NOUT; src = a.head_partial + o * H + i; }
+            else if (p < bo + NOUT) src = a.head_partial + head_off_dbo(H, NOUT) + (p - bo);
+            else {
+                is_phi = true;
+                phi_slot = a.slot_of_flat[p];
+                src = a.head_partial + head_off_phi(H, NOUT) + (phi_slot >= 0 ? phi_slot : 0);
+                if (phi_slot < 0) cnt = 0;
             }
-            g = s;
         }
     }
-    a.grad[p] = g * post;
+    float s = 0.f;
+    for (int z = zl; z < cnt; z += 8) s += src[(size_t)z * stride];
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    if (live && zl == 0) {
+        if (is_phi && phi_slot >= 0) {
+            // phi_raw: chained through the sigmoid squash
+            const float sg = 1.f / (1.f + expf(-a.theta[p]));
+            s *= a.slot[phi_slot].span * sg * (1.f - sg);
+        }
+        a.grad[p] = s * post;
+    }
 }
 
 struct WUpdArgs {
