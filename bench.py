@@ -50,6 +50,48 @@ def synth(n, seed):
     return (np.ascontiguousarray(np.stack([sw, dsw], 1)), {"ta": ta}), {"reco": reco}
 
 
+def wide_c5_leg(eh, device):
+    """BASELINE config 5 on one GPU (reported next to the headline, not instead of it): two-target Expo hybrid,
+    hidden 3 x 512, bf16 tcgen05 GEMMs, PerTarget(nseLoss, mse), batch 65536; tensor roofline of its hidden GEMMs."""
+    n = 1 << 20
+    rng = np.random.default_rng(2314)
+    T = (rng.random(n, dtype=np.float32) * 40 - 10).astype(np.float32)
+    SM = (rng.random(n, dtype=np.float32) * 0.8 + 0.1).astype(np.float32)
+    resp = 1.1 * np.exp(-8.0 * (SM - 0.6) ** 2) * np.exp(0.07 * T)
+    noise = 0.05 * float(resp.mean())
+    data = dict(T=T, SM=SM, Resp_obs=(resp + noise * rng.standard_normal(n, dtype=np.float32)).astype(np.float32),
+                Resp_obs2=(2.0 * resp + noise * rng.standard_normal(n, dtype=np.float32)).astype(np.float32))
+    model = eh.constructHybridModel({"Resp0": ["SM"]}, ["T"], ["Resp_obs", "Resp_obs2"], eh.Expo_resp_model2,
+                                    dict(k=(0.01, 0.0, 0.2), Resp0=(2.0, 0.0, 8.0)), ["k"],
+                                    hidden_layers=[512, 512, 512], activation="tanh", scale_nn_outputs=False)
+    xf, y = eh.prepare_data(model, data)
+    sess = eh.FusedSession(model, training_loss=eh.PerTarget("nseLoss", "mse"), agg="sum", opt=eh.Adam(0.001), device=device)
+    sess.upload(0, xf, y)
+    sess.set_params(model.initialparameters(np.random.default_rng(0)))
+    sess.set_perm(np.random.default_rng(7).permutation(n))
+    sess.run_steps(B, 0, 4)
+    k = 32
+    losses = sess.run_steps(B, 4, k)
+    ms, launches, _ = sess.last_timing()
+    sess.close()
+    flop = 2.0 * 3 * 2 * B * 512 * 512 * k  # two 512 x 512 hidden matrices x (forward, backward-data, weight-gradient)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    peak = float(peaks.get("bf16_tflops_sustained", 0) or 0)
+    tf = flop / (ms * 1e-3) / 1e12
+    return {"workload": "C5: two-target Expo hybrid [1-512-512-512-1] tanh, PerTarget(nseLoss, mse), Adam, batch 65536, 1 GPU",
+            "value": k * B / (ms * 1e-3), "unit": "samples/s", "us_per_step": 1e3 * ms / k, "steps": k, "dtype": "bf16 (fp32 accumulate)",
+            "gpu_launches_per_step": launches / k,
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": peak or None, "unit": "TFLOP/s",
+                         "frac": (tf / peak) if peak else None,
+                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peak else "unavailable",
+                         "flops_counted": "hidden-layer GEMMs only (2 * 3 * 2 * B * 512 * 512 per step)"},
+            "loss_first_last": [float(losses[0]), float(losses[-1])]}
+
+
 def make_model(eh):
     return eh.constructHybridModel(["sw_pot", "dsw_pot"], ["ta"], ["reco"], eh.RbQ10,
                                    dict(rb=(3.0, 0.0, 13.0), Q10=(2.0, 1.0, 4.0)), ["rb"], ["Q10"],
@@ -155,6 +197,7 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--n", type=int, default=N_PER_GPU)
+    ap.add_argument("--no-wide", action="store_true", help="skip the extra C5 (wide MLP, tcgen05) leg")
     ap.add_argument("--flags", type=int, default=0, help="EH_FLAG_* bits (1 = no CUDA graph, 2 = no PDL)")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -293,6 +336,13 @@ def main():
                                    "h2d_bytes_per_step": 8 * B, "d2h_bytes_per_step": 4, "steps": reps * kr,
                                    "api": "eh_epoch(page-locked host permutation, streamed in segments behind the training) on the dataset staged once by eh_upload"}
 
+    wide = None
+    if rank == 0 and world == 1 and not args.no_wide:
+        try:
+            wide = wide_c5_leg(eh, local)
+        except Exception as e:  # the extra leg must never take the headline line down
+            wide = {"error": str(e)[:200]}
+
     if rank == 0:
         line = {"metric": "training samples/sec (fwd+bwd+Adam)", "value": value, "unit": "samples/s", "n_gpus": world,
                 "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak",
@@ -303,6 +353,8 @@ def main():
                            "parallelism": f"dp{world}"},
                 "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
                 "final_loss": float(losses[-1])}
+        if wide is not None:
+            line["extra"] = {"c5_wide_mlp": wide}
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(eh, model)[0]
         print(json.dumps(line))

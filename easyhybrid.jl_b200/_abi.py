@@ -182,6 +182,7 @@ SIGNATURES = {
     "eh_comm_init": (C.c_int, [_p, C.c_int32, C.c_int32, _p]),
     "eh_last_timing": (C.c_int, [_p, _fp, _i64p, _fp]),
     "eh_set_profiling": (C.c_int, [_p, C.c_int32]),
+    "eh_selftest_wide_gemm": (C.c_int, [C.c_int32] * 6 + [C.c_void_p] * 5 + [C.c_int32, C.c_void_p]),
     "eh_host_alloc": (C.c_int, [C.POINTER(_p), C.c_size_t]),
     "eh_host_free": (C.c_int, [_p]),
 }

@@ -285,6 +285,14 @@ eh_status eh_host_free(void* p);
 eh_status eh_last_timing(eh_ctx* ctx, float* total_ms, int64_t* launches, float* step_kernel_ms);
 eh_status eh_set_profiling(eh_ctx* ctx, int32_t on);
 
+/* diagnostics: runs one tcgen05 GEMM of the wide-hidden-layer path on host matrices (bf16 bit patterns) so that a
+ * test harness can check the kernels in isolation.  mode 0: out = act(A B^T + bias), A [M x K], B [N x K];
+ * mode 1: out = (A B^T) .* act'(aux), aux [M x N]; both write bf16 [M x N].  mode 2: out[z] = A_z^T B_z for the
+ * `ksplits` row slices of A [K x M], B [K x N]; writes fp32 [ksplits][M x N].  ms_out (nullable): device time.  */
+eh_status eh_selftest_wide_gemm(int32_t mode, int32_t M, int32_t N, int32_t K, int32_t ksplits, int32_t act,
+                                const uint16_t* A, const uint16_t* B, const float* bias, const uint16_t* aux,
+                                void* out, int32_t device, float* ms_out);
+
 #ifdef __cplusplus
 }
 #endif

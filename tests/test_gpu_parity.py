@@ -224,8 +224,10 @@ def test_unsupported_models_fail_loudly(eh):
         eh.FusedSession(m)
     assert ei.value.status == _abi.EH_EUNSUPPORTED
     with pytest.raises(eh.EasyHybridCudaError) as ei:
-        eh.FusedSession(rbq10_model(eh, hidden=(512, 512, 512)))
+        eh.FusedSession(rbq10_model(eh, hidden=(64, 48)))   # between the register-tile variants and the wide path
     assert ei.value.status == _abi.EH_EUNSUPPORTED
+    # 3 x 512 is served by the wide (bf16 tcgen05) path since round 1
+    eh.FusedSession(rbq10_model(eh, hidden=(512, 512, 512))).close()
 
 
 def test_train_api_learns_q10(eh):

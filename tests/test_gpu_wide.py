@@ -122,3 +122,15 @@ def test_wide_unsupported_shapes_fail_loudly(eh):
     with pytest.raises(Exception) as ei:
         eh.FusedSession(model, training_loss="mse")
     assert "wide" in str(ei.value).lower() or "unsupported" in str(ei.value).lower()
+
+
+def test_tcgen05_gemm_kernels_against_torch():
+    """the three GEMM kinds in isolation (eh_selftest_wide_gemm): K-major forward / backward-data with fused
+    epilogues, MN-major split-K weight gradient"""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(
+        "wide_gemm_check", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "wide_gemm_check.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.main(False)

@@ -41,7 +41,8 @@ def run(mode, M, N, K, ks=1, act=1, time_it=False):
     dev = "cuda"
     Af, Bf = A.float().to(dev), B.float().to(dev)
     if mode == 0:
-        ref = torch.tanh(Af @ Bf.T + bias.to(dev)) if act == 1 else Af @ Bf.T + bias.to(dev)
+        z = Af @ Bf.T + bias.to(dev)
+        ref = torch.tanh(z) if act == 1 else (torch.sigmoid(z) if act == 2 else z)
         got = out.float().to(dev)
         tol = 1e-2
     elif mode == 1:
@@ -62,15 +63,21 @@ def run(mode, M, N, K, ks=1, act=1, time_it=False):
     return err < tol
 
 
-ok = True
-ok &= run(0, 256, 256, 128)
-ok &= run(0, 512, 512, 512)
-ok &= run(1, 512, 512, 512)
-ok &= run(2, 256, 256, 256, ks=1)
-ok &= run(2, 512, 512, 4096, ks=4)
-if len(sys.argv) > 1:
-    run(0, 65536, 512, 512, time_it=True)
-    run(1, 65536, 512, 512, time_it=True)
-    run(2, 512, 512, 65536, ks=16, time_it=True)
-print("WIDE GEMM", "OK" if ok else "FAILED")
-sys.exit(0 if ok else 1)
+def main(perf=False):
+    ok = True
+    ok &= run(0, 256, 256, 128)
+    ok &= run(0, 512, 512, 512)
+    ok &= run(0, 384, 256, 256, act=2)
+    ok &= run(1, 512, 512, 512)
+    ok &= run(2, 256, 256, 256, ks=1)
+    ok &= run(2, 512, 512, 4096, ks=4)
+    if perf:
+        run(0, 65536, 512, 512, time_it=True)
+        run(1, 65536, 512, 512, time_it=True)
+        run(2, 512, 512, 65536, ks=16, time_it=True)
+    print("WIDE GEMM", "OK" if ok else "FAILED")
+    return ok
+
+
+if __name__ == "__main__":
+    sys.exit(0 if main(len(sys.argv) > 1) else 1)
