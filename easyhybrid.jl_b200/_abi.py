@@ -35,6 +35,7 @@ EH_FLAG_TENSOR_PIPE = 16
 EH_SPLIT_TRAIN, EH_SPLIT_VAL = 0, 1
 EH_EVAL_STATS = 9
 EH_COMM_ID_BYTES = 128
+EH_DP_MOMENTS = 37
 
 
 class eh_pm_arg(C.Structure):
@@ -182,6 +183,8 @@ SIGNATURES = {
     "eh_comm_init": (C.c_int, [_p, C.c_int32, C.c_int32, _p]),
     "eh_last_timing": (C.c_int, [_p, _fp, _i64p, _fp]),
     "eh_set_profiling": (C.c_int, [_p, C.c_int32]),
+    "eh_dp_batch_moments": (C.c_int, [_p, C.c_int64, C.POINTER(C.c_double)]),
+    "eh_dp_set_batch_moments": (C.c_int, [_p, C.c_int64, C.POINTER(C.c_double)]),
     "eh_selftest_wide_gemm": (C.c_int, [C.c_int32] * 6 + [C.c_void_p] * 5 + [C.c_int32, C.c_void_p]),
     "eh_host_alloc": (C.c_int, [C.POINTER(_p), C.c_size_t]),
     "eh_host_free": (C.c_int, [_p]),

@@ -411,7 +411,9 @@ eh_status prepare_batch_rows_range(eh_ctx* c, int64_t n, int64_t B, int64_t b0, 
     const Split& sp = c->split[EH_SPLIT_TRAIN];
     const int64_t off = b0 * B;
     if (needs_data_stats(c) && c->world > 1)
-        return fail(c, EH_EUNSUPPORTED, "data-parallel mode needs NaN-free targets, no nseLoss and no input BatchNorm in this build");
+        return fail(c, EH_EUNSUPPORTED,
+                    "data-parallel mode with NaN targets, nseLoss or input BatchNorm: per-batch statistics are global -- call "
+                    "eh_dp_batch_moments, add the result over the ranks and hand it to eh_dp_set_batch_moments after eh_set_perm");
     if (needs_data_stats(c)) {
         StatArgs a;
         memset(&a, 0, sizeof a);
@@ -655,7 +657,7 @@ eh_status update_bn_running(eh_ctx* c, int64_t n, int64_t B, int64_t first, int6
     for (int64_t k = 0; k < nsteps; k++) {
         if (std::isnan(c->h_loss[k])) continue;
         int64_t b = (first + k) % nb;
-        int64_t Bk = std::min<int64_t>(B, n - b * B);
+        int64_t Bk = std::min<int64_t>(B, n - b * B) * c->world;  // rows of the global batch
         for (int i = 0; i < P; i++) {
             float mu = bb[(size_t)b * 2 * P + 2 * i], var = bb[(size_t)b * 2 * P + 2 * i + 1];
             float unb = Bk > 1 ? var * (float)Bk / (float)(Bk - 1) : var;
@@ -1775,6 +1777,68 @@ eh_status eh_comm_init(eh_ctx* c, int32_t rank, int32_t world, const void* ids)
     c->world = world;
     c->dp_steps = 0;
     c->perm_B = 0;  // per-batch scalars depend on the world size
+    return EH_OK;
+}
+
+// ---- data parallel: per-batch data statistics are statistics of the GLOBAL batch ----
+static void fill_stat_args(const eh_ctx* c, StatArgs& a, int64_t n, int64_t B)
+{
+    const Split& sp = c->split[EH_SPLIT_TRAIN];
+    memset(&a, 0, sizeof a);
+    a.rec = sp.rec; a.R4 = c->var->R4; a.idx = c->d_idx; a.n = n; a.Bfull = (int)B;
+    a.P = c->var->P; a.F = c->var->F; a.T = c->var->T;
+    for (int t = 0; t < MAXT; t++) { a.shift_y[t] = 0.f; a.loss_kind[t] = c->loss_kind[t]; }  // common shift on every rank
+    for (int k = 0; k < MAXP; k++) a.shift_x[k] = 0.f;
+    a.agg_mean = c->agg_mean; a.use_bn = 1;  // input sums are always taken: the ranks must agree on the layout
+    a.bscal = c->d_bscal; a.bn_batch = c->use_bn ? c->d_bn_batch : nullptr;
+}
+
+eh_status eh_dp_batch_moments(eh_ctx* c, int64_t B, double* out)
+{
+    if (!c) return EH_EINVAL;
+    if (!out || B <= 0) return fail(c, EH_EINVAL, "bad eh_dp_batch_moments arguments");
+    if (c->perm_n <= 0) return fail(c, EH_EINVAL, "no resident permutation (call eh_set_perm)");
+    CK(cudaSetDevice(c->device));
+    const int64_t n = c->perm_n, nb = (n + B - 1) / B;
+    eh_status s = ensure_bscal_cap(c, (size_t)nb);
+    if (s != EH_OK) return s;
+    double* d_mom = nullptr;
+    CK(dalloc(&d_mom, (size_t)nb * DP_MOMENTS));
+    StatArgs a;
+    fill_stat_args(c, a, n, B);
+    a.moments = d_mom;
+    k_batch_stats<<<(unsigned)nb, 256, 0, c->stream>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, d_mom, (size_t)nb * DP_MOMENTS * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_mom);
+    if (e != cudaSuccess) return fail(c, EH_ECUDA, "eh_dp_batch_moments: %s", cudaGetErrorString(e));
+    return EH_OK;
+}
+
+eh_status eh_dp_set_batch_moments(eh_ctx* c, int64_t B, const double* global)
+{
+    if (!c) return EH_EINVAL;
+    if (!global || B <= 0) return fail(c, EH_EINVAL, "bad eh_dp_set_batch_moments arguments");
+    if (c->perm_n <= 0) return fail(c, EH_EINVAL, "no resident permutation (call eh_set_perm)");
+    CK(cudaSetDevice(c->device));
+    const int64_t n = c->perm_n, nb = (n + B - 1) / B;
+    eh_status s = ensure_bscal_cap(c, (size_t)nb);
+    if (s != EH_OK) return s;
+    double* d_mom = nullptr;
+    CK(dalloc(&d_mom, (size_t)nb * DP_MOMENTS));
+    StatArgs a;
+    fill_stat_args(c, a, n, B);
+    a.use_bn = c->use_bn;
+    cudaError_t e = cudaMemcpyAsync(d_mom, global, (size_t)nb * DP_MOMENTS * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+        k_bscal_from_moments<<<(unsigned)((nb + 127) / 128), 128, 0, c->stream>>>(a, d_mom, (int)nb);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_mom);
+    if (e != cudaSuccess) return fail(c, EH_ECUDA, "eh_dp_set_batch_moments: %s", cudaGetErrorString(e));
+    c->perm_B = B;  // the rows of this permutation / batch size are in place
     return EH_OK;
 }
 

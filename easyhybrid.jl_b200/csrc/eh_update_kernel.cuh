@@ -193,7 +193,50 @@ struct StatArgs {
     int use_bn;
     float* bscal;       // [nbatches][BS_STRIDE]
     float* bn_batch;    // nullable [nbatches][2*P]: raw (mean, biased var) for the running-stat update
+    double* moments;    // nullable [nbatches][DP_MOMENTS]: write the raw sums instead of finalising (data-parallel
+                        // mode: the caller adds them over the ranks, k_bscal_from_moments finalises)
 };
+// raw per-batch sums: [cnt, S1, S2] per target, [S1, S2] per chain input, number of rows
+constexpr int DP_MOMENTS = 3 * MAXT + 2 * MAXP + 1;
+
+// finalise one per-batch scalar row from (possibly rank-summed) raw sums taken with the shifts in `a`
+__device__ inline void bscal_from_sums(const StatArgs& a, const double* m, int b)
+{
+    float* out = a.bscal + (size_t)b * BS_STRIDE;
+    const double rows = m[3 * MAXT + 2 * MAXP];
+    for (int t = 0; t < MAXT; t++) {
+        const double c = m[3 * t], u = m[3 * t + 1], w = m[3 * t + 2];
+        double sstot = c > 0 ? w - u * u / c : 0.0;
+        double aggw = a.agg_mean ? 1.0 / a.T : 1.0;
+        double ct = 0.0;
+        if (t < a.T) ct = (a.loss_kind[t] == LOSS_NSELOSS) ? aggw / sstot : aggw / c;
+        out[BS_C + t] = (float)ct;
+        out[BS_N + t] = (float)c;
+        out[BS_SS + t] = (float)sstot;
+    }
+    for (int k = 0; k < MAXP; k++) {
+        const double u = m[3 * MAXT + 2 * k], w = m[3 * MAXT + 2 * k + 1];
+        double mu = 0.0, var = 1.0 - 1e-5;
+        if (a.use_bn && k < a.P && rows > 0) {
+            mu = u / rows;
+            var = w / rows - mu * mu;
+            mu += (double)a.shift_x[k];
+            if (var < 0) var = 0;
+        }
+        out[BS_BN + 2 * k] = (float)mu;
+        out[BS_BN + 2 * k + 1] = (float)(1.0 / sqrt((double)(float)var + 1e-5));
+        if (a.bn_batch && k < a.P) {
+            a.bn_batch[(size_t)b * 2 * a.P + 2 * k] = (float)mu;
+            a.bn_batch[(size_t)b * 2 * a.P + 2 * k + 1] = (float)var;
+        }
+    }
+}
+
+__global__ void k_bscal_from_moments(const StatArgs a, const double* moments, int nbatches)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nbatches) bscal_from_sums(a, moments + (size_t)b * DP_MOMENTS, b);
+}
 
 __global__ void __launch_bounds__(256) k_batch_stats(const StatArgs a)
 {
@@ -240,35 +283,18 @@ __global__ void __launch_bounds__(256) k_batch_stats(const StatArgs a)
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        float* out = a.bscal + (size_t)b * BS_STRIDE;
         const int nw = blockDim.x >> 5;
-        for (int t = 0; t < MAXT; t++) {
-            double c = 0, u = 0, w = 0;
-            for (int q = 0; q < nw; q++) { c += sh[q][3 * t]; u += sh[q][3 * t + 1]; w += sh[q][3 * t + 2]; }
-            double sstot = c > 0 ? w - u * u / c : 0.0;
-            double aggw = a.agg_mean ? 1.0 / a.T : 1.0;
-            double ct = 0.0;
-            if (t < a.T) ct = (a.loss_kind[t] == LOSS_NSELOSS) ? aggw / sstot : aggw / c;
-            out[BS_C + t] = (float)ct;
-            out[BS_N + t] = (float)c;
-            out[BS_SS + t] = (float)sstot;
+        double m[DP_MOMENTS];
+        for (int i = 0; i < 3 * MAXT + 2 * MAXP; i++) {
+            double v = 0;
+            for (int q = 0; q < nw; q++) v += sh[q][i];
+            m[i] = v;
         }
-        for (int k = 0; k < MAXP; k++) {
-            double u = 0, w = 0;
-            for (int q = 0; q < nw; q++) { u += sh[q][3 * MAXT + 2 * k]; w += sh[q][3 * MAXT + 2 * k + 1]; }
-            double mu = 0.0, var = 1.0 - 1e-5;
-            if (a.use_bn && k < a.P && nb > 0) {
-                mu = u / nb;
-                var = w / nb - mu * mu;
-                mu += (double)a.shift_x[k];
-                if (var < 0) var = 0;
-            }
-            out[BS_BN + 2 * k] = (float)mu;
-            out[BS_BN + 2 * k + 1] = (float)(1.0 / sqrt((double)(float)var + 1e-5));
-            if (a.bn_batch && k < a.P) {
-                a.bn_batch[(size_t)b * 2 * a.P + 2 * k] = (float)mu;
-                a.bn_batch[(size_t)b * 2 * a.P + 2 * k + 1] = (float)var;
-            }
+        m[3 * MAXT + 2 * MAXP] = (double)nb;
+        if (a.moments) {
+            for (int i = 0; i < DP_MOMENTS; i++) a.moments[(size_t)b * DP_MOMENTS + i] = m[i];
+        } else {
+            bscal_from_sums(a, m, b);
         }
     }
 }

@@ -144,6 +144,7 @@ class FusedSession:
     def set_perm(self, perm0):
         a, p = self._idx1(perm0)
         self._ck(self.lib.eh_set_perm(self.h, p, a.size))
+        self._perm_n = int(a.size)
 
     def run_steps(self, batchsize, first_step, n_steps):
         losses = np.empty(n_steps, dtype=np.float32)
@@ -202,6 +203,20 @@ class FusedSession:
         assert len(blob) == world * _abi.EH_COMM_ID_BYTES
         self._ck(self.lib.eh_comm_init(self.h, rank, world, C.create_string_buffer(blob, len(blob))))
         self.rank, self.world = rank, world
+
+    def dp_exchange_batch_stats(self, batchsize, dist):
+        """data-parallel runs with NaN targets, nseLoss or input BatchNorm: make the per-batch data statistics
+        global (eh_dp_batch_moments -> sum over ranks -> eh_dp_set_batch_moments).  Call after set_perm."""
+        import torch
+        nb = (self._perm_n + batchsize - 1) // batchsize
+        mom = np.zeros((nb, _abi.EH_DP_MOMENTS), dtype=np.float64)
+        self._ck(self.lib.eh_dp_batch_moments(self.h, batchsize, mom.ctypes.data_as(C.POINTER(C.c_double))))
+        t = torch.from_numpy(mom)
+        if dist.get_backend() == "nccl":
+            t = t.cuda()
+        dist.all_reduce(t)
+        mom = np.ascontiguousarray(t.cpu().numpy())
+        self._ck(self.lib.eh_dp_set_batch_moments(self.h, batchsize, mom.ctypes.data_as(C.POINTER(C.c_double))))
 
     # ---- evaluation ----
     def eval(self, split, want_yhat=True, want_params=False):

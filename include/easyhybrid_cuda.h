@@ -258,7 +258,7 @@ eh_status eh_eval(eh_ctx* ctx, int32_t split, float* yhat, double* stats, float*
 /* ---- data parallel (one process per GPU of one NVLink / NVSwitch box) --------
  * Every rank owns a shard of the samples (its own eh_upload + eh_set_perm); global
  * batch k is the union of the ranks' local batches k, which must have the same
- * size on every rank.  Per step the ranks exchange ONE vector (loss-scaled
+ * size on every rank (see eh_dp_batch_moments for losses that need batch statistics).  Per step the ranks exchange ONE vector (loss-scaled
  * gradient + loss sums) inside the persistent kernel: rank r's CTA 0 stores it
  * into every peer's inbox through NVLink peer memory and raises a flag, all CTAs
  * sum the rank vectors in rank order and apply the optimiser redundantly, so
@@ -272,6 +272,16 @@ eh_status eh_eval(eh_ctx* ctx, int32_t split, float* yhat, double* stats, float*
 #define EH_COMM_ID_BYTES 128
 eh_status eh_comm_id(eh_ctx* ctx, void* id_out);
 eh_status eh_comm_init(eh_ctx* ctx, int32_t rank, int32_t world, const void* ids /* world x EH_COMM_ID_BYTES */);
+
+/* Data-parallel runs whose loss needs per-batch DATA statistics (valid-target counts with NaN targets, SS_tot of
+ * nseLoss, batch moments of the input BatchNorm): those are statistics of the GLOBAL batch.  After eh_set_perm every
+ * rank calls eh_dp_batch_moments (raw sums of its local batches, EH_DP_MOMENTS doubles per batch, taken with the
+ * same zero shift on every rank), the caller adds the arrays over the ranks with its own plumbing (the same one that
+ * carried the comm ids) and hands the sums to eh_dp_set_batch_moments on every rank; eh_run_steps then trains with
+ * them.  NaN-free mse / mae / rmse runs without BatchNorm do not need this.                                      */
+#define EH_DP_MOMENTS 37
+eh_status eh_dp_batch_moments(eh_ctx* ctx, int64_t B, double* out /* [ceil(n/B)][EH_DP_MOMENTS] */);
+eh_status eh_dp_set_batch_moments(eh_ctx* ctx, int64_t B, const double* summed /* same shape */);
 
 /* page-locked host buffers for callers that stream batches (eh_step_host_async copies
  * straight out of them with cudaMemcpyAsync; pageable memory also works, but synchronously) */

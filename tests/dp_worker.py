@@ -88,6 +88,37 @@ def main():
             assert abs(float(ps[-1]) - float(ref[-1])) <= 1e-4, (ps[-1], ref[-1])
             print("DP_NCCL_OK", losses[:3], want[:3])
         sess.close()
+        # ---- second scenario: NaN targets + input BatchNorm + nseLoss: per-batch statistics of the GLOBAL batch ----
+        if not os.environ.get("EH_DP_DEBUG"):
+            model2 = rbq10_model(eh, bn=True)
+            shards2 = [eh.prepare_data(model2, make_synth(n_local, seed=300 + r, nan_frac=0.04), drop_missing_rows=False) for r in range(world)]
+            X2 = np.concatenate([s[0][0] for s in shards2])
+            f2 = {"ta": np.concatenate([s[0][1]["ta"] for s in shards2])}
+            y2 = {"reco": np.concatenate([s[1]["reco"] for s in shards2])}
+            o2 = orc.Oracle(model2, training_loss="nseLoss", opt=eh.Adam(0.01))
+            xf, y = shards2[rank]
+            sess = eh.FusedSession(model2, training_loss="nseLoss", opt=eh.Adam(0.01), device=local)
+            sess.upload(0, xf, y)
+            sess.set_params(flat0)
+            sess.comm_init(rank, world, dist)
+            sess.set_perm(perms[rank])
+            sess.dp_exchange_batch_stats(B, dist)
+            dist.barrier()
+            losses = sess.run_steps(B, 0, 6)
+            ps = sess.get_params()
+            allps = [None] * world
+            dist.all_gather_object(allps, ps.tobytes())
+            if rank == 0:
+                assert all(b == allps[0] for b in allps), "replicas diverged (scenario 2)"
+                ref = flat0.copy()
+                want = []
+                for s in range(6):
+                    gi = global_batch_indices(perms, [n_local] * world, B, s % (n_local // B))
+                    want.append(o2.train_steps(ref, (X2, f2), y2, gi, world * B)[0])
+                np.testing.assert_allclose(losses, np.array(want), rtol=3e-4)
+                assert abs(float(ps[-1]) - float(ref[-1])) <= 2e-4, (ps[-1], ref[-1])
+                print("DP_NCCL_STATS_OK", losses[:3], want[:3])
+            sess.close()
     dist.destroy_process_group()
 
 
