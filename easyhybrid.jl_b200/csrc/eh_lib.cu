@@ -674,7 +674,11 @@ eh_status wide_run_steps(eh_ctx* c, int64_t n, int64_t B, int64_t first, int64_t
 {
     const Split& sp = c->split[EH_SPLIT_TRAIN];
     const int64_t nb = (n + B - 1) / B;
-    if (c->world > 1) return fail(c, EH_EUNSUPPORTED, "the wide (bf16 tcgen05) path is single-GPU in this build");
+    if (c->world > 1) {
+        if (!apply || grad_out_host) return fail(c, EH_EUNSUPPORTED, "data-parallel mode trains through eh_run_steps / eh_epoch only");
+        for (int t = 0; t < c->n_targ; t++)
+            if (c->loss_kind[t] == LOSS_RMSE) return fail(c, EH_EUNSUPPORTED, "rmse is not available in data-parallel mode on the wide path");
+    }
     for (int64_t b = 0; b < nb; b++)
         if (!eh::wide::WideNet::batch_ok(std::min<int64_t>(B, n - b * B)))
             return fail(c, EH_EUNSUPPORTED, "wide path: every batch must hold a multiple of 128 samples (got %lld)",
@@ -683,8 +687,14 @@ eh_status wide_run_steps(eh_ctx* c, int64_t n, int64_t B, int64_t first, int64_t
     for (int64_t k = 0; k < nsteps; k++) {
         const int64_t b = (first + k) % nb;
         const int64_t Bk = std::min<int64_t>(B, n - b * B);
+        eh::wide::WideDp dp;
+        memset(&dp, 0, sizeof dp);
+        if (c->world > 1) {
+            dp.world = c->world; dp.rank = c->rank; dp.tag = ++c->dp_steps; dp.err = c->d_dperr;
+            for (int r = 0; r < c->world; r++) dp.peer[r] = reinterpret_cast<float*>(c->dp_peer[r]);
+        }
         cudaError_t e = c->wide->step(sp.rec, c->d_idx + b * B, 0, (int)Bk, c->d_bscal + (size_t)b * BS_STRIDE, c->d_theta, c->d_m,
-                                      c->d_v, c->d_ost, c->d_grad, c->d_loss + k, apply, c->stream);
+                                      c->d_v, c->d_ost, c->d_grad, c->d_loss + k, apply, c->stream, c->world > 1 ? &dp : nullptr);
         if (e != cudaSuccess) return fail(c, EH_ECUDA, "wide path: %s", c->wide->error());
         if (apply) CK(refresh_tail(c));
     }
@@ -692,7 +702,13 @@ eh_status wide_run_steps(eh_ctx* c, int64_t n, int64_t B, int64_t first, int64_t
     CK(cudaMemcpyAsync(c->h_loss, c->d_loss, (size_t)nsteps * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     if (grad_out_host)
         CK(cudaMemcpyAsync(grad_out_host, c->d_grad, (size_t)c->nflat * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    unsigned herr = 0;
+    CK(cudaMemcpyAsync(&herr, c->d_dperr, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    if (herr) {
+        cudaMemset(c->d_dperr, 0, sizeof(unsigned));
+        return fail(c, EH_ENCCL, "wide path: a data-parallel peer never published its gradient");
+    }
     CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
     c->last_launches = nsteps * (3 + 5 * (int64_t)(c->var->NH - 1) + 4);
     c->last_step_ms = c->last_ms;
@@ -1744,7 +1760,8 @@ eh_status eh_comm_id(eh_ctx* c, void* id_out)
     if (!id_out) return fail(c, EH_EINVAL, "null id_out");
     CK(cudaSetDevice(c->device));
     if (!c->dp_block) {
-        const size_t bytes = (size_t)2 * EH_MAX_WORLD * rup4(c->var->NPART) * sizeof(uint2);  // {value, tag} slots
+        const size_t bytes = c->wide ? c->wide->dp_block_bytes()                                            // [2][xlen] floats + flags
+                                     : (size_t)2 * EH_MAX_WORLD * rup4(c->var->NPART) * sizeof(uint2);  // {value, tag} slots
         CK(cudaMalloc(&c->dp_block, bytes));
         CK(cudaMemset(c->dp_block, 0, bytes));
     }
@@ -1762,7 +1779,7 @@ eh_status eh_comm_init(eh_ctx* c, int32_t rank, int32_t world, const void* ids)
     if (world < 1 || world > EH_MAX_WORLD || rank < 0 || rank >= world || !ids)
         return fail(c, EH_EINVAL, "eh_comm_init: world must be 1..%d and 0 <= rank < world", EH_MAX_WORLD);
     if (!c->dp_block) return fail(c, EH_EINVAL, "eh_comm_init: call eh_comm_id on this ctx first");
-    if (!c->persist_ok) return fail(c, EH_EUNSUPPORTED, "data-parallel mode needs the persistent kernel, unavailable for this model");
+    if (!c->persist_ok && !c->wide) return fail(c, EH_EUNSUPPORTED, "data-parallel mode needs the persistent kernel, unavailable for this model");
     CK(cudaSetDevice(c->device));
     for (int r = 0; r < world; r++) {
         if (r == rank) { c->dp_peer[r] = c->dp_block; continue; }

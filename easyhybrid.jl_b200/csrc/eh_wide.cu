@@ -253,9 +253,13 @@ cudaError_t WideNet::forward(const float* rec, const int* idx, long long rec_bas
 }
 
 cudaError_t WideNet::step(const float* rec, const int* idx, long long rec_base, int B, const float* bscal, float* pblock, float* m,
-                          float* v, void* ost, float* grad, float* loss_out, int apply, cudaStream_t st)
+                          float* v, void* ost, float* grad_final, float* loss_out, int apply, cudaStream_t st, const WideDp* dp)
 {
     const int H = m_.H, NH = m_.NH;
+    const bool isdp = dp && dp->world > 1;
+    const int par = isdp ? (int)(dp->tag & 1u) : 0;
+    // data parallel: this rank's gradient goes into its exchange block, the all-reduce leaves the sum in grad_final
+    float* grad = isdp ? dp->peer[dp->rank] + (size_t)par * dp_xlen() : grad_final;
     WN(ensure(B));
     WN(forward(rec, idx, rec_base, 1ll << 62, B, bscal, pblock, st));
     const WideDims d = dims_of(m_);
@@ -286,9 +290,21 @@ cudaError_t WideNet::step(const float* rec, const int* idx, long long rec_base, 
     fa.T = m_.T; fa.agg_mean = m_.agg_mean;
     for (int t = 0; t < 4; t++) fa.loss_kind[t] = m_.loss_kind[t];
     for (int s = 0; s < 8; s++) fa.slot[s] = ha.slot[s];
-    fa.slot_of_flat = m_.d_slot_of_flat; fa.skip_out = skip_;
+    fa.slot_of_flat = m_.d_slot_of_flat; fa.skip_out = skip_; fa.dp = isdp ? 1 : 0;
     k_wide_gradfin<<<(gradfin_count(d) + 31) / 32, 256, 0, st>>>(fa);
     WN(cudaGetLastError());
+    if (isdp) {
+        AllredArgs ar{};
+        for (int r = 0; r < dp->world; r++) ar.peer[r] = dp->peer[r];
+        ar.world = dp->world; ar.rank = dp->rank; ar.par = par; ar.xlen = dp_xlen(); ar.nflat = m_.nflat; ar.tag = dp->tag;
+        ar.grad_out = grad_final; ar.stats = stats_; ar.loss_out = loss_out; ar.skip_out = skip_; ar.bscal = bscal;
+        ar.T = m_.T; ar.agg_mean = m_.agg_mean;
+        for (int t = 0; t < 4; t++) ar.loss_kind[t] = m_.loss_kind[t];
+        ar.err = dp->err;
+        k_wide_allreduce<<<2 * m_.nsm, 256, 0, st>>>(ar);
+        WN(cudaGetLastError());
+        grad = grad_final;
+    }
     if (apply) {
         WUpdArgs u{};
         u.d = d; u.theta = pblock; u.m = m; u.v = v; u.ost = reinterpret_cast<OptState*>(ost); u.grad = grad; u.skip = skip_;

@@ -18,6 +18,13 @@ cudaError_t gemm_bwd(const CUtensorMap& tmD, const CUtensorMap& tmWt, int M, int
 cudaError_t gemm_wgrad(const CUtensorMap& tmD, const CUtensorMap& tmA, int M, int N, int Kall, int ksplits, float* partial,
                        cudaStream_t st);
 
+struct WideDp {             // data-parallel state handed to WideNet::step
+    int world, rank;
+    float* peer[8];         // exchange blocks of all ranks as mapped in this process (own block at [rank])
+    unsigned tag;           // absolute step tag (grows by one per exchanged step, never reused)
+    unsigned* err;          // device flag raised when a peer never arrived
+};
+
 struct PSlotH { int role, idx; float lo, span, fixedv; };   // == eh::PSlot (kept POD here: this header is host-only)
 
 struct WideModel {          // filled by eh_lib's planner from the model descriptor
@@ -46,7 +53,10 @@ public:
     // one optimiser step (apply = 1) or loss + gradient only (apply = 0) on `B` samples rec[idx[.]];
     // grad: [nflat] device buffer receiving dL/dflat; loss_out: device (or pinned host) float
     cudaError_t step(const float* rec, const int* idx, long long rec_base, int B, const float* bscal, float* pblock, float* m,
-                     float* v, void* ost, float* grad, float* loss_out, int apply, cudaStream_t st);
+                     float* v, void* ost, float* grad, float* loss_out, int apply, cudaStream_t st, const WideDp* dp = nullptr);
+    // bytes of the exchange block a rank exposes in data-parallel mode: [2][xlen] floats + flags
+    size_t dp_block_bytes() const { return (size_t)2 * dp_xlen() * sizeof(float) + 256; }
+    int dp_xlen() const { return (m_.nflat + 16 + 31) / 32 * 32; }
     // test-mode forward of rows [row0, row0 + B) of a split: yhat / parout nullable device buffers with leading
     // dimension ldy; evalstat_dev: [T * 8] doubles, ACCUMULATED into (caller zeroes)
     cudaError_t eval_rows(const float* rec, long long nrec, long long row0, int Bvalid, const float* bscal, const float* pblock,

@@ -411,6 +411,8 @@ struct FinArgs {
     PSlot slot[MAXPS];
     const int* slot_of_flat;
     int* skip_out;                                // 1: all-masked batch (epoch.jl:17-19)
+    int dp;                                       // data parallel: the sums are per-rank; write the loss sums behind the
+                                                  // gradient (grad[nflat + t]) and leave loss / skip to k_wide_allreduce
 };
 
 // number of flat entries k_wide_gradfin produces: W_1 + b_1 (contiguous), b_2 .. b_NH, then everything from the output
@@ -445,10 +447,15 @@ __global__ void __launch_bounds__(256) k_wide_gradfin(const FinArgs a)
         L += (a.loss_kind[t] == LOSS_NSELOSS) ? acc / ss : (a.loss_kind[t] == LOSS_RMSE ? sqrtf(acc / n) : acc / n);
     }
     if (a.agg_mean) L /= (float)a.T;
+    if (a.dp) post = 1.f;   // rmse is refused in data-parallel mode
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        if (a.loss_out) *a.loss_out = ntot == 0.f ? __int_as_float(0x7fc00000) : L;
-        *a.skip_out = ntot == 0.f;
-        for (int t = 0; t < MAXT; t++) a.stats[t] = s_loss[t];
+        if (a.dp) {
+            for (int t = 0; t < MAXT; t++) a.grad[a.d.nflat + t] = s_loss[t];
+        } else {
+            if (a.loss_out) *a.loss_out = ntot == 0.f ? __int_as_float(0x7fc00000) : L;
+            *a.skip_out = ntot == 0.f;
+            for (int t = 0; t < MAXT; t++) a.stats[t] = s_loss[t];
+        }
     }
     const int q = blockIdx.x * 32 + (threadIdx.x >> 3), zl = threadIdx.x & 7;
     const int nq = gradfin_count(a.d);
@@ -497,6 +504,70 @@ __global__ void __launch_bounds__(256) k_wide_gradfin(const FinArgs a)
             s *= a.slot[phi_slot].span * sg * (1.f - sg);
         }
         a.grad[p] = s * post;
+    }
+}
+
+// ---- data parallel (one process per GPU): gradient all-reduce over NVLink peer memory ----
+// Every rank exposes [2 parities][xlen] floats (flat gradient, then MAXT loss sums) and two flags through CUDA IPC.
+// A rank publishes "my vector of step `tag` is complete" with a system-scope release store of its flag; every CTA
+// waits for all ranks' flags, then sums its slice of the vector over the ranks IN RANK ORDER straight out of the
+// peers' memory (bit-identical result everywhere, no NCCL, no second pass).  Double buffering by step parity is
+// enough: a rank can publish step s+2 only after it has seen every peer's step s+1 flag, which a peer raises after
+// it has finished reading step s.
+struct AllredArgs {
+    float* peer[EH_MAX_WORLD];   // rank r's exchange block as mapped here
+    int world, rank, par;
+    int xlen, nflat;
+    unsigned tag;
+    float* grad_out;             // [nflat] summed gradient
+    float* stats;                // [MAXT] summed loss sums
+    float* loss_out;             // nullable
+    int* skip_out;
+    const float* bscal;          // row of the GLOBAL batch
+    int T, agg_mean;
+    int loss_kind[MAXT];
+    unsigned* err;
+};
+__device__ __forceinline__ unsigned* allred_flag(float* block, int xlen, int par)
+{
+    return reinterpret_cast<unsigned*>(block + 2 * (size_t)xlen) + 16 * par;
+}
+__global__ void __launch_bounds__(256) k_wide_allreduce(const AllredArgs a)
+{
+    if (threadIdx.x == 0) {
+        if (blockIdx.x == 0) {
+            __threadfence_system();   // this rank's gradient kernels have completed: make their writes visible to peers
+            asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(allred_flag(a.peer[a.rank], a.xlen, a.par)), "r"(a.tag) : "memory");
+        }
+        for (int r = 0; r < a.world; r++) {
+            const unsigned* f = allred_flag(a.peer[r], a.xlen, a.par);
+            unsigned v, spins = 0;
+            do {
+                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+                if (v != a.tag && ++spins > (1u << 24)) { *a.err = 1; break; }
+            } while (v != a.tag);
+        }
+    }
+    __syncthreads();
+    const size_t off = (size_t)a.par * a.xlen;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < a.nflat; p += gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int r = 0; r < a.world; r++) s += __ldcv(a.peer[r] + off + p);
+        a.grad_out[p] = s;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        float L = 0.f, ntot = 0.f;
+        for (int t = 0; t < a.T; t++) {
+            float acc = 0.f;
+            for (int r = 0; r < a.world; r++) acc += __ldcv(a.peer[r] + off + a.nflat + t);
+            a.stats[t] = acc;
+            const float n = a.bscal[BS_N + t], ss = a.bscal[BS_SS + t];
+            ntot += n;
+            L += (a.loss_kind[t] == LOSS_NSELOSS) ? acc / ss : acc / n;
+        }
+        if (a.agg_mean) L /= (float)a.T;
+        if (a.loss_out) *a.loss_out = ntot == 0.f ? __int_as_float(0x7fc00000) : L;
+        *a.skip_out = ntot == 0.f;
     }
 }
 

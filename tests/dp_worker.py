@@ -119,6 +119,51 @@ def main():
                 assert abs(float(ps[-1]) - float(ref[-1])) <= 2e-4, (ps[-1], ref[-1])
                 print("DP_NCCL_STATS_OK", losses[:3], want[:3])
             sess.close()
+            # ---- third scenario: wide chain (bf16 tcgen05 path), two targets, PerTarget(nseLoss, mse): the 0.2 M-entry
+            # gradient is all-reduced over NVLink peer memory, the batch statistics are global ----
+            def expo2(n, seed):
+                rg = np.random.default_rng(seed)
+                T = rg.random(n) * 40 - 10
+                SM = rg.random(n) * 0.8 + 0.1
+                resp = 1.1 * np.exp(-8.0 * (SM - 0.6) ** 2) * np.exp(0.07 * T)
+                return {k: v.astype(np.float32) for k, v in dict(
+                    T=T, SM=SM, Resp_obs=resp + rg.standard_normal(n) * 0.05 * resp.mean(),
+                    Resp_obs2=2.0 * resp + rg.standard_normal(n) * 0.05 * resp.mean()).items()}
+            model3 = eh.constructHybridModel({"Resp0": ["SM"]}, ["T"], ["Resp_obs", "Resp_obs2"], eh.Expo_resp_model2,
+                                             dict(k=(0.01, 0.0, 0.2), Resp0=(2.0, 0.0, 8.0)), ["k"],
+                                             hidden_layers=[256, 256], activation="tanh", scale_nn_outputs=False)
+            nl3, B3, st3 = 4096, 1024, 8
+            shards3 = [eh.prepare_data(model3, expo2(nl3, 400 + r)) for r in range(world)]
+            perms3 = [np.random.default_rng(500 + r).permutation(nl3) for r in range(world)]
+            X3 = np.concatenate([s[0][0] for s in shards3])
+            f3 = {"T": np.concatenate([s[0][1]["T"] for s in shards3])}
+            y3 = {t: np.concatenate([s[1][t] for s in shards3]) for t in model3.targets}
+            loss3 = eh.PerTarget("nseLoss", "mse")
+            o3 = orc.Oracle(model3, training_loss=loss3, opt=eh.Adam(0.001))
+            flat3 = model3.initialparameters(np.random.default_rng(6))
+            xf, y = shards3[rank]
+            sess = eh.FusedSession(model3, training_loss=loss3, opt=eh.Adam(0.001), device=local)
+            sess.upload(0, xf, y)
+            sess.set_params(flat3)
+            sess.comm_init(rank, world, dist)
+            sess.set_perm(perms3[rank])
+            sess.dp_exchange_batch_stats(B3, dist)
+            dist.barrier()
+            losses = sess.run_steps(B3, 0, st3)
+            ps = sess.get_params()
+            allps = [None] * world
+            dist.all_gather_object(allps, ps.tobytes())
+            if rank == 0:
+                assert all(b == allps[0] for b in allps), "replicas diverged (wide path)"
+                ref = flat3.copy()
+                want = []
+                for s in range(st3):
+                    gi = global_batch_indices(perms3, [nl3] * world, B3, s % (nl3 // B3))
+                    want.append(o3.train_steps(ref, (X3, f3), y3, gi, world * B3)[0])
+                np.testing.assert_allclose(losses, np.array(want), rtol=5e-2)   # bf16 tolerance (tests/test_gpu_wide.py)
+                assert abs(float(ps[-1]) - float(ref[-1])) <= 2e-2, (ps[-1], ref[-1])
+                print("DP_NCCL_WIDE_OK", losses[:3], want[:3])
+            sess.close()
     dist.destroy_process_group()
 
 
