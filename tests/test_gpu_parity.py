@@ -214,6 +214,32 @@ def test_persistent_kernel_matches_step_kernels(eh, orc):
     assert np.array_equal(out[4][0], out[5][0]) and np.array_equal(out[4][1], out[7][1])
 
 
+@pytest.mark.parametrize("B", [8192, 1000])
+def test_step_host_async_stream_equals_epoch(eh, orc, B):
+    """streaming host batches (collect_dim_data |> gdev per step, src/training/epoch.jl:1-11) == the resident path
+    on the same batches: per-step losses and trained parameters; NaN targets exercise the per-batch counts"""
+    nb = 19
+    model, xf, y, flat, sess, o, rng = _setup(eh, orc, lambda e: rbq10_model(e), lambda: make_synth(nb * B + 77, nan_frac=0.03), "mse", "sum")
+    n = xf[0].shape[0]
+    perm = rng.permutation(n)[: nb * B]
+    want = sess.epoch(perm, B)
+    p_want = sess.get_params()
+    sess.set_params(flat)
+    sess.set_opt_state(None, None, 0)
+    losses = sess.pinned(np.zeros(nb, dtype=np.float32))
+    keep = []
+    for k in range(nb):
+        idx = perm[k * B:(k + 1) * B]
+        hb = sess.host_batch(sess.pinned(xf[0][idx]), [sess.pinned(xf[1]["ta"][idx])], [sess.pinned(y["reco"][idx])])
+        keep.append(hb)
+        sess.step_host_async(hb, losses, k)
+    sess.sync()
+    np.testing.assert_allclose(np.asarray(losses), want, rtol=2e-6)
+    np.testing.assert_allclose(sess.get_params(), p_want, rtol=0, atol=2e-6)
+    assert sess.get_opt_state()[2] == nb
+    sess.close()
+
+
 def test_unsupported_models_fail_loudly(eh):
     from easyhybrid_b200 import _abi
 
