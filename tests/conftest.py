@@ -63,6 +63,25 @@ def expo_model(eh, activation="sigmoid", scale=False, bn=False):
                                    input_batchnorm=bn)
 
 
+def make_expo2(n=500, seed=2314, nan_frac=0.0):
+    """Expo recipe with a second target = 2 x first + noise (configuration C5)."""
+    rng = np.random.default_rng(seed)
+    T = rng.random(n) * 40 - 10
+    SM = rng.random(n) * 0.8 + 0.1
+    resp = 1.1 * np.exp(-8.0 * (SM - 0.6) ** 2) * np.exp(0.07 * T)
+    obs = resp + rng.standard_normal(n) * 0.05 * resp.mean()
+    obs2 = 2.0 * resp + rng.standard_normal(n) * 0.05 * resp.mean()
+    if nan_frac:
+        obs2[rng.random(n) < nan_frac] = np.nan
+    return {k: v.astype(np.float32) for k, v in dict(T=T, SM=SM, Resp_obs=obs, Resp_obs2=obs2).items()}
+
+
+def expo2_model(eh, hidden=(16, 16), activation="tanh", scale=False):
+    return eh.constructHybridModel({"Resp0": ["SM"]}, ["T"], ["Resp_obs", "Resp_obs2"], eh.Expo_resp_model2,
+                                   dict(k=(0.01, 0.0, 0.2), Resp0=(2.0, 0.0, 8.0)), ["k"],
+                                   hidden_layers=list(hidden), activation=activation, scale_nn_outputs=scale)
+
+
 def linear_model(eh, two=False, activation="relu"):
     fn = eh.LinearModel2 if two else eh.LinearModel
     targets = ["var1", "var2"] if two else ["obs"]

@@ -54,6 +54,9 @@ def test_process_model_tracing_and_builtin_match(eh):
     assert eh.build_desc(expo_model(eh)).desc.process_model == _abi.PM["EXPO"]
     assert eh.build_desc(linear_model(eh)).desc.process_model == _abi.PM["LINEAR"]
     assert eh.build_desc(linear_model(eh, two=True)).desc.process_model == _abi.PM["LINEAR2"]
+    from conftest import expo2_model
+    d2 = eh.build_desc(expo2_model(eh, hidden=(512, 512, 512))).desc
+    assert d2.process_model == _abi.PM["EXPO2"] and d2.n_targ == 2 and d2.chains[0].n_hidden == 3
 
     def other(*, ta, Q10, rb):
         return {"reco": rb * np.exp(Q10) + np.sqrt(ta * ta)}
