@@ -56,6 +56,8 @@ cudaError_t gemm_prepare()
     if ((e = cudaFuncSetAttribute(k_wide_gemm<GEMM_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(GEMM_FWD))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_wide_gemm<GEMM_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(GEMM_BWD))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_wide_gemm<GEMM_WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(GEMM_WGRAD))) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_wide_gemm_p<GEMM_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, PG_SMEM)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_wide_gemm_p<GEMM_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, PG_SMEM)) != cudaSuccess) return e;
     done = true;
     return cudaSuccess;
 }
@@ -80,6 +82,38 @@ cudaError_t gemm_bwd(const CUtensorMap& tmD, const CUtensorMap& tmWt, int M, int
     k_wide_gemm<GEMM_BWD><<<dim3(M / BM, N / gemm_bn(GEMM_BWD), 1), GEMM_THREADS, gemm_smem(GEMM_BWD), st>>>(tmD, tmWt, g);
     return cudaGetLastError();
 }
+// persistent forms (one CTA per SM, 128 x 256 tiles, double-buffered accumulator); tmW / tmWt must be built with
+// box rows = PG_BN
+int persistent_grid(int M, int N)
+{
+    static int nsm = 0;
+    if (!nsm) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int tiles = (M / BM) * (N / PG_BN);
+    return tiles < nsm ? tiles : nsm;
+}
+cudaError_t gemm_fwd_p(const CUtensorMap& tmA, const CUtensorMap& tmW, int M, int N, int K, const float* bias, int act,
+                       __nv_bfloat16* out, cudaStream_t st)
+{
+    GemmArgs g{};
+    g.M = M; g.N = N; g.K = K; g.ksplits = 1; g.act = act; g.bias = bias; g.out16 = out;
+    k_wide_gemm_p<GEMM_FWD><<<persistent_grid(M, N), PG_THREADS, PG_SMEM, st>>>(tmA, tmW, g);
+    return cudaGetLastError();
+}
+cudaError_t gemm_bwd_p(const CUtensorMap& tmD, const CUtensorMap& tmWt, int M, int N, int K, const __nv_bfloat16* aux, int act,
+                       __nv_bfloat16* out, cudaStream_t st, float* colsum, const float* xb, const float* bscal, int R4, int P1,
+                       int use_bn)
+{
+    GemmArgs g{};
+    g.M = M; g.N = N; g.K = K; g.ksplits = 1; g.act = act; g.aux = aux; g.out16 = out;
+    g.colsum = colsum; g.xb = xb; g.bscal = bscal; g.R4 = R4; g.P1 = P1; g.use_bn = use_bn;
+    k_wide_gemm_p<GEMM_BWD><<<persistent_grid(M, N), PG_THREADS, PG_SMEM, st>>>(tmD, tmWt, g);
+    return cudaGetLastError();
+}
+
 // partial[z] = D[rows z]^T A[rows z]: D [Kall x M] bf16, A [Kall x N] bf16 (batch rows), ksplits slices of Kall
 cudaError_t gemm_wgrad(const CUtensorMap& tmD, const CUtensorMap& tmA, int M, int N, int Kall, int ksplits, float* partial,
                        cudaStream_t st)
@@ -140,6 +174,7 @@ WideNet* WideNet::create(const WideModel& m, char* err, size_t errlen)
 {
     WideNet* w = new WideNet();
     w->m_ = m;
+    w->persist_ = getenv("EH_WIDE_NO_PERSIST") == nullptr;   // persistent forward / backward-data GEMMs (default)
     auto bail = [&](const char* what, cudaError_t e) -> WideNet* {
         snprintf(err, errlen, "wide path: %s: %s", what, cudaGetErrorString(e));
         delete w;
@@ -156,8 +191,9 @@ WideNet* WideNet::create(const WideModel& m, char* err, size_t errlen)
     for (int l = 2; l <= m.NH; l++) {
         if ((e = cudaMalloc(&w->Wf_[l - 1], HH * 2)) != cudaSuccess) return bail("cudaMalloc", e);
         if ((e = cudaMalloc(&w->Wb_[l - 1], HH * 2)) != cudaSuccess) return bail("cudaMalloc", e);
-        if (!make_map_bf16(&w->tmWf_[l - 1], w->Wf_[l - 1], m.H, m.H, m.H, gemm_bn(GEMM_FWD)) ||
-            !make_map_bf16(&w->tmWb_[l - 1], w->Wb_[l - 1], m.H, m.H, m.H, gemm_bn(GEMM_BWD))) {
+        const int bn = w->persist_ ? PG_BN : gemm_bn(GEMM_FWD);
+        if (!make_map_bf16(&w->tmWf_[l - 1], w->Wf_[l - 1], m.H, m.H, m.H, bn) ||
+            !make_map_bf16(&w->tmWb_[l - 1], w->Wb_[l - 1], m.H, m.H, m.H, bn)) {
             snprintf(err, errlen, "wide path: cuTensorMapEncodeTiled failed for a weight image");
             delete w;
             return nullptr;
@@ -247,8 +283,10 @@ cudaError_t WideNet::forward(const float* rec, const int* idx, long long rec_bas
     const int rows_per_cta = (256 / (H / 8)) * FIRST_ROWS;
     k_wide_first<<<(unsigned)((B + rows_per_cta - 1) / rows_per_cta), 256, 0, st>>>(xb_, pblock, bscal, m_.use_bn, d, B, m_.act, A_[0]);
     WN(cudaGetLastError());
-    for (int l = 2; l <= m_.NH; l++)
-        WN(gemm_fwd(tmA_k_[l - 2], tmWf_[l - 1], B, H, H, pblock + m_.b_off[l - 1], m_.act, A_[l - 1], st));
+    for (int l = 2; l <= m_.NH; l++) {
+        if (persist_) WN(gemm_fwd_p(tmA_k_[l - 2], tmWf_[l - 1], B, H, H, pblock + m_.b_off[l - 1], m_.act, A_[l - 1], st));
+        else WN(gemm_fwd(tmA_k_[l - 2], tmWf_[l - 1], B, H, H, pblock + m_.b_off[l - 1], m_.act, A_[l - 1], st));
+    }
     return cudaSuccess;
 }
 
@@ -280,8 +318,12 @@ cudaError_t WideNet::step(const float* rec, const int* idx, long long rec_base, 
         WN(cudaGetLastError());
         // backward data; its epilogue also leaves the 32-row column sums of D_{l-1} (bias gradient of layer l-1 and,
         // for layer 1, the x-weighted sums = its weight gradient)
-        WN(gemm_bwd(tmD_k_[cur], tmWb_[l - 1], B, H, H, A_[l - 2], m_.act, D_[nxt], st, colsum_[l - 2], xb_, bscal, m_.R4,
-                    (l - 1 == 1) ? m_.P : 0, m_.use_bn));
+        if (persist_)
+            WN(gemm_bwd_p(tmD_k_[cur], tmWb_[l - 1], B, H, H, A_[l - 2], m_.act, D_[nxt], st, colsum_[l - 2], xb_, bscal, m_.R4,
+                          (l - 1 == 1) ? m_.P : 0, m_.use_bn));
+        else
+            WN(gemm_bwd(tmD_k_[cur], tmWb_[l - 1], B, H, H, A_[l - 2], m_.act, D_[nxt], st, colsum_[l - 2], xb_, bscal, m_.R4,
+                        (l - 1 == 1) ? m_.P : 0, m_.use_bn));
     }
     FinArgs fa{};
     fa.d = d; fa.head_partial = head_partial_; fa.n_head = n_head_; fa.n_slab = n_slab_;
@@ -375,8 +417,10 @@ extern "C" eh_status eh_selftest_wide_gemm(int32_t mode, int32_t M, int32_t N, i
                                            const uint16_t* A, const uint16_t* B, const float* bias, const uint16_t* aux,
                                            void* out, int32_t device, float* ms_out)
 {
-    if (!A || !B || !out || mode < 0 || mode > 2) return EH_EINVAL;
-    if (M % BM || N % gemm_bn(mode) || ksplits < 1) return EH_EINVAL;
+    if (!A || !B || !out || mode < 0 || mode > 4) return EH_EINVAL;
+    const bool pers = mode >= 3;   // 3 / 4: the persistent forms of 0 / 1
+    if (pers) mode -= 3;
+    if (M % BM || N % (pers ? PG_BN : gemm_bn(mode)) || ksplits < 1) return EH_EINVAL;
     WCK(cudaSetDevice(device));
     cudaDeviceProp prop;
     WCK(cudaGetDeviceProperties(&prop, device));
@@ -404,7 +448,7 @@ extern "C" eh_status eh_selftest_wide_gemm(int32_t mode, int32_t M, int32_t N, i
     else WCK(cudaMalloc(&dO16, (size_t)M * N * 2));
     CUtensorMap tmA, tmB;
     bool ok;
-    if (!wg) ok = make_map_bf16(&tmA, dA, K, M, K, BM) && make_map_bf16(&tmB, dB, K, N, K, gemm_bn(mode));
+    if (!wg) ok = make_map_bf16(&tmA, dA, K, M, K, BM) && make_map_bf16(&tmB, dB, K, N, K, pers ? PG_BN : gemm_bn(mode));
     else ok = make_map_bf16(&tmA, dA, M, K, M, BK) && make_map_bf16(&tmB, dB, N, K, N, BK);
     if (!ok) return EH_ECUDA;
     cudaEvent_t e0, e1;
@@ -413,7 +457,9 @@ extern "C" eh_status eh_selftest_wide_gemm(int32_t mode, int32_t M, int32_t N, i
     const int reps = ms_out ? 5 : 1;
     for (int r = 0; r < reps; r++) {
         if (r == reps - 1) WCK(cudaEventRecord(e0));
-        if (mode == GEMM_FWD) WCK(gemm_fwd(tmA, tmB, M, N, K, dBias, act, dO16, 0));
+        if (mode == GEMM_FWD && pers) WCK(gemm_fwd_p(tmA, tmB, M, N, K, dBias, act, dO16, 0));
+        else if (mode == GEMM_BWD && pers) WCK(gemm_bwd_p(tmA, tmB, M, N, K, dAux, act, dO16, 0, nullptr, nullptr, nullptr, 0, 0, 0));
+        else if (mode == GEMM_FWD) WCK(gemm_fwd(tmA, tmB, M, N, K, dBias, act, dO16, 0));
         else if (mode == GEMM_BWD) WCK(gemm_bwd(tmA, tmB, M, N, K, dAux, act, dO16, 0, nullptr, nullptr, nullptr, 0, 0, 0));
         else WCK(gemm_wgrad(tmA, tmB, M, N, K, ksplits, dO32, 0));
         if (r == reps - 1) WCK(cudaEventRecord(e1));

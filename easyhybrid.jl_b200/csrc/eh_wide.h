@@ -71,6 +71,7 @@ private:
                         const float* pblock, cudaStream_t st);
     WideModel m_{};
     int cap_ = 0, mapB_ = 0, n_head_ = 0, n_slab_ = 0, ksplit_ = 1;
+    bool persist_ = true;
     float* xb_ = nullptr;
     __nv_bfloat16* A_[8] = {nullptr};
     __nv_bfloat16* D_[2] = {nullptr, nullptr};

@@ -397,5 +397,248 @@ k_wide_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
 }
 
+
+// ---- persistent forward / backward-data GEMM -------------------------------------------------------------------------
+// One CTA per SM walks the 128 x 256 output tiles (tile t = blockIdx.x + i * gridDim.x).  Two accumulator buffers in
+// tensor memory (2 x 256 columns) let the MMA warp start tile i+1 while the EIGHT epilogue warps (two per TMEM lane
+// quarter, 128 columns each) drain tile i; the TMA producer simply keeps the 3-stage ring full across tile borders.
+// Barriers: full/empty per stage (TMA <-> MMA), tmem_full/tmem_empty per accumulator buffer (MMA <-> epilogue).
+constexpr int PG_BN = 256, PG_STAGES = 3, PG_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int PG_STAGE_BYTES = (BM + PG_BN) * BK * 2;          // 48 KB
+constexpr int PG_OPITCH = 128 * 2 + 16;                        // staged output row of one epilogue warp: 128 bf16 + pad
+constexpr int PG_STG_BYTES = 8 * 32 * PG_OPITCH;               // 69 632
+constexpr int PG_SIDE_BYTES = 2 * PG_BN * 4;                   // bias double buffer
+constexpr int PG_SMEM = PG_STAGES * PG_STAGE_BYTES + PG_STG_BYTES + PG_SIDE_BYTES + 1024 + 256;
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(PG_THREADS, 1)
+k_wide_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g)
+{
+    static_assert(MODE == GEMM_FWD || MODE == GEMM_BWD, "persistent form serves forward and backward-data");
+    constexpr int BN = PG_BN, STAGES = PG_STAGES, STAGE_BYTES = PG_STAGE_BYTES, A_STAGE_BYTES = BM * BK * 2;
+    constexpr int STG_OFF = STAGES * STAGE_BYTES, SIDE_OFF = STG_OFF + PG_STG_BYTES, BAR_OFF = SIDE_OFF + PG_SIDE_BYTES;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* gen_base = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bar0 = base + BAR_OFF;
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int b) { return bar0 + 8u * (2 * STAGES + b); };
+    auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * STAGES + 2 + b); };
+    const uint32_t tmem_slot = bar0 + 8u * (2 * STAGES + 4);
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + BAR_OFF + 8 * (2 * STAGES + 4));
+    float* s_bias = reinterpret_cast<float*>(gen_base + SIDE_OFF);                 // [2][BN]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_n = g.N / BN, num_tiles = (g.M / BM) * num_n;
+    const int nkb = g.K / BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int b = 0; b < 2; b++) {
+            mbar_init(tfull_bar(b), 1);
+            mbar_init(tempty_bar(b), 8);   // one arrival per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer: one continuous ring over all tiles of this CTA =====
+            int kbc = 0;
+            bool pok = true;
+            for (int t = blockIdx.x; t < num_tiles && pok; t += gridDim.x) {
+                const int m0 = (t / num_n) * BM, n0 = (t % num_n) * BN;
+                for (int kb = 0; kb < nkb && pok; kb++, kbc++) {
+                    const int s = kbc % STAGES;
+                    pok = mbar_wait(empty_bar(s), ((kbc / STAGES) & 1) ^ 1);
+                    if (!pok) break;
+                    const uint32_t sa = base + s * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+                    mbar_expect_tx(full_bar(s), STAGE_BYTES);
+                    tma_load_2d(sa, &tmA, kb * BK, m0, full_bar(s));
+                    tma_load_2d(sb, &tmB, kb * BK, n0, full_bar(s));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+            int kbc = 0, it = 0;
+            bool ok = true;
+            for (int t = blockIdx.x; t < num_tiles && ok; t += gridDim.x, it++) {
+                const int ab = it & 1;
+                ok = mbar_wait(tempty_bar(ab), ((it >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator buffer
+                tc_fence_after();
+                const uint32_t acc = tmem_base + (uint32_t)(ab * BN);
+                for (int kb = 0; kb < nkb && ok; kb++, kbc++) {
+                    const int s = kbc % STAGES;
+                    ok = mbar_wait(full_bar(s), (kbc / STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t sa = base + s * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; k++)
+                        tc_mma_bf16(acc, umma_desc(sa + k * UMMA_K * 2, 0, 1024), umma_desc(sb + k * UMMA_K * 2, 0, 1024), idesc,
+                                    (kb | k) ? 1u : 0u);
+                    tc_commit(empty_bar(s));
+                }
+                tc_commit(tfull_bar(ab));
+            }
+        }
+    } else {
+        // ===== epilogue: warps 2..9; TMEM lane quarter q = warp % 4, column half h = (warp - 2) / 4 =====
+        const int q = warp & 3, h = (warp - 2) >> 2;
+        const int et = (warp - 2) * 32 + lane;            // 0..255 among the epilogue threads
+        uint8_t* stg = gen_base + STG_OFF + (warp - 2) * (32 * PG_OPITCH);
+        int it = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, it++) {
+            const int ab = it & 1;
+            const int m0 = (t / num_n) * BM, n0 = (t % num_n) * BN;
+            const int row = m0 + q * 32 + lane;
+            const int ncol0 = n0 + h * 128;               // first output column of this warp
+            float* bias = s_bias + ab * BN;
+            uint4 apre[2][4];                              // BWD: activation chunks, two ahead
+            const uint4* ap = reinterpret_cast<const uint4*>(g.aux + (size_t)row * g.N + ncol0);
+            if (MODE == GEMM_FWD) {
+                bias[et] = __ldg(g.bias + n0 + et);
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            } else {
+#pragma unroll
+                for (int u = 0; u < 2; u++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) apre[u][j] = __ldg(ap + u * 4 + j);
+            }
+            mbar_wait(tfull_bar(ab), (it >> 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int cc = 0; cc < 4; cc++) {
+                const int c = cc * 32;
+                uint32_t r[32];
+                tc_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + h * 128 + c), r);
+                uint32_t o[16];
+                if (MODE == GEMM_FWD) {
+                    const float4* b4 = reinterpret_cast<const float4*>(bias + h * 128 + c);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const float4 b = b4[j];
+                        o[2 * j] = pack_bf16(act1(g.act, __uint_as_float(r[4 * j]) + b.x), act1(g.act, __uint_as_float(r[4 * j + 1]) + b.y));
+                        o[2 * j + 1] = pack_bf16(act1(g.act, __uint_as_float(r[4 * j + 2]) + b.z), act1(g.act, __uint_as_float(r[4 * j + 3]) + b.w));
+                    }
+                } else {
+                    uint4 cur[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) cur[j] = apre[cc & 1][j];
+                    if (cc + 2 < 4) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) apre[cc & 1][j] = __ldg(ap + (cc + 2) * 4 + j);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const uint32_t aw[4] = {cur[j].x, cur[j].y, cur[j].z, cur[j].w};
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            const float2 af = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw[e]));
+                            o[4 * j + e] = pack_bf16(__uint_as_float(r[8 * j + 2 * e]) * dact1(g.act, af.x),
+                                                     __uint_as_float(r[8 * j + 2 * e + 1]) * dact1(g.act, af.y));
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    *reinterpret_cast<uint4*>(stg + lane * PG_OPITCH + ((c >> 3) + j) * 16) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+            }
+            // this warp is done with the accumulator buffer: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(ab));
+            // BWD: column sums over this warp's 32 rows, straight from the staged strip (lane l owns columns 4l .. 4l+3)
+            float cs[4] = {0.f, 0.f, 0.f, 0.f}, cw[4][4];
+            const bool want_cs = MODE == GEMM_BWD && g.colsum != nullptr;
+            if (want_cs) {
+                float xr[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int p = 0; p < 4; p++) {
+                    cw[p][0] = cw[p][1] = cw[p][2] = cw[p][3] = 0.f;
+                    if (p < g.P1) {
+                        float x = g.xb[(size_t)row * g.R4 + p];
+                        if (g.use_bn) x = (x - g.bscal[BS_BN_OFF + 2 * p]) * g.bscal[BS_BN_OFF + 2 * p + 1];
+                        xr[p] = x;
+                    }
+                }
+#pragma unroll
+                for (int r2 = 0; r2 < 32; r2++) {
+                    const uint2 v = *reinterpret_cast<const uint2*>(stg + r2 * PG_OPITCH + lane * 8);
+                    const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.x));
+                    const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.y));
+                    cs[0] += f0.x; cs[1] += f0.y; cs[2] += f1.x; cs[3] += f1.y;
+#pragma unroll
+                    for (int p = 0; p < 4; p++) {
+                        if (p < g.P1) {
+                            const float x = __shfl_sync(0xffffffffu, xr[p], r2);
+                            cw[p][0] = fmaf(f0.x, x, cw[p][0]); cw[p][1] = fmaf(f0.y, x, cw[p][1]);
+                            cw[p][2] = fmaf(f1.x, x, cw[p][2]); cw[p][3] = fmaf(f1.y, x, cw[p][3]);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            // 128 bf16 per row = 16 lanes of 16 bytes: two rows per instruction
+#pragma unroll 4
+            for (int r0 = 0; r0 < 32; r0 += 2) {
+                const int rr = r0 + (lane >> 4), cc2 = lane & 15;
+                const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * PG_OPITCH + cc2 * 16);
+                *(reinterpret_cast<uint4*>(g.out16 + (size_t)(m0 + q * 32 + rr) * g.N + ncol0) + cc2) = v;
+            }
+            __syncwarp();
+            if (want_cs) {
+                // the strip is free now: park this warp's sums in it, combine the four lane-quarter warps of each
+                // column half in a fixed order, one 128-row slab per tile goes out
+                float* mine = reinterpret_cast<float*>(stg);
+                *reinterpret_cast<float4*>(mine + lane * 4) = make_float4(cs[0], cs[1], cs[2], cs[3]);
+#pragma unroll
+                for (int p = 0; p < 4; p++)
+                    if (p < g.P1) *reinterpret_cast<float4*>(mine + (1 + p) * 128 + lane * 4) = make_float4(cw[p][0], cw[p][1], cw[p][2], cw[p][3]);
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                const int h2 = et >> 7, cl = et & 127;   // thread et owns output column et of the tile
+                for (int p = 0; p <= g.P1; p++) {
+                    float v = 0.f;
+#pragma unroll
+                    for (int qq = 0; qq < 4; qq++) {
+                        const int wi = 4 * h2 + ((qq + 2) & 3);   // epilogue warp with lane quarter qq and column half h2
+                        v += reinterpret_cast<const float*>(gen_base + STG_OFF + wi * (32 * PG_OPITCH))[p * 128 + cl];
+                    }
+                    g.colsum[((size_t)(m0 / BM) * (1 + g.P1) + p) * g.N + n0 + et] = v;
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");   // the strips are rewritten by the next tile
+            }
+            __syncwarp();   // the strip is rewritten by the next tile
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
 }  // namespace wide
 }  // namespace eh

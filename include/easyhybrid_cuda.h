@@ -297,7 +297,7 @@ eh_status eh_set_profiling(eh_ctx* ctx, int32_t on);
 
 /* diagnostics: runs one tcgen05 GEMM of the wide-hidden-layer path on host matrices (bf16 bit patterns) so that a
  * test harness can check the kernels in isolation.  mode 0: out = act(A B^T + bias), A [M x K], B [N x K];
- * mode 1: out = (A B^T) .* act'(aux), aux [M x N]; both write bf16 [M x N].  mode 2: out[z] = A_z^T B_z for the
+ * mode 1: out = (A B^T) .* act'(aux), aux [M x N]; both write bf16 [M x N].  modes 3 / 4: the persistent forms of 0 / 1.  mode 2: out[z] = A_z^T B_z for the
  * `ksplits` row slices of A [K x M], B [K x N]; writes fp32 [ksplits][M x N].  ms_out (nullable): device time.  */
 eh_status eh_selftest_wide_gemm(int32_t mode, int32_t M, int32_t N, int32_t K, int32_t ksplits, int32_t act,
                                 const uint16_t* A, const uint16_t* B, const float* bias, const uint16_t* aux,

@@ -21,8 +21,9 @@ def ptr(t):
 
 
 def run(mode, M, N, K, ks=1, act=1, time_it=False):
-    g = torch.Generator().manual_seed(1234 + mode)
-    if mode < 2:
+    g = torch.Generator().manual_seed(1234 + mode % 3)
+    base = mode - 3 if mode >= 3 else mode
+    if base < 2:
         A = bf(torch.randn(M, K, generator=g) * 0.5)
         B = bf(torch.randn(N, K, generator=g) * (1.0 / K ** 0.5))
     else:
@@ -31,7 +32,7 @@ def run(mode, M, N, K, ks=1, act=1, time_it=False):
     bias = torch.randn(N, generator=g) * 0.1
     aux = bf(torch.tanh(torch.randn(M, N, generator=g)))
     ms = C.c_float(0)
-    if mode == 2:
+    if base == 2:
         out = torch.empty(ks, M, N, dtype=torch.float32)
     else:
         out = torch.empty(M, N, dtype=torch.bfloat16)
@@ -40,12 +41,12 @@ def run(mode, M, N, K, ks=1, act=1, time_it=False):
     assert st == 0, f"status {st}"
     dev = "cuda"
     Af, Bf = A.float().to(dev), B.float().to(dev)
-    if mode == 0:
+    if base == 0:
         z = Af @ Bf.T + bias.to(dev)
         ref = torch.tanh(z) if act == 1 else (torch.sigmoid(z) if act == 2 else z)
         got = out.float().to(dev)
         tol = 1e-2
-    elif mode == 1:
+    elif base == 1:
         a = aux.float().to(dev)
         ref = (Af @ Bf.T) * (1 - a * a)
         got = out.float().to(dev)
@@ -69,12 +70,17 @@ def main(perf=False):
     ok &= run(0, 512, 512, 512)
     ok &= run(0, 384, 256, 256, act=2)
     ok &= run(1, 512, 512, 512)
+    ok &= run(3, 256, 256, 128)
+    ok &= run(3, 2048, 512, 512)
+    ok &= run(4, 2048, 512, 512)
     ok &= run(2, 256, 256, 256, ks=1)
     ok &= run(2, 512, 512, 4096, ks=4)
     if perf:
         run(0, 65536, 512, 512, time_it=True)
         run(1, 65536, 512, 512, time_it=True)
         run(2, 512, 512, 65536, ks=16, time_it=True)
+        run(3, 65536, 512, 512, time_it=True)
+        run(4, 65536, 512, 512, time_it=True)
     print("WIDE GEMM", "OK" if ok else "FAILED")
     return ok
 
