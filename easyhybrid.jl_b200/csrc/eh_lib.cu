@@ -922,21 +922,25 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
     for (int l = 0; l < ch.n_hidden; l++) hmax = std::max(hmax, ch.hidden[l]);
     if (d->n_pm_args != 3 || d->pm_args[0].kind != 0 || d->pm_args[1].kind != 0 || d->pm_args[2].kind != 1)
         return fail(c, EH_EINVAL, "built-in process models take (param, param, forcing) arguments");
-    // wide chains (all hidden layers 256 or 512 wide): bf16 tcgen05 GEMM path
+    // Which path?  The exact-fp32 register-tile kernels exist for two hidden layers of width <= 32; every other chain
+    // (wider or deeper, up to 6 hidden layers of up to 512 units, padded to 256 / 512 internally) runs on the bf16
+    // tcgen05 GEMM path.
     bool wide = false;
-    if (hmax >= 256) {
-        bool same = true;
-        for (int l = 0; l < ch.n_hidden; l++) same &= (ch.hidden[l] == hmax);
-        if (!same ||
-            !eh::wide::WideNet::supported(ch.n_in, hmax, ch.n_hidden, ch.n_out, ch.activation, d->process_model))
+    const bool have_small = hmax <= 32 && find_variant(d->process_model, ch.n_in, ch.n_hidden, rup4(hmax), ch.n_out, ch.activation,
+                                                       d->scale_nn_outputs ? 1 : 0, 0) != nullptr;
+    if (!have_small) {
+        if (!eh::wide::WideNet::supported(ch.n_in, hmax, ch.n_hidden, ch.n_out, ch.activation, d->process_model))
             return fail(c, EH_EUNSUPPORTED,
-                        "wide chains need equal hidden widths of 256 or 512, 2..6 hidden layers, <= 4 inputs, <= 2 outputs and "
-                        "a tanh / sigmoid / relu activation (got n_in=%d hidden=%dx%d n_out=%d activation=%d)",
-                        ch.n_in, ch.n_hidden, hmax, ch.n_out, ch.activation);
+                        "no fused kernel for this chain: the register-tile kernels serve two hidden layers of width <= 32 (all "
+                        "activations, <= 12 inputs), the tensor-core path 2..6 hidden layers of width <= 512 with <= 4 inputs, "
+                        "<= 2 outputs and a tanh / sigmoid / relu activation (got process_model=%d n_in=%d hidden=%d x (<= %d) "
+                        "n_out=%d activation=%d scale_nn_outputs=%d)",
+                        d->process_model, ch.n_in, ch.n_hidden, hmax, ch.n_out, ch.activation, d->scale_nn_outputs);
         wide = true;
         Variant& wv = c->wide_var;
         memset(&wv, 0, sizeof wv);
-        wv.pm = d->process_model; wv.P = ch.n_in; wv.NH = ch.n_hidden; wv.H = hmax; wv.NOUT = ch.n_out; wv.act = ch.activation;
+        wv.pm = d->process_model; wv.P = ch.n_in; wv.NH = ch.n_hidden; wv.H = eh::wide::WideNet::padded_width(hmax);
+        wv.NOUT = ch.n_out; wv.act = ch.activation;
         wv.scale = d->scale_nn_outputs ? 1 : 0;
         wv.engine = 3; wv.chunk = 128;
         wv.F = 1; wv.NPS = 2;
@@ -1126,6 +1130,7 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
         eh::wide::WideModel& wm = c->wide_model;
         memset(&wm, 0, sizeof wm);
         wm.P = P; wm.H = H; wm.NH = NH; wm.NOUT = NOUT; wm.R4 = v->R4; wm.nflat = c->nflat; wm.ntheta = c->ntheta;
+        for (int l = 0; l < NH; l++) wm.hw[l] = ch.hidden[l];
         for (int l = 0; l < L; l++) { wm.w_off[l] = w_off[l]; wm.b_off[l] = b_off[l]; }
         wm.act = ch.activation; wm.scale = d->scale_nn_outputs ? 1 : 0; wm.pm = d->process_model;
         wm.T = v->T; wm.F = v->F; wm.NPS = v->NPS; wm.use_bn = c->use_bn; wm.agg_mean = c->agg_mean;

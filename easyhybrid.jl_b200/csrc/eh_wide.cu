@@ -148,7 +148,7 @@ WideDims dims_of(const WideModel& m)
 {
     WideDims d{};
     d.P = m.P; d.H = m.H; d.NH = m.NH; d.NOUT = m.NOUT; d.R4 = m.R4; d.nflat = m.nflat; d.ntheta = m.ntheta;
-    for (int i = 0; i < 8; i++) { d.w_off[i] = m.w_off[i]; d.b_off[i] = m.b_off[i]; }
+    for (int i = 0; i < 8; i++) { d.w_off[i] = m.w_off[i]; d.b_off[i] = m.b_off[i]; d.hw[i] = m.hw[i]; }
     return d;
 }
 }  // namespace
@@ -162,12 +162,12 @@ WideDims dims_of(const WideModel& m)
         }                                                                                              \
     } while (0)
 
-bool WideNet::supported(int P, int H, int NH, int NOUT, int act, int pm)
+bool WideNet::supported(int P, int hmax, int NH, int NOUT, int act, int pm)
 {
     if (P < 1 || P > 4 || NH < 2 || NH > 6 || NOUT < 1 || NOUT > 2) return false;
-    if (H != 256 && H != 512) return false;
+    if (hmax < 1 || hmax > 512) return false;
     if (act != ACT_TANH && act != ACT_SIGMOID && act != ACT_RELU && act != ACT_IDENTITY) return false;
-    return find_head(pm, NOUT, 0, H / 256) != nullptr;
+    return find_head(pm, NOUT, 0, padded_width(hmax) / 256) != nullptr;
 }
 
 WideNet* WideNet::create(const WideModel& m, char* err, size_t errlen)
@@ -191,6 +191,11 @@ WideNet* WideNet::create(const WideModel& m, char* err, size_t errlen)
     for (int l = 2; l <= m.NH; l++) {
         if ((e = cudaMalloc(&w->Wf_[l - 1], HH * 2)) != cudaSuccess) return bail("cudaMalloc", e);
         if ((e = cudaMalloc(&w->Wb_[l - 1], HH * 2)) != cudaSuccess) return bail("cudaMalloc", e);
+        if ((e = cudaMalloc(&w->Bp_[l - 1], (size_t)m.H * 4)) != cudaSuccess) return bail("cudaMalloc", e);
+        // padding (rows / columns / bias entries beyond the real widths) stays zero for good
+        cudaMemset(w->Wf_[l - 1], 0, HH * 2);
+        cudaMemset(w->Wb_[l - 1], 0, HH * 2);
+        cudaMemset(w->Bp_[l - 1], 0, (size_t)m.H * 4);
         const int bn = w->persist_ ? PG_BN : gemm_bn(GEMM_FWD);
         if (!make_map_bf16(&w->tmWf_[l - 1], w->Wf_[l - 1], m.H, m.H, m.H, bn) ||
             !make_map_bf16(&w->tmWb_[l - 1], w->Wb_[l - 1], m.H, m.H, m.H, bn)) {
@@ -214,6 +219,7 @@ WideNet::~WideNet()
         if (A_[i]) cudaFree(A_[i]);
         if (Wf_[i]) cudaFree(Wf_[i]);
         if (Wb_[i]) cudaFree(Wb_[i]);
+        if (Bp_[i]) cudaFree(Bp_[i]);
         if (colsum_[i]) cudaFree(colsum_[i]);
     }
     void* ps[] = {xb_, D_[0], D_[1], partial_, head_partial_, stats_, skip_, evalpart_};
@@ -265,7 +271,7 @@ cudaError_t WideNet::refresh_images(float* pblock, float* m, float* v, void* ost
     u.d = dims_of(m_);
     u.theta = pblock; u.m = m; u.v = v; u.ost = reinterpret_cast<OptState*>(ost);
     u.skip = skip_;
-    for (int l = 2; l <= m_.NH; l++) { u.Wf[l - 1] = Wf_[l - 1]; u.Wb[l - 1] = Wb_[l - 1]; }
+    for (int l = 2; l <= m_.NH; l++) { u.Wf[l - 1] = Wf_[l - 1]; u.Wb[l - 1] = Wb_[l - 1]; u.Bp[l - 1] = Bp_[l - 1]; }
     u.apply = 0;
     k_wide_update<<<(m_.nflat + 255) / 256, 256, 0, st>>>(u);
     WN(cudaGetLastError());
@@ -284,8 +290,8 @@ cudaError_t WideNet::forward(const float* rec, const int* idx, long long rec_bas
     k_wide_first<<<(unsigned)((B + rows_per_cta - 1) / rows_per_cta), 256, 0, st>>>(xb_, pblock, bscal, m_.use_bn, d, B, m_.act, A_[0]);
     WN(cudaGetLastError());
     for (int l = 2; l <= m_.NH; l++) {
-        if (persist_) WN(gemm_fwd_p(tmA_k_[l - 2], tmWf_[l - 1], B, H, H, pblock + m_.b_off[l - 1], m_.act, A_[l - 1], st));
-        else WN(gemm_fwd(tmA_k_[l - 2], tmWf_[l - 1], B, H, H, pblock + m_.b_off[l - 1], m_.act, A_[l - 1], st));
+        if (persist_) WN(gemm_fwd_p(tmA_k_[l - 2], tmWf_[l - 1], B, H, H, Bp_[l - 1], m_.act, A_[l - 1], st));
+        else WN(gemm_fwd(tmA_k_[l - 2], tmWf_[l - 1], B, H, H, Bp_[l - 1], m_.act, A_[l - 1], st));
     }
     return cudaSuccess;
 }
@@ -314,7 +320,7 @@ cudaError_t WideNet::step(const float* rec, const int* idx, long long rec_base, 
     for (int l = NH; l >= 2; l--) {
         const int cur = l & 1, nxt = (l - 1) & 1;
         WN(gemm_wgrad(tmD_mn_[cur], tmA_mn_[l - 2], H, H, B, ksplit_, partial_, st));
-        k_wide_wreduce<<<dim3(H / 32, H / 32), 256, 0, st>>>(partial_, ksplit_, H, grad + m_.w_off[l - 1]);
+        k_wide_wreduce<<<dim3(H / 32, H / 32), 256, 0, st>>>(partial_, ksplit_, H, m_.hw[l - 1], m_.hw[l - 2], grad + m_.w_off[l - 1]);
         WN(cudaGetLastError());
         // backward data; its epilogue also leaves the 32-row column sums of D_{l-1} (bias gradient of layer l-1 and,
         // for layer 1, the x-weighted sums = its weight gradient)
@@ -354,7 +360,7 @@ cudaError_t WideNet::step(const float* rec, const int* idx, long long rec_base, 
         for (int t = 0; t < 4; t++) u.loss_kind[t] = m_.loss_kind[t];
         u.opt_kind = m_.opt_kind; u.adamw_coupled = m_.adamw_coupled;
         u.eta = m_.eta; u.beta1 = m_.beta1; u.beta2 = m_.beta2; u.eps = m_.eps; u.lambda = m_.lambda;
-        for (int l = 2; l <= NH; l++) { u.Wf[l - 1] = Wf_[l - 1]; u.Wb[l - 1] = Wb_[l - 1]; }
+        for (int l = 2; l <= NH; l++) { u.Wf[l - 1] = Wf_[l - 1]; u.Wb[l - 1] = Wb_[l - 1]; u.Bp[l - 1] = Bp_[l - 1]; }
         u.apply = 1;
         k_wide_update<<<(m_.nflat + 255) / 256, 256, 0, st>>>(u);
         WN(cudaGetLastError());

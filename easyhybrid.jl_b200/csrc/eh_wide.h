@@ -28,7 +28,8 @@ struct WideDp {             // data-parallel state handed to WideNet::step
 struct PSlotH { int role, idx; float lo, span, fixedv; };   // == eh::PSlot (kept POD here: this header is host-only)
 
 struct WideModel {          // filled by eh_lib's planner from the model descriptor
-    int P, H, NH, NOUT, R4, nflat, ntheta;
+    int P, H, NH, NOUT, R4, nflat, ntheta;   // H: padded hidden width (256 / 512)
+    int hw[8];                               // real hidden widths (<= H)
     int w_off[8], b_off[8];
     int act, scale, pm, T, F, NPS, use_bn, agg_mean;
     int loss_kind[4];
@@ -43,7 +44,9 @@ struct WideModel {          // filled by eh_lib's planner from the model descrip
 // the wide-chain training step: owns activations / deltas / bf16 weight images / partial buffers
 class WideNet {
 public:
-    static bool supported(int P, int H, int NH, int NOUT, int act, int pm);
+    // hmax: widest hidden layer (padded up to 256 or 512 inside)
+    static bool supported(int P, int hmax, int NH, int NOUT, int act, int pm);
+    static int padded_width(int hmax) { return hmax <= 256 ? 256 : 512; }
     static WideNet* create(const WideModel& m, char* err, size_t errlen);
     ~WideNet();
     // largest batch the path accepts is bounded only by memory; B must be a multiple of 128
@@ -77,6 +80,7 @@ private:
     __nv_bfloat16* D_[2] = {nullptr, nullptr};
     __nv_bfloat16* Wf_[8] = {nullptr};
     __nv_bfloat16* Wb_[8] = {nullptr};
+    float* Bp_[8] = {nullptr};
     float* partial_ = nullptr;
     float* colsum_[8] = {nullptr};
     float* head_partial_ = nullptr;

@@ -31,10 +31,14 @@ __host__ __device__ constexpr int head_off_phi(int H, int NOUT) { return head_of
 __host__ __device__ constexpr int head_npart(int H, int NOUT) { return head_off_phi(H, NOUT) + MAXPS; }
 
 struct WideDims {
-    int P, H, NH, NOUT, R4;      // chain shape; floats per record
+    int P, H, NH, NOUT, R4;      // chain shape; floats per record.  H = PADDED hidden width (256 or 512): activation /
+                                 // delta rows, weight images and partial vectors are H wide
+    int hw[8];                   // real width of hidden layer l at [l-1] (<= H).  Units hw..H-1 of a layer are padding:
+                                 // zero weights in and out, so they never influence a result and receive no update
     int nflat, ntheta;
     // flat offsets (reference ComponentArray order): W_l is out x in column-major, i.e. index o + i * out
     int w_off[8], b_off[8];      // layer l (1-based) at [l-1]; l = NH+1 is the output layer
+    __host__ __device__ int din(int l) const { return l == 1 ? P : hw[l - 2]; }   // real fan-in of hidden layer l
 };
 
 // ---- gather: rec[idx[b]] -> xb[b] ---------------------------------------------------------------------------
@@ -65,14 +69,15 @@ __global__ void __launch_bounds__(256) k_wide_first(const float* xb, const float
     const int o0 = (threadIdx.x % per_row) * 8;
     const int r0 = (blockIdx.x * groups + threadIdx.x / per_row) * FIRST_ROWS;
     float bias[8], w[4][8], mu[4], rs[4];
+    const int h1 = d.hw[0];
 #pragma unroll
-    for (int j = 0; j < 8; j++) bias[j] = __ldg(theta + d.b_off[0] + o0 + j);
+    for (int j = 0; j < 8; j++) bias[j] = o0 + j < h1 ? __ldg(theta + d.b_off[0] + o0 + j) : 0.f;
 #pragma unroll
     for (int p = 0; p < 4; p++) {
         mu[p] = (use_bn && p < d.P) ? bscal[BS_BN + 2 * p] : 0.f;
         rs[p] = (use_bn && p < d.P) ? bscal[BS_BN + 2 * p + 1] : 1.f;
 #pragma unroll
-        for (int j = 0; j < 8; j++) w[p][j] = p < d.P ? __ldg(theta + d.w_off[0] + o0 + j + p * d.H) : 0.f;
+        for (int j = 0; j < 8; j++) w[p][j] = (p < d.P && o0 + j < h1) ? __ldg(theta + d.w_off[0] + o0 + j + p * h1) : 0.f;
     }
     for (int b = r0; b < r0 + FIRST_ROWS && b < B; b++) {
         float z[8];
@@ -154,7 +159,7 @@ __global__ void __launch_bounds__(256) k_wide_head(const HeadArgs a)
         for (int e = 0; e < 8; e++) {
             const int i = (c * 32 + lane) * 8 + e;
 #pragma unroll
-            for (int o = 0; o < NOUT; o++) w[o][c][e] = a.pblock[wo + o + i * NOUT];
+            for (int o = 0; o < NOUT; o++) w[o][c][e] = i < a.d.hw[a.d.NH - 1] ? a.pblock[wo + o + i * NOUT] : 0.f;
         }
     float bout[NOUT];
 #pragma unroll
@@ -379,7 +384,8 @@ __global__ void __launch_bounds__(512) k_wide_colsum(const __nv_bfloat16* D, con
 }
 
 // ---- split-K partials [S][H(o)][H(i)] -> flat gradient of W_l (index o + i * H), fixed summation order ----
-__global__ void __launch_bounds__(256) k_wide_wreduce(const float* partial, int S, int H, float* grad_w)
+// (H = padded width of the partial tiles; the flat block is hout x hin, real widths)
+__global__ void __launch_bounds__(256) k_wide_wreduce(const float* partial, int S, int H, int hout, int hin, float* grad_w)
 {
     __shared__ float tile[32][33];
     const int i0 = blockIdx.x * 32, o0 = blockIdx.y * 32;
@@ -394,7 +400,8 @@ __global__ void __launch_bounds__(256) k_wide_wreduce(const float* partial, int 
         tile[r][tx] = s;   // [o][i]
     }
     __syncthreads();
-    for (int r = ty; r < 32; r += 8) grad_w[(size_t)(i0 + r) * H + o0 + tx] = tile[tx][r];
+    for (int r = ty; r < 32; r += 8)
+        if (i0 + r < hin && o0 + tx < hout) grad_w[(size_t)(i0 + r) * hout + o0 + tx] = tile[tx][r];
 }
 
 struct FinArgs {
@@ -419,7 +426,9 @@ struct FinArgs {
 // layer on (W_o, b_o, phi)
 __host__ __device__ inline int gradfin_count(const WideDims& d)
 {
-    return d.P * d.H + d.H + (d.NH - 1) * d.H + (d.nflat - d.w_off[d.NH]);
+    int n = d.P * d.hw[0] + d.hw[0] + (d.nflat - d.w_off[d.NH]);
+    for (int l = 2; l <= d.NH; l++) n += d.hw[l - 1];
+    return n;
 }
 
 // ---- everything of the gradient that is not a hidden weight matrix, plus the loss value ----
@@ -467,19 +476,22 @@ __global__ void __launch_bounds__(256) k_wide_gradfin(const FinArgs a)
     int phi_slot = -1;
     bool is_phi = false;
     if (live) {
-        const int n1 = P * H + H;
+        const int h1 = a.d.hw[0];
+        const int n1 = P * h1 + h1;
+        int nb2 = 0;   // entries of b_2 .. b_NH
+        for (int l = 2; l <= NH; l++) nb2 += a.d.hw[l - 1];
         if (q < n1) {
             p = a.d.w_off[0] + q;
-            const int col = q < P * H ? (1 + q / H) * H + q % H : q - P * H;   // W_1[o][k] lives at (1 + k) H + o, b_1 at o
+            const int col = q < P * h1 ? (1 + q / h1) * H + q % h1 : q - P * h1;   // W_1[o][k] lives at (1 + k) H + o, b_1 at o
             src = a.colsum[0] + col; stride = (size_t)(1 + P) * H; cnt = a.n_slab;
-            if (NH == 1) { src = a.head_partial + head_off_dbh(H, NOUT) + (q - P * H); stride = HP; cnt = a.n_head; }
-        } else if (q < n1 + (NH - 1) * H) {
-            const int l = 2 + (q - n1) / H, o = (q - n1) % H;
+        } else if (q < n1 + nb2) {
+            int l = 2, o = q - n1;
+            while (o >= a.d.hw[l - 1]) { o -= a.d.hw[l - 1]; l++; }
             p = a.d.b_off[l - 1] + o;
             if (l == NH) { src = a.head_partial + head_off_dbh(H, NOUT) + o; stride = HP; cnt = a.n_head; }
             else { src = a.colsum[l - 1] + o; stride = H; cnt = a.n_slab; }
         } else {
-            p = a.d.w_off[NH] + (q - n1 - (NH - 1) * H);
+            p = a.d.w_off[NH] + (q - n1 - nb2);
             const int wo = a.d.w_off[NH], bo = a.d.b_off[NH];
             stride = HP; cnt = a.n_head;
             if (p < bo) { const int o = (p - wo) % NOUT, i = (p - wo) / NOUT; src = a.head_partial + o * H + i; }
@@ -583,7 +595,8 @@ struct WUpdArgs {
     float eta, beta1, beta2, eps, lambda;
     __nv_bfloat16* Wf[8];      // [l-1], l = 2..NH: W_l as [out][in]  (B operand of the forward GEMM)
     __nv_bfloat16* Wb[8];      //                  W_l as [in][out]  (B operand of the backward-data GEMM)
-    int apply;                 // 0: only refresh the bf16 images from theta
+    float* Bp[8];              // [l-1], l = 2..NH: b_l padded to H floats (the forward GEMM's epilogue reads H of them)
+    int apply;                 // 0: only refresh the images from theta
 };
 
 // ---- optimiser over the flat vector (Optimisers.jl rules) + bf16 weight images ----
@@ -596,7 +609,7 @@ __global__ void __launch_bounds__(256) k_wide_update(const WUpdArgs a)
         float g = a.grad[p];
         // hidden weight matrices come straight from the GEMM partials: apply the rmse factor here
         bool hidden = false;
-        for (int l = 2; l <= a.d.NH; l++) hidden |= (p >= a.d.w_off[l - 1] && p < a.d.w_off[l - 1] + a.d.H * a.d.H);
+        for (int l = 2; l <= a.d.NH; l++) hidden |= (p >= a.d.w_off[l - 1] && p < a.d.w_off[l - 1] + a.d.hw[l - 1] * a.d.hw[l - 2]);
         if (hidden)
             for (int t = 0; t < a.T; t++)
                 if (a.loss_kind[t] == LOSS_RMSE) g *= 1.f / (2.f * sqrtf(a.stats[t] / a.bscal[BS_N + t]));
@@ -620,12 +633,14 @@ __global__ void __launch_bounds__(256) k_wide_update(const WUpdArgs a)
         a.theta[p] = th;
     }
     for (int l = 2; l <= a.d.NH; l++) {
-        const int wo = a.d.w_off[l - 1], H = a.d.H;
-        if (p >= wo && p < wo + H * H) {
-            const int o = (p - wo) % H, i = (p - wo) / H;
+        const int wo = a.d.w_off[l - 1], bo = a.d.b_off[l - 1], H = a.d.H, ho = a.d.hw[l - 1], hi = a.d.hw[l - 2];
+        if (p >= wo && p < wo + ho * hi) {
+            const int o = (p - wo) % ho, i = (p - wo) / ho;
             const __nv_bfloat16 hb = __float2bfloat16_rn(th);
             a.Wb[l - 1][(size_t)i * H + o] = hb;
             a.Wf[l - 1][(size_t)o * H + i] = hb;
+        } else if (p >= bo && p < bo + ho) {
+            a.Bp[l - 1][p - bo] = th;
         }
     }
 }

@@ -250,10 +250,11 @@ def test_unsupported_models_fail_loudly(eh):
         eh.FusedSession(m)
     assert ei.value.status == _abi.EH_EUNSUPPORTED
     with pytest.raises(eh.EasyHybridCudaError) as ei:
-        eh.FusedSession(rbq10_model(eh, hidden=(64, 48)))   # between the register-tile variants and the wide path
+        eh.FusedSession(rbq10_model(eh, hidden=(600, 600)))   # wider than the tensor-core path takes
     assert ei.value.status == _abi.EH_EUNSUPPORTED
-    # 3 x 512 is served by the wide (bf16 tcgen05) path since round 1
+    # everything between the register-tile variants and 512 is served by the tensor-core (bf16 tcgen05) path
     eh.FusedSession(rbq10_model(eh, hidden=(512, 512, 512))).close()
+    eh.FusedSession(rbq10_model(eh, hidden=(64, 48))).close()
 
 
 def test_train_api_learns_q10(eh):

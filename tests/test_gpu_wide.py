@@ -54,6 +54,11 @@ CASES = [
     ("c5-3x512-pertarget", dict(hidden=(512, 512, 512), two=True), "PT", 2048),
     ("2x256-mse", dict(hidden=(256, 256), two=False, activation="sigmoid"), "mse", 1024),
     ("3x512-scale-nan", dict(hidden=(512, 512, 512), two=True, scale=True), "mse", 1536),
+    # widths between the register-tile kernels (<= 32) and 256 / 512 are padded inside the tensor-core path
+    ("2x64-mse", dict(hidden=(64, 64), two=False), "mse", 1024),
+    ("48-96-32-relu", dict(hidden=(48, 96, 32), two=True, activation="relu"), "mse", 1024),
+    ("3x16-deeper-than-the-aot-variants", dict(hidden=(16, 16, 16), two=False), "mse", 1024),
+    ("300-200-sigmoid-scale", dict(hidden=(300, 200), two=True, activation="sigmoid", scale=True), "PT", 1024),
 ]
 
 
@@ -118,10 +123,13 @@ def test_wide_training_reduces_loss_and_tracks_oracle(eh, orc):
 
 
 def test_wide_unsupported_shapes_fail_loudly(eh):
-    model = wide_model(eh, hidden=(512, 256))
-    with pytest.raises(Exception) as ei:
+    model = wide_model(eh, hidden=(1024, 1024))
+    with pytest.raises(eh.EasyHybridCudaError) as ei:
         eh.FusedSession(model, training_loss="mse")
-    assert "wide" in str(ei.value).lower() or "unsupported" in str(ei.value).lower()
+    assert "EH_EUNSUPPORTED" in str(ei.value) or "no fused kernel" in str(ei.value)
+    model = wide_model(eh, hidden=(64, 64), activation="swish")
+    with pytest.raises(eh.EasyHybridCudaError):
+        eh.FusedSession(model, training_loss="mse")
 
 
 def test_tcgen05_gemm_kernels_against_torch():
