@@ -913,20 +913,38 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
     if (d->n_targ < 1 || d->n_targ > MAXT) return fail(c, EH_EUNSUPPORTED, "n_targ=%d not in 1..%d", d->n_targ, MAXT);
     if (d->n_chains != 1)
         return fail(c, EH_EUNSUPPORTED, "n_chains=%d: only single-chain models have a fused kernel in this build", d->n_chains);
-    if (d->process_model == EH_PM_PROGRAM)
-        return fail(c, EH_EUNSUPPORTED, "traced process-model programs are not compiled in this build");
+    const bool is_prog = d->process_model == EH_PM_PROGRAM;
+    if (is_prog) {
+        // a traced process model: validated here, interpreted per sample by the tensor-core path's head kernel
+        if (d->pm_len < 1 || d->pm_len > PM_MAXLEN || !d->pm_prog || !d->pm_outputs)
+            return fail(c, EH_EUNSUPPORTED, "traced process model: 1..%d instructions supported (got %d)", PM_MAXLEN, d->pm_len);
+        if (d->n_params < 1 || d->n_params > MAXPS || d->n_forc < 0 || d->n_forc > 4 || d->n_targ > 2)
+            return fail(c, EH_EUNSUPPORTED, "traced process model: <= %d parameters, <= 4 forcings, <= 2 targets", MAXPS);
+        for (int i = 0; i < d->pm_len; i++) {
+            const eh_pm_instr& in = d->pm_prog[i];
+            const bool leaf = in.op == EH_OP_CONST || in.op == EH_OP_FORCING || in.op == EH_OP_PARAM;
+            const bool binary = in.op >= EH_OP_ADD && in.op <= EH_OP_MAX, unary = in.op >= EH_OP_NEG && in.op <= EH_OP_COS;
+            if (!leaf && !binary && !unary) return fail(c, EH_EINVAL, "pm_prog[%d]: unknown op %d", i, in.op);
+            if (in.op == EH_OP_FORCING && (in.a < 0 || in.a >= d->n_forc)) return fail(c, EH_EINVAL, "pm_prog[%d]: forcing %d out of range", i, in.a);
+            if (in.op == EH_OP_PARAM && (in.a < 0 || in.a >= d->n_params)) return fail(c, EH_EINVAL, "pm_prog[%d]: parameter %d out of range", i, in.a);
+            if ((binary || unary) && (in.a < 0 || in.a >= i)) return fail(c, EH_EINVAL, "pm_prog[%d]: operand a=%d is not an earlier value", i, in.a);
+            if (binary && (in.b < 0 || in.b >= i)) return fail(c, EH_EINVAL, "pm_prog[%d]: operand b=%d is not an earlier value", i, in.b);
+        }
+        for (int t = 0; t < d->n_targ; t++)
+            if (d->pm_outputs[t] < 0 || d->pm_outputs[t] >= d->pm_len) return fail(c, EH_EINVAL, "pm_outputs[%d] out of range", t);
+    }
     const eh_chain_desc& ch = d->chains[0];
     if (ch.n_in < 1 || ch.n_in > MAXP) return fail(c, EH_EUNSUPPORTED, "chain n_in=%d not in 1..%d", ch.n_in, MAXP);
     if (ch.n_hidden < 1) return fail(c, EH_EINVAL, "chain needs at least one hidden layer");
     int hmax = 0;
     for (int l = 0; l < ch.n_hidden; l++) hmax = std::max(hmax, ch.hidden[l]);
-    if (d->n_pm_args != 3 || d->pm_args[0].kind != 0 || d->pm_args[1].kind != 0 || d->pm_args[2].kind != 1)
+    if (!is_prog && (d->n_pm_args != 3 || d->pm_args[0].kind != 0 || d->pm_args[1].kind != 0 || d->pm_args[2].kind != 1))
         return fail(c, EH_EINVAL, "built-in process models take (param, param, forcing) arguments");
     // Which path?  The exact-fp32 register-tile kernels exist for two hidden layers of width <= 32; every other chain
     // (wider or deeper, up to 6 hidden layers of up to 512 units, padded to 256 / 512 internally) runs on the bf16
     // tcgen05 GEMM path.
     bool wide = false;
-    const bool have_small = hmax <= 32 && find_variant(d->process_model, ch.n_in, ch.n_hidden, rup4(hmax), ch.n_out, ch.activation,
+    const bool have_small = !is_prog && hmax <= 32 && find_variant(d->process_model, ch.n_in, ch.n_hidden, rup4(hmax), ch.n_out, ch.activation,
                                                        d->scale_nn_outputs ? 1 : 0, 0) != nullptr;
     if (!have_small) {
         if (!eh::wide::WideNet::supported(ch.n_in, hmax, ch.n_hidden, ch.n_out, ch.activation, d->process_model))
@@ -943,8 +961,8 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
         wv.NOUT = ch.n_out; wv.act = ch.activation;
         wv.scale = d->scale_nn_outputs ? 1 : 0;
         wv.engine = 3; wv.chunk = 128;
-        wv.F = 1; wv.NPS = 2;
-        wv.T = (d->process_model == EH_PM_LINEAR2 || d->process_model == EH_PM_EXPO2) ? 2 : 1;
+        wv.F = is_prog ? d->n_forc : 1; wv.NPS = is_prog ? d->n_params : 2;
+        wv.T = is_prog ? d->n_targ : ((d->process_model == EH_PM_LINEAR2 || d->process_model == EH_PM_EXPO2) ? 2 : 1);
         wv.R4 = rup4(wv.P + wv.F + wv.T);
         wv.NW = 0; wv.NPART = NSTAT; wv.off_stats = 0; wv.stage_floats = NSTAT; wv.max_warps = 8;
         wv.name = "wide/bf16-tcgen05";
@@ -1022,7 +1040,7 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
     memset(c->slots, 0, sizeof c->slots);
     for (int s = 0; s < MAXPS; s++) c->slots[s].role = ROLE_FIXED;
     for (int s = 0; s < v->NPS; s++) {
-        int pi = d->pm_args[s].index;
+        int pi = is_prog ? s : d->pm_args[s].index;   // traced programs address the parameter table directly
         if (pi < 0 || pi >= d->n_params) return fail(c, EH_EINVAL, "pm_args[%d].index out of range", s);
         PSlot& sl = c->slots[s];
         sl.role = d->role[pi];
@@ -1101,7 +1119,9 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
         if (ch.in_cols[k] < 0 || ch.in_cols[k] >= d->n_pred) return fail(c, EH_EINVAL, "chain in_cols[%d] out of range", k);
         c->src_kind[c->ncols] = 0; c->src_idx[c->ncols] = ch.in_cols[k]; c->ncols++;
     }
-    {
+    if (is_prog) {
+        for (int fi = 0; fi < d->n_forc; fi++) { c->src_kind[c->ncols] = 1; c->src_idx[c->ncols] = fi; c->ncols++; }
+    } else {
         int fi = d->pm_args[2].index;
         if (fi < 0 || fi >= d->n_forc) return fail(c, EH_EINVAL, "forcing index out of range");
         c->src_kind[c->ncols] = 1; c->src_idx[c->ncols] = fi; c->ncols++;
@@ -1143,6 +1163,14 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
         wm.opt_kind = c->opt_kind; wm.adamw_coupled = c->adamw_coupled;
         wm.eta = c->eta; wm.beta1 = c->beta1; wm.beta2 = c->beta2; wm.eps = c->eps; wm.lambda = c->lambda;
         wm.nsm = c->nsm;
+        if (is_prog) {
+            wm.prog_len = d->pm_len;
+            for (int i = 0; i < d->pm_len; i++) {
+                wm.prog_op[i] = (short)d->pm_prog[i].op; wm.prog_a[i] = (short)d->pm_prog[i].a; wm.prog_b[i] = (short)d->pm_prog[i].b;
+                wm.prog_imm[i] = d->pm_prog[i].imm;
+            }
+            for (int t = 0; t < d->n_targ; t++) wm.prog_out[t] = d->pm_outputs[t];
+        }
     }
     return EH_OK;
 }

@@ -15,10 +15,25 @@ namespace eh {
 
 constexpr int PMS_PER_SLOT = 4;
 
+// a traced process model: straight-line SSA program (eh_pm_instr of the C ABI), at most PM_MAXLEN instructions
+constexpr int PM_MAXLEN = 48;
+struct PmProgData {
+    int len, nt, nf, np;       // instructions, targets, forcings, parameters
+    int out[MAXT];             // value id of each target
+    short op[PM_MAXLEN], a[PM_MAXLEN], b[PM_MAXLEN];
+    float imm[PM_MAXLEN];
+};
+enum : int {   // == eh_pm_op of easyhybrid_cuda.h
+    POP_CONST = 0, POP_FORCING = 1, POP_PARAM = 2, POP_ADD = 10, POP_SUB = 11, POP_MUL = 12, POP_DIV = 13, POP_POW = 14,
+    POP_MIN = 15, POP_MAX = 16, POP_NEG = 20, POP_EXP = 21, POP_LOG = 22, POP_SQRT = 23, POP_TANH = 24, POP_SIGMOID = 25,
+    POP_ABS = 26, POP_SIN = 27, POP_COS = 28
+};
+
 // uniform-slot context handed to the functors
 struct PmCtx {
     const float* pms;          // [MAXPS * PMS_PER_SLOT] per-slot derived scalars
     const float* c;            // process-model constants
+    const PmProgData* prog;    // traced program (PmProgram only)
     unsigned uniform_mask;     // bit s set: slot s is GLOBAL / FIXED (same value for all samples)
     __device__ __forceinline__ bool uniform(int s) const { return (uniform_mask >> s) & 1u; }
 };
@@ -51,6 +66,7 @@ __device__ __forceinline__ float exp2_mul_hilo(float a, float Lh, float Ll)
 // reco = rb * Q10^(0.1 (ta - tref))      README.md:148-151, test/test_split_data_train.jl:36-39
 // slots: p0 = rb, p1 = Q10 ; f0 = ta ; const c0 = tref
 struct PmRbQ10 {
+    static constexpr bool DYNAMIC = false;
     static constexpr int ID = PM_RBQ10, NPS = 2, NF = 1, NT = 1;
     __device__ __forceinline__ static void fwd(const float* p, const float* f, const PmCtx& cx, float* y, float* sv)
     {
@@ -75,6 +91,7 @@ struct PmRbQ10 {
 // Resp = Resp0 * exp(k T)                 projects/ExpoHybrid/ExpoHybridEstim.jl:69-85
 // slots: p0 = Resp0, p1 = k ; f0 = T
 struct PmExpo {
+    static constexpr bool DYNAMIC = false;
     static constexpr int ID = PM_EXPO, NPS = 2, NF = 1, NT = 1;
     __device__ __forceinline__ static void fwd(const float* p, const float* f, const PmCtx& cx, float* y, float* sv)
     {
@@ -94,6 +111,7 @@ struct PmExpo {
 // y = a x + b                             src/models/LinearHM.jl:61-68, test/test_generic_hybrid_model.jl:10-12
 // slots: p0 = a, p1 = b ; f0 = x
 struct PmLinear {
+    static constexpr bool DYNAMIC = false;
     static constexpr int ID = PM_LINEAR, NPS = 2, NF = 1, NT = 1;
     __device__ __forceinline__ static void fwd(const float* p, const float* f, const PmCtx& cx, float* y, float* sv)
     {
@@ -109,6 +127,7 @@ struct PmLinear {
 
 // (var1 = a x + b, var2 = 2 a x + b)      test/test_compute_loss.jl:209-211
 struct PmLinear2 {
+    static constexpr bool DYNAMIC = false;
     static constexpr int ID = PM_LINEAR2, NPS = 2, NF = 1, NT = 2;
     __device__ __forceinline__ static void fwd(const float* p, const float* f, const PmCtx& cx, float* y, float* sv)
     {
@@ -128,6 +147,7 @@ struct PmLinear2 {
 // projects/ExpoHybrid/ExpoHybridEstim.jl:69-85 with a second target that is twice the first, the same
 // construction as test/test_compute_loss.jl:209-211 uses for the linear model)
 struct PmExpo2 {
+    static constexpr bool DYNAMIC = false;
     static constexpr int ID = PM_EXPO2, NPS = 2, NF = 1, NT = 2;
     __device__ __forceinline__ static void fwd(const float* p, const float* f, const PmCtx& cx, float* y, float* sv)
     {
@@ -142,6 +162,91 @@ struct PmExpo2 {
         const float g = fmaf(2.f, gy[1], gy[0]);
         gp[0] = g * sv[0];
         gp[1] = g * y[0] * f[0];
+    }
+};
+
+// Any other process model: the host traces `mechanistic_model(; forcings..., params...)`
+// (src/models/GenericHybridModel.jl:425) into a straight-line program; here it is interpreted per sample, and its
+// pullback is the reverse sweep over the same program (what Zygote does with the Julia closure).  Slot s = parameter s
+// of the descriptor, forcing k = forcing column k.  Compile-time maxima; the real counts come with the program.
+struct PmProgram {
+    static constexpr int ID = PM_PROGRAM, NPS = MAXPS, NF = 4, NT = 2;
+    static constexpr bool DYNAMIC = true;
+    __device__ __forceinline__ static void eval(const float* p, const float* f, const PmProgData& pg, float* v)
+    {
+        for (int i = 0; i < pg.len; i++) {
+            const int op = pg.op[i];
+            const float x = v[pg.a[i] < i ? pg.a[i] : 0], y = v[pg.b[i] < i ? pg.b[i] : 0];
+            float r;
+            switch (op) {
+            case POP_CONST: r = pg.imm[i]; break;
+            case POP_FORCING: r = f[pg.a[i]]; break;
+            case POP_PARAM: r = p[pg.a[i]]; break;
+            case POP_ADD: r = x + y; break;
+            case POP_SUB: r = x - y; break;
+            case POP_MUL: r = x * y; break;
+            case POP_DIV: r = x / y; break;
+            case POP_POW: r = powf(x, y); break;
+            case POP_MIN: r = x < y ? x : y; break;
+            case POP_MAX: r = x > y ? x : y; break;
+            case POP_NEG: r = -x; break;
+            case POP_EXP: r = expf(x); break;
+            case POP_LOG: r = logf(x); break;
+            case POP_SQRT: r = sqrtf(x); break;
+            case POP_TANH: r = tanhf(x); break;
+            case POP_SIGMOID: r = 1.f / (1.f + expf(-x)); break;
+            case POP_ABS: r = fabsf(x); break;
+            case POP_SIN: r = sinf(x); break;
+            default: r = cosf(x); break;
+            }
+            v[i] = r;
+        }
+    }
+    __device__ __forceinline__ static void fwd(const float* p, const float* f, const PmCtx& cx, float* y, float* sv)
+    {
+        const PmProgData& pg = *cx.prog;
+        float v[PM_MAXLEN];
+        eval(p, f, pg, v);
+        for (int t = 0; t < NT; t++) y[t] = t < pg.nt ? v[pg.out[t]] : 0.f;
+    }
+    __device__ __forceinline__ static void bwd(const float* p, const float* f, const PmCtx& cx, const float* y,
+                                               const float* sv, const float* gy, float* gp)
+    {
+        const PmProgData& pg = *cx.prog;
+        float v[PM_MAXLEN], g[PM_MAXLEN];
+        eval(p, f, pg, v);
+        for (int i = 0; i < pg.len; i++) g[i] = 0.f;
+        for (int t = 0; t < NT; t++)
+            if (t < pg.nt) g[pg.out[t]] += gy[t];
+        for (int s = 0; s < NPS; s++) gp[s] = 0.f;
+        for (int i = pg.len - 1; i >= 0; i--) {
+            const float gi = g[i];
+            const int op = pg.op[i], ia = pg.a[i], ib = pg.b[i];
+            if (op == POP_CONST || op == POP_FORCING) continue;
+            if (op == POP_PARAM) { gp[ia] += gi; continue; }
+            const float x = v[ia], yv = op < POP_NEG ? v[ib] : 0.f;
+            float ga = 0.f, gb = 0.f;
+            switch (op) {
+            case POP_ADD: ga = gi; gb = gi; break;
+            case POP_SUB: ga = gi; gb = -gi; break;
+            case POP_MUL: ga = gi * yv; gb = gi * x; break;
+            case POP_DIV: ga = gi / yv; gb = -ga * v[i]; break;
+            case POP_POW: ga = gi * yv * powf(x, yv - 1.f); gb = gi * v[i] * logf(x); break;
+            case POP_MIN: if (x < yv) ga = gi; else gb = gi; break;
+            case POP_MAX: if (x > yv) ga = gi; else gb = gi; break;
+            case POP_NEG: ga = -gi; break;
+            case POP_EXP: ga = gi * v[i]; break;
+            case POP_LOG: ga = gi / x; break;
+            case POP_SQRT: ga = gi / (2.f * v[i]); break;
+            case POP_TANH: ga = gi * (1.f - v[i] * v[i]); break;
+            case POP_SIGMOID: ga = gi * v[i] * (1.f - v[i]); break;
+            case POP_ABS: ga = x < 0.f ? -gi : (x > 0.f ? gi : 0.f); break;
+            case POP_SIN: ga = gi * cosf(x); break;
+            default: ga = -gi * sinf(x); break;
+            }
+            g[ia] += ga;
+            if (op < POP_NEG) g[ib] += gb;
+        }
     }
 };
 

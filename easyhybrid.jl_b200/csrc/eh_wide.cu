@@ -135,7 +135,8 @@ struct HeadEntry { int pm, nout, scale, hch; HeadKernel fn; };
 #define EH_HEAD(PMF, NOUT, SCALE, HCH) {PMF::ID, NOUT, SCALE, HCH, k_wide_head<HeadCfg<PMF, NOUT, (SCALE != 0)>, HCH>},
 #define EH_HEAD_PM(PMF) EH_HEAD(PMF, 1, 0, 1) EH_HEAD(PMF, 1, 1, 1) EH_HEAD(PMF, 2, 0, 1) EH_HEAD(PMF, 2, 1, 1) \
                         EH_HEAD(PMF, 1, 0, 2) EH_HEAD(PMF, 1, 1, 2) EH_HEAD(PMF, 2, 0, 2) EH_HEAD(PMF, 2, 1, 2)
-const HeadEntry g_heads[] = {EH_HEAD_PM(PmRbQ10) EH_HEAD_PM(PmExpo) EH_HEAD_PM(PmLinear) EH_HEAD_PM(PmLinear2) EH_HEAD_PM(PmExpo2)};
+const HeadEntry g_heads[] = {EH_HEAD_PM(PmRbQ10) EH_HEAD_PM(PmExpo) EH_HEAD_PM(PmLinear) EH_HEAD_PM(PmLinear2) EH_HEAD_PM(PmExpo2)
+                             EH_HEAD_PM(PmProgram)};
 
 HeadKernel find_head(int pm, int nout, int scale, int hch)
 {
@@ -204,6 +205,16 @@ WideNet* WideNet::create(const WideModel& m, char* err, size_t errlen)
             return nullptr;
         }
     }
+    if (m.pm == PM_PROGRAM) {
+        static_assert(PM_MAXLEN == 48, "WideModel program arrays");
+        PmProgData pd;
+        memset(&pd, 0, sizeof pd);
+        pd.len = m.prog_len; pd.nt = m.T; pd.nf = m.F; pd.np = m.NPS;
+        for (int t = 0; t < 4; t++) pd.out[t] = m.prog_out[t];
+        for (int i = 0; i < m.prog_len; i++) { pd.op[i] = m.prog_op[i]; pd.a[i] = m.prog_a[i]; pd.b[i] = m.prog_b[i]; pd.imm[i] = m.prog_imm[i]; }
+        if ((e = cudaMalloc(&w->d_prog_, sizeof pd)) != cudaSuccess) return bail("cudaMalloc", e);
+        if ((e = cudaMemcpy(w->d_prog_, &pd, sizeof pd, cudaMemcpyHostToDevice)) != cudaSuccess) return bail("cudaMemcpy", e);
+    }
     w->n_head_ = 2 * m.nsm;
     if ((e = cudaMalloc(&w->head_partial_, (size_t)w->n_head_ * head_npart(m.H, m.NOUT) * 4)) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc(&w->stats_, 16 * 4)) != cudaSuccess) return bail("cudaMalloc", e);
@@ -222,7 +233,7 @@ WideNet::~WideNet()
         if (Bp_[i]) cudaFree(Bp_[i]);
         if (colsum_[i]) cudaFree(colsum_[i]);
     }
-    void* ps[] = {xb_, D_[0], D_[1], partial_, head_partial_, stats_, skip_, evalpart_};
+    void* ps[] = {xb_, D_[0], D_[1], partial_, head_partial_, stats_, skip_, evalpart_, d_prog_};
     for (void* p : ps)
         if (p) cudaFree(p);
 }
@@ -311,6 +322,7 @@ cudaError_t WideNet::step(const float* rec, const int* idx, long long rec_base, 
     HeadArgs ha{};
     ha.A = A_[NH - 1]; ha.xb = xb_; ha.pblock = pblock; ha.bscal = bscal; ha.D = D_[NH & 1]; ha.partial = head_partial_;
     ha.d = d; ha.B = B; ha.Bvalid = B; ha.act = m_.act; ha.train = 1;
+    ha.prog = reinterpret_cast<const PmProgData*>(d_prog_); ha.nf = m_.F; ha.nt = m_.T;
     for (int t = 0; t < 4; t++) ha.loss_kind[t] = m_.loss_kind[t];
     for (int s = 0; s < 8; s++) { ha.slot[s].role = m_.slot[s].role; ha.slot[s].idx = m_.slot[s].idx; ha.slot[s].lo = m_.slot[s].lo; ha.slot[s].span = m_.slot[s].span; ha.slot[s].fixedv = m_.slot[s].fixedv; }
     for (int i = 0; i < 4; i++) ha.pmc[i] = m_.pmc[i];
@@ -393,6 +405,7 @@ cudaError_t WideNet::eval_rows(const float* rec, long long nrec, long long row0,
     ha.yhat = yhat; ha.parout = parout; ha.ldy = ldy; ha.row0 = row0; ha.evalstat = evalstat_dev ? evalpart_ : nullptr;
     for (int t = 0; t < 4; t++) { ha.shift_y[t] = shift_y[t]; ha.loss_kind[t] = m_.loss_kind[t]; }
     ha.d = dims_of(m_); ha.B = B; ha.Bvalid = Bvalid; ha.act = m_.act; ha.train = 0;
+    ha.prog = reinterpret_cast<const PmProgData*>(d_prog_); ha.nf = m_.F; ha.nt = m_.T;
     for (int s = 0; s < 8; s++) { ha.slot[s].role = m_.slot[s].role; ha.slot[s].idx = m_.slot[s].idx; ha.slot[s].lo = m_.slot[s].lo; ha.slot[s].span = m_.slot[s].span; ha.slot[s].fixedv = m_.slot[s].fixedv; }
     for (int i = 0; i < 4; i++) ha.pmc[i] = m_.pmc[i];
     const int head_smem = 8 * (m_.NOUT + 1) * H * (int)sizeof(float);

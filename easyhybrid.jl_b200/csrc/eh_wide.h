@@ -39,6 +39,11 @@ struct WideModel {          // filled by eh_lib's planner from the model descrip
     float eta, beta1, beta2, eps, lambda;
     const int* d_slot_of_flat;
     int nsm;
+    // traced process model (pm == PM_PROGRAM): eh_pm_instr fields, value ids of the targets
+    int prog_len;
+    short prog_op[48], prog_a[48], prog_b[48];
+    float prog_imm[48];
+    int prog_out[4];
 };
 
 // the wide-chain training step: owns activations / deltas / bf16 weight images / partial buffers
@@ -81,6 +86,7 @@ private:
     __nv_bfloat16* Wf_[8] = {nullptr};
     __nv_bfloat16* Wb_[8] = {nullptr};
     float* Bp_[8] = {nullptr};
+    void* d_prog_ = nullptr;   // PmProgData on the device
     float* partial_ = nullptr;
     float* colsum_[8] = {nullptr};
     float* head_partial_ = nullptr;

@@ -126,6 +126,8 @@ struct HeadArgs {
     int loss_kind[MAXT];
     PSlot slot[MAXPS];
     float pmc[4];
+    const PmProgData* prog;    // device copy of the traced program (PmProgram heads), else NULL
+    int nf, nt;                // real forcing / target counts (PmProgram heads; the built-in forms know theirs)
 };
 
 // ---- output layer + physics + loss seeds + backward into D_NH; one warp per sample row, 8 warps per CTA ----
@@ -139,12 +141,21 @@ __global__ void __launch_bounds__(256) k_wide_head(const HeadArgs a)
     const int H = a.d.H, P = a.d.P;
     __shared__ float s_pms[MAXPS * PMS_PER_SLOT + MAXPS];
     __shared__ float s_red[8][64];
+    __shared__ PmProgData s_prog;
     if (threadIdx.x < MAXPS * PMS_PER_SLOT + MAXPS) s_pms[threadIdx.x] = a.pblock[a.d.nflat + threadIdx.x];
+    if (PM::DYNAMIC) {
+        const int* src = reinterpret_cast<const int*>(a.prog);
+        int* dst = reinterpret_cast<int*>(&s_prog);
+        for (int i = threadIdx.x; i < (int)(sizeof(PmProgData) / 4); i += blockDim.x) dst[i] = src[i];
+    }
     __syncthreads();
+    // real forcing / target counts: compile-time for the built-in forms, from the program otherwise
+    const int nf = PM::DYNAMIC ? a.nf : F, nt = PM::DYNAMIC ? a.nt : T;
     // s_pms: [0..8) uniform slot values, [8..40) derived scalars -- same order as the parameter block tail
     PmCtx cx;
     cx.pms = s_pms + MAXPS;
     cx.c = a.pmc;
+    cx.prog = &s_prog;
     cx.uniform_mask = 0;
 #pragma unroll
     for (int s = 0; s < MAXPS; s++)
@@ -215,16 +226,16 @@ __global__ void __launch_bounds__(256) k_wide_head(const HeadArgs a)
         float f[F > 0 ? F : 1], y[T], pv[NPS], sg[NPS], yh[T], sv[4], gy[T], gp[NPS], dz[NOUT];
         const float* r = a.xb + (size_t)b * a.d.R4;
 #pragma unroll
-        for (int k = 0; k < F; k++) f[k] = r[P + k];
+        for (int k = 0; k < F; k++) f[k] = k < nf ? r[P + k] : 0.f;
 #pragma unroll
-        for (int k = 0; k < T; k++) y[k] = r[P + F + k];
+        for (int k = 0; k < T; k++) y[k] = k < nt ? r[P + nf + k] : __int_as_float(0x7fc00000);   // absent target = masked
         resolve_params<HC>(a.slot, s_pms, zo, pv, sg);
         PM::fwd(pv, f, cx, yh, sv);
         if (!a.train) {
             if (lane == 0) {
 #pragma unroll
                 for (int t = 0; t < T; t++) {
-                    if (a.yhat) a.yhat[(size_t)t * a.ldy + a.row0 + b] = yh[t];
+                    if (a.yhat && t < nt) a.yhat[(size_t)t * a.ldy + a.row0 + b] = yh[t];
                     if (y[t] == y[t]) {
                         const double yy = (double)y[t] - a.shift_y[t], hh = (double)yh[t] - a.shift_y[t], rr = (double)yh[t] - y[t];
                         est[t][0] += 1.0; est[t][1] += yy; est[t][2] += hh; est[t][3] += yy * yy;
@@ -299,10 +310,10 @@ __global__ void __launch_bounds__(256) k_wide_head(const HeadArgs a)
                 for (int t = 0; t < T; t++)
                     for (int q = 0; q < 8; q++) s_e[warp][t * 8 + q] = est[t][q];
             __syncthreads();
-            if (threadIdx.x < T * 8) {
+            if (threadIdx.x < nt * 8) {
                 double s = 0.0;
                 for (int wv = 0; wv < 8; wv++) s += s_e[wv][threadIdx.x];
-                a.evalstat[(size_t)blockIdx.x * (T * 8) + threadIdx.x] = s;
+                a.evalstat[(size_t)blockIdx.x * (nt * 8) + threadIdx.x] = s;
             }
         }
         return;

@@ -245,10 +245,14 @@ def test_unsupported_models_fail_loudly(eh):
 
     def other(*, ta, Q10, rb):
         return {"reco": rb * np.exp(Q10) + ta}
-    m = eh.constructHybridModel(["sw_pot"], ["ta"], ["reco"], other, dict(Q10=(2, 1, 4), rb=(3, 0, 13)), ["rb"], ["Q10"])
+    # a traced (non built-in) process model runs on the tensor-core path, which has no swish
+    m = eh.constructHybridModel(["sw_pot"], ["ta"], ["reco"], other, dict(Q10=(2, 1, 4), rb=(3, 0, 13)), ["rb"], ["Q10"],
+                                activation="swish")
     with pytest.raises(eh.EasyHybridCudaError) as ei:
         eh.FusedSession(m)
     assert ei.value.status == _abi.EH_EUNSUPPORTED
+    m = eh.constructHybridModel(["sw_pot"], ["ta"], ["reco"], other, dict(Q10=(2, 1, 4), rb=(3, 0, 13)), ["rb"], ["Q10"])
+    eh.FusedSession(m).close()
     with pytest.raises(eh.EasyHybridCudaError) as ei:
         eh.FusedSession(rbq10_model(eh, hidden=(600, 600)))   # wider than the tensor-core path takes
     assert ei.value.status == _abi.EH_EUNSUPPORTED

@@ -142,3 +142,50 @@ def test_tcgen05_gemm_kernels_against_torch():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     assert mod.main(False)
+
+
+def test_traced_process_model_runs_on_the_tensor_core_path(eh, orc):
+    """a process model that is none of the built-in forms (src/models/GenericHybridModel.jl:425 takes any callable):
+    traced into a straight-line program by the host, interpreted (value and pullback) in the head kernel"""
+    from conftest import make_synth
+
+    def custom(*, ta, dsw_pot, rb, Q10, alpha, tref=15.0):
+        return {"reco": rb * Q10 ** (0.1 * (ta - tref)) + alpha * np.tanh(0.05 * dsw_pot)}
+
+    model = eh.constructHybridModel(["sw_pot", "dsw_pot"], ["ta", "dsw_pot"], ["reco"], custom,
+                                    dict(rb=(3.0, 0.0, 13.0), Q10=(2.0, 1.0, 4.0), alpha=(0.5, -2.0, 2.0)), ["rb"], ["Q10", "alpha"],
+                                    hidden_layers=[32, 32], activation="tanh", scale_nn_outputs=True)
+    from easyhybrid_b200 import _abi
+    assert eh.build_desc(model).desc.process_model == _abi.PM["PROGRAM"]
+    n = 2048
+    table = make_synth(n, nan_frac=0.0)
+    table["reco"] = (table["reco"] + 0.3 * np.tanh(0.05 * table["dsw_pot"])).astype(np.float32)
+    xf, y = eh.prepare_data(model, table)
+    rng = np.random.default_rng(5)
+    flat = model.initialparameters(rng)
+    sess = eh.FusedSession(model, training_loss="mse", opt=eh.Adam(0.01))
+    sess.upload(0, xf, y)
+    sess.set_params(flat)
+    o = orc.Oracle(model, training_loss="mse", opt=eh.Adam(0.01))
+    idx = rng.permutation(n)[:1024]
+    L, g = sess.loss_grad(idx)
+    L64, g64 = o.loss_grad(flat, xf, y, idx, precision=64)
+    assert abs(L - L64) <= RTOL_LOSS * abs(L64), (L, L64)
+    for bname, sl in _blocks(model):
+        a, b = g[sl].astype(np.float64), g64[sl].astype(np.float64)
+        nb = np.linalg.norm(b)
+        if nb < 1e-12:
+            continue
+        assert float(a @ b / (np.linalg.norm(a) * nb)) >= COS_MIN, bname
+        assert abs(np.linalg.norm(a) - nb) <= RTOL_NORM * nb, bname
+    perm = np.concatenate([rng.permutation(n) for _ in range(10)])[: 40 * 512]
+    got = sess.epoch(perm, 512)
+    ref = flat.copy()
+    want = o.train_steps(ref, xf, y, perm, 512)
+    assert got[-1] < 0.5 * got[0]
+    assert np.allclose(got, want, rtol=5e-2, atol=1e-3), (got[-5:], want[-5:])
+    ps = sess.get_params()
+    assert np.allclose(ps[-2:], ref[-2:], atol=3e-2), (ps[-2:], ref[-2:])   # Q10 and alpha (raw)
+    yhat, stats, par = sess.eval(0, want_yhat=True, want_params=True)
+    assert np.allclose(yhat, o.forward(ps, xf, precision=64), rtol=3e-2, atol=3e-2)
+    sess.close()
