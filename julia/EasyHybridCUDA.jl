@@ -128,6 +128,18 @@ function epoch!(s::Session, perm::Vector{Int64}, batchsize::Integer)
 end
 
 "evaluate_acc: sufficient statistics (n, Sy, Sh, Syy, Shh, Syh, SSE, SAE, shift) per target + predictions"
+# data-parallel runs (one process per GPU): per-batch data statistics of the GLOBAL batch.  `allreduce_sum!` is the
+# caller's transport (e.g. MPI.Allreduce!(buf, +, comm)); call after eh_set_perm, before eh_run_steps.
+const EH_DP_MOMENTS = 37
+function dp_exchange_batch_stats!(s::Session, n::Integer, batchsize::Integer, allreduce_sum!)
+    nb = cld(n, batchsize)
+    mom = zeros(Float64, EH_DP_MOMENTS, nb)
+    check(s.ctx, ccall((:eh_dp_batch_moments, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}), s.ctx, batchsize, mom))
+    allreduce_sum!(mom)
+    check(s.ctx, ccall((:eh_dp_set_batch_moments, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}), s.ctx, batchsize, mom))
+    return nothing
+end
+
 function evaluate(s::Session, split::Integer, N::Integer, T::Integer)
     yhat = Matrix{Float32}(undef, N, T); stats = Matrix{Float64}(undef, 9, T)
     check(s.ctx, ccall((:eh_eval, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Float32}, Ptr{Float64}, Ptr{Float32}),
