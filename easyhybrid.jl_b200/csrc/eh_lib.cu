@@ -690,7 +690,7 @@ eh_status wide_run_steps(eh_ctx* c, int64_t n, int64_t B, int64_t first, int64_t
     }
     for (int64_t b = 0; b < nb; b++)
         if (!eh::wide::WideNet::batch_ok(std::min<int64_t>(B, n - b * B)))
-            return fail(c, EH_EUNSUPPORTED, "wide path: every batch must hold a multiple of 128 samples (got %lld)",
+            return fail(c, EH_EUNSUPPORTED, "wide path: batch size out of range (got %lld)",
                         (long long)std::min<int64_t>(B, n - b * B));
     CK(cudaEventRecord(c->ev0, c->stream));
     for (int64_t k = 0; k < nsteps; k++) {
@@ -1253,6 +1253,15 @@ eh_status enqueue_host_step(eh_ctx* c, HostStage& h, int64_t B, const float* X, 
         k_batch_stats<<<1, 256, 0, c->stream>>>(a);
         CK(cudaGetLastError());
     }
+    if (c->wide) {
+        if (c->world > 1) return fail(c, EH_EUNSUPPORTED, "host-batch steps of the tensor-core path are single-GPU: use eh_run_steps in data-parallel mode");
+        cudaError_t we = c->wide->step(h.d_rec, nullptr, 0, (int)B, h.d_bscal, c->d_theta, c->d_m, c->d_v, c->d_ost, c->d_grad, loss_dst, 1,
+                                       c->stream, nullptr);
+        if (we != cudaSuccess) return fail(c, EH_ECUDA, "wide path: %s", c->wide->error());
+        CK(refresh_tail(c));
+        CK(cudaEventRecord(h.freed, c->stream));
+        return EH_OK;
+    }
     if (c->world > 1) {
         // data parallel: one persistent launch of a single step (the exchange lives in that kernel)
         if (heavy) return fail(c, EH_EUNSUPPORTED, "data-parallel mode needs NaN-free targets, no nseLoss and no input BatchNorm");
@@ -1622,7 +1631,6 @@ eh_status eh_step_host(eh_ctx* c, int64_t B, const float* X, const float* const*
 {
     if (!c) return EH_EINVAL;
     if (B <= 0 || !X || !targ) return fail(c, EH_EINVAL, "bad eh_step_host arguments");
-    if (c->wide) return fail(c, EH_EUNSUPPORTED, "host-batch steps are not available on the wide (bf16 tcgen05) path: stage the split with eh_upload");
     CK(cudaSetDevice(c->device));
     HostStage& h = c->hs[0];
     eh_status s = ensure_host_stage(c, h, B);
@@ -1641,7 +1649,6 @@ eh_status eh_step_host_async(eh_ctx* c, int64_t B, const float* X, const float* 
 {
     if (!c) return EH_EINVAL;
     if (B <= 0 || !X || !targ) return fail(c, EH_EINVAL, "bad eh_step_host_async arguments");
-    if (c->wide) return fail(c, EH_EUNSUPPORTED, "host-batch steps are not available on the wide (bf16 tcgen05) path: stage the split with eh_upload");
     CK(cudaSetDevice(c->device));
     if (c->async_used == c->async_cap) {
         if (c->async_used) {

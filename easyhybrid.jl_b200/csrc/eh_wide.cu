@@ -289,12 +289,12 @@ cudaError_t WideNet::refresh_images(float* pblock, float* m, float* v, void* ost
     return cudaSuccess;
 }
 
-cudaError_t WideNet::forward(const float* rec, const int* idx, long long rec_base, long long nrec, int B, const float* bscal,
-                             const float* pblock, cudaStream_t st)
+cudaError_t WideNet::forward(const float* rec, const int* idx, long long rec_base, long long nrec, int B, int Bvalid,
+                             const float* bscal, const float* pblock, cudaStream_t st)
 {
     const int H = m_.H;
     const WideDims d = dims_of(m_);
-    k_wide_gather<<<(B + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float4*>(rec), idx, rec_base, nrec, B, m_.R4 / 4,
+    k_wide_gather<<<(B + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float4*>(rec), idx, rec_base, nrec, B, Bvalid, m_.R4 / 4,
                                                    reinterpret_cast<float4*>(xb_));
     WN(cudaGetLastError());
     const int rows_per_cta = (256 / (H / 8)) * FIRST_ROWS;
@@ -307,21 +307,23 @@ cudaError_t WideNet::forward(const float* rec, const int* idx, long long rec_bas
     return cudaSuccess;
 }
 
-cudaError_t WideNet::step(const float* rec, const int* idx, long long rec_base, int B, const float* bscal, float* pblock, float* m,
-                          float* v, void* ost, float* grad_final, float* loss_out, int apply, cudaStream_t st, const WideDp* dp)
+cudaError_t WideNet::step(const float* rec, const int* idx, long long rec_base, int Bvalid, const float* bscal, float* pblock,
+                          float* m, float* v, void* ost, float* grad_final, float* loss_out, int apply, cudaStream_t st,
+                          const WideDp* dp)
 {
     const int H = m_.H, NH = m_.NH;
+    const int B = (Bvalid + 127) / 128 * 128;   // GEMM tiles are 128 rows: padded rows are masked in the head kernel
     const bool isdp = dp && dp->world > 1;
     const int par = isdp ? (int)(dp->tag & 1u) : 0;
     // data parallel: this rank's gradient goes into its exchange block, the all-reduce leaves the sum in grad_final
     float* grad = isdp ? dp->peer[dp->rank] + (size_t)par * dp_xlen() : grad_final;
     WN(ensure(B));
-    WN(forward(rec, idx, rec_base, 1ll << 62, B, bscal, pblock, st));
+    WN(forward(rec, idx, rec_base, 1ll << 62, B, Bvalid, bscal, pblock, st));
     const WideDims d = dims_of(m_);
     HeadKernel hk = find_head(m_.pm, m_.NOUT, m_.scale, H / 256);
     HeadArgs ha{};
     ha.A = A_[NH - 1]; ha.xb = xb_; ha.pblock = pblock; ha.bscal = bscal; ha.D = D_[NH & 1]; ha.partial = head_partial_;
-    ha.d = d; ha.B = B; ha.Bvalid = B; ha.act = m_.act; ha.train = 1;
+    ha.d = d; ha.B = B; ha.Bvalid = Bvalid; ha.act = m_.act; ha.train = 1;
     ha.prog = reinterpret_cast<const PmProgData*>(d_prog_); ha.nf = m_.F; ha.nt = m_.T;
     for (int t = 0; t < 4; t++) ha.loss_kind[t] = m_.loss_kind[t];
     for (int s = 0; s < 8; s++) { ha.slot[s].role = m_.slot[s].role; ha.slot[s].idx = m_.slot[s].idx; ha.slot[s].lo = m_.slot[s].lo; ha.slot[s].span = m_.slot[s].span; ha.slot[s].fixedv = m_.slot[s].fixedv; }
@@ -398,7 +400,7 @@ cudaError_t WideNet::eval_rows(const float* rec, long long nrec, long long row0,
     const int H = m_.H, NH = m_.NH;
     const int B = (Bvalid + 127) / 128 * 128;
     WN(ensure(B));
-    WN(forward(rec, nullptr, row0, nrec, B, bscal, pblock, st));
+    WN(forward(rec, nullptr, row0, nrec, B, B, bscal, pblock, st));
     HeadKernel hk = find_head(m_.pm, m_.NOUT, m_.scale, H / 256);
     HeadArgs ha{};
     ha.A = A_[NH - 1]; ha.xb = xb_; ha.pblock = pblock; ha.bscal = bscal; ha.D = nullptr; ha.partial = nullptr;

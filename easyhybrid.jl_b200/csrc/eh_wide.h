@@ -54,8 +54,8 @@ public:
     static int padded_width(int hmax) { return hmax <= 256 ? 256 : 512; }
     static WideNet* create(const WideModel& m, char* err, size_t errlen);
     ~WideNet();
-    // largest batch the path accepts is bounded only by memory; B must be a multiple of 128
-    static bool batch_ok(long long B) { return B > 0 && B % 128 == 0; }
+    // any batch size: rows are padded up to a multiple of 128 inside and masked
+    static bool batch_ok(long long B) { return B > 0 && B < (1ll << 30); }
     // bf16 weight images from the fp32 master parameters (after eh_set_params)
     cudaError_t refresh_images(float* pblock, float* m, float* v, void* ost, cudaStream_t st);
     // one optimiser step (apply = 1) or loss + gradient only (apply = 0) on `B` samples rec[idx[.]];
@@ -75,8 +75,8 @@ public:
 private:
     WideNet() {}
     cudaError_t ensure(int B);
-    cudaError_t forward(const float* rec, const int* idx, long long rec_base, long long nrec, int B, const float* bscal,
-                        const float* pblock, cudaStream_t st);
+    cudaError_t forward(const float* rec, const int* idx, long long rec_base, long long nrec, int B, int Bvalid,
+                        const float* bscal, const float* pblock, cudaStream_t st);
     WideModel m_{};
     int cap_ = 0, mapB_ = 0, n_head_ = 0, n_slab_ = 0, ksplit_ = 1;
     bool persist_ = true;

@@ -42,13 +42,15 @@ struct WideDims {
 };
 
 // ---- gather: rec[idx[b]] -> xb[b] ---------------------------------------------------------------------------
-// (rows past `nrec` -- padding of an evaluation chunk up to a multiple of 128 -- repeat the last record)
+// (rows past `Bvalid` -- padding of a batch up to a multiple of 128 -- repeat the batch's first record; the head
+// kernel masks them; rows past `nrec` of a contiguous evaluation chunk repeat the last record)
 __global__ void __launch_bounds__(256) k_wide_gather(const float4* rec, const int* idx, long long rec_base, long long nrec, int B,
-                                                     int R4q, float4* xb)
+                                                     int Bvalid, int R4q, float4* xb)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
-    long long i = idx ? (long long)idx[b] : rec_base + b;
+    const int bs = b < Bvalid ? b : 0;
+    long long i = idx ? (long long)idx[bs] : rec_base + bs;
     if (i >= nrec) i = nrec - 1;
     for (int q = 0; q < R4q; q++) xb[(size_t)b * R4q + q] = __ldg(rec + i * R4q + q);
 }
@@ -199,7 +201,8 @@ __global__ void __launch_bounds__(256) k_wide_head(const HeadArgs a)
 #pragma unroll
         for (int q = 0; q < 8; q++) est[t][q] = 0.0;
 
-    for (int b = blockIdx.x * 8 + warp; b < a.Bvalid; b += gridDim.x * 8) {
+    for (int b = blockIdx.x * 8 + warp; b < (a.train ? a.B : a.Bvalid); b += gridDim.x * 8) {
+        const bool rowvalid = b < a.Bvalid;   // rows beyond: padding of the batch up to a multiple of 128 (train mode)
         float av[HCH][8];
         float zo[NOUT];
 #pragma unroll
@@ -252,7 +255,7 @@ __global__ void __launch_bounds__(256) k_wide_head(const HeadArgs a)
         }
 #pragma unroll
         for (int t = 0; t < T; t++) {
-            const bool m = (y[t] == y[t]);   // valid_mask = !isnan(y), src/training/train.jl:221-232
+            const bool m = rowvalid && (y[t] == y[t]);   // valid_mask = !isnan(y), src/training/train.jl:221-232
             const float rr = m ? yh[t] - y[t] : 0.f;
             const float c = a.bscal[BS_C + t];
             if (a.loss_kind[t] == LOSS_MAE) {

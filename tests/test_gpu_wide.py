@@ -189,3 +189,44 @@ def test_traced_process_model_runs_on_the_tensor_core_path(eh, orc):
     yhat, stats, par = sess.eval(0, want_yhat=True, want_params=True)
     assert np.allclose(yhat, o.forward(ps, xf, precision=64), rtol=3e-2, atol=3e-2)
     sess.close()
+
+
+def test_wide_ragged_batches_and_host_batches(eh, orc):
+    """batch sizes that are no multiple of the 128-row GEMM tile (partial last batch of an epoch,
+    src/data/loaders.jl:1-12 with partial = true) are padded and masked inside; host batches
+    (collect_dim_data |> gdev) take the same path"""
+    model = wide_model(eh, hidden=(256, 256), two=False)
+    n, B = 2500, 700                      # 4 batches: 700, 700, 700, 400
+    data = make_expo2(n, nan_frac=0.0)
+    xf, y = eh.prepare_data(model, data)
+    rng = np.random.default_rng(21)
+    flat = model.initialparameters(rng)
+    sess = eh.FusedSession(model, training_loss="mse", opt=eh.Adam(0.001))
+    sess.upload(0, xf, y)
+    sess.set_params(flat)
+    o = orc.Oracle(model, training_loss="mse", opt=eh.Adam(0.001))
+    for Bq in (333, 1, 129):
+        idx = rng.permutation(n)[:Bq]
+        L, g = sess.loss_grad(idx)
+        L64, g64 = o.loss_grad(flat, xf, y, idx, precision=64)
+        assert abs(L - L64) <= RTOL_LOSS * abs(L64), (Bq, L, L64)
+        cos = float(g @ g64 / (np.linalg.norm(g) * np.linalg.norm(g64)))
+        assert cos >= COS_MIN, (Bq, cos)
+    perm = rng.permutation(n)
+    got = sess.epoch(perm, B)
+    ref = flat.copy()
+    want = o.train_steps(ref, xf, y, perm, B)
+    assert got.shape == (4,) and np.allclose(got, want, rtol=3e-2), (got, want)
+    # the same four batches as host arrays
+    sess.set_params(flat)
+    sess.set_opt_state(None, None, 0)
+    losses = sess.pinned(np.zeros(4, dtype=np.float32))
+    keep = []
+    for k in range(4):
+        idx = perm[k * B:(k + 1) * B]
+        hb = sess.host_batch(sess.pinned(xf[0][idx]), [sess.pinned(xf[1]["T"][idx])], [sess.pinned(y["Resp_obs"][idx])])
+        keep.append(hb)
+        sess.step_host_async(hb, losses, k)
+    sess.sync()
+    assert np.allclose(np.asarray(losses), got, rtol=1e-5), (np.asarray(losses), got)
+    sess.close()
