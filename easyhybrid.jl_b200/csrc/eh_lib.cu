@@ -66,6 +66,7 @@ struct eh_ctx {
     eh::wide::WideNet* wide = nullptr;
     Variant wide_var{};
     eh::wide::WideModel wide_model{};
+    std::vector<int> h_wmap;        // [nflat][4] {kind, layer, image row, image column} of the embedded chain
     // model
     int n_pred_raw = 0, n_forc_raw = 0, n_targ = 0;
     int nflat = 0, ntheta = 0, nglob = 0;
@@ -907,12 +908,194 @@ eh_status epoch_pipelined(eh_ctx* c, const int64_t* perm1, int64_t n, int64_t B,
     return EH_OK;
 }
 
+// Plan for the tensor-core path: one or several Dense chains embedded block-diagonally into one padded chain
+// (eh_wide_kernels.cuh, WideDims).  Fills the parts of the ctx the shared host code reads (record layout, slots, loss,
+// optimiser) and the WideModel handed to WideNet::create.
+eh_status build_plan_wide(eh_ctx* c, const eh_model_desc* d, bool is_prog)
+{
+    const int NC = d->n_chains;
+    const eh_chain_desc& c0 = d->chains[0];
+    const int NH = c0.n_hidden;
+    int P = 0, NOUT = 0, wl[8] = {0};
+    for (int k = 0; k < NC; k++) {
+        const eh_chain_desc& ch = d->chains[k];
+        if (ch.n_hidden != NH || ch.activation != c0.activation || (ch.input_batchnorm != 0) != (c0.input_batchnorm != 0))
+            return fail(c, EH_EUNSUPPORTED, "chains of one model must share depth, activation and input_batchnorm on the tensor-core path");
+        if (ch.n_in < 1 || ch.n_out < 1) return fail(c, EH_EINVAL, "chain %d: n_in / n_out must be positive", k);
+        P += ch.n_in;
+        NOUT += ch.n_out;
+        for (int l = 0; l < ch.n_hidden && l < 8; l++) {
+            if (ch.hidden[l] < 1) return fail(c, EH_EINVAL, "chain %d: hidden width must be positive", k);
+            wl[l] += ch.hidden[l];
+        }
+    }
+    int hmax = 0;
+    for (int l = 0; l < NH && l < 8; l++) hmax = std::max(hmax, wl[l]);
+    if (NH > 7 || !eh::wide::WideNet::supported(P, hmax, NH, NOUT, c0.activation, d->process_model))
+        return fail(c, EH_EUNSUPPORTED,
+                    "no fused kernel for this model: the register-tile kernels serve one chain of two hidden layers of width <= 32 "
+                    "with a built-in process model (all activations, <= 12 inputs); the tensor-core path serves 1..4 chains of equal "
+                    "depth (2..6 hidden layers, summed width per layer <= 512, <= 4 inputs and <= 2 outputs in total, tanh / sigmoid "
+                    "/ relu) (got process_model=%d chains=%d inputs=%d hidden=%d x (<= %d) outputs=%d activation=%d)",
+                    d->process_model, NC, P, NH, hmax, NOUT, c0.activation);
+    const int HP = eh::wide::WideNet::padded_width(hmax);
+    Variant& wv = c->wide_var;
+    memset(&wv, 0, sizeof wv);
+    wv.pm = d->process_model; wv.P = P; wv.NH = NH; wv.H = HP; wv.NOUT = NOUT; wv.act = c0.activation;
+    wv.scale = d->scale_nn_outputs ? 1 : 0;
+    wv.engine = 3; wv.chunk = 128;
+    wv.F = is_prog ? d->n_forc : 1; wv.NPS = is_prog ? d->n_params : 2;
+    wv.T = is_prog ? d->n_targ : ((d->process_model == EH_PM_LINEAR2 || d->process_model == EH_PM_EXPO2) ? 2 : 1);
+    wv.R4 = rup4(wv.P + wv.F + wv.T);
+    wv.NW = 0; wv.NPART = NSTAT; wv.off_stats = 0; wv.stage_floats = NSTAT; wv.max_warps = 8;
+    wv.name = "wide/bf16-tcgen05";
+    if (wv.T != d->n_targ) return fail(c, EH_EINVAL, "process model yields %d targets, descriptor has %d", wv.T, d->n_targ);
+    const Variant* v = &wv;
+    c->var = v; c->var2 = nullptr;
+    c->n_pred_raw = d->n_pred; c->n_forc_raw = d->n_forc; c->n_targ = d->n_targ;
+    c->use_bn = c0.input_batchnorm ? 1 : 0;
+    c->real_in = P;
+    c->flags = (unsigned)d->flags;
+    c->persist_ok = false;
+    c->pm_id = d->process_model;
+
+    // flat layout (reference ComponentArray order): chain after chain, per layer W (out x in, column-major) then b; then phi.
+    // Embedding: chain k owns units [uoff[l], uoff[l] + h) of hidden layer l, inputs [ioff, ioff + n_in), outputs [ooff, ..)
+    c->h_wmap.assign((size_t)0, 0);
+    eh::wide::WideModel& wm = c->wide_model;
+    memset(&wm, 0, sizeof wm);
+    int off = 0, ioff = 0, ooff = 0, uoff[8] = {0};
+    std::vector<int> out_row0((size_t)NC, 0);
+    auto push = [&](int kind, int l, int r, int cc) { c->h_wmap.push_back(kind); c->h_wmap.push_back(l); c->h_wmap.push_back(r); c->h_wmap.push_back(cc); };
+    for (int k = 0; k < NC; k++) {
+        const eh_chain_desc& ch = d->chains[k];
+        out_row0[k] = ooff;
+        for (int l = 1; l <= NH + 1; l++) {
+            const int hout = l <= NH ? ch.hidden[l - 1] : ch.n_out;
+            const int hin = l == 1 ? ch.n_in : ch.hidden[l - 2];
+            const int ro = l <= NH ? uoff[l - 1] : ooff;             // image row origin (output units)
+            const int co = l == 1 ? ioff : uoff[l - 2];              // image column origin (input units)
+            if (l >= 2 && l <= NH) {
+                if (wm.n_blocks >= 32) return fail(c, EH_EUNSUPPORTED, "too many weight blocks");
+                auto& bk = wm.blocks[wm.n_blocks++];
+                bk.l = l; bk.flat_off = off; bk.hout = hout; bk.hin = hin; bk.o_off = ro; bk.i_off = co;
+            }
+            const int kind = l == 1 ? eh::wide::WK_W1 : (l <= NH ? eh::wide::WK_WH : eh::wide::WK_WO);
+            for (int i = 0; i < hin; i++)
+                for (int o = 0; o < hout; o++) push(kind, l, ro + o, co + i);
+            off += hout * hin;
+            for (int o = 0; o < hout; o++) push(l <= NH ? eh::wide::WK_B : eh::wide::WK_BO, l, ro + o, 0);
+            off += hout;
+        }
+        for (int l = 0; l < NH; l++) uoff[l] += ch.hidden[l];
+        ioff += ch.n_in;
+        ooff += ch.n_out;
+    }
+    c->ntheta = off;
+    int ng = 0;
+    for (int p = 0; p < d->n_params; p++)
+        if (d->role[p] == EH_ROLE_GLOBAL) ng = std::max(ng, d->role_index[p] + 1);
+    c->nglob = ng;
+    c->nflat = off + ng;
+    for (int g = 0; g < ng; g++) push(eh::wide::WK_PHI, 0, g, 0);
+    c->h_wsrc.assign((size_t)ng, -1);
+    for (int g = 0; g < ng; g++) c->h_wsrc[(size_t)g] = off + g;
+    c->h_pmap.assign((size_t)c->nflat, 0);
+    c->h_pspan.assign((size_t)c->nflat, 0.f);
+    c->h_cells.assign((size_t)2 * c->nflat, -1);
+
+    // canonical slots: built-in forms bind (param, param, forcing); traced programs address the parameter table directly
+    c->nparam_desc = d->n_params;
+    c->slot_of_param.assign((size_t)d->n_params, -1);
+    memset(c->slots, 0, sizeof c->slots);
+    for (int s = 0; s < MAXPS; s++) c->slots[s].role = ROLE_FIXED;
+    for (int s = 0; s < v->NPS; s++) {
+        const int pi = is_prog ? s : d->pm_args[s].index;
+        if (pi < 0 || pi >= d->n_params) return fail(c, EH_EINVAL, "pm_args[%d].index out of range", s);
+        PSlot& sl = c->slots[s];
+        sl.role = d->role[pi];
+        sl.lo = d->lower[pi];
+        sl.span = d->upper[pi] - d->lower[pi];
+        sl.fixedv = d->deflt[pi];
+        if (sl.role == EH_ROLE_NEURAL) {
+            const int chain = d->role_index[pi] >> 16, row = d->role_index[pi] & 0xffff;
+            if (chain < 0 || chain >= NC || row >= d->chains[chain].n_out)
+                return fail(c, EH_EINVAL, "neural parameter %d refers to chain %d row %d", pi, chain, row);
+            sl.idx = out_row0[(size_t)chain] + row;
+        } else if (sl.role == EH_ROLE_GLOBAL) {
+            sl.idx = d->role_index[pi];
+        }
+        c->slot_of_param[pi] = s;
+    }
+    for (int i = 0; i < 4; i++) c->pmc[i] = d->pm_consts[i];
+    c->h_slot_of_flat.assign((size_t)c->nflat, -1);
+    for (int g = 0; g < ng; g++)
+        for (int s = 0; s < v->NPS; s++)
+            if (c->slots[s].role == ROLE_GLOBAL && c->slots[s].idx == g) c->h_slot_of_flat[(size_t)off + g] = s;
+
+    // record columns: the chains' inputs one after the other, forcing(s), targets
+    c->ncols = 0;
+    for (int k = 0; k < NC; k++)
+        for (int q = 0; q < d->chains[k].n_in; q++) {
+            const int col = d->chains[k].in_cols[q];
+            if (col < 0 || col >= d->n_pred) return fail(c, EH_EINVAL, "chain %d in_cols[%d] out of range", k, q);
+            c->src_kind[c->ncols] = 0; c->src_idx[c->ncols] = col; c->ncols++;
+        }
+    if (is_prog) {
+        for (int fi = 0; fi < d->n_forc; fi++) { c->src_kind[c->ncols] = 1; c->src_idx[c->ncols] = fi; c->ncols++; }
+    } else {
+        const int fi = d->pm_args[2].index;
+        if (fi < 0 || fi >= d->n_forc) return fail(c, EH_EINVAL, "forcing index out of range");
+        c->src_kind[c->ncols] = 1; c->src_idx[c->ncols] = fi; c->ncols++;
+    }
+    for (int t = 0; t < d->n_targ; t++) { c->src_kind[c->ncols] = 1; c->src_idx[c->ncols] = d->n_forc + t; c->ncols++; }
+
+    // loss / optimiser
+    int n_rmse = 0;
+    for (int t = 0; t < d->n_targ; t++) {
+        const int lk = d->loss_per_target[t];
+        if (lk < 0 || lk > 3) return fail(c, EH_EINVAL, "loss_per_target[%d]=%d unknown", t, lk);
+        c->loss_kind[t] = lk;
+        if (lk == EH_LOSS_RMSE) n_rmse++;
+    }
+    if (n_rmse && d->n_targ > 1) return fail(c, EH_EUNSUPPORTED, "rmse training loss with more than one target");
+    c->agg_mean = d->agg == EH_AGG_MEAN;
+    c->opt_kind = d->opt_kind;
+    if (c->opt_kind < 0 || c->opt_kind > 3) return fail(c, EH_EINVAL, "opt_kind=%d unknown", d->opt_kind);
+    c->adamw_coupled = d->adamw_decay_coupled_eta;
+    c->eta = d->eta; c->beta1 = d->beta1; c->beta2 = d->beta2; c->eps = d->eps; c->lambda = d->lambda;
+    c->bn_mean.assign((size_t)P, 0.f);
+    c->bn_var.assign((size_t)P, 1.f);
+
+    wm.P = P; wm.H = HP; wm.NH = NH; wm.NOUT = NOUT; wm.R4 = v->R4; wm.nflat = c->nflat; wm.ntheta = c->ntheta;
+    wm.h_map = c->h_wmap.data();
+    wm.act = c0.activation; wm.scale = d->scale_nn_outputs ? 1 : 0; wm.pm = d->process_model;
+    wm.T = v->T; wm.F = v->F; wm.NPS = v->NPS; wm.use_bn = c->use_bn; wm.agg_mean = c->agg_mean;
+    for (int t = 0; t < MAXT; t++) wm.loss_kind[t] = c->loss_kind[t];
+    for (int s2 = 0; s2 < MAXPS; s2++) {
+        wm.slot[s2].role = c->slots[s2].role; wm.slot[s2].idx = c->slots[s2].idx; wm.slot[s2].lo = c->slots[s2].lo;
+        wm.slot[s2].span = c->slots[s2].span; wm.slot[s2].fixedv = c->slots[s2].fixedv;
+    }
+    for (int i = 0; i < 4; i++) wm.pmc[i] = c->pmc[i];
+    wm.opt_kind = c->opt_kind; wm.adamw_coupled = c->adamw_coupled;
+    wm.eta = c->eta; wm.beta1 = c->beta1; wm.beta2 = c->beta2; wm.eps = c->eps; wm.lambda = c->lambda;
+    wm.nsm = c->nsm;
+    if (is_prog) {
+        wm.prog_len = d->pm_len;
+        for (int i = 0; i < d->pm_len; i++) {
+            wm.prog_op[i] = (short)d->pm_prog[i].op; wm.prog_a[i] = (short)d->pm_prog[i].a; wm.prog_b[i] = (short)d->pm_prog[i].b;
+            wm.prog_imm[i] = d->pm_prog[i].imm;
+        }
+        for (int t = 0; t < d->n_targ; t++) wm.prog_out[t] = d->pm_outputs[t];
+    }
+    return EH_OK;
+}
+
 eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
 {
     if (d->abi_version != EH_ABI_VERSION) return fail(c, EH_EINVAL, "abi_version %d != %d", d->abi_version, EH_ABI_VERSION);
     if (d->n_targ < 1 || d->n_targ > MAXT) return fail(c, EH_EUNSUPPORTED, "n_targ=%d not in 1..%d", d->n_targ, MAXT);
-    if (d->n_chains != 1)
-        return fail(c, EH_EUNSUPPORTED, "n_chains=%d: only single-chain models have a fused kernel in this build", d->n_chains);
+    if (d->n_chains < 1 || d->n_chains > 4) return fail(c, EH_EUNSUPPORTED, "n_chains=%d not in 1..4", d->n_chains);
     const bool is_prog = d->process_model == EH_PM_PROGRAM;
     if (is_prog) {
         // a traced process model: validated here, interpreted per sample by the tensor-core path's head kernel
@@ -943,30 +1126,11 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
     // Which path?  The exact-fp32 register-tile kernels exist for two hidden layers of width <= 32; every other chain
     // (wider or deeper, up to 6 hidden layers of up to 512 units, padded to 256 / 512 internally) runs on the bf16
     // tcgen05 GEMM path.
-    bool wide = false;
-    const bool have_small = !is_prog && hmax <= 32 && find_variant(d->process_model, ch.n_in, ch.n_hidden, rup4(hmax), ch.n_out, ch.activation,
-                                                       d->scale_nn_outputs ? 1 : 0, 0) != nullptr;
-    if (!have_small) {
-        if (!eh::wide::WideNet::supported(ch.n_in, hmax, ch.n_hidden, ch.n_out, ch.activation, d->process_model))
-            return fail(c, EH_EUNSUPPORTED,
-                        "no fused kernel for this chain: the register-tile kernels serve two hidden layers of width <= 32 (all "
-                        "activations, <= 12 inputs), the tensor-core path 2..6 hidden layers of width <= 512 with <= 4 inputs, "
-                        "<= 2 outputs and a tanh / sigmoid / relu activation (got process_model=%d n_in=%d hidden=%d x (<= %d) "
-                        "n_out=%d activation=%d scale_nn_outputs=%d)",
-                        d->process_model, ch.n_in, ch.n_hidden, hmax, ch.n_out, ch.activation, d->scale_nn_outputs);
-        wide = true;
-        Variant& wv = c->wide_var;
-        memset(&wv, 0, sizeof wv);
-        wv.pm = d->process_model; wv.P = ch.n_in; wv.NH = ch.n_hidden; wv.H = eh::wide::WideNet::padded_width(hmax);
-        wv.NOUT = ch.n_out; wv.act = ch.activation;
-        wv.scale = d->scale_nn_outputs ? 1 : 0;
-        wv.engine = 3; wv.chunk = 128;
-        wv.F = is_prog ? d->n_forc : 1; wv.NPS = is_prog ? d->n_params : 2;
-        wv.T = is_prog ? d->n_targ : ((d->process_model == EH_PM_LINEAR2 || d->process_model == EH_PM_EXPO2) ? 2 : 1);
-        wv.R4 = rup4(wv.P + wv.F + wv.T);
-        wv.NW = 0; wv.NPART = NSTAT; wv.off_stats = 0; wv.stage_floats = NSTAT; wv.max_warps = 8;
-        wv.name = "wide/bf16-tcgen05";
-    }
+    const bool wide = false;   // (this function continues with the register-tile plan only)
+    const bool have_small = d->n_chains == 1 && !is_prog && hmax <= 32 &&
+                            find_variant(d->process_model, ch.n_in, ch.n_hidden, rup4(hmax), ch.n_out, ch.activation,
+                                         d->scale_nn_outputs ? 1 : 0, 0) != nullptr;
+    if (!have_small) return build_plan_wide(c, d, is_prog);
     // engine 0 (exact-fp32 FFMA2) by default; engine 1 (tensor pipe, 3xTF32) on request where a variant exists
     const Variant* v = wide ? &c->wide_var : nullptr;
     if (!v && (d->flags & EH_FLAG_TENSOR_PIPE))
@@ -1145,33 +1309,6 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
     c->eta = d->eta; c->beta1 = d->beta1; c->beta2 = d->beta2; c->eps = d->eps; c->lambda = d->lambda;
     c->bn_mean.assign((size_t)ch.n_in, 0.f);
     c->bn_var.assign((size_t)ch.n_in, 1.f);
-    if (wide) {
-        if (L > 8) return fail(c, EH_EUNSUPPORTED, "wide chains: at most 7 hidden layers");
-        eh::wide::WideModel& wm = c->wide_model;
-        memset(&wm, 0, sizeof wm);
-        wm.P = P; wm.H = H; wm.NH = NH; wm.NOUT = NOUT; wm.R4 = v->R4; wm.nflat = c->nflat; wm.ntheta = c->ntheta;
-        for (int l = 0; l < NH; l++) wm.hw[l] = ch.hidden[l];
-        for (int l = 0; l < L; l++) { wm.w_off[l] = w_off[l]; wm.b_off[l] = b_off[l]; }
-        wm.act = ch.activation; wm.scale = d->scale_nn_outputs ? 1 : 0; wm.pm = d->process_model;
-        wm.T = v->T; wm.F = v->F; wm.NPS = v->NPS; wm.use_bn = c->use_bn; wm.agg_mean = c->agg_mean;
-        for (int t = 0; t < MAXT; t++) wm.loss_kind[t] = c->loss_kind[t];
-        for (int s2 = 0; s2 < MAXPS; s2++) {
-            wm.slot[s2].role = c->slots[s2].role; wm.slot[s2].idx = c->slots[s2].idx; wm.slot[s2].lo = c->slots[s2].lo;
-            wm.slot[s2].span = c->slots[s2].span; wm.slot[s2].fixedv = c->slots[s2].fixedv;
-        }
-        for (int i = 0; i < 4; i++) wm.pmc[i] = c->pmc[i];
-        wm.opt_kind = c->opt_kind; wm.adamw_coupled = c->adamw_coupled;
-        wm.eta = c->eta; wm.beta1 = c->beta1; wm.beta2 = c->beta2; wm.eps = c->eps; wm.lambda = c->lambda;
-        wm.nsm = c->nsm;
-        if (is_prog) {
-            wm.prog_len = d->pm_len;
-            for (int i = 0; i < d->pm_len; i++) {
-                wm.prog_op[i] = (short)d->pm_prog[i].op; wm.prog_a[i] = (short)d->pm_prog[i].a; wm.prog_b[i] = (short)d->pm_prog[i].b;
-                wm.prog_imm[i] = d->pm_prog[i].imm;
-            }
-            for (int t = 0; t < d->n_targ; t++) wm.prog_out[t] = d->pm_outputs[t];
-        }
-    }
     return EH_OK;
 }
 

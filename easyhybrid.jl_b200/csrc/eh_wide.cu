@@ -149,7 +149,6 @@ WideDims dims_of(const WideModel& m)
 {
     WideDims d{};
     d.P = m.P; d.H = m.H; d.NH = m.NH; d.NOUT = m.NOUT; d.R4 = m.R4; d.nflat = m.nflat; d.ntheta = m.ntheta;
-    for (int i = 0; i < 8; i++) { d.w_off[i] = m.w_off[i]; d.b_off[i] = m.b_off[i]; d.hw[i] = m.hw[i]; }
     return d;
 }
 }  // namespace
@@ -189,21 +188,40 @@ WideNet* WideNet::create(const WideModel& m, char* err, size_t errlen)
     e = cudaFuncSetAttribute((const void*)hk, cudaFuncAttributeMaxDynamicSharedMemorySize, head_smem);
     if (e != cudaSuccess) return bail("head smem", e);
     const size_t HH = (size_t)m.H * m.H;
-    for (int l = 2; l <= m.NH; l++) {
+    const int bn = w->persist_ ? PG_BN : gemm_bn(GEMM_FWD);
+    // images of the embedded chain: everything outside the real entries (padding, other chains' units) stays zero
+    for (int l = 1; l <= m.NH; l++) {
+        if ((e = cudaMalloc(&w->Bp_[l - 1], (size_t)m.H * 4)) != cudaSuccess) return bail("cudaMalloc", e);
+        cudaMemset(w->Bp_[l - 1], 0, (size_t)m.H * 4);
+        if (l == 1) continue;
         if ((e = cudaMalloc(&w->Wf_[l - 1], HH * 2)) != cudaSuccess) return bail("cudaMalloc", e);
         if ((e = cudaMalloc(&w->Wb_[l - 1], HH * 2)) != cudaSuccess) return bail("cudaMalloc", e);
-        if ((e = cudaMalloc(&w->Bp_[l - 1], (size_t)m.H * 4)) != cudaSuccess) return bail("cudaMalloc", e);
-        // padding (rows / columns / bias entries beyond the real widths) stays zero for good
         cudaMemset(w->Wf_[l - 1], 0, HH * 2);
         cudaMemset(w->Wb_[l - 1], 0, HH * 2);
-        cudaMemset(w->Bp_[l - 1], 0, (size_t)m.H * 4);
-        const int bn = w->persist_ ? PG_BN : gemm_bn(GEMM_FWD);
         if (!make_map_bf16(&w->tmWf_[l - 1], w->Wf_[l - 1], m.H, m.H, m.H, bn) ||
             !make_map_bf16(&w->tmWb_[l - 1], w->Wb_[l - 1], m.H, m.H, m.H, bn)) {
             snprintf(err, errlen, "wide path: cuTensorMapEncodeTiled failed for a weight image");
             delete w;
             return nullptr;
         }
+    }
+    if ((e = cudaMalloc(&w->W1img_, (size_t)4 * m.H * 4)) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc(&w->WOimg_, (size_t)4 * m.H * 4)) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc(&w->BOimg_, 16)) != cudaSuccess) return bail("cudaMalloc", e);
+    cudaMemset(w->W1img_, 0, (size_t)4 * m.H * 4);
+    cudaMemset(w->WOimg_, 0, (size_t)4 * m.H * 4);
+    cudaMemset(w->BOimg_, 0, 16);
+    {
+        static_assert(sizeof(ParamMap) == 16, "ParamMap is four ints");
+        if ((e = cudaMalloc(&w->d_map_, (size_t)m.nflat * sizeof(ParamMap))) != cudaSuccess) return bail("cudaMalloc", e);
+        if ((e = cudaMemcpy(w->d_map_, m.h_map, (size_t)m.nflat * sizeof(ParamMap), cudaMemcpyHostToDevice)) != cudaSuccess) return bail("cudaMemcpy", e);
+        std::vector<int> small;
+        for (int p = 0; p < m.nflat; p++)
+            if (m.h_map[4 * p] != WK_WH) small.push_back(p);
+        w->n_small_ = (int)small.size();
+        if ((e = cudaMalloc(&w->d_small_, small.size() * sizeof(int) + 4)) != cudaSuccess) return bail("cudaMalloc", e);
+        if ((e = cudaMemcpy(w->d_small_, small.data(), small.size() * sizeof(int), cudaMemcpyHostToDevice)) != cudaSuccess) return bail("cudaMemcpy", e);
+        w->m_.h_map = nullptr;   // the caller's table is not retained
     }
     if (m.pm == PM_PROGRAM) {
         static_assert(PM_MAXLEN == 48, "WideModel program arrays");
@@ -233,7 +251,7 @@ WideNet::~WideNet()
         if (Bp_[i]) cudaFree(Bp_[i]);
         if (colsum_[i]) cudaFree(colsum_[i]);
     }
-    void* ps[] = {xb_, D_[0], D_[1], partial_, head_partial_, stats_, skip_, evalpart_, d_prog_};
+    void* ps[] = {xb_, D_[0], D_[1], partial_, head_partial_, stats_, skip_, evalpart_, d_prog_, W1img_, WOimg_, BOimg_, d_map_, d_small_};
     for (void* p : ps)
         if (p) cudaFree(p);
 }
@@ -282,7 +300,9 @@ cudaError_t WideNet::refresh_images(float* pblock, float* m, float* v, void* ost
     u.d = dims_of(m_);
     u.theta = pblock; u.m = m; u.v = v; u.ost = reinterpret_cast<OptState*>(ost);
     u.skip = skip_;
-    for (int l = 2; l <= m_.NH; l++) { u.Wf[l - 1] = Wf_[l - 1]; u.Wb[l - 1] = Wb_[l - 1]; u.Bp[l - 1] = Bp_[l - 1]; }
+    u.map = reinterpret_cast<const ParamMap*>(d_map_);
+    u.W1img = W1img_; u.WOimg = WOimg_; u.BOimg = BOimg_;
+    for (int l = 1; l <= m_.NH; l++) { u.Wf[l - 1] = Wf_[l - 1]; u.Wb[l - 1] = Wb_[l - 1]; u.Bp[l - 1] = Bp_[l - 1]; }
     u.apply = 0;
     k_wide_update<<<(m_.nflat + 255) / 256, 256, 0, st>>>(u);
     WN(cudaGetLastError());
@@ -298,7 +318,7 @@ cudaError_t WideNet::forward(const float* rec, const int* idx, long long rec_bas
                                                    reinterpret_cast<float4*>(xb_));
     WN(cudaGetLastError());
     const int rows_per_cta = (256 / (H / 8)) * FIRST_ROWS;
-    k_wide_first<<<(unsigned)((B + rows_per_cta - 1) / rows_per_cta), 256, 0, st>>>(xb_, pblock, bscal, m_.use_bn, d, B, m_.act, A_[0]);
+    k_wide_first<<<(unsigned)((B + rows_per_cta - 1) / rows_per_cta), 256, 0, st>>>(xb_, W1img_, Bp_[0], bscal, m_.use_bn, d, B, m_.act, A_[0]);
     WN(cudaGetLastError());
     for (int l = 2; l <= m_.NH; l++) {
         if (persist_) WN(gemm_fwd_p(tmA_k_[l - 2], tmWf_[l - 1], B, H, H, Bp_[l - 1], m_.act, A_[l - 1], st));
@@ -322,7 +342,8 @@ cudaError_t WideNet::step(const float* rec, const int* idx, long long rec_base, 
     const WideDims d = dims_of(m_);
     HeadKernel hk = find_head(m_.pm, m_.NOUT, m_.scale, H / 256);
     HeadArgs ha{};
-    ha.A = A_[NH - 1]; ha.xb = xb_; ha.pblock = pblock; ha.bscal = bscal; ha.D = D_[NH & 1]; ha.partial = head_partial_;
+    ha.A = A_[NH - 1]; ha.xb = xb_; ha.pblock = pblock; ha.WOimg = WOimg_; ha.BOimg = BOimg_; ha.bscal = bscal; ha.D = D_[NH & 1];
+    ha.partial = head_partial_;
     ha.d = d; ha.B = B; ha.Bvalid = Bvalid; ha.act = m_.act; ha.train = 1;
     ha.prog = reinterpret_cast<const PmProgData*>(d_prog_); ha.nf = m_.F; ha.nt = m_.T;
     for (int t = 0; t < 4; t++) ha.loss_kind[t] = m_.loss_kind[t];
@@ -334,8 +355,13 @@ cudaError_t WideNet::step(const float* rec, const int* idx, long long rec_base, 
     for (int l = NH; l >= 2; l--) {
         const int cur = l & 1, nxt = (l - 1) & 1;
         WN(gemm_wgrad(tmD_mn_[cur], tmA_mn_[l - 2], H, H, B, ksplit_, partial_, st));
-        k_wide_wreduce<<<dim3(H / 32, H / 32), 256, 0, st>>>(partial_, ksplit_, H, m_.hw[l - 1], m_.hw[l - 2], grad + m_.w_off[l - 1]);
-        WN(cudaGetLastError());
+        for (int bi = 0; bi < m_.n_blocks; bi++) {
+            const auto& bk = m_.blocks[bi];
+            if (bk.l != l) continue;
+            k_wide_wreduce<<<dim3((bk.hin + 31) / 32, (bk.hout + 31) / 32), 256, 0, st>>>(partial_, ksplit_, H, bk.hout, bk.hin, bk.o_off,
+                                                                                     bk.i_off, grad + bk.flat_off);
+            WN(cudaGetLastError());
+        }
         // backward data; its epilogue also leaves the 32-row column sums of D_{l-1} (bias gradient of layer l-1 and,
         // for layer 1, the x-weighted sums = its weight gradient)
         if (persist_)
@@ -347,13 +373,14 @@ cudaError_t WideNet::step(const float* rec, const int* idx, long long rec_base, 
     }
     FinArgs fa{};
     fa.d = d; fa.head_partial = head_partial_; fa.n_head = n_head_; fa.n_slab = n_slab_;
+    fa.map = reinterpret_cast<const ParamMap*>(d_map_); fa.small = d_small_; fa.n_small = n_small_;
     for (int l = 1; l < NH; l++) fa.colsum[l - 1] = colsum_[l - 1];
     fa.bscal = bscal; fa.theta = pblock; fa.grad = grad; fa.stats = stats_; fa.loss_out = loss_out;
     fa.T = m_.T; fa.agg_mean = m_.agg_mean;
     for (int t = 0; t < 4; t++) fa.loss_kind[t] = m_.loss_kind[t];
     for (int s = 0; s < 8; s++) fa.slot[s] = ha.slot[s];
     fa.slot_of_flat = m_.d_slot_of_flat; fa.skip_out = skip_; fa.dp = isdp ? 1 : 0;
-    k_wide_gradfin<<<(gradfin_count(d) + 31) / 32, 256, 0, st>>>(fa);
+    k_wide_gradfin<<<(n_small_ + 31) / 32, 256, 0, st>>>(fa);
     WN(cudaGetLastError());
     if (isdp) {
         AllredArgs ar{};
@@ -371,10 +398,12 @@ cudaError_t WideNet::step(const float* rec, const int* idx, long long rec_base, 
         WUpdArgs u{};
         u.d = d; u.theta = pblock; u.m = m; u.v = v; u.ost = reinterpret_cast<OptState*>(ost); u.grad = grad; u.skip = skip_;
         u.stats = stats_; u.bscal = bscal; u.T = m_.T;
+        u.map = reinterpret_cast<const ParamMap*>(d_map_);
+        u.W1img = W1img_; u.WOimg = WOimg_; u.BOimg = BOimg_;
         for (int t = 0; t < 4; t++) u.loss_kind[t] = m_.loss_kind[t];
         u.opt_kind = m_.opt_kind; u.adamw_coupled = m_.adamw_coupled;
         u.eta = m_.eta; u.beta1 = m_.beta1; u.beta2 = m_.beta2; u.eps = m_.eps; u.lambda = m_.lambda;
-        for (int l = 2; l <= NH; l++) { u.Wf[l - 1] = Wf_[l - 1]; u.Wb[l - 1] = Wb_[l - 1]; u.Bp[l - 1] = Bp_[l - 1]; }
+        for (int l = 1; l <= NH; l++) { u.Wf[l - 1] = Wf_[l - 1]; u.Wb[l - 1] = Wb_[l - 1]; u.Bp[l - 1] = Bp_[l - 1]; }
         u.apply = 1;
         k_wide_update<<<(m_.nflat + 255) / 256, 256, 0, st>>>(u);
         WN(cudaGetLastError());
@@ -403,7 +432,8 @@ cudaError_t WideNet::eval_rows(const float* rec, long long nrec, long long row0,
     WN(forward(rec, nullptr, row0, nrec, B, B, bscal, pblock, st));
     HeadKernel hk = find_head(m_.pm, m_.NOUT, m_.scale, H / 256);
     HeadArgs ha{};
-    ha.A = A_[NH - 1]; ha.xb = xb_; ha.pblock = pblock; ha.bscal = bscal; ha.D = nullptr; ha.partial = nullptr;
+    ha.A = A_[NH - 1]; ha.xb = xb_; ha.pblock = pblock; ha.WOimg = WOimg_; ha.BOimg = BOimg_; ha.bscal = bscal; ha.D = nullptr;
+    ha.partial = nullptr;
     ha.yhat = yhat; ha.parout = parout; ha.ldy = ldy; ha.row0 = row0; ha.evalstat = evalstat_dev ? evalpart_ : nullptr;
     for (int t = 0; t < 4; t++) { ha.shift_y[t] = shift_y[t]; ha.loss_kind[t] = m_.loss_kind[t]; }
     ha.d = dims_of(m_); ha.B = B; ha.Bvalid = Bvalid; ha.act = m_.act; ha.train = 0;

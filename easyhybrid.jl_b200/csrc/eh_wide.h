@@ -18,6 +18,9 @@ cudaError_t gemm_bwd(const CUtensorMap& tmD, const CUtensorMap& tmWt, int M, int
 cudaError_t gemm_wgrad(const CUtensorMap& tmD, const CUtensorMap& tmA, int M, int N, int Kall, int ksplits, float* partial,
                        cudaStream_t st);
 
+// where a flat parameter lives in the images of the embedded chain (== the WK_* enum of eh_wide_kernels.cuh)
+enum : int { WK_W1 = 0, WK_WH = 1, WK_B = 2, WK_WO = 3, WK_BO = 4, WK_PHI = 5 };
+
 struct WideDp {             // data-parallel state handed to WideNet::step
     int world, rank;
     float* peer[8];         // exchange blocks of all ranks as mapped in this process (own block at [rank])
@@ -28,9 +31,10 @@ struct WideDp {             // data-parallel state handed to WideNet::step
 struct PSlotH { int role, idx; float lo, span, fixedv; };   // == eh::PSlot (kept POD here: this header is host-only)
 
 struct WideModel {          // filled by eh_lib's planner from the model descriptor
-    int P, H, NH, NOUT, R4, nflat, ntheta;   // H: padded hidden width (256 / 512)
-    int hw[8];                               // real hidden widths (<= H)
-    int w_off[8], b_off[8];
+    int P, H, NH, NOUT, R4, nflat, ntheta;   // embedded chain: total inputs, padded hidden width (256 / 512), ...
+    const int* h_map;                        // [nflat][4] host: {kind, layer, image row, image column} per flat entry
+    int n_blocks;                            // hidden weight blocks (one per chain and hidden layer l >= 2)
+    struct { int l, flat_off, hout, hin, o_off, i_off; } blocks[32];
     int act, scale, pm, T, F, NPS, use_bn, agg_mean;
     int loss_kind[4];
     PSlotH slot[8];
@@ -49,7 +53,7 @@ struct WideModel {          // filled by eh_lib's planner from the model descrip
 // the wide-chain training step: owns activations / deltas / bf16 weight images / partial buffers
 class WideNet {
 public:
-    // hmax: widest hidden layer (padded up to 256 or 512 inside)
+    // hmax: widest embedded hidden layer (padded up to 256 or 512 inside)
     static bool supported(int P, int hmax, int NH, int NOUT, int act, int pm);
     static int padded_width(int hmax) { return hmax <= 256 ? 256 : 512; }
     static WideNet* create(const WideModel& m, char* err, size_t errlen);
@@ -86,6 +90,12 @@ private:
     __nv_bfloat16* Wf_[8] = {nullptr};
     __nv_bfloat16* Wb_[8] = {nullptr};
     float* Bp_[8] = {nullptr};
+    float* W1img_ = nullptr;
+    float* WOimg_ = nullptr;
+    float* BOimg_ = nullptr;
+    void* d_map_ = nullptr;    // ParamMap[nflat]
+    int* d_small_ = nullptr;   // flat indices assembled by k_wide_gradfin
+    int n_small_ = 0;
     void* d_prog_ = nullptr;   // PmProgData on the device
     float* partial_ = nullptr;
     float* colsum_[8] = {nullptr};

@@ -16,6 +16,7 @@
 #include <cuda_bf16.h>
 #include "eh_chunk.cuh"
 #include "eh_wide_gemm.cuh"
+#include "eh_wide.h"
 
 namespace eh {
 namespace wide {
@@ -30,15 +31,20 @@ __host__ __device__ constexpr int head_off_loss(int H, int NOUT) { return NOUT *
 __host__ __device__ constexpr int head_off_phi(int H, int NOUT) { return head_off_loss(H, NOUT) + MAXT; }
 __host__ __device__ constexpr int head_npart(int H, int NOUT) { return head_off_phi(H, NOUT) + MAXPS; }
 
+// Shape of the EMBEDDED chain the tensor-core path trains.  A model with several Dense chains (MultiNNHybridModel,
+// src/models/GenericHybridModel.jl:169-189: one chain per neural parameter) is embedded block-diagonally: chain c owns
+// the units [off_c, off_c + h_c) of every hidden layer, weights between units of different chains (and everything beyond
+// the real widths, up to the padded width H) are zeros in the bf16 / fp32 images and never receive an update, because
+// the optimiser only walks the flat parameter vector.  `ParamMap` says where a flat entry lives in the images.
 struct WideDims {
-    int P, H, NH, NOUT, R4;      // chain shape; floats per record.  H = PADDED hidden width (256 or 512): activation /
-                                 // delta rows, weight images and partial vectors are H wide
-    int hw[8];                   // real width of hidden layer l at [l-1] (<= H).  Units hw..H-1 of a layer are padding:
-                                 // zero weights in and out, so they never influence a result and receive no update
+    int P, H, NH, NOUT, R4;      // total chain inputs, padded hidden width (256 / 512), hidden layers, chain outputs, floats per record
     int nflat, ntheta;
-    // flat offsets (reference ComponentArray order): W_l is out x in column-major, i.e. index o + i * out
-    int w_off[8], b_off[8];      // layer l (1-based) at [l-1]; l = NH+1 is the output layer
-    __host__ __device__ int din(int l) const { return l == 1 ? P : hw[l - 2]; }   // real fan-in of hidden layer l
+};
+// kinds: WK_* (eh_wide.h)
+struct ParamMap {                // one per flat entry (reference ComponentArray order)
+    int kind;                    // WK_*
+    int l;                       // layer (1-based) for WK_W1 / WK_WH / WK_B
+    int r, c;                    // image row (output unit / chain output) and column (input unit / chain input / hidden unit)
 };
 
 // ---- gather: rec[idx[b]] -> xb[b] ---------------------------------------------------------------------------
@@ -60,26 +66,26 @@ __device__ __forceinline__ float dact_out(int act, float a) { return dact1(act, 
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) { return pack_bf16(lo, hi); }
 
 // ---- layer 1: A1[b][o] = act(b1[o] + sum_p xn[b][p] W1[o][p]) ----
+// W1img [P][H] / b1img [H]: fp32 images of the embedded first layer (zeros where a unit does not see an input).
 // A thread owns 8 consecutive outputs (their weights stay in registers) and walks FIRST_ROWS rows of the batch;
 // a CTA covers the whole width for 256 / (H / 8) row groups.
 constexpr int FIRST_ROWS = 16;
-__global__ void __launch_bounds__(256) k_wide_first(const float* xb, const float* theta, const float* bscal, int use_bn,
-                                                    WideDims d, int B, int act, __nv_bfloat16* A1)
+__global__ void __launch_bounds__(256) k_wide_first(const float* xb, const float* W1img, const float* b1img, const float* bscal,
+                                                    int use_bn, WideDims d, int B, int act, __nv_bfloat16* A1)
 {
     const int per_row = d.H / 8;                       // threads across the width
     const int groups = 256 / per_row;                  // row groups per CTA
     const int o0 = (threadIdx.x % per_row) * 8;
     const int r0 = (blockIdx.x * groups + threadIdx.x / per_row) * FIRST_ROWS;
     float bias[8], w[4][8], mu[4], rs[4];
-    const int h1 = d.hw[0];
 #pragma unroll
-    for (int j = 0; j < 8; j++) bias[j] = o0 + j < h1 ? __ldg(theta + d.b_off[0] + o0 + j) : 0.f;
+    for (int j = 0; j < 8; j++) bias[j] = __ldg(b1img + o0 + j);
 #pragma unroll
     for (int p = 0; p < 4; p++) {
         mu[p] = (use_bn && p < d.P) ? bscal[BS_BN + 2 * p] : 0.f;
         rs[p] = (use_bn && p < d.P) ? bscal[BS_BN + 2 * p + 1] : 1.f;
 #pragma unroll
-        for (int j = 0; j < 8; j++) w[p][j] = (p < d.P && o0 + j < h1) ? __ldg(theta + d.w_off[0] + o0 + j + p * h1) : 0.f;
+        for (int j = 0; j < 8; j++) w[p][j] = p < d.P ? __ldg(W1img + (size_t)p * d.H + o0 + j) : 0.f;
     }
     for (int b = r0; b < r0 + FIRST_ROWS && b < B; b++) {
         float z[8];
@@ -114,6 +120,8 @@ struct HeadArgs {
     const __nv_bfloat16* A;    // [B x H] last hidden activation
     const float* xb;           // [B x R4] compact batch records
     const float* pblock;       // flat theta/phi + tail
+    const float* WOimg;        // [NOUT][H] fp32 image of the embedded output layer
+    const float* BOimg;        // [4] its bias
     const float* bscal;        // per-batch scalar row
     __nv_bfloat16* D;          // out [B x H] delta of the last hidden layer
     float* partial;            // out [gridDim.x][head_npart]
@@ -163,8 +171,7 @@ __global__ void __launch_bounds__(256) k_wide_head(const HeadArgs a)
     for (int s = 0; s < MAXPS; s++)
         if (s >= NPS || a.slot[s].role != ROLE_NEURAL) cx.uniform_mask |= 1u << s;
 
-    // output-layer weights of my features: Wo[o][i] at wo_off + o + i * NOUT
-    const int wo = a.d.w_off[a.d.NH], bo = a.d.b_off[a.d.NH];
+    // output-layer weights of my features
     float w[NOUT][HCH][8];
 #pragma unroll
     for (int c = 0; c < HCH; c++)
@@ -172,11 +179,11 @@ __global__ void __launch_bounds__(256) k_wide_head(const HeadArgs a)
         for (int e = 0; e < 8; e++) {
             const int i = (c * 32 + lane) * 8 + e;
 #pragma unroll
-            for (int o = 0; o < NOUT; o++) w[o][c][e] = i < a.d.hw[a.d.NH - 1] ? a.pblock[wo + o + i * NOUT] : 0.f;
+            for (int o = 0; o < NOUT; o++) w[o][c][e] = a.WOimg[(size_t)o * H + i];
         }
     float bout[NOUT];
 #pragma unroll
-    for (int o = 0; o < NOUT; o++) bout[o] = a.pblock[bo + o];
+    for (int o = 0; o < NOUT; o++) bout[o] = a.BOimg[o];
 
     float gW[NOUT][HCH][8], gB[NOUT], gDb[HCH][8], lsum[MAXT], gphi[MAXPS];
     double est[T][8];
@@ -397,17 +404,21 @@ __global__ void __launch_bounds__(512) k_wide_colsum(const __nv_bfloat16* D, con
     }
 }
 
-// ---- split-K partials [S][H(o)][H(i)] -> flat gradient of W_l (index o + i * H), fixed summation order ----
-// (H = padded width of the partial tiles; the flat block is hout x hin, real widths)
-__global__ void __launch_bounds__(256) k_wide_wreduce(const float* partial, int S, int H, int hout, int hin, float* grad_w)
+// ---- split-K partials [S][H(o)][H(i)] -> flat gradient of one hidden weight block (index o + i * hout), fixed order ----
+// The block is the hout x hin matrix of one chain at layer l; it sits at rows o_off.., columns i_off.. of the H x H
+// product.  grid = (ceil(hin / 32), ceil(hout / 32)).
+__global__ void __launch_bounds__(256) k_wide_wreduce(const float* partial, int S, int H, int hout, int hin, int o_off, int i_off,
+                                                      float* grad_w)
 {
     __shared__ float tile[32][33];
     const int i0 = blockIdx.x * 32, o0 = blockIdx.y * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
     for (int r = ty; r < 32; r += 8) {
         float t[16];
+        const bool in = o0 + r < hout && i0 + tx < hin;
 #pragma unroll
-        for (int z = 0; z < 16; z++) t[z] = z < S ? __ldcs(partial + ((size_t)z * H + (o0 + r)) * H + i0 + tx) : 0.f;
+        for (int z = 0; z < 16; z++)
+            t[z] = (z < S && in) ? __ldcs(partial + ((size_t)z * H + (o_off + o0 + r)) * H + i_off + i0 + tx) : 0.f;
         float s = 0.f;
 #pragma unroll
         for (int z = 0; z < 16; z++) s += t[z];   // fixed order
@@ -420,12 +431,14 @@ __global__ void __launch_bounds__(256) k_wide_wreduce(const float* partial, int 
 
 struct FinArgs {
     WideDims d;
+    const ParamMap* map;                          // [nflat]
+    const int* small; int n_small;                // flat indices this kernel produces: everything but the hidden weight blocks
     const float* head_partial; int n_head;        // [n_head][head_npart]
-    const float* colsum[8]; int n_slab;           // per hidden layer l (index l-1): [n_slab][(1 + P1) * H], P1 = P for l = 1
+    const float* colsum[8]; int n_slab;           // per hidden layer l < NH (index l-1): [n_slab][(1 + P1) * H], P1 = P for l = 1
     const float* bscal;
     const float* theta;
-    float* grad;                                  // in/out flat gradient (hidden W_l, l >= 2, already there)
-    float* stats;                                 // out [MAXT] loss sums, [MAXT + q] unused
+    float* grad;                                  // in/out flat gradient (hidden weight blocks already there)
+    float* stats;                                 // out [MAXT] loss sums
     float* loss_out;                              // nullable
     int T, agg_mean;
     int loss_kind[MAXT];
@@ -436,18 +449,9 @@ struct FinArgs {
                                                   // gradient (grad[nflat + t]) and leave loss / skip to k_wide_allreduce
 };
 
-// number of flat entries k_wide_gradfin produces: W_1 + b_1 (contiguous), b_2 .. b_NH, then everything from the output
-// layer on (W_o, b_o, phi)
-__host__ __device__ inline int gradfin_count(const WideDims& d)
-{
-    int n = d.P * d.hw[0] + d.hw[0] + (d.nflat - d.w_off[d.NH]);
-    for (int l = 2; l <= d.NH; l++) n += d.hw[l - 1];
-    return n;
-}
-
-// ---- everything of the gradient that is not a hidden weight matrix, plus the loss value ----
-// 8 threads per entry walk the partial vectors (slabs of k_wide_colsum / CTAs of k_wide_head) with a stride of 8 and
-// combine in a fixed shuffle order: deterministic, and the dependent-load chains are 8x shorter.
+// ---- everything of the gradient that is not a hidden weight block, plus the loss value ----
+// 8 threads per entry walk the partial vectors (128-row slabs of the backward-data epilogues / CTAs of k_wide_head) with
+// a stride of 8 and combine in a fixed shuffle order: deterministic, and the dependent-load chains are 8x shorter.
 __global__ void __launch_bounds__(256) k_wide_gradfin(const FinArgs a)
 {
     const int H = a.d.H, NOUT = a.d.NOUT, NH = a.d.NH, P = a.d.P;
@@ -481,41 +485,28 @@ __global__ void __launch_bounds__(256) k_wide_gradfin(const FinArgs a)
         }
     }
     const int q = blockIdx.x * 32 + (threadIdx.x >> 3), zl = threadIdx.x & 7;
-    const int nq = gradfin_count(a.d);
-    const bool live = q < nq;
-    // entry q -> flat index p and the partial column that feeds it
-    int p = 0, cnt = 0;
+    const bool live = q < a.n_small;
+    int p = 0, cnt = 0, phi_slot = -1;
     size_t stride = 0;
     const float* src = nullptr;
-    int phi_slot = -1;
     bool is_phi = false;
     if (live) {
-        const int h1 = a.d.hw[0];
-        const int n1 = P * h1 + h1;
-        int nb2 = 0;   // entries of b_2 .. b_NH
-        for (int l = 2; l <= NH; l++) nb2 += a.d.hw[l - 1];
-        if (q < n1) {
-            p = a.d.w_off[0] + q;
-            const int col = q < P * h1 ? (1 + q / h1) * H + q % h1 : q - P * h1;   // W_1[o][k] lives at (1 + k) H + o, b_1 at o
-            src = a.colsum[0] + col; stride = (size_t)(1 + P) * H; cnt = a.n_slab;
-        } else if (q < n1 + nb2) {
-            int l = 2, o = q - n1;
-            while (o >= a.d.hw[l - 1]) { o -= a.d.hw[l - 1]; l++; }
-            p = a.d.b_off[l - 1] + o;
-            if (l == NH) { src = a.head_partial + head_off_dbh(H, NOUT) + o; stride = HP; cnt = a.n_head; }
-            else { src = a.colsum[l - 1] + o; stride = H; cnt = a.n_slab; }
-        } else {
-            p = a.d.w_off[NH] + (q - n1 - nb2);
-            const int wo = a.d.w_off[NH], bo = a.d.b_off[NH];
-            stride = HP; cnt = a.n_head;
-            if (p < bo) { const int o = (p - wo) % NOUT, i = (p - wo) / NOUT; src = a.head_partial + o * H + i; }
-            else if (p < bo + NOUT) src = a.head_partial + head_off_dbo(H, NOUT) + (p - bo);
-            else {
-                is_phi = true;
-                phi_slot = a.slot_of_flat[p];
-                src = a.head_partial + head_off_phi(H, NOUT) + (phi_slot >= 0 ? phi_slot : 0);
-                if (phi_slot < 0) cnt = 0;
-            }
+        p = a.small[q];
+        const ParamMap m = a.map[p];
+        if (m.kind == WK_W1) {            // W_1[r][c]: x-weighted column sums of D_1 live at (1 + c) H + r
+            src = a.colsum[0] + (size_t)(1 + m.c) * H + m.r; stride = (size_t)(1 + P) * H; cnt = a.n_slab;
+        } else if (m.kind == WK_B) {      // b_l[r]: column sums of D_l
+            if (m.l == NH) { src = a.head_partial + head_off_dbh(H, NOUT) + m.r; stride = HP; cnt = a.n_head; }
+            else { src = a.colsum[m.l - 1] + m.r; stride = (size_t)(m.l == 1 ? 1 + P : 1) * H; cnt = a.n_slab; }
+        } else if (m.kind == WK_WO) {
+            src = a.head_partial + (size_t)m.r * H + m.c; stride = HP; cnt = a.n_head;
+        } else if (m.kind == WK_BO) {
+            src = a.head_partial + head_off_dbo(H, NOUT) + m.r; stride = HP; cnt = a.n_head;
+        } else {                          // phi_raw
+            is_phi = true;
+            phi_slot = a.slot_of_flat[p];
+            src = a.head_partial + head_off_phi(H, NOUT) + (phi_slot >= 0 ? phi_slot : 0);
+            stride = HP; cnt = phi_slot >= 0 ? a.n_head : 0;
         }
     }
     float s = 0.f;
@@ -599,32 +590,36 @@ __global__ void __launch_bounds__(256) k_wide_allreduce(const AllredArgs a)
 
 struct WUpdArgs {
     WideDims d;
+    const ParamMap* map;
     float* theta; float* m; float* v; OptState* ost;
     const float* grad;
     const int* skip;
-    const float* stats;        // loss sums (for the rmse post factor of the hidden matrices)
+    const float* stats;        // loss sums (for the rmse post factor of the hidden blocks)
     const float* bscal;
     int loss_kind[MAXT]; int T;
     int opt_kind, adamw_coupled;
     float eta, beta1, beta2, eps, lambda;
+    // images of the embedded chain, all zero outside the real entries
+    float* W1img;              // [P][H] fp32
     __nv_bfloat16* Wf[8];      // [l-1], l = 2..NH: W_l as [out][in]  (B operand of the forward GEMM)
     __nv_bfloat16* Wb[8];      //                  W_l as [in][out]  (B operand of the backward-data GEMM)
-    float* Bp[8];              // [l-1], l = 2..NH: b_l padded to H floats (the forward GEMM's epilogue reads H of them)
+    float* Bp[8];              // [l-1], l = 1..NH: b_l padded to H floats
+    float* WOimg;              // [NOUT][H] fp32
+    float* BOimg;              // [4]
     int apply;                 // 0: only refresh the images from theta
 };
 
-// ---- optimiser over the flat vector (Optimisers.jl rules) + bf16 weight images ----
+// ---- optimiser over the flat vector (Optimisers.jl rules) + images for the next step ----
 __global__ void __launch_bounds__(256) k_wide_update(const WUpdArgs a)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= a.d.nflat) return;
+    const ParamMap mp = a.map[p];
     float th = a.theta[p];
     if (a.apply && !*a.skip) {
         float g = a.grad[p];
-        // hidden weight matrices come straight from the GEMM partials: apply the rmse factor here
-        bool hidden = false;
-        for (int l = 2; l <= a.d.NH; l++) hidden |= (p >= a.d.w_off[l - 1] && p < a.d.w_off[l - 1] + a.d.hw[l - 1] * a.d.hw[l - 2]);
-        if (hidden)
+        // hidden weight blocks come straight from the GEMM partials: apply the rmse factor here
+        if (mp.kind == WK_WH)
             for (int t = 0; t < a.T; t++)
                 if (a.loss_kind[t] == LOSS_RMSE) g *= 1.f / (2.f * sqrtf(a.stats[t] / a.bscal[BS_N + t]));
         const float b1t = a.ost->b1t, b2t = a.ost->b2t;
@@ -646,16 +641,19 @@ __global__ void __launch_bounds__(256) k_wide_update(const WUpdArgs a)
         th -= dx;
         a.theta[p] = th;
     }
-    for (int l = 2; l <= a.d.NH; l++) {
-        const int wo = a.d.w_off[l - 1], bo = a.d.b_off[l - 1], H = a.d.H, ho = a.d.hw[l - 1], hi = a.d.hw[l - 2];
-        if (p >= wo && p < wo + ho * hi) {
-            const int o = (p - wo) % ho, i = (p - wo) / ho;
-            const __nv_bfloat16 hb = __float2bfloat16_rn(th);
-            a.Wb[l - 1][(size_t)i * H + o] = hb;
-            a.Wf[l - 1][(size_t)o * H + i] = hb;
-        } else if (p >= bo && p < bo + ho) {
-            a.Bp[l - 1][p - bo] = th;
-        }
+    const int H = a.d.H;
+    if (mp.kind == WK_WH) {
+        const __nv_bfloat16 hb = __float2bfloat16_rn(th);
+        a.Wb[mp.l - 1][(size_t)mp.c * H + mp.r] = hb;
+        a.Wf[mp.l - 1][(size_t)mp.r * H + mp.c] = hb;
+    } else if (mp.kind == WK_W1) {
+        a.W1img[(size_t)mp.c * H + mp.r] = th;
+    } else if (mp.kind == WK_B) {
+        a.Bp[mp.l - 1][mp.r] = th;
+    } else if (mp.kind == WK_WO) {
+        a.WOimg[(size_t)mp.r * H + mp.c] = th;
+    } else if (mp.kind == WK_BO) {
+        a.BOimg[mp.r] = th;
     }
 }
 // step counters advance once per applied step (after k_wide_update of that step)

@@ -82,6 +82,14 @@ def expo2_model(eh, hidden=(16, 16), activation="tanh", scale=False):
                                    hidden_layers=list(hidden), activation=activation, scale_nn_outputs=scale)
 
 
+def rbq10_two_chain_model(eh, hidden=(16, 16), activation="tanh"):
+    """MultiNNHybridModel with two chains (src/models/GenericHybridModel.jl:169-189): rb and Q10 each get their own
+    network over their own predictors"""
+    return eh.constructHybridModel({"rb": ["sw_pot", "dsw_pot"], "Q10": ["ta"]}, ["ta"], ["reco"], eh.RbQ10,
+                                   dict(rb=(3.0, 0.0, 13.0), Q10=(2.0, 1.0, 4.0)), [],
+                                   hidden_layers=list(hidden), activation=activation, scale_nn_outputs=True)
+
+
 def linear_model(eh, two=False, activation="relu"):
     fn = eh.LinearModel2 if two else eh.LinearModel
     targets = ["var1", "var2"] if two else ["obs"]

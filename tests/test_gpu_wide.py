@@ -230,3 +230,42 @@ def test_wide_ragged_batches_and_host_batches(eh, orc):
     sess.sync()
     assert np.allclose(np.asarray(losses), got, rtol=1e-5), (np.asarray(losses), got)
     sess.close()
+
+
+def test_two_chain_model_embedded_block_diagonally(eh, orc):
+    """MultiNNHybridModel with a network per parameter (src/models/GenericHybridModel.jl:169-189, forward :458-530): the
+    two chains train as one block-diagonally embedded chain on the tensor-core path"""
+    from conftest import make_synth, rbq10_two_chain_model
+    model = rbq10_two_chain_model(eh, hidden=(24, 16))
+    n = 3000
+    xf, y = eh.prepare_data(model, make_synth(n, nan_frac=0.04), drop_missing_rows=False)
+    rng = np.random.default_rng(9)
+    flat = model.initialparameters(rng)
+    flat += (0.05 * rng.standard_normal(flat.size)).astype(np.float32)
+    sess = eh.FusedSession(model, training_loss="mse", opt=eh.Adam(0.01))
+    sess.upload(0, xf, y)
+    sess.set_params(flat)
+    o = orc.Oracle(model, training_loss="mse", opt=eh.Adam(0.01))
+    for B in (n, 500):
+        idx = rng.permutation(n)[:B]
+        L, g = sess.loss_grad(idx)
+        L64, g64 = o.loss_grad(flat, xf, y, idx, precision=64)
+        assert abs(L - L64) <= RTOL_LOSS * abs(L64), (B, L, L64)
+        # per chain: the gradient blocks of the flat vector
+        half = [slice(0, flat.size // 2 + 16), slice(flat.size // 2 + 16, flat.size)]
+        for sl in half + [slice(0, flat.size)]:
+            a, b = g[sl].astype(np.float64), g64[sl].astype(np.float64)
+            cos = float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b)))
+            assert cos >= COS_MIN, (B, sl, cos)
+            assert abs(np.linalg.norm(a) - np.linalg.norm(b)) <= RTOL_NORM * np.linalg.norm(b)
+    perm = np.concatenate([rng.permutation(n) for _ in range(6)])[: 30 * 512]
+    got = sess.epoch(perm, 512)
+    ref = flat.copy()
+    want = o.train_steps(ref, xf, y, perm, 512)
+    assert got[-1] < 0.5 * got[0]
+    assert np.allclose(got, want, rtol=5e-2, atol=1e-3), (got[-4:], want[-4:])
+    yhat, stats, par = sess.eval(0, want_yhat=True, want_params=True)
+    yo, po = o.forward(sess.get_params(), xf, precision=64, want_params=True)
+    assert np.allclose(yhat, yo, rtol=3e-2, atol=3e-2)
+    assert np.allclose(par, po, rtol=3e-2, atol=3e-2)   # both neural parameters per sample
+    sess.close()

@@ -5,7 +5,8 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import expo2_model, expo_model, linear_model, make_expo, make_expo2, make_linear, make_synth, rbq10_model
+from conftest import (expo2_model, expo_model, linear_model, make_expo, make_expo2, make_linear, make_synth, rbq10_model,
+                      rbq10_two_chain_model)
 from witness import objective
 
 
@@ -26,6 +27,8 @@ CASES = [
     ("linear2-mean", lambda eh: linear_model(eh, two=True, activation="tanh"), lambda: make_linear(400, two=True), "mse", "mean"),
     ("linear2-pertarget", lambda eh: linear_model(eh, two=True, activation="tanh"), lambda: make_linear(400, two=True), "PT", "sum"),
     # the two-target Expo form of the wide configuration (C5), here with a CPU-sized chain of three hidden layers
+    # two Dense chains (MultiNNHybridModel with a network per parameter)
+    ("rbq10-two-chains", lambda eh: rbq10_two_chain_model(eh), lambda: make_synth(300, nan_frac=0.05), "mse", "sum"),
     ("expo2-3x48-pertarget-nan", lambda eh: expo2_model(eh, hidden=(48, 48, 48)), lambda: make_expo2(300, nan_frac=0.1), "PT", "sum"),
 ]
 
