@@ -935,7 +935,7 @@ eh_status build_plan_wide(eh_ctx* c, const eh_model_desc* d, bool is_prog)
         return fail(c, EH_EUNSUPPORTED,
                     "no fused kernel for this model: the register-tile kernels serve one chain of two hidden layers of width <= 32 "
                     "with a built-in process model (all activations, <= 12 inputs); the tensor-core path serves 1..4 chains of equal "
-                    "depth (2..6 hidden layers, summed width per layer <= 512, <= 4 inputs and <= 2 outputs in total, tanh / sigmoid "
+                    "depth (2..6 hidden layers, summed width per layer <= 512, <= 8 inputs and <= 2 outputs in total, tanh / sigmoid "
                     "/ relu) (got process_model=%d chains=%d inputs=%d hidden=%d x (<= %d) outputs=%d activation=%d)",
                     d->process_model, NC, P, NH, hmax, NOUT, c0.activation);
     const int HP = eh::wide::WideNet::padded_width(hmax);

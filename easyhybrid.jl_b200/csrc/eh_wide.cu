@@ -164,7 +164,7 @@ WideDims dims_of(const WideModel& m)
 
 bool WideNet::supported(int P, int hmax, int NH, int NOUT, int act, int pm)
 {
-    if (P < 1 || P > 4 || NH < 2 || NH > 6 || NOUT < 1 || NOUT > 2) return false;
+    if (P < 1 || P > WIDE_MAXP || NH < 2 || NH > 6 || NOUT < 1 || NOUT > 2) return false;
     if (hmax < 1 || hmax > 512) return false;
     if (act != ACT_TANH && act != ACT_SIGMOID && act != ACT_RELU && act != ACT_IDENTITY) return false;
     return find_head(pm, NOUT, 0, padded_width(hmax) / 256) != nullptr;
@@ -205,10 +205,10 @@ WideNet* WideNet::create(const WideModel& m, char* err, size_t errlen)
             return nullptr;
         }
     }
-    if ((e = cudaMalloc(&w->W1img_, (size_t)4 * m.H * 4)) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc(&w->W1img_, (size_t)WIDE_MAXP * m.H * 4)) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc(&w->WOimg_, (size_t)4 * m.H * 4)) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc(&w->BOimg_, 16)) != cudaSuccess) return bail("cudaMalloc", e);
-    cudaMemset(w->W1img_, 0, (size_t)4 * m.H * 4);
+    cudaMemset(w->W1img_, 0, (size_t)WIDE_MAXP * m.H * 4);
     cudaMemset(w->WOimg_, 0, (size_t)4 * m.H * 4);
     cudaMemset(w->BOimg_, 0, 16);
     {

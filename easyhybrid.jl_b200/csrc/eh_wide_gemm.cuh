@@ -26,6 +26,7 @@ namespace eh {
 namespace wide {
 
 constexpr int BM = 128, BK = 64, UMMA_K = 16;
+constexpr int WIDE_MAXP = 8;          // chain inputs (all chains together) the tensor-core path takes
 constexpr int BS_BN_OFF = 3 * MAXT;   // == BS_BN of eh_chunk.cuh (per-batch scalar row: input BatchNorm mu / rstd)
 constexpr int GEMM_THREADS = 192;            // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2..5: epilogue
 // Tile width and pipeline depth per GEMM kind.
@@ -338,10 +339,10 @@ k_wide_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (MODE == GEMM_BWD && g.colsum != nullptr) {
             // column sums over this warp's 32 rows, straight from the staged bf16 strip: lane l owns columns 4l .. 4l+3
             __syncwarp();
-            float cs[4] = {0.f, 0.f, 0.f, 0.f}, cw[4][4];
-            float xr[4] = {0.f, 0.f, 0.f, 0.f};
+            float cs[4] = {0.f, 0.f, 0.f, 0.f}, cw[WIDE_MAXP][4];
+            float xr[WIDE_MAXP] = {0.f};
 #pragma unroll
-            for (int p = 0; p < 4; p++) {
+            for (int p = 0; p < WIDE_MAXP; p++) {
                 cw[p][0] = cw[p][1] = cw[p][2] = cw[p][3] = 0.f;
                 if (p < g.P1) {
                     float x = g.xb[(size_t)row * g.R4 + p];
@@ -356,7 +357,7 @@ k_wide_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.y));
                 cs[0] += f0.x; cs[1] += f0.y; cs[2] += f1.x; cs[3] += f1.y;
 #pragma unroll
-                for (int p = 0; p < 4; p++) {
+                for (int p = 0; p < WIDE_MAXP; p++) {
                     if (p < g.P1) {
                         const float x = __shfl_sync(0xffffffffu, xr[p], r);
                         cw[p][0] = fmaf(f0.x, x, cw[p][0]); cw[p][1] = fmaf(f0.y, x, cw[p][1]);
@@ -365,15 +366,15 @@ k_wide_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 }
             }
             // combine the four warps (fixed order) so that one 128-row slab per CTA goes out
-            float* s_cs = reinterpret_cast<float*>(gen_base + 4 * (32 * OPITCH));   // [4 warps][1 + P1][BN], behind the strips
-            *reinterpret_cast<float4*>(s_cs + (q * 5 + 0) * BN + lane * 4) = make_float4(cs[0], cs[1], cs[2], cs[3]);
+            float* s_cs = reinterpret_cast<float*>(gen_base + 4 * (32 * OPITCH));   // [4 warps][1 + WIDE_MAXP][BN], behind the strips
+            *reinterpret_cast<float4*>(s_cs + (q * (1 + WIDE_MAXP) + 0) * BN + lane * 4) = make_float4(cs[0], cs[1], cs[2], cs[3]);
 #pragma unroll
-            for (int p = 0; p < 4; p++)
-                if (p < g.P1) *reinterpret_cast<float4*>(s_cs + (q * 5 + 1 + p) * BN + lane * 4) = make_float4(cw[p][0], cw[p][1], cw[p][2], cw[p][3]);
+            for (int p = 0; p < WIDE_MAXP; p++)
+                if (p < g.P1) *reinterpret_cast<float4*>(s_cs + (q * (1 + WIDE_MAXP) + 1 + p) * BN + lane * 4) = make_float4(cw[p][0], cw[p][1], cw[p][2], cw[p][3]);
             asm volatile("bar.sync 1, 128;" ::: "memory");
             const int t = (warp - 2) * 32 + lane;   // column of the tile
             for (int p = 0; p <= g.P1; p++) {
-                const float v = ((s_cs[(0 * 5 + p) * BN + t] + s_cs[(1 * 5 + p) * BN + t]) + s_cs[(2 * 5 + p) * BN + t]) + s_cs[(3 * 5 + p) * BN + t];
+                const float v = ((s_cs[(0 * (1 + WIDE_MAXP) + p) * BN + t] + s_cs[(1 * (1 + WIDE_MAXP) + p) * BN + t]) + s_cs[(2 * (1 + WIDE_MAXP) + p) * BN + t]) + s_cs[(3 * (1 + WIDE_MAXP) + p) * BN + t];
                 g.colsum[((size_t)blockIdx.x * (1 + g.P1) + p) * g.N + n0 + t] = v;
             }
         }
@@ -571,12 +572,12 @@ k_wide_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(ab));
             // BWD: column sums over this warp's 32 rows, straight from the staged strip (lane l owns columns 4l .. 4l+3)
-            float cs[4] = {0.f, 0.f, 0.f, 0.f}, cw[4][4];
+            float cs[4] = {0.f, 0.f, 0.f, 0.f}, cw[WIDE_MAXP][4];
             const bool want_cs = MODE == GEMM_BWD && g.colsum != nullptr;
             if (want_cs) {
-                float xr[4] = {0.f, 0.f, 0.f, 0.f};
+                float xr[WIDE_MAXP] = {0.f};
 #pragma unroll
-                for (int p = 0; p < 4; p++) {
+                for (int p = 0; p < WIDE_MAXP; p++) {
                     cw[p][0] = cw[p][1] = cw[p][2] = cw[p][3] = 0.f;
                     if (p < g.P1) {
                         float x = g.xb[(size_t)row * g.R4 + p];
@@ -591,7 +592,7 @@ k_wide_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                     const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.y));
                     cs[0] += f0.x; cs[1] += f0.y; cs[2] += f1.x; cs[3] += f1.y;
 #pragma unroll
-                    for (int p = 0; p < 4; p++) {
+                    for (int p = 0; p < WIDE_MAXP; p++) {
                         if (p < g.P1) {
                             const float x = __shfl_sync(0xffffffffu, xr[p], r2);
                             cw[p][0] = fmaf(f0.x, x, cw[p][0]); cw[p][1] = fmaf(f0.y, x, cw[p][1]);
@@ -615,7 +616,7 @@ k_wide_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                 float* mine = reinterpret_cast<float*>(stg);
                 *reinterpret_cast<float4*>(mine + lane * 4) = make_float4(cs[0], cs[1], cs[2], cs[3]);
 #pragma unroll
-                for (int p = 0; p < 4; p++)
+                for (int p = 0; p < WIDE_MAXP; p++)
                     if (p < g.P1) *reinterpret_cast<float4*>(mine + (1 + p) * 128 + lane * 4) = make_float4(cw[p][0], cw[p][1], cw[p][2], cw[p][3]);
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 const int h2 = et >> 7, cl = et & 127;   // thread et owns output column et of the tile

@@ -77,11 +77,11 @@ __global__ void __launch_bounds__(256) k_wide_first(const float* xb, const float
     const int groups = 256 / per_row;                  // row groups per CTA
     const int o0 = (threadIdx.x % per_row) * 8;
     const int r0 = (blockIdx.x * groups + threadIdx.x / per_row) * FIRST_ROWS;
-    float bias[8], w[4][8], mu[4], rs[4];
+    float bias[8], w[WIDE_MAXP][8], mu[WIDE_MAXP], rs[WIDE_MAXP];
 #pragma unroll
     for (int j = 0; j < 8; j++) bias[j] = __ldg(b1img + o0 + j);
 #pragma unroll
-    for (int p = 0; p < 4; p++) {
+    for (int p = 0; p < WIDE_MAXP; p++) {
         mu[p] = (use_bn && p < d.P) ? bscal[BS_BN + 2 * p] : 0.f;
         rs[p] = (use_bn && p < d.P) ? bscal[BS_BN + 2 * p + 1] : 1.f;
 #pragma unroll
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(256) k_wide_first(const float* xb, const float
 #pragma unroll
         for (int j = 0; j < 8; j++) z[j] = bias[j];
 #pragma unroll
-        for (int p = 0; p < 4; p++) {
+        for (int p = 0; p < WIDE_MAXP; p++) {
             if (p < d.P) {
                 const float x = (xb[(size_t)b * d.R4 + p] - mu[p]) * rs[p];
 #pragma unroll

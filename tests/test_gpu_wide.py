@@ -269,3 +269,28 @@ def test_two_chain_model_embedded_block_diagonally(eh, orc):
     assert np.allclose(yhat, yo, rtol=3e-2, atol=3e-2)
     assert np.allclose(par, po, rtol=3e-2, atol=3e-2)   # both neural parameters per sample
     sess.close()
+
+
+def test_six_inputs_over_two_chains(eh, orc):
+    """more chain inputs than the four the first version of the path took (both chains see all three columns)"""
+    from conftest import make_synth
+    model = eh.constructHybridModel({"rb": ["sw_pot", "dsw_pot", "ta"], "Q10": ["ta", "sw_pot", "dsw_pot"]}, ["ta"], ["reco"], eh.RbQ10,
+                                    dict(rb=(3.0, 0.0, 13.0), Q10=(2.0, 1.0, 4.0)), [],
+                                    hidden_layers=[32, 32], activation="sigmoid", scale_nn_outputs=True, input_batchnorm=True)
+    n = 2048
+    xf, y = eh.prepare_data(model, make_synth(n))
+    rng = np.random.default_rng(13)
+    flat = model.initialparameters(rng)
+    flat += (0.05 * rng.standard_normal(flat.size)).astype(np.float32)
+    sess = eh.FusedSession(model, training_loss="mse")
+    sess.upload(0, xf, y)
+    sess.set_params(flat)
+    o = orc.Oracle(model, training_loss="mse")
+    idx = rng.permutation(n)[:1000]
+    L, g = sess.loss_grad(idx)
+    L64, g64 = o.loss_grad(flat, xf, y, idx, precision=64)
+    assert abs(L - L64) <= RTOL_LOSS * abs(L64), (L, L64)
+    cos = float(g @ g64 / (np.linalg.norm(g) * np.linalg.norm(g64)))
+    assert cos >= COS_MIN, cos
+    assert abs(np.linalg.norm(g) - np.linalg.norm(g64)) <= RTOL_NORM * np.linalg.norm(g64)
+    sess.close()

@@ -1,7 +1,7 @@
 """Small driver used under ncu: a handful of fused steps on the C3 workload (no timing claims)."""
 import sys
 import numpy as np
-sys.path.insert(0, ".")
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 import easyhybrid_b200 as eh
 from bench import synth, make_model, B
 
