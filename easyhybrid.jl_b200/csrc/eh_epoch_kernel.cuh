@@ -59,12 +59,6 @@ struct EpochArgs {
     unsigned* err;             // set to 1 when a bounded spin gives up (peer / CTA never arrived)
 };
 
-__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p)
-{
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
 // 8-byte accesses are single-copy atomic: value and tag always travel together
 __device__ __forceinline__ void st_volatile_v2(uint2* p, unsigned x, unsigned y)
 {
@@ -76,30 +70,11 @@ __device__ __forceinline__ uint2 ld_volatile_v2(const uint2* p)
     asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p)
-{
-    unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v)
-{
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 constexpr unsigned EH_SPIN_LIMIT = 1u << 26;  // ~seconds; then give up loudly instead of hanging the GPU
 
 __device__ __forceinline__ void cluster_sync_all()
 {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// read a float from the same shared-memory offset in CTA `rank` of this cluster (DSMEM)
-__device__ __forceinline__ float ld_dsmem(const float* local, unsigned rank)
-{
-    unsigned a = (unsigned)__cvta_generic_to_shared(local), ra;
-    float v;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
-    asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(ra) : "memory");
-    return v;
 }
 
 // shared-memory window address of `local` in CTA `rank` of this cluster
@@ -242,8 +217,6 @@ __global__ void __launch_bounds__(E::MAX_WARPS * 32, 1) k_epoch(const EpochArgs 
     const int G = gridDim.x;
     const int cs = a.csize;
     const int NC = G / cs;                               // clusters = published vectors per step
-    const unsigned crank = (unsigned)(blockIdx.x % cs);
-    const int cid = blockIdx.x / cs;
 
     for (int p = threadIdx.x; p < a.nflat; p += blockDim.x) {
         s_th[p] = a.pblock[p];

@@ -98,7 +98,6 @@ struct eh_ctx {
     int64_t geo_B = 0;
     int geo_cs = 0, geo_G = 0, geo_w = 0;
     size_t geo_work = 0;
-    unsigned* d_counter = nullptr;
     size_t stats_cap = 0;
     bool persist_ok = false;
     int pm_id = 0;
@@ -1493,7 +1492,6 @@ eh_status eh_create(eh_ctx** out, const eh_model_desc* desc)
         CK(cudaMemcpy(c->d_losskind, c->loss_kind, MAXT * sizeof(int), cudaMemcpyHostToDevice));
         CK(dalloc(&c->d_pbuf, (size_t)4 * (c->nsm + 8) * rup4(v->NPART)));  // [2][clusters][npartp] {value, tag}
         CK(cudaMemset(c->d_pbuf, 0, (size_t)4 * (c->nsm + 8) * rup4(v->NPART) * sizeof(float)));
-        CK(dalloc(&c->d_counter, (size_t)4));
         CK(dalloc(&c->d_dperr, (size_t)1));
         CK(cudaMemset(c->d_dperr, 0, sizeof(unsigned)));
         CK(dalloc(&c->d_m, (size_t)c->nflat));
@@ -1539,7 +1537,7 @@ void eh_destroy(eh_ctx* c)
         if (r != c->rank && c->dp_peer[r]) cudaIpcCloseMemHandle(c->dp_peer[r]);
     if (c->dp_block) cudaFree(c->dp_block);
     void* ptrs[] = {c->d_wsrc, c->d_pmap, c->d_pspan, c->d_theta, c->d_m, c->d_v, c->d_grad, c->d_ost, c->d_partial,
-                    c->d_gvec, c->d_dperr, c->d_cells, c->d_slot_of_flat, c->d_losskind, c->d_pbuf, c->d_stats, c->d_counter, c->d_bscal, c->d_bn_batch, c->d_idx, c->d_idx64, c->d_err, c->d_loss, c->d_evalpart,
+                    c->d_gvec, c->d_dperr, c->d_cells, c->d_slot_of_flat, c->d_losskind, c->d_pbuf, c->d_stats, c->d_bscal, c->d_bn_batch, c->d_idx, c->d_idx64, c->d_err, c->d_loss, c->d_evalpart,
                     c->d_bn_test, c->split[0].rec, c->split[1].rec};
     for (void* p : ptrs)
         if (p) cudaFree(p);

@@ -7,7 +7,7 @@
 //   gemm_fwd  x(NH-1)  tcgen05                                          A_l = act(A_{l-1} W_l^T + b_l)  bf16
 //   k_wide_head      output layer (fan-out NOUT is tiny), parameter squashing, process model, masked loss
 //                    seeds, analytic backward into D_NH, gradient of the output layer and of phi
-//   per hidden layer l = NH .. 2:   gemm_wgrad (dW_l partials), gemm_bwd (D_{l-1}), k_wide_colsum (db)
+//   per hidden layer l = NH .. 2:   gemm_wgrad (dW_l partials), gemm_bwd (D_{l-1}; its epilogue also emits the column sums = db)
 //   k_wide_wreduce   split-K partials -> flat gradient (fixed order)
 //   k_wide_gradfin   remaining gradient entries (W_1, biases, output layer, phi) and the loss value
 //   k_wide_update    optimiser over the flat vector, bf16 weight images for the next step
@@ -362,45 +362,6 @@ __global__ void __launch_bounds__(256) k_wide_head(const HeadArgs a)
         const int q = threadIdx.x;
         if (q < 4) out[head_off_dbo(H, NOUT) + q] = q < NOUT ? s : 0.f;
         else out[head_off_loss(H, NOUT) + (q - 4)] = s;   // loss sums then phi sums are contiguous
-    }
-}
-
-// ---- column sums of a delta matrix over a slab of rows: db partials (and dW_1 for the first layer) ----
-// grid = number of slabs; block = H / 2 threads (two adjacent columns each); out [slab][(1 + P1) * H]
-__global__ void __launch_bounds__(512) k_wide_colsum(const __nv_bfloat16* D, const float* xb, const float* bscal, int use_bn,
-                                                     int B, int H, int R4, int P1, int rows_per_slab, float* out)
-{
-    const int c2 = threadIdx.x;   // column pair
-    const int r0 = blockIdx.x * rows_per_slab;
-    const int r1 = min(B, r0 + rows_per_slab);
-    float s0 = 0.f, s1 = 0.f;
-    float w0[4] = {0.f, 0.f, 0.f, 0.f}, w1[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int rb = r0; rb < r1; rb += 8) {
-        __nv_bfloat162 raw[8];
-#pragma unroll
-        for (int u = 0; u < 8; u++)   // independent loads first: the slab is streamed, not chased
-            raw[u] = rb + u < r1 ? *reinterpret_cast<const __nv_bfloat162*>(D + (size_t)(rb + u) * H + 2 * c2) : __floats2bfloat162_rn(0.f, 0.f);
-#pragma unroll
-        for (int u = 0; u < 8; u++) {
-            const float2 dv = __bfloat1622float2(raw[u]);
-            s0 += dv.x;
-            s1 += dv.y;
-            if (P1 > 0 && rb + u < r1) {
-                for (int p = 0; p < P1; p++) {
-                    float x = xb[(size_t)(rb + u) * R4 + p];
-                    if (use_bn) x = (x - bscal[BS_BN + 2 * p]) * bscal[BS_BN + 2 * p + 1];
-                    w0[p] = fmaf(dv.x, x, w0[p]);
-                    w1[p] = fmaf(dv.y, x, w1[p]);
-                }
-            }
-        }
-    }
-    float* o = out + (size_t)blockIdx.x * (1 + P1) * H;
-    o[2 * c2] = s0;
-    o[2 * c2 + 1] = s1;
-    for (int p = 0; p < P1; p++) {
-        o[(1 + p) * H + 2 * c2] = w0[p];
-        o[(1 + p) * H + 2 * c2 + 1] = w1[p];
     }
 }
 

@@ -294,3 +294,14 @@ def test_six_inputs_over_two_chains(eh, orc):
     assert cos >= COS_MIN, cos
     assert abs(np.linalg.norm(g) - np.linalg.norm(g64)) <= RTOL_NORM * np.linalg.norm(g64)
     sess.close()
+
+
+def test_train_api_with_a_chain_outside_the_register_tile_variants(eh):
+    """train(model, data; ...) (src/training/train.jl) end to end on the tensor-core path: hidden [64, 64], ragged
+    batches (batchsize 300), evaluation metrics per epoch, Q10 recovered from the synthetic table (true value 2)"""
+    from conftest import make_synth, rbq10_model
+    model = rbq10_model(eh, hidden=(64, 64), activation="tanh", bn=True)
+    out = eh.train(model, make_synth(6000), nepochs=12, batchsize=300, opt=eh.Adam(0.01), loss_types=["mse", "r2"])
+    assert out is not None and len(out.train_history) == 13
+    assert out.val_history[-1]["mse"]["sum"] < out.val_history[0]["mse"]["sum"] * 0.1
+    assert abs(out.train_diffs["Q10"] - 2.0) < 0.25
