@@ -265,9 +265,9 @@ def main():
     per_gpu_sps = K * B / (dev_ms * 1e-3)
     achieved = per_gpu_sps * BYTES_PER_SAMPLE / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                # dram__bytes_read+write of k_epoch from ncu --set full (profiles/r1_k_epoch_v3_cs4_ncu_details.txt):
-                # 58.5 MB for a 12-step launch = 4.88 MB per step, scaled to this launch's K steps
-                "traffic": 4.88e6 * K, "traffic_algorithmic": float(K) * B * BYTES_PER_SAMPLE,
+                # dram__bytes_read+write of k_epoch from ncu --set full (profiles/r1_k_epoch_v5_ncu_details.txt):
+                # 57.8 + 0.85 MB for a 12-step launch = 4.89 MB per step, scaled to this launch's K steps
+                "traffic": 4.89e6 * K, "traffic_algorithmic": float(K) * B * BYTES_PER_SAMPLE,
                 "peak_source": peak_src,
                 "kernel": "k_epoch (persistent: fused fwd+process+loss+bwd, grid exchange, Adam; one launch = K steps)",
                 "kernel_us_per_step": 1e3 * dev_ms / K,
