@@ -602,6 +602,77 @@ __device__ __forceinline__ void chunk_dw_phase(const float* stage, int lane, con
     }
 }
 
+// ---- weight-gradient phase on the tensor pipe (3xTF32, fp32-level accuracy) ----
+// dW_l[j][k] += sum over the chunk's samples of delta_l[j][s] * a_{l-1}[k][s] is an (H x samples) x (samples x ka)
+// product: mma.m16n8k8 with the delta rows as A (row-major M x K, K = samples) and the activation rows as B (K x N),
+// both read straight from the feature-major staging tiles (rows of 32 samples, conflict-free in the k = sample
+// direction).  Compared with the 4x4 register tiles this trades 64 LDS.128 + 256 FFMA2 per chunk for 64 LDS.32 +
+// 48 HMMA, and halves the accumulator registers.  Columns past ka(l) of the last n-tile read whatever rows follow in
+// the staging tile (finite values) and are never stored.  Same wacc layout as chunk_dw_phase.
+template <class C>
+__device__ __forceinline__ void chunk_dw_phase_mma(const float* stage, int lane, float* wacc, bool first)
+{
+    constexpr ShapeDims D = C::D;
+    constexpr int RS = C::RS;
+    static_assert(C::H % 16 == 0 && C::LR == 1 && C::SPL == 1, "tensor-pipe dW: hidden width multiple of 16, output layer in registers");
+    constexpr int MT = C::H / 16;
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int l = 1; l <= D.nlt(); l++) {
+        const int ka = D.ka(l), nk = D.nk(l), b0 = D.blk0(l);
+        const int NT = (ka + 7) / 8;
+        float acc[MT][6][4];   // NT <= 6 for the shapes compiled (ka <= 48)
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+            for (int nt = 0; nt < 6; nt++)
+#pragma unroll
+                for (int q = 0; q < 4; q++) acc[mt][nt][q] = 0.f;
+#pragma unroll
+        for (int ks = 0; ks < C::CHUNKS / 8; ks++) {
+            const int k0 = 8 * ks + t;
+            unsigned bh[6][2], bl[6][2];
+#pragma unroll
+            for (int nt = 0; nt < 6; nt++) {
+                if (nt < NT) {
+                    const float* pb = stage + goff<RS>(D.gA(l), 8 * nt + g) + k0;
+                    split_tf32(pb[0], bh[nt][0], bl[nt][0]);
+                    split_tf32(pb[4], bh[nt][1], bl[nt][1]);
+                }
+            }
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++) {
+                const float* pa0 = stage + goff<RS>(D.gD(l), 16 * mt + g) + k0;
+                const float* pa1 = stage + goff<RS>(D.gD(l), 16 * mt + g + 8) + k0;
+                unsigned ah[4], al[4];
+                split_tf32(pa0[0], ah[0], al[0]);
+                split_tf32(pa1[0], ah[1], al[1]);
+                split_tf32(pa0[4], ah[2], al[2]);
+                split_tf32(pa1[4], ah[3], al[3]);
+#pragma unroll
+                for (int nt = 0; nt < 6; nt++)
+                    if (nt < NT) mma_3xtf32(acc[mt][nt], ah, al, bh[nt], bl[nt]);
+            }
+        }
+        // C fragment: rows g / g + 8 of the m-tile, columns 2t / 2t + 1 of the n-tile -> 4x4 tile cells of the partial vector
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+            for (int nt = 0; nt < 6; nt++) {
+                if (nt < NT) {
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const int j = 16 * mt + g + ((q >> 1) ? 8 : 0), k = 8 * nt + 2 * t + (q & 1);
+                        if (k < ka) {
+                            const int cell = ((j & 3) * 4 + (k & 3)) * C::NB + b0 + (j >> 2) * nk + (k >> 2);
+                            wacc[cell] = first ? acc[mt][nt][q] : wacc[cell] + acc[mt][nt][q];
+                        }
+                    }
+                }
+            }
+    }
+}
+
 // Sum NV per-lane values over the 32 lanes of a warp with a recursive-halving exchange: at each of
 // the 5 levels a lane keeps half of its values and ships the other half to its partner, so the whole
 // reduction costs NV-ish shuffles instead of 5*NV (SHFL shares the 128 B/clk LSU writeback path, which

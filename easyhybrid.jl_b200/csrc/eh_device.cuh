@@ -108,6 +108,27 @@ __device__ __forceinline__ double warp_sum_d(double v)
     return v;
 }
 
+// ---- tensor pipe, TF32 inputs with fp32-level accuracy (3xTF32) ------------------------------
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const unsigned (&a)[4], const unsigned (&b)[2])
+{
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void split_tf32(float x, unsigned& hi, unsigned& lo)
+{
+    hi = __float_as_uint(x) & 0xffffe000u;         // the tensor pipe reads exactly these bits
+    lo = __float_as_uint(x - __uint_as_float(hi));  // exact remainder (truncated to tf32 by the hardware)
+}
+// D += A B with fp32-level accuracy: small cross terms first
+__device__ __forceinline__ void mma_3xtf32(float (&d)[4], const unsigned (&ah)[4], const unsigned (&al)[4],
+                                           const unsigned (&bh)[2], const unsigned (&bl)[2])
+{
+    mma_tf32(d, al, bh);
+    mma_tf32(d, ah, bl);
+    mma_tf32(d, ah, bh);
+}
+
 // Programmatic dependent launch: wait for the producer grid / let the consumer start.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

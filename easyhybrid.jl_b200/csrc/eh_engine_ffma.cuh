@@ -16,6 +16,12 @@ struct EngFfma {
     static constexpr int OFF_STATS = C::D.npart_dw();
     static constexpr int CHUNK = C::CHUNKS;           // samples per warp pass
     static constexpr int MAX_WARPS = C::SPL == 2 ? 10 : 16;
+    // weight-gradient outer products on the tensor pipe (3xTF32) where the shape allows; the FFMA2 register tiles otherwise
+#ifdef EH_DW_FFMA
+    static constexpr bool DW_MMA = false;
+#else
+    static constexpr bool DW_MMA = C::LR == 1 && C::H % 16 == 0 && C::SPL == 1 && C::D.ka(C::D.nlt()) <= 48;
+#endif
 
     struct State {
         int nacc;  // chunks accumulated into this warp's reduction row this step
@@ -77,7 +83,8 @@ struct EngFfma {
         fetch(s, fa.rec, fa.idx, fa.rec_base, fa.B, next, fa.nchunks, lane);
         chunk_sample_phase<C>(rec, valid, sW, sS, stage, lane, slot, loss_kind, cx, s.st, s.la);
         __syncwarp();
-        chunk_dw_phase<C>(stage, lane, s.rowD, s.rowA, stage + C::STAGE_FLOATS, s.nacc == 0);
+        if constexpr (DW_MMA) chunk_dw_phase_mma<C>(stage, lane, stage + C::STAGE_FLOATS, s.nacc == 0);
+        else chunk_dw_phase<C>(stage, lane, s.rowD, s.rowA, stage + C::STAGE_FLOATS, s.nacc == 0);
         s.nacc++;
         __syncwarp();
     }
