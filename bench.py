@@ -121,27 +121,32 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), line.strip()))
 
-    def stop(self, t0, t1):
+    def stop(self, windows):
+        """windows: [(t0, t1), ...] -- the timed regions (device-resident leg and the end-to-end legs)"""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.05)
         self.proc.terminate()
         sm, smax, reasons = [], None, set()
+
+        def inside(t):
+            return any(t0 - 0.02 <= t <= t1 + 0.02 for (t0, t1) in windows)
+
         for (t, line) in self.rows:
             p = [x.strip() for x in line.split(",")]
             if len(p) < 7:
                 continue
             try:
-                if t0 - 0.02 <= t <= t1 + 0.02:
+                if inside(t):
                     sm.append(float(p[0]))
                 smax = float(p[1])
             except ValueError:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[3:7]):
-                if v.lower().startswith("active") and t0 - 0.02 <= t <= t1 + 0.02:
+                if v.lower().startswith("active") and inside(t):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "sampled_over": "the timed regions of the device-resident and end-to-end legs"}
 
 
 def measured_peaks():
@@ -249,7 +254,7 @@ def main():
     losses = sess.run_steps(B, W, K)
     t1 = time.perf_counter()
     barrier()
-    clocks = sampler.stop(t0, t1)
+    windows = [(t0, t1)]
     dev_ms, launches, _ = sess.last_timing()
     if dist is not None:
         import torch
@@ -305,6 +310,7 @@ def main():
         sess.sync()
         te1 = time.perf_counter()
         barrier()
+        windows.append((te0, te1))
         dt = te1 - te0
         if dist is not None:
             import torch
@@ -326,6 +332,7 @@ def main():
             sess.epoch(perm_pinned, B, one_based=True)
         tr1 = time.perf_counter()
         barrier()
+        windows.append((tr0, tr1))
         dtr = tr1 - tr0
         if dist is not None:
             import torch
@@ -336,6 +343,7 @@ def main():
                                    "h2d_bytes_per_step": 8 * B, "d2h_bytes_per_step": 4, "steps": reps * kr,
                                    "api": "eh_epoch(page-locked host permutation, streamed in segments behind the training) on the dataset staged once by eh_upload"}
 
+    clocks = sampler.stop(windows)
     wide = None
     if rank == 0 and world == 1 and not args.no_wide:
         try:

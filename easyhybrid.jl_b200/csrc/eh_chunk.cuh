@@ -187,8 +187,10 @@ __device__ __forceinline__ void chain_forward(const float* sW, float* stage, int
 // row (sigmoid-squashed into [lo, hi] iff scale_nn_outputs), GLOBAL / FIXED = per-step uniform
 // value from shared memory.  sg keeps sigma(z) for the backward.
 template <class C>
-__device__ __forceinline__ void resolve_params(const PSlot* slot, const float* sS, const float* zo, float* pv, float* sg)
+__device__ __forceinline__ void resolve_params(const PSlot* slot, const float* sS, const float* zo, float* pv, float* sg,
+                                               const PmCtx& cx)
 {
+    const bool scale = C::PM::DYNAMIC ? (cx.scale_rt != 0) : C::SCALE;
 #pragma unroll
     for (int s = 0; s < C::NPS; s++) {
         const PSlot sl = slot[s];
@@ -198,7 +200,7 @@ __device__ __forceinline__ void resolve_params(const PSlot* slot, const float* s
 #pragma unroll
             for (int o = 1; o < C::NOUT; o++)
                 if (sl.idx == o) z = zo[o];
-            if (C::SCALE) {
+            if (scale) {
                 sg[s] = sigmoid1(z);
                 pv[s] = fmaf(sg[s], sl.span, sl.lo);
             } else {
@@ -435,7 +437,7 @@ __device__ __forceinline__ void chunk_sample_phase(const float (*rec)[C::R4], co
         for (int k = 0; k < F; k++) f[k] = rec[s][P + k];
 #pragma unroll
         for (int k = 0; k < T; k++) y[k] = rec[s][P + F + k];
-        resolve_params<C>(slot, sS, zo[s], pv, sg);
+        resolve_params<C>(slot, sS, zo[s], pv, sg, cx);
         PM::fwd(pv, f, cx, yh, sv);
         // valid_mask = !isnan(y) (train.jl:221-232); seeds dL/dyhat
 #pragma unroll
@@ -459,7 +461,7 @@ __device__ __forceinline__ void chunk_sample_phase(const float (*rec)[C::R4], co
             const PSlot sl = slot[q];
             if (sl.role == ROLE_NEURAL) {
                 float g = gp[q];
-                if (C::SCALE) g *= sl.span * sg[q] * (1.f - sg[q]);
+                if (C::PM::DYNAMIC ? (cx.scale_rt != 0) : C::SCALE) g *= sl.span * sg[q] * (1.f - sg[q]);
 #pragma unroll
                 for (int o = 0; o < NOUT; o++)
                     if (sl.idx == o) dz[s][o] += g;

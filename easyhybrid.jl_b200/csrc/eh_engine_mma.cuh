@@ -217,7 +217,7 @@ struct EngMma {
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 float pv[NPS], sg[NPS], yh[T], sv[4], gy[T], gp[NPS];
-                resolve_params<C>(slot, sS, zo[h], pv, sg);
+                resolve_params<C>(slot, sS, zo[h], pv, sg, cx);
                 PM::fwd(pv, f[h], cx, yh, sv);
 #pragma unroll
                 for (int i = 0; i < T; i++) {

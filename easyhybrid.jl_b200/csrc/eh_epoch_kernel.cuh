@@ -48,6 +48,8 @@ struct EpochArgs {
     PSlot slot[MAXPS];
     float pmc[4];
     int use_bn;
+    const PmProgData* prog;    // traced process model (PmProgram variants), device memory
+    int scale_rt;              // PmProgram variants: scale_nn_outputs
     int pm_id;
     int opt_kind, adamw_coupled;
     float eta, beta1, beta2, eps, lambda;
@@ -242,6 +244,8 @@ __global__ void __launch_bounds__(E::MAX_WARPS * 32, 1) k_epoch(const EpochArgs 
     PmCtx cx;
     cx.pms = sS + SS_PMS;
     cx.c = a.pmc;
+    cx.prog = a.prog;
+    cx.scale_rt = a.scale_rt;
     cx.uniform_mask = 0;
 #pragma unroll
     for (int s = 0; s < MAXPS; s++)

@@ -26,6 +26,8 @@ struct EvalArgs {
     float* yhat;           // nullable [T][N]
     float* parout;         // nullable [NPS][N] (NEURAL slots only)
     double* partial;       // [gridDim.x][T * EVAL_NSTAT]
+    const PmProgData* prog;   // traced process model (PmProgram variants), device memory
+    int scale_rt;             // PmProgram variants: scale_nn_outputs
 };
 
 template <class C>
@@ -44,6 +46,8 @@ __global__ void __launch_bounds__(256) k_eval(const EvalArgs a)
     PmCtx cx;
     cx.pms = sS + SS_PMS;
     cx.c = a.pmc;
+    cx.prog = a.prog;
+    cx.scale_rt = a.scale_rt;
     cx.uniform_mask = 0;
 #pragma unroll
     for (int s = 0; s < MAXPS; s++)
@@ -75,7 +79,7 @@ __global__ void __launch_bounds__(256) k_eval(const EvalArgs a)
         float2 hp[HP];
         float zo[NOUT], pv[NPS], sg[NPS], yh[T], sv[4];
         chain_forward<C, false>(sW, nullptr, lane, x, hp, zo);
-        resolve_params<C>(a.slot, sS, zo, pv, sg);
+        resolve_params<C>(a.slot, sS, zo, pv, sg, cx);
         PM::fwd(pv, f, cx, yh, sv);
 
 #pragma unroll

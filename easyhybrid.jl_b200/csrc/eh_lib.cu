@@ -122,6 +122,11 @@ struct eh_ctx {
     // host-step pipeline
     HostStage hs[EH_HOST_SLOTS];
     int hs_next = 0;
+    bool small_prog = false;     // register-tile path with an interpreted process model (PmProgram variants)
+    int scale_rt = 0;            // scale_nn_outputs as the generic variants take it
+    PmProgData h_prog;           // the program, host copy
+    PmProgData* d_prog = nullptr;
+    bool host_zero_copy = true;  // EH_HOST_NO_ZEROCOPY=1: always stage host batches through the copy engine
     std::vector<std::pair<float*, float*>> pending_loss;  // (pinned src, user dst)
     float* h_async_loss = nullptr;                          // pinned ring
     size_t async_cap = 0, async_used = 0;
@@ -220,8 +225,7 @@ __global__ void __launch_bounds__(256) k_pack_count(const PackArgs a, int T, int
         float* r = a.rec + (a.rec_base + i) * a.R4;
         for (int c = 0; c < a.R4; c++) {
             float v = 0.f;
-            if (c < a.ncols)
-                v = a.src_kind[c] == 0 ? a.X[i * a.P_raw + a.src_idx[c]] : a.planes[(long long)a.src_idx[c] * a.N + i];
+            if (c < a.ncols) v = pack_load(a, c, i);
             r[c] = v;
             int t = c - ycol0;
             if (t >= 0 && t < T && v == v) valid[t] = 1;
@@ -231,6 +235,121 @@ __global__ void __launch_bounds__(256) k_pack_count(const PackArgs a, int T, int
         unsigned m = __ballot_sync(0xffffffffu, valid[t]);
         if ((threadIdx.x & 31) == 0 && m) atomicAdd(&cnt[t], __popc(m));
     }
+}
+
+// Zero-copy packer of the host-batch path: the caller's page-locked arrays are read straight over PCIe
+// (UVA device pointers of pinned host memory) and leave as packed records in HBM -- one launch on the copy
+// stream replaces the three cudaMemcpyAsync + the packer + the per-batch-scalar kernel.  The grid is kept
+// to EH_PACK_HOST_CTAS big CTAs so that the packer only ever occupies that many SMs next to a running step
+// kernel (step_geometry leaves them free); 16 x 1024 threads x >= 16 B keep > 256 KB in flight, enough to
+// cover the PCIe round trip at full rate.  The last CTA to finish (ticket) turns the valid-target counts
+// into the batch's scalar row, like k_bscal_from_counts.
+constexpr int EH_PACK_HOST_CTAS = 16;
+constexpr int EH_PACK_MAXPLANES = 24;
+struct PackHostArgs {
+    const float* X;                         // [N][P_raw], host memory mapped into the device address space
+    const float* plane[EH_PACK_MAXPLANES];  // forcings then targets, each [N], mapped host memory
+    long long N;
+    int P_raw, ncols, R4;
+    int x_pair;                             // columns 0,1 of a record are X[2i], X[2i+1] (one 8-byte load)
+    int src_kind[24], src_idx[24];
+    float* rec;                             // [N][R4] device
+    int T, ycol0, agg_mean;
+    int* cnt;                               // [MAXT + 1] valid-target counters + ticket (all zero between launches)
+    float* bscal;                           // per-batch scalar row to fill (NULL: K0 computes it from the records)
+};
+
+__device__ __forceinline__ float pack_host_load(const PackHostArgs& a, int c, long long i)
+{
+    if (c >= a.ncols) return 0.f;
+    const int k = a.src_kind[c];
+    if (k >= 2) return k == 2 ? 0.f : __int_as_float(0x7fc00000);   // padding columns of the generic variants: zero / NaN
+    return k == 0 ? __ldg(a.X + i * a.P_raw + a.src_idx[c]) : __ldg(a.plane[a.src_idx[c]] + i);
+}
+
+__global__ void __launch_bounds__(1024) k_pack_host(const PackHostArgs a)
+{
+    int valid[MAXT] = {0, 0, 0, 0};
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long first = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a.R4 == 4) {
+        // two samples per thread and trip: eight independent loads in flight before the first store
+        for (long long i = first; i < a.N; i += 2 * stride) {
+            const long long j = i + stride;
+            const bool two = j < a.N;
+            float r0[4], r1[4] = {0.f, 0.f, 0.f, 0.f};
+            int c0 = 0;
+            if (a.x_pair) {
+                const float2 x0 = __ldg(reinterpret_cast<const float2*>(a.X) + i);
+                r0[0] = x0.x; r0[1] = x0.y;
+                if (two) { const float2 x1 = __ldg(reinterpret_cast<const float2*>(a.X) + j); r1[0] = x1.x; r1[1] = x1.y; }
+                c0 = 2;
+            }
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+                if (c >= c0) {
+                    r0[c] = pack_host_load(a, c, i);
+                    if (two) r1[c] = pack_host_load(a, c, j);
+                }
+            reinterpret_cast<float4*>(a.rec)[i] = make_float4(r0[0], r0[1], r0[2], r0[3]);
+            if (two) reinterpret_cast<float4*>(a.rec)[j] = make_float4(r1[0], r1[1], r1[2], r1[3]);
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const int t = c - a.ycol0;
+                if (t >= 0 && t < a.T) {
+                    if (r0[c] == r0[c]) valid[t]++;
+                    if (two && r1[c] == r1[c]) valid[t]++;
+                }
+            }
+        }
+    } else {
+        for (long long i = first; i < a.N; i += stride) {
+            float* r = a.rec + i * a.R4;
+            for (int c = 0; c < a.R4; c++) {
+                const float v = pack_host_load(a, c, i);
+                r[c] = v;
+                const int t = c - a.ycol0;
+                if (t >= 0 && t < a.T && v == v) valid[t]++;
+            }
+        }
+    }
+    if (!a.bscal) return;
+    for (int t = 0; t < a.T; t++) {
+        const int s = __reduce_add_sync(0xffffffffu, valid[t]);
+        if ((threadIdx.x & 31) == 0 && s) atomicAdd(&a.cnt[t], s);   // integer atomics: deterministic
+    }
+    __shared__ int s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(&a.cnt[MAXT], 1) == (int)gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x < MAXT) {
+        const int t = threadIdx.x;
+        const float aggw = a.agg_mean ? 1.f / (float)a.T : 1.f;
+        const float n = t < a.T ? (float)atomicExch(&a.cnt[t], 0) : 0.f;   // read and re-arm for the next launch
+        a.bscal[BS_C + t] = t < a.T ? aggw / n : 0.f;
+        a.bscal[BS_N + t] = n;
+        a.bscal[BS_SS + t] = 0.f;
+    }
+    if (threadIdx.x == MAXT) atomicExch(&a.cnt[MAXT], 0);
+    if (threadIdx.x >= 32 && threadIdx.x < 32 + MAXP) {
+        const int k = threadIdx.x - 32;
+        a.bscal[BS_BN + 2 * k] = 0.f;
+        a.bscal[BS_BN + 2 * k + 1] = 1.f;
+    }
+}
+
+// device-visible address of a page-locked host array (cudaHostAlloc / cudaHostRegister), NULL for anything else
+const float* mapped_host_ptr(const float* p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+    return static_cast<const float*>(at.devicePointer);
 }
 
 struct Geom {
@@ -248,23 +367,24 @@ const Variant* pick_variant(const eh_ctx* c, int64_t B)
     return c->var;
 }
 
-Geom step_geometry(const eh_ctx* c, int64_t B)
+Geom step_geometry(const eh_ctx* c, int64_t B, int reserve_sms = 0)
 {
     const Variant* v = pick_variant(c, B);
+    const int nsm = std::max(1, c->nsm - reserve_sms);  // SMs left to a concurrently running zero-copy packer
     size_t fixed = (size_t)(rup4(v->NW) + SS_FLOATS) * 4;
     size_t stage = (size_t)std::max(v->stage_floats, v->NPART) * 4;  // staging tile, later one row of the reduction scratch
     int wmax = (int)std::min<size_t>((size_t)v->max_warps, (c->smem_optin - fixed - 8192) / stage);
     if (wmax < 1) wmax = 1;
     int64_t nchunks = (B + v->chunk - 1) / v->chunk;
     Geom g;
-    if (nchunks <= (int64_t)c->nsm * wmax) {
-        int w = (int)((nchunks + c->nsm - 1) / c->nsm);
+    if (nchunks <= (int64_t)nsm * wmax) {
+        int w = (int)((nchunks + nsm - 1) / nsm);
         w = std::max(1, std::min(w, wmax));
         g.nwarps = w;
         g.grid = (int)((nchunks + w - 1) / w);
     } else {
         g.nwarps = wmax;
-        g.grid = c->nsm;
+        g.grid = nsm;
     }
     if (g.grid < 1) g.grid = 1;
     g.smem = fixed + (size_t)g.nwarps * stage;
@@ -283,6 +403,8 @@ void fill_step_args(const eh_ctx* c, StepArgs& a)
     for (int s = 0; s < MAXPS; s++) a.slot[s] = c->slots[s];
     for (int i = 0; i < 4; i++) a.pmc[i] = c->pmc[i];
     a.use_bn = c->use_bn;
+    a.prog = c->d_prog;
+    a.scale_rt = c->scale_rt;
 }
 
 void fill_update_args(const eh_ctx* c, UpdateArgs& u)
@@ -426,7 +548,7 @@ eh_status prepare_batch_rows_range(eh_ctx* c, int64_t n, int64_t B, int64_t b0, 
         a.idx = c->d_idx + off;
         a.n = std::min<int64_t>(n, b1 * B) - off;
         a.Bfull = (int)B;
-        a.P = c->var->P; a.F = c->var->F; a.T = c->var->T;
+        a.P = c->var->P; a.F = c->var->F; a.T = c->n_targ;
         for (int t = 0; t < MAXT; t++) { a.shift_y[t] = sp.shift_y[t]; a.loss_kind[t] = c->loss_kind[t]; }
         for (int k = 0; k < MAXP; k++) a.shift_x[k] = sp.shift_x[k];
         a.agg_mean = c->agg_mean;
@@ -588,7 +710,7 @@ eh_status enqueue_persistent(eh_ctx* c, const float* rec, const int* idx, const 
     for (int t = 0; t < MAXT; t++) a.loss_kind[t] = c->loss_kind[t];
     for (int s = 0; s < MAXPS; s++) a.slot[s] = c->slots[s];
     for (int i = 0; i < 4; i++) a.pmc[i] = c->pmc[i];
-    a.use_bn = c->use_bn; a.pm_id = c->pm_id;
+    a.use_bn = c->use_bn; a.pm_id = c->pm_id; a.prog = c->d_prog; a.scale_rt = c->scale_rt;
     a.opt_kind = c->opt_kind; a.adamw_coupled = c->adamw_coupled;
     a.eta = c->eta; a.beta1 = c->beta1; a.beta2 = c->beta2; a.eps = c->eps; a.lambda = c->lambda;
     a.world = c->world; a.rank = c->rank; a.step_base = c->dp_steps; a.err = c->d_dperr;
@@ -1090,6 +1212,72 @@ eh_status build_plan_wide(eh_ctx* c, const eh_model_desc* d, bool is_prog)
     return EH_OK;
 }
 
+// The process model as a straight-line program for the generic variants: a traced one is taken as it is (already
+// validated), a built-in form is written out from its (param, param, forcing) binding -- PARAM operands address the
+// descriptor's parameter table, FORCING operands its forcing columns, like traced programs do.
+bool builtin_as_program(const eh_model_desc* d, bool is_prog, std::vector<eh_pm_instr>& prog, std::vector<int>& out)
+{
+    prog.clear();
+    out.clear();
+    if (is_prog) {
+        prog.assign(d->pm_prog, d->pm_prog + d->pm_len);
+        out.assign(d->pm_outputs, d->pm_outputs + d->n_targ);
+        return true;
+    }
+    auto emit = [&](int op, int a, int b, float imm) {
+        eh_pm_instr in;
+        memset(&in, 0, sizeof in);
+        in.op = op; in.a = a; in.b = b; in.imm = imm;
+        prog.push_back(in);
+        return (int)prog.size() - 1;
+    };
+    const int pa = emit(EH_OP_PARAM, d->pm_args[0].index, 0, 0.f);
+    const int pb = emit(EH_OP_PARAM, d->pm_args[1].index, 0, 0.f);
+    const int f = emit(EH_OP_FORCING, d->pm_args[2].index, 0, 0.f);
+    switch (d->process_model) {
+    case EH_PM_RBQ10: {   // rb * Q10^(0.1 (ta - tref))
+        const int tref = emit(EH_OP_CONST, 0, 0, d->pm_consts[0]);
+        const int dt = emit(EH_OP_SUB, f, tref, 0.f);
+        const int tenth = emit(EH_OP_CONST, 0, 0, 0.1f);
+        const int e = emit(EH_OP_MUL, tenth, dt, 0.f);
+        const int pw = emit(EH_OP_POW, pb, e, 0.f);
+        out.push_back(emit(EH_OP_MUL, pa, pw, 0.f));
+        break;
+    }
+    case EH_PM_EXPO:
+    case EH_PM_EXPO2: {   // Resp0 * exp(k T) (; twice that)
+        const int kt = emit(EH_OP_MUL, pb, f, 0.f);
+        const int ex = emit(EH_OP_EXP, kt, 0, 0.f);
+        const int y0 = emit(EH_OP_MUL, pa, ex, 0.f);
+        out.push_back(y0);
+        if (d->process_model == EH_PM_EXPO2) {
+            const int two = emit(EH_OP_CONST, 0, 0, 2.f);
+            out.push_back(emit(EH_OP_MUL, two, y0, 0.f));
+        }
+        break;
+    }
+    case EH_PM_LINEAR:
+    case EH_PM_LINEAR2: {   // a x + b (; 2 a x + b)
+        const int ax = emit(EH_OP_MUL, pa, f, 0.f);
+        out.push_back(emit(EH_OP_ADD, ax, pb, 0.f));
+        if (d->process_model == EH_PM_LINEAR2) {
+            const int two = emit(EH_OP_CONST, 0, 0, 2.f);
+            const int ax2 = emit(EH_OP_MUL, two, ax, 0.f);
+            out.push_back(emit(EH_OP_ADD, ax2, pb, 0.f));
+        }
+        break;
+    }
+    default:
+        return false;
+    }
+    if ((int)out.size() != d->n_targ) return false;
+    for (int k = 0; k < 3; k++) {
+        const int lim = k < 2 ? d->n_params : d->n_forc;
+        if (d->pm_args[k].index < 0 || d->pm_args[k].index >= lim) return false;
+    }
+    return true;
+}
+
 eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
 {
     if (d->abi_version != EH_ABI_VERSION) return fail(c, EH_EINVAL, "abi_version %d != %d", d->abi_version, EH_ABI_VERSION);
@@ -1126,24 +1314,43 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
     // (wider or deeper, up to 6 hidden layers of up to 512 units, padded to 256 / 512 internally) runs on the bf16
     // tcgen05 GEMM path.
     const bool wide = false;   // (this function continues with the register-tile plan only)
-    const bool have_small = d->n_chains == 1 && !is_prog && hmax <= 32 &&
-                            find_variant(d->process_model, ch.n_in, ch.n_hidden, rup4(hmax), ch.n_out, ch.activation,
-                                         d->scale_nn_outputs ? 1 : 0, 0) != nullptr;
-    if (!have_small) return build_plan_wide(c, d, is_prog);
-    // engine 0 (exact-fp32 FFMA2) by default; engine 1 (tensor pipe, 3xTF32) on request where a variant exists
-    const Variant* v = wide ? &c->wide_var : nullptr;
-    if (!v && (d->flags & EH_FLAG_TENSOR_PIPE))
-        v = find_variant(d->process_model, ch.n_in, ch.n_hidden, rup4(hmax), ch.n_out, ch.activation,
-                         d->scale_nn_outputs ? 1 : 0, 1);
-    if (!v)
-        v = find_variant(d->process_model, ch.n_in, ch.n_hidden, rup4(hmax), ch.n_out, ch.activation,
-                         d->scale_nn_outputs ? 1 : 0, 0);
-    if (!v)
-        return fail(c, EH_EUNSUPPORTED,
-                    "no fused kernel variant for process_model=%d n_in=%d hidden=%dx(<=%d) n_out=%d activation=%d scale_nn_outputs=%d",
-                    d->process_model, ch.n_in, ch.n_hidden, hmax, ch.n_out, ch.activation, d->scale_nn_outputs);
-    if (v->T != d->n_targ) return fail(c, EH_EINVAL, "process model yields %d targets, descriptor has %d", v->T, d->n_targ);
+    const int scale_flag = d->scale_nn_outputs ? 1 : 0;
+    const bool small_shape = d->n_chains == 1 && hmax <= 32;
+    const Variant* v = nullptr;
+    // 1. a specialised variant of a built-in form (the BASELINE configurations); engine 1 (tensor pipe, 3xTF32) on
+    //    request where one exists, engine 0 (exact-fp32 FFMA2) otherwise
+    if (small_shape && !is_prog) {
+        if (d->flags & EH_FLAG_TENSOR_PIPE)
+            v = find_variant(d->process_model, ch.n_in, ch.n_hidden, rup4(hmax), ch.n_out, ch.activation, scale_flag, 1);
+        if (!v) v = find_variant(d->process_model, ch.n_in, ch.n_hidden, rup4(hmax), ch.n_out, ch.activation, scale_flag, 0);
+    }
+    // 2. the generic exact-fp32 variants: the process model (a traced one, or a built-in form without a specialised
+    //    variant, rewritten as a program) is interpreted per sample -- value and reverse sweep -- inside the same
+    //    register-tile kernels; chain inputs are padded up to the compiled count (2 / 4 / 8) with zero columns,
+    //    scale_nn_outputs is a run-time flag.  EH_NO_SMALL_PROGRAM=1 sends these models to the tensor-core path.
+    std::vector<eh_pm_instr> prog;
+    std::vector<int> prog_out;
+    bool use_prog = false;
+    if (!v && small_shape && !getenv("EH_NO_SMALL_PROGRAM") && d->n_params >= 1 && d->n_params <= MAXPS && d->n_forc <= PmProgram::NF &&
+        d->n_targ <= PmProgram::NT) {
+        const Variant* vp = find_variant(EH_PM_PROGRAM, ch.n_in, ch.n_hidden, rup4(hmax), ch.n_out, ch.activation, 1, 0);
+        if (vp && builtin_as_program(d, is_prog, prog, prog_out)) { v = vp; use_prog = true; }
+    }
+    if (!v) return build_plan_wide(c, d, is_prog);
+    if (!use_prog && v->T != d->n_targ) return fail(c, EH_EINVAL, "process model yields %d targets, descriptor has %d", v->T, d->n_targ);
     c->var = v;
+    c->small_prog = use_prog;
+    c->scale_rt = scale_flag;
+    if (use_prog) {
+        PmProgData& pd = c->h_prog;
+        memset(&pd, 0, sizeof pd);
+        pd.len = (int)prog.size(); pd.nt = d->n_targ; pd.nf = d->n_forc; pd.np = d->n_params;
+        for (int t = 0; t < d->n_targ; t++) pd.out[t] = prog_out[(size_t)t];
+        for (int i = 0; i < pd.len; i++) {
+            pd.op[i] = (short)prog[(size_t)i].op; pd.a[i] = (short)prog[(size_t)i].a; pd.b[i] = (short)prog[(size_t)i].b;
+            pd.imm[i] = prog[(size_t)i].imm;
+        }
+    }
     c->var2 = (v->engine == 0) ? find_variant(v->pm, v->P, v->NH, v->H, v->NOUT, v->act, v->scale, 2) : nullptr;
     c->n_pred_raw = d->n_pred; c->n_forc_raw = d->n_forc; c->n_targ = d->n_targ;
     c->use_bn = ch.input_batchnorm ? 1 : 0;
@@ -1203,7 +1410,8 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
     memset(c->slots, 0, sizeof c->slots);
     for (int s = 0; s < MAXPS; s++) c->slots[s].role = ROLE_FIXED;
     for (int s = 0; s < v->NPS; s++) {
-        int pi = is_prog ? s : d->pm_args[s].index;   // traced programs address the parameter table directly
+        int pi = use_prog ? s : d->pm_args[s].index;   // programs address the parameter table directly
+        if (use_prog && pi >= d->n_params) continue;   // unused slot of the generic variant: FIXED, never read
         if (pi < 0 || pi >= d->n_params) return fail(c, EH_EINVAL, "pm_args[%d].index out of range", s);
         PSlot& sl = c->slots[s];
         sl.role = d->role[pi];
@@ -1274,15 +1482,21 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
     for (int g = 0; g < ng; g++)
         for (int s = 0; s < v->NPS; s++)
             if (c->slots[s].role == ROLE_GLOBAL && c->slots[s].idx == g) c->h_slot_of_flat[off + g] = s;
-    c->pm_id = d->process_model;
+    c->pm_id = use_prog ? (int)EH_PM_PROGRAM : d->process_model;
 
-    // record columns: chain inputs, the form's forcing, targets
+    // record columns: chain inputs, the form's forcing, targets.  The generic variants have compile-time maxima:
+    // missing inputs / forcings are zero columns (kind 2), missing targets NaN columns (kind 3: always masked)
     c->ncols = 0;
     for (int k = 0; k < ch.n_in; k++) {
         if (ch.in_cols[k] < 0 || ch.in_cols[k] >= d->n_pred) return fail(c, EH_EINVAL, "chain in_cols[%d] out of range", k);
         c->src_kind[c->ncols] = 0; c->src_idx[c->ncols] = ch.in_cols[k]; c->ncols++;
     }
-    if (is_prog) {
+    for (int k = ch.n_in; k < v->P; k++) { c->src_kind[c->ncols] = 2; c->src_idx[c->ncols] = 0; c->ncols++; }
+    if (use_prog) {
+        for (int fi = 0; fi < v->F; fi++) {
+            c->src_kind[c->ncols] = fi < d->n_forc ? 1 : 2; c->src_idx[c->ncols] = fi < d->n_forc ? fi : 0; c->ncols++;
+        }
+    } else if (is_prog) {
         for (int fi = 0; fi < d->n_forc; fi++) { c->src_kind[c->ncols] = 1; c->src_idx[c->ncols] = fi; c->ncols++; }
     } else {
         int fi = d->pm_args[2].index;
@@ -1290,6 +1504,7 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
         c->src_kind[c->ncols] = 1; c->src_idx[c->ncols] = fi; c->ncols++;
     }
     for (int t = 0; t < d->n_targ; t++) { c->src_kind[c->ncols] = 1; c->src_idx[c->ncols] = d->n_forc + t; c->ncols++; }
+    for (int t = d->n_targ; t < v->T; t++) { c->src_kind[c->ncols] = 3; c->src_idx[c->ncols] = 0; c->ncols++; }
 
     // loss / optimiser
     int n_rmse = 0;
@@ -1306,8 +1521,8 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
     if (c->opt_kind < 0 || c->opt_kind > 3) return fail(c, EH_EINVAL, "opt_kind=%d unknown", d->opt_kind);
     c->adamw_coupled = d->adamw_decay_coupled_eta;
     c->eta = d->eta; c->beta1 = d->beta1; c->beta2 = d->beta2; c->eps = d->eps; c->lambda = d->lambda;
-    c->bn_mean.assign((size_t)ch.n_in, 0.f);
-    c->bn_var.assign((size_t)ch.n_in, 1.f);
+    c->bn_mean.assign((size_t)std::max(ch.n_in, v->P), 0.f);   // padded inputs: statistics of a zero column, never read back
+    c->bn_var.assign((size_t)std::max(ch.n_in, v->P), 1.f);
     return EH_OK;
 }
 
@@ -1333,8 +1548,11 @@ eh_status ensure_host_stage(eh_ctx* c, HostStage& h, int64_t B)
     CK(dalloc(&h.d_planes, (size_t)cap * (c->n_forc_raw + c->n_targ)));
     CK(dalloc(&h.d_rec, (size_t)cap * c->var->R4));
     if (!h.d_cnt) {
-        CK(dalloc(&h.d_cnt, (size_t)MAXT));
-        CK(cudaMemsetAsync(h.d_cnt, 0, MAXT * sizeof(int), c->stream));  // (the packer's stream) k_bscal_from_counts re-zeroes it after every use
+        CK(dalloc(&h.d_cnt, (size_t)MAXT + 1));
+        // counters + ticket start at zero; every packer re-arms them after use.  Both streams may launch the
+        // first packer of this slot, so the clear is waited for once
+        CK(cudaMemsetAsync(h.d_cnt, 0, (MAXT + 1) * sizeof(int), c->stream));
+        CK(cudaStreamSynchronize(c->stream));
     }
     if (!h.d_bscal) CK(dalloc(&h.d_bscal, (size_t)BS_STRIDE));
     if (!h.d_loss) CK(dalloc(&h.d_loss, (size_t)1));
@@ -1343,6 +1561,8 @@ eh_status ensure_host_stage(eh_ctx* c, HostStage& h, int64_t B)
     h.cap = cap;
     return EH_OK;
 }
+
+eh_status enqueue_host_step_compute(eh_ctx* c, HostStage& h, int64_t B, float* loss_dst, bool heavy, int reserve_sms);
 
 // enqueue one host batch: H2D copies on the copy stream (they overlap the steps of earlier batches still running on
 // the compute stream; EH_HOST_SLOTS staging slots), then pack, per-batch scalars, K1, K2 on the compute stream.
@@ -1353,7 +1573,47 @@ eh_status enqueue_host_step(eh_ctx* c, HostStage& h, int64_t B, const float* X, 
 {
     const Variant* v = c->var;
     cudaStream_t cs = c->copy_stream;
+    bool heavy = c->use_bn;
+    for (int t = 0; t < c->n_targ; t++) heavy |= (c->loss_kind[t] == LOSS_NSELOSS);
+    // page-locked inputs are read in place by the packer (zero copy); anything else goes through the copy engine
+    bool zero_copy = c->host_zero_copy && c->n_forc_raw + c->n_targ <= EH_PACK_MAXPLANES;
+    PackHostArgs z;
+    if (zero_copy) {
+        memset(&z, 0, sizeof z);
+        z.X = c->n_pred_raw > 0 ? mapped_host_ptr(X) : nullptr;
+        zero_copy = c->n_pred_raw == 0 || z.X != nullptr;
+        for (int f = 0; zero_copy && f < c->n_forc_raw; f++) zero_copy = (z.plane[f] = mapped_host_ptr(forc[f])) != nullptr;
+        for (int t = 0; zero_copy && t < c->n_targ; t++)
+            zero_copy = (z.plane[c->n_forc_raw + t] = mapped_host_ptr(targ[t])) != nullptr;
+    }
     if (h.used) CK(cudaStreamWaitEvent(cs, h.freed, 0));  // the step that last read this slot must have retired
+    if (zero_copy) {
+        z.N = B; z.P_raw = c->n_pred_raw; z.ncols = c->ncols; z.R4 = v->R4;
+        for (int i = 0; i < c->ncols; i++) { z.src_kind[i] = c->src_kind[i]; z.src_idx[i] = c->src_idx[i]; }
+        z.x_pair = c->n_pred_raw == 2 && c->ncols >= 2 && c->src_kind[0] == 0 && c->src_idx[0] == 0 && c->src_kind[1] == 0 &&
+                   c->src_idx[1] == 1 && ((uintptr_t)z.X & 7) == 0;
+        z.rec = h.d_rec; z.T = c->n_targ; z.ycol0 = v->P + v->F; z.agg_mean = c->agg_mean;
+        z.cnt = h.d_cnt; z.bscal = heavy ? nullptr : h.d_bscal;
+        const int ctas = (int)std::min<int64_t>(EH_PACK_HOST_CTAS, (B + 1023) / 1024);
+        k_pack_host<<<ctas, 1024, 0, cs>>>(z);
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(h.ready, cs));
+        CK(cudaStreamWaitEvent(c->stream, h.ready, 0));
+        h.used = true;
+        if (heavy) {
+            StatArgs a;
+            memset(&a, 0, sizeof a);
+            a.rec = h.d_rec; a.R4 = v->R4; a.idx = nullptr; a.rec_base = 0; a.n = B; a.Bfull = (int)B;
+            a.P = v->P; a.F = v->F; a.T = c->n_targ;
+            const Split& sp = c->split[EH_SPLIT_TRAIN];
+            for (int t = 0; t < MAXT; t++) { a.shift_y[t] = sp.shift_y[t]; a.loss_kind[t] = c->loss_kind[t]; }
+            for (int k = 0; k < MAXP; k++) a.shift_x[k] = sp.shift_x[k];
+            a.agg_mean = c->agg_mean; a.use_bn = c->use_bn; a.bscal = h.d_bscal; a.bn_batch = nullptr;
+            k_batch_stats<<<1, 256, 0, c->stream>>>(a);
+            CK(cudaGetLastError());
+        }
+        return enqueue_host_step_compute(c, h, B, loss_dst, heavy, EH_PACK_HOST_CTAS);
+    }
     CK(cudaMemcpyAsync(h.d_X, X, (size_t)B * c->n_pred_raw * sizeof(float), cudaMemcpyHostToDevice, cs));
     for (int f = 0; f < c->n_forc_raw; f++)
         CK(cudaMemcpyAsync(h.d_planes + (size_t)f * B, forc[f], (size_t)B * sizeof(float), cudaMemcpyHostToDevice, cs));
@@ -1368,8 +1628,6 @@ eh_status enqueue_host_step(eh_ctx* c, HostStage& h, int64_t B, const float* X, 
     p.X = h.d_X; p.planes = h.d_planes; p.N = B; p.P_raw = c->n_pred_raw; p.ncols = c->ncols; p.R4 = v->R4;
     for (int i = 0; i < c->ncols; i++) { p.src_kind[i] = c->src_kind[i]; p.src_idx[i] = c->src_idx[i]; }
     p.rec = h.d_rec; p.rec_base = 0;
-    bool heavy = c->use_bn;
-    for (int t = 0; t < c->n_targ; t++) heavy |= (c->loss_kind[t] == LOSS_NSELOSS);
     if (!heavy) {
         k_pack_count<<<(unsigned)((B + 255) / 256), 256, 0, c->stream>>>(p, c->n_targ, v->P + v->F, h.d_cnt);
         CK(cudaGetLastError());
@@ -1381,7 +1639,7 @@ eh_status enqueue_host_step(eh_ctx* c, HostStage& h, int64_t B, const float* X, 
         StatArgs a;
         memset(&a, 0, sizeof a);
         a.rec = h.d_rec; a.R4 = v->R4; a.idx = nullptr; a.rec_base = 0; a.n = B; a.Bfull = (int)B;
-        a.P = v->P; a.F = v->F; a.T = v->T;
+        a.P = v->P; a.F = v->F; a.T = c->n_targ;
         const Split& sp = c->split[EH_SPLIT_TRAIN];
         for (int t = 0; t < MAXT; t++) { a.shift_y[t] = sp.shift_y[t]; a.loss_kind[t] = c->loss_kind[t]; }
         for (int k = 0; k < MAXP; k++) a.shift_x[k] = sp.shift_x[k];
@@ -1389,6 +1647,12 @@ eh_status enqueue_host_step(eh_ctx* c, HostStage& h, int64_t B, const float* X, 
         k_batch_stats<<<1, 256, 0, c->stream>>>(a);
         CK(cudaGetLastError());
     }
+    return enqueue_host_step_compute(c, h, B, loss_dst, heavy, 0);
+}
+
+// second half of a host-batch step: the records of slot `h` are ready on the compute stream
+eh_status enqueue_host_step_compute(eh_ctx* c, HostStage& h, int64_t B, float* loss_dst, bool heavy, int reserve_sms)
+{
     if (c->wide) {
         if (c->world > 1) return fail(c, EH_EUNSUPPORTED, "host-batch steps of the tensor-core path are single-GPU: use eh_run_steps in data-parallel mode");
         cudaError_t we = c->wide->step(h.d_rec, nullptr, 0, (int)B, h.d_bscal, c->d_theta, c->d_m, c->d_v, c->d_ost, c->d_grad, loss_dst, 1,
@@ -1415,7 +1679,7 @@ eh_status enqueue_host_step(eh_ctx* c, HostStage& h, int64_t B, const float* X, 
     fill_step_args(c, a);
     a.rec = reinterpret_cast<const float4*>(h.d_rec);
     a.idx = nullptr; a.rec_base = 0; a.B = (int)B; a.bscal = h.d_bscal;
-    Geom g = step_geometry(c, B);
+    Geom g = step_geometry(c, B, reserve_sms);
     const bool pdl = false;  // the step follows memcpy/pack work here, nothing to overlap with
     CK(pick_variant(c, B)->launch_step(a, g.grid, g.nwarps, g.smem, c->stream, pdl));
     UpdateArgs u;
@@ -1467,6 +1731,7 @@ eh_status eh_create(eh_ctx** out, const eh_model_desc* desc)
     auto cuda_setup = [&]() -> eh_status {
         CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        if (const char* e = getenv("EH_HOST_NO_ZEROCOPY")) c->host_zero_copy = !(e[0] && e[0] != '0');
         CK(cudaEventCreate(&c->ev0));
         CK(cudaEventCreate(&c->ev1));
         CK(cudaEventCreate(&c->ev2));
@@ -1503,6 +1768,10 @@ eh_status eh_create(eh_ctx** out, const eh_model_desc* desc)
         CK(dalloc(&c->d_err, (size_t)1));
         CK(dalloc(&c->d_evalpart, (size_t)c->nsm * 4 * MAXT * EVAL_NSTAT));
         CK(dalloc(&c->d_bn_test, (size_t)BS_STRIDE));
+        if (c->small_prog) {
+            CK(cudaMalloc((void**)&c->d_prog, sizeof(PmProgData)));
+            CK(cudaMemcpy(c->d_prog, &c->h_prog, sizeof(PmProgData), cudaMemcpyHostToDevice));
+        }
         CK(cudaMemset(c->d_theta, 0, ((size_t)c->nflat + PARAM_TAIL) * sizeof(float)));
         CK(refresh_tail(c));
         if (v->engine == 3) {
@@ -1538,7 +1807,7 @@ void eh_destroy(eh_ctx* c)
     if (c->dp_block) cudaFree(c->dp_block);
     void* ptrs[] = {c->d_wsrc, c->d_pmap, c->d_pspan, c->d_theta, c->d_m, c->d_v, c->d_grad, c->d_ost, c->d_partial,
                     c->d_gvec, c->d_dperr, c->d_cells, c->d_slot_of_flat, c->d_losskind, c->d_pbuf, c->d_stats, c->d_bscal, c->d_bn_batch, c->d_idx, c->d_idx64, c->d_err, c->d_loss, c->d_evalpart,
-                    c->d_bn_test, c->split[0].rec, c->split[1].rec};
+                    c->d_bn_test, c->d_prog, c->split[0].rec, c->split[1].rec};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (HostStage& h : c->hs) {
@@ -1847,7 +2116,7 @@ eh_status eh_eval(eh_ctx* c, int32_t split, float* yhat, double* stats, float* n
     memset(&a, 0, sizeof a);
     a.rec = reinterpret_cast<const float4*>(sp.rec);
     a.rec_base = 0; a.N = N; a.pblock = c->d_theta; a.nflat = c->nflat; a.wsrc = c->d_wsrc;
-    a.use_bn = c->use_bn;
+    a.use_bn = c->use_bn; a.prog = c->d_prog; a.scale_rt = c->scale_rt;
     if (c->use_bn) {
         // test mode: running statistics (LuxCore.testmode(st), compute_loss.jl:37)
         float row[BS_STRIDE];
@@ -1911,7 +2180,7 @@ eh_status eh_eval(eh_ctx* c, int32_t split, float* yhat, double* stats, float* n
     CK(cudaEventRecord(c->ev1, c->stream));
     std::vector<double> part((size_t)grid * v->T * EVAL_NSTAT);
     CK(cudaMemcpyAsync(part.data(), c->d_evalpart, part.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    if (yhat) CK(cudaMemcpyAsync(yhat, d_yhat, (size_t)N * v->T * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (yhat) CK(cudaMemcpyAsync(yhat, d_yhat, (size_t)N * c->n_targ * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
     c->last_launches = 1;
@@ -1926,7 +2195,7 @@ eh_status eh_eval(eh_ctx* c, int32_t split, float* yhat, double* stats, float* n
     if (d_yhat) cudaFree(d_yhat);
     if (d_par) cudaFree(d_par);
     if (stats) {
-        for (int t = 0; t < v->T; t++) {
+        for (int t = 0; t < c->n_targ; t++) {   // (the generic variants carry unused, always-masked target columns)
             for (int q = 0; q < EVAL_NSTAT; q++) {
                 double s = 0;
                 for (int g = 0; g < grid; g++) s += part[(size_t)g * v->T * EVAL_NSTAT + t * EVAL_NSTAT + q];
@@ -1987,7 +2256,7 @@ static void fill_stat_args(const eh_ctx* c, StatArgs& a, int64_t n, int64_t B)
     const Split& sp = c->split[EH_SPLIT_TRAIN];
     memset(&a, 0, sizeof a);
     a.rec = sp.rec; a.R4 = c->var->R4; a.idx = c->d_idx; a.n = n; a.Bfull = (int)B;
-    a.P = c->var->P; a.F = c->var->F; a.T = c->var->T;
+    a.P = c->var->P; a.F = c->var->F; a.T = c->n_targ;
     for (int t = 0; t < MAXT; t++) { a.shift_y[t] = 0.f; a.loss_kind[t] = c->loss_kind[t]; }  // common shift on every rank
     for (int k = 0; k < MAXP; k++) a.shift_x[k] = 0.f;
     a.agg_mean = c->agg_mean; a.use_bn = 1;  // input sums are always taken: the ranks must agree on the layout
@@ -2041,6 +2310,11 @@ eh_status eh_dp_set_batch_moments(eh_ctx* c, int64_t B, const double* global)
     if (e != cudaSuccess) return fail(c, EH_ECUDA, "eh_dp_set_batch_moments: %s", cudaGetErrorString(e));
     c->perm_B = B;  // the rows of this permutation / batch size are in place
     return EH_OK;
+}
+
+const char* eh_kernel_variant(const eh_ctx* c)
+{
+    return (c && c->var && c->var->name) ? c->var->name : "";
 }
 
 eh_status eh_host_alloc(void** out, size_t bytes)

@@ -34,6 +34,7 @@ struct PmCtx {
     const float* pms;          // [MAXPS * PMS_PER_SLOT] per-slot derived scalars
     const float* c;            // process-model constants
     const PmProgData* prog;    // traced program (PmProgram only)
+    int scale_rt;              // PmProgram only: scale_nn_outputs as a run-time flag (one compiled variant serves both)
     unsigned uniform_mask;     // bit s set: slot s is GLOBAL / FIXED (same value for all samples)
     __device__ __forceinline__ bool uniform(int s) const { return (uniform_mask >> s) & 1u; }
 };

@@ -30,6 +30,8 @@ struct StepArgs {
     PSlot slot[MAXPS];
     float pmc[4];             // process-model constants
     int use_bn;
+    const PmProgData* prog;   // traced process model (PmProgram variants), device memory
+    int scale_rt;             // PmProgram variants: scale_nn_outputs
 };
 
 // per-CTA work region (floats): staging tiles of all warps, reused as the [nwarps][NPART] reduction scratch
@@ -67,6 +69,8 @@ __global__ void __launch_bounds__(E::MAX_WARPS * 32, 1) k_step(const StepArgs a)
     PmCtx cx;
     cx.pms = sS + SS_PMS;
     cx.c = a.pmc;
+    cx.prog = a.prog;
+    cx.scale_rt = a.scale_rt;
     cx.uniform_mask = 0;
 #pragma unroll
     for (int s = 0; s < MAXPS; s++)

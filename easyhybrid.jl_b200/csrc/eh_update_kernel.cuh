@@ -309,11 +309,20 @@ struct PackArgs {
     int P_raw;
     int ncols;            // used columns of a record
     int R4;
-    int src_kind[24];     // 0: X row, 1: plane
+    int src_kind[24];     // 0: X row, 1: plane, 2: zeros, 3: NaNs
     int src_idx[24];
     float* rec;           // [N][R4]
     long long rec_base;   // first record to write
 };
+
+// column c of sample i: kind 0 = row of X, 1 = forcing / target plane, 2 = zero column, 3 = NaN column (the padding
+// inputs / forcings and the always-masked padding targets of the generic variants)
+__device__ __forceinline__ float pack_load(const PackArgs& a, int c, long long i)
+{
+    const int k = a.src_kind[c];
+    if (k >= 2) return k == 2 ? 0.f : __int_as_float(0x7fc00000);
+    return k == 0 ? a.X[i * a.P_raw + a.src_idx[c]] : a.planes[(long long)a.src_idx[c] * a.N + i];
+}
 
 __global__ void __launch_bounds__(256) k_pack(const PackArgs a)
 {
@@ -322,7 +331,7 @@ __global__ void __launch_bounds__(256) k_pack(const PackArgs a)
     float* r = a.rec + (a.rec_base + i) * a.R4;
     for (int c = 0; c < a.R4; c++) {
         float v = 0.f;
-        if (c < a.ncols) v = a.src_kind[c] == 0 ? a.X[i * a.P_raw + a.src_idx[c]] : a.planes[(long long)a.src_idx[c] * a.N + i];
+        if (c < a.ncols) v = pack_load(a, c, i);
         r[c] = v;
     }
 }

@@ -3,12 +3,17 @@
 
 namespace eh {
 
+constexpr int NGROUPS = 7;
 static const Variant* group(int k, int* n)
 {
     switch (k) {
     case 0: return variants_rbq10(n);
     case 1: return variants_expo(n);
     case 2: return variants_linear(n);
+    case 3: return variants_prog_tanh(n);
+    case 4: return variants_prog_sigmoid(n);
+    case 5: return variants_prog_relu(n);
+    case 6: return variants_prog_swish(n);
     default: *n = 0; return nullptr;
     }
 }
@@ -16,14 +21,14 @@ static const Variant* group(int k, int* n)
 int num_variants()
 {
     int tot = 0, n = 0;
-    for (int k = 0; k < 3; k++) { group(k, &n); tot += n; }
+    for (int k = 0; k < NGROUPS; k++) { group(k, &n); tot += n; }
     return tot;
 }
 
 const Variant* variant_at(int i)
 {
     int n = 0;
-    for (int k = 0; k < 3; k++) {
+    for (int k = 0; k < NGROUPS; k++) {
         const Variant* g = group(k, &n);
         if (i < n) return g + i;
         i -= n;
@@ -37,9 +42,12 @@ const Variant* find_variant(int pm, int P, int NH, int H, int NOUT, int act, int
     for (int i = 0; i < num_variants(); i++) {
         const Variant* v = variant_at(i);
         if (v->engine != engine) continue;
-        if (v->pm != pm || v->P != P || v->NH != NH || v->NOUT != NOUT || v->act != act || v->scale != scale) continue;
+        if (v->pm != pm || v->NH != NH || v->NOUT != NOUT || v->act != act || v->scale != scale) continue;
+        // hidden widths are padded up to the compiled width; the generic (interpreted process model) variants
+        // also pad the chain inputs with zero columns
         if (v->H < H) continue;
-        if (!best || v->H < best->H) best = v;
+        if (pm == PM_PROGRAM ? v->P < P : v->P != P) continue;
+        if (!best || v->H < best->H || (v->H == best->H && v->P < best->P)) best = v;
     }
     return best;
 }

@@ -32,5 +32,11 @@ const Variant* variant_at(int i);
 const Variant* variants_rbq10(int* n);
 const Variant* variants_expo(int* n);
 const Variant* variants_linear(int* n);
+// generic exact-fp32 variants: the process model is a traced program interpreted per sample (PmProgram);
+// one translation unit per activation
+const Variant* variants_prog_tanh(int* n);
+const Variant* variants_prog_sigmoid(int* n);
+const Variant* variants_prog_relu(int* n);
+const Variant* variants_prog_swish(int* n);
 
 }  // namespace eh

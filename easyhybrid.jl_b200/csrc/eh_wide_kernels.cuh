@@ -166,6 +166,7 @@ __global__ void __launch_bounds__(256) k_wide_head(const HeadArgs a)
     cx.pms = s_pms + MAXPS;
     cx.c = a.pmc;
     cx.prog = &s_prog;
+    cx.scale_rt = HC::SCALE ? 1 : 0;
     cx.uniform_mask = 0;
 #pragma unroll
     for (int s = 0; s < MAXPS; s++)
@@ -239,7 +240,7 @@ __global__ void __launch_bounds__(256) k_wide_head(const HeadArgs a)
         for (int k = 0; k < F; k++) f[k] = k < nf ? r[P + k] : 0.f;
 #pragma unroll
         for (int k = 0; k < T; k++) y[k] = k < nt ? r[P + nf + k] : __int_as_float(0x7fc00000);   // absent target = masked
-        resolve_params<HC>(a.slot, s_pms, zo, pv, sg);
+        resolve_params<HC>(a.slot, s_pms, zo, pv, sg, cx);
         PM::fwd(pv, f, cx, yh, sv);
         if (!a.train) {
             if (lane == 0) {

@@ -182,6 +182,10 @@ class FusedSession:
         if st != _abi.EH_OK:
             self._ck(st)
 
+    def kernel_variant(self):
+        """name of the compiled kernel family serving this model (eh_kernel_variant)"""
+        return (self.lib.eh_kernel_variant(self.h) or b"").decode()
+
     def sync(self):
         self._ck(self.lib.eh_sync(self.h))
         self._inflight = []

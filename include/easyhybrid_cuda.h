@@ -295,6 +295,12 @@ eh_status eh_host_free(void* p);
 eh_status eh_last_timing(eh_ctx* ctx, float* total_ms, int64_t* launches, float* step_kernel_ms);
 eh_status eh_set_profiling(eh_ctx* ctx, int32_t on);
 
+/* which compiled kernel family serves this ctx (static string, never NULL), e.g.
+ * "ffma2/PmRbQ10/P2/NH2/H16/O1/ACT_TANH/scale=true" (exact-fp32 register-tile kernels, specialised form),
+ * "ffma2/PmProgram/..." (same kernels, process model interpreted per sample) or "wide/bf16-tcgen05".
+ * The reference has no counterpart; callers use it to report / assert the path a model took.          */
+const char* eh_kernel_variant(const eh_ctx* ctx);
+
 /* diagnostics: runs one tcgen05 GEMM of the wide-hidden-layer path on host matrices (bf16 bit patterns) so that a
  * test harness can check the kernels in isolation.  mode 0: out = act(A B^T + bias), A [M x K], B [N x K];
  * mode 1: out = (A B^T) .* act'(aux), aux [M x N]; both write bf16 [M x N].  modes 3 / 4: the persistent forms of 0 / 1.  mode 2: out[z] = A_z^T B_z for the

@@ -240,6 +240,45 @@ def test_step_host_async_stream_equals_epoch(eh, orc, B):
     sess.close()
 
 
+HOST_CASES = [
+    ("rbq10-nan", lambda eh: rbq10_model(eh), lambda n: make_synth(n, nan_frac=0.04), "mse"),
+    ("rbq10-bn", lambda eh: rbq10_model(eh, bn=True), lambda n: make_synth(n, nan_frac=0.02), "mse"),
+    ("expo-nse", lambda eh: expo_model(eh), lambda n: make_expo(n), "nseLoss"),
+    ("linear2", lambda eh: linear_model(eh, two=True, activation="tanh"), lambda n: make_linear(n, two=True), "mse"),
+]
+
+
+@pytest.mark.parametrize("name,mk,mkdata,loss", HOST_CASES, ids=[c[0] for c in HOST_CASES])
+def test_zero_copy_host_batches_equal_copy_engine_path(eh, orc, monkeypatch, name, mk, mkdata, loss):
+    """page-locked host batches are packed in place over PCIe (k_pack_host); pageable ones -- or all of them with
+    EH_HOST_NO_ZEROCOPY=1 -- are staged by the copy engine.  Same records, same per-batch scalars: bit-identical
+    losses and parameters, also with NaN targets (valid counts), BatchNorm / nseLoss (K0 on the packed records),
+    records wider than one float4, ragged batch sizes."""
+    sizes = [4096, 1000, 33, 2048, 5]
+    n = sum(sizes)
+    results = []
+    for nozc in ("0", "1"):
+        monkeypatch.setenv("EH_HOST_NO_ZEROCOPY", nozc)
+        # (prepare_data drops rows without any valid target: generate more than needed)
+        model, xf, y, flat, sess, o, rng = _setup(eh, orc, mk, lambda: mkdata(n + n // 4), loss, "sum")
+        assert xf[0].shape[0] >= n
+        losses = sess.pinned(np.zeros(len(sizes), dtype=np.float32))
+        keep, a = [], 0
+        for k, b in enumerate(sizes):
+            sl = slice(a, a + b)
+            a += b
+            hb = sess.host_batch(sess.pinned(xf[0][sl]), [sess.pinned(xf[1][f][sl]) for f in model.forcing],
+                                 [sess.pinned(y[t][sl]) for t in model.targets])
+            keep.append(hb)
+            sess.step_host_async(hb, losses, k)
+        sess.sync()
+        results.append((np.array(losses), sess.get_params()))
+        sess.close()
+    assert np.array_equal(results[0][0], results[1][0])
+    assert np.array_equal(results[0][1], results[1][1])
+    assert np.isfinite(results[0][0]).all()
+
+
 def test_unsupported_models_fail_loudly(eh):
     from easyhybrid_b200 import _abi
 

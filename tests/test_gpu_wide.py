@@ -144,10 +144,13 @@ def test_tcgen05_gemm_kernels_against_torch():
     assert mod.main(False)
 
 
-def test_traced_process_model_runs_on_the_tensor_core_path(eh, orc):
+def test_traced_process_model_runs_on_the_tensor_core_path(eh, orc, monkeypatch):
     """a process model that is none of the built-in forms (src/models/GenericHybridModel.jl:425 takes any callable):
-    traced into a straight-line program by the host, interpreted (value and pullback) in the head kernel"""
+    traced into a straight-line program by the host, interpreted (value and pullback) in the head kernel.
+    (Chains this narrow normally take the exact-fp32 generic variants, tests/test_gpu_generic.py; EH_NO_SMALL_PROGRAM
+    sends the model to the tensor-core path, which is what wider chains with a traced model use.)"""
     from conftest import make_synth
+    monkeypatch.setenv("EH_NO_SMALL_PROGRAM", "1")
 
     def custom(*, ta, dsw_pot, rb, Q10, alpha, tref=15.0):
         return {"reco": rb * Q10 ** (0.1 * (ta - tref)) + alpha * np.tanh(0.05 * dsw_pot)}
@@ -164,6 +167,7 @@ def test_traced_process_model_runs_on_the_tensor_core_path(eh, orc):
     rng = np.random.default_rng(5)
     flat = model.initialparameters(rng)
     sess = eh.FusedSession(model, training_loss="mse", opt=eh.Adam(0.01))
+    assert sess.kernel_variant().startswith("wide/"), sess.kernel_variant()
     sess.upload(0, xf, y)
     sess.set_params(flat)
     o = orc.Oracle(model, training_loss="mse", opt=eh.Adam(0.01))
