@@ -51,6 +51,24 @@ struct HostStage {  // device staging for eh_step_host*: raw arrays + packed rec
 };
 constexpr int EH_HOST_SLOTS = 4;  // batches in flight between the copy engine and the step kernels
 
+// eh_step_host_async, grouped form: page-locked batches are packed (zero copy) into a ring of staging slots; every
+// EH_RING_GROUP batches ONE persistent launch runs that many optimiser steps over the group's slots, while the packers
+// of the next group keep the PCIe link busy.  Three groups: one training, one being packed, one draining.
+constexpr int EH_RING_GROUP = 16, EH_RING_NGRP = 3;
+struct HostRing {
+    float* d_rec = nullptr;    // [NGRP][GROUP * cap][R4]; slot k of a group starts at record k * B (B = the group's batch size)
+    float* d_bscal = nullptr;  // [NGRP * GROUP][BS_STRIDE]
+    int* d_cnt = nullptr;      // [NGRP * GROUP][MAXT + 1]
+    cudaEvent_t packed[2] = {nullptr, nullptr};  // last packer of the open group on either copy stream
+    cudaEvent_t freed[EH_RING_NGRP] = {nullptr, nullptr, nullptr};
+    bool used[EH_RING_NGRP] = {false, false, false};
+    int64_t cap = 0;           // samples per slot
+    int g = 0, k = 0;          // open group, batches packed into it so far
+    int64_t B = 0;             // batch size of the open group
+    float* loss0 = nullptr;    // page-locked loss cell of the group's first step (the others follow contiguously)
+    bool off = false;          // EH_HOST_NO_GROUPS=1
+};
+
 }  // namespace
 
 struct eh_ctx {
@@ -58,7 +76,7 @@ struct eh_ctx {
     int device = 0;
     int nsm = 0;
     size_t smem_optin = 0;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr, copy_stream2 = nullptr;
     const Variant* var = nullptr;   // engine chosen at eh_create (FFMA2 one sample per lane, or tensor pipe)
     const Variant* var2 = nullptr;  // FFMA2 two samples per lane: same layouts, used for large batches
     // wide-hidden-layer path (bf16 tcgen05 GEMMs, eh_wide.cu): `var` then points at `wide_var`, a descriptor
@@ -122,6 +140,7 @@ struct eh_ctx {
     // host-step pipeline
     HostStage hs[EH_HOST_SLOTS];
     int hs_next = 0;
+    HostRing ring;
     bool small_prog = false;     // register-tile path with an interpreted process model (PmProgram variants)
     int scale_rt = 0;            // scale_nn_outputs as the generic variants take it
     PmProgData h_prog;           // the program, host copy
@@ -239,11 +258,13 @@ __global__ void __launch_bounds__(256) k_pack_count(const PackArgs a, int T, int
 
 // Zero-copy packer of the host-batch path: the caller's page-locked arrays are read straight over PCIe
 // (UVA device pointers of pinned host memory) and leave as packed records in HBM -- one launch on the copy
-// stream replaces the three cudaMemcpyAsync + the packer + the per-batch-scalar kernel.  The grid is kept
-// to EH_PACK_HOST_CTAS big CTAs so that the packer only ever occupies that many SMs next to a running step
-// kernel (step_geometry leaves them free); 16 x 1024 threads x >= 16 B keep > 256 KB in flight, enough to
-// cover the PCIe round trip at full rate.  The last CTA to finish (ticket) turns the valid-target counts
-// into the batch's scalar row, like k_bscal_from_counts.
+// stream replaces the three cudaMemcpyAsync + the packer + the per-batch-scalar kernel.  Packers alternate
+// between two copy streams (the ramp-up / drain of one overlaps the other: 37 -> 44 GB/s measured; a large
+// cudaMemcpy reaches 55 GB/s on the same box, 1 MiB ones 33 GB/s) and together are kept to EH_PACK_HOST_CTAS
+// big CTAs, so that they only ever occupy that many SMs next to a running step / persistent kernel
+// (step_geometry and the 128-CTA persistent grid leave them free); measured insensitive to the grid between
+// 16 x 1024 and 296 x 256 threads.  The last CTA to finish (ticket) turns the valid-target counts into the
+// batch's scalar row, like k_bscal_from_counts.
 constexpr int EH_PACK_HOST_CTAS = 16;
 constexpr int EH_PACK_MAXPLANES = 24;
 struct PackHostArgs {
@@ -1572,7 +1593,9 @@ eh_status enqueue_host_step(eh_ctx* c, HostStage& h, int64_t B, const float* X, 
                             const float* const* targ, float* loss_dst)
 {
     const Variant* v = c->var;
-    cudaStream_t cs = c->copy_stream;
+    // staging slots alternate between two copy streams: the ramp-up / drain of one batch's transfer overlaps the
+    // next batch's (a single stream serialises them and leaves the PCIe link idle in between)
+    cudaStream_t cs = ((&h - c->hs) & 1) ? c->copy_stream2 : c->copy_stream;
     bool heavy = c->use_bn;
     for (int t = 0; t < c->n_targ; t++) heavy |= (c->loss_kind[t] == LOSS_NSELOSS);
     // page-locked inputs are read in place by the packer (zero copy); anything else goes through the copy engine
@@ -1594,7 +1617,7 @@ eh_status enqueue_host_step(eh_ctx* c, HostStage& h, int64_t B, const float* X, 
                    c->src_idx[1] == 1 && ((uintptr_t)z.X & 7) == 0;
         z.rec = h.d_rec; z.T = c->n_targ; z.ycol0 = v->P + v->F; z.agg_mean = c->agg_mean;
         z.cnt = h.d_cnt; z.bscal = heavy ? nullptr : h.d_bscal;
-        const int ctas = (int)std::min<int64_t>(EH_PACK_HOST_CTAS, (B + 1023) / 1024);
+        const int ctas = (int)std::min<int64_t>(EH_PACK_HOST_CTAS / 2, (B + 1023) / 1024);   // two packers may be in flight
         k_pack_host<<<ctas, 1024, 0, cs>>>(z);
         CK(cudaGetLastError());
         CK(cudaEventRecord(h.ready, cs));
@@ -1690,7 +1713,139 @@ eh_status enqueue_host_step_compute(eh_ctx* c, HostStage& h, int64_t B, float* l
     return EH_OK;
 }
 
+// ---- grouped host batches (HostRing) ----
+eh_status ensure_ring(eh_ctx* c, int64_t B)
+{
+    HostRing& r = c->ring;
+    if (B <= r.cap) return EH_OK;
+    // growing frees the buffers: nothing may still be reading or writing them (the open group is empty here)
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaStreamSynchronize(c->copy_stream));
+    CK(cudaStreamSynchronize(c->copy_stream2));
+    if (r.d_rec) cudaFree(r.d_rec);
+    r.d_rec = nullptr; r.cap = 0;
+    const int64_t cap = std::max<int64_t>(B, 4096);
+    const int nslots = EH_RING_NGRP * EH_RING_GROUP;
+    CK(dalloc(&r.d_rec, (size_t)nslots * cap * c->var->R4));
+    if (!r.d_bscal) {
+        CK(dalloc(&r.d_bscal, (size_t)nslots * BS_STRIDE));
+        CK(dalloc(&r.d_cnt, (size_t)nslots * (MAXT + 1)));
+        CK(cudaMemsetAsync(r.d_cnt, 0, (size_t)nslots * (MAXT + 1) * sizeof(int), c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        for (int i = 0; i < 2; i++) CK(cudaEventCreateWithFlags(&r.packed[i], cudaEventDisableTiming));
+        for (int i = 0; i < EH_RING_NGRP; i++) CK(cudaEventCreateWithFlags(&r.freed[i], cudaEventDisableTiming));
+    }
+    for (int i = 0; i < EH_RING_NGRP; i++) r.used[i] = false;
+    r.cap = cap;
+    return EH_OK;
+}
+
+// launch the open group: one persistent kernel for its k batches (or, if that launch is refused, k step / update pairs)
+eh_status flush_host_group(eh_ctx* c)
+{
+    HostRing& r = c->ring;
+    if (r.k == 0) return EH_OK;
+    const Variant* v = c->var;
+    const int k = r.k, g = r.g;
+    const int64_t B = r.B;
+    r.k = 0;
+    r.g = (g + 1) % EH_RING_NGRP;
+    CK(cudaEventRecord(r.packed[0], c->copy_stream));
+    CK(cudaStreamWaitEvent(c->stream, r.packed[0], 0));
+    if (k > 1) {
+        CK(cudaEventRecord(r.packed[1], c->copy_stream2));
+        CK(cudaStreamWaitEvent(c->stream, r.packed[1], 0));
+    }
+    const float* rec = r.d_rec + (size_t)g * EH_RING_GROUP * r.cap * v->R4;
+    const float* bscal = r.d_bscal + (size_t)g * EH_RING_GROUP * BS_STRIDE;
+    bool used = false;
+    eh_status s = enqueue_persistent(c, rec, nullptr, bscal, r.loss0, (int64_t)k * B, B, 0, k, &used, nullptr);
+    if (s != EH_OK) return s;
+    if (!used) {
+        for (int i = 0; i < k; i++) {
+            StepArgs a;
+            fill_step_args(c, a);
+            a.rec = reinterpret_cast<const float4*>(rec + (size_t)i * B * v->R4);
+            a.idx = nullptr; a.rec_base = 0; a.B = (int)B; a.bscal = bscal + (size_t)i * BS_STRIDE;
+            Geom geo = step_geometry(c, B, EH_PACK_HOST_CTAS);
+            CK(pick_variant(c, B)->launch_step(a, geo.grid, geo.nwarps, geo.smem, c->stream, false));
+            UpdateArgs u;
+            fill_update_args(c, u);
+            u.G = geo.grid; u.bscal = a.bscal; u.loss_out = r.loss0 + i;
+            CK(launch_update(u, c->stream, false));
+        }
+    }
+    CK(cudaEventRecord(r.freed[g], c->stream));
+    r.used[g] = true;
+    return EH_OK;
+}
+
+// pack one page-locked batch into the open group; *taken = false when the batch has to go the per-step way
+eh_status ring_enqueue(eh_ctx* c, int64_t B, const float* X, const float* const* forc, const float* const* targ, float* pin,
+                       bool* taken)
+{
+    *taken = false;
+    HostRing& r = c->ring;
+    const Variant* v = c->var;
+    bool heavy = c->use_bn;
+    for (int t = 0; t < c->n_targ; t++) heavy |= (c->loss_kind[t] == LOSS_NSELOSS);
+    if (r.off || !c->host_zero_copy || c->wide || c->world > 1 || heavy || !c->persist_ok || c->profiling ||
+        (c->flags & EH_FLAG_NO_PERSIST) || c->n_forc_raw + c->n_targ > EH_PACK_MAXPLANES)
+        return EH_OK;
+    PackHostArgs z;
+    memset(&z, 0, sizeof z);
+    if (c->n_pred_raw > 0 && !(z.X = mapped_host_ptr(X))) return EH_OK;
+    for (int f = 0; f < c->n_forc_raw; f++)
+        if (!(z.plane[f] = mapped_host_ptr(forc[f]))) return EH_OK;
+    for (int t = 0; t < c->n_targ; t++)
+        if (!(z.plane[c->n_forc_raw + t] = mapped_host_ptr(targ[t]))) return EH_OK;
+    if (r.k > 0 && B != r.B) {
+        eh_status s = flush_host_group(c);
+        if (s != EH_OK) return s;
+    }
+    if (B > r.cap) {
+        eh_status s = ensure_ring(c, B);
+        if (s != EH_OK) return s;
+    }
+    const int g = r.g, k = r.k;
+    if (k == 0) {
+        r.B = B;
+        r.loss0 = pin;
+        if (r.used[g]) {   // the launch that last trained on this group's slots must have retired
+            CK(cudaStreamWaitEvent(c->copy_stream, r.freed[g], 0));
+            CK(cudaStreamWaitEvent(c->copy_stream2, r.freed[g], 0));
+        }
+    }
+    const int slot = g * EH_RING_GROUP + k;
+    z.N = B; z.P_raw = c->n_pred_raw; z.ncols = c->ncols; z.R4 = v->R4;
+    for (int i = 0; i < c->ncols; i++) { z.src_kind[i] = c->src_kind[i]; z.src_idx[i] = c->src_idx[i]; }
+    z.x_pair = c->n_pred_raw == 2 && c->ncols >= 2 && c->src_kind[0] == 0 && c->src_idx[0] == 0 && c->src_kind[1] == 0 &&
+               c->src_idx[1] == 1 && ((uintptr_t)z.X & 7) == 0;
+    z.rec = r.d_rec + ((size_t)g * EH_RING_GROUP * r.cap + (size_t)k * B) * v->R4;
+    z.T = c->n_targ; z.ycol0 = v->P + v->F; z.agg_mean = c->agg_mean;
+    z.cnt = r.d_cnt + (size_t)slot * (MAXT + 1);
+    z.bscal = r.d_bscal + (size_t)slot * BS_STRIDE;
+    // two packers may be in flight (one per copy stream): half the reserved SMs each
+    const int ctas = (int)std::min<int64_t>(EH_PACK_HOST_CTAS / 2, (B + 1023) / 1024);
+    k_pack_host<<<ctas, 1024, 0, (k & 1) ? c->copy_stream2 : c->copy_stream>>>(z);
+    CK(cudaGetLastError());
+    r.k = k + 1;
+    *taken = true;
+    if (r.k == EH_RING_GROUP) return flush_host_group(c);
+    return EH_OK;
+}
+
 }  // namespace
+
+// every entry point that looks at or changes the training state first launches what eh_step_host_async still holds back
+#define EH_ENTER(c)                                             \
+    do {                                                        \
+        CK(cudaSetDevice((c)->device));                         \
+        if ((c)->ring.k) {                                      \
+            eh_status fs__ = flush_host_group(c);               \
+            if (fs__ != EH_OK) return fs__;                     \
+        }                                                       \
+    } while (0)
 
 // =============================== C ABI ===============================
 extern "C" {
@@ -1731,7 +1886,9 @@ eh_status eh_create(eh_ctx** out, const eh_model_desc* desc)
     auto cuda_setup = [&]() -> eh_status {
         CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&c->copy_stream2, cudaStreamNonBlocking));
         if (const char* e = getenv("EH_HOST_NO_ZEROCOPY")) c->host_zero_copy = !(e[0] && e[0] != '0');
+        if (const char* e = getenv("EH_HOST_NO_GROUPS")) c->ring.off = e[0] && e[0] != '0';
         CK(cudaEventCreate(&c->ev0));
         CK(cudaEventCreate(&c->ev1));
         CK(cudaEventCreate(&c->ev2));
@@ -1798,6 +1955,7 @@ void eh_destroy(eh_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    if (c->copy_stream2) cudaStreamSynchronize(c->copy_stream2);
     if (c->stream) cudaStreamSynchronize(c->stream);
     delete c->wide;
     c->wide = nullptr;
@@ -1810,6 +1968,16 @@ void eh_destroy(eh_ctx* c)
                     c->d_bn_test, c->d_prog, c->split[0].rec, c->split[1].rec};
     for (void* p : ptrs)
         if (p) cudaFree(p);
+    {
+        HostRing& r = c->ring;
+        void* rp[] = {r.d_rec, r.d_bscal, r.d_cnt};
+        for (void* p : rp)
+            if (p) cudaFree(p);
+        for (cudaEvent_t e : r.packed)
+            if (e) cudaEventDestroy(e);
+        for (cudaEvent_t e : r.freed)
+            if (e) cudaEventDestroy(e);
+    }
     for (HostStage& h : c->hs) {
         void* hp[] = {h.d_X, h.d_planes, h.d_rec, h.d_cnt, h.d_bscal, h.d_loss};
         for (void* p : hp)
@@ -1828,6 +1996,7 @@ void eh_destroy(eh_ctx* c)
     if (c->d_snap) cudaFree(c->d_snap);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->copy_stream2) cudaStreamDestroy(c->copy_stream2);
     delete c;
 }
 
@@ -1841,7 +2010,7 @@ eh_status eh_upload(eh_ctx* c, int32_t split, int64_t N, const float* X, const f
     if (!c) return EH_EINVAL;
     if (split < 0 || split > 1 || N < 0 || (N > 0 && (!X || !targ))) return fail(c, EH_EINVAL, "bad eh_upload arguments");
     if (N > 0x7fffffffLL) return fail(c, EH_EUNSUPPORTED, "split larger than 2^31-1 samples");
-    CK(cudaSetDevice(c->device));
+    EH_ENTER(c);
     Split& sp = c->split[split];
     if (sp.rec) { cudaFree(sp.rec); sp.rec = nullptr; }
     sp.N = N;
@@ -1891,7 +2060,7 @@ eh_status eh_set_params(eh_ctx* c, const float* flat, int64_t n)
 {
     if (!c) return EH_EINVAL;
     if (!flat || n != c->nflat) return fail(c, EH_EINVAL, "eh_set_params: expected %d entries, got %lld", c->nflat, (long long)n);
-    CK(cudaSetDevice(c->device));
+    EH_ENTER(c);
     CK(cudaMemcpyAsync(c->d_theta, flat, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     CK(refresh_tail(c));
     if (c->wide && c->wide->refresh_images(c->d_theta, c->d_m, c->d_v, c->d_ost, c->stream) != cudaSuccess)
@@ -1904,7 +2073,7 @@ eh_status eh_get_params(eh_ctx* c, float* flat, int64_t n)
 {
     if (!c) return EH_EINVAL;
     if (!flat || n != c->nflat) return fail(c, EH_EINVAL, "eh_get_params: expected %d entries, got %lld", c->nflat, (long long)n);
-    CK(cudaSetDevice(c->device));
+    EH_ENTER(c);
     CK(cudaMemcpyAsync(flat, c->d_theta, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return EH_OK;
@@ -1914,7 +2083,7 @@ eh_status eh_set_opt_state(eh_ctx* c, const float* m, const float* v, int64_t n,
 {
     if (!c) return EH_EINVAL;
     if (n != c->nflat || t < 0) return fail(c, EH_EINVAL, "eh_set_opt_state: bad size or step count");
-    CK(cudaSetDevice(c->device));
+    EH_ENTER(c);
     eh_status s = reset_opt_state(c);
     if (s != EH_OK) return s;
     if (m) CK(cudaMemcpy(c->d_m, m, (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
@@ -1930,7 +2099,7 @@ eh_status eh_get_opt_state(eh_ctx* c, float* m, float* v, int64_t n, int64_t* t)
 {
     if (!c) return EH_EINVAL;
     if (n != c->nflat) return fail(c, EH_EINVAL, "eh_get_opt_state: bad size");
-    CK(cudaSetDevice(c->device));
+    EH_ENTER(c);
     CK(cudaStreamSynchronize(c->stream));
     if (m) CK(cudaMemcpy(m, c->d_m, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
     if (v) CK(cudaMemcpy(v, c->d_v, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
@@ -1962,7 +2131,7 @@ static eh_status step_on_indices(eh_ctx* c, const int64_t* idx1, int64_t B, floa
 {
     if (!c) return EH_EINVAL;
     if (!idx1 || B <= 0) return fail(c, EH_EINVAL, "empty batch");
-    CK(cudaSetDevice(c->device));
+    EH_ENTER(c);
     const Split& sp = c->split[EH_SPLIT_TRAIN];
     if (!sp.rec) return fail(c, EH_EINVAL, "train split not uploaded");
     eh_status s = upload_indices(c, idx1, B, sp.N);
@@ -1991,7 +2160,7 @@ eh_status eh_set_perm(eh_ctx* c, const int64_t* perm1, int64_t n)
 {
     if (!c) return EH_EINVAL;
     if (!perm1 || n <= 0) return fail(c, EH_EINVAL, "empty permutation");
-    CK(cudaSetDevice(c->device));
+    EH_ENTER(c);
     const Split& sp = c->split[EH_SPLIT_TRAIN];
     if (!sp.rec) return fail(c, EH_EINVAL, "train split not uploaded");
     eh_status s = upload_indices(c, perm1, n, sp.N);
@@ -2006,7 +2175,7 @@ eh_status eh_run_steps(eh_ctx* c, int64_t B, int64_t first_step, int64_t n_steps
     if (!c) return EH_EINVAL;
     if (c->perm_n <= 0) return fail(c, EH_EINVAL, "no resident permutation (call eh_set_perm)");
     if (B <= 0) return fail(c, EH_EINVAL, "batch size must be positive");
-    CK(cudaSetDevice(c->device));
+    EH_ENTER(c);
     if (c->perm_B != B) {
         eh_status s = prepare_batch_rows(c, c->perm_n, B);
         if (s != EH_OK) return s;
@@ -2020,7 +2189,7 @@ eh_status eh_epoch(eh_ctx* c, const int64_t* perm1, int64_t n, int64_t B, float*
     if (!c) return EH_EINVAL;
     if (!perm1 || n <= 0) return fail(c, EH_EINVAL, "empty permutation");
     if (B <= 0) return fail(c, EH_EINVAL, "batch size must be positive");
-    CK(cudaSetDevice(c->device));
+    EH_ENTER(c);
     bool piped = false;
     eh_status ps = epoch_pipelined(c, perm1, n, B, losses, &piped);
     if (ps != EH_OK || piped) return ps;
@@ -2035,7 +2204,7 @@ eh_status eh_step_host(eh_ctx* c, int64_t B, const float* X, const float* const*
 {
     if (!c) return EH_EINVAL;
     if (B <= 0 || !X || !targ) return fail(c, EH_EINVAL, "bad eh_step_host arguments");
-    CK(cudaSetDevice(c->device));
+    EH_ENTER(c);
     HostStage& h = c->hs[0];
     eh_status s = ensure_host_stage(c, h, B);
     if (s != EH_OK) return s;
@@ -2053,7 +2222,7 @@ eh_status eh_step_host_async(eh_ctx* c, int64_t B, const float* X, const float* 
 {
     if (!c) return EH_EINVAL;
     if (B <= 0 || !X || !targ) return fail(c, EH_EINVAL, "bad eh_step_host_async arguments");
-    CK(cudaSetDevice(c->device));
+    CK(cudaSetDevice(c->device));   // (no flush: this call adds to the open group)
     if (c->async_used == c->async_cap) {
         if (c->async_used) {
             eh_status s = eh_sync(c);
@@ -2064,12 +2233,26 @@ eh_status eh_step_host_async(eh_ctx* c, int64_t B, const float* X, const float* 
             CK(cudaMallocHost((void**)&c->h_async_loss, c->async_cap * sizeof(float)));
         }
     }
+    {
+        // grouped form: the batch is packed now, its step runs with the group's persistent launch
+        bool taken = false;
+        eh_status rs = ring_enqueue(c, B, X, forc, targ, c->h_async_loss + c->async_used, &taken);
+        if (rs != EH_OK) return rs;
+        if (taken) {
+            c->pending_loss.emplace_back(c->h_async_loss + c->async_used, loss_slot);
+            c->async_used++;
+            return EH_OK;
+        }
+        rs = flush_host_group(c);   // keep the order of the steps
+        if (rs != EH_OK) return rs;
+    }
     HostStage& h = c->hs[c->hs_next];
     c->hs_next = (c->hs_next + 1) % EH_HOST_SLOTS;
     if (B > h.cap && h.used) {
         // growing a slot frees its buffers: nothing may still be reading them
         CK(cudaStreamSynchronize(c->stream));
         CK(cudaStreamSynchronize(c->copy_stream));
+        CK(cudaStreamSynchronize(c->copy_stream2));
     }
     eh_status s = ensure_host_stage(c, h, B);
     if (s != EH_OK) return s;
@@ -2085,7 +2268,7 @@ eh_status eh_step_host_async(eh_ctx* c, int64_t B, const float* X, const float* 
 eh_status eh_sync(eh_ctx* c)
 {
     if (!c) return EH_EINVAL;
-    CK(cudaSetDevice(c->device));
+    EH_ENTER(c);
     unsigned herr = 0;
     CK(cudaMemcpyAsync(&herr, c->d_dperr, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
@@ -2104,7 +2287,7 @@ eh_status eh_eval(eh_ctx* c, int32_t split, float* yhat, double* stats, float* n
 {
     if (!c) return EH_EINVAL;
     if (split < 0 || split > 1) return fail(c, EH_EINVAL, "bad split");
-    CK(cudaSetDevice(c->device));
+    EH_ENTER(c);
     const Split& sp = c->split[split];
     if (!sp.rec) return fail(c, EH_EINVAL, "split %d not uploaded", split);
     const Variant* v = c->var;
@@ -2211,7 +2394,7 @@ eh_status eh_comm_id(eh_ctx* c, void* id_out)
 {
     if (!c) return EH_EINVAL;
     if (!id_out) return fail(c, EH_EINVAL, "null id_out");
-    CK(cudaSetDevice(c->device));
+    EH_ENTER(c);
     if (!c->dp_block) {
         const size_t bytes = c->wide ? c->wide->dp_block_bytes()                                            // [2][xlen] floats + flags
                                      : (size_t)2 * EH_MAX_WORLD * rup4(c->var->NPART) * sizeof(uint2);  // {value, tag} slots
@@ -2233,7 +2416,7 @@ eh_status eh_comm_init(eh_ctx* c, int32_t rank, int32_t world, const void* ids)
         return fail(c, EH_EINVAL, "eh_comm_init: world must be 1..%d and 0 <= rank < world", EH_MAX_WORLD);
     if (!c->dp_block) return fail(c, EH_EINVAL, "eh_comm_init: call eh_comm_id on this ctx first");
     if (!c->persist_ok && !c->wide) return fail(c, EH_EUNSUPPORTED, "data-parallel mode needs the persistent kernel, unavailable for this model");
-    CK(cudaSetDevice(c->device));
+    EH_ENTER(c);
     for (int r = 0; r < world; r++) {
         if (r == rank) { c->dp_peer[r] = c->dp_block; continue; }
         cudaIpcMemHandle_t h;
@@ -2268,7 +2451,7 @@ eh_status eh_dp_batch_moments(eh_ctx* c, int64_t B, double* out)
     if (!c) return EH_EINVAL;
     if (!out || B <= 0) return fail(c, EH_EINVAL, "bad eh_dp_batch_moments arguments");
     if (c->perm_n <= 0) return fail(c, EH_EINVAL, "no resident permutation (call eh_set_perm)");
-    CK(cudaSetDevice(c->device));
+    EH_ENTER(c);
     const int64_t n = c->perm_n, nb = (n + B - 1) / B;
     eh_status s = ensure_bscal_cap(c, (size_t)nb);
     if (s != EH_OK) return s;
@@ -2291,7 +2474,7 @@ eh_status eh_dp_set_batch_moments(eh_ctx* c, int64_t B, const double* global)
     if (!c) return EH_EINVAL;
     if (!global || B <= 0) return fail(c, EH_EINVAL, "bad eh_dp_set_batch_moments arguments");
     if (c->perm_n <= 0) return fail(c, EH_EINVAL, "no resident permutation (call eh_set_perm)");
-    CK(cudaSetDevice(c->device));
+    EH_ENTER(c);
     const int64_t n = c->perm_n, nb = (n + B - 1) / B;
     eh_status s = ensure_bscal_cap(c, (size_t)nb);
     if (s != EH_OK) return s;

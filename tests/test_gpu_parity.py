@@ -214,13 +214,14 @@ def test_persistent_kernel_matches_step_kernels(eh, orc):
     assert np.array_equal(out[4][0], out[5][0]) and np.array_equal(out[4][1], out[7][1])
 
 
-@pytest.mark.parametrize("B", [8192, 1000])
-def test_step_host_async_stream_equals_epoch(eh, orc, B):
+@pytest.mark.parametrize("B,nb", [(8192, 19), (1000, 19), (2048, 53)])
+def test_step_host_async_stream_equals_epoch(eh, orc, B, nb):
     """streaming host batches (collect_dim_data |> gdev per step, src/training/epoch.jl:1-11) == the resident path
-    on the same batches: per-step losses and trained parameters; NaN targets exercise the per-batch counts"""
-    nb = 19
+    on the same batches: per-step losses and trained parameters; NaN targets exercise the per-batch counts.
+    53 batches: more than three groups of 16, i.e. the staging ring wraps around"""
     model, xf, y, flat, sess, o, rng = _setup(eh, orc, lambda e: rbq10_model(e), lambda: make_synth(nb * B + 77, nan_frac=0.03), "mse", "sum")
-    n = xf[0].shape[0]
+    n = xf[0].shape[0]   # (rows whose only target is NaN were dropped by prepare_data: the last batch is ragged)
+    nb = (min(n, nb * B) + B - 1) // B
     perm = rng.permutation(n)[: nb * B]
     want = sess.epoch(perm, B)
     p_want = sess.get_params()
@@ -257,7 +258,10 @@ def test_zero_copy_host_batches_equal_copy_engine_path(eh, orc, monkeypatch, nam
     sizes = [4096, 1000, 33, 2048, 5]
     n = sum(sizes)
     results = []
-    for nozc in ("0", "1"):
+    # 0: default (zero copy; batches without per-batch data statistics are grouped into persistent launches),
+    # 1: zero copy, one step / update launch pair per batch, 2: copy engine, one launch pair per batch
+    for nogroups, nozc in (("0", "0"), ("1", "0"), ("1", "1")):
+        monkeypatch.setenv("EH_HOST_NO_GROUPS", nogroups)
         monkeypatch.setenv("EH_HOST_NO_ZEROCOPY", nozc)
         # (prepare_data drops rows without any valid target: generate more than needed)
         model, xf, y, flat, sess, o, rng = _setup(eh, orc, mk, lambda: mkdata(n + n // 4), loss, "sum")
@@ -274,9 +278,11 @@ def test_zero_copy_host_batches_equal_copy_engine_path(eh, orc, monkeypatch, nam
         sess.sync()
         results.append((np.array(losses), sess.get_params()))
         sess.close()
-    assert np.array_equal(results[0][0], results[1][0])
-    assert np.array_equal(results[0][1], results[1][1])
+    assert np.array_equal(results[1][0], results[2][0])
+    assert np.array_equal(results[1][1], results[2][1])
     assert np.isfinite(results[0][0]).all()
+    # the persistent kernel sums in another order than the step / update pair: same losses to rounding
+    np.testing.assert_allclose(results[0][0], results[2][0], rtol=1e-5)
 
 
 def test_unsupported_models_fail_loudly(eh):
@@ -284,14 +290,23 @@ def test_unsupported_models_fail_loudly(eh):
 
     def other(*, ta, Q10, rb):
         return {"reco": rb * np.exp(Q10) + ta}
-    # a traced (non built-in) process model runs on the tensor-core path, which has no swish
+    # chains wider than 32 run on the tensor-core path, which has no swish
     m = eh.constructHybridModel(["sw_pot"], ["ta"], ["reco"], other, dict(Q10=(2, 1, 4), rb=(3, 0, 13)), ["rb"], ["Q10"],
-                                activation="swish")
+                                hidden_layers=[64, 64], activation="swish")
     with pytest.raises(eh.EasyHybridCudaError) as ei:
         eh.FusedSession(m)
     assert ei.value.status == _abi.EH_EUNSUPPORTED
-    m = eh.constructHybridModel(["sw_pot"], ["ta"], ["reco"], other, dict(Q10=(2, 1, 4), rb=(3, 0, 13)), ["rb"], ["Q10"])
-    eh.FusedSession(m).close()
+    # the same traced model on a narrow chain: generic exact-fp32 variant, any activation
+    m = eh.constructHybridModel(["sw_pot"], ["ta"], ["reco"], other, dict(Q10=(2, 1, 4), rb=(3, 0, 13)), ["rb"], ["Q10"],
+                                activation="swish")
+    sess = eh.FusedSession(m)
+    assert sess.kernel_variant().startswith("ffma2/PmProgram/"), sess.kernel_variant()
+    sess.close()
+    m = eh.constructHybridModel(["sw_pot"], ["ta"], ["reco"], other, dict(Q10=(2, 1, 4), rb=(3, 0, 13)), ["rb"], ["Q10"],
+                                hidden_layers=[64, 64])
+    sess = eh.FusedSession(m)
+    assert sess.kernel_variant().startswith("wide/"), sess.kernel_variant()
+    sess.close()
     with pytest.raises(eh.EasyHybridCudaError) as ei:
         eh.FusedSession(rbq10_model(eh, hidden=(600, 600)))   # wider than the tensor-core path takes
     assert ei.value.status == _abi.EH_EUNSUPPORTED
