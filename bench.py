@@ -318,7 +318,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         e2e = {"value": world * ke * B / dt, "unit": "samples/s", "h2d_bytes_per_step": B * BYTES_PER_SAMPLE,
-               "d2h_bytes_per_step": 4, "steps": ke, "api": "eh_step_host_async + eh_sync (page-locked host batches are read in place over PCIe by the packer kernel on two copy streams; every 16 batches one persistent launch runs their 16 optimiser steps; losses land in page-locked host memory)"}
+               "d2h_bytes_per_step": 4, "steps": ke, "api": "eh_step_host_async + eh_sync (page-locked host batches are read in place over PCIe by the packer kernel on four streams; every 16 batches one persistent launch runs their 16 optimiser steps; losses land in page-locked host memory)"}
         # the path train() takes: dataset staged once, every epoch call ships the host permutation (8 B/sample)
         # host->device and the per-step losses back
         kr = min(K, nb)

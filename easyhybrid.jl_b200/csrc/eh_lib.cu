@@ -50,6 +50,10 @@ struct HostStage {  // device staging for eh_step_host*: raw arrays + packed rec
     int64_t cap = 0;
 };
 constexpr int EH_HOST_SLOTS = 4;  // batches in flight between the copy engine and the step kernels
+#ifndef EH_NPACK_STREAMS
+#define EH_NPACK_STREAMS 4
+#endif
+constexpr int EH_NPACK = EH_NPACK_STREAMS;  // host-batch packers / copies in flight (one stream each)
 
 // eh_step_host_async, grouped form: page-locked batches are packed (zero copy) into a ring of staging slots; every
 // EH_RING_GROUP batches ONE persistent launch runs that many optimiser steps over the group's slots, while the packers
@@ -59,7 +63,7 @@ struct HostRing {
     float* d_rec = nullptr;    // [NGRP][GROUP * cap][R4]; slot k of a group starts at record k * B (B = the group's batch size)
     float* d_bscal = nullptr;  // [NGRP * GROUP][BS_STRIDE]
     int* d_cnt = nullptr;      // [NGRP * GROUP][MAXT + 1]
-    cudaEvent_t packed[2] = {nullptr, nullptr};  // last packer of the open group on either copy stream
+    cudaEvent_t packed[EH_NPACK] = {};  // last packer of the open group on each pack stream
     cudaEvent_t freed[EH_RING_NGRP] = {nullptr, nullptr, nullptr};
     bool used[EH_RING_NGRP] = {false, false, false};
     int64_t cap = 0;           // samples per slot
@@ -76,7 +80,8 @@ struct eh_ctx {
     int device = 0;
     int nsm = 0;
     size_t smem_optin = 0;
-    cudaStream_t stream = nullptr, copy_stream = nullptr, copy_stream2 = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t pack_stream[EH_NPACK] = {};   // packers of consecutive host batches rotate over these ([0] == copy_stream)
     const Variant* var = nullptr;   // engine chosen at eh_create (FFMA2 one sample per lane, or tensor pipe)
     const Variant* var2 = nullptr;  // FFMA2 two samples per lane: same layouts, used for large batches
     // wide-hidden-layer path (bf16 tcgen05 GEMMs, eh_wide.cu): `var` then points at `wide_var`, a descriptor
@@ -258,9 +263,10 @@ __global__ void __launch_bounds__(256) k_pack_count(const PackArgs a, int T, int
 
 // Zero-copy packer of the host-batch path: the caller's page-locked arrays are read straight over PCIe
 // (UVA device pointers of pinned host memory) and leave as packed records in HBM -- one launch on the copy
-// stream replaces the three cudaMemcpyAsync + the packer + the per-batch-scalar kernel.  Packers alternate
-// between two copy streams (the ramp-up / drain of one overlaps the other: 37 -> 44 GB/s measured; a large
-// cudaMemcpy reaches 55 GB/s on the same box, 1 MiB ones 33 GB/s) and together are kept to EH_PACK_HOST_CTAS
+// stream replaces the three cudaMemcpyAsync + the packer + the per-batch-scalar kernel.  Packers rotate
+// over EH_NPACK streams (the ramp-up / drain of one overlaps the others: 37 GB/s with one stream, 44 with two,
+// 49 with four, measured on 1 MiB batches; a 256 MiB cudaMemcpy reaches 55 GB/s on the same box, 1 MiB ones
+// 33 GB/s) and together are kept to EH_PACK_HOST_CTAS
 // big CTAs, so that they only ever occupy that many SMs next to a running step / persistent kernel
 // (step_geometry and the 128-CTA persistent grid leave them free); measured insensitive to the grid between
 // 16 x 1024 and 296 x 256 threads.  The last CTA to finish (ticket) turns the valid-target counts into the
@@ -699,8 +705,12 @@ eh_status enqueue_persistent(eh_ctx* c, const float* rec, const int* idx, const 
         if (max_ctas < cs) continue;
         int64_t per_round = (int64_t)max_ctas * wtry;
         int64_t rounds = (nchunks + per_round - 1) / per_round;
-        // fewest warps per CTA that still cover the batch in that many rounds, then the smallest grid that does
-        int w = ew ? wtry : (int)std::min<int64_t>(wtry, (nchunks + rounds * max_ctas - 1) / (rounds * max_ctas));
+        // fewest warps per CTA that still cover the batch in that many rounds -- but not fewer than 8: below that the
+        // per-step exchange and the optimiser (one element per thread and trip) dominate.  Measured (us per step,
+        // tools/geom_sweep.py): B = 512: 24.4 with 1 warp x 16 CTAs vs 8.7 with 8 warps x 4 CTAs; B = 4096: 28.3 vs 9.6;
+        // B = 16384: 13.2 (4 warps) vs 10.0 (8 warps x 64 CTAs); 16 warps only pay when they save a round (B = 65536).
+        // Then the smallest grid that covers the batch.
+        int w = ew ? wtry : (int)std::min<int64_t>(wtry, std::max<int64_t>(8, (nchunks + rounds * max_ctas - 1) / (rounds * max_ctas)));
         int G = (int)std::min<int64_t>(max_ctas, ((nchunks + (int64_t)w * rounds - 1) / ((int64_t)w * rounds) + cs - 1) / cs * cs);
         if (G < cs) G = cs;
         double cost = (double)rounds;  // strict '<' below keeps the preference order among equal round counts
@@ -1595,7 +1605,7 @@ eh_status enqueue_host_step(eh_ctx* c, HostStage& h, int64_t B, const float* X, 
     const Variant* v = c->var;
     // staging slots alternate between two copy streams: the ramp-up / drain of one batch's transfer overlaps the
     // next batch's (a single stream serialises them and leaves the PCIe link idle in between)
-    cudaStream_t cs = ((&h - c->hs) & 1) ? c->copy_stream2 : c->copy_stream;
+    cudaStream_t cs = c->pack_stream[(&h - c->hs) % EH_NPACK];
     bool heavy = c->use_bn;
     for (int t = 0; t < c->n_targ; t++) heavy |= (c->loss_kind[t] == LOSS_NSELOSS);
     // page-locked inputs are read in place by the packer (zero copy); anything else goes through the copy engine
@@ -1617,7 +1627,7 @@ eh_status enqueue_host_step(eh_ctx* c, HostStage& h, int64_t B, const float* X, 
                    c->src_idx[1] == 1 && ((uintptr_t)z.X & 7) == 0;
         z.rec = h.d_rec; z.T = c->n_targ; z.ycol0 = v->P + v->F; z.agg_mean = c->agg_mean;
         z.cnt = h.d_cnt; z.bscal = heavy ? nullptr : h.d_bscal;
-        const int ctas = (int)std::min<int64_t>(EH_PACK_HOST_CTAS / 2, (B + 1023) / 1024);   // two packers may be in flight
+        const int ctas = (int)std::min<int64_t>(EH_PACK_HOST_CTAS / EH_NPACK, (B + 1023) / 1024);   // EH_NPACK packers may be in flight
         k_pack_host<<<ctas, 1024, 0, cs>>>(z);
         CK(cudaGetLastError());
         CK(cudaEventRecord(h.ready, cs));
@@ -1720,8 +1730,7 @@ eh_status ensure_ring(eh_ctx* c, int64_t B)
     if (B <= r.cap) return EH_OK;
     // growing frees the buffers: nothing may still be reading or writing them (the open group is empty here)
     CK(cudaStreamSynchronize(c->stream));
-    CK(cudaStreamSynchronize(c->copy_stream));
-    CK(cudaStreamSynchronize(c->copy_stream2));
+    for (int i = 0; i < EH_NPACK; i++) CK(cudaStreamSynchronize(c->pack_stream[i]));
     if (r.d_rec) cudaFree(r.d_rec);
     r.d_rec = nullptr; r.cap = 0;
     const int64_t cap = std::max<int64_t>(B, 4096);
@@ -1732,7 +1741,7 @@ eh_status ensure_ring(eh_ctx* c, int64_t B)
         CK(dalloc(&r.d_cnt, (size_t)nslots * (MAXT + 1)));
         CK(cudaMemsetAsync(r.d_cnt, 0, (size_t)nslots * (MAXT + 1) * sizeof(int), c->stream));
         CK(cudaStreamSynchronize(c->stream));
-        for (int i = 0; i < 2; i++) CK(cudaEventCreateWithFlags(&r.packed[i], cudaEventDisableTiming));
+        for (int i = 0; i < EH_NPACK; i++) CK(cudaEventCreateWithFlags(&r.packed[i], cudaEventDisableTiming));
         for (int i = 0; i < EH_RING_NGRP; i++) CK(cudaEventCreateWithFlags(&r.freed[i], cudaEventDisableTiming));
     }
     for (int i = 0; i < EH_RING_NGRP; i++) r.used[i] = false;
@@ -1750,11 +1759,9 @@ eh_status flush_host_group(eh_ctx* c)
     const int64_t B = r.B;
     r.k = 0;
     r.g = (g + 1) % EH_RING_NGRP;
-    CK(cudaEventRecord(r.packed[0], c->copy_stream));
-    CK(cudaStreamWaitEvent(c->stream, r.packed[0], 0));
-    if (k > 1) {
-        CK(cudaEventRecord(r.packed[1], c->copy_stream2));
-        CK(cudaStreamWaitEvent(c->stream, r.packed[1], 0));
+    for (int i = 0; i < EH_NPACK && i < k; i++) {
+        CK(cudaEventRecord(r.packed[i], c->pack_stream[i]));
+        CK(cudaStreamWaitEvent(c->stream, r.packed[i], 0));
     }
     const float* rec = r.d_rec + (size_t)g * EH_RING_GROUP * r.cap * v->R4;
     const float* bscal = r.d_bscal + (size_t)g * EH_RING_GROUP * BS_STRIDE;
@@ -1812,8 +1819,7 @@ eh_status ring_enqueue(eh_ctx* c, int64_t B, const float* X, const float* const*
         r.B = B;
         r.loss0 = pin;
         if (r.used[g]) {   // the launch that last trained on this group's slots must have retired
-            CK(cudaStreamWaitEvent(c->copy_stream, r.freed[g], 0));
-            CK(cudaStreamWaitEvent(c->copy_stream2, r.freed[g], 0));
+            for (int i = 0; i < EH_NPACK; i++) CK(cudaStreamWaitEvent(c->pack_stream[i], r.freed[g], 0));
         }
     }
     const int slot = g * EH_RING_GROUP + k;
@@ -1825,9 +1831,9 @@ eh_status ring_enqueue(eh_ctx* c, int64_t B, const float* X, const float* const*
     z.T = c->n_targ; z.ycol0 = v->P + v->F; z.agg_mean = c->agg_mean;
     z.cnt = r.d_cnt + (size_t)slot * (MAXT + 1);
     z.bscal = r.d_bscal + (size_t)slot * BS_STRIDE;
-    // two packers may be in flight (one per copy stream): half the reserved SMs each
-    const int ctas = (int)std::min<int64_t>(EH_PACK_HOST_CTAS / 2, (B + 1023) / 1024);
-    k_pack_host<<<ctas, 1024, 0, (k & 1) ? c->copy_stream2 : c->copy_stream>>>(z);
+    // EH_NPACK packers may be in flight (one per pack stream): they share the reserved SMs
+    const int ctas = (int)std::min<int64_t>(EH_PACK_HOST_CTAS / EH_NPACK, (B + 1023) / 1024);
+    k_pack_host<<<ctas, 1024, 0, c->pack_stream[k % EH_NPACK]>>>(z);
     CK(cudaGetLastError());
     r.k = k + 1;
     *taken = true;
@@ -1886,7 +1892,8 @@ eh_status eh_create(eh_ctx** out, const eh_model_desc* desc)
     auto cuda_setup = [&]() -> eh_status {
         CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-        CK(cudaStreamCreateWithFlags(&c->copy_stream2, cudaStreamNonBlocking));
+        c->pack_stream[0] = c->copy_stream;
+        for (int i = 1; i < EH_NPACK; i++) CK(cudaStreamCreateWithFlags(&c->pack_stream[i], cudaStreamNonBlocking));
         if (const char* e = getenv("EH_HOST_NO_ZEROCOPY")) c->host_zero_copy = !(e[0] && e[0] != '0');
         if (const char* e = getenv("EH_HOST_NO_GROUPS")) c->ring.off = e[0] && e[0] != '0';
         CK(cudaEventCreate(&c->ev0));
@@ -1955,7 +1962,8 @@ void eh_destroy(eh_ctx* c)
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
-    if (c->copy_stream2) cudaStreamSynchronize(c->copy_stream2);
+    for (int i = 1; i < EH_NPACK; i++)
+        if (c->pack_stream[i]) cudaStreamSynchronize(c->pack_stream[i]);
     if (c->stream) cudaStreamSynchronize(c->stream);
     delete c->wide;
     c->wide = nullptr;
@@ -1996,7 +2004,8 @@ void eh_destroy(eh_ctx* c)
     if (c->d_snap) cudaFree(c->d_snap);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
-    if (c->copy_stream2) cudaStreamDestroy(c->copy_stream2);
+    for (int i = 1; i < EH_NPACK; i++)
+        if (c->pack_stream[i]) cudaStreamDestroy(c->pack_stream[i]);
     delete c;
 }
 
@@ -2251,8 +2260,7 @@ eh_status eh_step_host_async(eh_ctx* c, int64_t B, const float* X, const float* 
     if (B > h.cap && h.used) {
         // growing a slot frees its buffers: nothing may still be reading them
         CK(cudaStreamSynchronize(c->stream));
-        CK(cudaStreamSynchronize(c->copy_stream));
-        CK(cudaStreamSynchronize(c->copy_stream2));
+        for (int i = 0; i < EH_NPACK; i++) CK(cudaStreamSynchronize(c->pack_stream[i]));
     }
     eh_status s = ensure_host_stage(c, h, B);
     if (s != EH_OK) return s;

@@ -6,7 +6,7 @@ import easyhybrid_b200 as eh
 from bench import make_model, synth
 
 model = make_model(eh)
-for B in (65536, 16384):
+for B in (65536, 16384, 4096):
     n = 16 * B
     xf, y = synth(n, 1)
     sess = eh.FusedSession(model, opt=eh.Adam(0.01), device=0)
