@@ -270,8 +270,8 @@ def main():
     per_gpu_sps = K * B / (dev_ms * 1e-3)
     achieved = per_gpu_sps * BYTES_PER_SAMPLE / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                # dram__bytes_read+write of k_epoch from ncu --set full (profiles/r1_k_epoch_v5_ncu_details.txt):
-                # 57.8 + 0.85 MB for a 12-step launch = 4.89 MB per step, scaled to this launch's K steps
+                # dram__bytes_read+write of k_epoch from ncu --set full (profiles/r1_k_epoch_v6_ncu_details.txt; same in v5):
+                # 57.8 + 1.08 MB for a 12-step launch = 4.9 MB per step, scaled to this launch's K steps
                 "traffic": 4.89e6 * K, "traffic_algorithmic": float(K) * B * BYTES_PER_SAMPLE,
                 "peak_source": peak_src,
                 "kernel": "k_epoch (persistent: fused fwd+process+loss+bwd, grid exchange, Adam; one launch = K steps)",

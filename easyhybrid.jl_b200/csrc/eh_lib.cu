@@ -282,6 +282,8 @@ struct PackHostArgs {
     int src_kind[24], src_idx[24];
     float* rec;                             // [N][R4] device
     int T, ycol0, agg_mean;
+    int world;                              // data parallel: the scalar row describes the GLOBAL batch of world * N rows
+                                            // (NaN-free targets are a precondition of host batches in that mode)
     int* cnt;                               // [MAXT + 1] valid-target counters + ticket (all zero between launches)
     float* bscal;                           // per-batch scalar row to fill (NULL: K0 computes it from the records)
 };
@@ -357,7 +359,8 @@ __global__ void __launch_bounds__(1024) k_pack_host(const PackHostArgs a)
     if (threadIdx.x < MAXT) {
         const int t = threadIdx.x;
         const float aggw = a.agg_mean ? 1.f / (float)a.T : 1.f;
-        const float n = t < a.T ? (float)atomicExch(&a.cnt[t], 0) : 0.f;   // read and re-arm for the next launch
+        float n = t < a.T ? (float)atomicExch(&a.cnt[t], 0) : 0.f;   // read and re-arm for the next launch
+        if (a.world > 1 && t < a.T) n = (float)a.N * (float)a.world;
         a.bscal[BS_C + t] = t < a.T ? aggw / n : 0.f;
         a.bscal[BS_N + t] = n;
         a.bscal[BS_SS + t] = 0.f;
@@ -1768,6 +1771,8 @@ eh_status flush_host_group(eh_ctx* c)
     bool used = false;
     eh_status s = enqueue_persistent(c, rec, nullptr, bscal, r.loss0, (int64_t)k * B, B, 0, k, &used, nullptr);
     if (s != EH_OK) return s;
+    if (!used && c->world > 1)
+        return fail(c, EH_EUNSUPPORTED, "persistent kernel unavailable for this shape (data-parallel host batches need it): %s", c->err.c_str());
     if (!used) {
         for (int i = 0; i < k; i++) {
             StepArgs a;
@@ -1796,7 +1801,7 @@ eh_status ring_enqueue(eh_ctx* c, int64_t B, const float* X, const float* const*
     const Variant* v = c->var;
     bool heavy = c->use_bn;
     for (int t = 0; t < c->n_targ; t++) heavy |= (c->loss_kind[t] == LOSS_NSELOSS);
-    if (r.off || !c->host_zero_copy || c->wide || c->world > 1 || heavy || !c->persist_ok || c->profiling ||
+    if (r.off || !c->host_zero_copy || c->wide || heavy || !c->persist_ok || c->profiling ||
         (c->flags & EH_FLAG_NO_PERSIST) || c->n_forc_raw + c->n_targ > EH_PACK_MAXPLANES)
         return EH_OK;
     PackHostArgs z;
@@ -1828,7 +1833,7 @@ eh_status ring_enqueue(eh_ctx* c, int64_t B, const float* X, const float* const*
     z.x_pair = c->n_pred_raw == 2 && c->ncols >= 2 && c->src_kind[0] == 0 && c->src_idx[0] == 0 && c->src_kind[1] == 0 &&
                c->src_idx[1] == 1 && ((uintptr_t)z.X & 7) == 0;
     z.rec = r.d_rec + ((size_t)g * EH_RING_GROUP * r.cap + (size_t)k * B) * v->R4;
-    z.T = c->n_targ; z.ycol0 = v->P + v->F; z.agg_mean = c->agg_mean;
+    z.T = c->n_targ; z.ycol0 = v->P + v->F; z.agg_mean = c->agg_mean; z.world = c->world;
     z.cnt = r.d_cnt + (size_t)slot * (MAXT + 1);
     z.bscal = r.d_bscal + (size_t)slot * BS_STRIDE;
     // EH_NPACK packers may be in flight (one per pack stream): they share the reserved SMs

@@ -140,6 +140,9 @@ function dp_exchange_batch_stats!(s::Session, n::Integer, batchsize::Integer, al
     return nothing
 end
 
+"Name of the compiled kernel family that serves this model (specialised fp32, generic fp32, or bf16 tensor-core path)."
+kernel_variant(s::Session) = unsafe_string(ccall((:eh_kernel_variant, LIB), Cstring, (Ptr{Cvoid},), s.ctx))
+
 function evaluate(s::Session, split::Integer, N::Integer, T::Integer)
     yhat = Matrix{Float32}(undef, N, T); stats = Matrix{Float64}(undef, 9, T)
     check(s.ctx, ccall((:eh_eval, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Float32}, Ptr{Float64}, Ptr{Float32}),

@@ -87,6 +87,29 @@ def main():
             np.testing.assert_allclose(losses, np.array(want), rtol=2e-4)
             assert abs(float(ps[-1]) - float(ref[-1])) <= 1e-4, (ps[-1], ref[-1])
             print("DP_NCCL_OK", losses[:3], want[:3])
+        if not os.environ.get("EH_DP_DEBUG"):
+            # the same steps streamed as page-locked HOST batches (collect_dim_data |> gdev per step): packed in place
+            # over PCIe, trained in grouped persistent launches, exchange fused as above
+            sess.set_params(flat0)
+            sess.set_opt_state(None, None, 0)
+            dist.barrier()
+            nbl = n_local // B
+            hl = sess.pinned(np.zeros(steps, dtype=np.float32))
+            keep = []
+            for s in range(steps):
+                idx = perms[rank][(s % nbl) * B:(s % nbl + 1) * B]
+                hb = sess.host_batch(sess.pinned(xf[0][idx]), [sess.pinned(xf[1]["ta"][idx])], [sess.pinned(y["reco"][idx])])
+                keep.append(hb)
+                sess.step_host_async(hb, hl, s)
+            sess.sync()
+            np.testing.assert_allclose(np.asarray(hl), losses, rtol=2e-6)
+            ps_h = sess.get_params()
+            np.testing.assert_allclose(ps_h, ps, rtol=0, atol=2e-6)
+            allh = [None] * world
+            dist.all_gather_object(allh, ps_h.tobytes())
+            if rank == 0:
+                assert all(b == allh[0] for b in allh), "replicas diverged (host batches)"
+                print("DP_NCCL_HOST_OK")
         sess.close()
         # ---- second scenario: NaN targets + input BatchNorm + nseLoss: per-batch statistics of the GLOBAL batch ----
         if not os.environ.get("EH_DP_DEBUG"):
