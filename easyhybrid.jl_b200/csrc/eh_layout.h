@@ -85,5 +85,7 @@ constexpr int PARAM_TAIL = MAXPS + MAXPS * PMS_PER_SLOT_L;
 // statistics appended after the dW blocks in a partial vector:
 //   [T] sum of r^2 (or |r| for mae targets), [MAXPS] sum of g*dy/dslot for GLOBAL slots
 constexpr int NSTAT = MAXT + MAXPS;
+// longest partial vector k_update reduces in its shared memory (checked per variant at compile time and by the planner)
+constexpr int UPD_MAX_NPART = 4096;
 
 }  // namespace eh

@@ -1349,7 +1349,16 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
     // tcgen05 GEMM path.
     const bool wide = false;   // (this function continues with the register-tile plan only)
     const int scale_flag = d->scale_nn_outputs ? 1 : 0;
-    const bool small_shape = d->n_chains == 1 && hmax <= 32;
+    // (the register-tile kernels keep theta / m / v in shared memory and update them in one CTA: <= 2048 - NSTAT entries)
+    long long nflat_est = 0;
+    {
+        int prev = ch.n_in;
+        for (int l = 0; l < ch.n_hidden; l++) { nflat_est += (long long)(prev + 1) * ch.hidden[l]; prev = ch.hidden[l]; }
+        nflat_est += (long long)(prev + 1) * ch.n_out;
+        for (int p = 0; p < d->n_params; p++)
+            if (d->role[p] == EH_ROLE_GLOBAL) nflat_est++;
+    }
+    const bool small_shape = d->n_chains == 1 && hmax <= 32 && nflat_est <= 2048 - NSTAT;
     const Variant* v = nullptr;
     // 1. a specialised variant of a built-in form (the BASELINE configurations); engine 1 (tensor pipe, 3xTF32) on
     //    request where one exists, engine 0 (exact-fp32 FFMA2) otherwise
@@ -1368,7 +1377,7 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
     if (!v && small_shape && !getenv("EH_NO_SMALL_PROGRAM") && d->n_params >= 1 && d->n_params <= MAXPS && d->n_forc <= PmProgram::NF &&
         d->n_targ <= PmProgram::NT) {
         const Variant* vp = find_variant(EH_PM_PROGRAM, ch.n_in, ch.n_hidden, rup4(hmax), ch.n_out, ch.activation, 1, 0);
-        if (vp && builtin_as_program(d, is_prog, prog, prog_out)) { v = vp; use_prog = true; }
+        if (vp && vp->NPART <= UPD_MAX_NPART && builtin_as_program(d, is_prog, prog, prog_out)) { v = vp; use_prog = true; }
     }
     if (!v) return build_plan_wide(c, d, is_prog);
     if (!use_prog && v->T != d->n_targ) return fail(c, EH_EINVAL, "process model yields %d targets, descriptor has %d", v->T, d->n_targ);

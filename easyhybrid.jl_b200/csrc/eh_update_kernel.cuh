@@ -71,7 +71,7 @@ __global__ void k_param_tail(const TailArgs a)
 
 __global__ void __launch_bounds__(512, 1) k_update(const UpdateArgs a)
 {
-    __shared__ float red[2048];
+    __shared__ float red[UPD_MAX_NPART];
     __shared__ float s_loss, s_post;
     __shared__ int s_skip;
     pdl_wait();  // K1 of this step must be complete and flushed

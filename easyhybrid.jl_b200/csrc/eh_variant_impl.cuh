@@ -114,6 +114,7 @@ template <class E>
 static Variant make_variant(const char* name)
 {
     using C = typename E::Cfg;
+    static_assert(E::NPART <= UPD_MAX_NPART, "partial vector longer than k_update's shared-memory buffer");
     Variant v{};
     v.pm = C::PM::ID; v.P = C::P; v.NH = C::NH; v.H = C::H; v.NOUT = C::NOUT; v.act = C::ACT; v.scale = C::SCALE ? 1 : 0;
     v.engine = E::ENGINE;

@@ -44,10 +44,10 @@ def m_custom(eh, hidden=(16, 16), activation="tanh", scale=True, bn=False):
                                    hidden_layers=list(hidden), activation=activation, scale_nn_outputs=scale, input_batchnorm=bn)
 
 
-def m_two_neural(eh):
+def m_two_neural(eh, hidden=(16, 16)):
     return eh.constructHybridModel(["sw_pot", "dsw_pot"], ["ta", "dsw_pot"], ["reco"], custom_pm,
                                    dict(rb=(3.0, 0.0, 13.0), Q10=(2.0, 1.0, 4.0), alpha=(0.5, -2.0, 2.0)), ["rb", "Q10"], ["alpha"],
-                                   hidden_layers=[16, 16], activation="sigmoid", scale_nn_outputs=True)
+                                   hidden_layers=list(hidden), activation="sigmoid", scale_nn_outputs=True)
 
 
 def m_two_targets(eh):
@@ -71,6 +71,11 @@ CASES = [
     ("custom-two-neural", m_two_neural, lambda: _table(2000), "mse", "sum"),
     ("custom-two-targets-bn", m_two_targets, lambda: _table(2500, nan_frac=0.1, two=True), "PT", "mean"),
     ("rbq10-relu", lambda eh: rbq10_model(eh, activation="relu"), lambda: make_synth(2000), "rmse", "sum"),
+    # one and three hidden layers (the specialised variants and the tensor-core path start at two)
+    ("rbq10-one-hidden-layer", lambda eh: rbq10_model(eh, hidden=(16,)), lambda: make_synth(2000, nan_frac=0.03), "mse", "sum"),
+    ("rbq10-three-hidden-layers", lambda eh: rbq10_model(eh, hidden=(16, 12, 8), activation="sigmoid"), lambda: make_synth(2000), "mse", "sum"),
+    ("custom-three-hidden-two-neural", lambda eh: m_two_neural(eh, hidden=(32, 24, 20)), lambda: _table(2000), "mse", "sum"),
+    ("custom-one-hidden-32-swish", lambda eh: m_custom(eh, hidden=(24,), activation="swish"), lambda: _table(2000), "mae", "sum"),
     ("rbq10-three-inputs-swish", m_rbq10_three_inputs, lambda: make_synth(2000, nan_frac=0.03), "mse", "sum"),
 ]
 
@@ -108,7 +113,10 @@ def test_generic_variants_loss_and_gradient(eh, orc, name, mk, mkdata, loss, agg
     sess.close()
 
 
-@pytest.mark.parametrize("name,mk,mkdata,loss,agg", [CASES[0], CASES[5], CASES[7]], ids=[CASES[0][0], CASES[5][0], CASES[7][0]])
+TRAIN_CASES = [CASES[0], CASES[5], CASES[7], CASES[8], CASES[9], CASES[11]]
+
+
+@pytest.mark.parametrize("name,mk,mkdata,loss,agg", TRAIN_CASES, ids=[c[0] for c in TRAIN_CASES])
 def test_generic_variants_train_and_eval(eh, orc, name, mk, mkdata, loss, agg):
     """persistent epoch kernel, single steps and the eval kernel on the generic variants against the oracle"""
     model, xf, y, flat, sess, o, rng = _setup(eh, orc, mk, mkdata, loss, agg, opt=eh.Adam(0.01))
