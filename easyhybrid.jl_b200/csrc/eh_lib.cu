@@ -1338,10 +1338,23 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
             if (d->pm_outputs[t] < 0 || d->pm_outputs[t] >= d->pm_len) return fail(c, EH_EINVAL, "pm_outputs[%d] out of range", t);
     }
     const eh_chain_desc& ch = d->chains[0];
-    if (ch.n_in < 1 || ch.n_in > MAXP) return fail(c, EH_EUNSUPPORTED, "chain n_in=%d not in 1..%d", ch.n_in, MAXP);
-    if (ch.n_hidden < 1) return fail(c, EH_EINVAL, "chain needs at least one hidden layer");
+    const int NC = d->n_chains;
+    // several chains (MultiNNHybridModel, GenericHybridModel.jl:169-189, 458-530) are embedded block-diagonally into ONE
+    // chain: chain k owns a range of the inputs, of the units of every hidden layer and of the outputs; weights between
+    // units of different chains do not exist (zero cells of the image that no flat entry feeds).  Totals per level:
+    int Pt = 0, Ot = 0, wsum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    bool uniform = true;
+    for (int k = 0; k < NC; k++) {
+        const eh_chain_desc& ck = d->chains[k];
+        if (ck.n_in < 1) return fail(c, EH_EINVAL, "chain %d has no inputs", k);
+        if (ck.n_hidden < 1) return fail(c, EH_EINVAL, "chain needs at least one hidden layer");
+        if (ck.n_hidden != ch.n_hidden || ck.activation != ch.activation || ck.input_batchnorm != ch.input_batchnorm) uniform = false;
+        Pt += ck.n_in; Ot += ck.n_out;
+        for (int l = 0; l < ck.n_hidden && l < 8; l++) wsum[l] += ck.hidden[l];
+    }
+    if (NC == 1 && ch.n_in > MAXP) return fail(c, EH_EUNSUPPORTED, "chain n_in=%d not in 1..%d", ch.n_in, MAXP);
     int hmax = 0;
-    for (int l = 0; l < ch.n_hidden; l++) hmax = std::max(hmax, ch.hidden[l]);
+    for (int l = 0; l < ch.n_hidden && l < 8; l++) hmax = std::max(hmax, wsum[l]);
     if (!is_prog && (d->n_pm_args != 3 || d->pm_args[0].kind != 0 || d->pm_args[1].kind != 0 || d->pm_args[2].kind != 1))
         return fail(c, EH_EINVAL, "built-in process models take (param, param, forcing) arguments");
     // Which path?  The exact-fp32 register-tile kernels exist for two hidden layers of width <= 32; every other chain
@@ -1351,18 +1364,19 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
     const int scale_flag = d->scale_nn_outputs ? 1 : 0;
     // (the register-tile kernels keep theta / m / v in shared memory and update them in one CTA: <= 2048 - NSTAT entries)
     long long nflat_est = 0;
-    {
-        int prev = ch.n_in;
-        for (int l = 0; l < ch.n_hidden; l++) { nflat_est += (long long)(prev + 1) * ch.hidden[l]; prev = ch.hidden[l]; }
-        nflat_est += (long long)(prev + 1) * ch.n_out;
-        for (int p = 0; p < d->n_params; p++)
-            if (d->role[p] == EH_ROLE_GLOBAL) nflat_est++;
+    for (int k = 0; k < NC; k++) {
+        const eh_chain_desc& ck = d->chains[k];
+        int prev = ck.n_in;
+        for (int l = 0; l < ck.n_hidden; l++) { nflat_est += (long long)(prev + 1) * ck.hidden[l]; prev = ck.hidden[l]; }
+        nflat_est += (long long)(prev + 1) * ck.n_out;
     }
-    const bool small_shape = d->n_chains == 1 && hmax <= 32 && nflat_est <= 2048 - NSTAT;
+    for (int p = 0; p < d->n_params; p++)
+        if (d->role[p] == EH_ROLE_GLOBAL) nflat_est++;
+    const bool small_shape = uniform && ch.n_hidden <= 7 && hmax <= 32 && nflat_est <= 2048 - NSTAT;
     const Variant* v = nullptr;
     // 1. a specialised variant of a built-in form (the BASELINE configurations); engine 1 (tensor pipe, 3xTF32) on
     //    request where one exists, engine 0 (exact-fp32 FFMA2) otherwise
-    if (small_shape && !is_prog) {
+    if (small_shape && !is_prog && NC == 1) {
         if (d->flags & EH_FLAG_TENSOR_PIPE)
             v = find_variant(d->process_model, ch.n_in, ch.n_hidden, rup4(hmax), ch.n_out, ch.activation, scale_flag, 1);
         if (!v) v = find_variant(d->process_model, ch.n_in, ch.n_hidden, rup4(hmax), ch.n_out, ch.activation, scale_flag, 0);
@@ -1376,7 +1390,7 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
     bool use_prog = false;
     if (!v && small_shape && !getenv("EH_NO_SMALL_PROGRAM") && d->n_params >= 1 && d->n_params <= MAXPS && d->n_forc <= PmProgram::NF &&
         d->n_targ <= PmProgram::NT) {
-        const Variant* vp = find_variant(EH_PM_PROGRAM, ch.n_in, ch.n_hidden, rup4(hmax), ch.n_out, ch.activation, 1, 0);
+        const Variant* vp = find_variant(EH_PM_PROGRAM, Pt, ch.n_hidden, rup4(hmax), Ot, ch.activation, 1, 0);
         if (vp && vp->NPART <= UPD_MAX_NPART && builtin_as_program(d, is_prog, prog, prog_out)) { v = vp; use_prog = true; }
     }
     if (!v) return build_plan_wide(c, d, is_prog);
@@ -1397,21 +1411,27 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
     c->var2 = (v->engine == 0) ? find_variant(v->pm, v->P, v->NH, v->H, v->NOUT, v->act, v->scale, 2) : nullptr;
     c->n_pred_raw = d->n_pred; c->n_forc_raw = d->n_forc; c->n_targ = d->n_targ;
     c->use_bn = ch.input_batchnorm ? 1 : 0;
-    c->real_in = ch.n_in;
+    c->real_in = Pt;
     c->flags = (unsigned)d->flags;
 
-    // flat layout (reference ComponentArray order): per layer W (out x in, column-major) then b; then phi
+    // flat layout (reference ComponentArray order): chain after chain, per layer W (out x in, column-major) then b; then phi.
+    // Level 0 = inputs, 1..NH = hidden layers, L = outputs; chain k owns units [u0[k][lev], u0[k][lev] + cw[k][lev]).
     const ShapeDims& D = v->dims;
     const int L = ch.n_hidden + 1;
-    std::vector<int> width(L + 1);
-    width[0] = ch.n_in;
-    for (int l = 0; l < ch.n_hidden; l++) width[l + 1] = ch.hidden[l];
-    width[L] = ch.n_out;
-    std::vector<int> w_off(L), b_off(L);
+    std::vector<std::vector<int>> cw((size_t)NC, std::vector<int>((size_t)L + 1)), u0((size_t)NC, std::vector<int>((size_t)L + 1)),
+        w_off((size_t)NC, std::vector<int>((size_t)L)), b_off((size_t)NC, std::vector<int>((size_t)L));
+    std::vector<int> width((size_t)L + 1, 0);   // embedded (summed) width per level
     int off = 0;
-    for (int l = 0; l < L; l++) {
-        w_off[l] = off; off += width[l] * width[l + 1];
-        b_off[l] = off; off += width[l + 1];
+    for (int k = 0; k < NC; k++) {
+        const eh_chain_desc& ck = d->chains[k];
+        cw[k][0] = ck.n_in;
+        for (int l = 0; l < ck.n_hidden; l++) cw[k][l + 1] = ck.hidden[l];
+        cw[k][L] = ck.n_out;
+        for (int lev = 0; lev <= L; lev++) { u0[k][lev] = width[lev]; width[lev] += cw[k][lev]; }
+        for (int l = 0; l < L; l++) {
+            w_off[k][l] = off; off += cw[k][l] * cw[k][l + 1];
+            b_off[k][l] = off; off += cw[k][l + 1];
+        }
     }
     c->ntheta = off;
     int ng = 0;
@@ -1425,11 +1445,22 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
     const int H = wide ? v->H : D.H, P = wide ? v->P : D.P, NH = wide ? v->NH : D.NH, NOUT = wide ? v->NOUT : D.NOUT;
     c->h_wsrc.assign((size_t)v->NW + ng, -1);
     if (!wide) {
+    // flat entry behind image cell (layer l, embedded output unit j, embedded input unit k); -1: padding or a cell between
+    // units of different chains
     auto Wsrc = [&](int l /*1-based*/, int j, int k) -> int {
-        if (j >= width[l] || k >= width[l - 1]) return -1;
-        return w_off[l - 1] + j + k * width[l];
+        for (int q = 0; q < NC; q++) {
+            const int jj = j - u0[q][l], kk = k - u0[q][l - 1];
+            if (jj >= 0 && jj < cw[q][l] && kk >= 0 && kk < cw[q][l - 1]) return w_off[q][l - 1] + jj + kk * cw[q][l];
+        }
+        return -1;
     };
-    auto Bsrc = [&](int l, int j) -> int { return j < width[l] ? b_off[l - 1] + j : -1; };
+    auto Bsrc = [&](int l, int j) -> int {
+        for (int q = 0; q < NC; q++) {
+            const int jj = j - u0[q][l];
+            if (jj >= 0 && jj < cw[q][l]) return b_off[q][l - 1] + jj;
+        }
+        return -1;
+    };
     for (int k = 0; k < P; k++)
         for (int j = 0; j < H; j++) c->h_wsrc[D.off_w1f() + k * H + j] = Wsrc(1, j, k);
     for (int j = 0; j < H; j++) c->h_wsrc[D.off_b1() + j] = Bsrc(1, j);
@@ -1462,8 +1493,10 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
         sl.span = d->upper[pi] - d->lower[pi];
         sl.fixedv = d->deflt[pi];
         if (sl.role == EH_ROLE_NEURAL) {
-            if ((d->role_index[pi] >> 16) != 0) return fail(c, EH_EINVAL, "neural parameter refers to chain != 0");
-            sl.idx = d->role_index[pi] & 0xffff;
+            const int chain = d->role_index[pi] >> 16, row = d->role_index[pi] & 0xffff;
+            if (chain < 0 || chain >= NC || row >= d->chains[chain].n_out)
+                return fail(c, EH_EINVAL, "neural parameter %d refers to chain %d row %d", pi, chain, row);
+            sl.idx = u0[chain][L] + row;
             if (sl.idx >= NOUT) return fail(c, EH_EINVAL, "neural parameter row %d >= n_out %d", sl.idx, NOUT);
         } else if (sl.role == EH_ROLE_GLOBAL) {
             sl.idx = d->role_index[pi];
@@ -1479,29 +1512,37 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
         // padded-flat partial layout of the tensor-pipe engine (eh_engine_mma.cuh: O_W1 .. O_BO)
         const int o_w1 = 0, o_b1 = H * P, o_w2 = o_b1 + H, o_b2 = o_w2 + H * H, o_wo = o_b2 + H, o_bo = o_wo + NOUT * H;
         const int ow[3] = {o_w1, o_w2, o_wo}, ob[3] = {o_b1, o_b2, o_bo};
-        for (int l = 1; l <= L; l++)
+        for (int l = 1; l <= L; l++)   // (specialised variants: one chain)
             for (int j = 0; j < width[l]; j++) {
                 for (int k = 0; k < width[l - 1]; k++)
-                    c->h_pmap[w_off[l - 1] + j + k * width[l]] = (l == L) ? ow[2] + j * H + k : ow[l - 1] + j + k * H;
-                c->h_pmap[b_off[l - 1] + j] = ob[l - 1] + j;
+                    c->h_pmap[w_off[0][l - 1] + j + k * width[l]] = (l == L) ? ow[2] + j * H + k : ow[l - 1] + j + k * H;
+                c->h_pmap[b_off[0][l - 1] + j] = ob[l - 1] + j;
             }
     }
     for (int l = 1; l <= L && v->engine == 0 && !wide; l++) {
+        // (jj, kk): unit indices inside chain q; (j, k): the embedded units they live in
         if (l == L && D.LR) {
             // output layer kept in registers: [NOUT][H+1] block behind the statistics
-            for (int j = 0; j < width[l]; j++) {
-                for (int k = 0; k < width[l - 1]; k++) c->h_pmap[w_off[l - 1] + j + k * width[l]] = D.off_last() + j * (H + 1) + k;
-                c->h_pmap[b_off[l - 1] + j] = D.off_last() + j * (H + 1) + H;
-            }
+            for (int q = 0; q < NC; q++)
+                for (int jj = 0; jj < cw[q][l]; jj++) {
+                    const int j = u0[q][l] + jj;
+                    for (int kk = 0; kk < cw[q][l - 1]; kk++)
+                        c->h_pmap[w_off[q][l - 1] + jj + kk * cw[q][l]] = D.off_last() + j * (H + 1) + u0[q][l - 1] + kk;
+                    c->h_pmap[b_off[q][l - 1] + jj] = D.off_last() + j * (H + 1) + H;
+                }
             continue;
         }
         const int nk = D.nk(l), b0 = D.blk0(l);
-        for (int j = 0; j < width[l]; j++) {
-            for (int k = 0; k < width[l - 1]; k++)
-                c->h_pmap[w_off[l - 1] + j + k * width[l]] = (b0 + (j / 4) * nk + (k / 4)) * 16 + (j % 4) * 4 + (k % 4);
-            int kb = D.din(l);  // the "ones" row of the augmented input
-            c->h_pmap[b_off[l - 1] + j] = (b0 + (j / 4) * nk + (kb / 4)) * 16 + (j % 4) * 4 + (kb % 4);
-        }
+        for (int q = 0; q < NC; q++)
+            for (int jj = 0; jj < cw[q][l]; jj++) {
+                const int j = u0[q][l] + jj;
+                for (int kk = 0; kk < cw[q][l - 1]; kk++) {
+                    const int k = u0[q][l - 1] + kk;
+                    c->h_pmap[w_off[q][l - 1] + jj + kk * cw[q][l]] = (b0 + (j / 4) * nk + (k / 4)) * 16 + (j % 4) * 4 + (k % 4);
+                }
+                int kb = D.din(l);  // the "ones" row of the augmented input
+                c->h_pmap[b_off[q][l - 1] + jj] = (b0 + (j / 4) * nk + (kb / 4)) * 16 + (j % 4) * 4 + (kb % 4);
+            }
     }
     for (int g = 0; g < ng; g++) {
         int slot = MAXPS - 1;  // a statistics cell that stays zero (phi not used by the process model)
@@ -1530,11 +1571,13 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
     // record columns: chain inputs, the form's forcing, targets.  The generic variants have compile-time maxima:
     // missing inputs / forcings are zero columns (kind 2), missing targets NaN columns (kind 3: always masked)
     c->ncols = 0;
-    for (int k = 0; k < ch.n_in; k++) {
-        if (ch.in_cols[k] < 0 || ch.in_cols[k] >= d->n_pred) return fail(c, EH_EINVAL, "chain in_cols[%d] out of range", k);
-        c->src_kind[c->ncols] = 0; c->src_idx[c->ncols] = ch.in_cols[k]; c->ncols++;
-    }
-    for (int k = ch.n_in; k < v->P; k++) { c->src_kind[c->ncols] = 2; c->src_idx[c->ncols] = 0; c->ncols++; }
+    for (int q = 0; q < NC; q++)
+        for (int k = 0; k < d->chains[q].n_in; k++) {
+            const int col = d->chains[q].in_cols[k];
+            if (col < 0 || col >= d->n_pred) return fail(c, EH_EINVAL, "chain %d in_cols[%d] out of range", q, k);
+            c->src_kind[c->ncols] = 0; c->src_idx[c->ncols] = col; c->ncols++;
+        }
+    for (int k = Pt; k < v->P; k++) { c->src_kind[c->ncols] = 2; c->src_idx[c->ncols] = 0; c->ncols++; }
     if (use_prog) {
         for (int fi = 0; fi < v->F; fi++) {
             c->src_kind[c->ncols] = fi < d->n_forc ? 1 : 2; c->src_idx[c->ncols] = fi < d->n_forc ? fi : 0; c->ncols++;
@@ -1564,8 +1607,8 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
     if (c->opt_kind < 0 || c->opt_kind > 3) return fail(c, EH_EINVAL, "opt_kind=%d unknown", d->opt_kind);
     c->adamw_coupled = d->adamw_decay_coupled_eta;
     c->eta = d->eta; c->beta1 = d->beta1; c->beta2 = d->beta2; c->eps = d->eps; c->lambda = d->lambda;
-    c->bn_mean.assign((size_t)std::max(ch.n_in, v->P), 0.f);   // padded inputs: statistics of a zero column, never read back
-    c->bn_var.assign((size_t)std::max(ch.n_in, v->P), 1.f);
+    c->bn_mean.assign((size_t)std::max(Pt, v->P), 0.f);   // padded inputs: statistics of a zero column, never read back
+    c->bn_var.assign((size_t)std::max(Pt, v->P), 1.f);
     return EH_OK;
 }
 
