@@ -432,7 +432,7 @@ __device__ __forceinline__ void chunk_sample_phase(const float (*rec)[C::R4], co
     float dz[S][NOUT];
 #pragma unroll
     for (int s = 0; s < S; s++) {
-        float f[F > 0 ? F : 1], y[T], pv[NPS], sg[NPS], yh[T], sv[4], gy[T], gp[NPS];
+        float f[F > 0 ? F : 1], y[T], pv[NPS], sg[NPS], yh[T], sv[PM::NSV], gy[T], gp[NPS];
 #pragma unroll
         for (int k = 0; k < F; k++) f[k] = rec[s][P + k];
 #pragma unroll

@@ -216,7 +216,7 @@ struct EngMma {
             float dz[2][NOUT];
 #pragma unroll
             for (int h = 0; h < 2; h++) {
-                float pv[NPS], sg[NPS], yh[T], sv[4], gy[T], gp[NPS];
+                float pv[NPS], sg[NPS], yh[T], sv[PM::NSV], gy[T], gp[NPS];
                 resolve_params<C>(slot, sS, zo[h], pv, sg, cx);
                 PM::fwd(pv, f[h], cx, yh, sv);
 #pragma unroll

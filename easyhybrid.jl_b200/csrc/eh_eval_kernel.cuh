@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(256) k_eval(const EvalArgs a)
         for (int k = 0; k < T; k++) y[k] = p0[P + F + k];
 
         float2 hp[HP];
-        float zo[NOUT], pv[NPS], sg[NPS], yh[T], sv[4];
+        float zo[NOUT], pv[NPS], sg[NPS], yh[T], sv[PM::NSV];
         chain_forward<C, false>(sW, nullptr, lane, x, hp, zo);
         resolve_params<C>(a.slot, sS, zo, pv, sg, cx);
         PM::fwd(pv, f, cx, yh, sv);

@@ -68,6 +68,7 @@ __device__ __forceinline__ float exp2_mul_hilo(float a, float Lh, float Ll)
 // slots: p0 = rb, p1 = Q10 ; f0 = ta ; const c0 = tref
 struct PmRbQ10 {
     static constexpr bool DYNAMIC = false;
+    static constexpr int NSV = 4;   // floats of forward state kept for the backward
     static constexpr int ID = PM_RBQ10, NPS = 2, NF = 1, NT = 1;
     __device__ __forceinline__ static void fwd(const float* p, const float* f, const PmCtx& cx, float* y, float* sv)
     {
@@ -93,6 +94,7 @@ struct PmRbQ10 {
 // slots: p0 = Resp0, p1 = k ; f0 = T
 struct PmExpo {
     static constexpr bool DYNAMIC = false;
+    static constexpr int NSV = 4;   // floats of forward state kept for the backward
     static constexpr int ID = PM_EXPO, NPS = 2, NF = 1, NT = 1;
     __device__ __forceinline__ static void fwd(const float* p, const float* f, const PmCtx& cx, float* y, float* sv)
     {
@@ -113,6 +115,7 @@ struct PmExpo {
 // slots: p0 = a, p1 = b ; f0 = x
 struct PmLinear {
     static constexpr bool DYNAMIC = false;
+    static constexpr int NSV = 4;   // floats of forward state kept for the backward
     static constexpr int ID = PM_LINEAR, NPS = 2, NF = 1, NT = 1;
     __device__ __forceinline__ static void fwd(const float* p, const float* f, const PmCtx& cx, float* y, float* sv)
     {
@@ -129,6 +132,7 @@ struct PmLinear {
 // (var1 = a x + b, var2 = 2 a x + b)      test/test_compute_loss.jl:209-211
 struct PmLinear2 {
     static constexpr bool DYNAMIC = false;
+    static constexpr int NSV = 4;   // floats of forward state kept for the backward
     static constexpr int ID = PM_LINEAR2, NPS = 2, NF = 1, NT = 2;
     __device__ __forceinline__ static void fwd(const float* p, const float* f, const PmCtx& cx, float* y, float* sv)
     {
@@ -149,6 +153,7 @@ struct PmLinear2 {
 // construction as test/test_compute_loss.jl:209-211 uses for the linear model)
 struct PmExpo2 {
     static constexpr bool DYNAMIC = false;
+    static constexpr int NSV = 4;   // floats of forward state kept for the backward
     static constexpr int ID = PM_EXPO2, NPS = 2, NF = 1, NT = 2;
     __device__ __forceinline__ static void fwd(const float* p, const float* f, const PmCtx& cx, float* y, float* sv)
     {
@@ -173,6 +178,7 @@ struct PmExpo2 {
 struct PmProgram {
     static constexpr int ID = PM_PROGRAM, NPS = MAXPS, NF = 4, NT = 2;
     static constexpr bool DYNAMIC = true;
+    static constexpr int NSV = PM_MAXLEN;   // the forward values of all instructions: the reverse sweep reuses them
     __device__ __forceinline__ static void eval(const float* p, const float* f, const PmProgData& pg, float* v)
     {
         for (int i = 0; i < pg.len; i++) {
@@ -206,7 +212,7 @@ struct PmProgram {
     __device__ __forceinline__ static void fwd(const float* p, const float* f, const PmCtx& cx, float* y, float* sv)
     {
         const PmProgData& pg = *cx.prog;
-        float v[PM_MAXLEN];
+        float* v = sv;
         eval(p, f, pg, v);
         for (int t = 0; t < NT; t++) y[t] = t < pg.nt ? v[pg.out[t]] : 0.f;
     }
@@ -214,8 +220,8 @@ struct PmProgram {
                                                const float* sv, const float* gy, float* gp)
     {
         const PmProgData& pg = *cx.prog;
-        float v[PM_MAXLEN], g[PM_MAXLEN];
-        eval(p, f, pg, v);
+        const float* v = sv;   // forward values, left there by fwd
+        float g[PM_MAXLEN];
         for (int i = 0; i < pg.len; i++) g[i] = 0.f;
         for (int t = 0; t < NT; t++)
             if (t < pg.nt) g[pg.out[t]] += gy[t];

@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(256) k_wide_head(const HeadArgs a)
         for (int o = 0; o < NOUT; o++) zo[o] = warp_sum(zo[o]) + bout[o];
 
         // every lane evaluates the (cheap) per-sample scalar part redundantly: no broadcast needed afterwards
-        float f[F > 0 ? F : 1], y[T], pv[NPS], sg[NPS], yh[T], sv[4], gy[T], gp[NPS], dz[NOUT];
+        float f[F > 0 ? F : 1], y[T], pv[NPS], sg[NPS], yh[T], sv[PM::NSV], gy[T], gp[NPS], dz[NOUT];
         const float* r = a.xb + (size_t)b * a.d.R4;
 #pragma unroll
         for (int k = 0; k < F; k++) f[k] = k < nf ? r[P + k] : 0.f;

@@ -229,10 +229,17 @@ eh_status eh_step(eh_ctx* ctx, const int64_t* idx1, int64_t B, float* loss_out, 
 eh_status eh_step_host(eh_ctx* ctx, int64_t B, const float* X, const float* const* forc,
                        const float* const* targ, float* loss_out);
 
-/* Pipelined form of eh_step_host for streaming callers: enqueue the copy and
- * the step asynchronously (double-buffered pinned staging inside the ctx) and
- * return; losses[slot] is filled when the step retires.  eh_sync waits for
- * everything enqueued so far.                                                */
+/* Pipelined form of eh_step_host for streaming callers: enqueue the transfer
+ * and the step asynchronously and return; *loss_slot is filled by eh_sync,
+ * which waits for everything enqueued so far.  Page-locked arrays
+ * (eh_host_alloc, cudaHostAlloc / cudaHostRegister, CUDA.pin) are read IN
+ * PLACE over PCIe by a packer kernel -- no staging copy -- and the steps of up
+ * to 16 consecutive batches of equal size run inside one persistent launch
+ * (issued when the group is full, at eh_sync, or by any other entry point of
+ * this ctx); pageable arrays are staged through the copy engine, one launch
+ * pair per batch.  Either way the arrays must stay valid and unchanged until
+ * eh_sync returns (the rule cudaMemcpyAsync imposes).  Steps are applied in
+ * call order.                                                                */
 eh_status eh_step_host_async(eh_ctx* ctx, int64_t B, const float* X, const float* const* forc,
                              const float* const* targ, float* loss_slot);
 eh_status eh_sync(eh_ctx* ctx);
@@ -283,8 +290,8 @@ eh_status eh_comm_init(eh_ctx* ctx, int32_t rank, int32_t world, const void* ids
 eh_status eh_dp_batch_moments(eh_ctx* ctx, int64_t B, double* out /* [ceil(n/B)][EH_DP_MOMENTS] */);
 eh_status eh_dp_set_batch_moments(eh_ctx* ctx, int64_t B, const double* summed /* same shape */);
 
-/* page-locked host buffers for callers that stream batches (eh_step_host_async copies
- * straight out of them with cudaMemcpyAsync; pageable memory also works, but synchronously) */
+/* page-locked host buffers for callers that stream batches (eh_step_host_async reads them in
+ * place over PCIe; pageable memory also works, through the copy engine and synchronously) */
 eh_status eh_host_alloc(void** out, size_t bytes);
 eh_status eh_host_free(void* p);
 
