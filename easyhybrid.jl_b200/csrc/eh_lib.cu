@@ -59,6 +59,7 @@ constexpr int EH_NPACK = EH_NPACK_STREAMS;  // host-batch packers / copies in fl
 // EH_RING_GROUP batches ONE persistent launch runs that many optimiser steps over the group's slots, while the packers
 // of the next group keep the PCIe link busy.  Three groups: one training, one being packed, one draining.
 constexpr int EH_RING_GROUP = 16, EH_RING_NGRP = 3;
+constexpr int64_t EH_RING_MAX_BATCH = 1 << 18;   // batches beyond this take the one-launch-pair-per-batch form
 struct HostRing {
     float* d_rec = nullptr;    // [NGRP][GROUP * cap][R4]; slot k of a group starts at record k * B (B = the group's batch size)
     float* d_bscal = nullptr;  // [NGRP * GROUP][BS_STRIDE]
@@ -1856,6 +1857,8 @@ eh_status ring_enqueue(eh_ctx* c, int64_t B, const float* X, const float* const*
     const Variant* v = c->var;
     bool heavy = c->use_bn;
     for (int t = 0; t < c->n_targ; t++) heavy |= (c->loss_kind[t] == LOSS_NSELOSS);
+    // (large batches amortise their launches anyway; the ring would only cost memory: 48 slots)
+    if (B > EH_RING_MAX_BATCH) return EH_OK;
     if (r.off || !c->host_zero_copy || c->wide || heavy || !c->persist_ok || c->profiling ||
         (c->flags & EH_FLAG_NO_PERSIST) || c->n_forc_raw + c->n_targ > EH_PACK_MAXPLANES)
         return EH_OK;
