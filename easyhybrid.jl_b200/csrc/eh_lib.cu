@@ -1092,8 +1092,8 @@ eh_status build_plan_wide(eh_ctx* c, const eh_model_desc* d, bool is_prog)
     for (int l = 0; l < NH && l < 8; l++) hmax = std::max(hmax, wl[l]);
     if (NH > 7 || !eh::wide::WideNet::supported(P, hmax, NH, NOUT, c0.activation, d->process_model))
         return fail(c, EH_EUNSUPPORTED,
-                    "no fused kernel for this model: the register-tile kernels serve one chain of two hidden layers of width <= 32 "
-                    "with a built-in process model (all activations, <= 12 inputs); the tensor-core path serves 1..4 chains of equal "
+                    "no fused kernel for this model: the register-tile kernels serve 1..3 hidden layers of summed width <= 32 "
+                    "(all activations, <= 8 inputs, <= 2 outputs); the tensor-core path serves 1..4 chains of equal "
                     "depth (2..6 hidden layers, summed width per layer <= 512, <= 8 inputs and <= 2 outputs in total, tanh / sigmoid "
                     "/ relu) (got process_model=%d chains=%d inputs=%d hidden=%d x (<= %d) outputs=%d activation=%d)",
                     d->process_model, NC, P, NH, hmax, NOUT, c0.activation);
@@ -1361,7 +1361,7 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
     for (int l = 0; l < ch.n_hidden && l < 8; l++) hmax = std::max(hmax, wsum[l]);
     if (!is_prog && (d->n_pm_args != 3 || d->pm_args[0].kind != 0 || d->pm_args[1].kind != 0 || d->pm_args[2].kind != 1))
         return fail(c, EH_EINVAL, "built-in process models take (param, param, forcing) arguments");
-    // Which path?  The exact-fp32 register-tile kernels exist for two hidden layers of width <= 32; every other chain
+    // Which path?  The exact-fp32 register-tile kernels exist for one to three hidden layers of width <= 32; every other chain
     // (wider or deeper, up to 6 hidden layers of up to 512 units, padded to 256 / 512 internally) runs on the bf16
     // tcgen05 GEMM path.
     const bool wide = false;   // (this function continues with the register-tile plan only)
