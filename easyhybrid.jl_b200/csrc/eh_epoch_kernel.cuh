@@ -300,15 +300,20 @@ __global__ void __launch_bounds__(E::MAX_WARPS * 32, 1) k_epoch(const EpochArgs 
 
         E::step_begin(st, sW, lane);
         const FetchArgs fa{a.rec, a.idx ? a.idx + b * a.B : nullptr, a.idx ? 0 : b * a.B, Bk, nchunks};
-        for (int chunk = gw; chunk < nchunks; chunk += GW)
-            E::chunk(st, fa, chunk + GW, sW, sS, stage, lane, a.slot, a.loss_kind, cx);
-        if (a.dbg && lane == 0) a.dbg[((size_t)s * G + blockIdx.x) * 32 + 8 + warp] = clock64();
-        // prefetch my first sample of the next step: its latency hides behind the exchange below
-        if (s + 1 < a.nsteps) {
-            const long long b2 = bnext;
-            const int Bk2 = bnext == a.nb - 1 ? Blast : a.B;
-            E::fetch(st, a.rec, a.idx ? a.idx + b2 * a.B : nullptr, a.idx ? 0 : b2 * a.B, Bk2, gw, (Bk2 + E::CHUNK - 1) / E::CHUNK, lane);
+        // the records this warp needs first in the NEXT step are prefetched while it computes its last chunk of this
+        // step (index load + dependent record gather = two DRAM latencies, hidden behind ~12 000 cycles of compute
+        // instead of the much shorter exchange)
+        const long long b2 = bnext;
+        const int Bk2 = bnext == a.nb - 1 ? Blast : a.B;
+        const FetchArgs fn{a.rec, a.idx ? a.idx + b2 * a.B : nullptr, a.idx ? 0 : b2 * a.B, Bk2,
+                           s + 1 < a.nsteps ? (Bk2 + E::CHUNK - 1) / E::CHUNK : 0};
+        for (int chunk = gw; chunk < nchunks; chunk += GW) {
+            const bool last = chunk + GW >= nchunks;
+            E::chunk(st, last ? fn : fa, last ? gw : chunk + GW, sW, sS, stage, lane, a.slot, a.loss_kind, cx);
         }
+        if (a.dbg && lane == 0) a.dbg[((size_t)s * G + blockIdx.x) * 32 + 8 + warp] = clock64();
+        // a warp without a chunk in this step still has to fetch its first sample of the next one
+        if (gw >= nchunks) E::fetch(st, fn.rec, fn.idx, fn.rec_base, fn.B, gw, fn.nchunks, lane);
         __syncthreads();
         EH_STAMP(2)
         // CTA partial -> cpart (the scratch of cta_reduce aliases the staging tiles)
