@@ -164,7 +164,8 @@ def cpu_baseline(eh, model, seconds=12.0, max_steps=4000):
     o = orc.Oracle(model, opt=eh.Adam(0.01))
     flat = model.initialparameters(np.random.default_rng(0))
     rng = np.random.default_rng(1)
-    threads = orc.max_threads()
+    # all host cores: torchrun exports OMP_NUM_THREADS=1 to its workers, which would silently make this a 1-core number
+    threads = max(orc.max_threads(), len(os.sched_getaffinity(0)))
     o.train_steps(flat, xf, y, rng.permutation(n)[: 2 * B], B, nthreads=threads)  # warm-up
     steps, t0 = 0, time.perf_counter()
     while steps < max_steps and time.perf_counter() - t0 < seconds:
