@@ -365,6 +365,7 @@ __global__ void __launch_bounds__(E::MAX_WARPS * 32, 1) k_epoch(const EpochArgs 
         }
         const bool skip = ntot == 0.f;  // all-masked batch: epoch.jl:17-19
         if (blockIdx.x == 0 && threadIdx.x < MAXT) a.stats_out[(size_t)s * MAXT + threadIdx.x] = red[E::OFF_STATS + threadIdx.x];
+        EH_STAMP(29)
         if (!skip) {
             for (int p = threadIdx.x; p < a.nflat; p += blockDim.x) {
                 float g = red[t_pmap[p]] * post;
@@ -406,6 +407,7 @@ __global__ void __launch_bounds__(E::MAX_WARPS * 32, 1) k_epoch(const EpochArgs 
                     }
                 }
             }
+            EH_STAMP(30)
             b1t *= a.beta1;
             b2t *= a.beta2;
             tdone++;

@@ -18,4 +18,9 @@ for s in range(1, nsteps):
         if d[s, :, 27].any():
             rd = (d[s, :, 27] - d[s, :, 6]).astype(np.float64); ex = (d[s, :, 28] - d[s, :, 27]).astype(np.float64); ad = (d[s, :, 7] - d[s, :, 28]).astype(np.float64)
             print(f"     of which: rank exchange median {np.median(ex):.0f} (max {ex.max():.0f}), adam+init median {np.median(ad):.0f}")
+        if d[s, :, 29].any() and d[s, :, 30].any():
+            # finer stamps of thread 0 (every stamp itself costs ~350 cycles: clock read + global store)
+            sc = (d[s, :, 29] - d[s, :, 28]).astype(np.float64); lo = (d[s, :, 30] - d[s, :, 29]).astype(np.float64)
+            print(f"     adam phase of thread 0: batch scalars median {np.median(sc):.0f}, its one parameter {np.median(lo):.0f}"
+                  " (the step-top barrier then waits for the thread that owns a phi entry: sigmoid, squashing, double log2)")
         print(f"   per-warp compute: median {np.median(wend):.0f} min {wend.min():.0f} max {wend.max():.0f}; per-CTA slowest warp median {np.median(wend.max(axis=1)):.0f}")
