@@ -67,8 +67,9 @@ struct StepCfg {
 };
 
 // shared memory carve-up (floats): [weights NW pad4][scalars 128][per-warp stage ...]
-//   scalars: [0..8) uniform slot values, [16..48) per-slot derived scalars, [48..52) c_t, [56..80) BN (mu, rstd)
-constexpr int SS_SLOT = 0, SS_PMS = 16, SS_C = 48, SS_NV = 52, SS_BN = 56, SS_NV2 = 80, SS_FLOATS = 128;
+//   scalars: [0..8) uniform slot values, [16..48) per-slot derived scalars, [48..52) c_t, [56..80) BN (mu, rstd),
+//   [96..104) persistent kernel: span * sigma'(phi_g) of the global parameters, kept from their last update
+constexpr int SS_SLOT = 0, SS_PMS = 16, SS_C = 48, SS_NV = 52, SS_BN = 56, SS_NV2 = 80, SS_SGD = 96, SS_FLOATS = 128;
 
 // float offset of the staging row of feature k inside 4-row group g0 (+k/4).  Groups are 4 rows of RS floats
 // plus 4 floats of skew: the group stride is 20 mod 32 banks, so the 8 groups a quarter-warp of dW tiles

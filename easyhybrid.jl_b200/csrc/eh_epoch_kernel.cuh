@@ -233,6 +233,11 @@ __global__ void __launch_bounds__(E::MAX_WARPS * 32, 1) k_epoch(const EpochArgs 
         t_cell1[p] = a.cells[2 * p + 1];
         t_slot[p] = a.slot_of_flat[p];
         t_span[p] = a.pspan[p];
+        if (p >= a.ntheta && p - a.ntheta < MAXPS) {
+            // d(squashed phi)/d(raw phi), reused by the gradient of the next step (recomputed after every update)
+            const float sg0 = 1.f / (1.f + expf(-a.pblock[p]));
+            sS[SS_SGD + p - a.ntheta] = a.pspan[p] * sg0 * (1.f - sg0);
+        }
     }
     float b1t = a.ost->b1t, b2t = a.ost->b2t;
     long long tdone = 0, tskip = 0;
@@ -370,7 +375,10 @@ __global__ void __launch_bounds__(E::MAX_WARPS * 32, 1) k_epoch(const EpochArgs 
             for (int p = threadIdx.x; p < a.nflat; p += blockDim.x) {
                 float g = red[t_pmap[p]] * post;
                 float th = s_th[p];
-                if (p >= a.ntheta) {
+                const bool phi_cached = p >= a.ntheta && p - a.ntheta < MAXPS;
+                if (phi_cached) {
+                    g *= sS[SS_SGD + p - a.ntheta];
+                } else if (p >= a.ntheta) {
                     float sg = 1.f / (1.f + expf(-th));
                     g *= t_span[p] * sg * (1.f - sg);
                 }
@@ -396,12 +404,14 @@ __global__ void __launch_bounds__(E::MAX_WARPS * 32, 1) k_epoch(const EpochArgs 
                 if (c0 >= 0) sW[c0] = th;
                 if (c1 >= 0) sW[c1] = th;
                 if (p >= a.ntheta) {
+                    const float sgn = 1.f / (1.f + expf(-th));
+                    if (phi_cached) sS[SS_SGD + p - a.ntheta] = t_span[p] * sgn * (1.f - sgn);
                     const int sl = t_slot[p];
                     if (sl >= 0) {
                         const PSlot ps = a.slot[sl];
-                        float val = ps.lo + ps.span * (1.f / (1.f + expf(-th)));
+                        float val = ps.lo + ps.span * sgn;
                         float o4[4];
-                        pm_prep_slot(a.pm_id, sl, val, o4);
+                        pm_prep_slot_fast(a.pm_id, sl, val, o4);
                         sS[SS_SLOT + sl] = val;
                         for (int i = 0; i < 4; i++) sS[SS_PMS + sl * PMS_PER_SLOT + i] = o4[i];
                     }

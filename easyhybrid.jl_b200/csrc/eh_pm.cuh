@@ -54,6 +54,57 @@ __device__ inline void pm_prep_slot(int pm, int slot, float v, float* out4)
     }
 }
 
+// 2^(-j/64), j = 0 .. 64, correctly rounded
+static __constant__ double c_exp2_neg64[65] = {
+    1.0, 0.9892280131939755, 0.9785720620877001, 0.9680308967461472,
+    0.9576032806985737, 0.9472879907934828, 0.93708381705515, 0.9269895625416927,
+    0.9170040432046712, 0.9071260877501994, 0.8973545375015536, 0.8876882462632606,
+    0.8781260801866497, 0.8686669176368531, 0.859309649061239, 0.8500531768592617,
+    0.8408964152537145, 0.8318382901633682, 0.8228777390769825, 0.8140137109286739,
+    0.8052451659746271, 0.7965710756711335, 0.7879904225539432, 0.7795022001189185,
+    0.7711054127039704, 0.7627990753722692, 0.7545822137967114, 0.7464538641456324,
+    0.7384130729697497, 0.7304588970903235, 0.7225904034885233, 0.714806669195985,
+    0.7071067811865476, 0.6994898362691556, 0.691954940981916, 0.6845012114872953,
+    0.6771277734684463, 0.6698337620266515, 0.6626183215798707, 0.6554806057623822,
+    0.6484197773255048, 0.6414350080393891, 0.6345254785958666, 0.6276903785123455,
+    0.620928906036742, 0.614240268053435, 0.6076236799902345, 0.6010783657263515,
+    0.5946035575013605, 0.5881984958251406, 0.5818624293887887, 0.5755946149764913,
+    0.5693943173783458, 0.5632608093041209, 0.5571933712979462, 0.5511912916539204,
+    0.5452538663326288, 0.5393803988785599, 0.5335702003384118, 0.5278225891802786,
+    0.5221368912137069, 0.5165124395106142, 0.5109485743270583, 0.5054446430258502,
+    0.5};
+
+// log2 of a positive finite float in double precision (error < 1e-15): exponent + a 1/64 table step + a six-term log1p
+// series -- about a dozen FP64 operations instead of the ~35 of the library log2.  It sits on the critical path of every
+// optimiser step of the persistent kernel (the thread that owns Q10 computes it before the step-top barrier).
+__device__ __forceinline__ double log2_pos_fast(float v)
+{
+    if (!(v > 1e-30f) || !(v < 1e30f)) return log2((double)v);   // zero / negative / denormal / huge: library semantics
+    int e;
+    float m = 2.f * frexpf(v, &e);                 // v = m 2^(e-1), m in [1, 2)
+    const int j = __float2int_rn(__log2f(m) * 64.f);   // 0 .. 64
+    const double u = fma((double)m, c_exp2_neg64[j], -1.0);   // |u| < 2^(1/128) - 1 + rounding of j = 0.0055
+    double p = fma(u, -1.0 / 6.0, 0.2);
+    p = fma(u, p, -0.25);
+    p = fma(u, p, 1.0 / 3.0);
+    p = fma(u, p, -0.5);
+    p = fma(u, p, 1.0);                            // log1p(u) / u, next term u^6 / 7 < 4e-15 relative
+    return (double)(e - 1) + (double)j * (1.0 / 64.0) + u * p * 1.4426950408889634;
+}
+
+// pm_prep_slot with log2_pos_fast (persistent kernel)
+__device__ inline void pm_prep_slot_fast(int pm, int slot, float v, float* out4)
+{
+    out4[0] = out4[1] = out4[2] = out4[3] = 0.f;
+    if (pm == PM_RBQ10 && slot == 1) {
+        const double L = log2_pos_fast(v);
+        const float Lh = (float)L;
+        out4[0] = Lh;
+        out4[1] = (float)(L - (double)Lh);
+        out4[2] = 1.0f / v;
+    }
+}
+
 // 2^(a*(Lh+Ll)) with the product carried in two floats
 __device__ __forceinline__ float exp2_mul_hilo(float a, float Lh, float Ll)
 {
