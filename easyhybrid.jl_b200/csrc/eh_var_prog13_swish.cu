@@ -1,0 +1,17 @@
+// Generic exact-fp32 variants, activation ACT_SWISH, one or three hidden layers (chain inputs padded to 8): process model = traced program interpreted per sample
+// (PmProgram); hidden width 16 / 32, one or two chain outputs; scale_nn_outputs is a run-time flag (compiled with
+// SCALE = true).  One translation unit per (activation, depth group) keeps the parallel build balanced.  sm_100a
+#include "eh_variant_impl.cuh"
+namespace eh {
+#define LIST(X) \
+    X(PmProgram, 8, 1, 16, 1, ACT_SWISH, true) \
+    X(PmProgram, 8, 1, 16, 2, ACT_SWISH, true) \
+    X(PmProgram, 8, 1, 32, 1, ACT_SWISH, true) \
+    X(PmProgram, 8, 1, 32, 2, ACT_SWISH, true) \
+    X(PmProgram, 8, 3, 16, 1, ACT_SWISH, true) \
+    X(PmProgram, 8, 3, 16, 2, ACT_SWISH, true) \
+    X(PmProgram, 8, 3, 32, 1, ACT_SWISH, true) \
+    X(PmProgram, 8, 3, 32, 2, ACT_SWISH, true)
+static const Variant g[] = {LIST(EH_MAKE)};
+const Variant* variants_prog13_swish(int* n) { *n = (int)(sizeof(g) / sizeof(g[0])); return g; }
+}  // namespace eh

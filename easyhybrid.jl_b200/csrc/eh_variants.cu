@@ -3,7 +3,7 @@
 
 namespace eh {
 
-constexpr int NGROUPS = 7;
+constexpr int NGROUPS = 11;
 static const Variant* group(int k, int* n)
 {
     switch (k) {
@@ -14,6 +14,10 @@ static const Variant* group(int k, int* n)
     case 4: return variants_prog_sigmoid(n);
     case 5: return variants_prog_relu(n);
     case 6: return variants_prog_swish(n);
+    case 7: return variants_prog13_tanh(n);
+    case 8: return variants_prog13_sigmoid(n);
+    case 9: return variants_prog13_relu(n);
+    case 10: return variants_prog13_swish(n);
     default: *n = 0; return nullptr;
     }
 }

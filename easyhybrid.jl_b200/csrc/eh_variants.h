@@ -38,5 +38,9 @@ const Variant* variants_prog_tanh(int* n);
 const Variant* variants_prog_sigmoid(int* n);
 const Variant* variants_prog_relu(int* n);
 const Variant* variants_prog_swish(int* n);
+const Variant* variants_prog13_tanh(int* n);
+const Variant* variants_prog13_sigmoid(int* n);
+const Variant* variants_prog13_relu(int* n);
+const Variant* variants_prog13_swish(int* n);
 
 }  // namespace eh
