@@ -32,6 +32,23 @@ CASES = [
     ("expo2-3x48-pertarget-nan", lambda eh: expo2_model(eh, hidden=(48, 48, 48)), lambda: make_expo2(300, nan_frac=0.1), "PT", "sum"),
 ]
 
+# the models the generic exact-fp32 GPU variants are checked with (tests/test_gpu_generic.py): traced process models,
+# one / three hidden layers, several chains -- the oracle is their checker on the GPU, this is the oracle's own witness
+import test_gpu_generic as gg  # noqa: E402
+
+CASES += [
+    ("traced-custom", gg.m_custom, lambda: gg._table(300), "mse", "sum"),
+    ("traced-custom-nan-mae", gg.m_custom, lambda: gg._table(300, nan_frac=0.05), "mae", "sum"),
+    ("traced-relu32-noscale", lambda eh: gg.m_custom(eh, hidden=(32, 32), activation="relu", scale=False), lambda: gg._table(300), "mse", "sum"),
+    ("traced-swish-bn-nse", lambda eh: gg.m_custom(eh, hidden=(12, 12), activation="swish", bn=True), lambda: gg._table(300), "nseLoss", "sum"),
+    ("traced-two-neural", gg.m_two_neural, lambda: gg._table(300), "mse", "sum"),
+    ("traced-two-targets-bn", gg.m_two_targets, lambda: gg._table(400, nan_frac=0.1, two=True), "PT", "mean"),
+    ("rbq10-one-hidden-layer", lambda eh: rbq10_model(eh, hidden=(16,)), lambda: make_synth(300, nan_frac=0.03), "mse", "sum"),
+    ("rbq10-three-hidden-layers", lambda eh: rbq10_model(eh, hidden=(16, 12, 8), activation="sigmoid"), lambda: make_synth(300), "mse", "sum"),
+    ("rbq10-three-inputs-swish", gg.m_rbq10_three_inputs, lambda: make_synth(300, nan_frac=0.03), "mse", "sum"),
+    ("two-chains-six-inputs-bn", gg.m_two_chains_six_inputs, lambda: make_synth(300), "mse", "sum"),
+]
+
 
 @pytest.mark.parametrize("name,mk,mkdata,loss,agg", CASES, ids=[c[0] for c in CASES])
 def test_loss_and_grad_vs_autograd(eh, orc, name, mk, mkdata, loss, agg):
