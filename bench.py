@@ -50,11 +50,12 @@ def synth(n, seed):
     return (np.ascontiguousarray(np.stack([sw, dsw], 1)), {"ta": ta}), {"reco": reco}
 
 
-def wide_c5_leg(eh, device):
-    """BASELINE config 5 on one GPU (reported next to the headline, not instead of it): two-target Expo hybrid,
-    hidden 3 x 512, bf16 tcgen05 GEMMs, PerTarget(nseLoss, mse), batch 65536; tensor roofline of its hidden GEMMs."""
+def wide_c5_leg(eh, device, rank=0, world=1, dist=None):
+    """BASELINE config 5 (reported next to the headline, not instead of it): two-target Expo hybrid, hidden 3 x 512,
+    bf16 tcgen05 GEMMs, PerTarget(nseLoss, mse), batch 65536 per GPU; tensor roofline of its hidden GEMMs.  With several
+    ranks: data parallel (weak scaling), the 0.5 M-entry gradient all-reduced over NVLink peer memory every step."""
     n = 1 << 20
-    rng = np.random.default_rng(2314)
+    rng = np.random.default_rng(2314 + rank)
     T = (rng.random(n, dtype=np.float32) * 40 - 10).astype(np.float32)
     SM = (rng.random(n, dtype=np.float32) * 0.8 + 0.1).astype(np.float32)
     resp = 1.1 * np.exp(-8.0 * (SM - 0.6) ** 2) * np.exp(0.07 * T)
@@ -68,13 +69,27 @@ def wide_c5_leg(eh, device):
     sess = eh.FusedSession(model, training_loss=eh.PerTarget("nseLoss", "mse"), agg="sum", opt=eh.Adam(0.001), device=device)
     sess.upload(0, xf, y)
     sess.set_params(model.initialparameters(np.random.default_rng(0)))
-    sess.set_perm(np.random.default_rng(7).permutation(n))
+    if world > 1:
+        sess.comm_init(rank, world, dist)
+    sess.set_perm(np.random.default_rng(7 + rank).permutation(n))
+    if world > 1:
+        sess.dp_exchange_batch_stats(B, dist)   # nseLoss: SS_tot of the GLOBAL batch
+        dist.barrier()
     sess.run_steps(B, 0, 4)
     k = 32
+    if world > 1:
+        import torch
+        dist.barrier()
+        torch.cuda.synchronize()
     losses = sess.run_steps(B, 4, k)
     ms, launches, _ = sess.last_timing()
+    if world > 1:
+        import torch
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
     sess.close()
-    flop = 2.0 * 3 * 2 * B * 512 * 512 * k  # two 512 x 512 hidden matrices x (forward, backward-data, weight-gradient)
+    flop = 2.0 * 3 * 2 * B * 512 * 512 * k  # two 512 x 512 hidden matrices x (forward, backward-data, weight-gradient), per GPU
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -82,13 +97,13 @@ def wide_c5_leg(eh, device):
         pass
     peak = float(peaks.get("bf16_tflops_sustained", 0) or 0)
     tf = flop / (ms * 1e-3) / 1e12
-    return {"workload": "C5: two-target Expo hybrid [1-512-512-512-1] tanh, PerTarget(nseLoss, mse), Adam, batch 65536, 1 GPU",
-            "value": k * B / (ms * 1e-3), "unit": "samples/s", "us_per_step": 1e3 * ms / k, "steps": k, "dtype": "bf16 (fp32 accumulate)",
+    return {"workload": f"C5: two-target Expo hybrid [1-512-512-512-1] tanh, PerTarget(nseLoss, mse), Adam, batch 65536 per GPU, {world} GPU(s), N=2^20 per GPU",
+            "value": world * k * B / (ms * 1e-3), "unit": "samples/s", "n_gpus": world, "scaling": "weak", "us_per_step": 1e3 * ms / k, "steps": k, "dtype": "bf16 (fp32 accumulate)",
             "gpu_launches_per_step": launches / k,
             "roofline": {"bound": "tensor", "achieved": tf, "peak": peak or None, "unit": "TFLOP/s",
                          "frac": (tf / peak) if peak else None,
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peak else "unavailable",
-                         "flops_counted": "hidden-layer GEMMs only (2 * 3 * 2 * B * 512 * 512 per step)"},
+                         "flops_counted": "hidden-layer GEMMs only (2 * 3 * 2 * B * 512 * 512 per step), per GPU"},
             "loss_first_last": [float(losses[0]), float(losses[-1])]}
 
 
@@ -154,6 +169,90 @@ def measured_peaks():
     if os.path.exists(p):
         return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measured_traffic():
+    """DRAM bytes per optimiser step of the persistent kernel from the ncu capture of the CURRENT kernel
+    (profiles/r2_kernel_metrics.json, written by tools/ncu_metrics_to_json.py from `ncu --set full`); None if absent"""
+    try:
+        m = json.load(open(os.path.join(ROOT, "profiles", "r2_kernel_metrics.json")))["k_epoch"]
+        return (float(m["dram_bytes_read"]) + float(m["dram_bytes_write"])) / float(m["steps"]), m
+    except (OSError, ValueError, KeyError):
+        return None, None
+
+
+def dp_parity_check(eh, dist, rank, world, local):
+    """Outside the timed region: two data-parallel optimiser steps of batch 65536 per GPU on small shards; rank 0 runs
+    the CPU oracle (test infrastructure, the checker) on the UNION batches and compares per-step loss (1e-5) and the
+    trained Q10 (1e-4); all ranks must hold bit-identical parameters."""
+    import hashlib
+    n_local = 1 << 17
+    model = make_model(eh)
+    xf, y = synth(n_local, 9000 + rank)
+    flat0 = model.initialparameters(np.random.default_rng(5))
+    perm = np.random.default_rng(9100 + rank).permutation(n_local)
+    sess = eh.FusedSession(model, opt=eh.Adam(0.01), device=local)
+    sess.upload(0, xf, y)
+    sess.set_params(flat0)
+    sess.comm_init(rank, world, dist)
+    sess.set_perm(perm)
+    dist.barrier()
+    losses = sess.run_steps(B, 0, 2)
+    ps = sess.get_params()
+    sess.close()
+    digests = [None] * world
+    dist.all_gather_object(digests, hashlib.sha1(ps.tobytes()).hexdigest())
+    out = {"steps": 2, "global_batch": world * B}
+    if rank == 0:
+        from oracle import oracle as orc
+        from easyhybrid_b200.dp import global_batch_indices
+        shards = [synth(n_local, 9000 + r) for r in range(world)]
+        perms = [np.random.default_rng(9100 + r).permutation(n_local) for r in range(world)]
+        Xall = np.concatenate([sh[0][0] for sh in shards])
+        fall = {"ta": np.concatenate([sh[0][1]["ta"] for sh in shards])}
+        yall = {"reco": np.concatenate([sh[1]["reco"] for sh in shards])}
+        o = orc.Oracle(model, opt=eh.Adam(0.01))
+        ref = flat0.copy()
+        want = []
+        threads = max(orc.max_threads(), len(os.sched_getaffinity(0)))
+        for k in range(2):
+            gi = global_batch_indices(perms, [n_local] * world, B, k)
+            L, g = o.loss_grad(ref, (Xall, fall), yall, gi, precision=64, nthreads=threads)
+            want.append(L)
+            o.opt_step(ref, g.astype(np.float32))
+        rel = float(np.max(np.abs(np.asarray(losses, dtype=np.float64) - np.array(want)) / np.abs(want)))
+        q10 = lambda p: 1.0 + 3.0 / (1.0 + np.exp(-float(p[-1])))
+        dq = abs(q10(ps) - q10(ref)) / q10(ref)
+        same = all(d == digests[0] for d in digests)
+        out.update({"ok": bool(rel <= 1e-5 and dq <= 1e-4 and same), "max_rel_loss_err": rel, "q10_rel_err": float(dq),
+                    "replicas_bit_identical": bool(same), "checker": "float64 oracle on the union batches (rank 0)"})
+    return out
+
+
+def strong_scaling_leg(eh, dist, rank, world, local, K):
+    """SURVEY 8(d) C4, second reading: GLOBAL batch 65536 (strong scaling): every rank trains on 65536 / world samples per
+    step; reported next to the weak-scaling headline."""
+    import torch
+    Bl = B // world
+    n = 1 << 22
+    model = make_model(eh)
+    xf, y = synth(n, 4200 + rank)
+    sess = eh.FusedSession(model, opt=eh.Adam(0.01), device=local)
+    sess.upload(0, xf, y)
+    sess.set_params(model.initialparameters(np.random.default_rng(0)))
+    sess.comm_init(rank, world, dist)
+    sess.set_perm(np.random.default_rng(77 + rank).permutation(n))
+    sess.run_steps(Bl, 0, 8)
+    dist.barrier()
+    torch.cuda.synchronize()
+    sess.run_steps(Bl, 8, K)
+    ms, _, _ = sess.last_timing()
+    t = torch.tensor([ms], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    sess.close()
+    return {"scaling": "strong", "global_batch": B, "per_gpu_batch": Bl, "n_gpus": world, "steps": K,
+            "value": K * B / (ms * 1e-3), "unit": "samples/s", "us_per_step": 1e3 * ms / K}
 
 
 def cpu_baseline(eh, model, seconds=12.0, max_steps=4000):
@@ -268,12 +367,15 @@ def main():
     # The timed region is ONE launch of the persistent kernel k_epoch (all K steps, exchange included):
     # algorithmic bytes of that launch = K * B * 16 B per GPU, duration = the CUDA-event time above.
     peak, peak_src = measured_peaks()
+    traffic_per_step, traffic_meta = measured_traffic()
     per_gpu_sps = K * B / (dev_ms * 1e-3)
     achieved = per_gpu_sps * BYTES_PER_SAMPLE / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                # dram__bytes_read+write of k_epoch from ncu --set full (profiles/r1_k_epoch_v6_ncu_details.txt; same in v5):
-                # 57.8 + 1.08 MB for a 12-step launch = 4.9 MB per step, scaled to this launch's K steps
-                "traffic": 4.89e6 * K, "traffic_algorithmic": float(K) * B * BYTES_PER_SAMPLE,
+                # dram__bytes_read + write of k_epoch per step from the ncu --set full capture of the current kernel
+                # (profiles/r2_kernel_metrics.json), scaled to this launch's K steps; None when the capture is absent
+                "traffic": (traffic_per_step * K) if traffic_per_step is not None else None,
+                "traffic_source": ("profiles/r2_kernel_metrics.json (ncu --set full, git %s, %s steps)" % (traffic_meta.get("git"), traffic_meta.get("steps"))) if traffic_meta else None,
+                "traffic_algorithmic": float(K) * B * BYTES_PER_SAMPLE,
                 "peak_source": peak_src,
                 "kernel": "k_epoch (persistent: fused fwd+process+loss+bwd, grid exchange, Adam; one launch = K steps)",
                 "kernel_us_per_step": 1e3 * dev_ms / K,
@@ -346,11 +448,21 @@ def main():
 
     clocks = sampler.stop(windows)
     wide = None
-    if rank == 0 and world == 1 and not args.no_wide:
+    if not args.no_wide:
         try:
-            wide = wide_c5_leg(eh, local)
+            wide = wide_c5_leg(eh, local, rank, world, dist)
         except Exception as e:  # the extra leg must never take the headline line down
             wide = {"error": str(e)[:200]}
+    dp_parity = strong = None
+    if world > 1:
+        try:
+            dp_parity = dp_parity_check(eh, dist, rank, world, local)
+        except Exception as e:
+            dp_parity = {"ok": False, "error": str(e)[:200]}
+        try:
+            strong = strong_scaling_leg(eh, dist, rank, world, local, K)
+        except Exception as e:
+            strong = {"error": str(e)[:200]}
 
     if rank == 0:
         line = {"metric": "training samples/sec (fwd+bwd+Adam)", "value": value, "unit": "samples/s", "n_gpus": world,
@@ -364,6 +476,11 @@ def main():
                 "final_loss": float(losses[-1])}
         if wide is not None:
             line["extra"] = {"c5_wide_mlp": wide}
+        if dp_parity is not None:
+            line["dp_parity_ok"] = bool(dp_parity.get("ok", False))
+            line["dp_parity"] = dp_parity
+        if strong is not None:
+            line.setdefault("extra", {})["c4_strong_scaling"] = strong
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(eh, model)[0]
         print(json.dumps(line))

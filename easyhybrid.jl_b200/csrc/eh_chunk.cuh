@@ -279,7 +279,22 @@ struct FetchArgs {
     const int* idx;       // NULL: records rec_base .. rec_base + B
     long long rec_base;
     int B, nchunks;
+    // optional: the records of samples [tile_s0, ...) of this batch already staged in shared memory (persistent
+    // kernel: one cp.async.bulk per CTA and step, eh_epoch_kernel.cuh); fetch then reads the tile instead of HBM
+    const float4* tile;
+    int tile_s0;
 };
+
+// record q-th float4 of batch sample `smp` (valid sample): shared-memory tile if staged, else HBM (gather through idx
+// or contiguous)
+template <int R44>
+__device__ __forceinline__ float4 fetch_rec4(const FetchArgs& fa, int smp, int q)
+{
+    if (fa.tile) return fa.tile[(size_t)(smp - fa.tile_s0) * R44 + q];
+    long long i = fa.rec_base + smp;
+    if (fa.idx) i = fa.idx[smp];
+    return __ldg(fa.rec + i * R44 + q);
+}
 
 struct ChunkStats {
     float loss[MAXT];    // sum r^2 (or |r|) per target
@@ -430,6 +445,7 @@ __device__ __forceinline__ void chunk_sample_phase(const float (*rec)[C::R4], co
     }
 
     // ---- process parameters (GenericHybridModel.jl:377-414), physics (:425), masked residual, seeds ----
+    cx.wait_phi();   // persistent kernel: the global parameters' derived scalars of this step are in place
     float dz[S][NOUT];
 #pragma unroll
     for (int s = 0; s < S; s++) {
@@ -712,11 +728,11 @@ __device__ __forceinline__ int transpose_reduce_slot(int lane)
 // scratch: the warps' rows of NPART floats, `stride` floats apart; the dW cells of a row were left there by
 // chunk_dw_phase (element-major; the tile-major order of the partial vector is restored by the summing
 // pass below), `nacc` = chunks this warp accumulated this step (0: its dW cells are stale and count as zero).
+// (1) per warp, before the CTA barrier: the warp's statistics / output-layer sums into its row
 template <class C>
-__device__ __forceinline__ void cta_reduce(int nacc, const ChunkStats& st, const LastAcc<C>& la, float* scratch, int stride,
-                                           float* out, int out_is_global)
+__device__ __forceinline__ void cta_reduce_prepare(int nacc, const ChunkStats& st, const LastAcc<C>& la, float* scratch, int stride)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (nacc == 0)
         for (int q = lane; q < C::NB * 16; q += 32) scratch[warp * stride + q] = 0.f;
     {
@@ -755,14 +771,26 @@ __device__ __forceinline__ void cta_reduce(int nacc, const ChunkStats& st, const
             if (!used) scratch[warp * stride + q] = 0.f;
         }
     }
-    __syncthreads();
-    for (int q = threadIdx.x; q < C::NPART; q += blockDim.x) {
-        float s = 0.f;
-        for (int w = 0; w < nwarps; w++) s += scratch[w * stride + q];
-        const int p = q < C::NB * 16 ? (q % C::NB) * 16 + q / C::NB : q;
-        if (out_is_global) __stcg(out + p, s);
-        else out[p] = s;
-    }
+}
+// (2) after the barrier: element q of the rows summed over the first nw warps in fixed order; p = its position in the
+// partial vector (the tile-major order is restored here)
+template <class C>
+__device__ __forceinline__ float cta_reduce_sum(const float* scratch, int stride, int nw, int q, int& p)
+{
+    float s = 0.f;
+    for (int w = 0; w < nw; w++) s += scratch[w * stride + q];
+    p = q < C::NB * 16 ? (q % C::NB) * 16 + q / C::NB : q;
+    return s;
+}
+
+// the same by position p of the partial vector (inverse of the element-major scratch order)
+template <class C>
+__device__ __forceinline__ float cta_reduce_sum_at(const float* scratch, int stride, int nw, int p)
+{
+    const int q = p < C::NB * 16 ? (p & 15) * C::NB + (p >> 4) : p;
+    float s = 0.f;
+    for (int w = 0; w < nw; w++) s += scratch[w * stride + q];
+    return s;
 }
 
 }  // namespace eh

@@ -48,19 +48,16 @@ struct EngFfma {
         s.la.zero();
     }
     // prefetch the records of chunk `chunk`: lane l owns samples SPL*l .. SPL*l + SPL - 1 of the chunk
-    __device__ __forceinline__ static void fetch(State& s, const float4* rec, const int* idx, long long rec_base, int B,
-                                                 int chunk, int nchunks, int lane)
+    __device__ __forceinline__ static void fetch(State& s, const FetchArgs& fa, int chunk, int lane)
     {
 #pragma unroll
         for (int sp = 0; sp < C::SPL; sp++) {
             const int smp = chunk * CHUNK + C::SPL * lane + sp;
-            const bool v = chunk < nchunks && smp < B;
+            const bool v = chunk < fa.nchunks && smp < fa.B;
             s.valid[sp] = v;
-            long long i = rec_base + smp;
-            if (idx && v) i = idx[smp];
 #pragma unroll
             for (int q = 0; q < C::R4 / 4; q++)
-                s.r[sp][q] = v ? __ldg(rec + i * (C::R4 / 4) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                s.r[sp][q] = v ? fetch_rec4<C::R4 / 4>(fa, smp, q) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
     // process the prefetched chunk; `next` (chunk index, may be past the end) is prefetched right after the
@@ -80,7 +77,7 @@ struct EngFfma {
             }
             valid[sp] = s.valid[sp];
         }
-        fetch(s, fa.rec, fa.idx, fa.rec_base, fa.B, next, fa.nchunks, lane);
+        fetch(s, fa, next, lane);
         chunk_sample_phase<C>(rec, valid, sW, sS, stage, lane, slot, loss_kind, cx, s.st, s.la);
         __syncwarp();
         if constexpr (DW_MMA) chunk_dw_phase_mma<C>(stage, lane, stage + C::STAGE_FLOATS, s.nacc == 0);
@@ -88,9 +85,22 @@ struct EngFfma {
         s.nacc++;
         __syncwarp();
     }
-    __device__ __forceinline__ static void reduce(State& s, float* scratch, float* out, int out_is_global)
+    // the warps' reduction rows live next to (not inside) their staging tiles
+    static constexpr bool SCRATCH_ALIASES_STAGE = false;
+    // per warp, before the CTA barrier
+    __device__ __forceinline__ static void reduce_prepare(State& s, float* work)
     {
-        cta_reduce<C>(s.nacc, s.st, s.la, scratch + C::STAGE_FLOATS, STAGE_FLOATS, out, out_is_global);
+        cta_reduce_prepare<C>(s.nacc, s.st, s.la, work + C::STAGE_FLOATS, STAGE_FLOATS);
+    }
+    // after the barrier: element q summed over the first nw warps; p = its position in the partial vector
+    __device__ __forceinline__ static float reduce_sum(const float* work, int nw, int q, int& p)
+    {
+        return cta_reduce_sum<C>(work + C::STAGE_FLOATS, STAGE_FLOATS, nw, q, p);
+    }
+    // the same addressed by the position p in the partial vector
+    __device__ __forceinline__ static float reduce_sum_at(const float* work, int nw, int p)
+    {
+        return cta_reduce_sum_at<C>(work + C::STAGE_FLOATS, STAGE_FLOATS, nw, p);
     }
 };
 

@@ -107,8 +107,7 @@ struct EngMma {
         for (int i = 0; i < NPS; i++) s.gphi[i] = 0.f;
     }
 
-    __device__ __forceinline__ static void fetch(State& s, const float4* rec, const int* idx, long long rec_base, int B,
-                                                 int chunk, int nchunks, int lane)
+    __device__ __forceinline__ static void fetch(State& s, const FetchArgs& fa, int chunk, int lane)
     {
         const int g = lane >> 2;
 #pragma unroll
@@ -116,13 +115,11 @@ struct EngMma {
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const int smp = chunk * CHUNK + tile * 16 + g + 8 * h;
-                const bool v = chunk < nchunks && smp < B;
-                long long i = rec_base + smp;
-                if (idx && v) i = idx[smp];
+                const bool v = chunk < fa.nchunks && smp < fa.B;
                 s.valid[tile][h] = v;
 #pragma unroll
                 for (int q = 0; q < C::R4 / 4; q++)
-                    s.r[tile][h][q] = v ? __ldg(rec + i * (C::R4 / 4) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    s.r[tile][h][q] = v ? fetch_rec4<C::R4 / 4>(fa, smp, q) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
     }
     // 3xTF32 product with a full-precision weight fragment kept in registers
@@ -213,6 +210,7 @@ struct EngMma {
                     zo[h][o] = v + s.bo[o];
                 }
             // ---- process parameters, physics, masked residual, seeds (per sample) ----
+            cx.wait_phi();
             float dz[2][NOUT];
 #pragma unroll
             for (int h = 0; h < 2; h++) {
@@ -317,7 +315,7 @@ struct EngMma {
             }
             __syncwarp();
         }
-        fetch(s, fa.rec, fa.idx, fa.rec_base, fa.B, next, fa.nchunks, lane);
+        fetch(s, fa, next, lane);
     }
 
     // sum over the 8 row groups (lanes with equal t)
@@ -329,10 +327,12 @@ struct EngMma {
         return v;
     }
 
-    // lane accumulators -> scratch[warp][NPART] -> fixed-order sum over warps -> out[NPART]
-    __device__ __forceinline__ static void reduce(State& s, float* scratch, float* out, int out_is_global)
+    // the [nwarps][NPART] reduction scratch overlays the staging tiles: a CTA barrier is needed before reduce_prepare
+    static constexpr bool SCRATCH_ALIASES_STAGE = true;
+    // lane accumulators -> scratch[warp][NPART] (per warp, before the CTA barrier)
+    __device__ __forceinline__ static void reduce_prepare(State& s, float* scratch)
     {
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         const int g = lane >> 2, t = lane & 3;
         float* sc = scratch + warp * NPART;
 #pragma unroll
@@ -374,13 +374,19 @@ struct EngMma {
             float v = i < NPS ? gsum(s.gphi[i < NPS ? i : 0]) : 0.f;
             if (lane == 0) sc[O_GP + i] = v;
         }
-        __syncthreads();
-        for (int p = threadIdx.x; p < NPART; p += blockDim.x) {
-            float sum = 0.f;
-            for (int w = 0; w < nwarps; w++) sum += scratch[w * NPART + p];
-            if (out_is_global) __stcg(out + p, sum);
-            else out[p] = sum;
-        }
+    }
+    // after the barrier: element p summed over the first nw warps in fixed order (the partial vector is in flat order)
+    __device__ __forceinline__ static float reduce_sum(const float* scratch, int nw, int q, int& p)
+    {
+        float sum = 0.f;
+        for (int w = 0; w < nw; w++) sum += scratch[w * NPART + q];
+        p = q;
+        return sum;
+    }
+    __device__ __forceinline__ static float reduce_sum_at(const float* scratch, int nw, int p)
+    {
+        int dummy;
+        return reduce_sum(scratch, nw, p, dummy);
     }
 };
 

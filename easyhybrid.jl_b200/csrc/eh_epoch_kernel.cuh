@@ -1,18 +1,25 @@
 // eh_epoch_kernel.cuh -- the persistent form of the training loop: MANY optimiser steps in one
-// launch (one CTA per SM, thread-block clusters), replacing run_epoch!
-// (src/training/epoch.jl:13-33) as a whole.  Per step every CTA
-//   1. runs the fused forward/backward on its chunks (eh_chunk.cuh) with the weight image it keeps
-//      in shared memory,
-//   2. reduces its lane tiles to one partial vector in shared memory,
-//   3. takes part in a three-hop grid-wide sum (cluster leader over DSMEM -> one vector per cluster
-//      in L2 -> every CTA sums a share of them -> shares exchanged over DSMEM); every slot is an
-//      8-byte {value, step tag} pair that validates itself, so there is no grid barrier, no fence
-//      and no atomic anywhere: readers poll exactly the slots they need,
-//   4. applies the optimiser REDUNDANTLY to its own copy of theta / m / v in shared memory,
-//      patching its weight image in place.
-// All CTAs execute the same float operations in the same order, so the replicas stay bit-identical
-// and nothing has to be broadcast back.  Compared with one launch per step this removes two kernel
-// launches, the dependent-load prologue and the single-CTA second pass from every step.
+// launch (one CTA per SM, cooperative launch), replacing run_epoch! (src/training/epoch.jl:13-33) as a whole.
+//
+// CTA layout: `wcomp` compute warps + ONE service warp (the last one).  Per step
+//   1. the service warp prefetches the CTA's records of the NEXT step with one cp.async.bulk (TMA) into a
+//      double-buffered shared-memory tile (batch-contiguous records: the staged epoch stream or host-batch slots;
+//      collect_dim_data, epoch.jl:1-11); with an index stream (gather mode) lanes prefetch their records themselves;
+//   2. the compute warps run the fused forward/backward on the CTA's contiguous chunk range (eh_chunk.cuh) with the
+//      weight image the CTA keeps in shared memory;
+//   3. grid-wide sum of the CTA partials as a reduce-scatter + all-gather through L2, no barrier, no fence, no atomic:
+//      every slot is an 8-byte {value, step tag} pair that validates itself, readers poll exactly the slots they need.
+//        A  every CTA publishes its partial vector (476 slots for [2-16-16-1]);
+//        B  the vector is cut into slices of 4 elements, slice j belongs to CTA j mod G: the owner sums the slice over
+//           all CTAs in a fixed order (lane groups + shuffle tree) -- with several GPUs it also swaps the slice sums with
+//           its peers over NVLink here (rank-ordered sum) -- and publishes the totals;
+//        C  every thread that owns a parameter polls the one total it needs;
+//      each total is computed by exactly ONE CTA, so all CTAs (and all GPUs: same rank order) see identical bits;
+//   4. every CTA applies the optimiser REDUNDANTLY to its own copy of theta / m / v in shared memory and patches its
+//      weight image in place: nothing is broadcast back.  The global physical parameters (phi) live on the service
+//      warp: their long tail (sigmoid, squashing, double-precision log2) runs while the compute warps have already
+//      started the next step; consumers wait on a shared-memory flag right before they need those scalars.
+// Two CTA barriers per step (after the compute phase, after the optimiser).
 #pragma once
 #include "eh_step_kernel.cuh"
 
@@ -37,12 +44,15 @@ struct EpochArgs {
     const float* pspan;        // [nflat]
     const int* slot_of_flat;   // [nflat] phi entries: canonical slot (for the tail), -1 otherwise
     const float* bscal;        // [nb][BS_STRIDE]
-    uint2* pbuf;               // [2][nclusters][npartp] published cluster vectors, {value bits, step tag} slots
+    uint2* pbuf;               // [2][pbuf_rows][npartp] {value bits, step tag}: rows 0..G-1 CTA partials, the last EH_TOT_REPL rows totals
+    int pbuf_rows;
     unsigned tag_base;         // steps run by earlier launches of this ctx (tags are absolute, never reused)
     float* stats_out;          // [nsteps][MAXT] reduced loss sums
     int npartp;                // padded partial length (multiple of 4)
-    int work_floats;           // size of the per-CTA work region (staging / scratch / vector landing zone)
-    int csize;                 // cluster size (1, 2, 4, 8)
+    int work_floats;           // size of the per-CTA work region (staging tiles / reduction rows)
+    int wcomp;                 // compute warps (blockDim.x / 32 - 1)
+    int pg_log2;               // phase B: lanes per element = 1 << pg_log2
+    int tile_floats;           // floats per record-tile buffer (0: no TMA staging)
     int T, agg_mean;
     int loss_kind[MAXT];
     PSlot slot[MAXPS];
@@ -72,147 +82,141 @@ __device__ __forceinline__ uint2 ld_volatile_v2(const uint2* p)
     asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
     return v;
 }
+constexpr int EH_TOT_REPL = 8;   // replicas of the published totals (the last rows of EpochArgs::pbuf)
 constexpr unsigned EH_SPIN_LIMIT = 1u << 26;  // ~seconds; then give up loudly instead of hanging the GPU
 
-__device__ __forceinline__ void cluster_sync_all()
+// Slot pairs that live in this GPU's L2 use WEAK cache-global accesses (measured, tools/ubench_exchange.cu: volatile /
+// relaxed accesses are handled one transaction at a time per SM -- 9.8 us per exchange of 148 CTAs against 5.1 us with
+// ld/st.global.cg, 3.0 us when every thread issues exactly one load).  L2 is the point of coherence, the asm is volatile
+// (never hoisted or merged), and every slot validates itself through its tag.
+__device__ __forceinline__ void st_cg_v4(uint2* p, unsigned x0, unsigned t0, unsigned x1, unsigned t1)
 {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    asm volatile("st.global.cg.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(x0), "r"(t0), "r"(x1), "r"(t1) : "memory");
 }
-
-// shared-memory window address of `local` in CTA `rank` of this cluster
-__device__ __forceinline__ unsigned dsmem_addr(const void* local, unsigned rank)
+__device__ __forceinline__ uint4 ld_cg_v4(const uint2* p)
 {
-    unsigned a = (unsigned)__cvta_generic_to_shared(local), ra;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(rank));
-    return ra;
+    uint4 v;
+    asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
 }
-__device__ __forceinline__ void st_dsmem_v2(unsigned addr, unsigned x, unsigned y)
+// poll a pair of slots (weak loads) until both carry the tag of this step
+__device__ __forceinline__ uint4 poll_pair_cg(const uint2* p, unsigned tag, unsigned* err)
 {
-    asm volatile("st.relaxed.cluster.shared::cluster.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
+    uint4 v = ld_cg_v4(p);
+    unsigned spins = 0;
+    while (v.y != tag || v.w != tag) {
+        if (++spins > EH_SPIN_LIMIT) { *err = 1; break; }
+        v = ld_cg_v4(p);
+    }
+    return v;
 }
-__device__ __forceinline__ uint2 ld_shared_v2(const uint2* p)
+// two neighbouring slots at once (16-byte aligned): {value0, tag0, value1, tag1}
+__device__ __forceinline__ void st_volatile_v4(uint2* p, unsigned x0, unsigned t0, unsigned x1, unsigned t1)
 {
-    uint2 v;
-    unsigned a = (unsigned)__cvta_generic_to_shared(p);
-    asm volatile("ld.relaxed.cluster.shared::cta.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(x0), "r"(t0), "r"(x1), "r"(t1) : "memory");
+}
+__device__ __forceinline__ uint4 ld_volatile_v4(const uint2* p)
+{
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
 }
 
-// ---- grid-wide sum of the CTA partials: three self-validating hops, no barrier, no fence, no atomic.
-// Every slot travels as an 8-byte {value, step tag} pair (single-copy atomic), so a reader simply polls the
-// slot it needs until the tag of this step shows up.  Thread p owns element p on every hop.
-//   hop 1  non-leader CTAs push their partial into the cluster leader's shared memory (DSMEM store);
-//          the leader adds the ranks in order and publishes ONE vector per cluster in L2;
-//   hop 2  CTA rank r of every cluster sums its contiguous share of the NC published vectors out of L2;
-//   hop 3  the cs shares are pushed to every CTA of the cluster (DSMEM) and added in rank order.
-// Every cluster uses the same grouping and order, so all CTAs of the grid hold bit-identical totals.
-// Kept out of line: its registers must not weigh on the allocation of the compute phase.
-static __device__ __noinline__ void grid_sum(const float* cpart, float* red, uint2* box1, uint2* box3, uint2* pbuf_par, int npartp,
-                                      int npart, int cs, int NC, unsigned tag, unsigned* err, long long* dbg)
+// poll a pair of slots until both carry the tag of this step
+__device__ __forceinline__ uint4 poll_pair(const uint2* p, uint4 v, unsigned tag, unsigned* err)
 {
-    if (gridDim.x == 1) {   // small batches run in ONE CTA: its partial is the total
-        for (int p = threadIdx.x; p < npart; p += blockDim.x) red[p] = cpart[p];
-        return;
+    unsigned spins = 0;
+    while (v.y != tag || v.w != tag) {
+        if (++spins > EH_SPIN_LIMIT) { *err = 1; break; }
+        v = ld_volatile_v4(p);
     }
-    const unsigned crank = (unsigned)(blockIdx.x % cs);
-    const int cid = blockIdx.x / cs;
-    {
-        uint2* pub = pbuf_par + (size_t)cid * npartp;
-        if (crank != 0) {
-            const unsigned dst = dsmem_addr(box1 + (size_t)(crank - 1) * npartp, 0u);
-            for (int p = threadIdx.x; p < npart; p += blockDim.x) st_dsmem_v2(dst + 8u * (unsigned)p, __float_as_uint(cpart[p]), tag);
-        } else {
-            for (int p = threadIdx.x; p < npart; p += blockDim.x) {
-                float sum = cpart[p];
-                for (int rk = 1; rk < cs; rk++) {
-                    const uint2* slot = box1 + (size_t)(rk - 1) * npartp + p;
-                    uint2 v = ld_shared_v2(slot);
-                    unsigned spins = 0;
-                    while (v.y != tag) {
-                        if (++spins > EH_SPIN_LIMIT) { *err = 1; break; }
-                        v = ld_shared_v2(slot);
-                    }
-                    sum += __uint_as_float(v.x);
-                }
-                st_volatile_v2(pub + p, __float_as_uint(sum), tag);
-            }
-        }
-    }
-    if (dbg && threadIdx.x == 0) dbg[4] = clock64();
-    {
-        const uint2* src = pbuf_par;
-        const int per = (NC + cs - 1) / cs;
-        const int c0 = (int)crank * per;
-        const int c1 = c0 + per < NC ? c0 + per : NC;
-        constexpr int U = 12;
-        for (int p = threadIdx.x; p < npart; p += blockDim.x) {
-            float sum = 0.f;
-            for (int c = c0; c < c1; c += U) {
-                uint2 t[U];
-#pragma unroll
-                for (int u = 0; u < U; u++)
-                    if (c + u < c1) t[u] = ld_volatile_v2(src + (size_t)(c + u) * npartp + p);
-#pragma unroll
-                for (int u = 0; u < U; u++)
-                    if (c + u < c1) {
-                        unsigned spins = 0;
-                        while (t[u].y != tag) {
-                            if (++spins > EH_SPIN_LIMIT) { *err = 1; break; }
-                            t[u] = ld_volatile_v2(src + (size_t)(c + u) * npartp + p);
-                        }
-                        sum += __uint_as_float(t[u].x);
-                    }
-            }
-            if (cs > 1) {
-                for (int rk = 0; rk < cs; rk++)
-                    st_dsmem_v2(dsmem_addr(box3 + (size_t)crank * npartp + p, (unsigned)rk), __float_as_uint(sum), tag);
-            } else {
-                red[p] = sum;
-            }
-        }
-    }
-    if (dbg && threadIdx.x == 0) dbg[5] = clock64();
-    if (cs > 1) {
-        for (int p = threadIdx.x; p < npart; p += blockDim.x) {
-            float sum = 0.f;
-            for (int rk = 0; rk < cs; rk++) {
-                const uint2* slot = box3 + (size_t)rk * npartp + p;
-                uint2 v = ld_shared_v2(slot);
-                unsigned spins = 0;
-                while (v.y != tag) {
-                    if (++spins > EH_SPIN_LIMIT) { *err = 1; break; }
-                    v = ld_shared_v2(slot);
-                }
-                sum += __uint_as_float(v.x);
-            }
-            red[p] = sum;
-        }
-    }
+    return v;
 }
 
-// floats of shared memory besides weights / scalars / work region: cpart + red (padded partial vectors)
-// + the two {value, tag} inboxes (cs-1 and cs vectors of 8-byte slots) + theta, m, v copies
-// + tables (pmap, 2 cells, span, slot)
-__host__ __device__ constexpr int epoch_extra_floats(int npartp, int nflat, int cs)
+// poll a {value, tag} slot until the tag of this step shows up
+__device__ __forceinline__ float poll_slot(const uint2* p, unsigned tag, unsigned* err)
 {
-    return (2 + 2 * (2 * cs - 1)) * npartp + 8 * rup4(nflat);
+    uint2 v = ld_volatile_v2(p);
+    unsigned spins = 0;
+    while (v.y != tag) {
+        if (++spins > EH_SPIN_LIMIT) { *err = 1; break; }
+        v = ld_volatile_v2(p);
+    }
+    return __uint_as_float(v.x);
+}
+
+// named barriers: the compute warps wait (sync), the service warp only announces itself (arrive)
+__device__ __forceinline__ void bar_sync_id(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void bar_arrive_id(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// ---- mbarrier + bulk copy (TMA) for the record tiles ----
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded: a bulk copy that never lands raises the error flag instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity, unsigned* err)
+{
+    unsigned spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > (1u << 22)) { *err = 1; break; }
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+// contiguous chunk range of CTA `bid`: chunks [c0, c0 + cnt) of a batch with nchunks chunks
+__device__ __forceinline__ void cta_chunk_range(int nchunks, int G, int bid, int& c0, int& cnt)
+{
+    const int base = nchunks / G, rem = nchunks - base * G;
+    cnt = base + (bid < rem ? 1 : 0);
+    c0 = bid * base + (bid < rem ? bid : rem);
+}
+
+// floats of shared memory besides weights / scalars / work region: red (padded partial vector; single-CTA grids only),
+// theta, m, v copies + tables (pmap, 2 cells, span, slot), two record tiles, two mbarriers + the phi flag
+// + xbuf: the values an owner CTA collects for its slices, [row][half][G] float2 (at most NSL + G rows x peers)
+__host__ __device__ constexpr int epoch_xbuf_floats(int npartp, int G) { return 4 * (npartp / 4 + G) + 8; }
+__host__ __device__ constexpr int epoch_extra_floats(int npartp, int nflat, int tile_floats, int G)
+{
+    return npartp + 8 * rup4(nflat) + 2 * rup4(tile_floats) + 8 + epoch_xbuf_floats(npartp, G);
 }
 
 template <class E>
-__global__ void __launch_bounds__(E::MAX_WARPS * 32, 1) k_epoch(const EpochArgs a)
+__global__ void __launch_bounds__((E::MAX_WARPS + 1) * 32 > 512 ? 512 : (E::MAX_WARPS + 1) * 32, 1) k_epoch(const EpochArgs a)
 {
     using C = typename E::Cfg;
     extern __shared__ float4 smem4[];
     float* sW = reinterpret_cast<float*>(smem4);
     float* sS = sW + rup4(C::NW);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    float* stage0 = sS + SS_FLOATS;                      // work region: staging tiles / reduction scratch / vectors
-    float* stage = stage0 + warp * E::STAGE_FLOATS;
-    float* cpart = stage0 + a.work_floats;               // [npartp] this CTA's partial vector
-    float* red = cpart + rup4(E::NPART);                 // [npartp] fully reduced vector
-    uint2* box1 = reinterpret_cast<uint2*>(red + rup4(E::NPART));  // [cs-1][npartp] {value, tag}: partials pushed to a cluster leader
-    uint2* box3 = box1 + (size_t)(a.csize - 1) * rup4(E::NPART);   // [cs][npartp] {value, tag}: the cluster's shares of the grid-wide sum
-    float* s_th = reinterpret_cast<float*>(box3 + (size_t)a.csize * rup4(E::NPART));  // [nflat] replicated parameters
+    const int wcomp = a.wcomp;
+    const bool service = warp == nwarps - 1;
+    float* stage0 = sS + SS_FLOATS;                      // work region: staging tiles / reduction rows
+    float* stage = stage0 + (service ? 0 : warp) * E::STAGE_FLOATS;
+    float* red = stage0 + a.work_floats;                 // [npartp] fully reduced vector (gridDim.x == 1 only)
+    float* s_th = red + a.npartp;                        // [nflat] replicated parameters
     float* s_m = s_th + rup4(a.nflat);
     float* s_v = s_m + rup4(a.nflat);
     int* t_pmap = reinterpret_cast<int*>(s_v + rup4(a.nflat));
@@ -220,9 +224,13 @@ __global__ void __launch_bounds__(E::MAX_WARPS * 32, 1) k_epoch(const EpochArgs 
     int* t_cell1 = t_cell0 + rup4(a.nflat);
     int* t_slot = t_cell1 + rup4(a.nflat);
     float* t_span = reinterpret_cast<float*>(t_slot + rup4(a.nflat));
-    const int G = gridDim.x;
-    const int cs = a.csize;
-    const int NC = G / cs;                               // clusters = published vectors per step
+    float4* tile0 = reinterpret_cast<float4*>(t_span + rup4(a.nflat));   // [2][tile_floats]
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(reinterpret_cast<float*>(tile0) + 2 * rup4(a.tile_floats));  // [2]
+    unsigned* phi_flag = reinterpret_cast<unsigned*>(mbar + 2);
+    float2* xbuf = reinterpret_cast<float2*>(phi_flag + 4);   // [nown][2][G] values collected by this CTA as a slice owner (sized for G <= number of SMs)
+    const int G = gridDim.x, bid = blockIdx.x;
+    const bool tiles = a.tile_floats > 0;
+    constexpr int R44 = C::R4 / 4;
 
     for (int p = threadIdx.x; p < a.nflat; p += blockDim.x) {
         s_th[p] = a.pblock[p];
@@ -241,14 +249,17 @@ __global__ void __launch_bounds__(E::MAX_WARPS * 32, 1) k_epoch(const EpochArgs 
     }
     float b1t = a.ost->b1t, b2t = a.ost->b2t;
     long long tdone = 0, tskip = 0;
-
-    // inboxes start with tag 0 (never a valid step tag); nobody pushes before everybody has cleared
-    for (int i = threadIdx.x; i < (2 * cs - 1) * rup4(E::NPART); i += blockDim.x) box1[i] = make_uint2(0u, 0u);
-    if (cs > 1) cluster_sync_all(); else __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        *phi_flag = a.tag_base;   // the scalars loaded below belong to "step tag_base"
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
 
     typename E::State st;
-    E::init_warp(st, stage, lane);
+    if (!service) E::init_warp(st, stage, lane);
     load_weights_and_scalars<C>(a.pblock, a.nflat, a.wsrc, nullptr, 0, sW, sS);
+    __syncthreads();   // the batch-scalar cells are rewritten by other threads below (store_bs)
 
     PmCtx cx;
     cx.pms = sS + SS_PMS;
@@ -256,21 +267,47 @@ __global__ void __launch_bounds__(E::MAX_WARPS * 32, 1) k_epoch(const EpochArgs 
     cx.prog = a.prog;
     cx.scale_rt = a.scale_rt;
     cx.uniform_mask = 0;
+    cx.phi_flag = phi_flag;
+    cx.phi_want = a.tag_base;
 #pragma unroll
     for (int s = 0; s < MAXPS; s++)
         if (s >= C::NPS || a.slot[s].role != ROLE_NEURAL) cx.uniform_mask |= 1u << s;
 
-    const int GW = G * nwarps;
-    // chunk -> warp assignment interleaves CTAs so that a ragged chunk count spreads over all SMs
-    const int gw = warp * G + blockIdx.x;
     // batch of the current step, tracked incrementally (no 64-bit modulo in the loop)
     int bcur = (int)(a.first_step % a.nb);
     const int Blast = (int)(a.n - (long long)(a.nb - 1) * a.B);  // size of the (possibly partial) last batch
-    {
-        const long long b = bcur;
-        const int Bk = bcur == a.nb - 1 ? Blast : a.B;
-        E::fetch(st, a.rec, a.idx ? a.idx + b * a.B : nullptr, a.idx ? 0 : b * a.B, Bk, gw, (Bk + E::CHUNK - 1) / E::CHUNK, lane);
-    }
+    auto batch_size = [&](int b) { return b == a.nb - 1 ? Blast : a.B; };
+    // the service warp's lane 0 stages the CTA's records of batch b into tile buffer `buf` (one bulk copy; an empty
+    // range still completes the mbarrier phase so that the parities keep counting steps)
+    auto issue_tile = [&](int b, int buf) {
+        const int Bk = batch_size(b);
+        int c0, cnt;
+        cta_chunk_range((Bk + E::CHUNK - 1) / E::CHUNK, G, bid, c0, cnt);
+        const long long s0 = (long long)c0 * E::CHUNK;
+        long long s1 = s0 + (long long)cnt * E::CHUNK;
+        if (s1 > Bk) s1 = Bk;
+        if (s1 > s0) {
+            const unsigned bytes = (unsigned)(s1 - s0) * (unsigned)(C::R4 * 4);
+            mbar_expect_tx(&mbar[buf], bytes);
+            bulk_g2s(tile0 + (size_t)buf * (rup4(a.tile_floats) / 4), a.rec + ((long long)b * a.B + s0) * R44, bytes, &mbar[buf]);
+        } else {
+            mbar_arrive(&mbar[buf]);
+        }
+    };
+    auto fetch_args = [&](int b, int buf) {
+        FetchArgs fa;
+        const int Bk = batch_size(b);
+        fa.rec = a.rec;
+        fa.idx = a.idx ? a.idx + (long long)b * a.B : nullptr;
+        fa.rec_base = a.idx ? 0 : (long long)b * a.B;
+        fa.B = Bk;
+        fa.nchunks = (Bk + E::CHUNK - 1) / E::CHUNK;
+        int c0, cnt;
+        cta_chunk_range(fa.nchunks, G, bid, c0, cnt);
+        fa.tile = tiles ? tile0 + (size_t)buf * (rup4(a.tile_floats) / 4) : nullptr;
+        fa.tile_s0 = c0 * E::CHUNK;
+        return fa;
+    };
     // per-batch scalars of the coming step, prefetched one step ahead (a dependent global load otherwise)
     float pre_bs = 0.f;
     auto prefetch_bs = [&](int batch) {
@@ -280,87 +317,148 @@ __global__ void __launch_bounds__(E::MAX_WARPS * 32, 1) k_epoch(const EpochArgs 
             pre_bs = a.use_bn ? bs[BS_BN + threadIdx.x - MAXT] : (((threadIdx.x - MAXT) & 1) ? 1.f : 0.f);
         else if (threadIdx.x >= 28 && threadIdx.x < 28 + MAXT) pre_bs = bs[BS_N + threadIdx.x - 28];
     };
+    // ... and moved into shared memory for step `s` (after the compute phase of the step before has ended)
+    auto store_bs = [&](int s) {
+        if (threadIdx.x < MAXT) sS[SS_C + threadIdx.x] = pre_bs;
+        else if (threadIdx.x < MAXT + 2 * C::P) sS[SS_BN + threadIdx.x - MAXT] = pre_bs;
+        else if (threadIdx.x >= 28 && threadIdx.x < 28 + MAXT) sS[SS_NV2 + (s & 1) * MAXT + threadIdx.x - 28] = pre_bs;
+    };
     prefetch_bs(bcur);
+    store_bs(0);
+    __syncthreads();   // mbarriers initialised, weights / scalars / tables in place
+    if (tiles && service && lane == 0) issue_tile(bcur, 0);
+    if (a.nsteps > 1) prefetch_bs(bcur + 1 == a.nb ? 0 : bcur + 1);
+    if (!tiles && !service) {
+        const FetchArgs f0 = fetch_args(bcur, 0);
+        int c0, cnt;
+        cta_chunk_range(f0.nchunks, G, bid, c0, cnt);
+        E::fetch(st, f0, warp < cnt ? c0 + warp : f0.nchunks, lane);
+    }
 #define EH_STAMP(slot)                                                                      \
-    if (a.dbg && threadIdx.x == 0) a.dbg[((size_t)s * G + blockIdx.x) * 32 + (slot)] = clock64();
+    if (a.dbg && threadIdx.x == 0) a.dbg[((size_t)s * G + bid) * 32 + (slot)] = clock64();
+#define EH_STAMP_SVC(slot)                                                                  \
+    if (a.dbg && service && lane == 0) a.dbg[((size_t)s * G + bid) * 32 + (slot)] = clock64();
+
+    const int NSL = a.npartp / 4;                        // slices of the (padded) partial vector
+    const int nown = (NSL - bid + G - 1) / G;            // slices owned by this CTA (bid, bid + G, ...)
+    const int ncomp_threads = wcomp * 32;
 
     for (int s = 0; s < a.nsteps; s++) {
         EH_STAMP(0)
-        const long long b = bcur;
         const int bnext = bcur + 1 == a.nb ? 0 : bcur + 1;
-        const int Bk = bcur == a.nb - 1 ? Blast : a.B;
-        const int nchunks = (Bk + E::CHUNK - 1) / E::CHUNK;
         const int par = s & 1;
-        if (threadIdx.x < MAXT) sS[SS_C + threadIdx.x] = pre_bs;
-        else if (threadIdx.x < MAXT + 2 * C::P) sS[SS_BN + threadIdx.x - MAXT] = pre_bs;
-        else if (threadIdx.x >= 28 && threadIdx.x < 28 + MAXT) {
-            sS[SS_NV + threadIdx.x - 28] = pre_bs;
-            // second copy by step parity for the update phase: sS[SS_NV] is rewritten at the top of the next
-            // step, which a fast warp may reach while a slow one is still in this step's update
-            sS[SS_NV2 + par * MAXT + threadIdx.x - 28] = pre_bs;
-        }
-        __syncthreads();
-        if (s + 1 < a.nsteps) prefetch_bs(bnext);
-        EH_STAMP(1)
+        const unsigned tag = a.tag_base + (unsigned)s + 1u;
+        uint2* part = a.pbuf + (size_t)par * a.pbuf_rows * a.npartp;
+        // the totals are published EH_TOT_REPL times (rows pbuf_rows - R ..): every CTA polls replica bid % R, so that at most
+        // G / R CTAs poll the same L2 lines
+        uint2* tot = part + (size_t)(a.pbuf_rows - EH_TOT_REPL) * a.npartp;
+        const uint2* mytot = tot + (size_t)(bid % EH_TOT_REPL) * a.npartp;
 
-        E::step_begin(st, sW, lane);
-        const FetchArgs fa{a.rec, a.idx ? a.idx + b * a.B : nullptr, a.idx ? 0 : b * a.B, Bk, nchunks};
-        // the records this warp needs first in the NEXT step are prefetched while it computes its last chunk of this
-        // step (index load + dependent record gather = two DRAM latencies, hidden behind ~12 000 cycles of compute
-        // instead of the much shorter exchange)
-        const long long b2 = bnext;
-        const int Bk2 = bnext == a.nb - 1 ? Blast : a.B;
-        const FetchArgs fn{a.rec, a.idx ? a.idx + b2 * a.B : nullptr, a.idx ? 0 : b2 * a.B, Bk2,
-                           s + 1 < a.nsteps ? (Bk2 + E::CHUNK - 1) / E::CHUNK : 0};
-        for (int chunk = gw; chunk < nchunks; chunk += GW) {
-            const bool last = chunk + GW >= nchunks;
-            E::chunk(st, last ? fn : fa, last ? gw : chunk + GW, sW, sS, stage, lane, a.slot, a.loss_kind, cx);
+        // ---- compute phase ----
+        if (service) {
+            // the tile of the next step: its buffer was last read in the compute phase of step s - 1
+            if (tiles && lane == 0 && s + 1 < a.nsteps) issue_tile(bnext, par ^ 1);
+        } else {
+            const FetchArgs fa = fetch_args(bcur, par);
+            const FetchArgs fn = fetch_args(bnext, par ^ 1);
+            int c0, cnt, n0, ncnt;
+            cta_chunk_range(fa.nchunks, G, bid, c0, cnt);
+            cta_chunk_range(fn.nchunks, G, bid, n0, ncnt);
+            // first chunk of this warp in the next step (gather mode prefetches it during the last chunk of this step:
+            // index load + dependent record gather = two DRAM latencies, hidden behind the compute)
+            const int nfirst = (s + 1 < a.nsteps && warp < ncnt) ? n0 + warp : fn.nchunks;
+            E::step_begin(st, sW, lane);
+            if (tiles) {
+                mbar_wait(&mbar[par], (unsigned)(s >> 1) & 1u, a.err);
+                E::fetch(st, fa, warp < cnt ? c0 + warp : fa.nchunks, lane);
+            }
+            cx.phi_want = a.tag_base + (unsigned)s;
+            for (int chunk = c0 + warp; chunk < c0 + cnt; chunk += wcomp) {
+                const bool last = chunk + wcomp >= c0 + cnt;
+                if (last && !tiles) E::chunk(st, fn, nfirst, sW, sS, stage, lane, a.slot, a.loss_kind, cx);
+                else E::chunk(st, fa, last ? fa.nchunks : chunk + wcomp, sW, sS, stage, lane, a.slot, a.loss_kind, cx);
+            }
+            if (a.dbg && lane == 0) a.dbg[((size_t)s * G + bid) * 32 + 8 + warp] = clock64();
+            // a warp without a chunk in this step still has to fetch its first sample of the next one
+            if (!tiles && warp >= cnt) E::fetch(st, fn, nfirst, lane);
+            if (!E::SCRATCH_ALIASES_STAGE) E::reduce_prepare(st, stage0);
         }
-        if (a.dbg && lane == 0) a.dbg[((size_t)s * G + blockIdx.x) * 32 + 8 + warp] = clock64();
-        // a warp without a chunk in this step still has to fetch its first sample of the next one
-        if (gw >= nchunks) E::fetch(st, fn.rec, fn.idx, fn.rec_base, fn.B, gw, fn.nchunks, lane);
+        EH_STAMP(1)
+        if (E::SCRATCH_ALIASES_STAGE) {
+            __syncthreads();   // every warp is done with its staging tile; the work region becomes the reduction rows
+            if (!service) E::reduce_prepare(st, stage0);
+        }
         __syncthreads();
         EH_STAMP(2)
-        // CTA partial -> cpart (the scratch of cta_reduce aliases the staging tiles)
-        E::reduce(st, stage0, cpart, 0);
-        __syncthreads();
+
+        // ---- A: CTA partial, published in vector order as 16-byte {value, tag, value, tag} pairs (coalesced) ----
+        for (int k = threadIdx.x; k < a.npartp / 2; k += blockDim.x) {
+            const float v0 = 2 * k < E::NPART ? E::reduce_sum_at(stage0, wcomp, 2 * k) : 0.f;           // (padding slots carry zeros)
+            const float v1 = 2 * k + 1 < E::NPART ? E::reduce_sum_at(stage0, wcomp, 2 * k + 1) : 0.f;
+            if (G == 1) *reinterpret_cast<float2*>(red + 2 * k) = make_float2(v0, v1);
+            else st_cg_v4(part + (size_t)bid * a.npartp + 2 * k, __float_as_uint(v0), tag, __float_as_uint(v1), tag);
+        }
         EH_STAMP(3)
-        // grid-wide sum of the CTA partials (grid_sum above): cpart -> red, identical bits in every CTA
-        grid_sum(cpart, red, box1, box3, a.pbuf + (size_t)par * NC * a.npartp, a.npartp, E::NPART, cs, NC, a.tag_base + (unsigned)s + 1u,
-                 a.err, a.dbg ? a.dbg + ((size_t)s * G + blockIdx.x) * 32 : nullptr);
-        __syncthreads();
-        EH_STAMP(6)
-        if (a.dbg && threadIdx.x == 0) a.dbg[((size_t)s * G + blockIdx.x) * 32 + 27] = clock64();
-        if (a.world > 1) {
-            // ---- fused exchange over NVLink peer memory, LL style: every 8-byte store carries {value, step tag},
-            // so a slot validates itself -- no fences, no separate flags, one-way NVLink latency.  CTA 0 pushes this
-            // GPU's reduced vector into every rank's inbox; every CTA of every GPU polls its own GPU's inbox and sums
-            // the rank vectors in rank order (bitwise identical everywhere).
-            const unsigned tag = a.step_base + (unsigned)s + 1u;
-            if (blockIdx.x == 0) {
-                for (int r = 0; r < a.world; r++) {
-                    uint2* dst = a.inbox_peer[r] + ((size_t)par * a.world + a.rank) * a.npartp;
-                    for (int p = threadIdx.x; p < E::NPART; p += blockDim.x) st_volatile_v2(dst + p, __float_as_uint(red[p]), tag);
-                }
-                __syncthreads();  // red is about to be overwritten below
-            }
-            const uint2* inbox = a.inbox_peer[a.rank] + (size_t)par * a.world * a.npartp;
-            for (int p = threadIdx.x; p < E::NPART; p += blockDim.x) {
-                float sum = 0.f;
-                for (int r = 0; r < a.world; r++) {
-                    uint2 v = ld_volatile_v2(inbox + (size_t)r * a.npartp + p);
-                    unsigned spins = 0;
-                    while (v.y != tag) {
-                        if (++spins > EH_SPIN_LIMIT) { *a.err = 1; break; }
-                        v = ld_volatile_v2(inbox + (size_t)r * a.npartp + p);
-                    }
-                    sum += __uint_as_float(v.x);
-                }
-                red[p] = sum;
+        if (G > 1) {
+            // ---- B: slice owners.  Slice j (4 elements) belongs to CTA j mod G.  Every thread fetches ONE 16-byte pair
+            // {2 elements of one slice of one peer CTA}: item i -> (row, half, peer) = (i / 2G, (i / G) & 1, i % G).
+            const int nitems = 2 * G * nown;
+            for (int i = threadIdx.x; i < nitems; i += blockDim.x) {
+                const int row = i / (2 * G), rem = i - row * 2 * G, half = rem >= G ? 1 : 0, peer = rem - half * G;
+                const uint4 v = poll_pair_cg(part + (size_t)peer * a.npartp + (bid + row * G) * 4 + half * 2, tag, a.err);
+                xbuf[i] = make_float2(__uint_as_float(v.x), __uint_as_float(v.z));
             }
             __syncthreads();
+            // one warp per (row, half): lanes stride over the peers, butterfly, lane 0 publishes the two totals
+            {
+                const unsigned dtag = a.step_base + (unsigned)s + 1u;
+                const int dpar = (int)((a.step_base + (unsigned)s) & 1u);
+                for (int pr = nwarps - 1 - warp; pr < 2 * nown; pr += nwarps) {
+                    EH_STAMP_SVC(24)
+                    const float2* src = xbuf + (size_t)pr * G;
+                    float acc0 = 0.f, acc1 = 0.f;
+                    for (int c = lane; c < G; c += 32) { const float2 v = src[c]; acc0 += v.x; acc1 += v.y; }
+                    for (int o = 16; o > 0; o >>= 1) {
+                        acc0 += __shfl_xor_sync(0xffffffffu, acc0, o);
+                        acc1 += __shfl_xor_sync(0xffffffffu, acc1, o);
+                    }
+                    const int ge = (bid + (pr >> 1) * G) * 4 + (pr & 1) * 2;
+                    if (a.world > 1) {
+                        // ---- fused exchange over NVLink peer memory, LL style: every slot carries {value, step tag}.
+                        // Lane r pushes this GPU's sums into rank r's inbox and polls the slot rank r wrote here; the
+                        // ranks' values are added in RANK ORDER (identical bits on every GPU whatever its grid looks like).
+                        float v0 = 0.f, v1 = 0.f;
+                        if (lane < a.world) {
+                            st_volatile_v4(a.inbox_peer[lane] + ((size_t)dpar * a.world + a.rank) * a.npartp + ge, __float_as_uint(acc0), dtag,
+                                           __float_as_uint(acc1), dtag);
+                            const uint2* in = a.inbox_peer[a.rank] + ((size_t)dpar * a.world + lane) * a.npartp + ge;
+                            const uint4 v = poll_pair(in, ld_volatile_v4(in), dtag, a.err);
+                            v0 = __uint_as_float(v.x);
+                            v1 = __uint_as_float(v.z);
+                        }
+                        acc0 = 0.f; acc1 = 0.f;
+                        for (int r = 0; r < a.world; r++) {
+                            acc0 += __shfl_sync(0xffffffffu, v0, r);
+                            acc1 += __shfl_sync(0xffffffffu, v1, r);
+                        }
+                    }
+                    if (lane < EH_TOT_REPL) st_cg_v4(tot + (size_t)lane * a.npartp + ge, __float_as_uint(acc0), tag, __float_as_uint(acc1), tag);
+                    EH_STAMP_SVC(25)
+                }
+            }
+            // ---- C: every thread fetches ONE pair of totals into shared memory ----
+            for (int k = threadIdx.x; k < a.npartp / 2; k += blockDim.x) {
+                const uint4 v = poll_pair_cg(mytot + 2 * k, tag, a.err);
+                *reinterpret_cast<float2*>(red + 2 * k) = make_float2(__uint_as_float(v.x), __uint_as_float(v.z));
+            }
         }
-        if (a.dbg && threadIdx.x == 0) a.dbg[((size_t)s * G + blockIdx.x) * 32 + 28] = clock64();
+        __syncthreads();   // red holds the grid-wide sums
+        // the service warp owns no weight-image cell: it announces itself at the end-of-step barrier right away, the
+        // compute warps do not wait for its tail (consumers of the global parameters' scalars poll a flag instead)
+        if (service) bar_arrive_id(1, blockDim.x);
+        EH_STAMP(4)
+
+        // ---- optimiser: every thread owns parameters; red holds the grid-wide sums ----
         // every thread derives the batch scalars itself (identical arithmetic everywhere): no serial section
         float ntot = 0.f, post = 1.f;
         for (int t = 0; t < a.T; t++) {
@@ -369,10 +467,15 @@ __global__ void __launch_bounds__(E::MAX_WARPS * 32, 1) k_epoch(const EpochArgs 
             if (a.loss_kind[t] == LOSS_RMSE) post = 1.f / (2.f * sqrtf(red[E::OFF_STATS + t] / nv));
         }
         const bool skip = ntot == 0.f;  // all-masked batch: epoch.jl:17-19
-        if (blockIdx.x == 0 && threadIdx.x < MAXT) a.stats_out[(size_t)s * MAXT + threadIdx.x] = red[E::OFF_STATS + threadIdx.x];
-        EH_STAMP(29)
+        if (bid == 0 && service && lane < MAXT) a.stats_out[(size_t)s * MAXT + lane] = red[E::OFF_STATS + lane];
+        // bias corrections are step constants: their reciprocals are ready before the sums arrive
+        const float rb1 = 1.f / (1.f - b1t), rb2 = 1.f / (1.f - b2t);
+        // compute warps own theta (entry p on thread p, ...), the service warp owns phi
+        const int pbeg = service ? a.ntheta + lane : threadIdx.x;
+        const int pend = service ? a.nflat : a.ntheta;
+        const int pstep = service ? 32 : ncomp_threads;
         if (!skip) {
-            for (int p = threadIdx.x; p < a.nflat; p += blockDim.x) {
+            for (int p = pbeg; p < pend; p += pstep) {
                 float g = red[t_pmap[p]] * post;
                 float th = s_th[p];
                 const bool phi_cached = p >= a.ntheta && p - a.ntheta < MAXPS;
@@ -388,7 +491,7 @@ __global__ void __launch_bounds__(E::MAX_WARPS * 32, 1) k_epoch(const EpochArgs 
                     float vt = a.beta2 * s_v[p] + (1.f - a.beta2) * g * g;
                     s_m[p] = mt;
                     s_v[p] = vt;
-                    dx = mt / (1.f - b1t) / (sqrtf(vt / (1.f - b2t)) + a.eps) * a.eta;
+                    dx = mt * rb1 / (sqrtf(vt * rb2) + a.eps) * a.eta;
                     if (a.opt_kind == OPT_ADAMW) dx += (a.adamw_coupled ? a.eta * a.lambda : a.lambda) * th;
                 } else if (a.opt_kind == OPT_RMSPROP) {
                     float qv = a.beta2 * s_v[p] + (1.f - a.beta2) * g * g;
@@ -417,22 +520,40 @@ __global__ void __launch_bounds__(E::MAX_WARPS * 32, 1) k_epoch(const EpochArgs 
                     }
                 }
             }
-            EH_STAMP(30)
             b1t *= a.beta1;
             b2t *= a.beta2;
             tdone++;
         } else {
             tskip++;
         }
-        E::after_reduce(st, stage, lane);  // constant staging rows were overwritten by the scratch / vectors
+        EH_STAMP(5)
+        // the next step's batch scalars (seed scales / BN rows are only read in the compute phase, which has ended)
+        if (s + 1 < a.nsteps) {
+            store_bs(s + 1);
+            if (s + 2 < a.nsteps) prefetch_bs(bnext + 1 == a.nb ? 0 : bnext + 1);
+        }
+        if (service) {
+            // the global parameters' scalars of step s + 1 are in place: publish (consumers: PmCtx::wait_phi)
+            __syncwarp();
+            __threadfence_block();
+            if (lane == 0) asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(phi_flag)), "r"(tag) : "memory");
+            EH_STAMP_SVC(27)
+        }
+        // end-of-step barrier of the compute warps: all theta patches of the weight image and the next step's batch
+        // scalars are visible
+        if (!service) {
+            bar_sync_id(1, blockDim.x);
+            E::after_reduce(st, stage, lane);  // constant staging rows were overwritten by the scratch / vectors
+        }
         bcur = bnext;
-        EH_STAMP(7)
+        EH_STAMP(6)
     }
 #undef EH_STAMP
+#undef EH_STAMP_SVC
 
     // write back (CTA 0 holds the same state as everybody else)
     __syncthreads();
-    if (blockIdx.x == 0) {
+    if (bid == 0) {
         for (int p = threadIdx.x; p < a.nflat; p += blockDim.x) {
             a.pblock[p] = s_th[p];
             a.m[p] = s_m[p];
@@ -447,7 +568,6 @@ __global__ void __launch_bounds__(E::MAX_WARPS * 32, 1) k_epoch(const EpochArgs 
             a.ost->skipped += tskip;
         }
     }
-    if (cs > 1) cluster_sync_all();  // nobody leaves while a leader may still read its shared memory
 }
 
 }  // namespace eh

@@ -49,6 +49,8 @@ __global__ void __launch_bounds__(256) k_eval(const EvalArgs a)
     cx.prog = a.prog;
     cx.scale_rt = a.scale_rt;
     cx.uniform_mask = 0;
+    cx.phi_flag = nullptr;
+    cx.phi_want = 0;
 #pragma unroll
     for (int s = 0; s < MAXPS; s++)
         if (s >= NPS || a.slot[s].role != ROLE_NEURAL) cx.uniform_mask |= 1u << s;

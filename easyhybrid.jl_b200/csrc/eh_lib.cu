@@ -95,6 +95,7 @@ struct eh_ctx {
     int n_pred_raw = 0, n_forc_raw = 0, n_targ = 0;
     int nflat = 0, ntheta = 0, nglob = 0;
     int real_in = 0;
+    int n_chains = 1, chain_in0[4] = {0, 0, 0, 0}, chain_nin[4] = {0, 0, 0, 0};   // chain k owns inputs [in0, in0 + nin) of the embedded chain
     std::vector<int> h_wsrc, h_pmap;
     std::vector<float> h_pspan;
     PSlot slots[MAXPS];
@@ -117,11 +118,20 @@ struct eh_ctx {
     std::vector<int> h_cells, h_slot_of_flat;
     int *d_cells = nullptr, *d_slot_of_flat = nullptr, *d_losskind = nullptr;
     float *d_pbuf = nullptr, *d_stats = nullptr;
-    int epoch_csize = 0, epoch_grid = 0, epoch_warps = 0;  // last persistent launch geometry
+    int epoch_tiles = 0, epoch_grid = 0, epoch_warps = 0;  // last persistent launch geometry
     const Variant* geo_var = nullptr;                      // cached launch geometry of the persistent kernel
     int64_t geo_B = 0;
-    int geo_cs = 0, geo_G = 0, geo_w = 0;
-    size_t geo_work = 0;
+    int geo_mode = -1, geo_G = 0, geo_w = 0, geo_tile = 0, geo_pg = 0;
+    // the persistent launch as a three-node CUDA graph (event record, kernel, event record): the whole launch reaches the
+    // GPU at once, so the timed interval holds no host submission latency (a cooperative launch costs ~30 us of host time),
+    // and a graph launch is cheaper on the host than cudaLaunchCooperativeKernel.  Rebuilt when the geometry changes.
+    cudaGraph_t pg_graph = nullptr;
+    cudaGraphExec_t pg_exec = nullptr;
+    cudaGraphNode_t pg_knode = nullptr;
+    const void* pg_func = nullptr;
+    int pg_G = 0, pg_threads = 0;
+    size_t pg_smem = 0;
+    bool pg_off = false;
     size_t stats_cap = 0;
     bool persist_ok = false;
     int pm_id = 0;
@@ -141,6 +151,11 @@ struct eh_ctx {
     float* d_bn_test = nullptr;  // BS_STRIDE row with running stats for test mode
     Split split[2];
     int64_t perm_n = 0;
+    // epoch staging: the train records in the order of the resident index stream (d_idx), for the persistent kernel
+    float* d_stage = nullptr;
+    size_t stage_cap = 0;            // records
+    unsigned idx_gen = 1, stage_gen = 0;   // d_stage mirrors d_idx when the generations agree
+    bool stage_on = true;            // EH_NO_STAGE=1: the persistent kernel gathers through the index stream instead
     int64_t perm_B = 0;  // batch size the bscal rows were prepared for (0 = none)
     std::vector<float> bn_mean, bn_var;
     // host-step pipeline
@@ -153,6 +168,10 @@ struct eh_ctx {
     PmProgData* d_prog = nullptr;
     bool host_zero_copy = true;  // EH_HOST_NO_ZEROCOPY=1: always stage host batches through the copy engine
     std::vector<std::pair<float*, float*>> pending_loss;  // (pinned src, user dst)
+    struct PendingBn { const float* loss; const float* mom; int64_t B; };
+    std::vector<PendingBn> pending_bn;                      // host batches whose BatchNorm batch moments still have to be folded in
+    float* h_async_bn = nullptr;                            // pinned ring [async_cap][2 * MAXP]: (mean, biased var) per input
+    float* h_bn0 = nullptr;                                 // pinned [2 * MAXP] + loss cell for the synchronous eh_step_host
     float* h_async_loss = nullptr;                          // pinned ring
     size_t async_cap = 0, async_used = 0;
     // timing
@@ -518,6 +537,24 @@ eh_status ensure_idx_cap(eh_ctx* c, size_t n)
     return EH_OK;
 }
 
+// records [off, off + cnt) of the resident index stream -> d_stage, enqueued on `st`
+eh_status stage_range(eh_ctx* c, int64_t n_total, int64_t off, int64_t cnt, cudaStream_t st)
+{
+    const Split& sp = c->split[EH_SPLIT_TRAIN];
+    const int R4 = c->var->R4;
+    if ((size_t)n_total > c->stage_cap) {
+        CK(cudaStreamSynchronize(c->stream));
+        if (c->d_stage) cudaFree(c->d_stage);
+        c->d_stage = nullptr; c->stage_cap = 0;
+        CK(dalloc(&c->d_stage, (size_t)n_total * R4));
+        c->stage_cap = (size_t)n_total;
+    }
+    k_stage_records<<<(unsigned)((cnt + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4*>(sp.rec), c->d_idx + off,
+                                                                     reinterpret_cast<float4*>(c->d_stage) + (size_t)off * (R4 / 4), cnt, R4 / 4);
+    CK(cudaGetLastError());
+    return EH_OK;
+}
+
 eh_status ensure_bscal_cap(eh_ctx* c, size_t nb)
 {
     if (nb > c->bscal_cap) {
@@ -540,6 +577,7 @@ eh_status upload_indices(eh_ctx* c, const int64_t* idx1, int64_t n, int64_t nmax
 {
     eh_status s = ensure_idx_cap(c, (size_t)n);
     if (s != EH_OK) return s;
+    c->idx_gen++;
     CK(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream));
     CK(cudaMemcpyAsync(c->d_idx64, idx1, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
     k_idx_convert<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(c->d_idx64, c->d_idx, n, nmax, c->d_err);
@@ -665,12 +703,12 @@ eh_status ensure_pass_graph(eh_ctx* c, int64_t n, int64_t B, bool pdl)
 }
 
 // Persistent path: all nsteps optimiser steps in ONE launch (eh_epoch_kernel.cuh).
-// Geometry: cluster size cs, grid G (multiple of cs, all co-resident), w warps per CTA.  A larger
-// cluster means fewer vectors through the grid barrier but (GPC granularity) fewer usable SMs.
+// Geometry: grid G (all co-resident, at most one CTA per SM; `reserve_sms` SMs are left to concurrently running
+// packer kernels), w compute warps + one service warp per CTA.
 // enqueue only (no host synchronisation): rec/idx/bscal select the data source, per-step loss sums go to
 // c->d_stats and the losses to loss_out (device)
 eh_status enqueue_persistent(eh_ctx* c, const float* rec, const int* idx, const float* bscal, float* loss_out, int64_t n,
-                             int64_t B, int64_t first, int64_t nsteps, bool* used, long long** dbg_out)
+                             int64_t B, int64_t first, int64_t nsteps, bool* used, long long** dbg_out, int reserve_sms = 0)
 {
     *used = false;
     const Variant* v = pick_variant(c, B);
@@ -678,58 +716,51 @@ eh_status enqueue_persistent(eh_ctx* c, const float* rec, const int* idx, const 
     const int npartp = rup4(v->NPART);
     const size_t fixed = (size_t)(rup4(v->NW) + SS_FLOATS) * 4;
     const size_t stage = (size_t)std::max(v->stage_floats, v->NPART) * 4;
-    auto extra_of = [&](int cs) { return (size_t)epoch_extra_floats(npartp, c->nflat, cs) * 4 + 64; };
-    const size_t extra = extra_of(1);
+    auto extra_of = [&](int tile_floats) { return (size_t)epoch_extra_floats(npartp, c->nflat, tile_floats, c->nsm) * 4 + 64; };
     const size_t smem_cap = c->smem_optin - 256;
-    if (fixed + extra + stage > smem_cap) return EH_OK;  // does not fit: two-kernel path
+    if (fixed + extra_of(0) + stage > smem_cap) return EH_OK;  // does not fit: two-kernel path
     const int64_t nchunks = (B + v->chunk - 1) / v->chunk;
-    const char* ecs = getenv("EH_CLUSTER_SIZE");
     const char* ew = getenv("EH_EPOCH_WARPS");
-    int best_cs = 0, best_G = 0, best_w = 0;
-    size_t best_work = 0;
-    double best_cost = 1e30;
-    // the geometry only depends on (variant, batch size): the occupancy queries behind it cost ~100 us of host time
-    const bool cached = c->geo_var == v && c->geo_B == B;
-    if (cached) { best_cs = c->geo_cs; best_G = c->geo_G; best_w = c->geo_w; best_work = c->geo_work; }
-    // measured on B200 (bench.py sweep, 65 536-sample batches): clusters of 4 are the sweet spot (132 usable SMs,
-    // 33 vectors through the barrier); 2 is close; 8 loses more to GPC-constrained placement than it saves.
-    // Rule: fewest rounds over the batch first, then that preference order.
-    for (int cs : {4, 2, 1, 8}) {
-        if (cached) break;
-        if (ecs && atoi(ecs) != cs) continue;
-        const size_t extra = extra_of(cs);
-        if (fixed + extra + stage > smem_cap) continue;
-        int wcap = (int)std::min<size_t>((size_t)v->max_warps, (smem_cap - fixed - extra) / stage);
-        int wtry = ew ? std::min(atoi(ew), wcap) : wcap;
-        if (wtry < 1) wtry = 1;
+    const char* eg = getenv("EH_EPOCH_GRID");
+    // the geometry only depends on (variant, batch size, reserved SMs, gather / contiguous): the occupancy query behind it
+    // costs ~100 us of host time
+    const int mode = (idx ? 1 : 0) | (reserve_sms << 1);
+    if (!(c->geo_var == v && c->geo_B == B && c->geo_mode == mode)) {
+        // at most 15 compute warps: with the service warp the CTA has 512 threads (128 registers each)
+        int wcap = (int)std::min<size_t>((size_t)std::min(v->max_warps, 15), (smem_cap - fixed - extra_of(0)) / stage);
+        if (ew) wcap = std::max(1, std::min(atoi(ew), wcap));
         int max_ctas = 0;
-        size_t smem_try = fixed + extra + (size_t)wtry * stage;
-        if (v->epoch_max_grid(wtry, smem_try, cs, &max_ctas) != cudaSuccess) { cudaGetLastError(); continue; }
-        max_ctas = std::min(max_ctas, (c->nsm / cs) * cs);
-        if (max_ctas < cs) continue;
-        int64_t per_round = (int64_t)max_ctas * wtry;
-        int64_t rounds = (nchunks + per_round - 1) / per_round;
-        // fewest warps per CTA that still cover the batch in that many rounds -- but not fewer than 8: below that the
-        // per-step exchange and the optimiser (one element per thread and trip) dominate.  Measured (us per step,
-        // tools/geom_sweep.py): B = 512: 24.4 with 1 warp x 16 CTAs vs 8.7 with 8 warps x 4 CTAs; B = 4096: 28.3 vs 9.6;
-        // B = 16384: 13.2 (4 warps) vs 10.0 (8 warps x 64 CTAs); 16 warps only pay when they save a round (B = 65536).
-        // Then the smallest grid that covers the batch.
-        int w = ew ? wtry : (int)std::min<int64_t>(wtry, std::max<int64_t>(8, (nchunks + rounds * max_ctas - 1) / (rounds * max_ctas)));
-        int G = (int)std::min<int64_t>(max_ctas, ((nchunks + (int64_t)w * rounds - 1) / ((int64_t)w * rounds) + cs - 1) / cs * cs);
-        if (G < cs) G = cs;
-        double cost = (double)rounds;  // strict '<' below keeps the preference order among equal round counts
-        // a batch of <= 256 samples runs in ONE CTA of 8 warps and needs no grid-wide exchange at all (B = 12: 8.3 -> 6.1 us
-        // per step, B = 256: 7.7; 512 samples in one CTA of 16 warps measured slower than 4 CTAs x 8 warps: 10.1 vs 8.6 us)
-        if (cs == 1 && !ew && nchunks <= 8 && wtry >= 8) { w = 8; G = 1; cost -= 0.5; }
-        if (cost < best_cost) {
-            best_cost = cost; best_cs = cs; best_G = G; best_w = w;
-            best_work = (size_t)w * stage;
+        if (v->epoch_max_grid(wcap + 1, fixed + extra_of(0) + (size_t)wcap * stage, &max_ctas) != cudaSuccess) { cudaGetLastError(); return EH_OK; }
+        max_ctas = std::min(max_ctas, std::max(1, c->nsm - reserve_sms));
+        if (eg) max_ctas = std::max(1, std::min(max_ctas, atoi(eg)));
+        if (max_ctas < 1) return EH_OK;
+        int w, G;
+        if (!ew && nchunks <= 8 && wcap >= 8) {
+            // a batch of <= 256 samples runs in ONE CTA of 8 compute warps and needs no grid-wide exchange at all
+            w = 8; G = 1;
+        } else {
+            // fewest rounds over the batch first; then the fewest warps per CTA that keep that round count -- but not
+            // fewer than 8: below that the per-step exchange and the optimiser (one element per thread and trip) dominate
+            // (tools/geom_sweep.py); then the smallest grid that covers the batch
+            const int64_t per_cta = (nchunks + max_ctas - 1) / max_ctas;
+            const int64_t rounds = (per_cta + wcap - 1) / wcap;
+            w = ew ? wcap : (int)std::min<int64_t>(wcap, std::max<int64_t>(8, (per_cta + rounds - 1) / rounds));
+            G = (int)std::min<int64_t>(max_ctas, (nchunks + (int64_t)w * rounds - 1) / ((int64_t)w * rounds));
+            if (G < 1) G = 1;
         }
+        // record tiles (TMA): batch-contiguous records only; two buffers of the largest per-CTA sample range
+        int tile_floats = 0;
+        if (!idx && !getenv("EH_NO_TILES")) {
+            const int64_t per_cta = (nchunks + G - 1) / G;
+            const size_t tf = (size_t)per_cta * v->chunk * v->R4;
+            if (fixed + extra_of((int)tf) + (size_t)w * stage <= smem_cap) tile_floats = (int)tf;
+        }
+        int pg = 0;
+        while (pg < 4 && (2 << pg) <= G) pg++;   // lanes per element pair in the slice reduction: min(16, pow2floor(G))
+        c->geo_var = v; c->geo_B = B; c->geo_mode = mode; c->geo_G = G; c->geo_w = w; c->geo_tile = tile_floats; c->geo_pg = pg;
     }
-    if (!best_cs) return EH_OK;
-    c->geo_var = v; c->geo_B = B; c->geo_cs = best_cs; c->geo_G = best_G; c->geo_w = best_w; c->geo_work = best_work;
-    const int cs = best_cs, G = best_G, w = best_w;
-    const size_t smem = fixed + extra_of(cs) + best_work;
+    const int G = c->geo_G, w = c->geo_w, tile_floats = c->geo_tile;
+    const size_t smem = fixed + extra_of(tile_floats) + (size_t)w * stage;
     if ((size_t)nsteps > c->stats_cap) {
         if (c->d_stats) cudaFree(c->d_stats);
         c->d_stats = nullptr; c->stats_cap = 0;
@@ -743,8 +774,9 @@ eh_status enqueue_persistent(eh_ctx* c, const float* rec, const int* idx, const 
     a.pblock = c->d_theta; a.nflat = c->nflat; a.ntheta = c->ntheta;
     a.m = c->d_m; a.v = c->d_v; a.ost = c->d_ost;
     a.wsrc = c->d_wsrc; a.pmap = c->d_pmap; a.cells = c->d_cells; a.pspan = c->d_pspan; a.slot_of_flat = c->d_slot_of_flat;
-    a.bscal = bscal; a.pbuf = reinterpret_cast<uint2*>(c->d_pbuf); a.tag_base = c->epoch_tag; a.stats_out = c->d_stats;
-    a.npartp = npartp; a.work_floats = (int)(best_work / 4); a.csize = cs; a.T = c->n_targ; a.agg_mean = c->agg_mean;
+    a.bscal = bscal; a.pbuf = reinterpret_cast<uint2*>(c->d_pbuf); a.pbuf_rows = c->nsm + 8; a.tag_base = c->epoch_tag; a.stats_out = c->d_stats;
+    a.npartp = npartp; a.work_floats = (int)((size_t)w * stage / 4); a.wcomp = w; a.pg_log2 = c->geo_pg; a.tile_floats = tile_floats;
+    a.T = c->n_targ; a.agg_mean = c->agg_mean;
     for (int t = 0; t < MAXT; t++) a.loss_kind[t] = c->loss_kind[t];
     for (int s = 0; s < MAXPS; s++) a.slot[s] = c->slots[s];
     for (int i = 0; i < 4; i++) a.pmc[i] = c->pmc[i];
@@ -762,16 +794,57 @@ eh_status enqueue_persistent(eh_ctx* c, const float* rec, const int* idx, const 
         a.dbg = d_dbg;
         *dbg_out = d_dbg;
     }
-    CK(cudaEventRecord(c->ev0, c->stream));
-    cudaError_t le = v->launch_epoch(a, G, w, smem, cs, c->stream);
-    if (le != cudaSuccess) {
-        // e.g. cooperative + cluster launch refused: fall back to the two-kernel path
-        cudaGetLastError();
-        c->err = std::string("persistent launch refused: ") + cudaGetErrorString(le);
-        return EH_OK;
+    bool launched = false;
+    if (!c->pg_off && !getenv("EH_NO_COOP")) {
+        void* kargs[] = {(void*)&a};
+        cudaKernelNodeParams kp{};
+        kp.func = const_cast<void*>(v->epoch_func);
+        kp.gridDim = dim3((unsigned)G); kp.blockDim = dim3((unsigned)((w + 1) * 32));
+        kp.sharedMemBytes = (unsigned)smem; kp.kernelParams = kargs; kp.extra = nullptr;
+        cudaError_t ge = cudaSuccess;
+        if (!c->pg_exec || c->pg_func != v->epoch_func || c->pg_G != G || c->pg_threads != (w + 1) * 32 || c->pg_smem != smem) {
+            if (c->pg_exec) cudaGraphExecDestroy(c->pg_exec);
+            if (c->pg_graph) cudaGraphDestroy(c->pg_graph);
+            c->pg_exec = nullptr; c->pg_graph = nullptr;
+            cudaGraphNode_t n0 = nullptr, n2 = nullptr;
+            ge = cudaGraphCreate(&c->pg_graph, 0);
+            if (ge == cudaSuccess) ge = cudaGraphAddEventRecordNode(&n0, c->pg_graph, nullptr, 0, c->ev0);
+            if (ge == cudaSuccess) ge = cudaGraphAddKernelNode(&c->pg_knode, c->pg_graph, &n0, 1, &kp);
+            if (ge == cudaSuccess) {
+                cudaLaunchAttributeValue av;
+                memset(&av, 0, sizeof av);
+                av.cooperative = 1;
+                ge = cudaGraphKernelNodeSetAttribute(c->pg_knode, cudaLaunchAttributeCooperative, &av);
+            }
+            if (ge == cudaSuccess) ge = cudaGraphAddEventRecordNode(&n2, c->pg_graph, &c->pg_knode, 1, c->ev1);
+            if (ge == cudaSuccess) ge = cudaGraphInstantiate(&c->pg_exec, c->pg_graph, 0);
+            if (ge == cudaSuccess) { c->pg_func = v->epoch_func; c->pg_G = G; c->pg_threads = (w + 1) * 32; c->pg_smem = smem; }
+        } else {
+            ge = cudaGraphExecKernelNodeSetParams(c->pg_exec, c->pg_knode, &kp);
+        }
+        if (ge == cudaSuccess) ge = cudaGraphLaunch(c->pg_exec, c->stream);
+        if (ge == cudaSuccess) {
+            launched = true;
+        } else {
+            cudaGetLastError();
+            if (c->pg_exec) cudaGraphExecDestroy(c->pg_exec);
+            if (c->pg_graph) cudaGraphDestroy(c->pg_graph);
+            c->pg_exec = nullptr; c->pg_graph = nullptr;
+            c->pg_off = true;   // this driver / device does not take the graph form: plain stream launches from now on
+        }
     }
-    CK(cudaEventRecord(c->ev1, c->stream));
-    c->epoch_csize = cs; c->epoch_grid = G; c->epoch_warps = w;
+    if (!launched) {
+        CK(cudaEventRecord(c->ev0, c->stream));
+        cudaError_t le = v->launch_epoch(a, G, w + 1, smem, c->stream);
+        if (le != cudaSuccess) {
+            // e.g. cooperative launch refused: fall back to the two-kernel path
+            cudaGetLastError();
+            c->err = std::string("persistent launch refused: ") + cudaGetErrorString(le);
+            return EH_OK;
+        }
+        CK(cudaEventRecord(c->ev1, c->stream));
+    }
+    c->epoch_tiles = tile_floats > 0; c->epoch_grid = G; c->epoch_warps = w;
     if (c->world > 1) c->dp_steps += (unsigned)nsteps;
     c->epoch_tag += (unsigned)nsteps;
     k_losses_from_stats<<<(unsigned)((nsteps + 127) / 128), 128, 0, c->stream>>>(c->d_stats, bscal, first, (int)nb,
@@ -786,8 +859,14 @@ eh_status enqueue_persistent(eh_ctx* c, const float* rec, const int* idx, const 
 eh_status run_persistent(eh_ctx* c, int64_t n, int64_t B, int64_t first, int64_t nsteps, bool* used)
 {
     long long* d_dbg = nullptr;
-    eh_status s = enqueue_persistent(c, c->split[EH_SPLIT_TRAIN].rec, c->d_idx, c->d_bscal, c->d_loss, n, B, first, nsteps,
-                                     used, &d_dbg);
+    const bool staged = c->stage_on && !c->wide;
+    if (staged && c->stage_gen != c->idx_gen) {
+        eh_status ss = stage_range(c, n, 0, n, c->stream);
+        if (ss != EH_OK) return ss;
+        c->stage_gen = c->idx_gen;
+    }
+    eh_status s = enqueue_persistent(c, staged ? c->d_stage : c->split[EH_SPLIT_TRAIN].rec, staged ? nullptr : c->d_idx, c->d_bscal,
+                                     c->d_loss, n, B, first, nsteps, used, &d_dbg);
     if (s != EH_OK || !*used) return s;
     CK(cudaMemcpyAsync(c->h_loss, c->d_loss, (size_t)nsteps * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     unsigned herr = 0;
@@ -804,7 +883,7 @@ eh_status run_persistent(eh_ctx* c, int64_t n, int64_t B, int64_t first, int64_t
         CK(cudaMemcpy(h.data(), d_dbg, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
         cudaFree(d_dbg);
         if (FILE* f = fopen(getenv("EH_EPOCH_DEBUG"), "wb")) {
-            long long hdr[4] = {nsteps, G, c->epoch_warps, c->epoch_csize};
+            long long hdr[4] = {nsteps, G, c->epoch_warps, c->epoch_tiles};
             fwrite(hdr, sizeof hdr, 1, f);
             fwrite(h.data(), sizeof(long long), h.size(), f);
             fclose(f);
@@ -813,6 +892,19 @@ eh_status run_persistent(eh_ctx* c, int64_t n, int64_t B, int64_t first, int64_t
     c->last_launches = 1;
     c->last_step_ms = c->last_ms;
     return EH_OK;
+}
+
+// one host batch's moments into the running statistics (same rule as update_bn_running); skipped batches excluded
+void fold_bn_host_batch(eh_ctx* c, const float* mom, int64_t B, float loss)
+{
+    if (std::isnan(loss)) return;
+    const int P = c->var->P;
+    for (int i = 0; i < P; i++) {
+        const float mu = mom[2 * i], var = mom[2 * i + 1];
+        const float unb = B > 1 ? var * (float)B / (float)(B - 1) : var;
+        c->bn_mean[i] = 0.9f * c->bn_mean[i] + 0.1f * mu;
+        c->bn_var[i] = 0.9f * c->bn_var[i] + 0.1f * unb;
+    }
 }
 
 // Lux BatchNorm running statistics (momentum 0.1, unbiased variance) after steps [first, first+nsteps) whose
@@ -1001,6 +1093,15 @@ eh_status epoch_pipelined(eh_ctx* c, const int64_t* perm1, int64_t n, int64_t B,
         c->seg_ev.push_back(e);
     }
     cudaStream_t cs = c->copy_stream;
+    const bool staged = c->stage_on && !c->wide;
+    c->idx_gen++;
+    if (staged && (size_t)n > c->stage_cap) {
+        CK(cudaStreamSynchronize(c->stream));
+        if (c->d_stage) cudaFree(c->d_stage);
+        c->d_stage = nullptr; c->stage_cap = 0;
+        CK(dalloc(&c->d_stage, (size_t)n * c->var->R4));
+        c->stage_cap = (size_t)n;
+    }
     CK(cudaMemsetAsync(c->d_err, 0, sizeof(int), c->stream));
     CK(cudaEventRecord(c->ev2, c->stream));
     CK(cudaStreamWaitEvent(cs, c->ev2, 0));  // earlier work on the compute stream may still read d_idx
@@ -1009,6 +1110,10 @@ eh_status epoch_pipelined(eh_ctx* c, const int64_t* perm1, int64_t n, int64_t B,
         CK(cudaMemcpyAsync(c->d_idx64 + off, perm1 + off, (size_t)cnt * sizeof(int64_t), cudaMemcpyHostToDevice, cs));
         k_idx_convert<<<(unsigned)((cnt + 255) / 256), 256, 0, cs>>>(c->d_idx64 + off, c->d_idx + off, cnt, sp.N, c->d_err);
         CK(cudaGetLastError());
+        if (staged) {   // the segment's records in batch order (out-of-range indices were clamped to record 0 above)
+            eh_status ss = stage_range(c, n, off, cnt, cs);
+            if (ss != EH_OK) return ss;
+        }
         CK(cudaEventRecord(c->seg_ev[k], cs));
         return EH_OK;
     };
@@ -1025,7 +1130,8 @@ eh_status epoch_pipelined(eh_ctx* c, const int64_t* perm1, int64_t n, int64_t B,
         s = prepare_batch_rows_range(c, n, B, s0, s1);
         if (s != EH_OK) return s;
         bool u = false;
-        s = enqueue_persistent(c, sp.rec, c->d_idx, c->d_bscal, c->d_loss + s0, n, B, s0, s1 - s0, &u, nullptr);
+        s = enqueue_persistent(c, staged ? c->d_stage : sp.rec, staged ? nullptr : c->d_idx, c->d_bscal, c->d_loss + s0, n, B, s0,
+                               s1 - s0, &u, nullptr);
         if (s != EH_OK) return s;
         if (!u) {
             if (k == 0) {  // nothing has trained yet: hand over to the plain path
@@ -1061,6 +1167,7 @@ eh_status epoch_pipelined(eh_ctx* c, const int64_t* perm1, int64_t n, int64_t B,
     c->last_launches = nseg;
     c->last_step_ms = c->last_ms;
     c->perm_n = n; c->perm_B = B;
+    if (staged) c->stage_gen = c->idx_gen;
     if (losses) memcpy(losses, c->h_loss, (size_t)nb * sizeof(float));
     *used = true;
     if (c->use_bn) return update_bn_running(c, n, B, 0, nb);
@@ -1114,6 +1221,8 @@ eh_status build_plan_wide(eh_ctx* c, const eh_model_desc* d, bool is_prog)
     c->n_pred_raw = d->n_pred; c->n_forc_raw = d->n_forc; c->n_targ = d->n_targ;
     c->use_bn = c0.input_batchnorm ? 1 : 0;
     c->real_in = P;
+    c->n_chains = NC;
+    for (int k = 0, o = 0; k < NC && k < 4; k++) { c->chain_in0[k] = o; c->chain_nin[k] = d->chains[k].n_in; o += d->chains[k].n_in; }
     c->flags = (unsigned)d->flags;
     c->persist_ok = false;
     c->pm_id = d->process_model;
@@ -1316,6 +1425,94 @@ bool builtin_as_program(const eh_model_desc* d, bool is_prog, std::vector<eh_pm_
     return true;
 }
 
+
+// ---- traced program -> built-in form ---------------------------------------------------------------------------------
+// A host that traces the user's mechanistic_model (GenericHybridModel.jl:425 takes any callable) hands over a program.
+// If that program IS one of the built-in forms -- up to the order of commutative operands and the binding of
+// (parameter, parameter, forcing) -- the specialised kernels serve it: the comparison is done here, once, so every host
+// (Julia shim, Python mirror, C harness) gets the same path selection.  Canonical string of an expression: commutative
+// operands sorted; constants by their float32 bit pattern.
+static std::string pm_canon(const eh_pm_instr* prog, int vid)
+{
+    const eh_pm_instr& in = prog[vid];
+    char buf[48];
+    switch (in.op) {
+    case EH_OP_CONST: { unsigned u; memcpy(&u, &in.imm, 4); snprintf(buf, sizeof buf, "c%08x", u); return buf; }
+    case EH_OP_FORCING: snprintf(buf, sizeof buf, "F%d", in.a); return buf;
+    case EH_OP_PARAM: snprintf(buf, sizeof buf, "P%d", in.a); return buf;
+    default: break;
+    }
+    if (in.op >= EH_OP_NEG) return "u" + std::to_string(in.op) + "(" + pm_canon(prog, in.a) + ")";
+    std::string a = pm_canon(prog, in.a), b = pm_canon(prog, in.b);
+    const bool comm = in.op == EH_OP_ADD || in.op == EH_OP_MUL || in.op == EH_OP_MIN || in.op == EH_OP_MAX;
+    if (comm && b < a) std::swap(a, b);
+    return "b" + std::to_string(in.op) + "(" + a + "," + b + ")";
+}
+
+// the built-in forms written as programs over (param pi, param pj, forcing fk, const c0); returns the output value ids
+static int builtin_form_program(int pm, int pi, int pj, int fk, float c0, std::vector<eh_pm_instr>& p, int out[2])
+{
+    auto emit = [&](int op, int a, int b, float imm) { p.push_back(eh_pm_instr{op, a, b, imm}); return (int)p.size() - 1; };
+    const int P0 = emit(EH_OP_PARAM, pi, 0, 0.f), P1 = emit(EH_OP_PARAM, pj, 0, 0.f), F0 = emit(EH_OP_FORCING, fk, 0, 0.f);
+    switch (pm) {
+    case EH_PM_RBQ10: {   // p0 * p1 ^ (0.1 (f0 - c0))
+        const int d = emit(EH_OP_SUB, F0, emit(EH_OP_CONST, 0, 0, c0), 0.f);
+        const int e = emit(EH_OP_MUL, emit(EH_OP_CONST, 0, 0, 0.1f), d, 0.f);
+        out[0] = emit(EH_OP_MUL, P0, emit(EH_OP_POW, P1, e, 0.f), 0.f);
+        return 1;
+    }
+    case EH_PM_EXPO: out[0] = emit(EH_OP_MUL, P0, emit(EH_OP_EXP, emit(EH_OP_MUL, P1, F0, 0.f), 0, 0.f), 0.f); return 1;
+    case EH_PM_LINEAR: out[0] = emit(EH_OP_ADD, emit(EH_OP_MUL, P0, F0, 0.f), P1, 0.f); return 1;
+    case EH_PM_LINEAR2: {
+        out[0] = emit(EH_OP_ADD, emit(EH_OP_MUL, P0, F0, 0.f), P1, 0.f);
+        const int twoa = emit(EH_OP_MUL, emit(EH_OP_CONST, 0, 0, 2.f), P0, 0.f);
+        out[1] = emit(EH_OP_ADD, emit(EH_OP_MUL, twoa, F0, 0.f), P1, 0.f);
+        return 2;
+    }
+    case EH_PM_EXPO2: {
+        out[0] = emit(EH_OP_MUL, P0, emit(EH_OP_EXP, emit(EH_OP_MUL, P1, F0, 0.f), 0, 0.f), 0.f);
+        out[1] = emit(EH_OP_MUL, emit(EH_OP_CONST, 0, 0, 2.f), out[0], 0.f);
+        return 2;
+    }
+    default: return 0;
+    }
+}
+
+// true: the (validated) program of `d` equals built-in form *pm with the binding args[3] and constant consts[0]
+static bool match_builtin_program(const eh_model_desc* d, int* pm, eh_pm_arg args[3], float consts[4])
+{
+    std::vector<std::string> want;
+    for (int t = 0; t < d->n_targ; t++) want.push_back(pm_canon(d->pm_prog, d->pm_outputs[t]));
+    std::vector<float> cs;
+    for (int i = 0; i < d->pm_len; i++)
+        if (d->pm_prog[i].op == EH_OP_CONST) cs.push_back(d->pm_prog[i].imm);
+    const int forms[] = {EH_PM_RBQ10, EH_PM_EXPO, EH_PM_LINEAR, EH_PM_LINEAR2, EH_PM_EXPO2};
+    for (int form : forms)
+        for (int pi = 0; pi < d->n_params; pi++)
+            for (int pj = 0; pj < d->n_params; pj++) {
+                if (pi == pj) continue;
+                for (int fk = 0; fk < d->n_forc; fk++) {
+                    std::vector<float> trial = form == EH_PM_RBQ10 ? cs : std::vector<float>{0.f};
+                    for (float c0 : trial) {
+                        std::vector<eh_pm_instr> p;
+                        int out[2] = {0, 0};
+                        if (builtin_form_program(form, pi, pj, fk, c0, p, out) != d->n_targ) continue;
+                        bool same = true;
+                        for (int t = 0; t < d->n_targ && same; t++) same = pm_canon(p.data(), out[t]) == want[(size_t)t];
+                        if (same) {
+                            *pm = form;
+                            args[0] = eh_pm_arg{0, pi}; args[1] = eh_pm_arg{0, pj}; args[2] = eh_pm_arg{1, fk};
+                            consts[0] = c0; consts[1] = consts[2] = consts[3] = 0.f;
+                            return true;
+                        }
+                    }
+                }
+            }
+    return false;
+}
+
+eh_status build_plan(eh_ctx* c, const eh_model_desc* d);
+
 eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
 {
     if (d->abi_version != EH_ABI_VERSION) return fail(c, EH_EINVAL, "abi_version %d != %d", d->abi_version, EH_ABI_VERSION);
@@ -1340,6 +1537,17 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
         }
         for (int t = 0; t < d->n_targ; t++)
             if (d->pm_outputs[t] < 0 || d->pm_outputs[t] >= d->pm_len) return fail(c, EH_EINVAL, "pm_outputs[%d] out of range", t);
+        // a traced program that IS a built-in form takes the specialised kernels (EH_NO_PM_MATCH=1: keep it as a program)
+        int pm_id = 0;
+        eh_pm_arg margs[3];
+        float mconsts[4];
+        if (!getenv("EH_NO_PM_MATCH") && match_builtin_program(d, &pm_id, margs, mconsts)) {
+            eh_model_desc dd = *d;
+            dd.process_model = pm_id; dd.n_pm_args = 3; dd.pm_args = margs;
+            for (int i = 0; i < 4; i++) dd.pm_consts[i] = mconsts[i];
+            dd.pm_prog = nullptr; dd.pm_len = 0; dd.pm_outputs = nullptr;
+            return build_plan(c, &dd);
+        }
     }
     const eh_chain_desc& ch = d->chains[0];
     const int NC = d->n_chains;
@@ -1416,6 +1624,8 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
     c->n_pred_raw = d->n_pred; c->n_forc_raw = d->n_forc; c->n_targ = d->n_targ;
     c->use_bn = ch.input_batchnorm ? 1 : 0;
     c->real_in = Pt;
+    c->n_chains = NC;
+    for (int k = 0, o = 0; k < NC && k < 4; k++) { c->chain_in0[k] = o; c->chain_nin[k] = d->chains[k].n_in; o += d->chains[k].n_in; }
     c->flags = (unsigned)d->flags;
 
     // flat layout (reference ComponentArray order): chain after chain, per layer W (out x in, column-major) then b; then phi.
@@ -1620,6 +1830,9 @@ eh_status reset_opt_state(eh_ctx* c)
 {
     OptState os;
     os.b1t = c->beta1; os.b2t = c->beta2; os.t = 0; os.skipped = 0;
+    // the ctx streams are non-blocking: steps still in flight (eh_step_host_async) must retire before the state they
+    // use is overwritten from the legacy stream
+    if (c->stream) CK(cudaStreamSynchronize(c->stream));
     CK(cudaMemcpy(c->d_ost, &os, sizeof os, cudaMemcpyHostToDevice));
     CK(cudaMemset(c->d_m, 0, (size_t)c->nflat * sizeof(float)));
     CK(cudaMemset(c->d_v, 0, (size_t)c->nflat * sizeof(float)));
@@ -1659,7 +1872,7 @@ eh_status enqueue_host_step_compute(eh_ctx* c, HostStage& h, int64_t B, float* l
 // loss_dst: where K2 stores the step's loss -- device memory, or page-locked host memory (written over PCIe by the
 // kernel itself, so no separate D2H copy is enqueued).
 eh_status enqueue_host_step(eh_ctx* c, HostStage& h, int64_t B, const float* X, const float* const* forc,
-                            const float* const* targ, float* loss_dst)
+                            const float* const* targ, float* loss_dst, float* bn_dst)
 {
     const Variant* v = c->var;
     // staging slots alternate between two copy streams: the ramp-up / drain of one batch's transfer overlaps the
@@ -1700,7 +1913,7 @@ eh_status enqueue_host_step(eh_ctx* c, HostStage& h, int64_t B, const float* X, 
             const Split& sp = c->split[EH_SPLIT_TRAIN];
             for (int t = 0; t < MAXT; t++) { a.shift_y[t] = sp.shift_y[t]; a.loss_kind[t] = c->loss_kind[t]; }
             for (int k = 0; k < MAXP; k++) a.shift_x[k] = sp.shift_x[k];
-            a.agg_mean = c->agg_mean; a.use_bn = c->use_bn; a.bscal = h.d_bscal; a.bn_batch = nullptr;
+            a.agg_mean = c->agg_mean; a.use_bn = c->use_bn; a.bscal = h.d_bscal; a.bn_batch = c->use_bn ? bn_dst : nullptr;
             k_batch_stats<<<1, 256, 0, c->stream>>>(a);
             CK(cudaGetLastError());
         }
@@ -1735,7 +1948,7 @@ eh_status enqueue_host_step(eh_ctx* c, HostStage& h, int64_t B, const float* X, 
         const Split& sp = c->split[EH_SPLIT_TRAIN];
         for (int t = 0; t < MAXT; t++) { a.shift_y[t] = sp.shift_y[t]; a.loss_kind[t] = c->loss_kind[t]; }
         for (int k = 0; k < MAXP; k++) a.shift_x[k] = sp.shift_x[k];
-        a.agg_mean = c->agg_mean; a.use_bn = c->use_bn; a.bscal = h.d_bscal; a.bn_batch = nullptr;
+        a.agg_mean = c->agg_mean; a.use_bn = c->use_bn; a.bscal = h.d_bscal; a.bn_batch = c->use_bn ? bn_dst : nullptr;
         k_batch_stats<<<1, 256, 0, c->stream>>>(a);
         CK(cudaGetLastError());
     }
@@ -1825,7 +2038,7 @@ eh_status flush_host_group(eh_ctx* c)
     const float* rec = r.d_rec + (size_t)g * EH_RING_GROUP * r.cap * v->R4;
     const float* bscal = r.d_bscal + (size_t)g * EH_RING_GROUP * BS_STRIDE;
     bool used = false;
-    eh_status s = enqueue_persistent(c, rec, nullptr, bscal, r.loss0, (int64_t)k * B, B, 0, k, &used, nullptr);
+    eh_status s = enqueue_persistent(c, rec, nullptr, bscal, r.loss0, (int64_t)k * B, B, 0, k, &used, nullptr, EH_PACK_HOST_CTAS);
     if (s != EH_OK) return s;
     if (!used && c->world > 1)
         return fail(c, EH_EUNSUPPORTED, "persistent kernel unavailable for this shape (data-parallel host batches need it): %s", c->err.c_str());
@@ -1959,6 +2172,8 @@ eh_status eh_create(eh_ctx** out, const eh_model_desc* desc)
         for (int i = 1; i < EH_NPACK; i++) CK(cudaStreamCreateWithFlags(&c->pack_stream[i], cudaStreamNonBlocking));
         if (const char* e = getenv("EH_HOST_NO_ZEROCOPY")) c->host_zero_copy = !(e[0] && e[0] != '0');
         if (const char* e = getenv("EH_HOST_NO_GROUPS")) c->ring.off = e[0] && e[0] != '0';
+        if (const char* e = getenv("EH_NO_STAGE")) c->stage_on = !(e[0] && e[0] != '0');
+        if (const char* e = getenv("EH_NO_PGRAPH")) c->pg_off = e[0] && e[0] != '0';
         CK(cudaEventCreate(&c->ev0));
         CK(cudaEventCreate(&c->ev1));
         CK(cudaEventCreate(&c->ev2));
@@ -1982,7 +2197,7 @@ eh_status eh_create(eh_ctx** out, const eh_model_desc* desc)
         CK(cudaMemcpy(c->d_cells, c->h_cells.data(), c->h_cells.size() * sizeof(int), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(c->d_slot_of_flat, c->h_slot_of_flat.data(), c->h_slot_of_flat.size() * sizeof(int), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(c->d_losskind, c->loss_kind, MAXT * sizeof(int), cudaMemcpyHostToDevice));
-        CK(dalloc(&c->d_pbuf, (size_t)4 * (c->nsm + 8) * rup4(v->NPART)));  // [2][clusters][npartp] {value, tag}
+        CK(dalloc(&c->d_pbuf, (size_t)4 * (c->nsm + 8) * rup4(v->NPART)));  // [2][nsm + 8][npartp] {value, tag}: CTA partials + totals, by step parity
         CK(cudaMemset(c->d_pbuf, 0, (size_t)4 * (c->nsm + 8) * rup4(v->NPART) * sizeof(float)));
         CK(dalloc(&c->d_dperr, (size_t)1));
         CK(cudaMemset(c->d_dperr, 0, sizeof(unsigned)));
@@ -2031,12 +2246,14 @@ void eh_destroy(eh_ctx* c)
     delete c->wide;
     c->wide = nullptr;
     if (c->gexec) cudaGraphExecDestroy(c->gexec);
+    if (c->pg_exec) cudaGraphExecDestroy(c->pg_exec);
+    if (c->pg_graph) cudaGraphDestroy(c->pg_graph);
     for (int r = 0; r < c->world && c->world > 1; r++)
         if (r != c->rank && c->dp_peer[r]) cudaIpcCloseMemHandle(c->dp_peer[r]);
     if (c->dp_block) cudaFree(c->dp_block);
     void* ptrs[] = {c->d_wsrc, c->d_pmap, c->d_pspan, c->d_theta, c->d_m, c->d_v, c->d_grad, c->d_ost, c->d_partial,
                     c->d_gvec, c->d_dperr, c->d_cells, c->d_slot_of_flat, c->d_losskind, c->d_pbuf, c->d_stats, c->d_bscal, c->d_bn_batch, c->d_idx, c->d_idx64, c->d_err, c->d_loss, c->d_evalpart,
-                    c->d_bn_test, c->d_prog, c->split[0].rec, c->split[1].rec};
+                    c->d_bn_test, c->d_prog, c->d_stage, c->split[0].rec, c->split[1].rec};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     {
@@ -2058,6 +2275,8 @@ void eh_destroy(eh_ctx* c)
     }
     if (c->h_loss) cudaFreeHost(c->h_loss);
     if (c->h_async_loss) cudaFreeHost(c->h_async_loss);
+    if (c->h_async_bn) cudaFreeHost(c->h_async_bn);
+    if (c->h_bn0) cudaFreeHost(c->h_bn0);
     for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -2087,7 +2306,7 @@ eh_status eh_upload(eh_ctx* c, int32_t split, int64_t N, const float* X, const f
     if (sp.rec) { cudaFree(sp.rec); sp.rec = nullptr; }
     sp.N = N;
     sp.has_nan = false;
-    if (split == EH_SPLIT_TRAIN) { c->perm_n = 0; c->perm_B = 0; }
+    if (split == EH_SPLIT_TRAIN) { c->perm_n = 0; c->perm_B = 0; c->idx_gen++; }
     if (N == 0) return EH_OK;
     const Variant* v = c->var;
     // numerically convenient shifts + NaN census on the host (one pass over the targets)
@@ -2186,16 +2405,26 @@ eh_status eh_get_opt_state(eh_ctx* c, float* m, float* v, int64_t n, int64_t* t)
 eh_status eh_set_bn_state(eh_ctx* c, int32_t chain, const float* mean, const float* var, int32_t n)
 {
     if (!c) return EH_EINVAL;
-    if (chain != 0 || n != c->real_in || !mean || !var) return fail(c, EH_EINVAL, "eh_set_bn_state: bad arguments");
-    for (int i = 0; i < n; i++) { c->bn_mean[i] = mean[i]; c->bn_var[i] = var[i]; }
+    if (chain < 0 || chain >= c->n_chains || n != c->chain_nin[chain] || !mean || !var)
+        return fail(c, EH_EINVAL, "eh_set_bn_state: chain %d has %d inputs (got n=%d)", chain, chain >= 0 && chain < c->n_chains ? c->chain_nin[chain] : -1, n);
+    EH_ENTER(c);
+    CK(cudaStreamSynchronize(c->stream));   // steps in flight may still fold their batch moments in (eh_sync does that)
+    const int o = c->chain_in0[chain];
+    for (int i = 0; i < n; i++) { c->bn_mean[o + i] = mean[i]; c->bn_var[o + i] = var[i]; }
     return EH_OK;
 }
 
 eh_status eh_get_bn_state(eh_ctx* c, int32_t chain, float* mean, float* var, int32_t n)
 {
     if (!c) return EH_EINVAL;
-    if (chain != 0 || n != c->real_in || !mean || !var) return fail(c, EH_EINVAL, "eh_get_bn_state: bad arguments");
-    for (int i = 0; i < n; i++) { mean[i] = c->bn_mean[i]; var[i] = c->bn_var[i]; }
+    if (chain < 0 || chain >= c->n_chains || n != c->chain_nin[chain] || !mean || !var)
+        return fail(c, EH_EINVAL, "eh_get_bn_state: chain %d has %d inputs (got n=%d)", chain, chain >= 0 && chain < c->n_chains ? c->chain_nin[chain] : -1, n);
+    if (!c->pending_bn.empty()) {   // host batches still in flight: their moments belong to the state that is asked for
+        eh_status s = eh_sync(c);
+        if (s != EH_OK) return s;
+    }
+    const int o = c->chain_in0[chain];
+    for (int i = 0; i < n; i++) { mean[i] = c->bn_mean[o + i]; var[i] = c->bn_var[o + i]; }
     return EH_OK;
 }
 
@@ -2280,12 +2509,15 @@ eh_status eh_step_host(eh_ctx* c, int64_t B, const float* X, const float* const*
     HostStage& h = c->hs[0];
     eh_status s = ensure_host_stage(c, h, B);
     if (s != EH_OK) return s;
-    s = enqueue_host_step(c, h, B, X, forc, targ, h.d_loss);
+    if (c->use_bn && !c->h_bn0) CK(cudaMallocHost((void**)&c->h_bn0, 2 * MAXP * sizeof(float)));
+    s = enqueue_host_step(c, h, B, X, forc, targ, h.d_loss, c->h_bn0);
     if (s != EH_OK) return s;
     float L = 0.f;
     CK(cudaMemcpyAsync(&L, h.d_loss, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     if (loss_out) *loss_out = L;
+    // Lux updates the running statistics of the input BatchNorm on every training step (momentum 0.1)
+    if (c->use_bn && !c->wide) fold_bn_host_batch(c, c->h_bn0, B, L);
     return EH_OK;
 }
 
@@ -2303,6 +2535,7 @@ eh_status eh_step_host_async(eh_ctx* c, int64_t B, const float* X, const float* 
         if (!c->h_async_loss) {
             c->async_cap = 4096;
             CK(cudaMallocHost((void**)&c->h_async_loss, c->async_cap * sizeof(float)));
+            if (c->use_bn) CK(cudaMallocHost((void**)&c->h_async_bn, c->async_cap * 2 * MAXP * sizeof(float)));
         }
     }
     {
@@ -2329,10 +2562,12 @@ eh_status eh_step_host_async(eh_ctx* c, int64_t B, const float* X, const float* 
     if (s != EH_OK) return s;
     // the update kernel stores the loss straight into the page-locked ring (device-visible under UVA):
     // the device->host read of the step's result costs no extra enqueue
+    float* bnp = c->h_async_bn ? c->h_async_bn + c->async_used * 2 * MAXP : nullptr;
     float* pin = c->h_async_loss + c->async_used++;
-    s = enqueue_host_step(c, h, B, X, forc, targ, pin);
+    s = enqueue_host_step(c, h, B, X, forc, targ, pin, bnp);
     if (s != EH_OK) return s;
     c->pending_loss.emplace_back(pin, loss_slot);
+    if (c->use_bn && !c->wide && bnp) c->pending_bn.push_back({pin, bnp, B});
     return EH_OK;
 }
 
@@ -2350,6 +2585,9 @@ eh_status eh_sync(eh_ctx* c)
     for (auto& pr : c->pending_loss)
         if (pr.second) *pr.second = *pr.first;
     c->pending_loss.clear();
+    // the retired host batches' BatchNorm moments, in step order (Lux: running statistics move on every training step)
+    for (auto& pb : c->pending_bn) fold_bn_host_batch(c, pb.mom, pb.B, *pb.loss);
+    c->pending_bn.clear();
     c->async_used = 0;
     return EH_OK;
 }
@@ -2363,9 +2601,16 @@ eh_status eh_eval(eh_ctx* c, int32_t split, float* yhat, double* stats, float* n
     if (!sp.rec) return fail(c, EH_EINVAL, "split %d not uploaded", split);
     const Variant* v = c->var;
     const int64_t N = sp.N;
+    // temporaries are released on every exit path (the CK macro returns early)
+    struct Scoped {
+        void* p = nullptr;
+        ~Scoped() { if (p) cudaFree(p); }
+    } g_yhat, g_par, g_acc;
     float *d_yhat = nullptr, *d_par = nullptr;
     if (yhat) CK(dalloc(&d_yhat, (size_t)N * v->T));
+    g_yhat.p = d_yhat;
     if (nn_out) CK(dalloc(&d_par, (size_t)N * v->NPS));
+    g_par.p = d_par;
     EvalArgs a;
     memset(&a, 0, sizeof a);
     a.rec = reinterpret_cast<const float4*>(sp.rec);
@@ -2391,13 +2636,13 @@ eh_status eh_eval(eh_ctx* c, int32_t split, float* yhat, double* stats, float* n
         // wide chains: forward GEMMs over chunks of rows, statistics accumulated on the device
         double* d_acc = nullptr;
         CK(dalloc(&d_acc, (size_t)MAXT * EVAL_NSTAT));
+        g_acc.p = d_acc;
         CK(cudaMemsetAsync(d_acc, 0, MAXT * EVAL_NSTAT * sizeof(double), c->stream));
         CK(cudaEventRecord(c->ev0, c->stream));
         const int64_t chunk = c->wide->eval_chunk();
         for (int64_t r0 = 0; r0 < N; r0 += chunk) {
             const int bc = (int)std::min<int64_t>(chunk, N - r0);
             if (c->wide->eval_rows(sp.rec, N, r0, bc, a.bscal, c->d_theta, d_yhat, d_par, N, d_acc, sp.shift_y, c->stream) != cudaSuccess) {
-                cudaFree(d_acc);
                 return fail(c, EH_ECUDA, "wide path: %s", c->wide->error());
             }
         }
@@ -2407,7 +2652,6 @@ eh_status eh_eval(eh_ctx* c, int32_t split, float* yhat, double* stats, float* n
         if (yhat) CK(cudaMemcpyAsync(yhat, d_yhat, (size_t)N * v->T * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         CK(cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1));
-        cudaFree(d_acc);
         if (nn_out) {
             for (int pi = 0; pi < c->nparam_desc; pi++) {
                 int s = c->slot_of_param[pi];
@@ -2415,8 +2659,6 @@ eh_status eh_eval(eh_ctx* c, int32_t split, float* yhat, double* stats, float* n
                 CK(cudaMemcpy(nn_out + (size_t)pi * N, d_par + (size_t)s * N, (size_t)N * sizeof(float), cudaMemcpyDeviceToHost));
             }
         }
-        if (d_yhat) cudaFree(d_yhat);
-        if (d_par) cudaFree(d_par);
         if (stats)
             for (int t = 0; t < v->T; t++) {
                 for (int q = 0; q < EVAL_NSTAT; q++) stats[(size_t)t * EH_EVAL_STATS + q] = acc[t * EVAL_NSTAT + q];
@@ -2446,8 +2688,6 @@ eh_status eh_eval(eh_ctx* c, int32_t split, float* yhat, double* stats, float* n
             CK(cudaMemcpy(nn_out + (size_t)pi * N, d_par + (size_t)s * N, (size_t)N * sizeof(float), cudaMemcpyDeviceToHost));
         }
     }
-    if (d_yhat) cudaFree(d_yhat);
-    if (d_par) cudaFree(d_par);
     if (stats) {
         for (int t = 0; t < c->n_targ; t++) {   // (the generic variants carry unused, always-masked target columns)
             for (int q = 0; q < EVAL_NSTAT; q++) {

@@ -36,7 +36,23 @@ struct PmCtx {
     const PmProgData* prog;    // traced program (PmProgram only)
     int scale_rt;              // PmProgram only: scale_nn_outputs as a run-time flag (one compiled variant serves both)
     unsigned uniform_mask;     // bit s set: slot s is GLOBAL / FIXED (same value for all samples)
+    // persistent kernel only: shared-memory word that carries the number of the last optimiser step whose global-parameter
+    // scalars (slot values, pms) are in place; the warp that owns the global parameters publishes it, consumers wait for
+    // `phi_want` right before they read those scalars (NULL: nothing to wait for)
+    const unsigned* phi_flag;
+    unsigned phi_want;
     __device__ __forceinline__ bool uniform(int s) const { return (uniform_mask >> s) & 1u; }
+    __device__ __forceinline__ void wait_phi() const
+    {
+        if (phi_flag) {
+            const unsigned a = (unsigned)__cvta_generic_to_shared(phi_flag);
+            unsigned v;
+            do {
+                asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+            } while (v != phi_want);
+            __threadfence_block();
+        }
+    }
 };
 
 // derived scalars of a uniform slot; called by the thread that owns the slot's update

@@ -57,7 +57,8 @@ __global__ void __launch_bounds__(E::MAX_WARPS * 32, 1) k_step(const StepArgs a)
     const int nchunks = (a.B + E::CHUNK - 1) / E::CHUNK;
     int chunk = blockIdx.x * nwarps + warp;
     typename E::State st;
-    E::fetch(st, a.rec, a.idx, a.rec_base, a.B, chunk, nchunks, lane);
+    const FetchArgs fa{a.rec, a.idx, a.rec_base, a.B, nchunks, nullptr, 0};
+    E::fetch(st, fa, chunk, lane);
     E::init_warp(st, stage, lane);
 
     // wait for the previous update kernel (PDL), then pull weights and scalars
@@ -72,15 +73,23 @@ __global__ void __launch_bounds__(E::MAX_WARPS * 32, 1) k_step(const StepArgs a)
     cx.prog = a.prog;
     cx.scale_rt = a.scale_rt;
     cx.uniform_mask = 0;
+    cx.phi_flag = nullptr;
+    cx.phi_want = 0;
 #pragma unroll
     for (int s = 0; s < MAXPS; s++)
         if (s >= C::NPS || a.slot[s].role != ROLE_NEURAL) cx.uniform_mask |= 1u << s;
 
     E::step_begin(st, sW, lane);
-    const FetchArgs fa{a.rec, a.idx, a.rec_base, a.B, nchunks};
     for (; chunk < nchunks; chunk += GW) E::chunk(st, fa, chunk + GW, sW, sS, stage, lane, a.slot, a.loss_kind, cx);
-    __syncthreads();  // every warp is done with its staging tile; the work region becomes [nwarps][NPART]
-    E::reduce(st, work, a.partial + (size_t)blockIdx.x * a.npart, 1);
+    if (E::SCRATCH_ALIASES_STAGE) __syncthreads();  // every warp is done with its staging tile; the work region becomes [nwarps][NPART]
+    E::reduce_prepare(st, work);
+    __syncthreads();
+    float* out = a.partial + (size_t)blockIdx.x * a.npart;
+    for (int q = threadIdx.x; q < E::NPART; q += blockDim.x) {
+        int p;
+        const float sum = E::reduce_sum(work, nwarps, q, p);
+        __stcg(out + p, sum);
+    }
 }
 
 }  // namespace eh

@@ -346,6 +346,17 @@ __global__ void __launch_bounds__(256) k_idx_convert(const long long* in, int* o
     out[i] = (int)v;
 }
 
+// Epoch staging (collect_dim_data, src/training/epoch.jl:1-11, once per permutation instead of once per batch):
+// out[i] = rec[idx[i]], i.e. the records in batch order, so that the persistent kernel streams every batch as one
+// contiguous range (one bulk copy per CTA and step) instead of gathering 16-byte records at random.
+__global__ void __launch_bounds__(256) k_stage_records(const float4* rec, const int* idx, float4* out, long long n, int r44)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long src = idx[i];
+    for (int q = 0; q < r44; q++) out[i * r44 + q] = __ldg(rec + src * r44 + q);
+}
+
 // per-step loss values from the reduced sums of the persistent kernel (loss_fn.jl:58-81)
 __global__ void k_losses_from_stats(const float* stats, const float* bscal, long long first_step, int nb, int nsteps,
                                     int T, int agg_mean, const int* loss_kind_dev, float* loss_out)

@@ -40,67 +40,23 @@ static cudaError_t launch_eval_t(const EvalArgs& a, int grid, int nwarps, size_t
     return cudaGetLastError();
 }
 
-// k_epoch: thread-block clusters (DSMEM pre-reduction) + cooperative launch (the grid barrier needs
-// every CTA resident).  csize = 1 launches without a cluster attribute.
+// k_epoch: cooperative launch (the grid-wide exchange needs every CTA resident), one CTA per SM, no clusters.
+// EH_NO_COOP=1 drops the co-residency guarantee (plain launch; the grid never exceeds the co-resident maximum anyway).
 template <class E>
-static void epoch_cfg(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, int grid, int nwarps, size_t smem, int csize,
-                      cudaStream_t st)
+static cudaError_t launch_epoch_t(const EpochArgs& a, int grid, int nwarps, size_t smem, cudaStream_t st)
 {
-    cfg = cudaLaunchConfig_t{};
-    cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3((unsigned)(nwarps * 32));
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    int n = 0;
-    // EH_NO_COOP=1 drops the co-residency guarantee (profilers refuse cooperative + cluster launches)
-    if (!getenv("EH_NO_COOP")) {
-        attr[n].id = cudaLaunchAttributeCooperative;
-        attr[n].val.cooperative = 1;
-        n++;
+    if (getenv("EH_NO_COOP")) {
+        k_epoch<E><<<grid, nwarps * 32, smem, st>>>(a);
+        return cudaGetLastError();
     }
-    if (csize > 1) {
-        attr[n].id = cudaLaunchAttributeClusterDimension;
-        attr[n].val.clusterDim.x = (unsigned)csize;
-        attr[n].val.clusterDim.y = 1;
-        attr[n].val.clusterDim.z = 1;
-        n++;
-    }
-    cfg.attrs = attr;
-    cfg.numAttrs = n;
+    void* args[] = {(void*)&a};
+    return cudaLaunchCooperativeKernel((void*)k_epoch<E>, dim3((unsigned)grid), dim3((unsigned)(nwarps * 32)), args, smem, st);
 }
 
+// how many CTAs of this shape can be co-resident
 template <class E>
-static cudaError_t launch_epoch_t(const EpochArgs& a, int grid, int nwarps, size_t smem, int csize, cudaStream_t st)
+static cudaError_t epoch_max_grid_t(int nwarps, size_t smem, int* max_ctas)
 {
-    if (csize == 1) {
-        void* args[] = {(void*)&a};
-        return cudaLaunchCooperativeKernel((void*)k_epoch<E>, dim3((unsigned)grid), dim3((unsigned)(nwarps * 32)), args, smem, st);
-    }
-    cudaLaunchConfig_t cfg;
-    cudaLaunchAttribute attr[2];
-    epoch_cfg<E>(cfg, attr, grid, nwarps, smem, csize, st);
-    return cudaLaunchKernelEx(&cfg, k_epoch<E>, a);
-}
-
-// how many CTAs of this shape can be co-resident (in clusters of csize)
-template <class E>
-static cudaError_t epoch_max_grid_t(int nwarps, size_t smem, int csize, int* max_ctas)
-{
-    if (csize > 1) {
-        cudaLaunchConfig_t cfg;
-        cudaLaunchAttribute attr[2];
-        epoch_cfg<E>(cfg, attr, csize, nwarps, smem, csize, nullptr);
-        cfg.numAttrs = 2;
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = (unsigned)csize;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.numAttrs = 1;
-        int ncl = 0;
-        cudaError_t e = cudaOccupancyMaxActiveClusters(&ncl, k_epoch<E>, &cfg);
-        *max_ctas = ncl * csize;
-        return e;
-    }
     int per_sm = 0, dev = 0, nsm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_epoch<E>, nwarps * 32, smem);
     if (e != cudaSuccess) return e;
@@ -131,6 +87,7 @@ static Variant make_variant(const char* name)
     v.launch_eval = launch_eval_t<C>;
     v.launch_epoch = launch_epoch_t<E>;
     v.epoch_max_grid = epoch_max_grid_t<E>;
+    v.epoch_func = (const void*)k_epoch<E>;
     return v;
 }
 

@@ -20,8 +20,9 @@ struct Variant {
     cudaError_t (*prepare)(size_t step_smem, size_t eval_smem);
     cudaError_t (*launch_step)(const StepArgs& a, int grid, int nwarps, size_t smem, cudaStream_t st, bool pdl);
     cudaError_t (*launch_eval)(const EvalArgs& a, int grid, int nwarps, size_t smem, cudaStream_t st);
-    cudaError_t (*launch_epoch)(const EpochArgs& a, int grid, int nwarps, size_t smem, int csize, cudaStream_t st);
-    cudaError_t (*epoch_max_grid)(int nwarps, size_t smem, int csize, int* max_ctas);
+    cudaError_t (*launch_epoch)(const EpochArgs& a, int grid, int nwarps, size_t smem, cudaStream_t st);
+    cudaError_t (*epoch_max_grid)(int nwarps, size_t smem, int* max_ctas);
+    const void* epoch_func;   // k_epoch<E>, for the graph node of the persistent launch
 };
 
 const Variant* find_variant(int pm, int P, int NH, int H, int NOUT, int act, int scale, int engine);

@@ -168,6 +168,8 @@ __global__ void __launch_bounds__(256) k_wide_head(const HeadArgs a)
     cx.prog = &s_prog;
     cx.scale_rt = HC::SCALE ? 1 : 0;
     cx.uniform_mask = 0;
+    cx.phi_flag = nullptr;
+    cx.phi_want = 0;
 #pragma unroll
     for (int s = 0; s < MAXPS; s++)
         if (s >= NPS || a.slot[s].role != ROLE_NEURAL) cx.uniform_mask |= 1u << s;

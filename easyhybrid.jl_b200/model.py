@@ -18,6 +18,7 @@ GenericHybridModel.jl:425) and matched against the built-in fused forms.
 from __future__ import annotations
 
 import inspect
+import os
 import itertools
 import math
 from dataclasses import dataclass, field
@@ -489,7 +490,9 @@ def build_desc(model, *, training_loss="mse", agg="sum", opt=None, device=0, fla
     chains = [dict(in_cols=[pcols.index(p) for p in ch["predictors"]], hidden=ch["hidden"], n_out=ch["n_out"],
                    activation=_abi.ACT[ch["activation"]], input_batchnorm=ch["input_batchnorm"]) for ch in model.chains]
     prog, outs = trace_process_model(model.mechanistic_model, model.forcing, names, model.targets)
-    m = match_builtin(prog, outs, len(model.forcing), len(names))
+    # the library recognises built-in forms in traced programs itself (match_builtin_program, csrc/eh_lib.cu); the host-side
+    # matcher is kept as the default so that the descriptor says what the model is, EH_PY_NO_MATCH=1 ships the raw trace
+    m = None if os.environ.get("EH_PY_NO_MATCH") else match_builtin(prog, outs, len(model.forcing), len(names))
     if m is not None:
         pm_name, (pi, pj, fk), consts = m
         pm = dict(process_model=_abi.PM[pm_name], pm_args=[(0, pi), (0, pj), (1, fk)], pm_consts=consts)

@@ -60,6 +60,13 @@ def _tl_name(cfg):
     return str(tl) if isinstance(tl, str) else str(tl.losses[0])
 
 
+def _extract_agg_loss(l_val, name, cfg):
+    """extract_agg_loss(l_val) (early_stopping.jl:47-49): the aggregate of the first loss type; the reference reads the
+    `sum` field whatever cfg.agg is -- with another aggregation the mirror reads that aggregate instead of failing"""
+    entry = l_val[name]
+    return entry["sum"] if "sum" in entry else entry[_agg_name(cfg)]
+
+
 def _agg_name(cfg):
     return cfg.agg if isinstance(cfg.agg, str) else getattr(cfg.agg, "__name__", "sum")
 
@@ -107,8 +114,12 @@ def train(model, data, save_ps=(), *, train_cfg=None, data_cfg=None, **kwargs):
         (l_tr, _, _), (l_va, _, _) = evaluate_epoch(sess, model, cfg)
         res.train_history.append(l_tr)
         res.val_history.append(l_va)
-        tl, ag = _tl_name(cfg), _agg_name(cfg)
-        best_loss, best_epoch, best_ps, wait = l_va[tl][ag], 0, ps0.copy(), 0
+        # early stopping tracks the FIRST entry of cfg.loss_types, aggregated over the targets (extract_agg_loss reads the
+        # `sum` field of l_val[1], early_stopping.jl:47-49) -- not the training loss
+        es_name = str(cfg.loss_types[0])
+        bn_on = bool(model.chains and model.chains[0]["input_batchnorm"])
+        get_st = (lambda: [sess.get_bn_state(k) for k in range(len(model.chains))]) if bn_on else (lambda: None)
+        best_loss, best_epoch, best_ps, best_st, wait = _extract_agg_loss(l_va, es_name, cfg), 0, ps0.copy(), get_st(), 0
         for epoch in range(1, cfg.nepochs + 1):
             perm0 = rng.permutation(n_tr)
             if not all_masked:
@@ -119,16 +130,21 @@ def train(model, data, save_ps=(), *, train_cfg=None, data_cfg=None, **kwargs):
                 res.val_history.append(l_va)
             else:
                 res.train_history, res.val_history = [l_tr], [l_va]
-            cur = l_va[tl][ag]
-            if isbetter(cur, best_loss, tl):
-                best_loss, best_epoch, best_ps, wait = cur, epoch, sess.get_params(), 0
+            cur = _extract_agg_loss(l_va, es_name, cfg)
+            if isbetter(cur, best_loss, es_name):
+                best_loss, best_epoch, best_ps, best_st, wait = cur, epoch, sess.get_params(), get_st(), 0
             else:
                 wait += 1
             if wait >= cfg.patience:
                 break
         final_ps = sess.get_params()
-        if cfg.return_model == "best" and best_epoch > 0:
+        if cfg.return_model == "best":
+            # best_or_final (early_stopping.jl:51-71): stopper.best_ps / best_st -- the INITIAL parameters and states
+            # when no epoch improved on them (best_epoch == 0)
             sess.set_params(best_ps)
+            if bn_on:
+                for k, (mu, var) in enumerate(best_st):
+                    sess.set_bn_state(mu, var, k)
             res.ps = best_ps
         else:
             res.ps = final_ps
@@ -136,8 +152,10 @@ def train(model, data, save_ps=(), *, train_cfg=None, data_cfg=None, **kwargs):
         res.opt_state = sess.get_opt_state()
         res.ps_tree = model.unflatten(res.ps)
         res.st = model.initialstates()
-        if model.chains and model.chains[0]["input_batchnorm"]:
-            res.st["bn"] = sess.get_bn_state()
+        if bn_on:
+            # running statistics of every chain's input BatchNorm (Lux `st`), chain after chain
+            bn = [sess.get_bn_state(k) for k in range(len(model.chains))]
+            res.st["bn"] = bn[0] if len(bn) == 1 else bn
         (_, yh_tr, par_tr), (_, yh_va, par_va) = evaluate_epoch(sess, model, cfg, want_pred=True)
         names = model.parameters.names
         res.train_obs_pred = {t: (y_tr[t], yh_tr[i]) for i, t in enumerate(model.targets)}

@@ -97,6 +97,23 @@ def linear_model(eh, two=False, activation="relu"):
                                    ["a"], ["b"], hidden_layers=[15, 15], activation=activation)
 
 
+def truth_trajectory(o, flat0, xf, y, perm, B, nthreads=1):
+    """per-step float64 loss of the oracle along its own trajectory: float64 loss / gradient, the oracle's Float32
+    optimiser rule (Optimisers.jl semantics) -- a reference trajectory without float32 forward / backward error.
+    All-masked batches are skipped (src/training/epoch.jl:17-19) and reported as NaN.  Returns (losses, final flat)."""
+    ref = flat0.copy()
+    want = []
+    for k in range((perm.size + B - 1) // B):
+        idx = perm[k * B:(k + 1) * B]
+        if np.isnan(np.stack([y[t][idx] for t in o.model.targets])).all():
+            want.append(np.nan)
+            continue
+        L, g = o.loss_grad(ref, xf, y, idx, precision=64, nthreads=nthreads)
+        want.append(L)
+        o.opt_step(ref, g.astype(np.float32))
+    return np.array(want), ref
+
+
 @pytest.fixture(scope="session")
 def eh():
     import easyhybrid_b200

@@ -114,12 +114,10 @@ def test_generic_variants_loss_and_gradient(eh, orc, name, mk, mkdata, loss, agg
         idx = rng.permutation(n)[:B]
         L, g = sess.loss_grad(idx)
         L64, g64 = o.loss_grad(flat, xf, y, idx, precision=64)
-        L32, g32 = o.loss_grad(flat, xf, y, idx, precision=32)
         scale = np.abs(g64).max()
         assert abs(L - L64) <= RTOL_LOSS * abs(L64), (name, B, L, L64)
         err = np.abs(g - g64).max() / scale
-        err32 = np.abs(g32 - g64).max() / scale
-        assert err <= max(RTOL_GRAD, 1.25 * err32), (name, B, err, err32)
+        assert err <= RTOL_GRAD, (name, B, err)   # 1e-5 of the largest entry, no exception
     sess.close()
 
 
@@ -167,3 +165,39 @@ def test_traced_model_trains_through_train_api(eh):
     assert last < 0.03, last
     assert abs(res.train_diffs["Q10"] - 2.0) < 0.1, res.train_diffs["Q10"]
     assert abs(res.train_diffs["alpha"] - 0.3) < 0.15, res.train_diffs["alpha"]
+
+
+def test_library_recognises_builtin_forms_in_traced_programs(eh, monkeypatch):
+    """a host that only traces (the Julia shim) ships EH_PM_PROGRAM; eh_create matches it against the built-in forms and
+    takes the specialised kernels -- same variant, same numbers as with the host-side matcher"""
+    from conftest import expo_model, linear_model, make_synth, rbq10_model
+    for mk, want in ((rbq10_model, "ffma2/PmRbQ10/"), (expo_model, "ffma2/PmExpo/"), (linear_model, "ffma2/PmLinear/")):
+        monkeypatch.delenv("EH_PY_NO_MATCH", raising=False)
+        a = eh.FusedSession(mk(eh))
+        monkeypatch.setenv("EH_PY_NO_MATCH", "1")
+        b = eh.FusedSession(mk(eh))
+        assert a.kernel_variant() == b.kernel_variant() and b.kernel_variant().startswith(want), (a.kernel_variant(), b.kernel_variant())
+        a.close(); b.close()
+    # and a program that is NOT a built-in form stays a program
+    def other(*, ta, Q10, rb):
+        return {"reco": rb * np.exp(Q10) + ta}
+    m = eh.constructHybridModel(["sw_pot"], ["ta"], ["reco"], other, dict(Q10=(2, 1, 4), rb=(3, 0, 13)), ["rb"], ["Q10"])
+    s = eh.FusedSession(m)
+    assert s.kernel_variant().startswith("ffma2/PmProgram/")
+    s.close()
+    # numbers: loss / gradient identical either way
+    monkeypatch.delenv("EH_PY_NO_MATCH", raising=False)
+    model = rbq10_model(eh)
+    xf, y = eh.prepare_data(model, make_synth(1500))
+    flat = model.initialparameters(np.random.default_rng(1))
+    idx = np.arange(1000)
+    res = []
+    for env in (None, "1"):
+        if env:
+            monkeypatch.setenv("EH_PY_NO_MATCH", env)
+        sess = eh.FusedSession(model)
+        sess.upload(0, xf, y)
+        sess.set_params(flat)
+        res.append(sess.loss_grad(idx))
+        sess.close()
+    assert res[0][0] == res[1][0] and np.array_equal(res[0][1], res[1][1])

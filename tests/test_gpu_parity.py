@@ -7,12 +7,16 @@ can achieve on the same inputs."""
 import numpy as np
 import pytest
 
-from conftest import expo_model, linear_model, make_expo, make_linear, make_synth, rbq10_model
+from conftest import expo_model, linear_model, make_expo, make_linear, make_synth, rbq10_model, truth_trajectory
 
 pytestmark = pytest.mark.gpu
 
 RTOL_LOSS = 1e-5
 RTOL_GRAD = 1e-5
+# Single-sample batches: the seed 2 (yhat - y) c of ONE sample carries the whole Float32 rounding of yhat (no averaging),
+# so the Float32 reference itself misses 1e-5 there (measured: rbq10-swish, B = 1: Float32 oracle 1.82e-5, GPU 1.82e-5 --
+# gpurun_out / profiles/r2_parity_table.txt).  Every batch of two or more samples is held to 1e-5 without exception.
+RTOL_GRAD_SINGLE_SAMPLE = 2.5e-5
 
 CASES = [
     ("rbq10-tanh", lambda eh: rbq10_model(eh), lambda: make_synth(4000), "mse", "sum"),
@@ -59,14 +63,10 @@ def test_loss_and_gradient(eh, orc, name, mk, mkdata, loss, agg, engine_flags):
             continue
         L, g = sess.loss_grad(idx)
         L64, g64 = o.loss_grad(flat, xf, y, idx, precision=64)
-        L32, g32 = o.loss_grad(flat, xf, y, idx, precision=32)
         scale = np.abs(g64).max()
         assert abs(L - L64) <= RTOL_LOSS * abs(L64), (name, B, L, L64)
         err = np.abs(g - g64).max() / scale
-        err32 = np.abs(g32 - g64).max() / scale
-        # 1e-5 of the largest entry, or -- where Float32 arithmetic itself cannot reach that (tiny
-        # batches with cancelling terms) -- no worse than the reference-precision oracle
-        assert err <= max(RTOL_GRAD, 1.25 * err32), (name, B, err, err32)
+        assert err <= (RTOL_GRAD_SINGLE_SAMPLE if B == 1 else RTOL_GRAD), (name, B, err)
     sess.close()
 
 
@@ -76,10 +76,11 @@ def test_training_trajectory_rbq10(eh, orc):
                                               opt=None)
     perm = np.concatenate([rng.permutation(20000), rng.permutation(20000)])[: 50 * 512]
     got = sess.epoch(perm, 512)
-    ref = flat.copy()
-    want = o.train_steps(ref, xf, y, perm, 512)
-    np.testing.assert_allclose(got, want, rtol=2e-4)
-    assert abs(got[0] - want[0]) <= 1e-5 * abs(want[0])
+    # EVERY step within 1e-5 of the float64-gradient trajectory (the Float32 oracle, i.e. the reference's own precision,
+    # stays within 2e-6 of it on this run)
+    want, ref = truth_trajectory(o, flat, xf, y, perm, 512)
+    rel = np.abs(got - want) / np.abs(want)
+    assert rel.max() <= 1e-5, (int(rel.argmax()), float(rel.max()))
     ps = sess.get_params()
     q10 = lambda p: 1.0 + 3.0 / (1.0 + np.exp(-float(p[-1])))
     assert abs(q10(ps) - q10(ref)) <= 1e-4 * q10(ref)
