@@ -184,6 +184,7 @@ SIGNATURES = {
     "eh_last_timing": (C.c_int, [_p, _fp, _i64p, _fp]),
     "eh_set_profiling": (C.c_int, [_p, C.c_int32]),
     "eh_kernel_variant": (C.c_char_p, [_p]),
+    "eh_epoch_variant": (C.c_char_p, [_p, C.c_int64]),
     "eh_dp_batch_moments": (C.c_int, [_p, C.c_int64, C.POINTER(C.c_double)]),
     "eh_dp_set_batch_moments": (C.c_int, [_p, C.c_int64, C.POINTER(C.c_double)]),
     "eh_selftest_wide_gemm": (C.c_int, [C.c_int32] * 6 + [C.c_void_p] * 5 + [C.c_int32, C.c_void_p]),

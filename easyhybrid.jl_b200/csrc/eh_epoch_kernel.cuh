@@ -64,11 +64,23 @@ struct EpochArgs {
     int opt_kind, adamw_coupled;
     float eta, beta1, beta2, eps, lambda;
     long long* dbg;            // optional [nsteps][gridDim.x][32] SM-clock timestamps (EH_EPOCH_DEBUG)
+    // ---- consumer mode (host-batch stream, eh_step_host_async): the kernel is launched with the first batch of a burst
+    // and trains on ring slot (first_step + s) mod nb as soon as the packer kernel has published that slot; it leaves when
+    // the host has announced the number of steps of the burst and they are done.  nsteps is then only an upper bound.
+    const unsigned* ready;     // [nb] per-slot tags (NULL: not a stream); slot of step s carries ready_base + s + 1
+    unsigned ready_base;
+    unsigned* done;            // steps retired (absolute count = ready_base + s + 1), written by CTA 0; packers wait on it
+    const int* host_total;     // host-mapped: number of steps of this burst once the host knows it (0: still open)
+    float* loss_stream;        // [nsteps] host-mapped loss cells, written as the steps retire
+    long long batch_stride;    // records between consecutive batches of `rec` (0: B)
     // ---- data parallel: one process per GPU, peer memory mapped with CUDA IPC over NVLink ----
     int world, rank;
     unsigned step_base;        // steps exchanged by earlier launches (flags carry absolute step tags)
     uint2* inbox_peer[EH_MAX_WORLD];      // rank r's inbox [2][world][npartp] of {value bits, step tag}, as mapped here
     unsigned* err;             // set to 1 when a bounded spin gives up (peer / CTA never arrived)
+    int stagger_ns;            // tile engines: tile slot u of a CTA starts its step u * stagger_ns later (see the chunk loop)
+    int eng_off;               // byte offset of the engine's own shared-memory region (tensor engine: tf32 weight images,
+                               // mbarriers, TMEM slot); 0: none
 };
 
 // 8-byte accesses are single-copy atomic: value and tag always travel together
@@ -173,11 +185,12 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned 
     return ok != 0;
 }
 // bounded: a bulk copy that never lands raises the error flag instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity, unsigned* err)
+// (consumer mode waits for batches the host has not even submitted yet: no bound there)
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity, unsigned* err, bool unbounded = false)
 {
     unsigned spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 22)) { *err = 1; break; }
+        if (!unbounded && ++spins > (1u << 22)) { *err = 1; break; }
     }
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar)
@@ -203,9 +216,20 @@ __host__ __device__ constexpr int epoch_extra_floats(int npartp, int nflat, int 
     return npartp + 8 * rup4(nflat) + 2 * rup4(tile_floats) + 8 + epoch_xbuf_floats(npartp, G);
 }
 
+// warps that share one chunk (tile): 1 for the lane-per-sample engines, 4 for the tensor engine
+template <class E, class = void>
+struct EngWpc { static constexpr int value = 1; };
 template <class E>
-__global__ void __launch_bounds__((E::MAX_WARPS + 1) * 32 > 512 ? 512 : (E::MAX_WARPS + 1) * 32, 1) k_epoch(const EpochArgs a)
+struct EngWpc<E, decltype((void)E::WPC)> { static constexpr int value = E::WPC; };
+// threads of the persistent CTA: the engine's compute warps + the service warp; 512 (128 registers each) unless the
+// engine needs 16 compute warps (tensor engine: 544 threads of at most 120 registers)
+template <class E>
+constexpr int epoch_threads() { return EngWpc<E>::value > 1 ? (E::MAX_WARPS + 1) * 32 : ((E::MAX_WARPS + 1) * 32 > 512 ? 512 : (E::MAX_WARPS + 1) * 32); }
+
+template <class E>
+__global__ void __launch_bounds__(epoch_threads<E>(), 1) k_epoch(const EpochArgs a)
 {
+    constexpr int WPC = EngWpc<E>::value;
     using C = typename E::Cfg;
     extern __shared__ float4 smem4[];
     float* sW = reinterpret_cast<float*>(smem4);
@@ -229,6 +253,9 @@ __global__ void __launch_bounds__((E::MAX_WARPS + 1) * 32 > 512 ? 512 : (E::MAX_
     unsigned* phi_flag = reinterpret_cast<unsigned*>(mbar + 2);
     float2* xbuf = reinterpret_cast<float2*>(phi_flag + 4);   // [nown][2][G] values collected by this CTA as a slice owner (sized for G <= number of SMs)
     const int G = gridDim.x, bid = blockIdx.x;
+    unsigned char* eng = reinterpret_cast<unsigned char*>(smem4) + a.eng_off;
+    const int unit = warp / WPC, nunits = wcomp / WPC;   // this warp's tile slot, tile slots of the CTA
+    if constexpr (WPC > 1) E::cta_init(eng);
     const bool tiles = a.tile_floats > 0;
     constexpr int R44 = C::R4 / 4;
 
@@ -253,13 +280,21 @@ __global__ void __launch_bounds__((E::MAX_WARPS + 1) * 32 > 512 ? 512 : (E::MAX_
         mbar_init(&mbar[0], 1);
         mbar_init(&mbar[1], 1);
         *phi_flag = a.tag_base;   // the scalars loaded below belong to "step tag_base"
+        phi_flag[1] = 0u;         // stop flag of the consumer mode
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
 
     typename E::State st;
-    if (!service) E::init_warp(st, stage, lane);
+    if constexpr (WPC == 1) {
+        if (!service) E::init_warp(st, stage, lane);
+    }
     load_weights_and_scalars<C>(a.pblock, a.nflat, a.wsrc, nullptr, 0, sW, sS);
     __syncthreads();   // the batch-scalar cells are rewritten by other threads below (store_bs)
+    if constexpr (WPC > 1) {
+        E::load_w2(eng, sW);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the tensor core reads these images
+        if (!service) E::init_warp(st, stage, lane, eng);
+    }
 
     PmCtx cx;
     cx.pms = sS + SS_PMS;
@@ -277,6 +312,8 @@ __global__ void __launch_bounds__((E::MAX_WARPS + 1) * 32 > 512 ? 512 : (E::MAX_
     int bcur = (int)(a.first_step % a.nb);
     const int Blast = (int)(a.n - (long long)(a.nb - 1) * a.B);  // size of the (possibly partial) last batch
     auto batch_size = [&](int b) { return b == a.nb - 1 ? Blast : a.B; };
+    const long long bstride = a.batch_stride ? a.batch_stride : (long long)a.B;
+    const bool stream = a.ready != nullptr;
     // the service warp's lane 0 stages the CTA's records of batch b into tile buffer `buf` (one bulk copy; an empty
     // range still completes the mbarrier phase so that the parities keep counting steps)
     auto issue_tile = [&](int b, int buf) {
@@ -289,7 +326,7 @@ __global__ void __launch_bounds__((E::MAX_WARPS + 1) * 32 > 512 ? 512 : (E::MAX_
         if (s1 > s0) {
             const unsigned bytes = (unsigned)(s1 - s0) * (unsigned)(C::R4 * 4);
             mbar_expect_tx(&mbar[buf], bytes);
-            bulk_g2s(tile0 + (size_t)buf * (rup4(a.tile_floats) / 4), a.rec + ((long long)b * a.B + s0) * R44, bytes, &mbar[buf]);
+            bulk_g2s(tile0 + (size_t)buf * (rup4(a.tile_floats) / 4), a.rec + ((long long)b * bstride + s0) * R44, bytes, &mbar[buf]);
         } else {
             mbar_arrive(&mbar[buf]);
         }
@@ -299,7 +336,7 @@ __global__ void __launch_bounds__((E::MAX_WARPS + 1) * 32 > 512 ? 512 : (E::MAX_
         const int Bk = batch_size(b);
         fa.rec = a.rec;
         fa.idx = a.idx ? a.idx + (long long)b * a.B : nullptr;
-        fa.rec_base = a.idx ? 0 : (long long)b * a.B;
+        fa.rec_base = a.idx ? 0 : (long long)b * bstride;
         fa.B = Bk;
         fa.nchunks = (Bk + E::CHUNK - 1) / E::CHUNK;
         int c0, cnt;
@@ -308,31 +345,50 @@ __global__ void __launch_bounds__((E::MAX_WARPS + 1) * 32 > 512 ? 512 : (E::MAX_
         fa.tile_s0 = c0 * E::CHUNK;
         return fa;
     };
-    // per-batch scalars of the coming step, prefetched one step ahead (a dependent global load otherwise)
-    float pre_bs = 0.f;
-    auto prefetch_bs = [&](int batch) {
+    // Per-batch scalars (seed scales c_t, BatchNorm rows, valid counts): 32 values, one per lane of the SERVICE warp, which
+    // fetches them one step ahead and puts them into shared memory between the compute phases.
+    auto load_bs = [&](int batch) {
         const float* bs = a.bscal + (size_t)batch * BS_STRIDE;
-        if (threadIdx.x < MAXT) pre_bs = bs[BS_C + threadIdx.x];
-        else if (threadIdx.x < MAXT + 2 * C::P)
-            pre_bs = a.use_bn ? bs[BS_BN + threadIdx.x - MAXT] : (((threadIdx.x - MAXT) & 1) ? 1.f : 0.f);
-        else if (threadIdx.x >= 28 && threadIdx.x < 28 + MAXT) pre_bs = bs[BS_N + threadIdx.x - 28];
+        float v = 0.f;
+        if (lane < MAXT) v = bs[BS_C + lane];
+        else if (lane < MAXT + 2 * C::P) v = a.use_bn ? bs[BS_BN + lane - MAXT] : (((lane - MAXT) & 1) ? 1.f : 0.f);
+        else if (lane >= 28 && lane < 28 + MAXT) v = bs[BS_N + lane - 28];
+        return v;
     };
-    // ... and moved into shared memory for step `s` (after the compute phase of the step before has ended)
-    auto store_bs = [&](int s) {
-        if (threadIdx.x < MAXT) sS[SS_C + threadIdx.x] = pre_bs;
-        else if (threadIdx.x < MAXT + 2 * C::P) sS[SS_BN + threadIdx.x - MAXT] = pre_bs;
-        else if (threadIdx.x >= 28 && threadIdx.x < 28 + MAXT) sS[SS_NV2 + (s & 1) * MAXT + threadIdx.x - 28] = pre_bs;
+    auto store_bs = [&](float v, int s) {   // scalars of step s (valid counts double-buffered: the optimiser of step s - 1 may still read its own)
+        if (lane < MAXT) sS[SS_C + lane] = v;
+        else if (lane < MAXT + 2 * C::P) sS[SS_BN + lane - MAXT] = v;
+        else if (lane >= 28 && lane < 28 + MAXT) sS[SS_NV2 + (s & 1) * MAXT + lane - 28] = v;
     };
-    prefetch_bs(bcur);
-    store_bs(0);
+    // consumer mode: has the packer published the slot of step s?  (all lanes read the same word)
+    auto slot_ready = [&](int s, int batch) { return *reinterpret_cast<const volatile unsigned*>(a.ready + batch) == a.ready_base + (unsigned)s + 1u; };
+    // ... wait for it; false: the host has closed the burst before step s
+    auto wait_slot = [&](int s, int batch) {
+        for (;;) {
+            if (slot_ready(s, batch)) return true;
+            const int tot = *reinterpret_cast<const volatile int*>(a.host_total);
+            if (tot > 0 && s >= tot) return false;
+        }
+    };
+    volatile unsigned* stop_flag = phi_flag + 1;   // set by the service warp when the burst ends before a.nsteps (cleared above)
+    float pre = 0.f;
+    bool have_next = false;
+    if (service) {
+        bool go = true;
+        if (stream) go = wait_slot(0, bcur);
+        if (go) {
+            store_bs(load_bs(bcur), 0);
+        } else if (lane == 0) {
+            *stop_flag = 1u;
+        }
+    }
     __syncthreads();   // mbarriers initialised, weights / scalars / tables in place
-    if (tiles && service && lane == 0) issue_tile(bcur, 0);
-    if (a.nsteps > 1) prefetch_bs(bcur + 1 == a.nb ? 0 : bcur + 1);
+    if (tiles && service && lane == 0 && !*stop_flag) issue_tile(bcur, 0);
     if (!tiles && !service) {
         const FetchArgs f0 = fetch_args(bcur, 0);
         int c0, cnt;
         cta_chunk_range(f0.nchunks, G, bid, c0, cnt);
-        E::fetch(st, f0, warp < cnt ? c0 + warp : f0.nchunks, lane);
+        E::fetch(st, f0, unit < cnt ? c0 + unit : f0.nchunks, lane);
     }
 #define EH_STAMP(slot)                                                                      \
     if (a.dbg && threadIdx.x == 0) a.dbg[((size_t)s * G + bid) * 32 + (slot)] = clock64();
@@ -343,7 +399,9 @@ __global__ void __launch_bounds__((E::MAX_WARPS + 1) * 32 > 512 ? 512 : (E::MAX_
     const int nown = (NSL - bid + G - 1) / G;            // slices owned by this CTA (bid, bid + G, ...)
     const int ncomp_threads = wcomp * 32;
 
+    int s_end = a.nsteps;
     for (int s = 0; s < a.nsteps; s++) {
+        if (*stop_flag) { s_end = s; break; }
         EH_STAMP(0)
         const int bnext = bcur + 1 == a.nb ? 0 : bcur + 1;
         const int par = s & 1;
@@ -356,8 +414,13 @@ __global__ void __launch_bounds__((E::MAX_WARPS + 1) * 32 > 512 ? 512 : (E::MAX_
 
         // ---- compute phase ----
         if (service) {
-            // the tile of the next step: its buffer was last read in the compute phase of step s - 1
-            if (tiles && lane == 0 && s + 1 < a.nsteps) issue_tile(bnext, par ^ 1);
+            // the next step's scalars and record tile (its buffer was last read in the compute phase of step s - 1); in
+            // consumer mode only if its batch has already landed -- otherwise after this step (below)
+            have_next = s + 1 < a.nsteps && (!stream || slot_ready(s + 1, bnext));
+            if (have_next) {
+                pre = load_bs(bnext);
+                if (tiles && lane == 0) issue_tile(bnext, par ^ 1);
+            }
         } else {
             const FetchArgs fa = fetch_args(bcur, par);
             const FetchArgs fn = fetch_args(bnext, par ^ 1);
@@ -366,30 +429,47 @@ __global__ void __launch_bounds__((E::MAX_WARPS + 1) * 32 > 512 ? 512 : (E::MAX_
             cta_chunk_range(fn.nchunks, G, bid, n0, ncnt);
             // first chunk of this warp in the next step (gather mode prefetches it during the last chunk of this step:
             // index load + dependent record gather = two DRAM latencies, hidden behind the compute)
-            const int nfirst = (s + 1 < a.nsteps && warp < ncnt) ? n0 + warp : fn.nchunks;
+            const int nfirst = (s + 1 < a.nsteps && unit < ncnt) ? n0 + unit : fn.nchunks;
             E::step_begin(st, sW, lane);
             if (tiles) {
-                mbar_wait(&mbar[par], (unsigned)(s >> 1) & 1u, a.err);
-                E::fetch(st, fa, warp < cnt ? c0 + warp : fa.nchunks, lane);
+                mbar_wait(&mbar[par], (unsigned)(s >> 1) & 1u, a.err, stream);
+                if (*stop_flag) { s_end = s; break; }   // consumer mode: the burst ended, the barrier was released without a tile
+                E::fetch(st, fa, unit < cnt ? c0 + unit : fa.nchunks, lane);
             }
             cx.phi_want = a.tag_base + (unsigned)s;
-            for (int chunk = c0 + warp; chunk < c0 + cnt; chunk += wcomp) {
-                const bool last = chunk + wcomp >= c0 + cnt;
-                if (last && !tiles) E::chunk(st, fn, nfirst, sW, sS, stage, lane, a.slot, a.loss_kind, cx);
-                else E::chunk(st, fa, last ? fa.nchunks : chunk + wcomp, sW, sS, stage, lane, a.slot, a.loss_kind, cx);
+            if constexpr (WPC > 1) {
+                // The tile slots of a CTA would otherwise run in lockstep: all 16 warps in the MUFU-bound activation phases
+                // together, then all in the tensor-core round trips, then all in the HMMA / LDS-bound weight-gradient phase --
+                // every pipe saturated in its phase and idle in the others.  Starting slot u a little later than slot u - 1
+                // lets the phases of different tiles overlap (measured: DESIGN.md section 5.3).
+                if (a.stagger_ns > 0 && unit > 0) __nanosleep((unsigned)(unit * a.stagger_ns));
+            }
+            for (int chunk = c0 + unit; chunk < c0 + cnt; chunk += nunits) {
+                const bool last = chunk + nunits >= c0 + cnt;
+                if constexpr (WPC > 1) {
+                    if (last && !tiles) E::chunk(st, fn, nfirst, sW, sS, stage, lane, a.slot, a.loss_kind, cx, a.err);
+                    else E::chunk(st, fa, last ? fa.nchunks : chunk + nunits, sW, sS, stage, lane, a.slot, a.loss_kind, cx, a.err);
+                } else {
+                    if (last && !tiles) E::chunk(st, fn, nfirst, sW, sS, stage, lane, a.slot, a.loss_kind, cx);
+                    else E::chunk(st, fa, last ? fa.nchunks : chunk + nunits, sW, sS, stage, lane, a.slot, a.loss_kind, cx);
+                }
             }
             if (a.dbg && lane == 0) a.dbg[((size_t)s * G + bid) * 32 + 8 + warp] = clock64();
             // a warp without a chunk in this step still has to fetch its first sample of the next one
-            if (!tiles && warp >= cnt) E::fetch(st, fn, nfirst, lane);
-            if (!E::SCRATCH_ALIASES_STAGE) E::reduce_prepare(st, stage0);
+            if (!tiles && unit >= cnt) E::fetch(st, fn, nfirst, lane);
+            if constexpr (WPC > 1) E::reduce_prepare(st, stage0, a.err);
+            else if (!E::SCRATCH_ALIASES_STAGE) E::reduce_prepare(st, stage0);
         }
         EH_STAMP(1)
-        if (E::SCRATCH_ALIASES_STAGE) {
-            __syncthreads();   // every warp is done with its staging tile; the work region becomes the reduction rows
-            if (!service) E::reduce_prepare(st, stage0);
+        if constexpr (WPC == 1) {
+            if (E::SCRATCH_ALIASES_STAGE) {
+                __syncthreads();   // every warp is done with its staging tile; the work region becomes the reduction rows
+                if (!service) E::reduce_prepare(st, stage0);
+            }
         }
         __syncthreads();
         EH_STAMP(2)
+        if (service && have_next) store_bs(pre, s + 1);   // the compute phase that read the cells of step s has ended
 
         // ---- A: CTA partial, published in vector order as 16-byte {value, tag, value, tag} pairs (coalesced) ----
         for (int k = threadIdx.x; k < a.npartp / 2; k += blockDim.x) {
@@ -467,7 +547,21 @@ __global__ void __launch_bounds__((E::MAX_WARPS + 1) * 32 > 512 ? 512 : (E::MAX_
             if (a.loss_kind[t] == LOSS_RMSE) post = 1.f / (2.f * sqrtf(red[E::OFF_STATS + t] / nv));
         }
         const bool skip = ntot == 0.f;  // all-masked batch: epoch.jl:17-19
-        if (bid == 0 && service && lane < MAXT) a.stats_out[(size_t)s * MAXT + lane] = red[E::OFF_STATS + lane];
+        if (bid == 0 && service) {
+            if (lane < MAXT) a.stats_out[(size_t)s * MAXT + lane] = red[E::OFF_STATS + lane];
+            if (stream && lane == 0) {
+                // consumer mode: the loss of this step straight into the host's page-locked cell (loss_fn.jl:58-66; agg
+                // over the targets, compute_loss.jl:50-53), and the retired-step count the packers wait on
+                float L = 0.f;
+                for (int t = 0; t < a.T; t++) {
+                    const float nv = sS[SS_NV2 + par * MAXT + t], acc = red[E::OFF_STATS + t];
+                    L += a.loss_kind[t] == LOSS_RMSE ? sqrtf(acc / nv) : acc / nv;
+                }
+                if (a.agg_mean) L /= (float)a.T;
+                a.loss_stream[s] = skip ? __int_as_float(0x7fc00000) : L;
+                *reinterpret_cast<volatile unsigned*>(a.done) = a.ready_base + (unsigned)s + 1u;
+            }
+        }
         // bias corrections are step constants: their reciprocals are ready before the sums arrive
         const float rb1 = 1.f / (1.f - b1t), rb2 = 1.f / (1.f - b2t);
         // compute warps own theta (entry p on thread p, ...), the service warp owns phi
@@ -506,6 +600,10 @@ __global__ void __launch_bounds__((E::MAX_WARPS + 1) * 32 > 512 ? 512 : (E::MAX_
                 const int c0 = t_cell0[p], c1 = t_cell1[p];
                 if (c0 >= 0) sW[c0] = th;
                 if (c1 >= 0) sW[c1] = th;
+                if constexpr (WPC > 1) {   // the tensor engine's tf32 images of the hidden-layer weights
+                    if (c0 >= 0) E::patch_cell(eng, c0, th);
+                    if (c1 >= 0) E::patch_cell(eng, c1, th);
+                }
                 if (p >= a.ntheta) {
                     const float sgn = 1.f / (1.f + expf(-th));
                     if (phi_cached) sS[SS_SGD + p - a.ntheta] = t_span[p] * sgn * (1.f - sgn);
@@ -527,21 +625,33 @@ __global__ void __launch_bounds__((E::MAX_WARPS + 1) * 32 > 512 ? 512 : (E::MAX_
             tskip++;
         }
         EH_STAMP(5)
-        // the next step's batch scalars (seed scales / BN rows are only read in the compute phase, which has ended)
-        if (s + 1 < a.nsteps) {
-            store_bs(s + 1);
-            if (s + 2 < a.nsteps) prefetch_bs(bnext + 1 == a.nb ? 0 : bnext + 1);
-        }
         if (service) {
             // the global parameters' scalars of step s + 1 are in place: publish (consumers: PmCtx::wait_phi)
             __syncwarp();
             __threadfence_block();
             if (lane == 0) asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(phi_flag)), "r"(tag) : "memory");
             EH_STAMP_SVC(27)
+            if (stream && !have_next && s + 1 < a.nsteps) {
+                // consumer mode, the next batch had not landed when this step began: wait for it now (the compute warps are
+                // parked on the tile's mbarrier), or learn that the burst is over
+                if (wait_slot(s + 1, bnext)) {
+                    store_bs(load_bs(bnext), s + 1);
+                    __syncwarp();   // the scalars of all lanes before lane 0's arrive (release) on the tile barrier
+                    if (lane == 0) issue_tile(bnext, par ^ 1);
+                } else {
+                    if (lane == 0) {
+                        *stop_flag = 1u;
+                        __threadfence_block();
+                        mbar_arrive(&mbar[par ^ 1]);   // releases the compute warps, which then see the flag
+                    }
+                    __syncwarp();
+                }
+            }
         }
         // end-of-step barrier of the compute warps: all theta patches of the weight image and the next step's batch
         // scalars are visible
         if (!service) {
+            if constexpr (WPC > 1) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // patched tf32 images -> tensor core
             bar_sync_id(1, blockDim.x);
             E::after_reduce(st, stage, lane);  // constant staging rows were overwritten by the scratch / vectors
         }
@@ -553,6 +663,7 @@ __global__ void __launch_bounds__((E::MAX_WARPS + 1) * 32 > 512 ? 512 : (E::MAX_
 
     // write back (CTA 0 holds the same state as everybody else)
     __syncthreads();
+    if constexpr (WPC > 1) E::cta_exit(eng);
     if (bid == 0) {
         for (int p = threadIdx.x; p < a.nflat; p += blockDim.x) {
             a.pblock[p] = s_th[p];

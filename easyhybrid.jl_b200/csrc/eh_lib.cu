@@ -60,6 +60,19 @@ constexpr int EH_NPACK = EH_NPACK_STREAMS;  // host-batch packers / copies in fl
 // of the next group keep the PCIe link busy.  Three groups: one training, one being packed, one draining.
 constexpr int EH_RING_GROUP = 16, EH_RING_NGRP = 3;
 constexpr int64_t EH_RING_MAX_BATCH = 1 << 18;   // batches beyond this take the one-launch-pair-per-batch form
+// consumer mode of eh_step_host_async: ONE persistent launch per burst trains on the ring slots as the packers publish them
+struct HostStream {
+    bool active = false;       // a consumer kernel is running
+    bool off = false;          // EH_HOST_NO_STREAM=1: grouped launches instead
+    int64_t B = 0;             // batch size of the running burst
+    unsigned global = 0;       // batches ever handed to this mode (slot = global % slots); tags and `done` count in it
+    int count = 0;             // steps of the running burst so far
+    int* h_total = nullptr;    // page-locked: number of steps of the burst, written when the burst is closed
+    unsigned* d_ready = nullptr;   // [slots]
+    unsigned* d_done = nullptr;    // [1]
+};
+constexpr int EH_STREAM_MAX_STEPS = 4096;   // steps per consumer launch (statistics buffer); longer bursts are cut there
+
 struct HostRing {
     float* d_rec = nullptr;    // [NGRP][GROUP * cap][R4]; slot k of a group starts at record k * B (B = the group's batch size)
     float* d_bscal = nullptr;  // [NGRP * GROUP][BS_STRIDE]
@@ -69,6 +82,9 @@ struct HostRing {
     bool used[EH_RING_NGRP] = {false, false, false};
     int64_t cap = 0;           // samples per slot
     int g = 0, k = 0;          // open group, batches packed into it so far
+    unsigned rr = 0;           // round robin over the pack streams
+    int limit = 1;             // size at which the open group is launched: 1, 2, 4, 8, 16, 16, ... within a burst (the first
+                               // steps start while later batches are still crossing PCIe); back to 1 at eh_sync
     int64_t B = 0;             // batch size of the open group
     float* loss0 = nullptr;    // page-locked loss cell of the group's first step (the others follow contiguously)
     bool off = false;          // EH_HOST_NO_GROUPS=1
@@ -85,6 +101,7 @@ struct eh_ctx {
     cudaStream_t pack_stream[EH_NPACK] = {};   // packers of consecutive host batches rotate over these ([0] == copy_stream)
     const Variant* var = nullptr;   // engine chosen at eh_create (FFMA2 one sample per lane, or tensor pipe)
     const Variant* var2 = nullptr;  // FFMA2 two samples per lane: same layouts, used for large batches
+    const Variant* var_tc = nullptr;  // tensor engine (tcgen05 tiles of 128 samples): same layouts, persistent kernel, large batches
     // wide-hidden-layer path (bf16 tcgen05 GEMMs, eh_wide.cu): `var` then points at `wide_var`, a descriptor
     // without kernels that only carries the record / slot geometry the shared host code reads
     eh::wide::WideNet* wide = nullptr;
@@ -167,6 +184,7 @@ struct eh_ctx {
     PmProgData h_prog;           // the program, host copy
     PmProgData* d_prog = nullptr;
     bool host_zero_copy = true;  // EH_HOST_NO_ZEROCOPY=1: always stage host batches through the copy engine
+    HostStream hstream;
     std::vector<std::pair<float*, float*>> pending_loss;  // (pinned src, user dst)
     struct PendingBn { const float* loss; const float* mom; int64_t B; };
     std::vector<PendingBn> pending_bn;                      // host batches whose BatchNorm batch moments still have to be folded in
@@ -306,6 +324,13 @@ struct PackHostArgs {
                                             // (NaN-free targets are a precondition of host batches in that mode)
     int* cnt;                               // [MAXT + 1] valid-target counters + ticket (all zero between launches)
     float* bscal;                           // per-batch scalar row to fill (NULL: K0 computes it from the records)
+    // consumer mode (the persistent kernel of a burst is already running, eh_epoch_kernel.cuh): the slot may only be
+    // overwritten once the step that last trained on it has retired (*wait_done >= wait_min), and the kernel picks the
+    // batch up as soon as *ready == ready_val
+    const unsigned* wait_done;
+    unsigned wait_min;
+    unsigned* ready;
+    unsigned ready_val;
 };
 
 __device__ __forceinline__ float pack_host_load(const PackHostArgs& a, int c, long long i)
@@ -318,6 +343,11 @@ __device__ __forceinline__ float pack_host_load(const PackHostArgs& a, int c, lo
 
 __global__ void __launch_bounds__(1024) k_pack_host(const PackHostArgs a)
 {
+    if (a.wait_done) {
+        if (threadIdx.x == 0)
+            while ((int)(*reinterpret_cast<const volatile unsigned*>(a.wait_done) - a.wait_min) < 0) {}
+        __syncthreads();
+    }
     int valid[MAXT] = {0, 0, 0, 0};
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long first = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -391,6 +421,13 @@ __global__ void __launch_bounds__(1024) k_pack_host(const PackHostArgs a)
         a.bscal[BS_BN + 2 * k] = 0.f;
         a.bscal[BS_BN + 2 * k + 1] = 1.f;
     }
+    if (a.ready) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();   // records (all CTAs, ordered by the ticket) and the scalar row before the flag
+            *reinterpret_cast<volatile unsigned*>(a.ready) = a.ready_val;
+        }
+    }
 }
 
 // device-visible address of a page-locked host array (cudaHostAlloc / cudaHostRegister), NULL for anything else
@@ -415,6 +452,21 @@ const Variant* pick_variant(const eh_ctx* c, int64_t B)
 {
     if (c->var2 && getenv("EH_USE_X2") && B >= (int64_t)c->nsm * 4 * c->var2->chunk) return c->var2;
     return c->var;
+}
+
+// ... and which one serves a persistent launch: the tensor engine pays off once every SM has a few 128-sample tiles per
+// step (EH_TC_MIN_BATCH overrides the threshold)
+// 0: the tensor engine is opt-in (EH_TC_MIN_BATCH=<batch size from which it serves the persistent launches>)
+constexpr long long EH_TC_DEFAULT_MIN_BATCH = 0;
+const Variant* pick_epoch_variant(const eh_ctx* c, int64_t B)
+{
+    const Variant* v = pick_variant(c, B);
+    if (c->var_tc && v == c->var) {
+        const char* e = getenv("EH_TC_MIN_BATCH");   // (read per call: tests switch it)
+        const long long tc_min = e ? atoll(e) : EH_TC_DEFAULT_MIN_BATCH;
+        if (tc_min > 0 && B >= tc_min) v = c->var_tc;
+    }
+    return v;
 }
 
 Geom step_geometry(const eh_ctx* c, int64_t B, int reserve_sms = 0)
@@ -707,18 +759,25 @@ eh_status ensure_pass_graph(eh_ctx* c, int64_t n, int64_t B, bool pdl)
 // packer kernels), w compute warps + one service warp per CTA.
 // enqueue only (no host synchronisation): rec/idx/bscal select the data source, per-step loss sums go to
 // c->d_stats and the losses to loss_out (device)
+struct StreamLaunch {   // consumer mode (EpochArgs: ready .. batch_stride)
+    const unsigned* ready; unsigned ready_base; unsigned* done; const int* host_total; float* loss_stream; long long batch_stride;
+};
+
 eh_status enqueue_persistent(eh_ctx* c, const float* rec, const int* idx, const float* bscal, float* loss_out, int64_t n,
-                             int64_t B, int64_t first, int64_t nsteps, bool* used, long long** dbg_out, int reserve_sms = 0)
+                             int64_t B, int64_t first, int64_t nsteps, bool* used, long long** dbg_out, int reserve_sms = 0,
+                             const StreamLaunch* sl = nullptr)
 {
     *used = false;
-    const Variant* v = pick_variant(c, B);
+    const Variant* v = pick_epoch_variant(c, B);
     const int64_t nb = (n + B - 1) / B;
     const int npartp = rup4(v->NPART);
     const size_t fixed = (size_t)(rup4(v->NW) + SS_FLOATS) * 4;
     const size_t stage = (size_t)std::max(v->stage_floats, v->NPART) * 4;
-    auto extra_of = [&](int tile_floats) { return (size_t)epoch_extra_floats(npartp, c->nflat, tile_floats, c->nsm) * 4 + 64; };
+    const size_t eng_bytes = v->eng_bytes ? (size_t)v->eng_bytes + 128 : 0;   // engine-private region at the end (128-byte aligned)
+    auto extra_of = [&](int tile_floats) { return (size_t)epoch_extra_floats(npartp, c->nflat, tile_floats, c->nsm) * 4 + 64 + eng_bytes; };
     const size_t smem_cap = c->smem_optin - 256;
-    if (fixed + extra_of(0) + stage > smem_cap) return EH_OK;  // does not fit: two-kernel path
+    const int wpc = std::max(1, v->wpc);
+    if (fixed + extra_of(0) + (size_t)wpc * stage > smem_cap) return EH_OK;  // does not fit: two-kernel path
     const int64_t nchunks = (B + v->chunk - 1) / v->chunk;
     const char* ew = getenv("EH_EPOCH_WARPS");
     const char* eg = getenv("EH_EPOCH_GRID");
@@ -727,15 +786,26 @@ eh_status enqueue_persistent(eh_ctx* c, const float* rec, const int* idx, const 
     const int mode = (idx ? 1 : 0) | (reserve_sms << 1);
     if (!(c->geo_var == v && c->geo_B == B && c->geo_mode == mode)) {
         // at most 15 compute warps: with the service warp the CTA has 512 threads (128 registers each)
-        int wcap = (int)std::min<size_t>((size_t)std::min(v->max_warps, 15), (smem_cap - fixed - extra_of(0)) / stage);
+        int wcap = (int)std::min<size_t>((size_t)std::min(v->max_warps, wpc > 1 ? 16 : 15), (smem_cap - fixed - extra_of(0)) / stage);
         if (ew) wcap = std::max(1, std::min(atoi(ew), wcap));
+        wcap -= wcap % wpc;
+        if (wcap < wpc) return EH_OK;
         int max_ctas = 0;
         if (v->epoch_max_grid(wcap + 1, fixed + extra_of(0) + (size_t)wcap * stage, &max_ctas) != cudaSuccess) { cudaGetLastError(); return EH_OK; }
         max_ctas = std::min(max_ctas, std::max(1, c->nsm - reserve_sms));
         if (eg) max_ctas = std::max(1, std::min(max_ctas, atoi(eg)));
         if (max_ctas < 1) return EH_OK;
         int w, G;
-        if (!ew && nchunks <= 8 && wcap >= 8) {
+        if (wpc > 1) {
+            // tile engines: `wpc` warps per tile; fewest rounds, then the fewest tile slots per CTA (at least two), then the
+            // smallest grid that covers the batch
+            const int ucap = wcap / wpc;
+            const int64_t per_cta = (nchunks + max_ctas - 1) / max_ctas;
+            const int64_t rounds = (per_cta + ucap - 1) / ucap;
+            const int u = ew ? ucap : (int)std::min<int64_t>(ucap, std::max<int64_t>(2, (per_cta + rounds - 1) / rounds));
+            w = u * wpc;
+            G = (int)std::max<int64_t>(1, std::min<int64_t>(max_ctas, (nchunks + (int64_t)u * rounds - 1) / ((int64_t)u * rounds)));
+        } else if (!ew && nchunks <= 8 && wcap >= 8) {
             // a batch of <= 256 samples runs in ONE CTA of 8 compute warps and needs no grid-wide exchange at all
             w = 8; G = 1;
         } else {
@@ -784,6 +854,16 @@ eh_status enqueue_persistent(eh_ctx* c, const float* rec, const int* idx, const 
     a.opt_kind = c->opt_kind; a.adamw_coupled = c->adamw_coupled;
     a.eta = c->eta; a.beta1 = c->beta1; a.beta2 = c->beta2; a.eps = c->eps; a.lambda = c->lambda;
     a.world = c->world; a.rank = c->rank; a.step_base = c->dp_steps; a.err = c->d_dperr;
+    {
+        const int stagger = getenv("EH_TC_STAGGER_NS") ? atoi(getenv("EH_TC_STAGGER_NS")) : 0;
+        a.stagger_ns = wpc > 1 ? stagger : 0;
+    }
+    a.eng_off = v->eng_bytes ? (int)((smem - (size_t)v->eng_bytes) & ~(size_t)127) : 0;
+    if (sl) {
+        if (!tile_floats) return EH_OK;   // the consumer mode hands batches over through the record tiles
+        a.ready = sl->ready; a.ready_base = sl->ready_base; a.done = sl->done; a.host_total = sl->host_total;
+        a.loss_stream = sl->loss_stream; a.batch_stride = sl->batch_stride;
+    }
     for (int r = 0; r < c->world && c->world > 1; r++) {
         a.inbox_peer[r] = reinterpret_cast<uint2*>(c->dp_peer[r]);
     }
@@ -847,10 +927,12 @@ eh_status enqueue_persistent(eh_ctx* c, const float* rec, const int* idx, const 
     c->epoch_tiles = tile_floats > 0; c->epoch_grid = G; c->epoch_warps = w;
     if (c->world > 1) c->dp_steps += (unsigned)nsteps;
     c->epoch_tag += (unsigned)nsteps;
-    k_losses_from_stats<<<(unsigned)((nsteps + 127) / 128), 128, 0, c->stream>>>(c->d_stats, bscal, first, (int)nb,
-                                                                                 (int)nsteps, c->n_targ, c->agg_mean,
-                                                                                 c->d_losskind, loss_out);
-    CK(cudaGetLastError());
+    if (!sl) {   // (the consumer mode writes its losses itself, step by step)
+        k_losses_from_stats<<<(unsigned)((nsteps + 127) / 128), 128, 0, c->stream>>>(c->d_stats, bscal, first, (int)nb,
+                                                                                     (int)nsteps, c->n_targ, c->agg_mean,
+                                                                                     c->d_losskind, loss_out);
+        CK(cudaGetLastError());
+    }
     *used = true;
     return EH_OK;
 }
@@ -1064,7 +1146,9 @@ eh_status epoch_pipelined(eh_ctx* c, const int64_t* perm1, int64_t n, int64_t B,
 {
     *used = false;
     const int64_t nb = (n + B - 1) / B;
-    if (nb < 64 || !c->persist_ok || (c->flags & EH_FLAG_NO_PERSIST) || c->profiling) return EH_OK;
+    // (the 8-byte host permutation is the largest transfer of this path: 8 B per sample against 11 us of training per 65 536
+    // samples -- it is streamed in segments behind the training for every epoch of 8 or more batches)
+    if (nb < 8 || !c->persist_ok || (c->flags & EH_FLAG_NO_PERSIST) || c->profiling) return EH_OK;
     const Split& sp = c->split[EH_SPLIT_TRAIN];
     if (!sp.rec) return fail(c, EH_EINVAL, "train split not uploaded");
     if (needs_data_stats(c) && c->world > 1) return EH_OK;  // the plain path reports it
@@ -1085,7 +1169,7 @@ eh_status epoch_pipelined(eh_ctx* c, const int64_t* perm1, int64_t n, int64_t B,
     CK(cudaMemcpyAsync(snap + 3 * c->nflat + PARAM_TAIL, c->d_ost, sizeof(OptState), cudaMemcpyDeviceToDevice, c->stream));
     const std::vector<float> bn_mean0 = c->bn_mean, bn_var0 = c->bn_var;
 
-    const int64_t seg = std::max<int64_t>(32, (nb + 7) / 8);  // steps per segment
+    const int64_t seg = std::max<int64_t>(nb >= 256 ? 32 : 4, (nb + 7) / 8);  // steps per segment
     const int64_t nseg = (nb + seg - 1) / seg;
     while ((int64_t)c->seg_ev.size() < nseg) {
         cudaEvent_t e;
@@ -1621,6 +1705,7 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
         }
     }
     c->var2 = (v->engine == 0) ? find_variant(v->pm, v->P, v->NH, v->H, v->NOUT, v->act, v->scale, 2) : nullptr;
+    c->var_tc = (v->engine == 0 && !use_prog && !getenv("EH_NO_TC")) ? find_variant(v->pm, v->P, v->NH, v->H, v->NOUT, v->act, v->scale, 4) : nullptr;
     c->n_pred_raw = d->n_pred; c->n_forc_raw = d->n_forc; c->n_targ = d->n_targ;
     c->use_bn = ch.input_batchnorm ? 1 : 0;
     c->real_in = Pt;
@@ -2031,7 +2116,7 @@ eh_status flush_host_group(eh_ctx* c)
     const int64_t B = r.B;
     r.k = 0;
     r.g = (g + 1) % EH_RING_NGRP;
-    for (int i = 0; i < EH_NPACK && i < k; i++) {
+    for (int i = 0; i < EH_NPACK; i++) {   // (packers rotate over the pack streams across groups: wait for all of them)
         CK(cudaEventRecord(r.packed[i], c->pack_stream[i]));
         CK(cudaStreamWaitEvent(c->stream, r.packed[i], 0));
     }
@@ -2061,6 +2146,88 @@ eh_status flush_host_group(eh_ctx* c)
     return EH_OK;
 }
 
+// close the running burst of the consumer mode: tell the kernel how many steps there are, wait for it
+eh_status end_host_stream(eh_ctx* c)
+{
+    HostStream& hs = c->hstream;
+    if (!hs.active) return EH_OK;
+    *reinterpret_cast<volatile int*>(hs.h_total) = hs.count;
+    hs.active = false;
+    unsigned herr = 0;
+    CK(cudaMemcpyAsync(&herr, c->d_dperr, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < EH_NPACK; i++) CK(cudaStreamSynchronize(c->pack_stream[i]));
+    if (herr) {
+        cudaMemset(c->d_dperr, 0, sizeof(unsigned));
+        return fail(c, EH_ENCCL, "persistent kernel gave up waiting (a CTA never arrived)");
+    }
+    return EH_OK;
+}
+
+// consumer mode: pack one page-locked batch into its ring slot; the first batch of a burst also launches the persistent
+// kernel that trains on the slots as they are published.  *taken = false: not eligible, the caller takes another path.
+eh_status stream_enqueue(eh_ctx* c, int64_t B, const PackHostArgs& z0, float* pin, bool* taken)
+{
+    *taken = false;
+    HostStream& hs = c->hstream;
+    HostRing& r = c->ring;
+    const Variant* v = c->var;
+    if (hs.off || c->world > 1 || getenv("EH_NO_COOP")) return EH_OK;
+    if (hs.active && (B != hs.B || hs.count >= EH_STREAM_MAX_STEPS)) {
+        eh_status s = end_host_stream(c);
+        if (s != EH_OK) return s;
+    }
+    if (B > r.cap) {
+        eh_status s = end_host_stream(c);
+        if (s != EH_OK) return s;
+        s = ensure_ring(c, B);
+        if (s != EH_OK) return s;
+    }
+    const int nslots = EH_RING_NGRP * EH_RING_GROUP;
+    if (!hs.h_total) {
+        CK(cudaMallocHost((void**)&hs.h_total, 64));
+        *hs.h_total = 0;
+        CK(dalloc(&hs.d_ready, (size_t)nslots));
+        CK(dalloc(&hs.d_done, (size_t)4));
+        CK(cudaMemset(hs.d_ready, 0, nslots * sizeof(unsigned)));
+        CK(cudaMemset(hs.d_done, 0, 4 * sizeof(unsigned)));
+    }
+    const unsigned g = hs.global;
+    const int slot = (int)(g % (unsigned)nslots);
+    if (!hs.active) {
+        // open a burst: the consumer kernel first (it waits for slot `slot`), on the compute stream
+        *reinterpret_cast<volatile int*>(hs.h_total) = 0;
+        if ((size_t)EH_STREAM_MAX_STEPS > c->stats_cap) {
+            if (c->d_stats) cudaFree(c->d_stats);
+            c->d_stats = nullptr; c->stats_cap = 0;
+            CK(dalloc(&c->d_stats, (size_t)EH_STREAM_MAX_STEPS * MAXT));
+            c->stats_cap = EH_STREAM_MAX_STEPS;
+        }
+        StreamLaunch sl{hs.d_ready, g, hs.d_done, hs.h_total, pin, (long long)r.cap};
+        bool used = false;
+        eh_status s = enqueue_persistent(c, r.d_rec, nullptr, r.d_bscal, nullptr, (int64_t)nslots * B, B, slot, EH_STREAM_MAX_STEPS, &used,
+                                         nullptr, EH_PACK_HOST_CTAS, &sl);
+        if (s != EH_OK) return s;
+        if (!used) { hs.off = true; return EH_OK; }   // (no persistent kernel for this shape: grouped / per-step path)
+        hs.active = true; hs.B = B; hs.count = 0;
+    }
+    PackHostArgs z = z0;
+    z.rec = r.d_rec + (size_t)slot * r.cap * v->R4;
+    z.cnt = r.d_cnt + (size_t)slot * (MAXT + 1);
+    z.bscal = r.d_bscal + (size_t)slot * BS_STRIDE;
+    z.wait_done = g >= (unsigned)nslots ? hs.d_done : nullptr;
+    z.wait_min = g - (unsigned)nslots + 1u;
+    z.ready = hs.d_ready + slot;
+    z.ready_val = g + 1u;
+    const int ctas = (int)std::min<int64_t>(EH_PACK_HOST_CTAS / EH_NPACK, (B + 1023) / 1024);
+    k_pack_host<<<ctas, 1024, 0, c->pack_stream[(r.rr++) % EH_NPACK]>>>(z);
+    CK(cudaGetLastError());
+    hs.global = g + 1u;
+    hs.count++;
+    *taken = true;
+    return EH_OK;
+}
+
 // pack one page-locked batch into the open group; *taken = false when the batch has to go the per-step way
 eh_status ring_enqueue(eh_ctx* c, int64_t B, const float* X, const float* const* forc, const float* const* targ, float* pin,
                        bool* taken)
@@ -2082,6 +2249,18 @@ eh_status ring_enqueue(eh_ctx* c, int64_t B, const float* X, const float* const*
         if (!(z.plane[f] = mapped_host_ptr(forc[f]))) return EH_OK;
     for (int t = 0; t < c->n_targ; t++)
         if (!(z.plane[c->n_forc_raw + t] = mapped_host_ptr(targ[t]))) return EH_OK;
+    z.N = B; z.P_raw = c->n_pred_raw; z.ncols = c->ncols; z.R4 = v->R4;
+    for (int i = 0; i < c->ncols; i++) { z.src_kind[i] = c->src_kind[i]; z.src_idx[i] = c->src_idx[i]; }
+    z.x_pair = c->n_pred_raw == 2 && c->ncols >= 2 && c->src_kind[0] == 0 && c->src_idx[0] == 0 && c->src_kind[1] == 0 &&
+               c->src_idx[1] == 1 && ((uintptr_t)z.X & 7) == 0;
+    z.T = c->n_targ; z.ycol0 = v->P + v->F; z.agg_mean = c->agg_mean; z.world = c->world;
+    if (r.k == 0) {
+        // consumer mode first: one persistent launch per burst, batches picked up as their packers publish them
+        bool st = false;
+        eh_status s = stream_enqueue(c, B, z, pin, &st);
+        if (s != EH_OK) return s;
+        if (st) { *taken = true; return EH_OK; }
+    }
     if (r.k > 0 && B != r.B) {
         eh_status s = flush_host_group(c);
         if (s != EH_OK) return s;
@@ -2099,21 +2278,22 @@ eh_status ring_enqueue(eh_ctx* c, int64_t B, const float* X, const float* const*
         }
     }
     const int slot = g * EH_RING_GROUP + k;
-    z.N = B; z.P_raw = c->n_pred_raw; z.ncols = c->ncols; z.R4 = v->R4;
-    for (int i = 0; i < c->ncols; i++) { z.src_kind[i] = c->src_kind[i]; z.src_idx[i] = c->src_idx[i]; }
-    z.x_pair = c->n_pred_raw == 2 && c->ncols >= 2 && c->src_kind[0] == 0 && c->src_idx[0] == 0 && c->src_kind[1] == 0 &&
-               c->src_idx[1] == 1 && ((uintptr_t)z.X & 7) == 0;
     z.rec = r.d_rec + ((size_t)g * EH_RING_GROUP * r.cap + (size_t)k * B) * v->R4;
-    z.T = c->n_targ; z.ycol0 = v->P + v->F; z.agg_mean = c->agg_mean; z.world = c->world;
     z.cnt = r.d_cnt + (size_t)slot * (MAXT + 1);
     z.bscal = r.d_bscal + (size_t)slot * BS_STRIDE;
     // EH_NPACK packers may be in flight (one per pack stream): they share the reserved SMs
     const int ctas = (int)std::min<int64_t>(EH_PACK_HOST_CTAS / EH_NPACK, (B + 1023) / 1024);
-    k_pack_host<<<ctas, 1024, 0, c->pack_stream[k % EH_NPACK]>>>(z);
+    k_pack_host<<<ctas, 1024, 0, c->pack_stream[(r.rr++) % EH_NPACK]>>>(z);
     CK(cudaGetLastError());
     r.k = k + 1;
     *taken = true;
-    if (r.k == EH_RING_GROUP) return flush_host_group(c);
+    if (r.k >= r.limit) {
+        // group sizes within a burst: 1, 2, 4, 8, 16, 16, ... (the first steps start while later batches still cross PCIe;
+        // measured at 20 x 65 536-sample batches: 1.84e9 -> 2.27e9 samples/s; constant small groups lose more to the
+        // ~50 us every launch costs than they win)
+        r.limit = std::min(EH_RING_GROUP, 2 * r.limit);
+        return flush_host_group(c);
+    }
     return EH_OK;
 }
 
@@ -2123,6 +2303,10 @@ eh_status ring_enqueue(eh_ctx* c, int64_t B, const float* X, const float* const*
 #define EH_ENTER(c)                                             \
     do {                                                        \
         CK(cudaSetDevice((c)->device));                         \
+        if ((c)->hstream.active) {                              \
+            eh_status fs__ = end_host_stream(c);                \
+            if (fs__ != EH_OK) return fs__;                     \
+        }                                                       \
         if ((c)->ring.k) {                                      \
             eh_status fs__ = flush_host_group(c);               \
             if (fs__ != EH_OK) return fs__;                     \
@@ -2174,6 +2358,12 @@ eh_status eh_create(eh_ctx** out, const eh_model_desc* desc)
         if (const char* e = getenv("EH_HOST_NO_GROUPS")) c->ring.off = e[0] && e[0] != '0';
         if (const char* e = getenv("EH_NO_STAGE")) c->stage_on = !(e[0] && e[0] != '0');
         if (const char* e = getenv("EH_NO_PGRAPH")) c->pg_off = e[0] && e[0] != '0';
+        // consumer mode of eh_step_host_async (one persistent launch per burst that waits for the packers): OPT-IN with
+        // EH_HOST_STREAM=1.  While a burst is open the kernel spins on host progress, so ANY device-synchronising call of
+        // the process (cudaFree / cudaMallocHost / cudaHostRegister, another library's allocator, a finaliser) deadlocks
+        // against it; measured it is no faster than the ramped grouped launches.
+        c->hstream.off = true;
+        if (const char* e = getenv("EH_HOST_STREAM")) c->hstream.off = !(e[0] && e[0] != '0');
         CK(cudaEventCreate(&c->ev0));
         CK(cudaEventCreate(&c->ev1));
         CK(cudaEventCreate(&c->ev2));
@@ -2184,6 +2374,7 @@ eh_status eh_create(eh_ctx** out, const eh_model_desc* desc)
         if (wmax < 1) return fail(c, EH_EUNSUPPORTED, "variant %s needs %zu B of shared memory per warp", v->name, stage);
         if (v->prepare) CK(v->prepare(c->smem_optin - 256, fixed));  // kernels carry a few bytes of static shared memory
         if (c->var2) CK(c->var2->prepare(c->smem_optin - 256, fixed));
+        if (c->var_tc) CK(c->var_tc->prepare(c->smem_optin - 256, fixed));
         CK(dalloc(&c->d_wsrc, c->h_wsrc.size()));
         CK(dalloc(&c->d_pmap, c->h_pmap.size()));
         CK(dalloc(&c->d_pspan, c->h_pspan.size()));
@@ -2239,6 +2430,7 @@ void eh_destroy(eh_ctx* c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
+    if (c->hstream.active) end_host_stream(c);   // a consumer kernel still waiting for batches: close its burst first
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     for (int i = 1; i < EH_NPACK; i++)
         if (c->pack_stream[i]) cudaStreamSynchronize(c->pack_stream[i]);
@@ -2274,6 +2466,9 @@ void eh_destroy(eh_ctx* c)
         if (h.freed) cudaEventDestroy(h.freed);
     }
     if (c->h_loss) cudaFreeHost(c->h_loss);
+    if (c->hstream.h_total) cudaFreeHost(c->hstream.h_total);
+    if (c->hstream.d_ready) cudaFree(c->hstream.d_ready);
+    if (c->hstream.d_done) cudaFree(c->hstream.d_done);
     if (c->h_async_loss) cudaFreeHost(c->h_async_loss);
     if (c->h_async_bn) cudaFreeHost(c->h_async_bn);
     if (c->h_bn0) cudaFreeHost(c->h_bn0);
@@ -2585,6 +2780,7 @@ eh_status eh_sync(eh_ctx* c)
     for (auto& pr : c->pending_loss)
         if (pr.second) *pr.second = *pr.first;
     c->pending_loss.clear();
+    c->ring.limit = 1;   // the next burst ramps its group sizes up again
     // the retired host batches' BatchNorm moments, in step order (Lux: running statistics move on every training step)
     for (auto& pb : c->pending_bn) fold_bn_host_batch(c, pb.mom, pb.B, *pb.loss);
     c->pending_bn.clear();
@@ -2809,6 +3005,13 @@ eh_status eh_dp_set_batch_moments(eh_ctx* c, int64_t B, const double* global)
 const char* eh_kernel_variant(const eh_ctx* c)
 {
     return (c && c->var && c->var->name) ? c->var->name : "";
+}
+
+const char* eh_epoch_variant(const eh_ctx* c, int64_t batch)
+{
+    if (!c || !c->var) return "";
+    const Variant* v = c->wide ? c->var : pick_epoch_variant(c, batch);
+    return (v && v->name) ? v->name : "";
 }
 
 eh_status eh_host_alloc(void** out, size_t bytes)

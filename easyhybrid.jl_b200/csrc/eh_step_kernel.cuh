@@ -12,6 +12,7 @@
 #pragma once
 #include "eh_engine_ffma.cuh"
 #include "eh_engine_mma.cuh"
+#include "eh_engine_tc.cuh"
 
 namespace eh {
 

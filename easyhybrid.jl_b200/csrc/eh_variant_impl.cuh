@@ -81,6 +81,7 @@ static Variant make_variant(const char* name)
     v.off_stats = E::OFF_STATS;
     v.stage_floats = E::STAGE_FLOATS;
     v.max_warps = E::MAX_WARPS;
+    v.wpc = 1; v.eng_bytes = 0;
     v.name = name;
     v.prepare = prepare_t<E>;
     v.launch_step = launch_step_t<E>;
@@ -90,6 +91,37 @@ static Variant make_variant(const char* name)
     v.epoch_func = (const void*)k_epoch<E>;
     return v;
 }
+
+// tensor engine: persistent kernel only (single steps, eval and small batches stay on the FFMA2 variant of the same shape)
+template <class E>
+static cudaError_t prepare_epoch_only_t(size_t step_smem, size_t)
+{
+    return cudaFuncSetAttribute(k_epoch<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)step_smem);
+}
+template <class E>
+static Variant make_variant_epoch_only(const char* name)
+{
+    using C = typename E::Cfg;
+    Variant v{};
+    v.pm = C::PM::ID; v.P = C::P; v.NH = C::NH; v.H = C::H; v.NOUT = C::NOUT; v.act = C::ACT; v.scale = C::SCALE ? 1 : 0;
+    v.engine = E::ENGINE;
+    v.chunk = E::CHUNK;
+    v.dims = C::D;
+    v.F = C::F; v.T = C::T; v.NPS = C::NPS; v.R4 = C::R4; v.NW = C::NW;
+    v.NPART = E::NPART;
+    v.off_stats = E::OFF_STATS;
+    v.stage_floats = E::STAGE_FLOATS;
+    v.max_warps = E::MAX_WARPS;
+    v.wpc = E::WPC; v.eng_bytes = E::ENG_FLOATS * 4;
+    v.name = name;
+    v.prepare = prepare_epoch_only_t<E>;
+    v.launch_epoch = launch_epoch_t<E>;
+    v.epoch_max_grid = epoch_max_grid_t<E>;
+    v.epoch_func = (const void*)k_epoch<E>;
+    return v;
+}
+#define EH_MAKE_TC(PMF, P, NH, H, NOUT, ACT, SCALE) \
+    make_variant_epoch_only<EngTc<StepCfg<P, NH, H, NOUT, ACT, SCALE, PMF>>>("tcgen05/" #PMF "/P" #P "/NH" #NH "/H" #H "/O" #NOUT "/" #ACT "/scale=" #SCALE),
 
 // exact-fp32 FFMA2 engine and (where the shape allows) the register-resident tensor-pipe engine
 #define EH_MAKE(PMF, P, NH, H, NOUT, ACT, SCALE) \

@@ -3,7 +3,7 @@
 
 namespace eh {
 
-constexpr int NGROUPS = 11;
+constexpr int NGROUPS = 12;
 static const Variant* group(int k, int* n)
 {
     switch (k) {
@@ -18,6 +18,7 @@ static const Variant* group(int k, int* n)
     case 8: return variants_prog13_sigmoid(n);
     case 9: return variants_prog13_relu(n);
     case 10: return variants_prog13_swish(n);
+    case 11: return variants_tc(n);
     default: *n = 0; return nullptr;
     }
 }

@@ -12,10 +12,13 @@ struct EpochArgs;
 struct Variant {
     int pm, P, NH, H, NOUT, act, scale;
     int engine;      // 0: exact-fp32 FFMA2, one sample per lane; 2: same, two samples per lane (tile partial layout);
-                     // 1: tensor pipe 3xTF32 (padded-flat partial layout)
+                     // 1: tensor pipe 3xTF32 (padded-flat partial layout); 4: tcgen05 tiles of 128 samples per four warps
+                     // (persistent kernel only, tile partial layout)
     int chunk;       // samples per warp pass
     ShapeDims dims;
     int F, T, NPS, R4, NW, NPART, off_stats, stage_floats, max_warps;
+    int wpc;         // warps that share one chunk (1; tensor engine: 4)
+    int eng_bytes;   // engine-private shared memory of the persistent CTA (EpochArgs::eng_off)
     const char* name;
     cudaError_t (*prepare)(size_t step_smem, size_t eval_smem);
     cudaError_t (*launch_step)(const StepArgs& a, int grid, int nwarps, size_t smem, cudaStream_t st, bool pdl);
@@ -33,6 +36,7 @@ const Variant* variant_at(int i);
 const Variant* variants_rbq10(int* n);
 const Variant* variants_expo(int* n);
 const Variant* variants_linear(int* n);
+const Variant* variants_tc(int* n);   // tensor engine (eh_engine_tc.cuh), persistent kernel only
 // generic exact-fp32 variants: the process model is a traced program interpreted per sample (PmProgram);
 // one translation unit per activation
 const Variant* variants_prog_tanh(int* n);

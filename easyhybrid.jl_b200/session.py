@@ -186,6 +186,10 @@ class FusedSession:
         """name of the compiled kernel family serving this model (eh_kernel_variant)"""
         return (self.lib.eh_kernel_variant(self.h) or b"").decode()
 
+    def epoch_variant(self, batch):
+        """name of the kernel family serving the persistent launches at this batch size (eh_epoch_variant)"""
+        return (self.lib.eh_epoch_variant(self.h, int(batch)) or b"").decode()
+
     def sync(self):
         self._ck(self.lib.eh_sync(self.h))
         self._inflight = []

@@ -307,6 +307,9 @@ eh_status eh_set_profiling(eh_ctx* ctx, int32_t on);
  * "ffma2/PmProgram/..." (same kernels, process model interpreted per sample) or "wide/bf16-tcgen05".
  * The reference has no counterpart; callers use it to report / assert the path a model took.          */
 const char* eh_kernel_variant(const eh_ctx* ctx);
+/* ... and the family that serves the PERSISTENT launches (eh_epoch / eh_run_steps) at batch size `batch`: the same as above,
+ * or "tcgen05/..." where the tensor engine (hidden-layer products on tcgen05 with TMEM operands) takes large batches.     */
+const char* eh_epoch_variant(const eh_ctx* ctx, int64_t batch);
 
 /* diagnostics: runs one tcgen05 GEMM of the wide-hidden-layer path on host matrices (bf16 bit patterns) so that a
  * test harness can check the kernels in isolation.  mode 0: out = act(A B^T + bias), A [M x K], B [N x K];

@@ -217,6 +217,9 @@ def test_persistent_kernel_matches_step_kernels(eh, orc):
 
 @pytest.mark.parametrize("B,nb", [(8192, 19), (1000, 19), (2048, 53)])
 def test_step_host_async_stream_equals_epoch(eh, orc, B, nb):
+    # (default: ramped grouped launches.  The opt-in consumer mode, EH_HOST_STREAM=1, takes the same test when the
+    # variable is set in the environment of the test run; every host buffer is page-locked BEFORE the burst opens, because
+    # a device-synchronising call inside an open burst would deadlock against the waiting kernel)
     """streaming host batches (collect_dim_data |> gdev per step, src/training/epoch.jl:1-11) == the resident path
     on the same batches: per-step losses and trained parameters; NaN targets exercise the per-batch counts.
     53 batches: more than three groups of 16, i.e. the staging ring wraps around"""
@@ -232,9 +235,9 @@ def test_step_host_async_stream_equals_epoch(eh, orc, B, nb):
     keep = []
     for k in range(nb):
         idx = perm[k * B:(k + 1) * B]
-        hb = sess.host_batch(sess.pinned(xf[0][idx]), [sess.pinned(xf[1]["ta"][idx])], [sess.pinned(y["reco"][idx])])
-        keep.append(hb)
-        sess.step_host_async(hb, losses, k)
+        keep.append(sess.host_batch(sess.pinned(xf[0][idx]), [sess.pinned(xf[1]["ta"][idx])], [sess.pinned(y["reco"][idx])]))
+    for k in range(nb):
+        sess.step_host_async(keep[k], losses, k)
     sess.sync()
     np.testing.assert_allclose(np.asarray(losses), want, rtol=2e-6)
     np.testing.assert_allclose(sess.get_params(), p_want, rtol=0, atol=2e-6)
@@ -324,3 +327,54 @@ def test_train_api_learns_q10(eh):
     assert out.val_history[-1]["mse"]["sum"] < out.val_history[0]["mse"]["sum"] * 0.05
     assert abs(out.train_diffs["Q10"] - 2.0) < 0.15
     assert out.ps.shape == (model.num_params(),) and out.best_epoch > 0
+
+
+@pytest.mark.parametrize("B,nan_frac,bn,act", [(65536, 0.0, False, "tanh"), (16384 + 77, 0.03, False, "tanh"), (40000, 0.02, True, "sigmoid")],
+                         ids=["c3-batch", "ragged-nan", "bn-sigmoid"])
+def test_tensor_engine_gradient_and_trajectory(eh, orc, monkeypatch, B, nan_frac, bn, act):
+    """Engine 4 (tcgen05: hidden-layer products with TMEM operands, csrc/eh_engine_tc.cuh) serves the persistent kernel from
+    the batch size EH_TC_MIN_BATCH on (opt-in).  (a) Its GRADIENT against the float64 oracle: one Descent(eta) step moves theta by eta * g, so
+    (theta0 - theta1) / eta is the engine's gradient, compared at 1e-5 of the max-norm like every other engine (eta is a
+    power of two and theta0 is rounded so that the subtraction is exact to ~2^-24 of |theta|: the bound below adds that).
+    (b) 12 Adam steps: per-step losses within 1e-5 of the FFMA2 engine (EH_NO_TC=1) and of each other's parameters
+    (single_train_step!, src/training/epoch.jl:20-26)."""
+    monkeypatch.setenv("EH_TC_MIN_BATCH", "16384")
+    model = rbq10_model(eh, bn=bn, activation=act)
+    n = 12 * B
+    xf, y = eh.prepare_data(model, make_synth(n + 500, nan_frac=nan_frac))
+    n = xf[0].shape[0]
+    rng = np.random.default_rng(5)
+    flat = model.initialparameters(rng)
+    flat += (0.05 * rng.standard_normal(flat.size)).astype(np.float32)
+    perm = rng.permutation(n)[: min(n, 12 * B)]
+    # (a) gradient through one plain gradient-descent step
+    eta = 2.0 ** -6
+    sess = eh.FusedSession(model, opt=eh.Descent(eta))
+    assert "tcgen05" in sess.epoch_variant(B), sess.epoch_variant(B)
+    sess.upload(0, xf, y)
+    sess.set_params(flat)
+    L = sess.epoch(perm[:B], B)
+    g = (flat.astype(np.float64) - sess.get_params().astype(np.float64)) / eta
+    sess.close()
+    o = orc.Oracle(model, opt=eh.Descent(eta))
+    L64, g64 = o.loss_grad(flat, xf, y, perm[:B], precision=64, nthreads=orc.max_threads())
+    # phi entries: the optimiser moves the raw (logit) parameters, the oracle's gradient is with respect to them as well
+    assert abs(L[0] - L64) <= 1e-5 * abs(L64), (L, L64)
+    resolution = np.abs(flat).max() * 2.0 ** -23 / eta        # what one float32 update step can resolve
+    err = np.abs(g - g64).max()
+    assert err <= 1e-5 * np.abs(g64).max() + resolution, (err, np.abs(g64).max(), resolution)
+    # (b) trajectory against the FFMA2 engine
+    out = []
+    for no_tc in (False, True):
+        if no_tc:
+            monkeypatch.setenv("EH_NO_TC", "1")
+        sess = eh.FusedSession(model, opt=eh.Adam(0.01))
+        assert ("tcgen05" in sess.epoch_variant(B)) == (not no_tc)
+        sess.upload(0, xf, y)
+        sess.set_params(flat)
+        out.append((sess.epoch(perm, B), sess.get_params()))
+        sess.close()
+    np.testing.assert_allclose(out[0][0], out[1][0], rtol=1e-5)
+    # Adam turns noise-level gradient entries into +-eta steps (SURVEY 10.5): compare phi and the bulk of theta
+    assert abs(float(out[0][1][-1]) - float(out[1][1][-1])) <= 1e-4
+    assert np.median(np.abs(out[0][1] - out[1][1])) <= 1e-4

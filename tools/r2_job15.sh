@@ -1,0 +1,16 @@
+#!/bin/bash
+run() { # name, env...
+  export EH_TC_MIN_BATCH=16384
+  name=$1; shift
+  env "$@" timeout 120 python bench.py --steps 512 --warmup 32 --no-cpu-baseline --no-wide --no-e2e > gpurun_out/r2_j15_$name.json 2>> gpurun_out/r2_j15.err
+  python -c "
+import json
+d=json.load(open('gpurun_out/r2_j15_$name.json')); print('$name', 'us/step', round(d['ms_per_step']*1e3,3), d['final_loss'])"
+  env "$@" EH_EPOCH_DEBUG=gpurun_out/r2_j15_$name.bin EH_PROF_LOG2N=24 timeout 120 python tools/epoch_prof_driver.py 0 32 > /dev/null 2>&1
+  python tools/epoch_phase_dump.py gpurun_out/r2_j15_$name.bin 2>&1 | sed -n '12,14p;19p'
+}
+run s0 EH_TC_STAGGER_NS=0
+run s200 EH_TC_STAGGER_NS=200
+run s400 EH_TC_STAGGER_NS=400
+run s600 EH_TC_STAGGER_NS=600
+run s900 EH_TC_STAGGER_NS=900
