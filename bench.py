@@ -291,7 +291,7 @@ def run_reference(args):
             "config": {"workload": "C3: RbQ10 [2-16-16-1] tanh, mse, Adam(0.01), batch 65536 (CPU: bounded sample of 2^22)"},
             "cpu_baseline": cb, "gpu_launches": 0,
             "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 def main():
@@ -483,7 +483,7 @@ def main():
             line.setdefault("extra", {})["c4_strong_scaling"] = strong
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(eh, model)[0]
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)   # (flushed here: a block-buffered line was lost at interpreter exit under torchrun)
     sess.close()
     if dist is not None:
         dist.destroy_process_group()

@@ -94,18 +94,32 @@ __device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity, unsigned
 }
 // this thread's row of 16 values into the A-operand columns of the group: hi = the bits the tensor core reads (tf32:
 // sign, exponent, 10 mantissa bits), lo = the exact remainder
+__device__ __forceinline__ void st8(uint32_t taddr, const float (&r)[8])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(__float_as_uint(r[0])),
+                 "r"(__float_as_uint(r[1])), "r"(__float_as_uint(r[2])), "r"(__float_as_uint(r[3])), "r"(__float_as_uint(r[4])),
+                 "r"(__float_as_uint(r[5])), "r"(__float_as_uint(r[6])), "r"(__float_as_uint(r[7]))
+                 : "memory");
+}
+// (eight values at a time, hi before lo: at most 16 staging registers are live next to the row itself)
 __device__ __forceinline__ void put_row(uint32_t tm, const float2 (&v)[8])
 {
-    float h[16], l[16];
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-        h[2 * k] = __uint_as_float(__float_as_uint(v[k].x) & 0xffffe000u);
-        h[2 * k + 1] = __uint_as_float(__float_as_uint(v[k].y) & 0xffffe000u);
-        l[2 * k] = v[k].x - h[2 * k];
-        l[2 * k + 1] = v[k].y - h[2 * k + 1];
+    for (int q = 0; q < 2; q++) {
+        float h[8], l[8];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            h[2 * k] = __uint_as_float(__float_as_uint(v[4 * q + k].x) & 0xffffe000u);
+            h[2 * k + 1] = __uint_as_float(__float_as_uint(v[4 * q + k].y) & 0xffffe000u);
+        }
+        st8(tm + COL_AH + 8 * q, h);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            l[2 * k] = v[4 * q + k].x - h[2 * k];
+            l[2 * k + 1] = v[4 * q + k].y - h[2 * k + 1];
+        }
+        st8(tm + COL_AL + 8 * q, l);
     }
-    st16(tm + COL_AH, h);
-    st16(tm + COL_AL, l);
     wait_st();
 }
 // the group's issuing thread: Z = A B^T with B = the weight image at `wh` / `wl` (hi / lo planes), two k-steps of 8

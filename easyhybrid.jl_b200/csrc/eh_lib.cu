@@ -859,6 +859,9 @@ eh_status enqueue_persistent(eh_ctx* c, const float* rec, const int* idx, const 
         a.stagger_ns = wpc > 1 ? stagger : 0;
     }
     a.eng_off = v->eng_bytes ? (int)((smem - (size_t)v->eng_bytes) & ~(size_t)127) : 0;
+    if (getenv("EH_DEBUG_GEOM"))
+        fprintf(stderr, "[eh] persistent launch: %s G=%d warps=%d+1 smem=%zu (fixed %zu, per-warp %zu, tile %d floats) eng_off=%d eng_bytes=%d steps=%lld\n",
+                v->name, G, w, smem, fixed, stage, tile_floats, a.eng_off, v->eng_bytes, (long long)nsteps);
     if (sl) {
         if (!tile_floats) return EH_OK;   // the consumer mode hands batches over through the record tiles
         a.ready = sl->ready; a.ready_base = sl->ready_base; a.done = sl->done; a.host_total = sl->host_total;

@@ -1,6 +1,6 @@
 #!/bin/bash
+export EH_TC_MIN_BATCH=16384
 run() { # name, env...
-  export EH_TC_MIN_BATCH=16384
   name=$1; shift
   env "$@" timeout 120 python bench.py --steps 512 --warmup 32 --no-cpu-baseline --no-wide --no-e2e > gpurun_out/r2_j15_$name.json 2>> gpurun_out/r2_j15.err
   python -c "
@@ -10,7 +10,7 @@ d=json.load(open('gpurun_out/r2_j15_$name.json')); print('$name', 'us/step', rou
   python tools/epoch_phase_dump.py gpurun_out/r2_j15_$name.bin 2>&1 | sed -n '12,14p;19p'
 }
 run s0 EH_TC_STAGGER_NS=0
-run s200 EH_TC_STAGGER_NS=200
-run s400 EH_TC_STAGGER_NS=400
-run s600 EH_TC_STAGGER_NS=600
-run s900 EH_TC_STAGGER_NS=900
+run s150 EH_TC_STAGGER_NS=150
+run s300 EH_TC_STAGGER_NS=300
+run s500 EH_TC_STAGGER_NS=500
+run s800 EH_TC_STAGGER_NS=800
