@@ -398,6 +398,7 @@ __global__ void __launch_bounds__(epoch_threads<E>(), 1) k_epoch(const EpochArgs
     const int NSL = a.npartp / 4;                        // slices of the (padded) partial vector
     const int nown = (NSL - bid + G - 1) / G;            // slices owned by this CTA (bid, bid + G, ...)
     const int ncomp_threads = wcomp * 32;
+    const int Gp = (G + 3) & ~3;
 
     int s_end = a.nsteps;
     for (int s = 0; s < a.nsteps; s++) {
@@ -476,17 +477,25 @@ __global__ void __launch_bounds__(epoch_threads<E>(), 1) k_epoch(const EpochArgs
             const float v0 = 2 * k < E::NPART ? E::reduce_sum_at(stage0, wcomp, 2 * k) : 0.f;           // (padding slots carry zeros)
             const float v1 = 2 * k + 1 < E::NPART ? E::reduce_sum_at(stage0, wcomp, 2 * k + 1) : 0.f;
             if (G == 1) *reinterpret_cast<float2*>(red + 2 * k) = make_float2(v0, v1);
-            else st_cg_v4(part + (size_t)bid * a.npartp + 2 * k, __float_as_uint(v0), tag, __float_as_uint(v1), tag);
+            // slice-major layout [slice = k / 2][CTA][4 slots]: the owner of a slice finds the contributions of all CTAs in ONE
+            // contiguous run of 32 * G bytes (coalesced loads in phase B; the two halves of a sector come from lanes k, k + 1)
+            // (runs padded to whole 128-byte lines: Gp = G rounded up to a multiple of 4)
+            else st_cg_v4(part + ((size_t)(k >> 1) * Gp + bid) * 4 + (k & 1) * 2, __float_as_uint(v0), tag, __float_as_uint(v1), tag);
         }
         EH_STAMP(3)
+        // bias corrections are step constants: their reciprocals are taken here, before the sums arrive.  The optimiser rule
+        // uses MUFU-based division / square root (2 ulp): the IEEE sequences (~150 dependent cycles each, three of them in
+        // a row on every thread) sat on the critical path of every step; the difference is 1e-7 of an update.
+        const float rb1 = __fdividef(1.f, 1.f - b1t), rb2 = __fdividef(1.f, 1.f - b2t);
         if (G > 1) {
             // ---- B: slice owners.  Slice j (4 elements) belongs to CTA j mod G.  Every thread fetches ONE 16-byte pair
-            // {2 elements of one slice of one peer CTA}: item i -> (row, half, peer) = (i / 2G, (i / G) & 1, i % G).
+            // {2 elements of one slice of one peer CTA}; consecutive threads read consecutive pairs of the slice's run:
+            // item i -> (row, peer, half) = (i / 2G, (i % 2G) / 2, i & 1); xbuf keeps the [row][half][peer] order of the sums.
             const int nitems = 2 * G * nown;
             for (int i = threadIdx.x; i < nitems; i += blockDim.x) {
-                const int row = i / (2 * G), rem = i - row * 2 * G, half = rem >= G ? 1 : 0, peer = rem - half * G;
-                const uint4 v = poll_pair_cg(part + (size_t)peer * a.npartp + (bid + row * G) * 4 + half * 2, tag, a.err);
-                xbuf[i] = make_float2(__uint_as_float(v.x), __uint_as_float(v.z));
+                const int row = i / (2 * G), rem = i - row * 2 * G, half = rem & 1, peer = rem >> 1;
+                const uint4 v = poll_pair_cg(part + (size_t)(bid + row * G) * Gp * 4 + rem * 2, tag, a.err);
+                xbuf[(row * 2 + half) * G + peer] = make_float2(__uint_as_float(v.x), __uint_as_float(v.z));
             }
             __syncthreads();
             // one warp per (row, half): lanes stride over the peers, butterfly, lane 0 publishes the two totals
@@ -562,8 +571,6 @@ __global__ void __launch_bounds__(epoch_threads<E>(), 1) k_epoch(const EpochArgs
                 *reinterpret_cast<volatile unsigned*>(a.done) = a.ready_base + (unsigned)s + 1u;
             }
         }
-        // bias corrections are step constants: their reciprocals are ready before the sums arrive
-        const float rb1 = 1.f / (1.f - b1t), rb2 = 1.f / (1.f - b2t);
         // compute warps own theta (entry p on thread p, ...), the service warp owns phi
         const int pbeg = service ? a.ntheta + lane : threadIdx.x;
         const int pend = service ? a.nflat : a.ntheta;
@@ -585,12 +592,12 @@ __global__ void __launch_bounds__(epoch_threads<E>(), 1) k_epoch(const EpochArgs
                     float vt = a.beta2 * s_v[p] + (1.f - a.beta2) * g * g;
                     s_m[p] = mt;
                     s_v[p] = vt;
-                    dx = mt * rb1 / (sqrtf(vt * rb2) + a.eps) * a.eta;
+                    dx = __fdividef(mt * rb1, sqrt_approx(vt * rb2) + a.eps) * a.eta;
                     if (a.opt_kind == OPT_ADAMW) dx += (a.adamw_coupled ? a.eta * a.lambda : a.lambda) * th;
                 } else if (a.opt_kind == OPT_RMSPROP) {
                     float qv = a.beta2 * s_v[p] + (1.f - a.beta2) * g * g;
                     s_v[p] = qv;
-                    dx = g * a.eta / (sqrtf(qv) + a.eps);
+                    dx = __fdividef(g * a.eta, sqrt_approx(qv) + a.eps);
                 } else {
                     dx = a.eta * g;
                 }
