@@ -31,12 +31,6 @@ __device__ __forceinline__ float rcp_approx(float x)
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-__device__ __forceinline__ float sqrt_approx(float x)
-{
-    float y;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
 __device__ __forceinline__ float2 ex2_2(float2 x) { return f2(ex2_approx(x.x), ex2_approx(x.y)); }
 __device__ __forceinline__ float2 rcp_2(float2 x) { return f2(rcp_approx(x.x), rcp_approx(x.y)); }
 
