@@ -58,6 +58,12 @@ struct StepCfg {
     static constexpr int R4 = rup4(P_ + PM::NF + PM::NT);  // floats per record
     static constexpr int NB = D.nblocks();
     static constexpr int NBI = (NB + 31) / 32;             // dW tiles per lane
+    // the warps' reduction rows keep the dW cells element-major with an ODD block stride (cell e * NBP + b): conflict-free for
+    // the lanes of the dW phase (consecutive b) and nearly so for the CTA-level sum, which walks the partial vector in its
+    // own tile-major order (consecutive e) -- with the even stride NB that pass ran into 4-way bank conflicts
+    static constexpr int NBP = NB | 1;
+    static constexpr int SCR_PAD = (NBP - NB) * 16;        // floats the row is longer than the partial vector
+    static constexpr int SCR = D.npart() + SCR_PAD;
     static constexpr int GS = 4 * RS + 4;                  // floats per 4-row staging group (bank skew, see goff)
     static constexpr int AUXOFF = D.ngroups() * GS;        // swish sigma rows start here
     static constexpr int STAGE_FLOATS = AUXOFF + (ACT_ == ACT_SWISH ? NH_ * H_ * RS : 0);  // per warp
@@ -597,7 +603,7 @@ __device__ __forceinline__ void chunk_dw_phase(const float* stage, int lane, con
             const int b = lane + 32 * i;
             float2 acc[16];
 #pragma unroll
-            for (int e = 0; e < 16; e++) acc[e] = f2(first ? 0.f : wacc[e * C::NB + b], 0.f);
+            for (int e = 0; e < 16; e++) acc[e] = f2(first ? 0.f : wacc[e * C::NBP + b], 0.f);
             const float* pd = stage + rowD[i];
             const float* pa = stage + rowA[i];
 #pragma unroll 2
@@ -616,7 +622,7 @@ __device__ __forceinline__ void chunk_dw_phase(const float* stage, int lane, con
                     }
             }
 #pragma unroll
-            for (int e = 0; e < 16; e++) wacc[e * C::NB + b] = acc[e].x + acc[e].y;
+            for (int e = 0; e < 16; e++) wacc[e * C::NBP + b] = acc[e].x + acc[e].y;
         }
     }
 }
@@ -683,7 +689,7 @@ __device__ __forceinline__ void chunk_dw_phase_mma(const float* stage, int lane,
                     for (int q = 0; q < 4; q++) {
                         const int j = 16 * mt + g + ((q >> 1) ? 8 : 0), k = 8 * nt + 2 * t + (q & 1);
                         if (k < ka) {
-                            const int cell = ((j & 3) * 4 + (k & 3)) * C::NB + b0 + (j >> 2) * nk + (k >> 2);
+                            const int cell = ((j & 3) * 4 + (k & 3)) * C::NBP + b0 + (j >> 2) * nk + (k >> 2);
                             wacc[cell] = first ? acc[mt][nt][q] : wacc[cell] + acc[mt][nt][q];
                         }
                     }
@@ -734,7 +740,7 @@ __device__ __forceinline__ void cta_reduce_prepare(int nacc, const ChunkStats& s
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (nacc == 0)
-        for (int q = lane; q < C::NB * 16; q += 32) scratch[warp * stride + q] = 0.f;
+        for (int q = lane; q < C::NBP * 16; q += 32) scratch[warp * stride + q] = 0.f;
     {
         // all per-lane scalars (loss sums, phi sums, output-layer gradient) in one exchange
         constexpr int NLASTV = C::LR ? C::NLAST : 0;
@@ -763,33 +769,30 @@ __device__ __forceinline__ void cta_reduce_prepare(int nacc, const ChunkStats& s
         if (i < C::T) dst = C::D.npart_dw() + i;
         else if (i < C::T + C::NPS) dst = C::D.npart_dw() + MAXT + (i - C::T);
         else if (i < NV) dst = C::D.off_last() + (i - C::T - C::NPS);
-        if (dst >= 0) scratch[warp * stride + dst] = v[0];
+        if (dst >= 0) scratch[warp * stride + C::SCR_PAD + dst] = v[0];
         // cells of the statistics block that no lane writes
         for (int q = C::D.npart_dw() + lane; q < C::NPART; q += 32) {
             bool used = (q < C::D.npart_dw() + C::T) || (q >= C::D.npart_dw() + MAXT && q < C::D.npart_dw() + MAXT + C::NPS) ||
                         (q >= C::D.off_last() && q < C::D.off_last() + NLASTV);
-            if (!used) scratch[warp * stride + q] = 0.f;
+            if (!used) scratch[warp * stride + C::SCR_PAD + q] = 0.f;
         }
     }
 }
-// (2) after the barrier: element q of the rows summed over the first nw warps in fixed order; p = its position in the
-// partial vector (the tile-major order is restored here)
-template <class C>
-__device__ __forceinline__ float cta_reduce_sum(const float* scratch, int stride, int nw, int q, int& p)
-{
-    float s = 0.f;
-    for (int w = 0; w < nw; w++) s += scratch[w * stride + q];
-    p = q < C::NB * 16 ? (q % C::NB) * 16 + q / C::NB : q;
-    return s;
-}
-
-// the same by position p of the partial vector (inverse of the element-major scratch order)
+// (2) after the barrier: position p of the partial vector summed over the first nw warps in fixed order (the cell of
+// the element-major row it lives in: see StepCfg::NBP)
 template <class C>
 __device__ __forceinline__ float cta_reduce_sum_at(const float* scratch, int stride, int nw, int p)
 {
-    const int q = p < C::NB * 16 ? (p & 15) * C::NB + (p >> 4) : p;
+    const int q = p < C::NB * 16 ? (p & 15) * C::NBP + (p >> 4) : p + C::SCR_PAD;
+    // all rows are fetched before the first addition (independent loads; rows past nw count as +0, which leaves the sum's
+    // bits alone): a rolled loop over a run-time warp count pays one shared-memory latency per row
+    float r[16];
+#pragma unroll
+    for (int w = 0; w < 16; w++) r[w] = w < nw ? scratch[w * stride + q] : 0.f;
     float s = 0.f;
-    for (int w = 0; w < nw; w++) s += scratch[w * stride + q];
+#pragma unroll
+    for (int w = 0; w < 16; w++) s += r[w];
+    for (int w = 16; w < nw; w++) s += scratch[w * stride + q];
     return s;
 }
 

@@ -11,7 +11,7 @@ struct EngFfma {
     static constexpr int ENGINE = C::SPL == 2 ? 2 : 0;
     // per-warp shared memory: the staging tile, then the warp's row of the CTA reduction (dW tile sums between
     // chunks + its statistics); separate regions, so nothing has to be re-initialised after a reduction
-    static constexpr int STAGE_FLOATS = C::STAGE_FLOATS + rup4(C::NPART);
+    static constexpr int STAGE_FLOATS = C::STAGE_FLOATS + rup4(C::SCR);
     static constexpr int NPART = C::NPART;
     static constexpr int OFF_STATS = C::D.npart_dw();
     static constexpr int CHUNK = C::CHUNKS;           // samples per warp pass
@@ -92,12 +92,7 @@ struct EngFfma {
     {
         cta_reduce_prepare<C>(s.nacc, s.st, s.la, work + C::STAGE_FLOATS, STAGE_FLOATS);
     }
-    // after the barrier: element q summed over the first nw warps; p = its position in the partial vector
-    __device__ __forceinline__ static float reduce_sum(const float* work, int nw, int q, int& p)
-    {
-        return cta_reduce_sum<C>(work + C::STAGE_FLOATS, STAGE_FLOATS, nw, q, p);
-    }
-    // the same addressed by the position p in the partial vector
+    // after the barrier: position p of the partial vector summed over the first nw warps
     __device__ __forceinline__ static float reduce_sum_at(const float* work, int nw, int p)
     {
         return cta_reduce_sum_at<C>(work + C::STAGE_FLOATS, STAGE_FLOATS, nw, p);

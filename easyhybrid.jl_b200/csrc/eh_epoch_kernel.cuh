@@ -472,15 +472,19 @@ __global__ void __launch_bounds__(epoch_threads<E>(), 1) k_epoch(const EpochArgs
         EH_STAMP(2)
         if (service && have_next) store_bs(pre, s + 1);   // the compute phase that read the cells of step s has ended
 
-        // ---- A: CTA partial, published in vector order as 16-byte {value, tag, value, tag} pairs (coalesced) ----
-        for (int k = threadIdx.x; k < a.npartp / 2; k += blockDim.x) {
-            const float v0 = 2 * k < E::NPART ? E::reduce_sum_at(stage0, wcomp, 2 * k) : 0.f;           // (padding slots carry zeros)
-            const float v1 = 2 * k + 1 < E::NPART ? E::reduce_sum_at(stage0, wcomp, 2 * k + 1) : 0.f;
-            if (G == 1) *reinterpret_cast<float2*>(red + 2 * k) = make_float2(v0, v1);
-            // slice-major layout [slice = k / 2][CTA][4 slots]: the owner of a slice finds the contributions of all CTAs in ONE
-            // contiguous run of 32 * G bytes (coalesced loads in phase B; the two halves of a sector come from lanes k, k + 1)
-            // (runs padded to whole 128-byte lines: Gp = G rounded up to a multiple of 4)
-            else st_cg_v4(part + ((size_t)(k >> 1) * Gp + bid) * 4 + (k & 1) * 2, __float_as_uint(v0), tag, __float_as_uint(v1), tag);
+        // ---- A: CTA partial: ONE element per thread (every row fetched at once), neighbours paired with a shuffle and published
+        // as 16-byte {value, tag, value, tag} pairs.  Slice-major layout [slice][CTA][4 slots]: the owner of a slice finds the
+        // contributions of all CTAs in ONE contiguous run of 32 * Gp bytes, Gp = G rounded up to a multiple of 4 (whole
+        // 128-byte lines; coalesced loads in phase B) ----
+        for (int p0 = 0; p0 < a.npartp; p0 += blockDim.x) {
+            const int p = p0 + threadIdx.x;
+            const float v0 = p < E::NPART ? E::reduce_sum_at(stage0, wcomp, p) : 0.f;   // (padding slots carry zeros)
+            const float v1 = __shfl_down_sync(0xffffffffu, v0, 1);
+            if (p < a.npartp && !(p & 1)) {
+                const int k = p >> 1;
+                if (G == 1) *reinterpret_cast<float2*>(red + p) = make_float2(v0, v1);
+                else st_cg_v4(part + ((size_t)(k >> 1) * Gp + bid) * 4 + (k & 1) * 2, __float_as_uint(v0), tag, __float_as_uint(v1), tag);
+            }
         }
         EH_STAMP(3)
         // bias corrections are step constants: their reciprocals are taken here, before the sums arrive (IEEE division and

@@ -86,11 +86,7 @@ __global__ void __launch_bounds__(E::MAX_WARPS * 32, 1) k_step(const StepArgs a)
     E::reduce_prepare(st, work);
     __syncthreads();
     float* out = a.partial + (size_t)blockIdx.x * a.npart;
-    for (int q = threadIdx.x; q < E::NPART; q += blockDim.x) {
-        int p;
-        const float sum = E::reduce_sum(work, nwarps, q, p);
-        __stcg(out + p, sum);
-    }
+    for (int p = threadIdx.x; p < E::NPART; p += blockDim.x) __stcg(out + p, E::reduce_sum_at(work, nwarps, p));
 }
 
 }  // namespace eh
