@@ -111,7 +111,8 @@ __device__ __forceinline__ uint4 ld_cg_v4(const uint2* p)
     asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
 }
-// poll a pair of slots (weak loads) until both carry the tag of this step
+// poll a pair of slots (weak loads) until both carry the tag of this step (a __nanosleep back-off of 20 / 100 ns between
+// attempts was measured: 10.75 -> 10.77 / 10.81 us per step, i.e. the retries are not what loads L2)
 __device__ __forceinline__ uint4 poll_pair_cg(const uint2* p, unsigned tag, unsigned* err)
 {
     uint4 v = ld_cg_v4(p);
