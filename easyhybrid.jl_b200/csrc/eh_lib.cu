@@ -83,6 +83,7 @@ struct HostRing {
     int64_t cap = 0;           // samples per slot
     int g = 0, k = 0;          // open group, batches packed into it so far
     unsigned rr = 0;           // round robin over the pack streams
+    int launches = 0;          // groups launched in the running burst
     int limit = 1;             // size at which the open group is launched: 1, 2, 4, 8, 16, 16, ... within a burst (the first
                                // steps start while later batches are still crossing PCIe); back to 1 at eh_sync
     int64_t B = 0;             // batch size of the open group
@@ -2232,6 +2233,27 @@ eh_status stream_enqueue(eh_ctx* c, int64_t B, const PackHostArgs& z0, float* pi
 }
 
 // pack one page-locked batch into the open group; *taken = false when the batch has to go the per-step way
+// size of the next group of a burst.  Default ramp 1, 2, 4, 8, 16, 16, ...; EH_RING_RAMP="a,b,c,..." overrides it (the last
+// entry repeats), for experiments
+int next_group_size(HostRing& r)
+{
+    static std::vector<int> ramp = [] {
+        std::vector<int> v;
+        if (const char* e = getenv("EH_RING_RAMP")) {
+            for (const char* p = e; *p;) {
+                int x = atoi(p);
+                if (x >= 1) v.push_back(std::min(x, EH_RING_GROUP));
+                while (*p && *p != ',') p++;
+                if (*p == ',') p++;
+            }
+        }
+        return v;
+    }();
+    r.launches++;
+    if (ramp.empty()) return std::min(EH_RING_GROUP, 2 * r.limit);
+    return ramp[std::min<size_t>((size_t)r.launches, ramp.size() - 1)];
+}
+
 eh_status ring_enqueue(eh_ctx* c, int64_t B, const float* X, const float* const* forc, const float* const* targ, float* pin,
                        bool* taken)
 {
@@ -2294,7 +2316,7 @@ eh_status ring_enqueue(eh_ctx* c, int64_t B, const float* X, const float* const*
         // group sizes within a burst: 1, 2, 4, 8, 16, 16, ... (the first steps start while later batches still cross PCIe;
         // measured at 20 x 65 536-sample batches: 1.84e9 -> 2.27e9 samples/s; constant small groups lose more to the
         // ~50 us every launch costs than they win)
-        r.limit = std::min(EH_RING_GROUP, 2 * r.limit);
+        r.limit = next_group_size(r);
         return flush_host_group(c);
     }
     return EH_OK;
@@ -2784,6 +2806,8 @@ eh_status eh_sync(eh_ctx* c)
         if (pr.second) *pr.second = *pr.first;
     c->pending_loss.clear();
     c->ring.limit = 1;   // the next burst ramps its group sizes up again
+    c->ring.launches = 0;
+    if (const char* e = getenv("EH_RING_RAMP")) c->ring.limit = std::max(1, std::min(atoi(e), EH_RING_GROUP));
     // the retired host batches' BatchNorm moments, in step order (Lux: running statistics move on every training step)
     for (auto& pb : c->pending_bn) fold_bn_host_batch(c, pb.mom, pb.B, *pb.loss);
     c->pending_bn.clear();
