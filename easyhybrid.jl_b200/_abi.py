@@ -17,7 +17,7 @@ STATUS_NAMES = {0: "EH_OK", 1: "EH_EINVAL", 2: "EH_ENOMEM", 3: "EH_ECUDA", 4: "E
 
 ACT = {"identity": 0, "tanh": 1, "sigmoid": 2, "relu": 3, "swish": 4}
 ROLE_NEURAL, ROLE_GLOBAL, ROLE_FIXED = 0, 1, 2
-LOSS = {"mse": 0, "rmse": 1, "mae": 2, "nseLoss": 3}
+LOSS = {"mse": 0, "rmse": 1, "mae": 2, "nseLoss": 3, "pearsonLoss": 4, "kgeLoss": 5, "pbkgeLoss": 6}
 AGG = {"sum": 0, "mean": 1}
 OPT = {"Adam": 0, "AdamW": 1, "RMSProp": 2, "Descent": 3}
 PM = {"RBQ10": 0, "EXPO": 1, "LINEAR": 2, "LINEAR2": 3, "EXPO2": 4, "PROGRAM": 100}

@@ -21,7 +21,8 @@ namespace eh {
 // per-batch scalar row (floats): seed scale c_t, n_valid_t, SS_tot_t, then (mu, rstd) per chain input
 constexpr int MAXP = 12;  // chain inputs
 constexpr int EH_MAX_WORLD = 8;  // GPUs of one NVSwitch box
-constexpr int BS_C = 0, BS_N = MAXT, BS_SS = 2 * MAXT, BS_BN = 3 * MAXT, BS_STRIDE = 3 * MAXT + 2 * MAXP;
+// ... then, for LOSS_AFFINE targets: seed coefficients sa, sb, sc and the loss value, written by the pre-pass (k_stat_seeds)
+constexpr int BS_C = 0, BS_N = MAXT, BS_SS = 2 * MAXT, BS_BN = 3 * MAXT, BS_AFF = 3 * MAXT + 2 * MAXP, BS_STRIDE = BS_AFF + 4 * MAXT;
 
 enum : int { OPT_ADAM = 0, OPT_ADAMW = 1, OPT_RMSPROP = 2, OPT_DESCENT = 3 };
 enum : int { UPD_FULL = 0, UPD_REDUCE_ONLY = 1, UPD_FROM_VECTOR = 2 };
@@ -75,7 +76,8 @@ struct StepCfg {
 // shared memory carve-up (floats): [weights NW pad4][scalars 128][per-warp stage ...]
 //   scalars: [0..8) uniform slot values, [16..48) per-slot derived scalars, [48..52) c_t, [56..80) BN (mu, rstd),
 //   [96..104) persistent kernel: span * sigma'(phi_g) of the global parameters, kept from their last update
-constexpr int SS_SLOT = 0, SS_PMS = 16, SS_C = 48, SS_NV = 52, SS_BN = 56, SS_NV2 = 80, SS_SGD = 96, SS_FLOATS = 128;
+//   [104..116) seed coefficients sa, sb, sc of LOSS_AFFINE targets
+constexpr int SS_SLOT = 0, SS_PMS = 16, SS_C = 48, SS_NV = 52, SS_BN = 56, SS_NV2 = 80, SS_SGD = 96, SS_AFF = 104, SS_FLOATS = 128;
 
 // float offset of the staging row of feature k inside 4-row group g0 (+k/4).  Groups are 4 rows of RS floats
 // plus 4 floats of skew: the group stride is 20 mod 32 banks, so the 8 groups a quarter-warp of dW tiles
@@ -234,6 +236,7 @@ __device__ __forceinline__ void load_weights_and_scalars(const float* pblock, in
     if (threadIdx.x < MAXT) sS[SS_C + threadIdx.x] = bscal ? bscal[BS_C + threadIdx.x] : 0.f;
     if (threadIdx.x < 2 * C::P)
         sS[SS_BN + threadIdx.x] = use_bn ? bscal[BS_BN + threadIdx.x] : ((threadIdx.x & 1) ? 1.f : 0.f);
+    if (threadIdx.x < 3 * MAXT) sS[SS_AFF + threadIdx.x] = bscal ? bscal[BS_AFF + threadIdx.x] : 0.f;
 }
 
 // constant rows of a warp's staging tile: the "1" feature of every augmented input, zero padding
@@ -471,6 +474,10 @@ __device__ __forceinline__ void chunk_sample_phase(const float (*rec)[C::R4], co
             if (loss_kind[t] == LOSS_MAE) {
                 st.loss[t] += fabsf(r);
                 gy[t] = r > 0.f ? c : (r < 0.f ? -c : 0.f);
+            } else if (loss_kind[t] == LOSS_AFFINE) {
+                // seeds of the prediction-statistics losses (pre-pass): sa + sb yhat + sc y, zero where the target is missing
+                st.loss[t] = fmaf(r, r, st.loss[t]);
+                gy[t] = m ? fmaf(sS[SS_AFF + MAXT + t], yh[t], fmaf(sS[SS_AFF + 2 * MAXT + t], y[t], sS[SS_AFF + t])) : 0.f;
             } else {
                 st.loss[t] = fmaf(r, r, st.loss[t]);
                 gy[t] = 2.f * c * r;

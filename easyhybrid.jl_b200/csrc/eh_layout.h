@@ -18,7 +18,12 @@ namespace eh {
 
 enum : int { ACT_IDENTITY = 0, ACT_TANH = 1, ACT_SIGMOID = 2, ACT_RELU = 3, ACT_SWISH = 4 };
 enum : int { ROLE_NEURAL = 0, ROLE_GLOBAL = 1, ROLE_FIXED = 2 };
-enum : int { LOSS_MSE = 0, LOSS_RMSE = 1, LOSS_MAE = 2, LOSS_NSELOSS = 3 };
+enum : int { LOSS_MSE = 0, LOSS_RMSE = 1, LOSS_MAE = 2, LOSS_NSELOSS = 3,
+              // ABI kinds whose seeds depend on statistics of the batch's predictions (a forward pre-pass computes them)
+              LOSS_PEARSONLOSS = 4, LOSS_KGELOSS = 5, LOSS_PBKGELOSS = 6,
+              // what the step kernels see for those targets (and for rmse over several targets): seeds that are affine in
+              // (1, yhat, y) with three per-batch coefficients, dL/dyhat_i = sa + sb yhat_i + sc y_i
+              LOSS_AFFINE = 7 };
 enum : int { PM_RBQ10 = 0, PM_EXPO = 1, PM_LINEAR = 2, PM_LINEAR2 = 3, PM_EXPO2 = 4, PM_PROGRAM = 100 };
 
 constexpr int MAXPS = 8;   // process-parameter slots

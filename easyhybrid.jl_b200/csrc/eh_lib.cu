@@ -118,7 +118,11 @@ struct eh_ctx {
     std::vector<float> h_pspan;
     PSlot slots[MAXPS];
     float pmc[4] = {0, 0, 0, 0};
-    int loss_kind[MAXT] = {0, 0, 0, 0};
+    int loss_kind[MAXT] = {0, 0, 0, 0};   // as the kernels see it (LOSS_AFFINE for the prediction-statistics losses)
+    int loss_kind_abi[MAXT] = {0, 0, 0, 0};
+    bool stat_loss = false;   // some target's seeds need statistics of the predictions: forward pre-pass per step, no persistent kernel
+    double* d_statpart = nullptr;
+    int statpart_cap = 0;
     int agg_mean = 0;
     int opt_kind = 0, adamw_coupled = 1;
     float eta = 0.01f, beta1 = 0.9f, beta2 = 0.999f, eps = 1e-8f, lambda = 0.f;
@@ -691,6 +695,42 @@ eh_status prepare_batch_rows(eh_ctx* c, int64_t n, int64_t B) { return prepare_b
 
 // enqueue the K1/K2 launches of batches [b0, b1) of the resident index stream; the loss of
 // batch b goes to loss_base[b - b0]
+// Pre-pass of the prediction-statistics losses (rmse over several targets, pearsonLoss, kgeLoss, pbkgeLoss): forward over the
+// batch with the CURRENT parameters and the batch's own scalar row (train-mode BatchNorm), sufficient statistics per
+// target (k_eval), then the seed coefficients and the loss value into the row (k_stat_seeds).
+eh_status enqueue_stat_prepass(eh_ctx* c, const float* rec, const int* idx, int64_t B, float* bscal_row)
+{
+    const Variant* v = c->var;
+    const Split& sp = c->split[EH_SPLIT_TRAIN];
+    const int nwarps = 8;
+    const int64_t nchunks = (B + CHUNK - 1) / CHUNK;
+    int grid = (int)std::min<int64_t>((nchunks + nwarps - 1) / nwarps, (int64_t)c->nsm * 2);
+    if (grid < 1) grid = 1;
+    if (grid > c->statpart_cap) {
+        if (c->d_statpart) cudaFree(c->d_statpart);
+        c->d_statpart = nullptr; c->statpart_cap = 0;
+        CK(dalloc(&c->d_statpart, (size_t)c->nsm * 2 * MAXT * EVAL_NSTAT));
+        c->statpart_cap = c->nsm * 2;
+    }
+    EvalArgs a;
+    memset(&a, 0, sizeof a);
+    a.rec = reinterpret_cast<const float4*>(rec);
+    a.idx = idx; a.rec_base = 0; a.N = B; a.pblock = c->d_theta; a.nflat = c->nflat; a.wsrc = c->d_wsrc;
+    a.use_bn = c->use_bn; a.bscal = bscal_row; a.prog = c->d_prog; a.scale_rt = c->scale_rt;
+    for (int s = 0; s < MAXPS; s++) a.slot[s] = c->slots[s];
+    for (int i = 0; i < 4; i++) a.pmc[i] = c->pmc[i];
+    for (int t = 0; t < MAXT; t++) a.shift_y[t] = sp.shift_y[t];
+    a.partial = c->d_statpart;
+    CK(v->launch_eval(a, grid, nwarps, (size_t)(rup4(v->NW) + SS_FLOATS) * 4, c->stream));
+    StatSeedArgs z;
+    memset(&z, 0, sizeof z);
+    z.partial = c->d_statpart; z.nparts = grid; z.Tk = v->T; z.T = c->n_targ; z.agg_mean = c->agg_mean; z.bscal = bscal_row;
+    for (int t = 0; t < MAXT; t++) { z.kind[t] = c->loss_kind[t] == LOSS_AFFINE ? c->loss_kind_abi[t] : -1; z.shift_y[t] = sp.shift_y[t]; }
+    k_stat_seeds<<<1, 32, 0, c->stream>>>(z);
+    CK(cudaGetLastError());
+    return EH_OK;
+}
+
 eh_status enqueue_steps(eh_ctx* c, int64_t n, int64_t B, int64_t b0, int64_t b1, float* loss_base, int apply,
                         bool want_grad, bool pdl, bool profile, int64_t prof_off)
 {
@@ -708,6 +748,10 @@ eh_status enqueue_steps(eh_ctx* c, int64_t n, int64_t B, int64_t b0, int64_t b1,
         a.idx = c->d_idx + b * B;
         a.B = (int)Bk;
         a.bscal = c->d_bscal + (size_t)b * BS_STRIDE;
+        if (c->stat_loss) {
+            eh_status ps = enqueue_stat_prepass(c, sp.rec, a.idx, Bk, c->d_bscal + (size_t)b * BS_STRIDE);
+            if (ps != EH_OK) return ps;
+        }
         if (profile) CK(cudaEventRecord(c->prof_ev[2 * (prof_off + b - b0)], c->stream));
         CK(pick_variant(c, Bk)->launch_step(a, g.grid, g.nwarps, g.smem, c->stream, pdl));
         if (profile) CK(cudaEventRecord(c->prof_ev[2 * (prof_off + b - b0) + 1], c->stream));
@@ -1077,8 +1121,9 @@ eh_status run_steps(eh_ctx* c, int64_t n, int64_t B, int64_t first, int64_t nste
     if (s != EH_OK) return s;
     if (c->wide) return wide_run_steps(c, n, B, first, nsteps, losses, apply, grad_out_host);
     const bool profile = c->profiling != 0;
-    const bool pdl = !(c->flags & EH_FLAG_NO_PDL) && !profile;
-    const bool use_graph = !(c->flags & EH_FLAG_NO_GRAPH) && !profile && apply && !grad_out_host && nsteps >= nb && nb >= 4;
+    // (steps with a statistics pre-pass are launched one by one: no PDL chaining, no pass graph)
+    const bool pdl = !(c->flags & EH_FLAG_NO_PDL) && !profile && !c->stat_loss;
+    const bool use_graph = !(c->flags & EH_FLAG_NO_GRAPH) && !profile && apply && !grad_out_host && nsteps >= nb && nb >= 4 && !c->stat_loss;
     if (profile) {
         while ((int64_t)c->prof_ev.size() < 2 * nsteps) {
             cudaEvent_t e;
@@ -1410,7 +1455,8 @@ eh_status build_plan_wide(eh_ctx* c, const eh_model_desc* d, bool is_prog)
     int n_rmse = 0;
     for (int t = 0; t < d->n_targ; t++) {
         const int lk = d->loss_per_target[t];
-        if (lk < 0 || lk > 3) return fail(c, EH_EINVAL, "loss_per_target[%d]=%d unknown", t, lk);
+        if (lk < 0 || lk > EH_LOSS_PBKGELOSS) return fail(c, EH_EINVAL, "loss_per_target[%d]=%d unknown", t, lk);
+        if (lk > EH_LOSS_NSELOSS) return fail(c, EH_EUNSUPPORTED, "pearsonLoss / kgeLoss / pbkgeLoss are not available on the tensor-core path (chains wider than 32)");
         c->loss_kind[t] = lk;
         if (lk == EH_LOSS_RMSE) n_rmse++;
     }
@@ -1895,15 +1941,21 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
     for (int t = 0; t < d->n_targ; t++) { c->src_kind[c->ncols] = 1; c->src_idx[c->ncols] = d->n_forc + t; c->ncols++; }
     for (int t = d->n_targ; t < v->T; t++) { c->src_kind[c->ncols] = 3; c->src_idx[c->ncols] = 0; c->ncols++; }
 
-    // loss / optimiser
-    int n_rmse = 0;
+    // loss / optimiser.  rmse over several targets and pearsonLoss / kgeLoss / pbkgeLoss need statistics of the batch's
+    // predictions before the seeds exist: those targets run as LOSS_AFFINE behind a forward pre-pass (enqueue_stat_prepass)
     for (int t = 0; t < d->n_targ; t++) {
         int lk = d->loss_per_target[t];
-        if (lk < 0 || lk > 3) return fail(c, EH_EINVAL, "loss_per_target[%d]=%d unknown", t, lk);
-        c->loss_kind[t] = lk;
-        if (lk == EH_LOSS_RMSE) n_rmse++;
+        if (lk < 0 || lk > EH_LOSS_PBKGELOSS) return fail(c, EH_EINVAL, "loss_per_target[%d]=%d unknown", t, lk);
+        c->loss_kind_abi[t] = lk;
+        const bool stat = lk >= EH_LOSS_PEARSONLOSS || (lk == EH_LOSS_RMSE && d->n_targ > 1);
+        c->loss_kind[t] = stat ? (int)LOSS_AFFINE : lk;
+        c->stat_loss |= stat;
     }
-    if (n_rmse && d->n_targ > 1) return fail(c, EH_EUNSUPPORTED, "rmse training loss with more than one target");
+    if (c->stat_loss) {
+        if (v->engine != 0)
+            return fail(c, EH_EUNSUPPORTED, "rmse over several targets / pearsonLoss / kgeLoss / pbkgeLoss run on the FFMA2 engine (drop EH_FLAG_TENSOR_PIPE)");
+        c->persist_ok = false;   // one launch pair (+ pre-pass) per step
+    }
 
     c->agg_mean = d->agg == EH_AGG_MEAN;
     c->opt_kind = d->opt_kind;
@@ -1967,7 +2019,7 @@ eh_status enqueue_host_step(eh_ctx* c, HostStage& h, int64_t B, const float* X, 
     // staging slots alternate between two copy streams: the ramp-up / drain of one batch's transfer overlaps the
     // next batch's (a single stream serialises them and leaves the PCIe link idle in between)
     cudaStream_t cs = c->pack_stream[(&h - c->hs) % EH_NPACK];
-    bool heavy = c->use_bn;
+    bool heavy = c->use_bn || c->stat_loss;
     for (int t = 0; t < c->n_targ; t++) heavy |= (c->loss_kind[t] == LOSS_NSELOSS);
     // page-locked inputs are read in place by the packer (zero copy); anything else goes through the copy engine
     bool zero_copy = c->host_zero_copy && c->n_forc_raw + c->n_targ <= EH_PACK_MAXPLANES;
@@ -2068,6 +2120,10 @@ eh_status enqueue_host_step_compute(eh_ctx* c, HostStage& h, int64_t B, float* l
         if (!used) return fail(c, EH_EUNSUPPORTED, "persistent kernel unavailable for this shape: %s", c->err.c_str());
         CK(cudaEventRecord(h.freed, c->stream));
         return EH_OK;
+    }
+    if (c->stat_loss) {
+        eh_status ps = enqueue_stat_prepass(c, h.d_rec, nullptr, B, h.d_bscal);
+        if (ps != EH_OK) return ps;
     }
     StepArgs a;
     fill_step_args(c, a);
@@ -2260,7 +2316,7 @@ eh_status ring_enqueue(eh_ctx* c, int64_t B, const float* X, const float* const*
     *taken = false;
     HostRing& r = c->ring;
     const Variant* v = c->var;
-    bool heavy = c->use_bn;
+    bool heavy = c->use_bn || c->stat_loss;
     for (int t = 0; t < c->n_targ; t++) heavy |= (c->loss_kind[t] == LOSS_NSELOSS);
     // (large batches amortise their launches anyway; the ring would only cost memory: 48 slots)
     if (B > EH_RING_MAX_BATCH) return EH_OK;
@@ -2469,7 +2525,7 @@ void eh_destroy(eh_ctx* c)
         if (r != c->rank && c->dp_peer[r]) cudaIpcCloseMemHandle(c->dp_peer[r]);
     if (c->dp_block) cudaFree(c->dp_block);
     void* ptrs[] = {c->d_wsrc, c->d_pmap, c->d_pspan, c->d_theta, c->d_m, c->d_v, c->d_grad, c->d_ost, c->d_partial,
-                    c->d_gvec, c->d_dperr, c->d_cells, c->d_slot_of_flat, c->d_losskind, c->d_pbuf, c->d_stats, c->d_bscal, c->d_bn_batch, c->d_idx, c->d_idx64, c->d_err, c->d_loss, c->d_evalpart,
+                    c->d_gvec, c->d_dperr, c->d_cells, c->d_slot_of_flat, c->d_losskind, c->d_pbuf, c->d_stats, c->d_bscal, c->d_bn_batch, c->d_idx, c->d_idx64, c->d_err, c->d_loss, c->d_evalpart, c->d_statpart,
                     c->d_bn_test, c->d_prog, c->d_stage, c->split[0].rec, c->split[1].rec};
     for (void* p : ptrs)
         if (p) cudaFree(p);

@@ -113,6 +113,7 @@ __global__ void __launch_bounds__(512, 1) k_update(const UpdateArgs a)
                 post = 1.f / (2.f * lt);  // d sqrt(mse) = d mse / (2 rmse); single-target only (host checks)
                 break;
             case LOSS_MAE: lt = acc / n; break;
+            case LOSS_AFFINE: lt = a.bscal[BS_AFF + 3 * MAXT + t]; break;  // value left by the pre-pass (k_stat_seeds)
             default: lt = acc / ss; break;  // nseLoss = SSE / SS_tot
             }
             L += lt;

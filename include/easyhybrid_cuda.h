@@ -77,7 +77,16 @@ typedef enum {
 typedef enum { EH_ROLE_NEURAL = 0, EH_ROLE_GLOBAL = 1, EH_ROLE_FIXED = 2 } eh_role;
 
 /* per-target loss (src/losses/loss_fn.jl:58-81) */
-typedef enum { EH_LOSS_MSE = 0, EH_LOSS_RMSE = 1, EH_LOSS_MAE = 2, EH_LOSS_NSELOSS = 3 } eh_loss;
+/* training losses of src/losses/loss_fn.jl:58-179.  The last three (and rmse over more than one target) depend on
+ * statistics of the batch's PREDICTIONS (mean, variance, covariance with the observations): their steps run a forward
+ * pre-pass over the batch first and take the one-launch-pair-per-step path (no persistent kernel, single GPU, exact-fp32
+ * kernels only).                                                                                                      */
+typedef enum {
+    EH_LOSS_MSE = 0, EH_LOSS_RMSE = 1, EH_LOSS_MAE = 2, EH_LOSS_NSELOSS = 3,
+    EH_LOSS_PEARSONLOSS = 4, /* 1 - cor(yhat, y)                                                loss_fn.jl:75-77   */
+    EH_LOSS_KGELOSS = 5,     /* sqrt((r-1)^2 + (sigma_s/sigma_o - 1)^2 + (mu_s/mu_o - 1)^2)     loss_fn.jl:104-127 */
+    EH_LOSS_PBKGELOSS = 6    /* sqrt((r-1)^2 + (mu_s/mu_o - 1)^2)                               loss_fn.jl:160-174 */
+} eh_loss;
 
 /* agg over targets (src/config/TrainingConfig.jl:77; compute_loss.jl:50-53) */
 typedef enum { EH_AGG_SUM = 0, EH_AGG_MEAN = 1 } eh_agg;

@@ -58,7 +58,7 @@ end
 
 const EH_ABI_VERSION = Int32(1)
 const ACT = Dict(:identity => 0, :tanh => 1, :tanh_fast => 1, :sigmoid => 2, :sigmoid_fast => 2, :σ => 2, :relu => 3, :swish => 4)
-const LOSS = Dict(:mse => 0, :rmse => 1, :mae => 2, :nseLoss => 3)
+const LOSS = Dict(:mse => 0, :rmse => 1, :mae => 2, :nseLoss => 3, :pearsonLoss => 4, :kgeLoss => 5, :pbkgeLoss => 6)
 const PM_RBQ10, PM_EXPO, PM_LINEAR, PM_LINEAR2, PM_EXPO2, PM_PROGRAM = 0, 1, 2, 3, 4, 100
 const OP = Dict(:const => 0, :forcing => 1, :param => 2, :add => 10, :sub => 11, :mul => 12, :div => 13, :pow => 14, :min => 15,
     :max => 16, :neg => 20, :exp => 21, :log => 22, :sqrt => 23, :tanh => 24, :sigmoid => 25, :abs => 26, :sin => 27, :cos => 28)

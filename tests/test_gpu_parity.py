@@ -378,3 +378,53 @@ def test_tensor_engine_gradient_and_trajectory(eh, orc, monkeypatch, B, nan_frac
     # Adam turns noise-level gradient entries into +-eta steps: compare phi and the bulk of theta
     assert abs(float(out[0][1][-1]) - float(out[1][1][-1])) <= 1e-4
     assert np.median(np.abs(out[0][1] - out[1][1])) <= 1e-4
+
+
+STAT_CASES = [
+    ("rbq10-pearson-nan", lambda eh: rbq10_model(eh), lambda: make_synth(3000, nan_frac=0.05), "pearsonLoss", "sum"),
+    ("rbq10-kge", lambda eh: rbq10_model(eh, activation="sigmoid"), lambda: make_synth(3000), "kgeLoss", "sum"),
+    ("expo-pbkge-bn", lambda eh: expo_model(eh, bn=True), lambda: make_expo(800), "pbkgeLoss", "sum"),
+    ("linear2-rmse-two-targets", lambda eh: linear_model(eh, two=True, activation="tanh"), lambda: make_linear(1500, two=True), "rmse", "mean"),
+    ("linear2-kge-mse", lambda eh: linear_model(eh, two=True, activation="tanh"), lambda: make_linear(1500, two=True), "PT-kge-mse", "sum"),
+]
+
+
+@pytest.mark.parametrize("name,mk,mkdata,loss,agg", STAT_CASES, ids=[c[0] for c in STAT_CASES])
+def test_prediction_statistics_losses(eh, orc, name, mk, mkdata, loss, agg):
+    """rmse over several targets, pearsonLoss, kgeLoss, pbkgeLoss (src/losses/loss_fn.jl:58-60, 75-77, 104-127, 160-174): their
+    seeds depend on the mean / variance / covariance of the batch's predictions, so every step runs a forward pre-pass
+    (k_eval over the batch + k_stat_seeds) and then the ordinary step kernels with affine seeds.  Loss and gradient at
+    1e-5 of the float64 checker; a 12-step Adam trajectory; the host-batch form walks the same trajectory."""
+    model = mk(eh)
+    tl = eh.PerTarget("kgeLoss", "mse") if loss == "PT-kge-mse" else loss
+    xf, y = eh.prepare_data(model, mkdata())
+    n = xf[0].shape[0]
+    rng = np.random.default_rng(11)
+    flat = model.initialparameters(rng)
+    flat += (0.05 * rng.standard_normal(flat.size)).astype(np.float32)
+    sess = eh.FusedSession(model, training_loss=tl, agg=agg)
+    sess.upload(0, xf, y)
+    sess.set_params(flat)
+    o = orc.Oracle(model, training_loss=tl, agg=agg)
+    for B in (n, 517, 64):
+        idx = rng.permutation(n)[:B]
+        L, g = sess.loss_grad(idx)
+        L64, g64 = o.loss_grad(flat, xf, y, idx, precision=64)
+        assert abs(L - L64) <= RTOL_LOSS * abs(L64), (name, B, L, L64)
+        assert np.abs(g - g64).max() <= RTOL_GRAD * np.abs(g64).max(), (name, B, np.abs(g - g64).max() / np.abs(g64).max())
+    B = 256
+    perm = rng.permutation(n)[: 12 * B]
+    got = sess.epoch(perm, B)
+    p_epoch = sess.get_params()
+    want, ref = truth_trajectory(o, flat, xf, y, perm, B)
+    np.testing.assert_allclose(got, want, rtol=2e-4)
+    # the same batches handed over as host arrays (collect_dim_data |> gdev per step)
+    sess.set_params(flat)
+    sess.set_opt_state(None, None, 0)
+    host = []
+    for k in range((perm.size + B - 1) // B):   # (the smallest data set has fewer than 12 batches; its last one is ragged)
+        idx = perm[k * B:(k + 1) * B]
+        host.append(sess.step_host((xf[0][idx], {f: xf[1][f][idx] for f in model.forcing}), {t: y[t][idx] for t in model.targets}))
+    np.testing.assert_allclose(host, got, rtol=2e-6)
+    np.testing.assert_allclose(sess.get_params(), p_epoch, rtol=0, atol=2e-6)
+    sess.close()

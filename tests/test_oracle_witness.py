@@ -43,6 +43,12 @@ CASES += [
     ("traced-swish-bn-nse", lambda eh: gg.m_custom(eh, hidden=(12, 12), activation="swish", bn=True), lambda: gg._table(300), "nseLoss", "sum"),
     ("traced-two-neural", gg.m_two_neural, lambda: gg._table(300), "mse", "sum"),
     ("traced-two-targets-bn", gg.m_two_targets, lambda: gg._table(400, nan_frac=0.1, two=True), "PT", "mean"),
+    # losses whose seeds depend on statistics of the predictions (forward pre-pass): loss_fn.jl:75-77, 104-127, 160-174
+    ("rbq10-pearson", lambda eh: rbq10_model(eh), lambda: make_synth(300, nan_frac=0.05), "pearsonLoss", "sum"),
+    ("rbq10-kge", lambda eh: rbq10_model(eh), lambda: make_synth(300), "kgeLoss", "sum"),
+    ("expo-pbkge-bn", lambda eh: expo_model(eh, bn=True), lambda: make_expo(300), "pbkgeLoss", "sum"),
+    ("linear2-rmse-two-targets", lambda eh: linear_model(eh, two=True, activation="tanh"), lambda: make_linear(400, two=True), "rmse", "mean"),
+    ("linear2-kge-mse", lambda eh: linear_model(eh, two=True, activation="tanh"), lambda: make_linear(400, two=True), "PT-kge-mse", "sum"),
     ("rbq10-one-hidden-layer", lambda eh: rbq10_model(eh, hidden=(16,)), lambda: make_synth(300, nan_frac=0.03), "mse", "sum"),
     ("rbq10-three-hidden-layers", lambda eh: rbq10_model(eh, hidden=(16, 12, 8), activation="sigmoid"), lambda: make_synth(300), "mse", "sum"),
     ("rbq10-three-inputs-swish", gg.m_rbq10_three_inputs, lambda: make_synth(300, nan_frac=0.03), "mse", "sum"),
@@ -55,6 +61,8 @@ def test_loss_and_grad_vs_autograd(eh, orc, name, mk, mkdata, loss, agg):
     model = mk(eh)
     if loss == "PT":
         loss = eh.PerTarget("nseLoss", "mse")
+    if loss == "PT-kge-mse":
+        loss = eh.PerTarget("kgeLoss", "mse")
     xf, y = _prep(eh, model, mkdata())
     rng = np.random.default_rng(7)
     flat = model.initialparameters(rng)

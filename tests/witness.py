@@ -68,6 +68,18 @@ def objective(model, flat, xf, y, idx, training_loss="mse", agg="sum", bn_eps=1e
             terms.append((yh - yv).abs().mean())
         elif lt == "nseLoss":
             terms.append(((yh - yv) ** 2).sum() / ((yv - yv.mean()) ** 2).sum())
+        elif lt in ("pearsonLoss", "kgeLoss", "pbkgeLoss"):
+            # loss_fn.jl:75-77, 104-127, 160-174: Statistics.cor / std (corrected) / mean
+            ds, do = yh - yh.mean(), yv - yv.mean()
+            r = (ds * do).sum() / torch.sqrt((ds ** 2).sum() * (do ** 2).sum())
+            alpha = torch.sqrt((ds ** 2).sum() / (do ** 2).sum())
+            beta = yh.mean() / yv.mean()
+            if lt == "pearsonLoss":
+                terms.append(1.0 - r)
+            elif lt == "kgeLoss":
+                terms.append(torch.sqrt((r - 1) ** 2 + (alpha - 1) ** 2 + (beta - 1) ** 2))
+            else:
+                terms.append(torch.sqrt((r - 1) ** 2 + (beta - 1) ** 2))
         else:
             raise ValueError(lt)
     L = sum(terms) if agg == "sum" else sum(terms) / len(terms)
