@@ -94,7 +94,11 @@ __device__ __forceinline__ uint2 ld_volatile_v2(const uint2* p)
     asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
     return v;
 }
-constexpr int EH_TOT_REPL = 8;   // replicas of the published totals (the last rows of EpochArgs::pbuf)
+#ifndef EH_TOT_REPL_N
+#define EH_TOT_REPL_N 8
+#endif
+constexpr int EH_TOT_REPL = EH_TOT_REPL_N;   // replicas of the published totals (the last rows of EpochArgs::pbuf; at most 32)
+constexpr int EH_PBUF_EXTRA_ROWS = 32;       // rows of pbuf behind the CTA partials
 constexpr unsigned EH_SPIN_LIMIT = 1u << 26;  // ~seconds; then give up loudly instead of hanging the GPU
 
 // Slot pairs that live in this GPU's L2 use WEAK cache-global accesses (measured, tools/ubench_exchange.cu: volatile /

@@ -889,7 +889,7 @@ eh_status enqueue_persistent(eh_ctx* c, const float* rec, const int* idx, const 
     a.pblock = c->d_theta; a.nflat = c->nflat; a.ntheta = c->ntheta;
     a.m = c->d_m; a.v = c->d_v; a.ost = c->d_ost;
     a.wsrc = c->d_wsrc; a.pmap = c->d_pmap; a.cells = c->d_cells; a.pspan = c->d_pspan; a.slot_of_flat = c->d_slot_of_flat;
-    a.bscal = bscal; a.pbuf = reinterpret_cast<uint2*>(c->d_pbuf); a.pbuf_rows = c->nsm + 8; a.tag_base = c->epoch_tag; a.stats_out = c->d_stats;
+    a.bscal = bscal; a.pbuf = reinterpret_cast<uint2*>(c->d_pbuf); a.pbuf_rows = c->nsm + EH_PBUF_EXTRA_ROWS; a.tag_base = c->epoch_tag; a.stats_out = c->d_stats;
     a.npartp = npartp; a.work_floats = (int)((size_t)w * stage / 4); a.wcomp = w; a.pg_log2 = c->geo_pg; a.tile_floats = tile_floats;
     a.T = c->n_targ; a.agg_mean = c->agg_mean;
     for (int t = 0; t < MAXT; t++) a.loss_kind[t] = c->loss_kind[t];
@@ -2469,8 +2469,8 @@ eh_status eh_create(eh_ctx** out, const eh_model_desc* desc)
         CK(cudaMemcpy(c->d_cells, c->h_cells.data(), c->h_cells.size() * sizeof(int), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(c->d_slot_of_flat, c->h_slot_of_flat.data(), c->h_slot_of_flat.size() * sizeof(int), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(c->d_losskind, c->loss_kind, MAXT * sizeof(int), cudaMemcpyHostToDevice));
-        CK(dalloc(&c->d_pbuf, (size_t)4 * (c->nsm + 8) * rup4(v->NPART)));  // [2][nsm + 8][npartp] {value, tag}: CTA partials + totals, by step parity
-        CK(cudaMemset(c->d_pbuf, 0, (size_t)4 * (c->nsm + 8) * rup4(v->NPART) * sizeof(float)));
+        CK(dalloc(&c->d_pbuf, (size_t)4 * (c->nsm + EH_PBUF_EXTRA_ROWS) * rup4(v->NPART)));  // [2][rows][npartp] {value, tag}: CTA partials + totals, by step parity
+        CK(cudaMemset(c->d_pbuf, 0, (size_t)4 * (c->nsm + EH_PBUF_EXTRA_ROWS) * rup4(v->NPART) * sizeof(float)));
         CK(dalloc(&c->d_dperr, (size_t)1));
         CK(cudaMemset(c->d_dperr, 0, sizeof(unsigned)));
         CK(dalloc(&c->d_m, (size_t)c->nflat));
