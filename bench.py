@@ -454,6 +454,8 @@ def main():
         except Exception as e:  # the extra leg must never take the headline line down
             wide = {"error": str(e)[:200]}
     dp_parity = strong = None
+    if os.environ.get("EH_BENCH_DEBUG"):
+        print("[bench] rank %d: headline + e2e + wide legs done" % rank, file=sys.stderr, flush=True)
     if world > 1:
         try:
             dp_parity = dp_parity_check(eh, dist, rank, world, local)
@@ -483,7 +485,10 @@ def main():
             line.setdefault("extra", {})["c4_strong_scaling"] = strong
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(eh, model)[0]
-        print(json.dumps(line), flush=True)   # (flushed here: a block-buffered line was lost at interpreter exit under torchrun)
+        out = json.dumps(line)
+        if os.environ.get("EH_BENCH_DEBUG"):
+            print("[bench] rank 0 writes %d bytes to fd %d (isatty %s)" % (len(out), sys.stdout.fileno(), sys.stdout.isatty()), file=sys.stderr, flush=True)
+        print(out, flush=True)   # (flushed here: a block-buffered line was lost at interpreter exit under torchrun)
     sess.close()
     if dist is not None:
         dist.destroy_process_group()
