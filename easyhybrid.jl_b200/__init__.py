@@ -13,7 +13,7 @@ from .data import prepare_data, split_data, splitobs_indices, valid_mask
 from .losses import (LOSS_TYPES, assemble_losses, bestdirection, check_training_loss, isbetter,
                      metrics_from_stats)
 from .model import (Expo_resp_model, Expo_resp_model2, LinearModel, LinearModel2, MultiNNHybridModel, ParameterContainer,
-                    PerTarget, RbQ10, SingleNNHybridModel, build_desc, build_parameters, constructHybridModel,
+                    PerTarget, RbQ10, SingleNNHybridModel, WeightL2, build_desc, build_parameters, constructHybridModel,
                     default, hard_sigmoid, inv_hard_sigmoid, inv_sigmoid, lower, scale_single_param,
                     scale_single_param_minmax, upper)
 from .session import FusedSession

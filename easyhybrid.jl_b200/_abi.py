@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-EH_ABI_VERSION = 1
+EH_ABI_VERSION = 2
 
 # eh_status
 EH_OK, EH_EINVAL, EH_ENOMEM, EH_ECUDA, EH_ENCCL, EH_EUNSUPPORTED = range(6)
@@ -85,6 +85,7 @@ class eh_model_desc(C.Structure):
         ("adamw_decay_coupled_eta", C.c_int32),
         ("device", C.c_int32),
         ("flags", C.c_int32),
+        ("l2_lambda", C.c_float), ("l2_normalize", C.c_int32), ("l2_chain_mask", C.c_uint32),
     ]
 
 
@@ -98,7 +99,8 @@ class DescBundle:
 
     def __init__(self, *, n_pred, n_forc, n_targ, chains, roles, role_index, deflt, lower, upper,
                  scale_nn_outputs, process_model, pm_args=(), pm_consts=(), pm_prog=(), pm_outputs=(),
-                 loss_per_target, agg, opt_kind, eta, beta1, beta2, eps, lam, adamw_coupled=1, device=0, flags=0):
+                 loss_per_target, agg, opt_kind, eta, beta1, beta2, eps, lam, adamw_coupled=1, device=0, flags=0,
+                 l2_lambda=0.0, l2_normalize=0, l2_chain_mask=0):
         self._keep = []
         d = eh_model_desc()
         d.abi_version = EH_ABI_VERSION
@@ -146,6 +148,7 @@ class DescBundle:
         d.adamw_decay_coupled_eta = int(adamw_coupled)
         d.device = device
         d.flags = flags
+        d.l2_lambda, d.l2_normalize, d.l2_chain_mask = float(l2_lambda), int(l2_normalize), int(l2_chain_mask)
         self._keep += [cds, a_role, a_ri, a_d, a_l, a_u, args, prog, outs, lpt]
         self.desc = d
 

@@ -120,6 +120,10 @@ struct eh_ctx {
     float pmc[4] = {0, 0, 0, 0};
     int loss_kind[MAXT] = {0, 0, 0, 0};   // as the kernels see it (LOSS_AFFINE for the prediction-statistics losses)
     int loss_kind_abi[MAXT] = {0, 0, 0, 0};
+    bool l2_on = false;       // native weight_l2 extra loss: one launch pair per step (k_update adds the term)
+    float l2_aggw = 1.f, l2_loss_coef = 0.f;
+    std::vector<float> h_l2coef;
+    float* d_l2coef = nullptr;
     bool stat_loss = false;   // some target's seeds need statistics of the predictions: forward pre-pass per step, no persistent kernel
     double* d_statpart = nullptr;
     int statpart_cap = 0;
@@ -536,6 +540,7 @@ void fill_update_args(const eh_ctx* c, UpdateArgs& u)
     for (int t = 0; t < MAXT; t++) u.loss_kind[t] = c->loss_kind[t];
     u.opt_kind = c->opt_kind;
     u.adamw_coupled = c->adamw_coupled;
+    u.l2coef = c->l2_on ? c->d_l2coef : nullptr; u.l2_aggw = c->l2_aggw; u.l2_loss_coef = c->l2_loss_coef;
     u.eta = c->eta; u.beta1 = c->beta1; u.beta2 = c->beta2; u.eps = c->eps; u.lambda = c->lambda;
     u.slot_of_flat = c->d_slot_of_flat;
     for (int s = 0; s < MAXPS; s++) u.slot[s] = c->slots[s];
@@ -1649,7 +1654,8 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d);
 
 eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
 {
-    if (d->abi_version != EH_ABI_VERSION) return fail(c, EH_EINVAL, "abi_version %d != %d", d->abi_version, EH_ABI_VERSION);
+    // (version 1 descriptors end before the weight_l2 fields: those are only read from version >= 2)
+    if (d->abi_version < 1 || d->abi_version > EH_ABI_VERSION) return fail(c, EH_EINVAL, "abi_version %d not in 1..%d", d->abi_version, EH_ABI_VERSION);
     if (d->n_targ < 1 || d->n_targ > MAXT) return fail(c, EH_EUNSUPPORTED, "n_targ=%d not in 1..%d", d->n_targ, MAXT);
     if (d->n_chains < 1 || d->n_chains > 4) return fail(c, EH_EUNSUPPORTED, "n_chains=%d not in 1..4", d->n_chains);
     const bool is_prog = d->process_model == EH_PM_PROGRAM;
@@ -1789,6 +1795,25 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
     c->nglob = ng;
     c->nflat = off + ng;
     if (!wide && c->nflat > 2048 - NSTAT) return fail(c, EH_EUNSUPPORTED, "parameter vector too long for the single-CTA update");
+    // native extra loss lambda * weight_l2(ps.<chains>; normalize) (ABI version 2; extract_weights.jl:55-91,
+    // compute_loss.jl:31-34): per flat entry the coefficient of its own value in the gradient, 2 lambda [/ n] for the
+    // `weight` entries of the selected chains, 0 elsewhere
+    c->l2_on = d->abi_version >= 2 && d->l2_lambda != 0.f;
+    if (c->l2_on) {
+        if (wide) return fail(c, EH_EUNSUPPORTED, "weight_l2 extra loss is not available on the tensor-core path (chains wider than 32)");
+        long long nw = 0;
+        for (int k = 0; k < NC; k++)
+            if (!d->l2_chain_mask || ((d->l2_chain_mask >> k) & 1u))
+                for (int l = 0; l < L; l++) nw += (long long)cw[k][l] * cw[k][l + 1];
+        const double lam = (double)d->l2_lambda / ((d->l2_normalize && nw > 0) ? (double)nw : 1.0);
+        c->l2_aggw = d->agg == EH_AGG_MEAN ? 0.5f : 1.0f;
+        c->l2_loss_coef = (float)lam;
+        c->h_l2coef.assign((size_t)c->nflat, 0.f);
+        for (int k = 0; k < NC; k++)
+            if (!d->l2_chain_mask || ((d->l2_chain_mask >> k) & 1u))
+                for (int l = 0; l < L; l++)
+                    for (int i = 0; i < cw[k][l] * cw[k][l + 1]; i++) c->h_l2coef[(size_t)w_off[k][l] + i] = (float)(2.0 * lam);
+    }
 
     // smem weight image gather table
     const int H = wide ? v->H : D.H, P = wide ? v->P : D.P, NH = wide ? v->NH : D.NH, NOUT = wide ? v->NOUT : D.NOUT;
@@ -1951,6 +1976,7 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
         c->loss_kind[t] = stat ? (int)LOSS_AFFINE : lk;
         c->stat_loss |= stat;
     }
+    if (c->l2_on) c->persist_ok = false;   // the extra term lives in k_update
     if (c->stat_loss) {
         if (v->engine != 0)
             return fail(c, EH_EUNSUPPORTED, "rmse over several targets / pearsonLoss / kgeLoss / pbkgeLoss run on the FFMA2 engine (drop EH_FLAG_TENSOR_PIPE)");
@@ -2459,6 +2485,10 @@ eh_status eh_create(eh_ctx** out, const eh_model_desc* desc)
         CK(dalloc(&c->d_wsrc, c->h_wsrc.size()));
         CK(dalloc(&c->d_pmap, c->h_pmap.size()));
         CK(dalloc(&c->d_pspan, c->h_pspan.size()));
+        if (c->l2_on) {
+            CK(dalloc(&c->d_l2coef, c->h_l2coef.size()));
+            CK(cudaMemcpy(c->d_l2coef, c->h_l2coef.data(), c->h_l2coef.size() * sizeof(float), cudaMemcpyHostToDevice));
+        }
         CK(cudaMemcpy(c->d_wsrc, c->h_wsrc.data(), c->h_wsrc.size() * sizeof(int), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(c->d_pmap, c->h_pmap.data(), c->h_pmap.size() * sizeof(int), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(c->d_pspan, c->h_pspan.data(), c->h_pspan.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -2525,7 +2555,7 @@ void eh_destroy(eh_ctx* c)
         if (r != c->rank && c->dp_peer[r]) cudaIpcCloseMemHandle(c->dp_peer[r]);
     if (c->dp_block) cudaFree(c->dp_block);
     void* ptrs[] = {c->d_wsrc, c->d_pmap, c->d_pspan, c->d_theta, c->d_m, c->d_v, c->d_grad, c->d_ost, c->d_partial,
-                    c->d_gvec, c->d_dperr, c->d_cells, c->d_slot_of_flat, c->d_losskind, c->d_pbuf, c->d_stats, c->d_bscal, c->d_bn_batch, c->d_idx, c->d_idx64, c->d_err, c->d_loss, c->d_evalpart, c->d_statpart,
+                    c->d_gvec, c->d_dperr, c->d_cells, c->d_slot_of_flat, c->d_losskind, c->d_pbuf, c->d_stats, c->d_bscal, c->d_bn_batch, c->d_idx, c->d_idx64, c->d_err, c->d_loss, c->d_evalpart, c->d_statpart, c->d_l2coef,
                     c->d_bn_test, c->d_prog, c->d_stage, c->split[0].rec, c->split[1].rec};
     for (void* p : ptrs)
         if (p) cudaFree(p);

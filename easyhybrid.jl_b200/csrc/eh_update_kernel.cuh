@@ -30,6 +30,10 @@ struct UpdateArgs {
     int loss_kind[MAXT];
     int opt_kind, adamw_coupled;
     float eta, beta1, beta2, eps, lambda;
+    // native extra loss lambda * weight_l2 (extract_weights.jl:55-91): loss = agg([L, E]), E = l2_loss_coef * sum over the
+    // flagged entries of theta^2; gradient: aggw * (g + l2coef[p] * theta[p]) with l2coef = 2 * l2_loss_coef on the flagged entries
+    const float* l2coef;   // [nflat] or NULL
+    float l2_aggw, l2_loss_coef;
     // parameter-block tail (uniform slot values + derived process-model scalars)
     const int* slot_of_flat;  // [nflat] phi entries: canonical slot, -1 otherwise
     PSlot slot[MAXPS];
@@ -74,8 +78,17 @@ __global__ void __launch_bounds__(512, 1) k_update(const UpdateArgs a)
     __shared__ float red[UPD_MAX_NPART];
     __shared__ float s_loss, s_post;
     __shared__ int s_skip;
+    __shared__ float s_l2w[16];
     pdl_wait();  // K1 of this step must be complete and flushed
     pdl_launch_dependents();  // let the next K1 start its data prefetch
+    if (a.l2coef) {
+        // sum of squares of the flagged weights (before this step's update), fixed order: thread stride, warp tree, 16 warps
+        float s = 0.f;
+        for (int p = threadIdx.x; p < a.nflat; p += blockDim.x)
+            if (a.l2coef[p] != 0.f) s = fmaf(a.theta[p], a.theta[p], s);
+        s = warp_sum(s);
+        if ((threadIdx.x & 31) == 0) s_l2w[threadIdx.x >> 5] = s;
+    }
 
     if (a.mode != UPD_FROM_VECTOR) {
         for (int p = threadIdx.x; p < a.npart; p += blockDim.x) {
@@ -119,6 +132,11 @@ __global__ void __launch_bounds__(512, 1) k_update(const UpdateArgs a)
             L += lt;
         }
         if (a.agg_mean) L /= (float)a.T;
+        if (a.l2coef) {
+            float s = 0.f;
+            for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += s_l2w[w];
+            L = a.l2_aggw * (L + a.l2_loss_coef * s);
+        }
         // all-masked batch: skipped by run_epoch! (epoch.jl:17-19, 35-37)
         int skip = (ntot == 0.f);
         s_skip = skip;
@@ -140,6 +158,7 @@ __global__ void __launch_bounds__(512, 1) k_update(const UpdateArgs a)
             float sg = 1.f / (1.f + expf(-th));
             g *= a.pspan[p] * sg * (1.f - sg);
         }
+        if (a.l2coef) g = a.l2_aggw * fmaf(a.l2coef[p], th, g);
         if (a.grad_out) a.grad_out[p] = g;
         if (!a.apply || skip) continue;
         float dx;

@@ -467,7 +467,46 @@ def predictor_columns(model):
     return cols
 
 
-def build_desc(model, *, training_loss="mse", agg="sum", opt=None, device=0, flags=0):
+class WeightL2:
+    """Declarative form of the reference's documented extra loss (src/utils/extract_weights.jl:55-91, hook
+    src/losses/compute_loss.jl:31-34):
+
+        extra_loss = (ŷ, ps) -> (; l2 = λ * weight_l2(ps.<branch>; normalize),)
+
+    A closure cannot cross the C ABI; ``WeightL2(lam, branches, normalize)`` says the same thing as data.  ``branches``:
+    names of the Dense chains whose `weight` arrays take part (MultiNNHybridModel: the neural parameter names; ``None`` =
+    every chain, i.e. ``weight_l2(ps)``).  ONE extra term: loss = agg([L, λ·Σw² [/ n]])."""
+
+    def __init__(self, lam, branches=None, normalize=False):
+        # (λ travels as Float32, like every scalar of the reference's Float32 path)
+        self.lam, self.branches, self.normalize = float(np.float32(lam)), (None if branches is None else [str(b) for b in branches]), bool(normalize)
+
+    def chain_mask(self, model):
+        if self.branches is None:
+            return 0
+        names = [ch["name"] for ch in model.chains]
+        mask = 0
+        for b in self.branches:
+            if b not in names:
+                raise KeyError(f"WeightL2: no Dense chain named {b!r} (chains: {names})")
+            mask |= 1 << names.index(b)
+        return mask
+
+    def value(self, model, flat):
+        """λ·weight_l2 of a flat parameter vector (host side: evaluation-mode losses, tests)"""
+        import numpy as np
+        s, n, off = 0.0, 0, 0
+        names = [ch["name"] for ch in model.chains]
+        for ch, shapes in zip(model.chains, model.layer_shapes()):
+            for (o, i) in shapes:
+                if self.branches is None or ch["name"] in self.branches:
+                    w = np.asarray(flat[off:off + o * i], dtype=np.float64)
+                    s += float((w * w).sum()); n += o * i
+                off += o * i + o
+        return self.lam * (s / n if (self.normalize and n) else s)
+
+
+def build_desc(model, *, training_loss="mse", agg="sum", opt=None, device=0, flags=0, extra_loss=None):
     """eh_model_desc for ``model`` + the TrainConfig fields that select the path
     (training_loss, agg, opt: src/config/TrainingConfig.jl:43, 64, 77)."""
     from .config import Adam  # local import: config imports nothing from here
@@ -505,6 +544,8 @@ def build_desc(model, *, training_loss="mse", agg="sum", opt=None, device=0, fla
             raise AssertionError("Length of targets and PerTarget losses tuple must match")
     else:
         losses = [training_loss] * len(model.targets)
+    if extra_loss is not None and not isinstance(extra_loss, WeightL2):
+        raise NotImplementedError("extra_loss closures cannot cross the C ABI; WeightL2(lam, branches, normalize) is the native form")
     for l in losses:
         if str(l) not in _abi.LOSS:
             raise ValueError(f"training loss {l!r} has no fused kernel (supported: {sorted(_abi.LOSS)})")
@@ -518,7 +559,10 @@ def build_desc(model, *, training_loss="mse", agg="sum", opt=None, device=0, fla
         scale_nn_outputs=model.scale_nn_outputs, loss_per_target=[_abi.LOSS[str(l)] for l in losses],
         agg=_abi.AGG[agg_name], opt_kind=_abi.OPT[type(opt).__name__], eta=opt.eta, beta1=opt.beta[0],
         beta2=opt.beta[1], eps=opt.epsilon, lam=getattr(opt, "lambda_", 0.0),
-        adamw_coupled=int(getattr(opt, "couple", True)), device=device, flags=flags, **pm)
+        adamw_coupled=int(getattr(opt, "couple", True)), device=device, flags=flags,
+        l2_lambda=(extra_loss.lam if extra_loss is not None else 0.0),
+        l2_normalize=int(extra_loss.normalize) if extra_loss is not None else 0,
+        l2_chain_mask=(extra_loss.chain_mask(model) if extra_loss is not None else 0), **pm)
 
 
 class PerTarget:

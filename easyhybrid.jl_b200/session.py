@@ -27,10 +27,10 @@ def _ptr_array(arrs):
 
 
 class FusedSession:
-    def __init__(self, model, *, training_loss="mse", agg="sum", opt=None, device=0, flags=0):
+    def __init__(self, model, *, training_loss="mse", agg="sum", opt=None, device=0, flags=0, extra_loss=None):
         self.lib = load()
         self.model = model
-        self.bundle = build_desc(model, training_loss=training_loss, agg=agg, opt=opt, device=device, flags=flags)
+        self.bundle = build_desc(model, training_loss=training_loss, agg=agg, opt=opt, device=device, flags=flags, extra_loss=extra_loss)
         h = C.c_void_p()
         st = self.lib.eh_create(C.byref(h), self.bundle.byref())
         if st != _abi.EH_OK:

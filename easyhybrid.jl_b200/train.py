@@ -85,8 +85,10 @@ def train(model, data, save_ps=(), *, train_cfg=None, data_cfg=None, **kwargs):
         warnings.warn(f"Unknown kwargs ignored on the Optimisers.jl path: {', '.join(rest)}")
     if not is_optimisers_rule(train_cfg.opt):
         raise NotImplementedError("only Optimisers.jl rules (Adam, AdamW, RMSProp, Descent) take the fused CUDA path")
-    if train_cfg.extra_loss is not None:
-        raise NotImplementedError("extra_loss closures cannot cross the C ABI (EH_EUNSUPPORTED)")
+    from .model import WeightL2
+    if train_cfg.extra_loss is not None and not isinstance(train_cfg.extra_loss, WeightL2):
+        raise NotImplementedError("extra_loss closures cannot cross the C ABI (EH_EUNSUPPORTED); "
+                                  "WeightL2(lam, branches, normalize) is the native form of lambda * weight_l2(ps.<branch>)")
     cfg = validate_config(train_cfg)
     rng = np.random.default_rng(cfg.random_seed)  # seed! before split, loader and init (train.jl:98)
 
@@ -99,7 +101,7 @@ def train(model, data, save_ps=(), *, train_cfg=None, data_cfg=None, **kwargs):
     _, all_masked = valid_mask(y_tr)
 
     device = cfg.gdev if isinstance(cfg.gdev, int) else 0
-    sess = FusedSession(model, training_loss=cfg.training_loss, agg=cfg.agg, opt=cfg.opt, device=device)
+    sess = FusedSession(model, training_loss=cfg.training_loss, agg=cfg.agg, opt=cfg.opt, device=device, extra_loss=cfg.extra_loss)
     try:
         sess.upload(0, xf_tr, y_tr)
         sess.upload(1, xf_va, y_va)

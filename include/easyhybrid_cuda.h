@@ -53,7 +53,7 @@
 extern "C" {
 #endif
 
-#define EH_ABI_VERSION 1
+#define EH_ABI_VERSION 2   /* 2: the weight_l2 fields at the end of eh_model_desc (a version-1 descriptor is still accepted) */
 
 typedef struct eh_ctx eh_ctx; /* opaque; one per training run */
 
@@ -183,6 +183,16 @@ typedef struct {
     /* device / data parallel */
     int32_t device;                 /* CUDA device ordinal for this ctx */
     int32_t flags;                  /* EH_FLAG_* */
+
+    /* ---- ABI version 2 ----
+     * native extra loss: the reference's documented use of TrainConfig.extra_loss,
+     *     extra_loss = (yhat, ps) -> (; l2 = lambda * weight_l2(ps.<branch>; normalize),)
+     * (src/utils/extract_weights.jl:55-91, hook: src/losses/compute_loss.jl:31-34), as ONE extra term over the `weight`
+     * arrays (not the biases) of the selected chains:  E = lambda * sum(w^2) [/ number of weights],  loss = agg([L, E])
+     * with the TrainConfig's agg (sum: L + E; mean: (L + E) / 2).  Steps then take the one-launch-pair-per-step path.  */
+    float l2_lambda;                /* 0: no extra loss */
+    int32_t l2_normalize;           /* weight_l2(...; normalize = true) */
+    uint32_t l2_chain_mask;         /* bit k: chain k takes part; 0 = every chain */
 } eh_model_desc;
 
 #define EH_FLAG_NO_GRAPH 1u   /* launch every step individually (debug / profiling) */

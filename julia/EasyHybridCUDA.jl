@@ -20,7 +20,8 @@
 #      ONE call (eh_epoch) with the DataLoader's own permutation, so batch composition is the reference's.
 #
 # Not supported (eh_create answers EH_EUNSUPPORTED and the caller keeps AutoZygote()): per-branch optimisers,
-# `extra_loss` closures, Chain-valued `hidden_layers`, LSTM models.
+# arbitrary `extra_loss` closures (the documented one, λ * weight_l2(ps.<branch>), is native: FusedCUDA(weight_l2 = ...)),
+# Chain-valued `hidden_layers`, LSTM models.
 module EasyHybridCUDA
 
 using EasyHybrid
@@ -54,9 +55,10 @@ struct EhModelDesc
     opt_kind::Int32; eta::Float32; beta1::Float32; beta2::Float32; eps::Float32; lambda::Float32
     adamw_decay_coupled_eta::Int32
     device::Int32; flags::Int32
+    l2_lambda::Float32; l2_normalize::Int32; l2_chain_mask::UInt32      # ABI version 2: native weight_l2 extra loss
 end
 
-const EH_ABI_VERSION = Int32(1)
+const EH_ABI_VERSION = Int32(2)
 const ACT = Dict(:identity => 0, :tanh => 1, :tanh_fast => 1, :sigmoid => 2, :sigmoid_fast => 2, :σ => 2, :relu => 3, :swish => 4)
 const LOSS = Dict(:mse => 0, :rmse => 1, :mae => 2, :nseLoss => 3, :pearsonLoss => 4, :kgeLoss => 5, :pbkgeLoss => 6)
 const PM_RBQ10, PM_EXPO, PM_LINEAR, PM_LINEAR2, PM_EXPO2, PM_PROGRAM = 0, 1, 2, 3, 4, 100
@@ -182,7 +184,8 @@ loss_ids(l::PerTarget, nt) = (length(l) == nt || error("PerTarget needs one loss
 Describes `model` (SingleNNHybridModel or MultiNNHybridModel) to the library: chains, parameter roles and bounds
 (ParameterContainer order), the traced process model (a built-in form when one matches), loss and optimiser.
 """
-function Session(model::Union{SingleNNHybridModel, MultiNNHybridModel}, opt, training_loss, agg; device = 0, flags = 0)
+function Session(model::Union{SingleNNHybridModel, MultiNNHybridModel}, opt, training_loss, agg; device = 0, flags = 0,
+                 weight_l2 = nothing)   # (lambda = ..., branches = nothing | [:Rb, ...], normalize = false)
     model.config.hidden_layers isa Lux.Chain && error("FusedCUDA: Chain-valued hidden_layers are not supported")
     tbl = model.parameters                                   # ParameterContainer: values = (name = (default, lower, upper), ...)
     names = collect(keys(tbl.values))
@@ -210,6 +213,15 @@ function Session(model::Union{SingleNNHybridModel, MultiNNHybridModel}, opt, tra
     pmargs = bi === nothing ? EhPmArg[] : EhPmArg[EhPmArg(0, bi[2][1]), EhPmArg(0, bi[2][2]), EhPmArg(1, bi[2][3])]
     losses = loss_ids(training_loss, length(model.targets))
     kind, eta, b1, b2, eps, lambda = optimiser_fields(opt)
+    # native form of  extra_loss = (ŷ, ps) -> (; l2 = λ * weight_l2(ps.<branch>; normalize),)  (src/utils/extract_weights.jl:55-91)
+    l2_lambda, l2_norm, l2_mask = 0.0f0, Int32(0), UInt32(0)
+    if weight_l2 !== nothing
+        l2_lambda = Float32(weight_l2.lambda); l2_norm = Int32(get(weight_l2, :normalize, false))
+        br = get(weight_l2, :branches, nothing)
+        if br !== nothing && model isa MultiNNHybridModel
+            for b in br; l2_mask |= UInt32(1) << (findfirst(==(b), collect(keys(model.NNs))) - 1); end
+        end
+    end
     ctx = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve in_cols hidden role ridx de lo up instr outs pmargs losses begin
         cdesc = EhChainDesc[EhChainDesc(length(in_cols[i]), pointer(in_cols[i]), length(hidden[i]), pointer(hidden[i]), ch[i][4],
@@ -222,7 +234,7 @@ function Session(model::Union{SingleNNHybridModel, MultiNNHybridModel}, opt, tra
                 (bi === nothing ? 0.0f0 : bi[3], 0.0f0, 0.0f0, 0.0f0),
                 bi === nothing ? pointer(instr) : C_NULL, bi === nothing ? length(instr) : 0, bi === nothing ? pointer(outs) : C_NULL,
                 pointer(losses), agg === sum ? 0 : 1,
-                kind, eta, b1, b2, eps, lambda, 1, device, flags))
+                kind, eta, b1, b2, eps, lambda, 1, device, flags, l2_lambda, l2_norm, l2_mask))
             st = ccall((:eh_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Ref{EhModelDesc}), ctx, desc)
             st == 0 || error("eh_create (status $st): " * last_error(C_NULL))
         end
@@ -308,13 +320,14 @@ mutable struct FusedCUDA <: ADTypes.AbstractADType
     device::Int32
     training_loss::Union{Symbol, PerTarget}
     agg::Function
+    weight_l2::Union{Nothing, NamedTuple}   # (lambda = 1f-3, branches = [:Rb], normalize = true): the documented extra_loss, natively
     session::Union{Nothing, Session}
 end
-FusedCUDA(; device = 0, training_loss = :mse, agg = sum) = FusedCUDA(Int32(device), training_loss, agg, nothing)
+FusedCUDA(; device = 0, training_loss = :mse, agg = sum, weight_l2 = nothing) = FusedCUDA(Int32(device), training_loss, agg, weight_l2, nothing)
 
 function session!(b::FusedCUDA, model, opt, ps)
     if b.session === nothing
-        b.session = Session(model, opt, b.training_loss, b.agg; device = b.device)
+        b.session = Session(model, opt, b.training_loss, b.agg; device = b.device, weight_l2 = b.weight_l2)
         set_params!(b.session, ps)
     end
     return b.session

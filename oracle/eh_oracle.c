@@ -77,6 +77,8 @@ typedef struct {
     int agg;
     int opt_kind, adamw_coupled;
     float eta, beta1, beta2, eps, lambda;
+    /* native extra loss lambda * weight_l2(ps.<chains>; normalize) (extract_weights.jl:55-91, compute_loss.jl:31-34) */
+    float l2_lambda; int l2_normalize; unsigned l2_mask;
     int64_t n_flat, phi_off;
     int n_glob;
     int tot_act, maxw, tot_in, any_bn;
@@ -231,6 +233,7 @@ eho_plan* eho_plan_new(const eh_model_desc* d)
     pl->agg = d->agg;
     pl->opt_kind = d->opt_kind; pl->adamw_coupled = d->adamw_decay_coupled_eta;
     pl->eta = d->eta; pl->beta1 = d->beta1; pl->beta2 = d->beta2; pl->eps = d->eps; pl->lambda = d->lambda;
+    if (d->abi_version >= 2) { pl->l2_lambda = d->l2_lambda; pl->l2_normalize = d->l2_normalize; pl->l2_mask = d->l2_chain_mask; }
     pl->bn_rmean = (float*)calloc((size_t)(tot_in > 0 ? tot_in : 1), sizeof(float));
     pl->bn_rvar = (float*)calloc((size_t)(tot_in > 0 ? tot_in : 1), sizeof(float));
     for (int i = 0; i < tot_in; i++) pl->bn_rvar[i] = 1.0f; /* Lux BatchNorm initial running_var = 1 */

@@ -86,11 +86,11 @@ def _ptrs(arrs):
 class Oracle:
     """CPU restatement of the hybrid training step for one model descriptor."""
 
-    def __init__(self, model, *, training_loss="mse", agg="sum", opt=None):
+    def __init__(self, model, *, training_loss="mse", agg="sum", opt=None, extra_loss=None):
         from easyhybrid_b200.model import build_desc
         self.L = lib()
         self.model = model
-        self.bundle = build_desc(model, training_loss=training_loss, agg=agg, opt=opt)
+        self.bundle = build_desc(model, training_loss=training_loss, agg=agg, opt=opt, extra_loss=extra_loss)
         self.plan = self.L.eho_plan_new(self.bundle.byref())
         if not self.plan:
             raise RuntimeError("oracle: unsupported descriptor")

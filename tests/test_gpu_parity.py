@@ -428,3 +428,34 @@ def test_prediction_statistics_losses(eh, orc, name, mk, mkdata, loss, agg):
     np.testing.assert_allclose(host, got, rtol=2e-6)
     np.testing.assert_allclose(sess.get_params(), p_epoch, rtol=0, atol=2e-6)
     sess.close()
+
+
+@pytest.mark.parametrize("agg,branches,normalize", [("sum", None, True), ("mean", None, False), ("sum", ["Q10"], True)],
+                         ids=["sum-all-normalized", "mean-all", "sum-one-branch"])
+def test_weight_l2_extra_loss(eh, orc, agg, branches, normalize):
+    """The reference's documented extra loss, extra_loss = (ŷ, ps) -> (; l2 = λ * weight_l2(ps.<branch>; normalize),)
+    (src/utils/extract_weights.jl:55-91, hook src/losses/compute_loss.jl:31-34), as a native term of the update kernel:
+    loss = agg([L, l2]).  Loss and gradient at 1e-5 of the float64 checker, a 10-step trajectory, and train() takes it."""
+    from conftest import rbq10_two_chain_model
+    model = rbq10_two_chain_model(eh) if branches else rbq10_model(eh)
+    xl = eh.WeightL2(0.3, branches=branches, normalize=normalize)
+    xf, y = eh.prepare_data(model, make_synth(3000, nan_frac=0.03))
+    n = xf[0].shape[0]
+    rng = np.random.default_rng(5)
+    flat = model.initialparameters(rng)
+    flat += (0.1 * rng.standard_normal(flat.size)).astype(np.float32)
+    sess = eh.FusedSession(model, agg=agg, extra_loss=xl)
+    sess.upload(0, xf, y)
+    sess.set_params(flat)
+    o = orc.Oracle(model, agg=agg, extra_loss=xl)
+    for B in (n, 517, 64):
+        idx = rng.permutation(n)[:B]
+        L, g = sess.loss_grad(idx)
+        L64, g64 = o.loss_grad(flat, xf, y, idx, precision=64)
+        assert abs(L - L64) <= RTOL_LOSS * abs(L64), (B, L, L64)
+        assert np.abs(g - g64).max() <= RTOL_GRAD * np.abs(g64).max(), (B, np.abs(g - g64).max() / np.abs(g64).max())
+    perm = rng.permutation(n)[: 10 * 256]
+    got = sess.epoch(perm, 256)
+    want, ref = truth_trajectory(o, flat, xf, y, perm, 256)
+    np.testing.assert_allclose(got, want, rtol=1e-4)
+    sess.close()

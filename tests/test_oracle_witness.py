@@ -56,6 +56,28 @@ CASES += [
 ]
 
 
+@pytest.mark.parametrize("agg,branches,normalize", [("sum", None, True), ("mean", None, False), ("sum", ["Q10"], True)])
+def test_weight_l2_extra_loss_vs_autograd(eh, orc, agg, branches, normalize):
+    """extra_loss = (ŷ, ps) -> (; l2 = λ * weight_l2(ps.<branch>; normalize),) (extract_weights.jl:55-91), loss = agg([L, l2])
+    (compute_loss.jl:31-34), in its native declarative form WeightL2"""
+    from conftest import rbq10_two_chain_model
+    model = rbq10_two_chain_model(eh) if branches else rbq10_model(eh)
+    xl = eh.WeightL2(0.3, branches=branches, normalize=normalize)
+    xf, y = _prep(eh, model, make_synth(300, nan_frac=0.05))
+    rng = np.random.default_rng(3)
+    flat = model.initialparameters(rng)
+    flat += (0.1 * rng.standard_normal(flat.size)).astype(np.float32)
+    idx = rng.permutation(xf[0].shape[0])[:200]
+    o = orc.Oracle(model, training_loss="mse", agg=agg, extra_loss=xl)
+    L, g = o.loss_grad(flat, xf, y, idx, precision=64)
+    Lw, gw = objective(model, flat, xf, y, idx, training_loss="mse", agg=agg, extra_loss=xl)
+    L0, _ = orc.Oracle(model, training_loss="mse", agg=agg).loss_grad(flat, xf, y, idx, precision=64)
+    assert abs(L - Lw) <= 1e-10 * abs(Lw) and np.abs(g - gw).max() <= 1e-9 * np.abs(gw).max()
+    # and the host-side value (evaluation-mode bookkeeping) is the same term
+    w2 = 0.5 if agg == "mean" else 1.0
+    assert abs(L - w2 * (L0 + xl.value(model, flat))) <= 1e-6 * abs(L)
+
+
 @pytest.mark.parametrize("name,mk,mkdata,loss,agg", CASES, ids=[c[0] for c in CASES])
 def test_loss_and_grad_vs_autograd(eh, orc, name, mk, mkdata, loss, agg):
     model = mk(eh)

@@ -10,7 +10,7 @@ ACTS = {"tanh": torch.tanh, "sigmoid": torch.sigmoid, "relu": torch.relu,
         "swish": lambda z: z * torch.sigmoid(z), "identity": lambda z: z}
 
 
-def objective(model, flat, xf, y, idx, training_loss="mse", agg="sum", bn_eps=1e-5):
+def objective(model, flat, xf, y, idx, training_loss="mse", agg="sum", bn_eps=1e-5, extra_loss=None):
     """returns (loss, grad) in float64; flat is the reference-ordered parameter vector"""
     from easyhybrid_b200.model import PerTarget, predictor_columns
     X, forc = xf
@@ -83,6 +83,16 @@ def objective(model, flat, xf, y, idx, training_loss="mse", agg="sum", bn_eps=1e
         else:
             raise ValueError(lt)
     L = sum(terms) if agg == "sum" else sum(terms) / len(terms)
+    if extra_loss is not None:
+        # extra_loss = (ŷ, ps) -> (; l2 = λ * weight_l2(ps.<branches>; normalize),): loss = agg([L, l2]) (compute_loss.jl:31-34)
+        s, n, off = 0.0, 0, 0
+        for ch, shapes in zip(model.chains, model.layer_shapes()):
+            for (o, i) in shapes:
+                if extra_loss.branches is None or ch["name"] in extra_loss.branches:
+                    s = s + (th[off:off + o * i] ** 2).sum(); n += o * i
+                off += o * i + o
+        E = extra_loss.lam * (s / n if extra_loss.normalize else s)
+        L = (L + E) if agg == "sum" else (L + E) / 2
     L.backward()
     return float(L.detach()), th.grad.numpy().copy()
 
