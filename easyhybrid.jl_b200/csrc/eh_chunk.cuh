@@ -110,7 +110,7 @@ __device__ __forceinline__ void stage_get(const float* row, int lane, float (&v)
 // src/models/NNModels.jl:225-230).  hp holds neuron PAIRS; returns a_NH in hp, outputs in zo.
 template <class C, bool STAGE>
 __device__ __forceinline__ void chain_forward(const float* sW, float* stage, int lane, const float* x, float2* hp,
-                                              float* zo)
+                                              float* zo, const unsigned* pass = nullptr)
 {
     constexpr ShapeDims D = C::D;
     constexpr int P = C::P, NH = C::NH, H = C::H, NOUT = C::NOUT, HP = C::H / 2;
@@ -140,7 +140,13 @@ __device__ __forceinline__ void chain_forward(const float* sW, float* stage, int
 #pragma unroll
         for (int j = 0; j < HP; j++) {
             float2 aux = f2s(0.f);
+            const float2 z = hp[j];
             hp[j] = act_fwd2<C::ACT>(hp[j], aux);
+            if (C::PM::DYNAMIC && pass) {
+                const unsigned m = pass[l - 1] >> (2 * j);
+                if (m & 1u) hp[j].x = z.x;
+                if (m & 2u) hp[j].y = z.y;
+            }
             if (STAGE && l + 1 <= D.nlt()) {
                 stage[goff<RS>(D.gA(l + 1), 2 * j) + lane] = hp[j].x;
                 stage[goff<RS>(D.gA(l + 1), 2 * j + 1) + lane] = hp[j].y;
@@ -229,7 +235,7 @@ __device__ __forceinline__ void load_weights_and_scalars(const float* pblock, in
 {
     for (int i = threadIdx.x; i < C::NW; i += blockDim.x) {
         int s = wsrc[i];
-        sW[i] = s >= 0 ? __ldcg(pblock + s) : 0.f;
+        sW[i] = s >= 0 ? __ldcg(pblock + s) : (s == -2 ? 1.f : 0.f);   // -2: the 1 of a pass-through unit
     }
     if (threadIdx.x < MAXPS) sS[SS_SLOT + threadIdx.x] = __ldcg(pblock + nflat + threadIdx.x);
     if (threadIdx.x < MAXPS * PMS_PER_SLOT) sS[SS_PMS + threadIdx.x] = __ldcg(pblock + nflat + MAXPS + threadIdx.x);
@@ -386,7 +392,13 @@ __device__ __forceinline__ void chunk_sample_phase(const float (*rec)[C::R4], co
 #pragma unroll
             for (int s = 0; s < S; s++) {
                 float2 aux = f2s(0.f);
+                const float2 z = hp[s][j];
                 hp[s][j] = act_fwd2<C::ACT>(hp[s][j], aux);
+                if (C::PM::DYNAMIC) {   // pass-through units of a shallower chain keep z
+                    const unsigned m = cx.pass[l - 1] >> (2 * j);
+                    if (m & 1u) hp[s][j].x = z.x;
+                    if (m & 2u) hp[s][j].y = z.y;
+                }
                 lo[s] = hp[s][j].x; hi[s] = hp[s][j].y; axl[s] = aux.x; axh[s] = aux.y;
             }
             if (l + 1 <= D.nlt()) {
@@ -557,7 +569,13 @@ __device__ __forceinline__ void chunk_sample_phase(const float (*rec)[C::R4], co
             for (int s = 0; s < S; s++) {
                 float2 al = (l < NH) ? f2(alo[s], ahi[s]) : hp[s][k];
                 float2 aux = (C::ACT == ACT_SWISH) ? f2(xlo[s], xhi[s]) : f2s(0.f);
-                d[s][k] = mul2(d[s][k], act_bwd2<C::ACT>(al, aux));
+                float2 ga = act_bwd2<C::ACT>(al, aux);
+                if (C::PM::DYNAMIC) {
+                    const unsigned m = cx.pass[l - 1] >> (2 * k);
+                    if (m & 1u) ga.x = 1.f;
+                    if (m & 2u) ga.y = 1.f;
+                }
+                d[s][k] = mul2(d[s][k], ga);
                 dlo[s] = d[s][k].x;
                 dhi[s] = d[s][k].y;
             }

@@ -60,6 +60,7 @@ struct EpochArgs {
     int use_bn;
     const PmProgData* prog;    // traced process model (PmProgram variants), device memory
     int scale_rt;              // PmProgram variants: scale_nn_outputs
+    unsigned pass_mask[3];     // PmProgram variants: pass-through units per hidden layer (PmCtx::pass)
     int pm_id;
     int opt_kind, adamw_coupled;
     float eta, beta1, beta2, eps, lambda;
@@ -306,6 +307,7 @@ __global__ void __launch_bounds__(epoch_threads<E>(), 1) k_epoch(const EpochArgs
     cx.c = a.pmc;
     cx.prog = a.prog;
     cx.scale_rt = a.scale_rt;
+    for (int l = 0; l < 3; l++) cx.pass[l] = a.pass_mask[l];
     cx.uniform_mask = 0;
     cx.phi_flag = phi_flag;
     cx.phi_want = a.tag_base;

@@ -29,6 +29,7 @@ struct EvalArgs {
     double* partial;       // [gridDim.x][T * EVAL_NSTAT]
     const PmProgData* prog;   // traced process model (PmProgram variants), device memory
     int scale_rt;             // PmProgram variants: scale_nn_outputs
+    unsigned pass_mask[3];    // PmProgram variants: pass-through units per hidden layer (PmCtx::pass)
 };
 
 template <class C>
@@ -49,6 +50,7 @@ __global__ void __launch_bounds__(256) k_eval(const EvalArgs a)
     cx.c = a.pmc;
     cx.prog = a.prog;
     cx.scale_rt = a.scale_rt;
+    for (int l = 0; l < 3; l++) cx.pass[l] = a.pass_mask[l];
     cx.uniform_mask = 0;
     cx.phi_flag = nullptr;
     cx.phi_want = 0;
@@ -81,7 +83,7 @@ __global__ void __launch_bounds__(256) k_eval(const EvalArgs a)
 
         float2 hp[HP];
         float zo[NOUT], pv[NPS], sg[NPS], yh[T], sv[PM::NSV];
-        chain_forward<C, false>(sW, nullptr, lane, x, hp, zo);
+        chain_forward<C, false>(sW, nullptr, lane, x, hp, zo, cx.pass);
         resolve_params<C>(a.slot, sS, zo, pv, sg, cx);
         PM::fwd(pv, f, cx, yh, sv);
 

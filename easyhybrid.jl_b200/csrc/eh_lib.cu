@@ -190,6 +190,7 @@ struct eh_ctx {
     HostRing ring;
     bool small_prog = false;     // register-tile path with an interpreted process model (PmProgram variants)
     int scale_rt = 0;            // scale_nn_outputs as the generic variants take it
+    unsigned pass_mask[3] = {0, 0, 0};   // generic variants: pass-through units per hidden layer (chains of unequal depth)
     PmProgData h_prog;           // the program, host copy
     PmProgData* d_prog = nullptr;
     bool host_zero_copy = true;  // EH_HOST_NO_ZEROCOPY=1: always stage host batches through the copy engine
@@ -516,6 +517,7 @@ void fill_step_args(const eh_ctx* c, StepArgs& a)
     a.use_bn = c->use_bn;
     a.prog = c->d_prog;
     a.scale_rt = c->scale_rt;
+    for (int l = 0; l < 3; l++) a.pass_mask[l] = c->pass_mask[l];
 }
 
 void fill_update_args(const eh_ctx* c, UpdateArgs& u)
@@ -722,6 +724,7 @@ eh_status enqueue_stat_prepass(eh_ctx* c, const float* rec, const int* idx, int6
     a.rec = reinterpret_cast<const float4*>(rec);
     a.idx = idx; a.rec_base = 0; a.N = B; a.pblock = c->d_theta; a.nflat = c->nflat; a.wsrc = c->d_wsrc;
     a.use_bn = c->use_bn; a.bscal = bscal_row; a.prog = c->d_prog; a.scale_rt = c->scale_rt;
+    for (int l = 0; l < 3; l++) a.pass_mask[l] = c->pass_mask[l];
     for (int s = 0; s < MAXPS; s++) a.slot[s] = c->slots[s];
     for (int i = 0; i < 4; i++) a.pmc[i] = c->pmc[i];
     for (int t = 0; t < MAXT; t++) a.shift_y[t] = sp.shift_y[t];
@@ -901,6 +904,7 @@ eh_status enqueue_persistent(eh_ctx* c, const float* rec, const int* idx, const 
     for (int s = 0; s < MAXPS; s++) a.slot[s] = c->slots[s];
     for (int i = 0; i < 4; i++) a.pmc[i] = c->pmc[i];
     a.use_bn = c->use_bn; a.pm_id = c->pm_id; a.prog = c->d_prog; a.scale_rt = c->scale_rt;
+    for (int l = 0; l < 3; l++) a.pass_mask[l] = c->pass_mask[l];
     a.opt_kind = c->opt_kind; a.adamw_coupled = c->adamw_coupled;
     a.eta = c->eta; a.beta1 = c->beta1; a.beta2 = c->beta2; a.eps = c->eps; a.lambda = c->lambda;
     a.world = c->world; a.rank = c->rank; a.step_base = c->dp_steps; a.err = c->d_dperr;
@@ -1694,19 +1698,26 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
     // several chains (MultiNNHybridModel, GenericHybridModel.jl:169-189, 458-530) are embedded block-diagonally into ONE
     // chain: chain k owns a range of the inputs, of the units of every hidden layer and of the outputs; weights between
     // units of different chains do not exist (zero cells of the image that no flat entry feeds).  Totals per level:
+    // Chains of different depth (hidden sizes differ per parameter, GenericHybridModel.jl:169-189): the embedded chain
+    // has the depth of the deepest one; a shallower chain carries its last hidden layer forward through pass-through
+    // units (weight 1 from the unit below, no bias, identity activation -- cells fed by no flat entry) up to the common
+    // output layer.  Only the generic variants know pass-through units.
     int Pt = 0, Ot = 0, wsum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    bool uniform = true;
+    bool uniform = true, same_depth = true;
+    int NHmax = 0;
+    for (int k = 0; k < NC; k++) NHmax = std::max(NHmax, d->chains[k].n_hidden);
     for (int k = 0; k < NC; k++) {
         const eh_chain_desc& ck = d->chains[k];
         if (ck.n_in < 1) return fail(c, EH_EINVAL, "chain %d has no inputs", k);
         if (ck.n_hidden < 1) return fail(c, EH_EINVAL, "chain needs at least one hidden layer");
-        if (ck.n_hidden != ch.n_hidden || ck.activation != ch.activation || ck.input_batchnorm != ch.input_batchnorm) uniform = false;
+        if (ck.activation != ch.activation || ck.input_batchnorm != ch.input_batchnorm) uniform = false;
+        if (ck.n_hidden != NHmax) same_depth = false;
         Pt += ck.n_in; Ot += ck.n_out;
-        for (int l = 0; l < ck.n_hidden && l < 8; l++) wsum[l] += ck.hidden[l];
+        for (int l = 0; l < NHmax && l < 8; l++) wsum[l] += ck.hidden[std::min(l, ck.n_hidden - 1)];
     }
     if (NC == 1 && ch.n_in > MAXP) return fail(c, EH_EUNSUPPORTED, "chain n_in=%d not in 1..%d", ch.n_in, MAXP);
     int hmax = 0;
-    for (int l = 0; l < ch.n_hidden && l < 8; l++) hmax = std::max(hmax, wsum[l]);
+    for (int l = 0; l < NHmax && l < 8; l++) hmax = std::max(hmax, wsum[l]);
     if (!is_prog && (d->n_pm_args != 3 || d->pm_args[0].kind != 0 || d->pm_args[1].kind != 0 || d->pm_args[2].kind != 1))
         return fail(c, EH_EINVAL, "built-in process models take (param, param, forcing) arguments");
     // Which path?  The exact-fp32 register-tile kernels exist for one to three hidden layers of width <= 32; every other chain
@@ -1724,7 +1735,7 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
     }
     for (int p = 0; p < d->n_params; p++)
         if (d->role[p] == EH_ROLE_GLOBAL) nflat_est++;
-    const bool small_shape = uniform && ch.n_hidden <= 7 && hmax <= 32 && nflat_est <= 2048 - NSTAT;
+    const bool small_shape = uniform && NHmax <= 3 && hmax <= 32 && nflat_est <= 2048 - NSTAT;
     const Variant* v = nullptr;
     // 1. a specialised variant of a built-in form (the BASELINE configurations); engine 1 (tensor pipe, 3xTF32) on
     //    request where one exists, engine 0 (exact-fp32 FFMA2) otherwise
@@ -1742,9 +1753,12 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
     bool use_prog = false;
     if (!v && small_shape && !getenv("EH_NO_SMALL_PROGRAM") && d->n_params >= 1 && d->n_params <= MAXPS && d->n_forc <= PmProgram::NF &&
         d->n_targ <= PmProgram::NT) {
-        const Variant* vp = find_variant(EH_PM_PROGRAM, Pt, ch.n_hidden, rup4(hmax), Ot, ch.activation, 1, 0);
+        const Variant* vp = find_variant(EH_PM_PROGRAM, Pt, NHmax, rup4(hmax), Ot, ch.activation, 1, 0);
         if (vp && vp->NPART <= UPD_MAX_NPART && builtin_as_program(d, is_prog, prog, prog_out)) { v = vp; use_prog = true; }
     }
+    if (!v && !same_depth)
+        return fail(c, EH_EUNSUPPORTED, "chains of different depth run on the exact-fp32 generic kernels only: <= 3 hidden layers, "
+                                        "summed width <= 32 per layer, <= 8 chain inputs, <= 2 chain outputs");
     if (!v) return build_plan_wide(c, d, is_prog);
     if (!use_prog && v->T != d->n_targ) return fail(c, EH_EINVAL, "process model yields %d targets, descriptor has %d", v->T, d->n_targ);
     c->var = v;
@@ -1772,7 +1786,7 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
     // flat layout (reference ComponentArray order): chain after chain, per layer W (out x in, column-major) then b; then phi.
     // Level 0 = inputs, 1..NH = hidden layers, L = outputs; chain k owns units [u0[k][lev], u0[k][lev] + cw[k][lev]).
     const ShapeDims& D = v->dims;
-    const int L = ch.n_hidden + 1;
+    const int L = NHmax + 1;
     std::vector<std::vector<int>> cw((size_t)NC, std::vector<int>((size_t)L + 1)), u0((size_t)NC, std::vector<int>((size_t)L + 1)),
         w_off((size_t)NC, std::vector<int>((size_t)L)), b_off((size_t)NC, std::vector<int>((size_t)L));
     std::vector<int> width((size_t)L + 1, 0);   // embedded (summed) width per level
@@ -1780,10 +1794,17 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
     for (int k = 0; k < NC; k++) {
         const eh_chain_desc& ck = d->chains[k];
         cw[k][0] = ck.n_in;
-        for (int l = 0; l < ck.n_hidden; l++) cw[k][l + 1] = ck.hidden[l];
+        for (int l = 0; l < NHmax; l++) cw[k][l + 1] = ck.hidden[std::min(l, ck.n_hidden - 1)];
         cw[k][L] = ck.n_out;
         for (int lev = 0; lev <= L; lev++) { u0[k][lev] = width[lev]; width[lev] += cw[k][lev]; }
         for (int l = 0; l < L; l++) {
+            // embedded layers [n_hidden, L-1) of a shallower chain are pass-through: no flat entries (offset -1)
+            const bool pass = l >= ck.n_hidden && l < L - 1;
+            if (pass) {
+                w_off[k][l] = b_off[k][l] = -1;
+                for (int j = 0; j < cw[k][l + 1]; j++) c->pass_mask[l] |= 1u << (u0[k][l + 1] + j);
+                continue;
+            }
             w_off[k][l] = off; off += cw[k][l] * cw[k][l + 1];
             b_off[k][l] = off; off += cw[k][l + 1];
         }
@@ -1804,7 +1825,7 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
         long long nw = 0;
         for (int k = 0; k < NC; k++)
             if (!d->l2_chain_mask || ((d->l2_chain_mask >> k) & 1u))
-                for (int l = 0; l < L; l++) nw += (long long)cw[k][l] * cw[k][l + 1];
+                for (int l = 0; l < L; l++) nw += w_off[k][l] < 0 ? 0 : (long long)cw[k][l] * cw[k][l + 1];
         const double lam = (double)d->l2_lambda / ((d->l2_normalize && nw > 0) ? (double)nw : 1.0);
         c->l2_aggw = d->agg == EH_AGG_MEAN ? 0.5f : 1.0f;
         c->l2_loss_coef = (float)lam;
@@ -1812,7 +1833,7 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
         for (int k = 0; k < NC; k++)
             if (!d->l2_chain_mask || ((d->l2_chain_mask >> k) & 1u))
                 for (int l = 0; l < L; l++)
-                    for (int i = 0; i < cw[k][l] * cw[k][l + 1]; i++) c->h_l2coef[(size_t)w_off[k][l] + i] = (float)(2.0 * lam);
+                    for (int i = 0; w_off[k][l] >= 0 && i < cw[k][l] * cw[k][l + 1]; i++) c->h_l2coef[(size_t)w_off[k][l] + i] = (float)(2.0 * lam);
     }
 
     // smem weight image gather table
@@ -1824,14 +1845,17 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
     auto Wsrc = [&](int l /*1-based*/, int j, int k) -> int {
         for (int q = 0; q < NC; q++) {
             const int jj = j - u0[q][l], kk = k - u0[q][l - 1];
-            if (jj >= 0 && jj < cw[q][l] && kk >= 0 && kk < cw[q][l - 1]) return w_off[q][l - 1] + jj + kk * cw[q][l];
+            if (jj >= 0 && jj < cw[q][l] && kk >= 0 && kk < cw[q][l - 1]) {
+                if (w_off[q][l - 1] < 0) return jj == kk ? -2 : -1;   // pass-through layer: identity
+                return w_off[q][l - 1] + jj + kk * cw[q][l];
+            }
         }
         return -1;
     };
     auto Bsrc = [&](int l, int j) -> int {
         for (int q = 0; q < NC; q++) {
             const int jj = j - u0[q][l];
-            if (jj >= 0 && jj < cw[q][l]) return b_off[q][l - 1] + jj;
+            if (jj >= 0 && jj < cw[q][l]) return b_off[q][l - 1] < 0 ? -1 : b_off[q][l - 1] + jj;
         }
         return -1;
     };
@@ -1908,7 +1932,7 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
         }
         const int nk = D.nk(l), b0 = D.blk0(l);
         for (int q = 0; q < NC; q++)
-            for (int jj = 0; jj < cw[q][l]; jj++) {
+            for (int jj = 0; w_off[q][l - 1] >= 0 && jj < cw[q][l]; jj++) {
                 const int j = u0[q][l] + jj;
                 for (int kk = 0; kk < cw[q][l - 1]; kk++) {
                     const int k = u0[q][l - 1] + kk;
@@ -2925,6 +2949,7 @@ eh_status eh_eval(eh_ctx* c, int32_t split, float* yhat, double* stats, float* n
     a.rec = reinterpret_cast<const float4*>(sp.rec);
     a.rec_base = 0; a.N = N; a.pblock = c->d_theta; a.nflat = c->nflat; a.wsrc = c->d_wsrc;
     a.use_bn = c->use_bn; a.prog = c->d_prog; a.scale_rt = c->scale_rt;
+    for (int l = 0; l < 3; l++) a.pass_mask[l] = c->pass_mask[l];
     if (c->use_bn) {
         // test mode: running statistics (LuxCore.testmode(st), compute_loss.jl:37)
         float row[BS_STRIDE];

@@ -33,6 +33,7 @@ struct StepArgs {
     int use_bn;
     const PmProgData* prog;   // traced process model (PmProgram variants), device memory
     int scale_rt;             // PmProgram variants: scale_nn_outputs
+    unsigned pass_mask[3];    // PmProgram variants: pass-through units per hidden layer (PmCtx::pass)
 };
 
 // per-CTA work region (floats): staging tiles of all warps, reused as the [nwarps][NPART] reduction scratch
@@ -73,6 +74,7 @@ __global__ void __launch_bounds__(E::MAX_WARPS * 32, 1) k_step(const StepArgs a)
     cx.c = a.pmc;
     cx.prog = a.prog;
     cx.scale_rt = a.scale_rt;
+    for (int l = 0; l < 3; l++) cx.pass[l] = a.pass_mask[l];
     cx.uniform_mask = 0;
     cx.phi_flag = nullptr;
     cx.phi_want = 0;

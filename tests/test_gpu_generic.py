@@ -70,6 +70,22 @@ def m_two_chains_six_inputs(eh):
                                    hidden_layers=[12, 8], activation="sigmoid", scale_nn_outputs=True, input_batchnorm=True)
 
 
+def m_two_chains_unequal_depth(eh, activation="tanh", bn=False):
+    # hidden_layers as a NamedTuple per parameter (GenericHybridModel.jl:168-174): three hidden layers for rb, one for Q10
+    return eh.constructHybridModel({"rb": ["sw_pot", "dsw_pot"], "Q10": ["ta"]}, ["ta"], ["reco"], eh.RbQ10,
+                                   dict(rb=(3.0, 0.0, 13.0), Q10=(2.0, 1.0, 4.0)), [],
+                                   hidden_layers={"rb": [16, 12, 8], "Q10": [10]}, activation=activation,
+                                   scale_nn_outputs=True, input_batchnorm=bn)
+
+
+def m_traced_unequal_depth(eh):
+    # chains of depth 1 and 2 (the shallow one first) feeding a traced process model with a global parameter besides; relu
+    return eh.constructHybridModel({"rb": ["sw_pot", "dsw_pot"], "Q10": ["ta", "sw_pot"]}, ["ta", "dsw_pot"], ["reco"], custom_pm,
+                                   dict(rb=(3.0, 0.0, 13.0), Q10=(2.0, 1.0, 4.0), alpha=(0.5, -2.0, 2.0)), ["alpha"],
+                                   hidden_layers={"rb": [9], "Q10": [8, 7]}, activation="relu", scale_nn_outputs=True,
+                                   input_batchnorm=True)   # (normalised inputs: relu into a saturating sigmoid is ill-conditioned in fp32)
+
+
 CASES = [
     ("custom-tanh16", m_custom, lambda: _table(3000), "mse", "sum"),
     ("custom-nan", m_custom, lambda: _table(3000, nan_frac=0.05), "mae", "sum"),
@@ -87,6 +103,10 @@ CASES = [
     # several chains, embedded block-diagonally into one chain of the summed widths (<= 32)
     ("two-chains-rbq10", lambda eh: rbq10_two_chain_model(eh, hidden=(16, 16)), lambda: make_synth(2000, nan_frac=0.03), "mse", "sum"),
     ("two-chains-six-inputs-bn", m_two_chains_six_inputs, lambda: make_synth(2000), "mse", "sum"),
+    # chains of different depth: the shallower chain's last hidden layer rides on pass-through units
+    ("two-chains-depth-3-and-1", m_two_chains_unequal_depth, lambda: make_synth(2000, nan_frac=0.03), "mse", "sum"),
+    ("two-chains-depth-3-and-1-swish-bn", lambda eh: m_two_chains_unequal_depth(eh, "swish", True), lambda: make_synth(2000), "nseLoss", "sum"),
+    ("traced-chains-depth-1-and-2-relu", m_traced_unequal_depth, lambda: _table(2000), "mse", "mean"),
 ]
 
 
@@ -121,7 +141,7 @@ def test_generic_variants_loss_and_gradient(eh, orc, name, mk, mkdata, loss, agg
     sess.close()
 
 
-TRAIN_CASES = [CASES[0], CASES[5], CASES[7], CASES[8], CASES[9], CASES[11], CASES[12], CASES[13]]
+TRAIN_CASES = [CASES[0], CASES[5], CASES[7], CASES[8], CASES[9], CASES[11], CASES[12], CASES[13], CASES[14], CASES[15], CASES[16]]
 
 
 @pytest.mark.parametrize("name,mk,mkdata,loss,agg", TRAIN_CASES, ids=[c[0] for c in TRAIN_CASES])
