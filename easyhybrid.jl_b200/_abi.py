@@ -32,6 +32,7 @@ EH_FLAG_NO_GRAPH = 1
 EH_FLAG_NO_PDL = 2
 EH_FLAG_NO_PERSIST = 4
 EH_FLAG_TENSOR_PIPE = 16
+EH_FLAG_JIT = 32
 EH_SPLIT_TRAIN, EH_SPLIT_VAL = 0, 1
 EH_EVAL_STATS = 9
 EH_COMM_ID_BYTES = 128
@@ -187,6 +188,7 @@ SIGNATURES = {
     "eh_last_timing": (C.c_int, [_p, _fp, _i64p, _fp]),
     "eh_set_profiling": (C.c_int, [_p, C.c_int32]),
     "eh_kernel_variant": (C.c_char_p, [_p]),
+    "eh_jit_check": (C.c_int32, [_p, C.c_char_p, C.c_size_t]),
     "eh_epoch_variant": (C.c_char_p, [_p, C.c_int64]),
     "eh_dp_batch_moments": (C.c_int, [_p, C.c_int64, C.POINTER(C.c_double)]),
     "eh_dp_set_batch_moments": (C.c_int, [_p, C.c_int64, C.POINTER(C.c_double)]),

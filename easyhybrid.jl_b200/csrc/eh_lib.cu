@@ -18,6 +18,7 @@
 
 #include "../../include/easyhybrid_cuda.h"
 #include "eh_variants.h"
+#include "eh_jit.h"
 #include "eh_update_kernel.cuh"
 #include "eh_epoch_kernel.cuh"
 #include "eh_eval_kernel.cuh"
@@ -103,6 +104,12 @@ struct eh_ctx {
     const Variant* var = nullptr;   // engine chosen at eh_create (FFMA2 one sample per lane, or tensor pipe)
     const Variant* var2 = nullptr;  // FFMA2 two samples per lane: same layouts, used for large batches
     const Variant* var_tc = nullptr;  // tensor engine (tcgen05 tiles of 128 samples): same layouts, persistent kernel, large batches
+    // traced process model compiled at run time (eh_jit.cu): `var` then points at `jit_var`, a copy of the generic
+    // variant of the shape (same layouts) without launchers -- the kernels are the handles in `jit`
+    bool jit_on = false;
+    Variant jit_var{};
+    eh::JitKernels jit;
+    std::string jit_cubin, jit_names[3];
     // wide-hidden-layer path (bf16 tcgen05 GEMMs, eh_wide.cu): `var` then points at `wide_var`, a descriptor
     // without kernels that only carries the record / slot geometry the shared host code reads
     eh::wide::WideNet* wide = nullptr;
@@ -464,6 +471,29 @@ const Variant* pick_variant(const eh_ctx* c, int64_t B)
     return c->var;
 }
 
+// launchers: compiled-in variants bring their own (eh_variant_impl.cuh); the run-time compiled one goes through its handles
+static bool is_jit(const eh_ctx* c, const Variant* v) { return c->jit_on && v == &c->jit_var; }
+static cudaError_t vlaunch_step(const eh_ctx* c, const Variant* v, const StepArgs& a, int grid, int nwarps, size_t smem, cudaStream_t st, bool pdl)
+{
+    if (is_jit(c, v)) return jit_launch(c->jit.k_step, &a, grid, nwarps * 32, smem, st, pdl);
+    return v->launch_step(a, grid, nwarps, smem, st, pdl);
+}
+static cudaError_t vlaunch_eval(const eh_ctx* c, const Variant* v, const EvalArgs& a, int grid, int nwarps, size_t smem, cudaStream_t st)
+{
+    if (is_jit(c, v)) return jit_launch(c->jit.k_eval, &a, grid, nwarps * 32, smem, st, false);
+    return v->launch_eval(a, grid, nwarps, smem, st);
+}
+static cudaError_t vlaunch_epoch(const eh_ctx* c, const Variant* v, const EpochArgs& a, int grid, int nwarps, size_t smem, cudaStream_t st)
+{
+    if (is_jit(c, v)) return jit_launch_cooperative(c->jit.k_epoch, &a, grid, nwarps * 32, smem, st);
+    return v->launch_epoch(a, grid, nwarps, smem, st);
+}
+static cudaError_t vepoch_max_grid(const eh_ctx* c, const Variant* v, int nwarps, size_t smem, int* max_ctas)
+{
+    if (is_jit(c, v)) return jit_max_grid(c->jit.k_epoch, nwarps * 32, smem, max_ctas);
+    return v->epoch_max_grid(nwarps, smem, max_ctas);
+}
+
 // ... and which one serves a persistent launch: the tensor engine pays off once every SM has a few 128-sample tiles per
 // step (EH_TC_MIN_BATCH overrides the threshold)
 // 0: the tensor engine is opt-in (EH_TC_MIN_BATCH=<batch size from which it serves the persistent launches>)
@@ -729,7 +759,7 @@ eh_status enqueue_stat_prepass(eh_ctx* c, const float* rec, const int* idx, int6
     for (int i = 0; i < 4; i++) a.pmc[i] = c->pmc[i];
     for (int t = 0; t < MAXT; t++) a.shift_y[t] = sp.shift_y[t];
     a.partial = c->d_statpart;
-    CK(v->launch_eval(a, grid, nwarps, (size_t)(rup4(v->NW) + SS_FLOATS) * 4, c->stream));
+    CK(vlaunch_eval(c, v, a, grid, nwarps, (size_t)(rup4(v->NW) + SS_FLOATS) * 4, c->stream));
     StatSeedArgs z;
     memset(&z, 0, sizeof z);
     z.partial = c->d_statpart; z.nparts = grid; z.Tk = v->T; z.T = c->n_targ; z.agg_mean = c->agg_mean; z.bscal = bscal_row;
@@ -761,7 +791,7 @@ eh_status enqueue_steps(eh_ctx* c, int64_t n, int64_t B, int64_t b0, int64_t b1,
             if (ps != EH_OK) return ps;
         }
         if (profile) CK(cudaEventRecord(c->prof_ev[2 * (prof_off + b - b0)], c->stream));
-        CK(pick_variant(c, Bk)->launch_step(a, g.grid, g.nwarps, g.smem, c->stream, pdl));
+        CK(vlaunch_step(c, pick_variant(c, Bk), a, g.grid, g.nwarps, g.smem, c->stream, pdl));
         if (profile) CK(cudaEventRecord(c->prof_ev[2 * (prof_off + b - b0) + 1], c->stream));
         u.G = g.grid;
         u.bscal = a.bscal;
@@ -844,7 +874,7 @@ eh_status enqueue_persistent(eh_ctx* c, const float* rec, const int* idx, const 
         wcap -= wcap % wpc;
         if (wcap < wpc) return EH_OK;
         int max_ctas = 0;
-        if (v->epoch_max_grid(wcap + 1, fixed + extra_of(0) + (size_t)wcap * stage, &max_ctas) != cudaSuccess) { cudaGetLastError(); return EH_OK; }
+        if (vepoch_max_grid(c, v, wcap + 1, fixed + extra_of(0) + (size_t)wcap * stage, &max_ctas) != cudaSuccess) { cudaGetLastError(); return EH_OK; }
         max_ctas = std::min(max_ctas, std::max(1, c->nsm - reserve_sms));
         if (eg) max_ctas = std::max(1, std::min(max_ctas, atoi(eg)));
         if (max_ctas < 1) return EH_OK;
@@ -972,7 +1002,7 @@ eh_status enqueue_persistent(eh_ctx* c, const float* rec, const int* idx, const 
     }
     if (!launched) {
         CK(cudaEventRecord(c->ev0, c->stream));
-        cudaError_t le = v->launch_epoch(a, G, w + 1, smem, c->stream);
+        cudaError_t le = vlaunch_epoch(c, v, a, G, w + 1, smem, c->stream);
         if (le != cudaSuccess) {
             // e.g. cooperative launch refused: fall back to the two-kernel path
             cudaGetLastError();
@@ -1774,7 +1804,23 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
             pd.imm[i] = prog[(size_t)i].imm;
         }
     }
-    c->var2 = (v->engine == 0) ? find_variant(v->pm, v->P, v->NH, v->H, v->NOUT, v->act, v->scale, 2) : nullptr;
+    // run-time specialisation of the traced program (EH_FLAG_JIT, or EH_JIT=1 for every traced model; EH_JIT=0: never)
+    {
+        const char* ej = getenv("EH_JIT");
+        const bool want = use_prog && (ej ? (ej[0] && ej[0] != '0') : (d->flags & EH_FLAG_JIT) != 0);
+        if (want) {
+            std::string jerr;
+            if (!jit_compile(c->h_prog, *v, &c->jit_cubin, c->jit_names, &c->jit.name, &c->jit.from_cache, &c->jit.compile_seconds, &jerr))
+                return fail(c, EH_EUNSUPPORTED, "run-time specialisation of the traced process model failed: %s", jerr.c_str());
+            c->jit_var = *v;
+            c->jit_var.name = c->jit.name.c_str();
+            c->jit_var.prepare = nullptr; c->jit_var.launch_step = nullptr; c->jit_var.launch_eval = nullptr;
+            c->jit_var.launch_epoch = nullptr; c->jit_var.epoch_max_grid = nullptr; c->jit_var.epoch_func = nullptr;
+            c->jit_on = true;
+            c->var = v = &c->jit_var;
+        }
+    }
+    c->var2 = (v->engine == 0 && !c->jit_on) ? find_variant(v->pm, v->P, v->NH, v->H, v->NOUT, v->act, v->scale, 2) : nullptr;
     c->var_tc = (v->engine == 0 && !use_prog && !getenv("EH_NO_TC")) ? find_variant(v->pm, v->P, v->NH, v->H, v->NOUT, v->act, v->scale, 4) : nullptr;
     c->n_pred_raw = d->n_pred; c->n_forc_raw = d->n_forc; c->n_targ = d->n_targ;
     c->use_bn = ch.input_batchnorm ? 1 : 0;
@@ -2181,7 +2227,7 @@ eh_status enqueue_host_step_compute(eh_ctx* c, HostStage& h, int64_t B, float* l
     a.idx = nullptr; a.rec_base = 0; a.B = (int)B; a.bscal = h.d_bscal;
     Geom g = step_geometry(c, B, reserve_sms);
     const bool pdl = false;  // the step follows memcpy/pack work here, nothing to overlap with
-    CK(pick_variant(c, B)->launch_step(a, g.grid, g.nwarps, g.smem, c->stream, pdl));
+    CK(vlaunch_step(c, pick_variant(c, B), a, g.grid, g.nwarps, g.smem, c->stream, pdl));
     UpdateArgs u;
     fill_update_args(c, u);
     u.G = g.grid; u.bscal = h.d_bscal; u.loss_out = loss_dst;
@@ -2244,7 +2290,7 @@ eh_status flush_host_group(eh_ctx* c)
             a.rec = reinterpret_cast<const float4*>(rec + (size_t)i * B * v->R4);
             a.idx = nullptr; a.rec_base = 0; a.B = (int)B; a.bscal = bscal + (size_t)i * BS_STRIDE;
             Geom geo = step_geometry(c, B, EH_PACK_HOST_CTAS);
-            CK(pick_variant(c, B)->launch_step(a, geo.grid, geo.nwarps, geo.smem, c->stream, false));
+            CK(vlaunch_step(c, pick_variant(c, B), a, geo.grid, geo.nwarps, geo.smem, c->stream, false));
             UpdateArgs u;
             fill_update_args(c, u);
             u.G = geo.grid; u.bscal = a.bscal; u.loss_out = r.loss0 + i;
@@ -2503,6 +2549,13 @@ eh_status eh_create(eh_ctx** out, const eh_model_desc* desc)
         size_t stage = (size_t)std::max(v->stage_floats, v->NPART) * 4;
         int wmax = (int)std::min<size_t>((size_t)v->max_warps, (c->smem_optin - fixed - 8192) / stage);
         if (wmax < 1) return fail(c, EH_EUNSUPPORTED, "variant %s needs %zu B of shared memory per warp", v->name, stage);
+        if (c->jit_on) {
+            std::string jerr;
+            if (!jit_load(c->jit_cubin, c->jit_names, &c->jit, &jerr)) return fail(c, EH_ECUDA, "run-time compiled kernels: %s", jerr.c_str());
+            c->jit_var.epoch_func = c->jit.k_epoch;
+            std::string().swap(c->jit_cubin);
+            CK(jit_prepare(c->jit, c->smem_optin - 256, fixed));
+        }
         if (v->prepare) CK(v->prepare(c->smem_optin - 256, fixed));  // kernels carry a few bytes of static shared memory
         if (c->var2) CK(c->var2->prepare(c->smem_optin - 256, fixed));
         if (c->var_tc) CK(c->var_tc->prepare(c->smem_optin - 256, fixed));
@@ -2574,6 +2627,7 @@ void eh_destroy(eh_ctx* c)
     c->wide = nullptr;
     if (c->gexec) cudaGraphExecDestroy(c->gexec);
     if (c->pg_exec) cudaGraphExecDestroy(c->pg_exec);
+    jit_unload(&c->jit);
     if (c->pg_graph) cudaGraphDestroy(c->pg_graph);
     for (int r = 0; r < c->world && c->world > 1; r++)
         if (r != c->rank && c->dp_peer[r]) cudaIpcCloseMemHandle(c->dp_peer[r]);
@@ -3006,7 +3060,7 @@ eh_status eh_eval(eh_ctx* c, int32_t split, float* yhat, double* stats, float* n
     if (grid < 1) grid = 1;
     size_t smem = (size_t)(rup4(v->NW) + SS_FLOATS) * 4;
     CK(cudaEventRecord(c->ev0, c->stream));
-    CK(v->launch_eval(a, grid, nwarps, smem, c->stream));
+    CK(vlaunch_eval(c, v, a, grid, nwarps, smem, c->stream));
     CK(cudaEventRecord(c->ev1, c->stream));
     std::vector<double> part((size_t)grid * v->T * EVAL_NSTAT);
     CK(cudaMemcpyAsync(part.data(), c->d_evalpart, part.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -3143,6 +3197,23 @@ eh_status eh_dp_set_batch_moments(eh_ctx* c, int64_t B, const double* global)
 const char* eh_kernel_variant(const eh_ctx* c)
 {
     return (c && c->var && c->var->name) ? c->var->name : "";
+}
+
+eh_status eh_jit_check(const eh_model_desc* desc, char* info, size_t info_bytes)
+{
+    if (!desc) return fail(nullptr, EH_EINVAL, "null argument");
+    eh_ctx* c = new (std::nothrow) eh_ctx();
+    if (!c) return fail(nullptr, EH_ENOMEM, "out of host memory");
+    c->nsm = 148; c->smem_optin = 232448;   // B200; the plan does not depend on a device being present
+    eh_model_desc d = *desc;
+    d.flags |= EH_FLAG_JIT;
+    eh_status s = build_plan(c, &d);
+    if (s == EH_OK && !c->jit_on) s = fail(c, EH_EUNSUPPORTED, "the planner did not choose a generic exact-fp32 variant for this model (variant %s)", c->var ? c->var->name : "?");
+    if (s != EH_OK) g_create_error = c->err;
+    if (s == EH_OK && info && info_bytes)
+        snprintf(info, info_bytes, "%s cubin=%zu cached=%d seconds=%.2f", c->jit.name.c_str(), c->jit_cubin.size(), c->jit.from_cache ? 1 : 0, c->jit.compile_seconds);
+    delete c;
+    return s;
 }
 
 const char* eh_epoch_variant(const eh_ctx* c, int64_t batch)

@@ -27,9 +27,13 @@ def _ptr_array(arrs):
 
 
 class FusedSession:
-    def __init__(self, model, *, training_loss="mse", agg="sum", opt=None, device=0, flags=0, extra_loss=None):
+    def __init__(self, model, *, training_loss="mse", agg="sum", opt=None, device=0, flags=0, extra_loss=None, jit=False):
+        """jit=True: a traced process model is compiled into the kernels at creation (NVRTC, EH_FLAG_JIT; seconds the first
+        time, cached on disk afterwards) instead of being interpreted per sample."""
         self.lib = load()
         self.model = model
+        if jit:
+            flags |= _abi.EH_FLAG_JIT
         self.bundle = build_desc(model, training_loss=training_loss, agg=agg, opt=opt, device=device, flags=flags, extra_loss=extra_loss)
         h = C.c_void_p()
         st = self.lib.eh_create(C.byref(h), self.bundle.byref())

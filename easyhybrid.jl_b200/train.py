@@ -76,7 +76,7 @@ def run_epoch(sess, perm0, cfg):
     return sess.epoch(perm0, cfg.batchsize)
 
 
-def train(model, data, save_ps=(), *, train_cfg=None, data_cfg=None, **kwargs):
+def train(model, data, save_ps=(), *, train_cfg=None, data_cfg=None, jit=False, **kwargs):
     """train(model, data; kwargs...) -- flat kwargs override TrainConfig / DataConfig fields
     (train.jl:211-219, 300-314).  Returns TrainResults, or None when a split is empty."""
     train_cfg, data_cfg, rest = override_configs(train_cfg or TrainConfig(), data_cfg or DataConfig(), kwargs)
@@ -101,7 +101,7 @@ def train(model, data, save_ps=(), *, train_cfg=None, data_cfg=None, **kwargs):
     _, all_masked = valid_mask(y_tr)
 
     device = cfg.gdev if isinstance(cfg.gdev, int) else 0
-    sess = FusedSession(model, training_loss=cfg.training_loss, agg=cfg.agg, opt=cfg.opt, device=device, extra_loss=cfg.extra_loss)
+    sess = FusedSession(model, training_loss=cfg.training_loss, agg=cfg.agg, opt=cfg.opt, device=device, extra_loss=cfg.extra_loss, jit=jit)
     try:
         sess.upload(0, xf_tr, y_tr)
         sess.upload(1, xf_va, y_va)

@@ -202,6 +202,11 @@ typedef struct {
                                   fp32-level accuracy) where a variant exists; default is the exact-fp32
                                   FFMA2 engine */
 
+#define EH_FLAG_JIT 32u       /* traced process model (EH_PM_PROGRAM) on the exact-fp32 path: compile the program into the
+                                  kernels at eh_create (NVRTC, a few seconds, cached on disk under $EH_JIT_CACHE or
+                                  ~/.cache/easyhybrid_b200) instead of interpreting it per sample.  eh_create fails with
+                                  EH_EUNSUPPORTED if NVRTC is not available; models that take another path ignore it */
+
 enum { EH_SPLIT_TRAIN = 0, EH_SPLIT_VAL = 1 };
 
 /* number of doubles written per target by eh_eval (sufficient statistics):
@@ -326,6 +331,11 @@ eh_status eh_set_profiling(eh_ctx* ctx, int32_t on);
  * "ffma2/PmProgram/..." (same kernels, process model interpreted per sample) or "wide/bf16-tcgen05".
  * The reference has no counterpart; callers use it to report / assert the path a model took.          */
 const char* eh_kernel_variant(const eh_ctx* ctx);
+/* Plans `desc` as eh_create would and compiles its traced process model with NVRTC (EH_FLAG_JIT implied) WITHOUT touching a
+ * device: EH_OK and a one-line description ("nvrtc/PmTraced#<hash>/... cubin=<bytes> cached=<0|1> seconds=<s>") in `info`,
+ * or the planner's / compiler's error through eh_last_error(NULL).  For build checks and for warming the disk cache.
+ * The reference has no counterpart (Julia compiles the user's closure itself, GenericHybridModel.jl:425). */
+eh_status eh_jit_check(const eh_model_desc* desc, char* info, size_t info_bytes);
 /* ... and the family that serves the PERSISTENT launches (eh_epoch / eh_run_steps) at batch size `batch`: the same as above,
  * or "tcgen05/..." where the tensor engine (hidden-layer products on tcgen05 with TMEM operands) takes large batches.     */
 const char* eh_epoch_variant(const eh_ctx* ctx, int64_t batch);
