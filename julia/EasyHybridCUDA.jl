@@ -310,24 +310,31 @@ end
 # ---------------------------------------------------------------------------------------------------------------
 # The backend type and the two seams
 # ---------------------------------------------------------------------------------------------------------------
+const EH_FLAG_JIT = 32   # include/easyhybrid_cuda.h
+
 """
-    FusedCUDA(; device = 0, training_loss = :mse, agg = sum)
+    FusedCUDA(; device = 0, training_loss = :mse, agg = sum, weight_l2 = nothing, jit = false)
 
 `autodiff_backend = FusedCUDA()` selects the fused sm_100a path.  `training_loss` / `agg` repeat the TrainConfig fields
 (the per-step seam only sees the closure built by `build_loss_fn`, not the config); a `PerTarget((:nseLoss, :mse))` goes here too.
+`jit = true`: a `mechanistic_model` that is not one of the built-in forms is compiled into the kernels instead of being
+interpreted per sample (a few seconds at the first `eh_create`, cached on disk afterwards).
 """
 mutable struct FusedCUDA <: ADTypes.AbstractADType
     device::Int32
     training_loss::Union{Symbol, PerTarget}
     agg::Function
     weight_l2::Union{Nothing, NamedTuple}   # (lambda = 1f-3, branches = [:Rb], normalize = true): the documented extra_loss, natively
+    jit::Bool                               # compile a traced mechanistic_model into the kernels (NVRTC at eh_create, cached on disk)
     session::Union{Nothing, Session}
 end
-FusedCUDA(; device = 0, training_loss = :mse, agg = sum, weight_l2 = nothing) = FusedCUDA(Int32(device), training_loss, agg, weight_l2, nothing)
+FusedCUDA(; device = 0, training_loss = :mse, agg = sum, weight_l2 = nothing, jit = false) =
+    FusedCUDA(Int32(device), training_loss, agg, weight_l2, jit, nothing)
 
 function session!(b::FusedCUDA, model, opt, ps)
     if b.session === nothing
-        b.session = Session(model, opt, b.training_loss, b.agg; device = b.device, weight_l2 = b.weight_l2)
+        b.session = Session(model, opt, b.training_loss, b.agg; device = b.device, weight_l2 = b.weight_l2,
+                            flags = b.jit ? EH_FLAG_JIT : 0)
         set_params!(b.session, ps)
     end
     return b.session
