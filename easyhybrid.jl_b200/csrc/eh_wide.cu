@@ -56,8 +56,10 @@ cudaError_t gemm_prepare()
     if ((e = cudaFuncSetAttribute(k_wide_gemm<GEMM_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(GEMM_FWD))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_wide_gemm<GEMM_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(GEMM_BWD))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_wide_gemm<GEMM_WGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(GEMM_WGRAD))) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_wide_gemm_p<GEMM_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, PG_SMEM)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_wide_gemm_p<GEMM_BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, PG_SMEM)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_wide_gemm_p<GEMM_FWD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PG_SMEM)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_wide_gemm_p<GEMM_BWD, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PG_SMEM)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_wide_gemm_p<GEMM_FWD, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PG_SMEM)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_wide_gemm_p<GEMM_BWD, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PG_SMEM)) != cudaSuccess) return e;
     done = true;
     return cudaSuccess;
 }
@@ -83,7 +85,50 @@ cudaError_t gemm_bwd(const CUtensorMap& tmD, const CUtensorMap& tmWt, int M, int
     return cudaGetLastError();
 }
 // persistent forms (one CTA per SM, 128 x 256 tiles, double-buffered accumulator); tmW / tmWt must be built with
-// box rows = PG_BN
+// box rows = pg_box_rows().  With an even number of row tiles the CTAs run
+// can run as clusters of two that share the weight tile by multicast (EH_WIDE_CLUSTER=1; measured 4 us SLOWER per GEMM than
+// single CTAs: the kernels are bound by shared-memory bandwidth -- TMA writes plus MMA operand reads -- not by L2 reads).
+static bool pg_cluster() { static const bool on = getenv("EH_WIDE_CLUSTER") != nullptr; return on; }
+int pg_box_rows() { return pg_cluster() ? PG_BN / 2 : PG_BN; }
+template <int MODE>
+static cudaError_t launch_gemm_p(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& g, cudaStream_t st)
+{
+    static int nsm = 0, max_clusters = -1;
+    if (!nsm) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int mt = g.M / BM, nn = g.N / PG_BN;
+    cudaLaunchConfig_t cfg{};
+    cfg.blockDim = dim3(PG_THREADS);
+    cfg.dynamicSmemBytes = PG_SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    if (pg_cluster()) {
+        if (mt % 2) return cudaErrorInvalidValue;   // (the opt-in cluster form needs an even number of row tiles)
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if (max_clusters < 0) {
+            cfg.gridDim = dim3((unsigned)(nsm & ~1));
+            int mc = 0;
+            if (cudaOccupancyMaxActiveClusters(&mc, k_wide_gemm_p<MODE, 2>, &cfg) != cudaSuccess || mc < 1) { cudaGetLastError(); mc = 0; }
+            max_clusters = mc;
+        }
+        if (max_clusters > 0) {
+            const int units = (mt / 2) * nn;
+            const int ncl = std::min(std::min(max_clusters, nsm / 2), units);
+            cfg.gridDim = dim3((unsigned)(2 * ncl));
+            return cudaLaunchKernelEx(&cfg, k_wide_gemm_p<MODE, 2>, tmA, tmB, g);
+        }
+        cfg.attrs = nullptr;
+        cfg.numAttrs = 0;
+    }
+    cfg.gridDim = dim3((unsigned)std::min(mt * nn, nsm));
+    return cudaLaunchKernelEx(&cfg, k_wide_gemm_p<MODE, 1>, tmA, tmB, g);
+}
 int persistent_grid(int M, int N)
 {
     static int nsm = 0;
@@ -100,8 +145,7 @@ cudaError_t gemm_fwd_p(const CUtensorMap& tmA, const CUtensorMap& tmW, int M, in
 {
     GemmArgs g{};
     g.M = M; g.N = N; g.K = K; g.ksplits = 1; g.act = act; g.bias = bias; g.out16 = out;
-    k_wide_gemm_p<GEMM_FWD><<<persistent_grid(M, N), PG_THREADS, PG_SMEM, st>>>(tmA, tmW, g);
-    return cudaGetLastError();
+    return launch_gemm_p<GEMM_FWD>(tmA, tmW, g, st);
 }
 cudaError_t gemm_bwd_p(const CUtensorMap& tmD, const CUtensorMap& tmWt, int M, int N, int K, const __nv_bfloat16* aux, int act,
                        __nv_bfloat16* out, cudaStream_t st, float* colsum, const float* xb, const float* bscal, int R4, int P1,
@@ -110,8 +154,7 @@ cudaError_t gemm_bwd_p(const CUtensorMap& tmD, const CUtensorMap& tmWt, int M, i
     GemmArgs g{};
     g.M = M; g.N = N; g.K = K; g.ksplits = 1; g.act = act; g.aux = aux; g.out16 = out;
     g.colsum = colsum; g.xb = xb; g.bscal = bscal; g.R4 = R4; g.P1 = P1; g.use_bn = use_bn;
-    k_wide_gemm_p<GEMM_BWD><<<persistent_grid(M, N), PG_THREADS, PG_SMEM, st>>>(tmD, tmWt, g);
-    return cudaGetLastError();
+    return launch_gemm_p<GEMM_BWD>(tmD, tmWt, g, st);
 }
 
 // partial[z] = D[rows z]^T A[rows z]: D [Kall x M] bf16, A [Kall x N] bf16 (batch rows), ksplits slices of Kall
@@ -188,7 +231,7 @@ WideNet* WideNet::create(const WideModel& m, char* err, size_t errlen)
     e = cudaFuncSetAttribute((const void*)hk, cudaFuncAttributeMaxDynamicSharedMemorySize, head_smem);
     if (e != cudaSuccess) return bail("head smem", e);
     const size_t HH = (size_t)m.H * m.H;
-    const int bn = w->persist_ ? PG_BN : gemm_bn(GEMM_FWD);
+    const int bn = w->persist_ ? pg_box_rows() : gemm_bn(GEMM_FWD);
     // images of the embedded chain: everything outside the real entries (padding, other chains' units) stays zero
     for (int l = 1; l <= m.NH; l++) {
         if ((e = cudaMalloc(&w->Bp_[l - 1], (size_t)m.H * 4)) != cudaSuccess) return bail("cudaMalloc", e);
@@ -318,7 +361,12 @@ cudaError_t WideNet::forward(const float* rec, const int* idx, long long rec_bas
                                                    reinterpret_cast<float4*>(xb_));
     WN(cudaGetLastError());
     const int rows_per_cta = (256 / (H / 8)) * FIRST_ROWS;
-    k_wide_first<<<(unsigned)((B + rows_per_cta - 1) / rows_per_cta), 256, 0, st>>>(xb_, W1img_, Bp_[0], bscal, m_.use_bn, d, B, m_.act, A_[0]);
+    {
+        const unsigned g1 = (unsigned)((B + rows_per_cta - 1) / rows_per_cta);
+        if (d.P <= 2) k_wide_first<2><<<g1, 256, 0, st>>>(xb_, W1img_, Bp_[0], bscal, m_.use_bn, d, B, m_.act, A_[0]);
+        else if (d.P <= 4) k_wide_first<4><<<g1, 256, 0, st>>>(xb_, W1img_, Bp_[0], bscal, m_.use_bn, d, B, m_.act, A_[0]);
+        else k_wide_first<8><<<g1, 256, 0, st>>>(xb_, W1img_, Bp_[0], bscal, m_.use_bn, d, B, m_.act, A_[0]);
+    }
     WN(cudaGetLastError());
     for (int l = 2; l <= m_.NH; l++) {
         if (persist_) WN(gemm_fwd_p(tmA_k_[l - 2], tmWf_[l - 1], B, H, H, Bp_[l - 1], m_.act, A_[l - 1], st));
@@ -499,7 +547,7 @@ extern "C" eh_status eh_selftest_wide_gemm(int32_t mode, int32_t M, int32_t N, i
     else WCK(cudaMalloc(&dO16, (size_t)M * N * 2));
     CUtensorMap tmA, tmB;
     bool ok;
-    if (!wg) ok = make_map_bf16(&tmA, dA, K, M, K, BM) && make_map_bf16(&tmB, dB, K, N, K, pers ? PG_BN : gemm_bn(mode));
+    if (!wg) ok = make_map_bf16(&tmA, dA, K, M, K, BM) && make_map_bf16(&tmB, dB, K, N, K, pers ? pg_box_rows() : gemm_bn(mode));
     else ok = make_map_bf16(&tmA, dA, M, K, M, BK) && make_map_bf16(&tmB, dB, N, K, N, BK);
     if (!ok) return EH_ECUDA;
     cudaEvent_t e0, e1;

@@ -401,26 +401,64 @@ k_wide_gemm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
 // ---- persistent forward / backward-data GEMM -------------------------------------------------------------------------
 // One CTA per SM walks the 128 x 256 output tiles (tile t = blockIdx.x + i * gridDim.x).  Two accumulator buffers in
-// tensor memory (2 x 256 columns) let the MMA warp start tile i+1 while the EIGHT epilogue warps (two per TMEM lane
-// quarter, 128 columns each) drain tile i; the TMA producer simply keeps the 3-stage ring full across tile borders.
+// tensor memory (2 x 256 columns) let the MMA warp start tile i+1 while the SIXTEEN epilogue warps (four per TMEM lane
+// quarter, 64 columns each) drain tile i; the TMA producer simply keeps the 3-stage ring full across tile borders.
+// The epilogue is a chain of dependent long-latency steps (tcgen05.ld -> math -> STS -> LDS -> STG); with two warps per
+// scheduler (the first form: eight warps of 128 columns) it, not the tensor pipe, set the pace: 6.4 us per tile against
+// 2.2 us of MMAs.  PG_EPI_WARPS = 8 keeps that form for comparison.
 // Barriers: full/empty per stage (TMA <-> MMA), tmem_full/tmem_empty per accumulator buffer (MMA <-> epilogue).
-constexpr int PG_BN = 256, PG_STAGES = 3, PG_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+#ifndef PG_EPI_WARPS
+#define PG_EPI_WARPS 16
+#endif
+constexpr int PG_BN = 256, PG_STAGES = 3, PG_THREADS = (2 + PG_EPI_WARPS) * 32;   // warp 0 TMA, warp 1 MMA, then the epilogue warps
+constexpr int PG_EPI_THREADS = PG_EPI_WARPS * 32;
+constexpr int PG_CW = PG_BN / (PG_EPI_WARPS / 4);              // output columns of one epilogue warp (64)
 constexpr int PG_STAGE_BYTES = (BM + PG_BN) * BK * 2;          // 48 KB
-constexpr int PG_OPITCH = 128 * 2 + 16;                        // staged output row of one epilogue warp: 128 bf16 + pad
-constexpr int PG_STG_BYTES = 8 * 32 * PG_OPITCH;               // 69 632
+constexpr int PG_OPITCH = PG_CW * 2 + 16;                      // staged row of one epilogue warp: PG_CW bf16 + pad
+constexpr int PG_STG_BYTES = PG_EPI_WARPS * 32 * PG_OPITCH;    // 73 728
 constexpr int PG_SIDE_BYTES = 2 * PG_BN * 4;                   // bias double buffer
 constexpr int PG_SMEM = PG_STAGES * PG_STAGE_BYTES + PG_STG_BYTES + PG_SIDE_BYTES + 1024 + 256;
+static_assert(PG_SMEM <= 232448, "persistent GEMM: shared memory");
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// cluster forms: the TMA box lands at the same shared-memory offset of every CTA in `mask` and completes bytes on the
+// barrier at the same offset there; the commit arrives on the barrier at the same offset of every CTA in `mask`
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar, uint16_t mask)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 
-template <int MODE>
+// CL = 2: clusters of two CTAs work on two row tiles of the SAME column tile at a time; each CTA fetches one half of the
+// weight tile of a stage (128 of the 256 rows) and multicasts it into both, so a tile costs 256 KB of L2 reads instead of
+// 384 KB -- the kernel runs at the L2 throughput limit (about 12 TB/s), not at the tensor pipe's.  A stage is reusable
+// when BOTH CTAs' MMAs have read it (the commits arrive on both empty barriers).  tmB: box of BN rows for CL = 1, BN / 2 for CL = 2.
+template <int MODE, int CL>
 __global__ void __launch_bounds__(PG_THREADS, 1)
 k_wide_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs g)
 {
     static_assert(MODE == GEMM_FWD || MODE == GEMM_BWD, "persistent form serves forward and backward-data");
+    static_assert(CL == 1 || CL == 2, "cluster of one or two CTAs");
     constexpr int BN = PG_BN, STAGES = PG_STAGES, STAGE_BYTES = PG_STAGE_BYTES, A_STAGE_BYTES = BM * BK * 2;
     constexpr int STG_OFF = STAGES * STAGE_BYTES, SIDE_OFF = STG_OFF + PG_STG_BYTES, BAR_OFF = SIDE_OFF + PG_SIDE_BYTES;
     extern __shared__ uint8_t smem_raw[];
@@ -436,19 +474,26 @@ k_wide_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     float* s_bias = reinterpret_cast<float*>(gen_base + SIDE_OFF);                 // [2][BN]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_n = g.N / BN, num_tiles = (g.M / BM) * num_n;
+    const int num_n = g.N / BN;
     const int nkb = g.K / BK;
+    // work units: (row-tile group of CL tiles, column tile); cluster cid walks units cid, cid + ncl, ...; CTA `crank` of
+    // the cluster takes row tile mp * CL + crank of the group
+    const int crank = CL > 1 ? (int)cluster_ctarank() : 0;
+    const int cid = blockIdx.x / CL, ncl = gridDim.x / CL;
+    const int num_units = (g.M / BM / CL) * num_n;
+    auto unit_m0 = [&](int u) { return ((u / num_n) * CL + crank) * BM; };
+    auto unit_n0 = [&](int u) { return (u % num_n) * BN; };
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         for (int s = 0; s < STAGES; s++) {
             mbar_init(full_bar(s), 1);
-            mbar_init(empty_bar(s), 1);
+            mbar_init(empty_bar(s), CL);
         }
         for (int b = 0; b < 2; b++) {
             mbar_init(tfull_bar(b), 1);
-            mbar_init(tempty_bar(b), 8);   // one arrival per epilogue warp
+            mbar_init(tempty_bar(b), PG_EPI_WARPS);   // one arrival per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -459,16 +504,18 @@ k_wide_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();   // the peer's barriers exist before anything arrives on them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
     if (warp == 0) {
         if (lane == 0) {
             // ===== TMA producer: one continuous ring over all tiles of this CTA =====
+            constexpr int B_HALF_BYTES = (BN / 2) * BK * 2;
             int kbc = 0;
             bool pok = true;
-            for (int t = blockIdx.x; t < num_tiles && pok; t += gridDim.x) {
-                const int m0 = (t / num_n) * BM, n0 = (t % num_n) * BN;
+            for (int u = cid; u < num_units && pok; u += ncl) {
+                const int m0 = unit_m0(u), n0 = unit_n0(u);
                 for (int kb = 0; kb < nkb && pok; kb++, kbc++) {
                     const int s = kbc % STAGES;
                     pok = mbar_wait(empty_bar(s), ((kbc / STAGES) & 1) ^ 1);
@@ -476,7 +523,11 @@ k_wide_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                     const uint32_t sa = base + s * STAGE_BYTES, sb = sa + A_STAGE_BYTES;
                     mbar_expect_tx(full_bar(s), STAGE_BYTES);
                     tma_load_2d(sa, &tmA, kb * BK, m0, full_bar(s));
-                    tma_load_2d(sb, &tmB, kb * BK, n0, full_bar(s));
+                    if (CL > 1) {
+                        tma_load_2d_mc(sb + crank * B_HALF_BYTES, &tmB, kb * BK, n0 + crank * (BN / 2), full_bar(s), (uint16_t)3);
+                    } else {
+                        tma_load_2d(sb, &tmB, kb * BK, n0, full_bar(s));   // one box of BN rows
+                    }
                 }
             }
         }
@@ -486,7 +537,7 @@ k_wide_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
             int kbc = 0, it = 0;
             bool ok = true;
-            for (int t = blockIdx.x; t < num_tiles && ok; t += gridDim.x, it++) {
+            for (int u = cid; u < num_units && ok; u += ncl, it++) {
                 const int ab = it & 1;
                 ok = mbar_wait(tempty_bar(ab), ((it >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator buffer
                 tc_fence_after();
@@ -500,44 +551,57 @@ k_wide_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                     for (int k = 0; k < BK / UMMA_K; k++)
                         tc_mma_bf16(acc, umma_desc(sa + k * UMMA_K * 2, 0, 1024), umma_desc(sb + k * UMMA_K * 2, 0, 1024), idesc,
                                     (kb | k) ? 1u : 0u);
-                    tc_commit(empty_bar(s));
+                    if (CL > 1) tc_commit_mc(empty_bar(s), (uint16_t)3);
+                    else tc_commit(empty_bar(s));
                 }
                 tc_commit(tfull_bar(ab));
             }
         }
     } else {
-        // ===== epilogue: warps 2..9; TMEM lane quarter q = warp % 4, column half h = (warp - 2) / 4 =====
+        // ===== epilogue: warps 2..; TMEM lane quarter q = warp % 4, column slice h = (warp - 2) / 4 of PG_CW columns =====
+        constexpr int CW = PG_CW, NCC = CW / 32;
+        constexpr int LPR = CW / 8, RPI = 32 / LPR;        // 16-byte lanes per staged row, rows per warp-wide instruction
+        constexpr int NAUX = 32 / RPI;                     // 16-byte pieces of the activation strip per thread
         const int q = warp & 3, h = (warp - 2) >> 2;
-        const int et = (warp - 2) * 32 + lane;            // 0..255 among the epilogue threads
+        const int et = (warp - 2) * 32 + lane;            // 0.. among the epilogue threads
         uint8_t* stg = gen_base + STG_OFF + (warp - 2) * (32 * PG_OPITCH);
+        const int prow = lane / LPR, pc16 = lane % LPR;    // this lane's place in the coalesced strip walk
+        // BWD: the activation strip (32 rows x CW columns of A_{l-1}) of the NEXT tile travels in registers while this
+        // tile is worked on, read in the coalesced pattern (full 16-byte lanes of consecutive row pieces)
+        uint4 apre[MODE == GEMM_BWD ? NAUX : 1];
+        auto load_aux = [&](int u) {
+            const int m0 = unit_m0(u), n0 = unit_n0(u);
+            const uint4* ap = reinterpret_cast<const uint4*>(g.aux + (size_t)(m0 + q * 32 + prow) * g.N + n0 + h * CW) + pc16;
+#pragma unroll
+            for (int i = 0; i < NAUX; i++) apre[i] = __ldg(ap + (size_t)i * RPI * (g.N / 8));
+        };
+        if (MODE == GEMM_BWD && cid < num_units) load_aux(cid);
         int it = 0;
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, it++) {
+        for (int u = cid; u < num_units; u += ncl, it++) {
             const int ab = it & 1;
-            const int m0 = (t / num_n) * BM, n0 = (t % num_n) * BN;
+            const int m0 = unit_m0(u), n0 = unit_n0(u);
             const int row = m0 + q * 32 + lane;
-            const int ncol0 = n0 + h * 128;               // first output column of this warp
+            const int ncol0 = n0 + h * CW;                // first output column of this warp
             float* bias = s_bias + ab * BN;
-            uint4 apre[2][4];                              // BWD: activation chunks, two ahead
-            const uint4* ap = reinterpret_cast<const uint4*>(g.aux + (size_t)row * g.N + ncol0);
             if (MODE == GEMM_FWD) {
-                bias[et] = __ldg(g.bias + n0 + et);
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (et < BN) bias[et] = __ldg(g.bias + n0 + et);
+                asm volatile("bar.sync 1, %0;" ::"n"(PG_EPI_THREADS) : "memory");
             } else {
 #pragma unroll
-                for (int u = 0; u < 2; u++)
-#pragma unroll
-                    for (int j = 0; j < 4; j++) apre[u][j] = __ldg(ap + u * 4 + j);
+                for (int i = 0; i < NAUX; i++) *reinterpret_cast<uint4*>(stg + (i * RPI + prow) * PG_OPITCH + pc16 * 16) = apre[i];
+                __syncwarp();
+                if (u + ncl < num_units) load_aux(u + ncl);
             }
             mbar_wait(tfull_bar(ab), (it >> 1) & 1);
             tc_fence_after();
 #pragma unroll
-            for (int cc = 0; cc < 4; cc++) {
+            for (int cc = 0; cc < NCC; cc++) {
                 const int c = cc * 32;
                 uint32_t r[32];
-                tc_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + h * 128 + c), r);
+                tc_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + h * CW + c), r);
                 uint32_t o[16];
                 if (MODE == GEMM_FWD) {
-                    const float4* b4 = reinterpret_cast<const float4*>(bias + h * 128 + c);
+                    const float4* b4 = reinterpret_cast<const float4*>(bias + h * CW + c);
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
                         const float4 b = b4[j];
@@ -545,16 +609,11 @@ k_wide_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                         o[2 * j + 1] = pack_bf16(act1(g.act, __uint_as_float(r[4 * j + 2]) + b.z), act1(g.act, __uint_as_float(r[4 * j + 3]) + b.w));
                     }
                 } else {
-                    uint4 cur[4];
-#pragma unroll
-                    for (int j = 0; j < 4; j++) cur[j] = apre[cc & 1][j];
-                    if (cc + 2 < 4) {
-#pragma unroll
-                        for (int j = 0; j < 4; j++) apre[cc & 1][j] = __ldg(ap + (cc + 2) * 4 + j);
-                    }
+                    // this thread's own row of the activation strip; the result goes back to the same bytes
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
-                        const uint32_t aw[4] = {cur[j].x, cur[j].y, cur[j].z, cur[j].w};
+                        const uint4 cur = *reinterpret_cast<const uint4*>(stg + lane * PG_OPITCH + ((c >> 3) + j) * 16);
+                        const uint32_t aw[4] = {cur.x, cur.y, cur.z, cur.w};
 #pragma unroll
                         for (int e = 0; e < 4; e++) {
                             const float2 af = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw[e]));
@@ -571,14 +630,17 @@ k_wide_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(ab));
-            // BWD: column sums over this warp's 32 rows, straight from the staged strip (lane l owns columns 4l .. 4l+3)
-            float cs[4] = {0.f, 0.f, 0.f, 0.f}, cw[WIDE_MAXP][4];
+            // BWD: column sums over this warp's 32 rows, straight from the staged strip (lane l owns columns NCC l .. NCC l + NCC - 1)
+            float cs[NCC], cw[WIDE_MAXP][NCC];
             const bool want_cs = MODE == GEMM_BWD && g.colsum != nullptr;
             if (want_cs) {
                 float xr[WIDE_MAXP] = {0.f};
 #pragma unroll
+                for (int k = 0; k < NCC; k++) cs[k] = 0.f;
+#pragma unroll
                 for (int p = 0; p < WIDE_MAXP; p++) {
-                    cw[p][0] = cw[p][1] = cw[p][2] = cw[p][3] = 0.f;
+#pragma unroll
+                    for (int k = 0; k < NCC; k++) cw[p][k] = 0.f;
                     if (p < g.P1) {
                         float x = g.xb[(size_t)row * g.R4 + p];
                         if (g.use_bn) x = (x - g.bscal[BS_BN_OFF + 2 * p]) * g.bscal[BS_BN_OFF + 2 * p + 1];
@@ -587,54 +649,66 @@ k_wide_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                 }
 #pragma unroll
                 for (int r2 = 0; r2 < 32; r2++) {
-                    const uint2 v = *reinterpret_cast<const uint2*>(stg + r2 * PG_OPITCH + lane * 8);
-                    const float2 f0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.x));
-                    const float2 f1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.y));
-                    cs[0] += f0.x; cs[1] += f0.y; cs[2] += f1.x; cs[3] += f1.y;
+                    float f[NCC];
+#pragma unroll
+                    for (int k = 0; k < NCC; k += 2) {
+                        const uint32_t v = *reinterpret_cast<const uint32_t*>(stg + r2 * PG_OPITCH + lane * (2 * NCC) + 2 * k);
+                        const float2 ff = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v));
+                        f[k] = ff.x; f[k + 1] = ff.y;
+                    }
+#pragma unroll
+                    for (int k = 0; k < NCC; k++) cs[k] += f[k];
 #pragma unroll
                     for (int p = 0; p < WIDE_MAXP; p++) {
                         if (p < g.P1) {
                             const float x = __shfl_sync(0xffffffffu, xr[p], r2);
-                            cw[p][0] = fmaf(f0.x, x, cw[p][0]); cw[p][1] = fmaf(f0.y, x, cw[p][1]);
-                            cw[p][2] = fmaf(f1.x, x, cw[p][2]); cw[p][3] = fmaf(f1.y, x, cw[p][3]);
+#pragma unroll
+                            for (int k = 0; k < NCC; k++) cw[p][k] = fmaf(f[k], x, cw[p][k]);
                         }
                     }
                 }
             }
             __syncwarp();
-            // 128 bf16 per row = 16 lanes of 16 bytes: two rows per instruction
+            // CW bf16 per row = LPR lanes of 16 bytes: RPI rows per instruction
 #pragma unroll 4
-            for (int r0 = 0; r0 < 32; r0 += 2) {
-                const int rr = r0 + (lane >> 4), cc2 = lane & 15;
-                const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * PG_OPITCH + cc2 * 16);
-                *(reinterpret_cast<uint4*>(g.out16 + (size_t)(m0 + q * 32 + rr) * g.N + ncol0) + cc2) = v;
+            for (int r0 = 0; r0 < 32; r0 += RPI) {
+                const int rr = r0 + prow;
+                const uint4 v = *reinterpret_cast<const uint4*>(stg + rr * PG_OPITCH + pc16 * 16);
+                *(reinterpret_cast<uint4*>(g.out16 + (size_t)(m0 + q * 32 + rr) * g.N + ncol0) + pc16) = v;
             }
             __syncwarp();
             if (want_cs) {
                 // the strip is free now: park this warp's sums in it, combine the four lane-quarter warps of each
-                // column half in a fixed order, one 128-row slab per tile goes out
+                // column slice in a fixed order, one 128-row slab per tile goes out
                 float* mine = reinterpret_cast<float*>(stg);
-                *reinterpret_cast<float4*>(mine + lane * 4) = make_float4(cs[0], cs[1], cs[2], cs[3]);
+#pragma unroll
+                for (int k = 0; k < NCC; k++) mine[lane * NCC + k] = cs[k];
 #pragma unroll
                 for (int p = 0; p < WIDE_MAXP; p++)
-                    if (p < g.P1) *reinterpret_cast<float4*>(mine + (1 + p) * 128 + lane * 4) = make_float4(cw[p][0], cw[p][1], cw[p][2], cw[p][3]);
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                const int h2 = et >> 7, cl = et & 127;   // thread et owns output column et of the tile
-                for (int p = 0; p <= g.P1; p++) {
-                    float v = 0.f;
+                    if (p < g.P1) {
 #pragma unroll
-                    for (int qq = 0; qq < 4; qq++) {
-                        const int wi = 4 * h2 + ((qq + 2) & 3);   // epilogue warp with lane quarter qq and column half h2
-                        v += reinterpret_cast<const float*>(gen_base + STG_OFF + wi * (32 * PG_OPITCH))[p * 128 + cl];
+                        for (int k = 0; k < NCC; k++) mine[(1 + p) * CW + lane * NCC + k] = cw[p][k];
                     }
-                    g.colsum[((size_t)(m0 / BM) * (1 + g.P1) + p) * g.N + n0 + et] = v;
+                asm volatile("bar.sync 1, %0;" ::"n"(PG_EPI_THREADS) : "memory");
+                if (et < BN) {
+                    const int h2 = et / CW, cl = et % CW;   // thread et owns output column et of the tile
+                    for (int p = 0; p <= g.P1; p++) {
+                        float v = 0.f;
+#pragma unroll
+                        for (int qq = 0; qq < 4; qq++) {
+                            const int wi = 4 * h2 + ((qq + 2) & 3);   // epilogue warp with lane quarter qq and column slice h2
+                            v += reinterpret_cast<const float*>(gen_base + STG_OFF + wi * (32 * PG_OPITCH))[p * CW + cl];
+                        }
+                        g.colsum[((size_t)(m0 / BM) * (1 + g.P1) + p) * g.N + n0 + et] = v;
+                    }
                 }
-                asm volatile("bar.sync 1, 256;" ::: "memory");   // the strips are rewritten by the next tile
+                asm volatile("bar.sync 1, %0;" ::"n"(PG_EPI_THREADS) : "memory");   // the strips are rewritten by the next tile
             }
             __syncwarp();   // the strip is rewritten by the next tile
         }
     }
     __syncthreads();
+    if (CL > 1) cluster_sync_all();   // no multicast write or remote arrival may find this CTA gone
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");

@@ -70,41 +70,51 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) { return pack_bf16
 // A thread owns 8 consecutive outputs (their weights stay in registers) and walks FIRST_ROWS rows of the batch;
 // a CTA covers the whole width for 256 / (H / 8) row groups.
 constexpr int FIRST_ROWS = 16;
-__global__ void __launch_bounds__(256) k_wide_first(const float* xb, const float* W1img, const float* b1img, const float* bscal,
-                                                    int use_bn, WideDims d, int B, int act, __nv_bfloat16* A1)
+// PMAX: compile-time bound on the chain inputs (2 / 4 / 8) -- the weights a thread keeps in registers.  Rows go four at
+// a time with their inputs loaded first: the kernel is a stream of 16-byte stores (H bf16 per row) and must not wait for
+// one L2 round trip per row.
+template <int PMAX>
+__global__ void __launch_bounds__(256) k_wide_first(const float* __restrict__ xb, const float* __restrict__ W1img,
+                                                    const float* __restrict__ b1img, const float* __restrict__ bscal, int use_bn,
+                                                    WideDims d, int B, int act, __nv_bfloat16* __restrict__ A1)
 {
     const int per_row = d.H / 8;                       // threads across the width
     const int groups = 256 / per_row;                  // row groups per CTA
     const int o0 = (threadIdx.x % per_row) * 8;
     const int r0 = (blockIdx.x * groups + threadIdx.x / per_row) * FIRST_ROWS;
-    float bias[8], w[WIDE_MAXP][8], mu[WIDE_MAXP], rs[WIDE_MAXP];
+    float bias[8], w[PMAX][8], mu[PMAX], rs[PMAX];
 #pragma unroll
     for (int j = 0; j < 8; j++) bias[j] = __ldg(b1img + o0 + j);
 #pragma unroll
-    for (int p = 0; p < WIDE_MAXP; p++) {
+    for (int p = 0; p < PMAX; p++) {
         mu[p] = (use_bn && p < d.P) ? bscal[BS_BN + 2 * p] : 0.f;
         rs[p] = (use_bn && p < d.P) ? bscal[BS_BN + 2 * p + 1] : 1.f;
 #pragma unroll
         for (int j = 0; j < 8; j++) w[p][j] = p < d.P ? __ldg(W1img + (size_t)p * d.H + o0 + j) : 0.f;
     }
-    for (int b = r0; b < r0 + FIRST_ROWS && b < B; b++) {
-        float z[8];
+    for (int b0 = r0; b0 < r0 + FIRST_ROWS && b0 < B; b0 += 4) {
+        float x[4][PMAX];
 #pragma unroll
-        for (int j = 0; j < 8; j++) z[j] = bias[j];
+        for (int i = 0; i < 4; i++)
 #pragma unroll
-        for (int p = 0; p < WIDE_MAXP; p++) {
-            if (p < d.P) {
-                const float x = (xb[(size_t)b * d.R4 + p] - mu[p]) * rs[p];
+            for (int p = 0; p < PMAX; p++)
+                x[i][p] = (b0 + i < B && p < d.P) ? (__ldg(xb + (size_t)(b0 + i) * d.R4 + p) - mu[p]) * rs[p] : 0.f;
 #pragma unroll
-                for (int j = 0; j < 8; j++) z[j] = fmaf(x, w[p][j], z[j]);
-            }
+        for (int i = 0; i < 4; i++) {
+            float z[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) z[j] = bias[j];
+#pragma unroll
+            for (int p = 0; p < PMAX; p++)
+#pragma unroll
+                for (int j = 0; j < 8; j++) z[j] = fmaf(x[i][p], w[p][j], z[j]);
+            uint4 o;
+            o.x = pack2(act_bf16(act, z[0]), act_bf16(act, z[1]));
+            o.y = pack2(act_bf16(act, z[2]), act_bf16(act, z[3]));
+            o.z = pack2(act_bf16(act, z[4]), act_bf16(act, z[5]));
+            o.w = pack2(act_bf16(act, z[6]), act_bf16(act, z[7]));
+            if (b0 + i < B) *reinterpret_cast<uint4*>(A1 + (size_t)(b0 + i) * d.H + o0) = o;
         }
-        uint4 o;
-        o.x = pack2(act_bf16(act, z[0]), act_bf16(act, z[1]));
-        o.y = pack2(act_bf16(act, z[2]), act_bf16(act, z[3]));
-        o.z = pack2(act_bf16(act, z[4]), act_bf16(act, z[5]));
-        o.w = pack2(act_bf16(act, z[6]), act_bf16(act, z[7]));
-        *reinterpret_cast<uint4*>(A1 + (size_t)b * d.H + o0) = o;
     }
 }
 
@@ -143,7 +153,7 @@ struct HeadArgs {
 // ---- output layer + physics + loss seeds + backward into D_NH; one warp per sample row, 8 warps per CTA ----
 // H / 256 chunks of 8 consecutive features per lane (16-byte bf16 accesses).
 template <class HC, int HCH>
-__global__ void __launch_bounds__(256) k_wide_head(const HeadArgs a)
+__global__ void __launch_bounds__(256, 2) k_wide_head(const HeadArgs a)
 {
     using PM = typename HC::PM;
     constexpr int NOUT = HC::NOUT, T = HC::T, F = HC::F, NPS = HC::NPS;
@@ -189,7 +199,10 @@ __global__ void __launch_bounds__(256) k_wide_head(const HeadArgs a)
     for (int o = 0; o < NOUT; o++) bout[o] = a.BOimg[o];
 
     float gW[NOUT][HCH][8], gB[NOUT], gDb[HCH][8], lsum[MAXT], gphi[MAXPS];
-    double est[T][8];
+    // eval mode: sufficient statistics per warp, kept in shared memory (32 registers the training loop needs for its row prefetch)
+    __shared__ double s_e[8][MAXT * 8];
+    if (lane == 0)
+        for (int i = 0; i < MAXT * 8; i++) s_e[warp][i] = 0.0;
 #pragma unroll
     for (int o = 0; o < NOUT; o++) {
         gB[o] = 0.f;
@@ -206,20 +219,33 @@ __global__ void __launch_bounds__(256) k_wide_head(const HeadArgs a)
     for (int t = 0; t < MAXT; t++) lsum[t] = 0.f;
 #pragma unroll
     for (int q = 0; q < MAXPS; q++) gphi[q] = 0.f;
-#pragma unroll
-    for (int t = 0; t < T; t++)
-#pragma unroll
-        for (int q = 0; q < 8; q++) est[t][q] = 0.0;
 
-    for (int b = blockIdx.x * 8 + warp; b < (a.train ? a.B : a.Bvalid); b += gridDim.x * 8) {
+    // the activations of a warp's NEXT row travel in registers while the current row is worked on (its chain of
+    // dependent steps -- dot product, warp sum, process model, delta -- would otherwise wait for HBM once per row)
+    const int bend = a.train ? a.B : a.Bvalid, bstep = gridDim.x * 8;
+    uint4 nxt[HCH];
+    {
+        const int b1 = blockIdx.x * 8 + warp;
+#pragma unroll
+        for (int c = 0; c < HCH; c++)
+            nxt[c] = b1 < bend ? __ldg(reinterpret_cast<const uint4*>(a.A + (size_t)b1 * H + (c * 32 + lane) * 8)) : make_uint4(0, 0, 0, 0);
+    }
+    for (int b = blockIdx.x * 8 + warp; b < bend; b += bstep) {
         const bool rowvalid = b < a.Bvalid;   // rows beyond: padding of the batch up to a multiple of 128 (train mode)
         float av[HCH][8];
         float zo[NOUT];
 #pragma unroll
         for (int o = 0; o < NOUT; o++) zo[o] = 0.f;
+        uint4 cur[HCH];
+#pragma unroll
+        for (int c = 0; c < HCH; c++) cur[c] = nxt[c];
+        if (b + bstep < bend) {
+#pragma unroll
+            for (int c = 0; c < HCH; c++) nxt[c] = __ldg(reinterpret_cast<const uint4*>(a.A + (size_t)(b + bstep) * H + (c * 32 + lane) * 8));
+        }
 #pragma unroll
         for (int c = 0; c < HCH; c++) {
-            const uint4 raw = *reinterpret_cast<const uint4*>(a.A + (size_t)b * H + (c * 32 + lane) * 8);
+            const uint4 raw = cur[c];
             const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
             for (int e = 0; e < 4; e++) {
@@ -251,8 +277,9 @@ __global__ void __launch_bounds__(256) k_wide_head(const HeadArgs a)
                     if (a.yhat && t < nt) a.yhat[(size_t)t * a.ldy + a.row0 + b] = yh[t];
                     if (y[t] == y[t]) {
                         const double yy = (double)y[t] - a.shift_y[t], hh = (double)yh[t] - a.shift_y[t], rr = (double)yh[t] - y[t];
-                        est[t][0] += 1.0; est[t][1] += yy; est[t][2] += hh; est[t][3] += yy * yy;
-                        est[t][4] += hh * hh; est[t][5] += yy * hh; est[t][6] += rr * rr; est[t][7] += fabs(rr);
+                        double* e8 = &s_e[warp][t * 8];
+                        e8[0] += 1.0; e8[1] += yy; e8[2] += hh; e8[3] += yy * yy;
+                        e8[4] += hh * hh; e8[5] += yy * hh; e8[6] += rr * rr; e8[7] += fabs(rr);
                     }
                 }
                 if (a.parout) {
@@ -318,10 +345,6 @@ __global__ void __launch_bounds__(256) k_wide_head(const HeadArgs a)
 
     if (!a.train) {
         if (a.evalstat) {
-            __shared__ double s_e[8][MAXT * 8];
-            if (lane == 0)
-                for (int t = 0; t < T; t++)
-                    for (int q = 0; q < 8; q++) s_e[warp][t * 8 + q] = est[t][q];
             __syncthreads();
             if (threadIdx.x < nt * 8) {
                 double s = 0.0;
