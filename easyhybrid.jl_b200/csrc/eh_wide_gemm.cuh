@@ -17,6 +17,7 @@
 // operands: they are fetched as MN-major tiles (64 columns x 64 batch rows per TMA box), so neither
 // activations nor deltas are ever transposed in memory.
 #pragma once
+#include <type_traits>
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -631,42 +632,53 @@ k_wide_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(ab));
             // BWD: column sums over this warp's 32 rows, straight from the staged strip (lane l owns columns NCC l .. NCC l + NCC - 1)
+            // (the input-weighted sums exist for the layer-1 call only; the loop is specialised on their count -- unrolled over
+            // WIDE_MAXP with a run-time bound it cost 1 000 mostly predicated-off instructions per tile and warp)
             float cs[NCC], cw[WIDE_MAXP][NCC];
             const bool want_cs = MODE == GEMM_BWD && g.colsum != nullptr;
             if (want_cs) {
-                float xr[WIDE_MAXP] = {0.f};
 #pragma unroll
                 for (int k = 0; k < NCC; k++) cs[k] = 0.f;
 #pragma unroll
-                for (int p = 0; p < WIDE_MAXP; p++) {
+                for (int p = 0; p < WIDE_MAXP; p++)
 #pragma unroll
                     for (int k = 0; k < NCC; k++) cw[p][k] = 0.f;
-                    if (p < g.P1) {
-                        float x = g.xb[(size_t)row * g.R4 + p];
-                        if (g.use_bn) x = (x - g.bscal[BS_BN_OFF + 2 * p]) * g.bscal[BS_BN_OFF + 2 * p + 1];
-                        xr[p] = x;
-                    }
-                }
+                auto colsums = [&](auto pn_c) {
+                    constexpr int PN = decltype(pn_c)::value;
+                    float xr[PN > 0 ? PN : 1];
 #pragma unroll
-                for (int r2 = 0; r2 < 32; r2++) {
-                    float f[NCC];
-#pragma unroll
-                    for (int k = 0; k < NCC; k += 2) {
-                        const uint32_t v = *reinterpret_cast<const uint32_t*>(stg + r2 * PG_OPITCH + lane * (2 * NCC) + 2 * k);
-                        const float2 ff = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v));
-                        f[k] = ff.x; f[k + 1] = ff.y;
-                    }
-#pragma unroll
-                    for (int k = 0; k < NCC; k++) cs[k] += f[k];
-#pragma unroll
-                    for (int p = 0; p < WIDE_MAXP; p++) {
+                    for (int p = 0; p < PN; p++) {
+                        xr[p] = 0.f;
                         if (p < g.P1) {
+                            float x = g.xb[(size_t)row * g.R4 + p];
+                            if (g.use_bn) x = (x - g.bscal[BS_BN_OFF + 2 * p]) * g.bscal[BS_BN_OFF + 2 * p + 1];
+                            xr[p] = x;
+                        }
+                    }
+#pragma unroll 8
+                    for (int r2 = 0; r2 < 32; r2++) {
+                        float f[NCC];
+#pragma unroll
+                        for (int k = 0; k < NCC; k += 2) {
+                            const uint32_t v = *reinterpret_cast<const uint32_t*>(stg + r2 * PG_OPITCH + lane * (2 * NCC) + 2 * k);
+                            const float2 ff = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v));
+                            f[k] = ff.x; f[k + 1] = ff.y;
+                        }
+#pragma unroll
+                        for (int k = 0; k < NCC; k++) cs[k] += f[k];
+#pragma unroll
+                        for (int p = 0; p < PN; p++) {
                             const float x = __shfl_sync(0xffffffffu, xr[p], r2);
 #pragma unroll
                             for (int k = 0; k < NCC; k++) cw[p][k] = fmaf(f[k], x, cw[p][k]);
                         }
                     }
-                }
+                };
+                if (g.P1 == 0) colsums(std::integral_constant<int, 0>{});
+                else if (g.P1 == 1) colsums(std::integral_constant<int, 1>{});
+                else if (g.P1 == 2) colsums(std::integral_constant<int, 2>{});
+                else if (g.P1 <= 4) colsums(std::integral_constant<int, 4>{});
+                else colsums(std::integral_constant<int, WIDE_MAXP>{});
             }
             __syncwarp();
             // CW bf16 per row = LPR lanes of 16 bytes: RPI rows per instruction
