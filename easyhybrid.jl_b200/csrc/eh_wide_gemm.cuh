@@ -417,7 +417,7 @@ constexpr int PG_CW = PG_BN / (PG_EPI_WARPS / 4);              // output columns
 constexpr int PG_STAGE_BYTES = (BM + PG_BN) * BK * 2;          // 48 KB
 constexpr int PG_OPITCH = PG_CW * 2 + 16;                      // staged row of one epilogue warp: PG_CW bf16 + pad
 constexpr int PG_STG_BYTES = PG_EPI_WARPS * 32 * PG_OPITCH;    // 73 728
-constexpr int PG_SIDE_BYTES = 2 * PG_BN * 4;                   // bias double buffer
+constexpr int PG_SIDE_BYTES = PG_EPI_WARPS * PG_CW * 4;         // bias values, one private copy per epilogue warp
 constexpr int PG_SMEM = PG_STAGES * PG_STAGE_BYTES + PG_STG_BYTES + PG_SIDE_BYTES + 1024 + 256;
 static_assert(PG_SMEM <= 232448, "persistent GEMM: shared memory");
 
@@ -472,7 +472,7 @@ k_wide_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     auto tempty_bar = [&](int b) { return bar0 + 8u * (2 * STAGES + 2 + b); };
     const uint32_t tmem_slot = bar0 + 8u * (2 * STAGES + 4);
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + BAR_OFF + 8 * (2 * STAGES + 4));
-    float* s_bias = reinterpret_cast<float*>(gen_base + SIDE_OFF);                 // [2][BN]
+    float* s_bias = reinterpret_cast<float*>(gen_base + SIDE_OFF);                 // [epilogue warp][PG_CW]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_n = g.N / BN;
@@ -564,7 +564,6 @@ k_wide_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         constexpr int LPR = CW / 8, RPI = 32 / LPR;        // 16-byte lanes per staged row, rows per warp-wide instruction
         constexpr int NAUX = 32 / RPI;                     // 16-byte pieces of the activation strip per thread
         const int q = warp & 3, h = (warp - 2) >> 2;
-        const int et = (warp - 2) * 32 + lane;            // 0.. among the epilogue threads
         uint8_t* stg = gen_base + STG_OFF + (warp - 2) * (32 * PG_OPITCH);
         const int prow = lane / LPR, pc16 = lane % LPR;    // this lane's place in the coalesced strip walk
         // BWD: the activation strip (32 rows x CW columns of A_{l-1}) of the NEXT tile travels in registers while this
@@ -583,10 +582,12 @@ k_wide_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             const int m0 = unit_m0(u), n0 = unit_n0(u);
             const int row = m0 + q * 32 + lane;
             const int ncol0 = n0 + h * CW;                // first output column of this warp
-            float* bias = s_bias + ab * BN;
+            float* bias = s_bias + (warp - 2) * CW;      // this warp's own copy: no CTA-wide barrier per tile
             if (MODE == GEMM_FWD) {
-                if (et < BN) bias[et] = __ldg(g.bias + n0 + et);
-                asm volatile("bar.sync 1, %0;" ::"n"(PG_EPI_THREADS) : "memory");
+                __syncwarp();
+#pragma unroll
+                for (int k = 0; k < CW / 32; k++) bias[k * 32 + lane] = __ldg(g.bias + ncol0 + k * 32 + lane);
+                __syncwarp();
             } else {
 #pragma unroll
                 for (int i = 0; i < NAUX; i++) *reinterpret_cast<uint4*>(stg + (i * RPI + prow) * PG_OPITCH + pc16 * 16) = apre[i];
@@ -602,7 +603,7 @@ k_wide_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                 tc_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN + h * CW + c), r);
                 uint32_t o[16];
                 if (MODE == GEMM_FWD) {
-                    const float4* b4 = reinterpret_cast<const float4*>(bias + h * CW + c);
+                    const float4* b4 = reinterpret_cast<const float4*>(bias + c);
 #pragma unroll
                     for (int j = 0; j < 8; j++) {
                         const float4 b = b4[j];
@@ -701,20 +702,21 @@ k_wide_gemm_p(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 #pragma unroll
                         for (int k = 0; k < NCC; k++) mine[(1 + p) * CW + lane * NCC + k] = cw[p][k];
                     }
-                asm volatile("bar.sync 1, %0;" ::"n"(PG_EPI_THREADS) : "memory");
-                if (et < BN) {
-                    const int h2 = et / CW, cl = et % CW;   // thread et owns output column et of the tile
+                // (only the four warps of this column slice meet: named barrier 2 + h, 128 threads)
+                asm volatile("bar.sync %0, 128;" ::"r"(2 + h) : "memory");
+                const int ti = ((warp - 2) & 3) * 32 + lane;   // 0..127 among the warps of the slice
+                if (ti < CW) {
                     for (int p = 0; p <= g.P1; p++) {
                         float v = 0.f;
 #pragma unroll
                         for (int qq = 0; qq < 4; qq++) {
-                            const int wi = 4 * h2 + ((qq + 2) & 3);   // epilogue warp with lane quarter qq and column slice h2
-                            v += reinterpret_cast<const float*>(gen_base + STG_OFF + wi * (32 * PG_OPITCH))[p * CW + cl];
+                            const int wi = 4 * h + ((qq + 2) & 3);   // epilogue warp with lane quarter qq of this column slice
+                            v += reinterpret_cast<const float*>(gen_base + STG_OFF + wi * (32 * PG_OPITCH))[p * CW + ti];
                         }
-                        g.colsum[((size_t)(m0 / BM) * (1 + g.P1) + p) * g.N + n0 + et] = v;
+                        g.colsum[((size_t)(m0 / BM) * (1 + g.P1) + p) * g.N + n0 + h * CW + ti] = v;
                     }
                 }
-                asm volatile("bar.sync 1, %0;" ::"n"(PG_EPI_THREADS) : "memory");   // the strips are rewritten by the next tile
+                asm volatile("bar.sync %0, 128;" ::"r"(2 + h) : "memory");   // the strips are rewritten by the next tile
             }
             __syncwarp();   // the strip is rewritten by the next tile
         }
