@@ -443,13 +443,26 @@ __global__ void __launch_bounds__(256) k_wide_gradfin(const FinArgs a)
 {
     const int H = a.d.H, NOUT = a.d.NOUT, NH = a.d.NH, P = a.d.P;
     const int HP = head_npart(H, NOUT);
+    // loss sums of the head CTAs: all 256 threads fetch (one 16-byte load per head CTA), fixed combination order
     __shared__ float s_loss[MAXT];
-    if (threadIdx.x < 32) {
-        for (int t = 0; t < MAXT; t++) {
-            float s = 0.f;
-            for (int g = threadIdx.x; g < a.n_head; g += 32) s += a.head_partial[(size_t)g * HP + head_off_loss(H, NOUT) + t];
-            s = warp_sum(s);
-            if (threadIdx.x == 0) s_loss[t] = s;
+    __shared__ float s_lw[8][MAXT];
+    {
+        static_assert(MAXT == 4, "one float4 of loss sums per head CTA");
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int g = threadIdx.x; g < a.n_head; g += 256) {
+            const float4 v = *reinterpret_cast<const float4*>(a.head_partial + (size_t)g * HP + head_off_loss(H, NOUT));
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        acc.x = warp_sum(acc.x); acc.y = warp_sum(acc.y); acc.z = warp_sum(acc.z); acc.w = warp_sum(acc.w);
+        if ((threadIdx.x & 31) == 0) {
+            float* d4 = s_lw[threadIdx.x >> 5];
+            d4[0] = acc.x; d4[1] = acc.y; d4[2] = acc.z; d4[3] = acc.w;
+        }
+        __syncthreads();
+        if (threadIdx.x < MAXT) {
+            float t8 = 0.f;
+            for (int wv = 0; wv < 8; wv++) t8 += s_lw[wv][threadIdx.x];
+            s_loss[threadIdx.x] = t8;
         }
     }
     __syncthreads();
@@ -497,7 +510,19 @@ __global__ void __launch_bounds__(256) k_wide_gradfin(const FinArgs a)
         }
     }
     float s = 0.f;
-    for (int z = zl; z < cnt; z += 8) s += src[(size_t)z * stride];
+    {
+        // four independent loads in flight per thread (the partial vectors are L2-resident: latency, not bandwidth)
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int z = zl;
+        for (; z + 24 < cnt; z += 32) {
+            s0 += src[(size_t)z * stride];
+            s1 += src[(size_t)(z + 8) * stride];
+            s2 += src[(size_t)(z + 16) * stride];
+            s3 += src[(size_t)(z + 24) * stride];
+        }
+        for (; z < cnt; z += 8) s0 += src[(size_t)z * stride];
+        s = (s0 + s1) + (s2 + s3);
+    }
     s += __shfl_xor_sync(0xffffffffu, s, 4);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
     s += __shfl_xor_sync(0xffffffffu, s, 1);
