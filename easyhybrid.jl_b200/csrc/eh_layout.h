@@ -1,5 +1,5 @@
 // eh_layout.h -- compile-time shape math shared by the fused step kernel (device)
-// and the host planner (eh_plan.cpp).  No includes, NVRTC-clean.
+// and the host planner (eh_plan.cu).  No includes, NVRTC-clean.
 //
 // A "shape" is one Dense chain  P -> H -> ... -> H -> NOUT  with NH hidden
 // layers, every hidden width padded up to H (multiple of 4) with zero weights.

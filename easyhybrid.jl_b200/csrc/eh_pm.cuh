@@ -36,7 +36,7 @@ struct PmCtx {
     const PmProgData* prog;    // traced program (PmProgram only)
     int scale_rt;              // PmProgram only: scale_nn_outputs as a run-time flag (one compiled variant serves both)
     unsigned pass[3];          // PmProgram only: bit j of pass[l-1] = unit j of hidden layer l is a pass-through unit (identity
-                               // activation) -- the tail of a chain shallower than the embedded depth (MultiNN, eh_lib.cu planner)
+                               // activation) -- the tail of a chain shallower than the embedded depth (MultiNN, eh_plan.cu)
     unsigned uniform_mask;     // bit s set: slot s is GLOBAL / FIXED (same value for all samples)
     // persistent kernel only: shared-memory word that carries the number of the last optimiser step whose global-parameter
     // scalars (slot values, pms) are in place; the warp that owns the global parameters publishes it, consumers wait for
