@@ -444,38 +444,56 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
     //    scale_nn_outputs is a run-time flag.  EH_NO_SMALL_PROGRAM=1 sends these models to the tensor-core path.
     std::vector<eh_pm_instr> prog;
     std::vector<int> prog_out;
-    bool use_prog = false;
+    bool use_prog = false, auto_jit = false;
+    PmProgData pd;
+    // run-time specialisation of the traced program (EH_FLAG_JIT, or EH_JIT=1 for every traced model; EH_JIT=0: never)
+    const char* env_jit = getenv("EH_JIT");
+    const bool want_jit = env_jit ? (env_jit[0] && env_jit[0] != '0') : (d->flags & EH_FLAG_JIT) != 0;
     if (!v && small_shape && !getenv("EH_NO_SMALL_PROGRAM") && d->n_params >= 1 && d->n_params <= MAXPS && d->n_forc <= PmProgram::NF &&
         d->n_targ <= PmProgram::NT) {
-        const Variant* vp = find_variant(EH_PM_PROGRAM, Pt, NHmax, rup4(hmax), Ot, ch.activation, 1, 0);
+        // (with run-time compilation the tightest shape that holds the model is taken -- inputs padded to 2 / 4 / 8 / 12,
+        // width 8 / 16 / 24 / 32, up to four chain outputs; the compiled-in variants know 2 / 4 / 8 inputs, width 16 / 32 and
+        // one or two outputs)
+        const Variant* vp = want_jit ? find_shape(Pt, NHmax, rup4(hmax), Ot, ch.activation)
+                                     : find_variant(EH_PM_PROGRAM, Pt, NHmax, rup4(hmax), Ot, ch.activation, 1, 0);
+        // a shape without a compiled-in variant is compiled at run time without being asked (unless EH_JIT=0): the
+        // alternative would be the bf16 path or a refusal
+        if (!vp && !want_jit && !env_jit) {
+            vp = find_shape(Pt, NHmax, rup4(hmax), Ot, ch.activation);
+            auto_jit = vp != nullptr;
+        }
         if (vp && vp->NPART <= UPD_MAX_NPART && builtin_as_program(d, is_prog, prog, prog_out)) { v = vp; use_prog = true; }
+        if (use_prog) {
+            memset(&pd, 0, sizeof pd);
+            pd.len = (int)prog.size(); pd.nt = d->n_targ; pd.nf = d->n_forc; pd.np = d->n_params;
+            for (int t = 0; t < d->n_targ; t++) pd.out[t] = prog_out[(size_t)t];
+            for (int i = 0; i < pd.len; i++) {
+                pd.op[i] = (short)prog[(size_t)i].op; pd.a[i] = (short)prog[(size_t)i].a; pd.b[i] = (short)prog[(size_t)i].b;
+                pd.imm[i] = prog[(size_t)i].imm;
+            }
+            if (want_jit || auto_jit) {
+                std::string jerr;
+                if (jit_compile(pd, *v, &c->jit_cubin, c->jit_names, &c->jit.name, &c->jit.from_cache, &c->jit.compile_seconds, &jerr)) {
+                    c->jit_on = true;
+                } else if (want_jit) {
+                    return fail(c, EH_EUNSUPPORTED, "run-time specialisation of the traced process model failed: %s", jerr.c_str());
+                } else {
+                    v = nullptr; use_prog = false;   // no NVRTC on this machine: the model takes whatever path is left
+                }
+            }
+        }
     }
     if (!v && !same_depth)
         return fail(c, EH_EUNSUPPORTED, "chains of different depth run on the exact-fp32 generic kernels only: <= 3 hidden layers, "
-                                        "summed width <= 32 per layer, <= 8 chain inputs, <= 2 chain outputs");
+                                        "summed width <= 32 per layer, <= 12 chain inputs, <= 4 chain outputs");
     if (!v) return build_plan_wide(c, d, is_prog);
     if (!use_prog && v->T != d->n_targ) return fail(c, EH_EINVAL, "process model yields %d targets, descriptor has %d", v->T, d->n_targ);
     c->var = v;
     c->small_prog = use_prog;
     c->scale_rt = scale_flag;
-    if (use_prog) {
-        PmProgData& pd = c->h_prog;
-        memset(&pd, 0, sizeof pd);
-        pd.len = (int)prog.size(); pd.nt = d->n_targ; pd.nf = d->n_forc; pd.np = d->n_params;
-        for (int t = 0; t < d->n_targ; t++) pd.out[t] = prog_out[(size_t)t];
-        for (int i = 0; i < pd.len; i++) {
-            pd.op[i] = (short)prog[(size_t)i].op; pd.a[i] = (short)prog[(size_t)i].a; pd.b[i] = (short)prog[(size_t)i].b;
-            pd.imm[i] = prog[(size_t)i].imm;
-        }
-    }
-    // run-time specialisation of the traced program (EH_FLAG_JIT, or EH_JIT=1 for every traced model; EH_JIT=0: never)
+    if (use_prog) c->h_prog = pd;
     {
-        const char* ej = getenv("EH_JIT");
-        const bool want = use_prog && (ej ? (ej[0] && ej[0] != '0') : (d->flags & EH_FLAG_JIT) != 0);
-        if (want) {
-            std::string jerr;
-            if (!jit_compile(c->h_prog, *v, &c->jit_cubin, c->jit_names, &c->jit.name, &c->jit.from_cache, &c->jit.compile_seconds, &jerr))
-                return fail(c, EH_EUNSUPPORTED, "run-time specialisation of the traced process model failed: %s", jerr.c_str());
+        if (c->jit_on) {
             c->jit_var = *v;
             c->jit_var.name = c->jit.name.c_str();
             c->jit_var.prepare = nullptr; c->jit_var.launch_step = nullptr; c->jit_var.launch_eval = nullptr;

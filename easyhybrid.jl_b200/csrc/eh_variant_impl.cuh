@@ -92,6 +92,27 @@ static Variant make_variant(const char* name)
     return v;
 }
 
+// layout descriptor of a shape WITHOUT compiled-in kernels: what the planner and the launch geometry need to know about a
+// generic variant that only exists once eh_jit.cu has compiled it (run-time specialisation, EH_FLAG_JIT)
+template <class E>
+static Variant make_shape(const char* name)
+{
+    using C = typename E::Cfg;
+    Variant v{};
+    v.pm = C::PM::ID; v.P = C::P; v.NH = C::NH; v.H = C::H; v.NOUT = C::NOUT; v.act = C::ACT; v.scale = C::SCALE ? 1 : 0;
+    v.engine = E::ENGINE;
+    v.chunk = E::CHUNK;
+    v.dims = C::D;
+    v.F = C::F; v.T = C::T; v.NPS = C::NPS; v.R4 = C::R4; v.NW = C::NW;
+    v.NPART = E::NPART;
+    v.off_stats = E::OFF_STATS;
+    v.stage_floats = E::STAGE_FLOATS;
+    v.max_warps = E::MAX_WARPS;
+    v.wpc = 1; v.eng_bytes = 0;
+    v.name = name;
+    return v;
+}
+
 // tensor engine: persistent kernel only (single steps, eval and small batches stay on the FFMA2 variant of the same shape)
 template <class E>
 static cudaError_t prepare_epoch_only_t(size_t step_smem, size_t)

@@ -29,6 +29,10 @@ struct Variant {
 };
 
 const Variant* find_variant(int pm, int P, int NH, int H, int NOUT, int act, int scale, int engine);
+// generic (PmProgram-layout) shapes that exist as descriptors only -- their kernels are compiled at run time (eh_jit.cu):
+// chain inputs padded to 2 / 4 / 8 / 12, one to three hidden layers of width 8 / 16 / 24 / 32, one to four chain outputs,
+// any activation.  The tightest shape that holds (P, H); NULL if none does.
+const Variant* find_shape(int P, int NH, int H, int NOUT, int act);
 int num_variants();
 const Variant* variant_at(int i);
 

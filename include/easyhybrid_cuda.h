@@ -205,7 +205,9 @@ typedef struct {
 #define EH_FLAG_JIT 32u       /* traced process model (EH_PM_PROGRAM) on the exact-fp32 path: compile the program into the
                                   kernels at eh_create (NVRTC, a few seconds, cached on disk under $EH_JIT_CACHE or
                                   ~/.cache/easyhybrid_b200) instead of interpreting it per sample.  eh_create fails with
-                                  EH_EUNSUPPORTED if NVRTC is not available; models that take another path ignore it */
+                                  EH_EUNSUPPORTED if NVRTC is not available; models that take another path ignore it.
+                                  Shapes without a compiled-in generic variant -- 9..12 chain inputs, 3 or 4 chain outputs
+                                  -- are compiled this way WITHOUT the flag (EH_JIT=0 in the environment forbids it) */
 
 enum { EH_SPLIT_TRAIN = 0, EH_SPLIT_VAL = 1 };
 

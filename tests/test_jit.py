@@ -48,11 +48,54 @@ def test_models_off_the_generic_path_are_refused(eh, tmp_path, monkeypatch):
     assert st != 0 and "did not choose a generic" in err, (st, info, err)
 
 
+def three_param_pm(*, ta, dsw_pot, rb, Q10, alpha, tref=15.0):
+    return {"reco": rb * Q10 ** (0.1 * (ta - tref)) + alpha * np.tanh(0.05 * dsw_pot)}
+
+
+def m_three_neural(eh):
+    # three neural parameters out of ONE chain (SingleNNHybridModel, GenericHybridModel.jl:89-157) of widths 24 / 20: three
+    # chain outputs and width 24 exist as run-time compiled shapes only
+    return eh.constructHybridModel(["sw_pot", "dsw_pot", "ta"], ["ta", "dsw_pot"], ["reco"], three_param_pm,
+                                   dict(rb=(3.0, 0.0, 13.0), Q10=(2.0, 1.0, 4.0), alpha=(0.5, -2.0, 2.0)), ["rb", "Q10", "alpha"], [],
+                                   hidden_layers=[24, 20], activation="tanh", scale_nn_outputs=True, input_batchnorm=True)
+
+
+def _table_wide(n, seed=9):
+    t = gg._table(n)
+    rng = np.random.default_rng(seed)
+    for k in range(7):
+        t["z%d" % k] = rng.standard_normal(n).astype(np.float32)
+    return t
+
+
+def m_ten_inputs(eh):
+    # ten predictors: inputs padded to 12 (the compiled-in variants stop at 8)
+    return eh.constructHybridModel(["sw_pot", "dsw_pot", "ta"] + ["z%d" % k for k in range(7)], ["ta", "dsw_pot"], ["reco"], gg.custom_pm,
+                                   dict(rb=(3.0, 0.0, 13.0), Q10=(2.0, 1.0, 4.0), alpha=(0.5, -2.0, 2.0)), ["rb"], ["Q10", "alpha"],
+                                   hidden_layers=[16], activation="sigmoid", scale_nn_outputs=True, input_batchnorm=True)
+
+
+def test_shapes_beyond_the_compiled_in_variants(eh, tmp_path, monkeypatch):
+    """three chain outputs / width 24 / ten inputs: EH_EUNSUPPORTED-or-bf16 without run-time compilation, exact fp32 with it"""
+    monkeypatch.setenv("EH_JIT_CACHE", str(tmp_path))
+    st, info, err = _check(eh, m_three_neural(eh), training_loss="mse", agg="sum")
+    assert st == 0 and "/P4/NH2/H24/O3/ACT_TANH" in info, (info, err)
+    st, info, err = _check(eh, m_ten_inputs(eh), training_loss="mse", agg="sum")
+    assert st == 0 and "/P12/NH1/H16/O1/ACT_SIGMOID" in info, (info, err)
+    # the tightest shape is taken where a compiled-in variant would pad: hidden 12 -> width 16 there, 12 -> 16 here too,
+    # but 8 -> 8 instead of 16
+    st, info, err = _check(eh, gg.m_custom(eh, hidden=(8, 8)), training_loss="mse", agg="sum")
+    assert st == 0 and "/P2/NH2/H8/O1/" in info, (info, err)
+
+
 JIT_CASES = [
     ("custom-tanh16", gg.m_custom, lambda: gg._table(3000, nan_frac=0.05), "mse", "sum"),
     ("custom-two-targets-bn", gg.m_two_targets, lambda: gg._table(2500, nan_frac=0.1, two=True), "PT", "mean"),
     ("traced-chains-depth-1-and-2-relu", gg.m_traced_unequal_depth, lambda: gg._table(2000), "mse", "mean"),
+    ("three-neural-parameters-width-24", m_three_neural, lambda: gg._table(2000, nan_frac=0.03), "mse", "sum"),
+    ("ten-inputs", m_ten_inputs, lambda: _table_wide(2000), "nseLoss", "sum"),
 ]
+JIT_ONLY = {"three-neural-parameters-width-24", "ten-inputs"}   # no compiled-in variant: nothing to compare the interpreter with
 
 
 @pytest.mark.gpu
@@ -67,22 +110,27 @@ def test_compiled_program_matches_checker_and_interpreter(eh, orc, name, mk, mkd
     flat += (0.05 * rng.standard_normal(flat.size)).astype(np.float32)
     o = orc.Oracle(model, training_loss=loss, agg=agg, opt=eh.Adam(0.01))
     sj = eh.FusedSession(model, training_loss=loss, agg=agg, opt=eh.Adam(0.01), jit=True)
-    si = eh.FusedSession(model, training_loss=loss, agg=agg, opt=eh.Adam(0.01))
     assert sj.kernel_variant().startswith("nvrtc/PmTraced#"), sj.kernel_variant()
-    assert si.kernel_variant().startswith("ffma2/PmProgram/"), si.kernel_variant()
+    si = None
+    if name not in JIT_ONLY:
+        si = eh.FusedSession(model, training_loss=loss, agg=agg, opt=eh.Adam(0.01))
+        assert si.kernel_variant().startswith("ffma2/PmProgram/"), si.kernel_variant()
     n = xf[0].shape[0]
     for s in (sj, si):
+        if s is None:
+            continue
         s.upload(0, xf, y)
         s.set_params(flat)
     for B in (n, 517, 12):
         idx = rng.permutation(n)[:B]
         L, g = sj.loss_grad(idx)
-        Li, gi = si.loss_grad(idx)
         L64, g64 = o.loss_grad(flat, xf, y, idx, precision=64)
         scale = np.abs(g64).max()
         assert abs(L - L64) <= 2e-6 * abs(L64), (name, B, L, L64)
         assert np.abs(g - g64).max() <= 1e-5 * scale, (name, B)
-        assert np.abs(g - gi).max() <= 2e-6 * scale and abs(L - Li) <= 1e-6 * abs(Li)   # same formulas, contraction aside
+        if si is not None:
+            Li, gi = si.loss_grad(idx)
+            assert np.abs(g - gi).max() <= 2e-6 * scale and abs(L - Li) <= 1e-6 * abs(Li)   # same formulas, contraction aside
     # persistent epoch kernel, single step, eval
     B = 256
     perm = np.concatenate([rng.permutation(n) for _ in range(3)])[: 20 * B]
@@ -90,7 +138,8 @@ def test_compiled_program_matches_checker_and_interpreter(eh, orc, name, mk, mkd
     ref = flat.copy()
     want = o.train_steps(ref, xf, y, perm, B)
     np.testing.assert_allclose(got, want, rtol=2e-4)
-    np.testing.assert_allclose(got, si.epoch(perm, B), rtol=2e-5)
+    if si is not None:
+        np.testing.assert_allclose(got, si.epoch(perm, B), rtol=2e-5)
     L1 = sj.step(perm[:B])
     Lo = o.train_steps(ref, xf, y, perm[:B], B)
     assert abs(L1 - Lo[0]) <= 2e-4 * abs(Lo[0])
@@ -99,7 +148,20 @@ def test_compiled_program_matches_checker_and_interpreter(eh, orc, name, mk, mkd
     want_y = o.forward(ps, xf, precision=64)
     assert np.allclose(yhat, want_y, rtol=2e-5, atol=2e-5)
     sj.close()
-    si.close()
+    if si is not None:
+        si.close()
+
+
+@pytest.mark.gpu
+def test_shapes_without_a_compiled_in_variant_compile_unasked(eh, monkeypatch):
+    """three chain outputs: no flag needed -- run-time compilation is the only exact-fp32 path; EH_JIT=0 forbids it and the
+    model is refused (the tensor-core path takes one or two chain outputs)"""
+    sess = eh.FusedSession(m_three_neural(eh))
+    assert sess.kernel_variant().startswith("nvrtc/PmTraced#") and "/O3/" in sess.kernel_variant(), sess.kernel_variant()
+    sess.close()
+    monkeypatch.setenv("EH_JIT", "0")
+    with pytest.raises(eh.EasyHybridCudaError):
+        eh.FusedSession(m_three_neural(eh))
 
 
 @pytest.mark.gpu

@@ -57,6 +57,13 @@ CASES += [
     ("two-chains-depth-3-and-1-swish-bn", lambda eh: gg.m_two_chains_unequal_depth(eh, "swish", True), lambda: make_synth(300), "nseLoss", "sum"),
     ("traced-chains-depth-1-and-2-relu", gg.m_traced_unequal_depth, lambda: gg._table(300), "mse", "mean"),
 ]
+# shapes the GPU only reaches with run-time compilation (tests/test_jit.py): three chain outputs, ten inputs
+import test_jit as tj  # noqa: E402
+
+CASES += [
+    ("three-neural-parameters-width-24", tj.m_three_neural, lambda: gg._table(300, nan_frac=0.03), "mse", "sum"),
+    ("ten-inputs", tj.m_ten_inputs, lambda: tj._table_wide(300), "nseLoss", "sum"),
+]
 
 
 @pytest.mark.parametrize("agg,branches,normalize", [("sum", None, True), ("mean", None, False), ("sum", ["Q10"], True)])
