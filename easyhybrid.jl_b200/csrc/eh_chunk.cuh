@@ -106,6 +106,36 @@ __device__ __forceinline__ void stage_get(const float* row, int lane, float (&v)
     }
 }
 
+// activation of the unit pair (j2, j2 + 1) of hidden layer l: the chain's activation, or -- run-time compiled models whose
+// chains differ in activation (MultiNNHybridModel with an activation per parameter, GenericHybridModel.jl:168-174) -- the
+// one the generated functor names for each unit.  l and j2 are constants after unrolling, so nothing is selected at run time.
+template <class C>
+__device__ __forceinline__ float2 unit_act_fwd2(int l, int j2, float2 z, float2& aux)
+{
+    if constexpr (C::PM::UNIT_ACT) {
+        const int cx = C::PM::unit_act(l, j2), cy = C::PM::unit_act(l, j2 + 1);
+        float2 ax = f2s(0.f), ay = f2s(0.f);
+        const float2 rx = act_fwd2_rt(cx, z, ax);
+        const float2 ry = (cy == cx) ? rx : act_fwd2_rt(cy, z, ay);
+        aux = f2(ax.x, cy == cx ? ax.y : ay.y);
+        return f2(rx.x, ry.y);
+    } else {
+        return act_fwd2<C::ACT>(z, aux);
+    }
+}
+template <class C>
+__device__ __forceinline__ float2 unit_act_bwd2(int l, int j2, float2 a, float2 aux)
+{
+    if constexpr (C::PM::UNIT_ACT) {
+        const int cx = C::PM::unit_act(l, j2), cy = C::PM::unit_act(l, j2 + 1);
+        const float2 rx = act_bwd2_rt(cx, a, aux);
+        const float2 ry = (cy == cx) ? rx : act_bwd2_rt(cy, a, aux);
+        return f2(rx.x, ry.y);
+    } else {
+        return act_bwd2<C::ACT>(a, aux);
+    }
+}
+
 // Dense chain forward for the sample of this lane (prepare_hidden_chain,
 // src/models/NNModels.jl:225-230).  hp holds neuron PAIRS; returns a_NH in hp, outputs in zo.
 template <class C, bool STAGE>
@@ -141,7 +171,7 @@ __device__ __forceinline__ void chain_forward(const float* sW, float* stage, int
         for (int j = 0; j < HP; j++) {
             float2 aux = f2s(0.f);
             const float2 z = hp[j];
-            hp[j] = act_fwd2<C::ACT>(hp[j], aux);
+            hp[j] = unit_act_fwd2<C>(l, 2 * j, hp[j], aux);
             if (C::PM::DYNAMIC && pass) {
                 const unsigned m = pass[l - 1] >> (2 * j);
                 if (m & 1u) hp[j].x = z.x;
@@ -393,7 +423,7 @@ __device__ __forceinline__ void chunk_sample_phase(const float (*rec)[C::R4], co
             for (int s = 0; s < S; s++) {
                 float2 aux = f2s(0.f);
                 const float2 z = hp[s][j];
-                hp[s][j] = act_fwd2<C::ACT>(hp[s][j], aux);
+                hp[s][j] = unit_act_fwd2<C>(l, 2 * j, hp[s][j], aux);
                 if (C::PM::DYNAMIC) {   // pass-through units of a shallower chain keep z
                     const unsigned m = cx.pass[l - 1] >> (2 * j);
                     if (m & 1u) hp[s][j].x = z.x;
@@ -569,7 +599,7 @@ __device__ __forceinline__ void chunk_sample_phase(const float (*rec)[C::R4], co
             for (int s = 0; s < S; s++) {
                 float2 al = (l < NH) ? f2(alo[s], ahi[s]) : hp[s][k];
                 float2 aux = (C::ACT == ACT_SWISH) ? f2(xlo[s], xhi[s]) : f2s(0.f);
-                float2 ga = act_bwd2<C::ACT>(al, aux);
+                float2 ga = unit_act_bwd2<C>(l, 2 * k, al, aux);
                 if (C::PM::DYNAMIC) {
                     const unsigned m = cx.pass[l - 1] >> (2 * k);
                     if (m & 1u) ga.x = 1.f;

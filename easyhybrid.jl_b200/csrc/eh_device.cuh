@@ -105,6 +105,29 @@ __device__ __forceinline__ float2 act_bwd2(float2 a, float2 aux)
     return f2s(1.f);
 }
 
+// the same with the activation as a value: for call sites where it is a compile-time constant only after unrolling (the
+// per-unit activations of run-time compiled models whose chains differ in activation); the switch folds away
+__device__ __forceinline__ float2 act_fwd2_rt(int act, float2 z, float2& aux)
+{
+    switch (act) {
+    case ACT_TANH: return act_fwd2<ACT_TANH>(z, aux);
+    case ACT_SIGMOID: return act_fwd2<ACT_SIGMOID>(z, aux);
+    case ACT_RELU: return act_fwd2<ACT_RELU>(z, aux);
+    case ACT_SWISH: return act_fwd2<ACT_SWISH>(z, aux);
+    default: return z;
+    }
+}
+__device__ __forceinline__ float2 act_bwd2_rt(int act, float2 a, float2 aux)
+{
+    switch (act) {
+    case ACT_TANH: return act_bwd2<ACT_TANH>(a, aux);
+    case ACT_SIGMOID: return act_bwd2<ACT_SIGMOID>(a, aux);
+    case ACT_RELU: return act_bwd2<ACT_RELU>(a, aux);
+    case ACT_SWISH: return act_bwd2<ACT_SWISH>(a, aux);
+    default: return f2s(1.f);
+    }
+}
+
 __device__ __forceinline__ float warp_sum(float v)
 {
 #pragma unroll

@@ -230,7 +230,7 @@ void cache_write(const std::string& dir, const std::string& path, const std::str
 
 }  // namespace
 
-std::string jit_source(const PmProgData& pd, const Variant& shape)
+std::string jit_source(const PmProgData& pd, const Variant& shape, const unsigned char* unit_act)
 {
     std::string s;
     s += "// generated by eh_jit.cu: traced process model, " + std::to_string(pd.len) + " instructions\n";
@@ -238,6 +238,29 @@ std::string jit_source(const PmProgData& pd, const Variant& shape)
     s += "struct PmTraced {\n";
     s += "    static constexpr int ID = PM_PROGRAM, NPS = PmProgram::NPS, NF = PmProgram::NF, NT = PmProgram::NT;\n";
     s += "    static constexpr bool DYNAMIC = true;\n";
+    if (!unit_act) {
+        s += "    static constexpr bool UNIT_ACT = false;\n";
+    } else {
+        // activation of unit j of hidden layer l as a chain of comparisons over runs of equal codes: plain arithmetic on
+        // what are constants after unrolling
+        s += "    static constexpr bool UNIT_ACT = true;\n";
+        s += "    __device__ __forceinline__ static constexpr int unit_act(int l, int j)\n    {\n";
+        for (int l = 1; l <= 3; l++) {
+            s += "        if (l == " + std::to_string(l) + ") return ";
+            const unsigned char* row = unit_act + (l - 1) * 32;
+            std::string e;
+            int j = 0;
+            while (j < 32) {
+                int k = j;
+                while (k < 32 && row[k] == row[j]) k++;
+                if (k < 32) e += "j < " + std::to_string(k) + " ? " + std::to_string((int)row[j]) + " : ";
+                else e += std::to_string((int)row[j]);
+                j = k;
+            }
+            s += e + ";\n";
+        }
+        s += "        return 0;\n    }\n";
+    }
     s += "    static constexpr int NSV = " + std::to_string(pd.len > 0 ? pd.len : 1) + ";\n";
     s += "    __device__ __forceinline__ static void fwd(const float* p, const float* f, const PmCtx&, float* y, float* sv)\n    {\n";
     for (int i = 0; i < pd.len; i++) s += fwd_stmt(pd, i);
@@ -264,8 +287,8 @@ std::string jit_source(const PmProgData& pd, const Variant& shape)
     return s;
 }
 
-bool jit_compile(const PmProgData& pd, const Variant& shape, std::string* cubin, std::string names[3], std::string* tag,
-                 bool* from_cache, double* seconds, std::string* err)
+bool jit_compile(const PmProgData& pd, const Variant& shape, const unsigned char* unit_act, std::string* cubin, std::string names[3],
+                 std::string* tag, bool* from_cache, double* seconds, std::string* err)
 {
     if (shape.pm != PM_PROGRAM || shape.engine != 0) { *err = "run-time specialisation starts from a generic FFMA2 variant"; return false; }
     for (int i = 0; i < pd.len; i++) {
@@ -275,7 +298,7 @@ bool jit_compile(const PmProgData& pd, const Variant& shape, std::string* cubin,
         if (op == POP_PARAM && (pd.a[i] < 0 || pd.a[i] >= MAXPS)) { *err = "malformed program"; return false; }
         if (op == POP_FORCING && (pd.a[i] < 0 || pd.a[i] >= PmProgram::NF)) { *err = "malformed program"; return false; }
     }
-    const std::string src = jit_source(pd, shape);
+    const std::string src = jit_source(pd, shape, unit_act);
     const Nvrtc& n = nvrtc();
     int vmaj = 0, vmin = 0;
     if (n.h) n.Version(&vmaj, &vmin);
@@ -286,7 +309,8 @@ bool jit_compile(const PmProgData& pd, const Variant& shape, std::string* cubin,
     char hs[32];
     snprintf(hs, sizeof hs, "%016llx", (unsigned long long)h);
     char tg[160];
-    snprintf(tg, sizeof tg, "nvrtc/PmTraced#%.8s/P%d/NH%d/H%d/O%d/%s", hs, shape.P, shape.NH, shape.H, shape.NOUT, act_token(shape.act));
+    snprintf(tg, sizeof tg, "nvrtc/PmTraced#%.8s/P%d/NH%d/H%d/O%d/%s", hs, shape.P, shape.NH, shape.H, shape.NOUT,
+             unit_act ? "ACT_PER_UNIT" : act_token(shape.act));
     *tag = tg;
     *seconds = 0.0;
     const std::string dir = cache_dir(), path = dir + "/" + hs + ".ehjit";

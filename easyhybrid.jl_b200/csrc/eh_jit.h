@@ -26,12 +26,14 @@ struct JitKernels {
 };
 
 // generated translation unit for program `pd` on the shape of `shape` (a PmProgram variant); exposed for tests
-std::string jit_source(const PmProgData& pd, const Variant& shape);
+// unit_act: NULL, or [3][32] activation codes (ACT_*) of the units of hidden layers 1..3 for models whose chains differ in
+// activation (the shape's own activation is then only the container: it decides whether swish's sigma rows exist)
+std::string jit_source(const PmProgData& pd, const Variant& shape, const unsigned char* unit_act = nullptr);
 
 // source -> cubin (disk cache first, NVRTC otherwise).  No device needed.  Returns false with *err set when NVRTC is not
 // available or the compilation fails.  names[3]: lowered names of k_step, k_epoch, k_eval.
-bool jit_compile(const PmProgData& pd, const Variant& shape, std::string* cubin, std::string names[3], std::string* tag,
-                 bool* from_cache, double* seconds, std::string* err);
+bool jit_compile(const PmProgData& pd, const Variant& shape, const unsigned char* unit_act, std::string* cubin, std::string names[3],
+                 std::string* tag, bool* from_cache, double* seconds, std::string* err);
 
 // cubin -> kernels on the current device
 bool jit_load(const std::string& cubin, const std::string names[3], JitKernels* out, std::string* err);

@@ -397,14 +397,16 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
     // units (weight 1 from the unit below, no bias, identity activation -- cells fed by no flat entry) up to the common
     // output layer.  Only the generic variants know pass-through units.
     int Pt = 0, Ot = 0, wsum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    bool uniform = true, same_depth = true;
+    bool uniform = true, same_depth = true, same_act = true, any_swish = false;
     int NHmax = 0;
     for (int k = 0; k < NC; k++) NHmax = std::max(NHmax, d->chains[k].n_hidden);
     for (int k = 0; k < NC; k++) {
         const eh_chain_desc& ck = d->chains[k];
         if (ck.n_in < 1) return fail(c, EH_EINVAL, "chain %d has no inputs", k);
         if (ck.n_hidden < 1) return fail(c, EH_EINVAL, "chain needs at least one hidden layer");
-        if (ck.activation != ch.activation || ck.input_batchnorm != ch.input_batchnorm) uniform = false;
+        if (ck.input_batchnorm != ch.input_batchnorm) uniform = false;
+        if (ck.activation != ch.activation) same_act = false;
+        if (ck.activation == EH_ACT_SWISH) any_swish = true;
         if (ck.n_hidden != NHmax) same_depth = false;
         Pt += ck.n_in; Ot += ck.n_out;
         for (int l = 0; l < NHmax && l < 8; l++) wsum[l] += ck.hidden[std::min(l, ck.n_hidden - 1)];
@@ -446,6 +448,7 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
     std::vector<int> prog_out;
     bool use_prog = false, auto_jit = false;
     PmProgData pd;
+    unsigned char unit_act[3][32];
     // run-time specialisation of the traced program (EH_FLAG_JIT, or EH_JIT=1 for every traced model; EH_JIT=0: never)
     const char* env_jit = getenv("EH_JIT");
     const bool want_jit = env_jit ? (env_jit[0] && env_jit[0] != '0') : (d->flags & EH_FLAG_JIT) != 0;
@@ -454,13 +457,33 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
         // (with run-time compilation the tightest shape that holds the model is taken -- inputs padded to 2 / 4 / 8 / 12,
         // width 8 / 16 / 24 / 32, up to four chain outputs; the compiled-in variants know 2 / 4 / 8 inputs, width 16 / 32 and
         // one or two outputs)
-        const Variant* vp = want_jit ? find_shape(Pt, NHmax, rup4(hmax), Ot, ch.activation)
-                                     : find_variant(EH_PM_PROGRAM, Pt, NHmax, rup4(hmax), Ot, ch.activation, 1, 0);
+        // chains that differ in activation (an activation per parameter, GenericHybridModel.jl:168-174): every unit gets its
+        // own activation in the generated code; the shape's activation is only the container (swish if any chain uses it:
+        // its sigma rows must exist).  Run-time compiled only.
+        const int act_shape = same_act ? ch.activation : (any_swish ? (int)EH_ACT_SWISH : ch.activation);
+        const Variant* vp = (want_jit || !same_act) ? find_shape(Pt, NHmax, rup4(hmax), Ot, act_shape)
+                                                    : find_variant(EH_PM_PROGRAM, Pt, NHmax, rup4(hmax), Ot, ch.activation, 1, 0);
         // a shape without a compiled-in variant is compiled at run time without being asked (unless EH_JIT=0): the
         // alternative would be the bf16 path or a refusal
-        if (!vp && !want_jit && !env_jit) {
+        if (!same_act) {
+            auto_jit = !want_jit && !env_jit && vp != nullptr;
+            if (!want_jit && !auto_jit) vp = nullptr;
+        } else if (!vp && !want_jit && !env_jit) {
             vp = find_shape(Pt, NHmax, rup4(hmax), Ot, ch.activation);
             auto_jit = vp != nullptr;
+        }
+        if (vp && !same_act) {
+            for (int l = 0; l < 3; l++)
+                for (int j = 0; j < 32; j++) unit_act[l][j] = (unsigned char)act_shape;
+            for (int l = 0; l < NHmax; l++) {
+                int u = 0;
+                for (int k = 0; k < NC; k++) {
+                    const eh_chain_desc& ck = d->chains[k];
+                    const int wk = ck.hidden[std::min(l, ck.n_hidden - 1)];
+                    for (int j = 0; j < wk && u + j < 32; j++) unit_act[l][u + j] = (unsigned char)(l < ck.n_hidden ? ck.activation : (int)EH_ACT_IDENTITY);
+                    u += wk;
+                }
+            }
         }
         if (vp && vp->NPART <= UPD_MAX_NPART && builtin_as_program(d, is_prog, prog, prog_out)) { v = vp; use_prog = true; }
         if (use_prog) {
@@ -473,7 +496,7 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
             }
             if (want_jit || auto_jit) {
                 std::string jerr;
-                if (jit_compile(pd, *v, &c->jit_cubin, c->jit_names, &c->jit.name, &c->jit.from_cache, &c->jit.compile_seconds, &jerr)) {
+                if (jit_compile(pd, *v, same_act ? nullptr : &unit_act[0][0], &c->jit_cubin, c->jit_names, &c->jit.name, &c->jit.from_cache, &c->jit.compile_seconds, &jerr)) {
                     c->jit_on = true;
                 } else if (want_jit) {
                     return fail(c, EH_EUNSUPPORTED, "run-time specialisation of the traced process model failed: %s", jerr.c_str());
@@ -483,6 +506,9 @@ eh_status build_plan(eh_ctx* c, const eh_model_desc* d)
             }
         }
     }
+    if (!v && !same_act)
+        return fail(c, EH_EUNSUPPORTED, "chains that differ in activation need run-time compilation (NVRTC; not with EH_JIT=0) on the exact-fp32 "
+                                        "generic kernels: <= 3 hidden layers, summed width <= 32 per layer, <= 12 chain inputs, <= 4 chain outputs");
     if (!v && !same_depth)
         return fail(c, EH_EUNSUPPORTED, "chains of different depth run on the exact-fp32 generic kernels only: <= 3 hidden layers, "
                                         "summed width <= 32 per layer, <= 12 chain inputs, <= 4 chain outputs");

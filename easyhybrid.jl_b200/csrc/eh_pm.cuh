@@ -137,6 +137,7 @@ __device__ __forceinline__ float exp2_mul_hilo(float a, float Lh, float Ll)
 // slots: p0 = rb, p1 = Q10 ; f0 = ta ; const c0 = tref
 struct PmRbQ10 {
     static constexpr bool DYNAMIC = false;
+    static constexpr bool UNIT_ACT = false;
     static constexpr int NSV = 4;   // floats of forward state kept for the backward
     static constexpr int ID = PM_RBQ10, NPS = 2, NF = 1, NT = 1;
     __device__ __forceinline__ static void fwd(const float* p, const float* f, const PmCtx& cx, float* y, float* sv)
@@ -163,6 +164,7 @@ struct PmRbQ10 {
 // slots: p0 = Resp0, p1 = k ; f0 = T
 struct PmExpo {
     static constexpr bool DYNAMIC = false;
+    static constexpr bool UNIT_ACT = false;
     static constexpr int NSV = 4;   // floats of forward state kept for the backward
     static constexpr int ID = PM_EXPO, NPS = 2, NF = 1, NT = 1;
     __device__ __forceinline__ static void fwd(const float* p, const float* f, const PmCtx& cx, float* y, float* sv)
@@ -184,6 +186,7 @@ struct PmExpo {
 // slots: p0 = a, p1 = b ; f0 = x
 struct PmLinear {
     static constexpr bool DYNAMIC = false;
+    static constexpr bool UNIT_ACT = false;
     static constexpr int NSV = 4;   // floats of forward state kept for the backward
     static constexpr int ID = PM_LINEAR, NPS = 2, NF = 1, NT = 1;
     __device__ __forceinline__ static void fwd(const float* p, const float* f, const PmCtx& cx, float* y, float* sv)
@@ -201,6 +204,7 @@ struct PmLinear {
 // (var1 = a x + b, var2 = 2 a x + b)      test/test_compute_loss.jl:209-211
 struct PmLinear2 {
     static constexpr bool DYNAMIC = false;
+    static constexpr bool UNIT_ACT = false;
     static constexpr int NSV = 4;   // floats of forward state kept for the backward
     static constexpr int ID = PM_LINEAR2, NPS = 2, NF = 1, NT = 2;
     __device__ __forceinline__ static void fwd(const float* p, const float* f, const PmCtx& cx, float* y, float* sv)
@@ -222,6 +226,7 @@ struct PmLinear2 {
 // construction as test/test_compute_loss.jl:209-211 uses for the linear model)
 struct PmExpo2 {
     static constexpr bool DYNAMIC = false;
+    static constexpr bool UNIT_ACT = false;
     static constexpr int NSV = 4;   // floats of forward state kept for the backward
     static constexpr int ID = PM_EXPO2, NPS = 2, NF = 1, NT = 2;
     __device__ __forceinline__ static void fwd(const float* p, const float* f, const PmCtx& cx, float* y, float* sv)
@@ -247,6 +252,7 @@ struct PmExpo2 {
 struct PmProgram {
     static constexpr int ID = PM_PROGRAM, NPS = MAXPS, NF = 4, NT = 2;
     static constexpr bool DYNAMIC = true;
+    static constexpr bool UNIT_ACT = false;   // per-unit activations: run-time compiled functors only (eh_jit.cu)
     static constexpr int NSV = PM_MAXLEN;   // the forward values of all instructions: the reverse sweep reuses them
     __device__ __forceinline__ static void eval(const float* p, const float* f, const PmProgData& pg, float* v)
     {

@@ -207,7 +207,8 @@ typedef struct {
                                   ~/.cache/easyhybrid_b200) instead of interpreting it per sample.  eh_create fails with
                                   EH_EUNSUPPORTED if NVRTC is not available; models that take another path ignore it.
                                   Shapes without a compiled-in generic variant -- 9..12 chain inputs, 3 or 4 chain outputs
-                                  -- are compiled this way WITHOUT the flag (EH_JIT=0 in the environment forbids it) */
+                                  or chains that differ in activation -- are compiled this way WITHOUT the flag (EH_JIT=0 in the
+                                  environment forbids it) */
 
 enum { EH_SPLIT_TRAIN = 0, EH_SPLIT_VAL = 1 };
 

@@ -78,6 +78,15 @@ def m_two_chains_unequal_depth(eh, activation="tanh", bn=False):
                                    scale_nn_outputs=True, input_batchnorm=bn)
 
 
+def m_chains_mixed_activation(eh, acts=("tanh", "relu"), hidden=None, bn=True):
+    # an activation per parameter (activation as a NamedTuple, GenericHybridModel.jl:168-174), here also with unequal depth
+    hidden = hidden or {"rb": [12, 10], "Q10": [7]}
+    return eh.constructHybridModel({"rb": ["sw_pot", "dsw_pot"], "Q10": ["ta", "sw_pot"]}, ["ta", "dsw_pot"], ["reco"], custom_pm,
+                                   dict(rb=(3.0, 0.0, 13.0), Q10=(2.0, 1.0, 4.0), alpha=(0.5, -2.0, 2.0)), ["alpha"],
+                                   hidden_layers=hidden, activation={"rb": acts[0], "Q10": acts[1]}, scale_nn_outputs=True,
+                                   input_batchnorm=bn)
+
+
 def m_traced_unequal_depth(eh):
     # chains of depth 1 and 2 (the shallow one first) feeding a traced process model with a global parameter besides; relu
     return eh.constructHybridModel({"rb": ["sw_pot", "dsw_pot"], "Q10": ["ta", "sw_pot"]}, ["ta", "dsw_pot"], ["reco"], custom_pm,

@@ -86,6 +86,9 @@ def test_shapes_beyond_the_compiled_in_variants(eh, tmp_path, monkeypatch):
     # but 8 -> 8 instead of 16
     st, info, err = _check(eh, gg.m_custom(eh, hidden=(8, 8)), training_loss="mse", agg="sum")
     assert st == 0 and "/P2/NH2/H8/O1/" in info, (info, err)
+    # an activation per chain
+    st, info, err = _check(eh, gg.m_chains_mixed_activation(eh), training_loss="mse", agg="sum")
+    assert st == 0 and info.split()[0].endswith("/P4/NH2/H24/O2/ACT_PER_UNIT"), (info, err)
 
 
 JIT_CASES = [
@@ -95,7 +98,13 @@ JIT_CASES = [
     ("three-neural-parameters-width-24", m_three_neural, lambda: gg._table(2000, nan_frac=0.03), "mse", "sum"),
     ("ten-inputs", m_ten_inputs, lambda: _table_wide(2000), "nseLoss", "sum"),
 ]
-JIT_ONLY = {"three-neural-parameters-width-24", "ten-inputs"}   # no compiled-in variant: nothing to compare the interpreter with
+JIT_CASES += [
+    # chains that differ in activation: per-unit activations in the generated code
+    ("chains-tanh-and-relu-depth-2-and-1", gg.m_chains_mixed_activation, lambda: gg._table(2000, nan_frac=0.03), "mse", "sum"),
+    ("chains-swish-and-sigmoid", lambda eh: gg.m_chains_mixed_activation(eh, ("swish", "sigmoid"), {"rb": [9, 9], "Q10": [6, 5]}),
+     lambda: gg._table(2000), "mae", "sum"),
+]
+JIT_ONLY = {"three-neural-parameters-width-24", "ten-inputs", "chains-tanh-and-relu-depth-2-and-1", "chains-swish-and-sigmoid"}   # no compiled-in variant: nothing to compare the interpreter with
 
 
 @pytest.mark.gpu

@@ -63,6 +63,9 @@ import test_jit as tj  # noqa: E402
 CASES += [
     ("three-neural-parameters-width-24", tj.m_three_neural, lambda: gg._table(300, nan_frac=0.03), "mse", "sum"),
     ("ten-inputs", tj.m_ten_inputs, lambda: tj._table_wide(300), "nseLoss", "sum"),
+    ("chains-tanh-and-relu-depth-2-and-1", gg.m_chains_mixed_activation, lambda: gg._table(300, nan_frac=0.03), "mse", "sum"),
+    ("chains-swish-and-sigmoid", lambda eh: gg.m_chains_mixed_activation(eh, ("swish", "sigmoid"), {"rb": [9, 9], "Q10": [6, 5]}),
+     lambda: gg._table(300), "mae", "sum"),
 ]
 
 
