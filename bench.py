@@ -50,6 +50,32 @@ def synth(n, seed):
     return (np.ascontiguousarray(np.stack([sw, dsw], 1)), {"ta": ta}), {"reco": reco}
 
 
+def traced_model_leg(eh, device, xf, y, n, B):
+    """The headline workload with its process model written as a user callable the library has no built-in form for (it is
+    traced into a program): per-step time with the program interpreted per sample (compiled-in generic variant) and compiled
+    into the kernels at run time (NVRTC; the compilation itself is outside the timed region).  Rank 0, one GPU."""
+    def custom(*, ta, rb, Q10, tref=15.0):
+        return {"reco": rb * Q10 ** (0.1 * (ta - tref)) + 0.0 * ta}
+    model = eh.constructHybridModel(["sw_pot", "dsw_pot"], ["ta"], ["reco"], custom, dict(rb=(3.0, 0.0, 13.0), Q10=(2.0, 1.0, 4.0)),
+                                    ["rb"], ["Q10"], hidden_layers=[16, 16], activation="tanh", scale_nn_outputs=True)
+    out = {"workload": "C3 with the process model as a traced callable (rb * Q10^(0.1 (ta - 15)) + 0 * ta), batch %d" % B}
+    for key, jit in (("interpreted", False), ("compiled_nvrtc", True)):
+        t0 = time.perf_counter()
+        sess = eh.FusedSession(model, opt=eh.Adam(0.01), device=device, jit=jit)
+        t_create = time.perf_counter() - t0
+        sess.upload(0, xf, y)
+        sess.set_params(model.initialparameters(np.random.default_rng(0)))
+        sess.set_perm(np.random.default_rng(7).permutation(n))
+        sess.run_steps(B, 0, 32)
+        K = 128
+        losses = sess.run_steps(B, 32, K)
+        ms, _, _ = sess.last_timing()
+        out[key] = {"us_per_step": 1e3 * ms / K, "samples_per_s": K * B / (ms * 1e-3), "variant": sess.kernel_variant(),
+                    "create_s": round(t_create, 2), "final_loss": float(losses[-1])}
+        sess.close()
+    return out
+
+
 def wide_c5_leg(eh, device, rank=0, world=1, dist=None):
     """BASELINE config 5 (reported next to the headline, not instead of it): two-target Expo hybrid, hidden 3 x 512,
     bf16 tcgen05 GEMMs, PerTarget(nseLoss, mse), batch 65536 per GPU; tensor roofline of its hidden GEMMs.  With several
@@ -453,6 +479,12 @@ def main():
             wide = wide_c5_leg(eh, local, rank, world, dist)
         except Exception as e:  # the extra leg must never take the headline line down
             wide = {"error": str(e)[:200]}
+    traced = None
+    if not args.no_wide and rank == 0 and world == 1:
+        try:
+            traced = traced_model_leg(eh, local, xf, y, n, B)
+        except Exception as e:
+            traced = {"error": str(e)[:200]}
     dp_parity = strong = None
     if os.environ.get("EH_BENCH_DEBUG"):
         print("[bench] rank %d: headline + e2e + wide legs done" % rank, file=sys.stderr, flush=True)
@@ -478,6 +510,8 @@ def main():
                 "final_loss": float(losses[-1])}
         if wide is not None:
             line["extra"] = {"c5_wide_mlp": wide}
+        if traced is not None:
+            line.setdefault("extra", {})["traced_process_model"] = traced
         if dp_parity is not None:
             line["dp_parity_ok"] = bool(dp_parity.get("ok", False))
             line["dp_parity"] = dp_parity
