@@ -227,7 +227,7 @@ WideNet* WideNet::create(const WideModel& m, char* err, size_t errlen)
     if (e != cudaSuccess) return bail("gemm_prepare", e);
     HeadKernel hk = find_head(m.pm, m.NOUT, m.scale, m.H / 256);
     if (!hk) { snprintf(err, errlen, "wide path: no head kernel for this process model / shape"); delete w; return nullptr; }
-    const int head_smem = 8 * (m.NOUT + 1) * m.H * (int)sizeof(float);
+    const int head_smem = (8 * (m.NOUT + 1) + m.NOUT) * m.H * (int)sizeof(float);   // warps' scratch / row rings + the output-layer weights
     e = cudaFuncSetAttribute((const void*)hk, cudaFuncAttributeMaxDynamicSharedMemorySize, head_smem);
     if (e != cudaSuccess) return bail("head smem", e);
     const size_t HH = (size_t)m.H * m.H;
@@ -276,7 +276,7 @@ WideNet* WideNet::create(const WideModel& m, char* err, size_t errlen)
         if ((e = cudaMalloc(&w->d_prog_, sizeof pd)) != cudaSuccess) return bail("cudaMalloc", e);
         if ((e = cudaMemcpy(w->d_prog_, &pd, sizeof pd, cudaMemcpyHostToDevice)) != cudaSuccess) return bail("cudaMemcpy", e);
     }
-    w->n_head_ = 2 * m.nsm;
+    w->n_head_ = 3 * m.nsm;   // three CTAs of the head kernel are resident per SM (80 registers)
     if ((e = cudaMalloc(&w->head_partial_, (size_t)w->n_head_ * head_npart(m.H, m.NOUT) * 4)) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc(&w->stats_, 16 * 4)) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc(&w->skip_, 4)) != cudaSuccess) return bail("cudaMalloc", e);
@@ -397,7 +397,7 @@ cudaError_t WideNet::step(const float* rec, const int* idx, long long rec_base, 
     for (int t = 0; t < 4; t++) ha.loss_kind[t] = m_.loss_kind[t];
     for (int s = 0; s < 8; s++) { ha.slot[s].role = m_.slot[s].role; ha.slot[s].idx = m_.slot[s].idx; ha.slot[s].lo = m_.slot[s].lo; ha.slot[s].span = m_.slot[s].span; ha.slot[s].fixedv = m_.slot[s].fixedv; }
     for (int i = 0; i < 4; i++) ha.pmc[i] = m_.pmc[i];
-    const int head_smem = 8 * (m_.NOUT + 1) * H * (int)sizeof(float);
+    const int head_smem = (8 * (m_.NOUT + 1) + m_.NOUT) * H * (int)sizeof(float);
     hk<<<n_head_, 256, head_smem, st>>>(ha);
     WN(cudaGetLastError());
     for (int l = NH; l >= 2; l--) {
@@ -488,7 +488,7 @@ cudaError_t WideNet::eval_rows(const float* rec, long long nrec, long long row0,
     ha.prog = reinterpret_cast<const PmProgData*>(d_prog_); ha.nf = m_.F; ha.nt = m_.T;
     for (int s = 0; s < 8; s++) { ha.slot[s].role = m_.slot[s].role; ha.slot[s].idx = m_.slot[s].idx; ha.slot[s].lo = m_.slot[s].lo; ha.slot[s].span = m_.slot[s].span; ha.slot[s].fixedv = m_.slot[s].fixedv; }
     for (int i = 0; i < 4; i++) ha.pmc[i] = m_.pmc[i];
-    const int head_smem = 8 * (m_.NOUT + 1) * H * (int)sizeof(float);
+    const int head_smem = (8 * (m_.NOUT + 1) + m_.NOUT) * H * (int)sizeof(float);
     hk<<<n_head_, 256, head_smem, st>>>(ha);
     WN(cudaGetLastError());
     if (evalstat_dev) {

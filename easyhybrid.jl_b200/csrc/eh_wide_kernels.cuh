@@ -153,7 +153,7 @@ struct HeadArgs {
 // ---- output layer + physics + loss seeds + backward into D_NH; one warp per sample row, 8 warps per CTA ----
 // H / 256 chunks of 8 consecutive features per lane (16-byte bf16 accesses).
 template <class HC, int HCH>
-__global__ void __launch_bounds__(256, 2) k_wide_head(const HeadArgs a)
+__global__ void __launch_bounds__(256, 3) k_wide_head(const HeadArgs a)
 {
     using PM = typename HC::PM;
     constexpr int NOUT = HC::NOUT, T = HC::T, F = HC::F, NPS = HC::NPS;
@@ -184,16 +184,19 @@ __global__ void __launch_bounds__(256, 2) k_wide_head(const HeadArgs a)
     for (int s = 0; s < MAXPS; s++)
         if (s >= NPS || a.slot[s].role != ROLE_NEURAL) cx.uniform_mask |= 1u << s;
 
-    // output-layer weights of my features
-    float w[NOUT][HCH][8];
-#pragma unroll
-    for (int c = 0; c < HCH; c++)
-#pragma unroll
-        for (int e = 0; e < 8; e++) {
-            const int i = (c * 32 + lane) * 8 + e;
-#pragma unroll
-            for (int o = 0; o < NOUT; o++) w[o][c][e] = a.WOimg[(size_t)o * H + i];
-        }
+    // output-layer weights: a CTA copy in shared memory behind the warps' scratch ([NOUT][H]); a lane reads the eight of
+    // its features where it needs them (registers are what limits the number of resident warps here, and with it how well
+    // the long per-row dependency chain is hidden)
+    extern __shared__ float s_vec[];   // [8][(NOUT + 1) * H] reduction scratch / row rings, then [NOUT][H] weights
+    float* s_w = s_vec + 8 * (NOUT + 1) * H;
+    // lane-major: float4 number ((o * HCH + c) * 2 + half) * 32 + lane holds features (c * 32 + lane) * 8 + 4 half .. + 3 of
+    // output o, so that a warp's LDS.128 walks consecutive 16-byte words (feature-major it was a 2-way bank conflict and the
+    // shared-memory pipe, at 64 % busy, set the pace of the kernel)
+    for (int i = threadIdx.x; i < NOUT * H; i += blockDim.x) {
+        const int o = i / H, f = i % H, c = f >> 8, ln = (f >> 3) & 31, half = (f >> 2) & 1, e = f & 3;
+        s_w[((((o * HCH + c) * 2 + half) * 32 + ln) << 2) + e] = a.WOimg[i];
+    }
+    __syncthreads();
     float bout[NOUT];
 #pragma unroll
     for (int o = 0; o < NOUT; o++) bout[o] = a.BOimg[o];
@@ -220,43 +223,65 @@ __global__ void __launch_bounds__(256, 2) k_wide_head(const HeadArgs a)
 #pragma unroll
     for (int q = 0; q < MAXPS; q++) gphi[q] = 0.f;
 
-    // the activations of a warp's NEXT row travel in registers while the current row is worked on (its chain of
-    // dependent steps -- dot product, warp sum, process model, delta -- would otherwise wait for HBM once per row)
+    // The activations of a warp's next FOUR rows are in flight (cp.async into a ring in shared memory) while the current row
+    // is worked on: the row's chain of dependent steps -- dot product, warp sum, process model, delta -- is long, and with one
+    // row in flight per warp the kernel was bound by memory-level parallelism (16 KB per SM: 3 TB/s).  The ring aliases the
+    // warp's own slice of the reduction scratch, which is only written after the loop.
+    constexpr int DEPTH = 4;
     const int bend = a.train ? a.B : a.Bvalid, bstep = gridDim.x * 8;
-    uint4 nxt[HCH];
-    {
-        const int b1 = blockIdx.x * 8 + warp;
+    const uint32_t ring = (uint32_t)__cvta_generic_to_shared(s_vec) + (uint32_t)(warp * (NOUT + 1) * H * 4);
+    const int row_bytes = H * 2;
+    auto fetch_row = [&](int brow, int slot) {
+        if (brow < bend) {
 #pragma unroll
-        for (int c = 0; c < HCH; c++)
-            nxt[c] = b1 < bend ? __ldg(reinterpret_cast<const uint4*>(a.A + (size_t)b1 * H + (c * 32 + lane) * 8)) : make_uint4(0, 0, 0, 0);
-    }
-    for (int b = blockIdx.x * 8 + warp; b < bend; b += bstep) {
+            for (int c = 0; c < HCH; c++)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring + (uint32_t)(slot * row_bytes + (c * 32 + lane) * 16)),
+                             "l"(a.A + (size_t)brow * H + (c * 32 + lane) * 8)
+                             : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");   // (an empty group keeps the count uniform)
+    };
+#pragma unroll
+    for (int dd = 0; dd < DEPTH; dd++) fetch_row(blockIdx.x * 8 + warp + dd * bstep, dd);
+    int it = 0;
+    for (int b = blockIdx.x * 8 + warp; b < bend; b += bstep, it++) {
         const bool rowvalid = b < a.Bvalid;   // rows beyond: padding of the batch up to a multiple of 128 (train mode)
-        float av[HCH][8];
         float zo[NOUT];
 #pragma unroll
         for (int o = 0; o < NOUT; o++) zo[o] = 0.f;
-        uint4 cur[HCH];
-#pragma unroll
-        for (int c = 0; c < HCH; c++) cur[c] = nxt[c];
-        if (b + bstep < bend) {
-#pragma unroll
-            for (int c = 0; c < HCH; c++) nxt[c] = __ldg(reinterpret_cast<const uint4*>(a.A + (size_t)(b + bstep) * H + (c * 32 + lane) * 8));
-        }
-#pragma unroll
-        for (int c = 0; c < HCH; c++) {
-            const uint4 raw = cur[c];
+        const int slot = it & (DEPTH - 1);
+        asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH - 1) : "memory");   // this row has landed (each lane reads its own 16 bytes)
+        // my eight activations of chunk c, from the ring (read again in the delta loop instead of living in registers)
+        auto load_av = [&](int c, float (&av)[8]) {
+            uint4 raw;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w)
+                         : "r"(ring + (uint32_t)(slot * row_bytes + (c * 32 + lane) * 16))
+                         : "memory");
             const uint32_t rw[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
             for (int e = 0; e < 4; e++) {
                 const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rw[e]));
-                av[c][2 * e] = f.x;
-                av[c][2 * e + 1] = f.y;
+                av[2 * e] = f.x;
+                av[2 * e + 1] = f.y;
             }
+        };
+        auto load_w = [&](int o, int c, float (&w)[8]) {
+            const float4 w0 = reinterpret_cast<const float4*>(s_w)[((o * HCH + c) * 2 + 0) * 32 + lane];
+            const float4 w1 = reinterpret_cast<const float4*>(s_w)[((o * HCH + c) * 2 + 1) * 32 + lane];
+            w[0] = w0.x; w[1] = w0.y; w[2] = w0.z; w[3] = w0.w; w[4] = w1.x; w[5] = w1.y; w[6] = w1.z; w[7] = w1.w;
+        };
 #pragma unroll
-            for (int e = 0; e < 8; e++)
+        for (int c = 0; c < HCH; c++) {
+            float av[8];
+            load_av(c, av);
 #pragma unroll
-                for (int o = 0; o < NOUT; o++) zo[o] = fmaf(av[c][e], w[o][c][e], zo[o]);
+            for (int o = 0; o < NOUT; o++) {
+                float w[8];
+                load_w(o, c, w);
+#pragma unroll
+                for (int e = 0; e < 8; e++) zo[o] = fmaf(av[e], w[e], zo[o]);
+            }
         }
 #pragma unroll
         for (int o = 0; o < NOUT; o++) zo[o] = warp_sum(zo[o]) + bout[o];
@@ -288,6 +313,8 @@ __global__ void __launch_bounds__(256, 2) k_wide_head(const HeadArgs a)
                         if (a.slot[q].role == ROLE_NEURAL) a.parout[(size_t)q * a.ldy + a.row0 + b] = pv[q];
                 }
             }
+            __syncwarp();
+            fetch_row(b + DEPTH * bstep, slot);
             continue;
         }
 #pragma unroll
@@ -324,23 +351,32 @@ __global__ void __launch_bounds__(256, 2) k_wide_head(const HeadArgs a)
         // delta of the last hidden layer for my features, its column sums, and the output-layer gradient
 #pragma unroll
         for (int c = 0; c < HCH; c++) {
-            float dv[8];
+            float dv[8], av[8], sacc[8];
+            load_av(c, av);
+#pragma unroll
+            for (int e = 0; e < 8; e++) sacc[e] = 0.f;
+#pragma unroll
+            for (int o = 0; o < NOUT; o++) {
+                float w[8];
+                load_w(o, c, w);
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    sacc[e] = fmaf(dz[o], w[e], sacc[e]);
+                    gW[o][c][e] = fmaf(dz[o], av[e], gW[o][c][e]);
+                }
+            }
 #pragma unroll
             for (int e = 0; e < 8; e++) {
-                float s = 0.f;
-#pragma unroll
-                for (int o = 0; o < NOUT; o++) {
-                    s = fmaf(dz[o], w[o][c][e], s);
-                    gW[o][c][e] = fmaf(dz[o], av[c][e], gW[o][c][e]);
-                }
                 // round first: db must be the column sum of the very deltas the weight-gradient GEMM reads
-                dv[e] = __bfloat162float(__float2bfloat16_rn(s * dact_out(a.act, av[c][e])));
+                dv[e] = __bfloat162float(__float2bfloat16_rn(sacc[e] * dact_out(a.act, av[e])));
                 gDb[c][e] += dv[e];
             }
             uint4 o4;
             o4.x = pack2(dv[0], dv[1]); o4.y = pack2(dv[2], dv[3]); o4.z = pack2(dv[4], dv[5]); o4.w = pack2(dv[6], dv[7]);
             *reinterpret_cast<uint4*>(a.D + (size_t)b * H + (c * 32 + lane) * 8) = o4;
         }
+        __syncwarp();
+        fetch_row(b + DEPTH * bstep, slot);   // the slot is free now
     }
 
     if (!a.train) {
@@ -356,7 +392,8 @@ __global__ void __launch_bounds__(256, 2) k_wide_head(const HeadArgs a)
     }
     // CTA reduction in a fixed order: per-feature vectors through shared memory, warp by warp
     float* out = a.partial + (size_t)blockIdx.x * head_npart(H, NOUT);
-    extern __shared__ float s_vec[];   // [8][(NOUT + 1) * H]
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
     const int VS = (NOUT + 1) * H;
 #pragma unroll
     for (int c = 0; c < HCH; c++)
