@@ -277,6 +277,12 @@ WideNet* WideNet::create(const WideModel& m, char* err, size_t errlen)
         if ((e = cudaMemcpy(w->d_prog_, &pd, sizeof pd, cudaMemcpyHostToDevice)) != cudaSuccess) return bail("cudaMemcpy", e);
     }
     w->n_head_ = 3 * m.nsm;   // three CTAs of the head kernel are resident per SM (80 registers)
+    if (cudaStreamCreateWithFlags(&w->side_, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&w->ev_wgrad_, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&w->ev_wred_, cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        if (w->side_) cudaStreamDestroy(w->side_);
+        w->side_ = nullptr;   // no side stream: the reductions stay on the main stream
+    }
     if ((e = cudaMalloc(&w->head_partial_, (size_t)w->n_head_ * head_npart(m.H, m.NOUT) * 4)) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc(&w->stats_, 16 * 4)) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc(&w->skip_, 4)) != cudaSuccess) return bail("cudaMalloc", e);
@@ -287,6 +293,9 @@ WideNet* WideNet::create(const WideModel& m, char* err, size_t errlen)
 
 WideNet::~WideNet()
 {
+    if (side_) { cudaStreamSynchronize(side_); cudaStreamDestroy(side_); }
+    if (ev_wgrad_) cudaEventDestroy(ev_wgrad_);
+    if (ev_wred_) cudaEventDestroy(ev_wred_);
     for (int i = 0; i < 8; i++) {
         if (A_[i]) cudaFree(A_[i]);
         if (Wf_[i]) cudaFree(Wf_[i]);
@@ -400,16 +409,26 @@ cudaError_t WideNet::step(const float* rec, const int* idx, long long rec_base, 
     const int head_smem = (8 * (m_.NOUT + 1) + m_.NOUT) * H * (int)sizeof(float);
     hk<<<n_head_, 256, head_smem, st>>>(ha);
     WN(cudaGetLastError());
+    const bool fork = side_ != nullptr && !getenv("EH_WIDE_NO_SIDE_STREAM");
+    bool pending = false;   // a split-K reduction is in flight on the side stream (it reads partial_, it writes grad)
     for (int l = NH; l >= 2; l--) {
         const int cur = l & 1, nxt = (l - 1) & 1;
+        if (pending) { WN(cudaStreamWaitEvent(st, ev_wred_, 0)); pending = false; }   // partial_ is free again
         WN(gemm_wgrad(tmD_mn_[cur], tmA_mn_[l - 2], H, H, B, ksplit_, partial_, st));
+        cudaStream_t rs = st;
+        if (fork) {
+            WN(cudaEventRecord(ev_wgrad_, st));
+            WN(cudaStreamWaitEvent(side_, ev_wgrad_, 0));
+            rs = side_;
+        }
         for (int bi = 0; bi < m_.n_blocks; bi++) {
             const auto& bk = m_.blocks[bi];
             if (bk.l != l) continue;
-            k_wide_wreduce<<<dim3((bk.hin + 31) / 32, (bk.hout + 31) / 32), 256, 0, st>>>(partial_, ksplit_, H, bk.hout, bk.hin, bk.o_off,
+            k_wide_wreduce<<<dim3((bk.hin + 31) / 32, (bk.hout + 31) / 32), 256, 0, rs>>>(partial_, ksplit_, H, bk.hout, bk.hin, bk.o_off,
                                                                                      bk.i_off, grad + bk.flat_off);
             WN(cudaGetLastError());
         }
+        if (fork) { WN(cudaEventRecord(ev_wred_, side_)); pending = true; }
         // backward data; its epilogue also leaves the 32-row column sums of D_{l-1} (bias gradient of layer l-1 and,
         // for layer 1, the x-weighted sums = its weight gradient)
         if (persist_)
@@ -419,6 +438,7 @@ cudaError_t WideNet::step(const float* rec, const int* idx, long long rec_base, 
             WN(gemm_bwd(tmD_k_[cur], tmWb_[l - 1], B, H, H, A_[l - 2], m_.act, D_[nxt], st, colsum_[l - 2], xb_, bscal, m_.R4,
                         (l - 1 == 1) ? m_.P : 0, m_.use_bn));
     }
+    if (pending) WN(cudaStreamWaitEvent(st, ev_wred_, 0));   // the flat gradient is complete from here on
     FinArgs fa{};
     fa.d = d; fa.head_partial = head_partial_; fa.n_head = n_head_; fa.n_slab = n_slab_;
     fa.map = reinterpret_cast<const ParamMap*>(d_map_); fa.small = d_small_; fa.n_small = n_small_;

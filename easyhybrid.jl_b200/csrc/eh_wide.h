@@ -98,6 +98,9 @@ private:
     int n_small_ = 0;
     void* d_prog_ = nullptr;   // PmProgData on the device
     float* partial_ = nullptr;
+    // the split-K reductions (latency-bound, a few CTAs) run on a side stream next to the backward-data GEMM of their layer
+    cudaStream_t side_ = nullptr;
+    cudaEvent_t ev_wgrad_ = nullptr, ev_wred_ = nullptr;
     float* colsum_[8] = {nullptr};
     float* head_partial_ = nullptr;
     float* stats_ = nullptr;
