@@ -24,6 +24,23 @@ def custom_two_targets(*, ta, dsw_pot, rb, Q10, alpha, tref=15.0):
     return {"reco": r + alpha * np.tanh(0.05 * dsw_pot), "reco2": 2.0 * r + alpha}
 
 
+def many_ops_pm(*, ta, dsw_pot, rb, Q10, alpha, tref=15.0):
+    """every operation the program format knows except pow / tanh (custom_pm has those): exp, log, sqrt, abs, sin, cos, min,
+    max, div, neg, sub -- the reverse sweep of each is exercised (interpreter and run-time compiled code)"""
+    t = 0.1 * (ta - tref)
+    a = np.exp(t * np.log(Q10))
+    b = np.sqrt(rb * rb + 1.0) / (1.0 + np.abs(alpha))
+    c = np.sin(0.05 * dsw_pot) * np.cos(alpha)
+    d = np.minimum(rb, 4.0) + np.maximum(alpha, -0.25) - (-t)
+    return {"reco": a * b + 0.1 * c + 0.01 * d}
+
+
+def m_many_ops(eh):
+    return eh.constructHybridModel(["sw_pot", "dsw_pot"], ["ta", "dsw_pot"], ["reco"], many_ops_pm,
+                                   dict(rb=(3.0, 0.0, 13.0), Q10=(2.0, 1.0, 4.0), alpha=(0.5, -2.0, 2.0)), ["rb"], ["Q10", "alpha"],
+                                   hidden_layers=[16, 16], activation="tanh", scale_nn_outputs=True, input_batchnorm=True)
+
+
 def _table(n, nan_frac=0.0, two=False):
     t = make_synth(n, nan_frac=0.0)
     t["reco"] = (t["reco"] + 0.3 * np.tanh(0.05 * t["dsw_pot"])).astype(np.float32)
@@ -112,6 +129,7 @@ CASES = [
     # several chains, embedded block-diagonally into one chain of the summed widths (<= 32)
     ("two-chains-rbq10", lambda eh: rbq10_two_chain_model(eh, hidden=(16, 16)), lambda: make_synth(2000, nan_frac=0.03), "mse", "sum"),
     ("two-chains-six-inputs-bn", m_two_chains_six_inputs, lambda: make_synth(2000), "mse", "sum"),
+    ("traced-all-operations", m_many_ops, lambda: _table(2000, nan_frac=0.03), "mse", "sum"),
     # chains of different depth: the shallower chain's last hidden layer rides on pass-through units
     ("two-chains-depth-3-and-1", m_two_chains_unequal_depth, lambda: make_synth(2000, nan_frac=0.03), "mse", "sum"),
     ("two-chains-depth-3-and-1-swish-bn", lambda eh: m_two_chains_unequal_depth(eh, "swish", True), lambda: make_synth(2000), "nseLoss", "sum"),
@@ -150,7 +168,10 @@ def test_generic_variants_loss_and_gradient(eh, orc, name, mk, mkdata, loss, agg
     sess.close()
 
 
-TRAIN_CASES = [CASES[0], CASES[5], CASES[7], CASES[8], CASES[9], CASES[11], CASES[12], CASES[13], CASES[14], CASES[15], CASES[16]]
+TRAIN_CASES = [c for c in CASES if c[0] in ("custom-tanh16", "custom-two-targets-bn", "rbq10-one-hidden-layer", "rbq10-three-hidden-layers",
+                                            "custom-three-hidden-two-neural", "rbq10-three-inputs-swish", "two-chains-rbq10", "two-chains-six-inputs-bn",
+                                            "traced-all-operations", "two-chains-depth-3-and-1", "two-chains-depth-3-and-1-swish-bn",
+                                            "traced-chains-depth-1-and-2-relu")]
 
 
 @pytest.mark.parametrize("name,mk,mkdata,loss,agg", TRAIN_CASES, ids=[c[0] for c in TRAIN_CASES])

@@ -92,6 +92,7 @@ def test_shapes_beyond_the_compiled_in_variants(eh, tmp_path, monkeypatch):
 
 
 JIT_CASES = [
+    ("traced-all-operations", gg.m_many_ops, lambda: gg._table(2000, nan_frac=0.03), "mse", "sum"),
     ("custom-tanh16", gg.m_custom, lambda: gg._table(3000, nan_frac=0.05), "mse", "sum"),
     ("custom-two-targets-bn", gg.m_two_targets, lambda: gg._table(2500, nan_frac=0.1, two=True), "PT", "mean"),
     ("traced-chains-depth-1-and-2-relu", gg.m_traced_unequal_depth, lambda: gg._table(2000), "mse", "mean"),

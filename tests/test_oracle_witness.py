@@ -53,6 +53,7 @@ CASES += [
     ("rbq10-three-hidden-layers", lambda eh: rbq10_model(eh, hidden=(16, 12, 8), activation="sigmoid"), lambda: make_synth(300), "mse", "sum"),
     ("rbq10-three-inputs-swish", gg.m_rbq10_three_inputs, lambda: make_synth(300, nan_frac=0.03), "mse", "sum"),
     ("two-chains-six-inputs-bn", gg.m_two_chains_six_inputs, lambda: make_synth(300), "mse", "sum"),
+    ("traced-all-operations", gg.m_many_ops, lambda: gg._table(300, nan_frac=0.03), "mse", "sum"),
     ("two-chains-depth-3-and-1", gg.m_two_chains_unequal_depth, lambda: make_synth(300, nan_frac=0.03), "mse", "sum"),
     ("two-chains-depth-3-and-1-swish-bn", lambda eh: gg.m_two_chains_unequal_depth(eh, "swish", True), lambda: make_synth(300), "nseLoss", "sum"),
     ("traced-chains-depth-1-and-2-relu", gg.m_traced_unequal_depth, lambda: gg._table(300), "mse", "mean"),

@@ -118,8 +118,15 @@ def _call_torch(fn, kwargs):
         def __rpow__(self, o): return T(torch.as_tensor(self._w(o), dtype=torch.float64) ** self.v)
         def __neg__(self): return T(-self.v)
 
+        def __abs__(self): return T(torch.abs(self.v))
+
         def __array_ufunc__(self, ufunc, method, *inputs, **kw):
-            f = {"exp": torch.exp, "log": torch.log, "sqrt": torch.sqrt, "tanh": torch.tanh}[ufunc.__name__]
+            name = ufunc.__name__
+            if name in ("minimum", "maximum"):
+                a, b = (x.v if isinstance(x, T) else torch.as_tensor(float(np.float32(x)), dtype=torch.float64) for x in inputs)
+                return T(torch.minimum(a, b) if name == "minimum" else torch.maximum(a, b))
+            f = {"exp": torch.exp, "log": torch.log, "sqrt": torch.sqrt, "tanh": torch.tanh, "sin": torch.sin, "cos": torch.cos,
+                 "absolute": torch.abs, "negative": torch.neg}[name]
             return T(f(inputs[0].v))
     out = fn(**{k: T(v) for k, v in kwargs.items()})
     return {k: (v.v if isinstance(v, T) else v) for k, v in out.items()}
