@@ -175,6 +175,34 @@ def test_shapes_without_a_compiled_in_variant_compile_unasked(eh, monkeypatch):
 
 
 @pytest.mark.gpu
+def test_host_batches_through_compiled_kernels(eh):
+    """collect_dim_data |> gdev path (eh_step_host, and the asynchronous grouped form) == resident-dataset path, bit for
+    bit, with the run-time compiled kernels"""
+    model = gg.m_custom(eh)
+    xf, y = eh.prepare_data(model, gg._table(3000, nan_frac=0.03))
+    rng = np.random.default_rng(2)
+    flat = model.initialparameters(rng)
+    sess = eh.FusedSession(model, opt=eh.Adam(0.01), jit=True)
+    assert sess.kernel_variant().startswith("nvrtc/")
+    sess.upload(0, xf, y)
+    sess.set_params(flat)
+    B, nb = 500, 6
+    perm = rng.permutation(xf[0].shape[0])[: B * nb]
+    want = sess.epoch(perm, B)
+    p1 = sess.get_params()
+    sess.set_params(flat)
+    sess.set_opt_state(None, None, 0)
+    got = []
+    for k in range(nb):
+        idx = perm[k * B:(k + 1) * B]
+        xb = (xf[0][idx], {f: xf[1][f][idx] for f in model.forcing})
+        got.append(sess.step_host(xb, {t: y[t][idx] for t in model.targets}))
+    np.testing.assert_allclose(got, want, rtol=2e-6)
+    np.testing.assert_allclose(sess.get_params(), p1, rtol=0, atol=2e-6)
+    sess.close()
+
+
+@pytest.mark.gpu
 def test_train_api_with_compiled_program(eh):
     table = gg._table(8192)
     res = eh.train(gg.m_custom(eh), table, nepochs=30, batchsize=512, opt=eh.Adam(0.01), training_loss="mse", random_seed=1,
