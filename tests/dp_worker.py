@@ -111,6 +111,30 @@ def main():
                 assert all(b == allh[0] for b in allh), "replicas diverged (host batches)"
                 print("DP_NCCL_HOST_OK")
         sess.close()
+        if not os.environ.get("EH_DP_DEBUG"):
+            # ---- the same model written as a traced callable and compiled at run time (NVRTC): the fused exchange lives in the
+            # run-time compiled persistent kernel as well; same trajectory as the built-in form ----
+            def traced_rbq10(*, ta, rb, Q10, tref=15.0):
+                return {"reco": rb * Q10 ** (0.1 * (ta - tref)) + 0.0 * ta}
+            modelj = eh.constructHybridModel(["sw_pot", "dsw_pot"], ["ta"], ["reco"], traced_rbq10, dict(rb=(3.0, 0.0, 13.0), Q10=(2.0, 1.0, 4.0)),
+                                             ["rb"], ["Q10"], hidden_layers=[16, 16], activation="tanh", scale_nn_outputs=True)
+            xf, y = shards[rank]
+            sj = eh.FusedSession(modelj, opt=eh.Adam(0.01), device=local, jit=True)
+            assert sj.kernel_variant().startswith("nvrtc/"), sj.kernel_variant()
+            sj.upload(0, xf, y)
+            sj.set_params(flat0)
+            sj.comm_init(rank, world, dist)
+            sj.set_perm(perms[rank])
+            dist.barrier()
+            lj = sj.run_steps(B, 0, steps)
+            pj = sj.get_params()
+            allj = [None] * world
+            dist.all_gather_object(allj, pj.tobytes())
+            np.testing.assert_allclose(lj, losses, rtol=2e-5)
+            if rank == 0:
+                assert all(b == allj[0] for b in allj), "replicas diverged (run-time compiled kernels)"
+                print("DP_NCCL_JIT_OK", lj[:3])
+            sj.close()
         # ---- second scenario: NaN targets + input BatchNorm + nseLoss: per-batch statistics of the GLOBAL batch ----
         if not os.environ.get("EH_DP_DEBUG"):
             model2 = rbq10_model(eh, bn=True)

@@ -35,4 +35,4 @@ def test_dp_fused_exchange_two_gpus():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     r = _torchrun(2, "nccl", 29612)
-    assert r.returncode == 0 and "DP_NCCL_OK" in r.stdout and "DP_NCCL_HOST_OK" in r.stdout and "DP_NCCL_STATS_OK" in r.stdout and "DP_NCCL_WIDE_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+    assert r.returncode == 0 and "DP_NCCL_OK" in r.stdout and "DP_NCCL_HOST_OK" in r.stdout and "DP_NCCL_STATS_OK" in r.stdout and "DP_NCCL_WIDE_OK" in r.stdout and "DP_NCCL_JIT_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
